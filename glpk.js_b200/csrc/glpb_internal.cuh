@@ -1,0 +1,154 @@
+/* glpb_internal.cuh -- shared declarations of libglpb200 (sm_100a).
+ *
+ * Device data layout (all 0-based; "k" numbers variables 0..m+n-1, auxiliary
+ * rows first, exactly the reference's 1..m+n shifted by one):
+ *
+ *   A   CSC  a_ptr[n+1] a_ind[nnz] a_val[nnz]   scaled values rii*a*sjj
+ *   A'  CSR  at_ptr[m+1] at_ind[nnz] at_val[nnz]
+ *   type[m+n] i8, lb/ub/coef[m+n] f64 (scaled; coef = working costs)
+ *   head[m+n] i32  (first m basic, then n non-basic), bind[m+n] = head^-1
+ *   stat[n] i8, bbar[m], cbar[n], gamma[max(m,n)], refsp[m+n] i8
+ *
+ * Basis inverse ("structural kernel" form).  With P_S the basic positions
+ * that hold structural columns and R_N the rows whose auxiliary variable is
+ * non-basic (|P_S| = |R_N| = k), the only non-trivial block of inv(B) is
+ *      T = inv(B)[P_S, R_N] = -inv(A[R_N, J_B])          (k x k, dense)
+ * kept column-major in HBM with leading dimension ldt; rslot/slot_pos map
+ * positions <-> rows of T, cslot/slot_row map constraint rows <-> columns.
+ * FTRAN / BTRAN are one GEMV with T plus one gather pass over A' / A; a basis
+ * change is a rank-1 update of T plus O(k) bookkeeping.
+ */
+#ifndef GLPB_INTERNAL_CUH
+#define GLPB_INTERNAL_CUH
+
+#include <cuda_runtime.h>
+#include <cfloat>
+#include <climits>
+#include <cstdint>
+#include <string>
+#include <vector>
+#include "../../include/glpb200.h"
+
+/* GLP_* constants (lib/glpk.js) */
+enum { GLP_MIN = 1, GLP_MAX = 2 };
+enum { GLP_CV = 1, GLP_IV = 2 };
+enum { GLP_FR = 1, GLP_LO = 2, GLP_UP = 3, GLP_DB = 4, GLP_FX = 5 };
+enum { GLP_BS = 1, GLP_NL = 2, GLP_NU = 3, GLP_NF = 4, GLP_NS = 5 };
+enum { GLP_UNDEF = 1, GLP_FEAS = 2, GLP_INFEAS = 3, GLP_NOFEAS = 4, GLP_OPT = 5, GLP_UNBND = 6 };
+enum { GLP_PRIMAL = 1, GLP_DUALP = 2, GLP_DUAL = 3 };
+enum { GLP_PT_STD = 0x11, GLP_PT_PSE = 0x22 };
+enum { GLP_RT_STD = 0x11, GLP_RT_HAR = 0x22 };
+enum { GLP_BR_FFV = 1, GLP_BR_LFV = 2, GLP_BR_MFV = 3, GLP_BR_DTH = 4, GLP_BR_PCH = 5 };
+enum { GLP_BT_DFS = 1, GLP_BT_BFS = 2, GLP_BT_BLB = 3, GLP_BT_BPH = 4 };
+enum { GLP_PP_NONE = 0, GLP_PP_ROOT = 1, GLP_PP_ALL = 2 };
+enum { GLP_EBADB = 1, GLP_ESING = 2, GLP_ECOND = 3, GLP_EBOUND = 4, GLP_EFAIL = 5,
+       GLP_EOBJLL = 6, GLP_EOBJUL = 7, GLP_EITLIM = 8, GLP_ETMLIM = 9, GLP_ENOPFS = 10,
+       GLP_ENODFS = 11, GLP_EROOT = 12, GLP_ESTOP = 13, GLP_EMIPGAP = 14 };
+
+#define GLPB_KAPPA 0.10   /* lib/glpspx01.js:3 */
+
+/* iteration status written by the device, read by the host loop controller */
+enum {
+    ST_OK = 0,
+    ST_NONE1 = 1,      /* pricing found nothing (primal chuzc q / dual chuzr p) */
+    ST_D1D2 = 2,       /* primal: reduced cost of xN[q] inaccurate             */
+    ST_NONE2 = 3,      /* ratio test found nothing                             */
+    ST_PIVSMALL = 4,   /* pivot below 1e-5(1+0.01 max)                         */
+    ST_PIV12 = 5,      /* tcol[p] and trow[q] disagree                         */
+    ST_SINGULAR = 6,   /* refactorisation met a zero pivot                     */
+};
+
+#define P_NONE (-1)
+#define P_FLIP (-2)
+
+/* device control block; one per handle */
+struct Ctrl {
+    int status;
+    int q, p, p_stat;
+    int phase;
+    int k;              /* current size of T                                  */
+    int flag;           /* generic boolean result of check_* kernels          */
+    int cnt;            /* generic counter result (set_aux_obj)               */
+    int skip2;          /* ratio test: second pass not needed                 */
+    int sing;           /* refactorisation: singular                          */
+    int pad0, pad1;
+    double teta, delta, new_dq, tmax;
+    double tcol_max, trow_max, eps;
+    double piv1, piv2, d1, d2;
+    double gamma_q, delta_q;
+    double obj;         /* dual: tracked objective (bbar[0] in the reference)  */
+    double big, scal;   /* scratch scalars                                    */
+    double max_a;       /* largest |a| seen when building the kernel matrix   */
+    unsigned int ticket[16];
+};
+
+/* key used by every arg-reduction */
+struct Key {
+    double a, b, c;
+    int pos, aux;
+};
+
+struct glpb_prob {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int m = 0, n = 0, nnz = 0, dir = GLP_MIN;
+    double c0 = 0.0;
+    int ldt = 0;               /* leading dimension / capacity of T */
+    /* ---- host copies of the unscaled problem (the glp_prob fields) ---- */
+    std::vector<int> h_type, h_kind, h_stat;     /* [m+n] / [n] / [m+n] GLP_BS.. */
+    std::vector<double> h_lb, h_ub, h_coef, h_rii, h_sjj;
+    std::vector<int> h_aptr, h_aind;             /* host CSC (for B&B preprocessing) */
+    std::vector<double> h_aval;
+    std::vector<int> h_atptr, h_atind;           /* host CSR */
+    std::vector<double> h_atval;
+    std::vector<int> h_head;                     /* [m], values k+1 */
+    int valid = 0;
+    int pbs_stat = GLP_UNDEF, dbs_stat = GLP_UNDEF;
+    double obj_val = 0.0;
+    int it_cnt = 0, some = 0;
+    std::vector<double> h_prim, h_dual;          /* [m+n] */
+    int mip_stat = GLP_UNDEF;
+    double mip_obj = 0.0;
+    std::vector<double> h_mipx;
+    long mip_nodes = 0;
+    glpb_bfcp bfcp = {100, 0.10, 1e-6};
+    /* ---- device arrays ---- */
+    int *a_ptr = nullptr, *a_ind = nullptr, *at_ptr = nullptr, *at_ind = nullptr;
+    double *a_val = nullptr, *at_val = nullptr;
+    signed char *type = nullptr, *orig_type = nullptr, *stat = nullptr, *refsp = nullptr;
+    double *lb = nullptr, *ub = nullptr, *coef = nullptr, *orig_lb = nullptr, *orig_ub = nullptr;
+    double *obj = nullptr;            /* [n+1]: obj[0] = c0, obj[1+j] scaled original costs */
+    int *head = nullptr, *bind = nullptr;
+    double *bbar = nullptr, *cbar = nullptr, *gamma = nullptr;
+    double *tcol = nullptr, *trow = nullptr, *rho = nullptr;
+    double *svec = nullptr;           /* [n] PSE inner products s_j (primal) */
+    double *w1 = nullptr, *w2 = nullptr, *w3 = nullptr, *w4 = nullptr, *w5 = nullptr; /* [m] work */
+    double *yk = nullptr, *wk = nullptr;   /* [ldt] work in kernel space */
+    double *T = nullptr, *partial = nullptr;
+    int partial_rows = 0;
+    int *rslot = nullptr, *slot_pos = nullptr, *cslot = nullptr, *slot_row = nullptr;
+    int *gj_piv = nullptr;
+    double *gj_row = nullptr, *gj_col = nullptr;
+    Key *scratch = nullptr;           /* block partials of reductions */
+    Ctrl *ctrl = nullptr;             /* device */
+    Ctrl *h_ctrl = nullptr;           /* pinned host mirror */
+    double zeta = 1.0;
+    /* ---- counters ---- */
+    long n_iter = 0, n_refac = 0, n_launch = 0, n_sync = 0, n_update = 0;
+    double last_solve_us = 0.0;
+    int trace = 0;
+};
+
+void glpb_set_error(const char *fmt, ...);
+
+#define CK(call)                                                               \
+    do {                                                                       \
+        cudaError_t e__ = (call);                                              \
+        if (e__ != cudaSuccess) {                                              \
+            glpb_set_error("%s:%d: %s: %s", __FILE__, __LINE__, #call,         \
+                           cudaGetErrorString(e__));                           \
+            return GLPB_ENODEV;                                                \
+        }                                                                      \
+    } while (0)
+
+#endif

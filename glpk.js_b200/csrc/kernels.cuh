@@ -1,0 +1,1469 @@
+/* kernels.cuh -- hand-written sm_100a kernels of the simplex hot path.
+ *
+ * Every kernel that belongs to the iteration starts with
+ *     if (ctrl->status != ST_OK) return;
+ * so that the host can enqueue a whole iteration (or several) and look at the
+ * control block once: the first kernel that meets one of the reference's
+ * exceptional branches records it and the rest of the queue drains as no-ops.
+ *
+ * Selection kernels (pricing, ratio tests) use __dmul_rn/__dadd_rn/__ddiv_rn so
+ * that no FMA contraction can make them differ from the reference's IEEE
+ * double arithmetic: fed the same arrays they return the same index.
+ * Reductions are two-stage and combine block partials in index order, so the
+ * result does not depend on block scheduling.
+ */
+#ifndef GLPB_KERNELS_CUH
+#define GLPB_KERNELS_CUH
+#include "glpb_internal.cuh"
+
+#define FULLMASK 0xffffffffu
+
+/* ------------------------------------------------------------------ */
+/* reduction machinery                                                */
+/* ------------------------------------------------------------------ */
+
+__device__ __forceinline__ Key key_shfl_down(const Key &v, int off)
+{
+    Key o;
+    o.a = __shfl_down_sync(FULLMASK, v.a, off);
+    o.b = __shfl_down_sync(FULLMASK, v.b, off);
+    o.c = __shfl_down_sync(FULLMASK, v.c, off);
+    o.pos = __shfl_down_sync(FULLMASK, v.pos, off);
+    o.aux = __shfl_down_sync(FULLMASK, v.aux, off);
+    return o;
+}
+
+/* result valid in thread 0 of the block; all threads must call */
+template <class Comb>
+__device__ Key block_reduce(Key v, const Key &none, Comb comb)
+{
+    __shared__ Key sm[32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        Key o = key_shfl_down(v, off);
+        comb(v, o);
+    }
+    __syncthreads(); /* protect sm against a previous use */
+    if (lane == 0) sm[w] = v;
+    __syncthreads();
+    const int nw = (blockDim.x + 31) >> 5;
+    if (w == 0) {
+        v = (lane < nw) ? sm[lane] : none;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            Key o = key_shfl_down(v, off);
+            comb(v, o);
+        }
+    }
+    return v;
+}
+
+/* two-stage grid reduction; fin(result) runs in one thread of the last block */
+template <class Comb, class Fin>
+__device__ void grid_reduce(Key v, const Key &none, Key *scratch, unsigned int *ticket,
+                            Comb comb, Fin fin)
+{
+    __shared__ int is_last;
+    v = block_reduce(v, none, comb);
+    if (threadIdx.x == 0) {
+        scratch[blockIdx.x] = v;
+        __threadfence();
+        unsigned int t = atomicAdd(ticket, 1u);
+        is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        Key r = none;
+        for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) {
+            Key o;
+            o.a = __ldcg(&scratch[i].a); o.b = __ldcg(&scratch[i].b); o.c = __ldcg(&scratch[i].c);
+            o.pos = __ldcg(&scratch[i].pos); o.aux = __ldcg(&scratch[i].aux);
+            comb(r, o);
+        }
+        /* NOTE: per-thread accumulation above visits partials in a fixed
+           strided order, the tree below is fixed too: deterministic */
+        r = block_reduce(r, none, comb);
+        if (threadIdx.x == 0) {
+            *ticket = 0u;
+            fin(r);
+        }
+    }
+}
+
+struct CombArgMax { /* larger a wins, then smaller pos */
+    __device__ void operator()(Key &v, const Key &o) const
+    {
+        if (o.a > v.a || (o.a == v.a && o.pos < v.pos)) v = o;
+    }
+};
+struct CombRatio1 { /* smaller a (ratio), then larger b (|alfa|), then smaller pos */
+    __device__ void operator()(Key &v, const Key &o) const
+    {
+        if (o.a < v.a || (o.a == v.a && (o.b > v.b || (o.b == v.b && o.pos < v.pos)))) v = o;
+    }
+};
+struct CombRatio2 { /* larger b (|alfa|), then smaller pos */
+    __device__ void operator()(Key &v, const Key &o) const
+    {
+        if (o.b > v.b || (o.b == v.b && o.pos < v.pos)) v = o;
+    }
+};
+struct CombSum2 { /* a and b are sums, c is a maximum, aux a count, pos unused */
+    __device__ void operator()(Key &v, const Key &o) const
+    {
+        v.a += o.a; v.b += o.b; v.c = fmax(v.c, o.c); v.aux += o.aux;
+    }
+};
+
+__device__ __forceinline__ void atomic_max_abs(double *addr, double x)
+{
+    atomicMax((unsigned long long *)addr, (unsigned long long)__double_as_longlong(fabs(x)));
+}
+
+__device__ __forceinline__ double relax(double rtol, double bnd)
+{
+    /* rtol * (1.0 + kappa * |bnd|) without contraction */
+    return __dmul_rn(rtol, __dadd_rn(1.0, __dmul_rn(GLPB_KAPPA, fabs(bnd))));
+}
+
+__device__ __forceinline__ double get_xN(const signed char *stat, const int *head, const double *lb,
+                                         const double *ub, int m, int j)
+{
+    int k = head[m + j];
+    switch (stat[j]) {
+    case GLP_NL: return lb[k];
+    case GLP_NU: return ub[k];
+    case GLP_NF: return 0.0;
+    default: return lb[k]; /* GLP_NS */
+    }
+}
+
+/* ------------------------------------------------------------------ */
+/* pricing                                                            */
+/* ------------------------------------------------------------------ */
+
+/* chuzc (primal pricing), lib/glpspx01.js:646-688.
+   Algorithmic bytes: 17 per column (stat 1 + cbar 8 + gamma 8). */
+__global__ void k_chuzc_primal(Ctrl *ctrl, int n, const signed char *__restrict__ stat,
+                               const double *__restrict__ cbar, const double *__restrict__ gamma,
+                               double tol_dj, int set_status, Key *scratch)
+{
+    if (ctrl->status != ST_OK) return;
+    Key none = {0.0, 0.0, 0.0, INT_MAX, 0};
+    Key v = none;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+        double dj = cbar[j];
+        bool ok;
+        switch (stat[j]) {
+        case GLP_NL: ok = !(dj >= -tol_dj); break;
+        case GLP_NU: ok = !(dj <= +tol_dj); break;
+        case GLP_NF: ok = !(-tol_dj <= dj && dj <= +tol_dj); break;
+        default: ok = false;
+        }
+        if (ok) {
+            double temp = __ddiv_rn(__dmul_rn(dj, dj), gamma[j]);
+            if (v.a < temp) { v.a = temp; v.pos = j; }
+        }
+    }
+    grid_reduce(v, none, scratch, &ctrl->ticket[0], CombArgMax(), [=](const Key &r) {
+        ctrl->q = (r.a > 0.0 && r.pos != INT_MAX) ? r.pos : P_NONE;
+        ctrl->big = 0.0;
+        if (ctrl->q == P_NONE && set_status) ctrl->status = ST_NONE1;
+    });
+}
+
+/* chuzr (dual pricing), lib/glpspx02.js:572-625.
+   Algorithmic bytes: 37 per row (head 4, type 1, lb 8, ub 8, bbar 8, gamma 8). */
+__global__ void k_chuzr_dual(Ctrl *ctrl, int m, const signed char *__restrict__ type,
+                             const double *__restrict__ lb, const double *__restrict__ ub,
+                             const int *__restrict__ head, const double *__restrict__ bbar,
+                             const double *__restrict__ gamma, double tol_bnd, int set_status,
+                             Key *scratch)
+{
+    if (ctrl->status != ST_OK) return;
+    Key none = {0.0, 0.0, 0.0, INT_MAX, 0};
+    Key v = none;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
+        int k = head[i];
+        int t = type[k];
+        double ri = 0.0, bi = bbar[i];
+        if (t == GLP_LO || t == GLP_DB || t == GLP_FX) {
+            double l = lb[k], eps = relax(tol_bnd, l);
+            if (bi < __dsub_rn(l, eps)) ri = __dsub_rn(l, bi);
+        }
+        if (t == GLP_UP || t == GLP_DB || t == GLP_FX) {
+            double u = ub[k], eps = relax(tol_bnd, u);
+            if (bi > __dadd_rn(u, eps)) ri = __dsub_rn(u, bi);
+        }
+        if (ri != 0.0) {
+            double g = gamma[i];
+            if (g < DBL_EPSILON) g = DBL_EPSILON;
+            double temp = __ddiv_rn(__dmul_rn(ri, ri), g);
+            if (v.a < temp) { v.a = temp; v.b = ri; v.pos = i; }
+        }
+    }
+    grid_reduce(v, none, scratch, &ctrl->ticket[0], CombArgMax(), [=](const Key &r) {
+        bool found = (r.a > 0.0 && r.pos != INT_MAX);
+        ctrl->p = found ? r.pos : P_NONE;
+        ctrl->delta = found ? r.b : 0.0;
+        ctrl->big = 0.0;
+        if (!found && set_status) ctrl->status = ST_NONE1;
+    });
+}
+
+/* ------------------------------------------------------------------ */
+/* ratio tests                                                        */
+/* ------------------------------------------------------------------ */
+
+/* chuzr (primal ratio test), lib/glpspx01.js:808-1028, one pass per launch.
+   ind == NULL: dense mode over positions 0..num-1 with the significance mask
+   |tcol| >= ctrl->eps; ind != NULL: the caller's sorted list (kernel parity).
+   Ties are broken by list position, as the sequential loop does.
+   Algorithmic bytes: 49 per examined entry and pass. */
+__global__ void k_ratio_primal(Ctrl *ctrl, int pass, int m, const signed char *__restrict__ type,
+                               const double *__restrict__ lb, const double *__restrict__ ub,
+                               const double *__restrict__ coef, const int *__restrict__ head,
+                               const double *__restrict__ bbar, const double *__restrict__ tcol,
+                               const int *__restrict__ ind, int num, double rtol, int rigorous,
+                               Key *scratch)
+{
+    if (ctrl->status != ST_OK) return;
+    if (pass == 2 && ctrl->skip2) return;
+    const int q = ctrl->q, phase = ctrl->phase;
+    const double s = (ctrl->d1 > 0.0 ? -1.0 : +1.0); /* d1 holds the (corrected) cbar[q] */
+    const double eps = (ind == nullptr ? ctrl->eps : 0.0);
+    const double tmax = ctrl->tmax;
+    const int kq = head[m + q];
+    Key none = {DBL_MAX, 0.0, 0.0, INT_MAX, 0};
+    Key v = none;
+    if (pass == 1 && blockIdx.x == 0 && threadIdx.x == 0 && type[kq] == GLP_DB) {
+        v.a = __dsub_rn(ub[kq], lb[kq]); v.b = 1.0; v.pos = -1; v.aux = 0;
+    }
+    for (int pos = blockIdx.x * blockDim.x + threadIdx.x; pos < num; pos += gridDim.x * blockDim.x) {
+        int i = ind ? ind[pos] : pos;
+        double tc = tcol[i];
+        if (tc == 0.0 || fabs(tc) < eps) continue;
+        int k = head[i];
+        double alfa = __dmul_rn(s, tc), t, bi = bbar[i];
+        int tk = type[k], i_stat;
+        double ck = (phase == 1 ? coef[k] : 0.0);
+        if (alfa > 0.0) {
+            if (phase == 1 && ck < 0.0) {
+                double b = lb[k];
+                t = (pass == 1) ? __dadd_rn(b, relax(rtol, b)) : b;
+                i_stat = GLP_NL;
+            } else if (phase == 1 && ck > 0.0)
+                continue;
+            else if (tk == GLP_UP || tk == GLP_DB || tk == GLP_FX) {
+                double b = ub[k];
+                t = (pass == 1) ? __dadd_rn(b, relax(rtol, b)) : b;
+                i_stat = GLP_NU;
+            } else
+                continue;
+        } else {
+            if (phase == 1 && ck > 0.0) {
+                double b = ub[k];
+                t = (pass == 1) ? __dsub_rn(b, relax(rtol, b)) : b;
+                i_stat = GLP_NU;
+            } else if (phase == 1 && ck < 0.0)
+                continue;
+            else if (tk == GLP_LO || tk == GLP_DB || tk == GLP_FX) {
+                double b = lb[k];
+                t = (pass == 1) ? __dsub_rn(b, relax(rtol, b)) : b;
+                i_stat = GLP_NL;
+            } else
+                continue;
+        }
+        t = __ddiv_rn(__dsub_rn(t, bi), alfa);
+        if (t < 0.0) t = 0.0;
+        Key c = {t, fabs(alfa), 0.0, pos, i_stat};
+        if (pass == 1) CombRatio1()(v, c);
+        else if (t <= tmax) CombRatio2()(v, c);
+    }
+    auto fin = [=](const Key &r) {
+        int p, p_stat = r.aux;
+        double teta = r.a;
+        if (r.pos == INT_MAX) p = P_NONE;
+        else if (r.pos == -1) p = P_FLIP;
+        else p = ind ? ind[r.pos] : r.pos;
+        if (pass == 1) {
+            ctrl->skip2 = (rtol == 0.0 || p < 0 || teta == 0.0);
+            ctrl->tmax = teta;
+            if (!ctrl->skip2) { ctrl->p = p; return; }
+        }
+        if (p >= 0 && type[head[p]] == GLP_FX) p_stat = GLP_NS;
+        ctrl->p = p;
+        ctrl->p_stat = p_stat;
+        ctrl->teta = __dmul_rn(s, teta);
+        if (p == P_NONE) { ctrl->status = ST_NONE2; return; }
+        if (p >= 0) {
+            double piv = tcol[p];
+            double e5 = 1e-5 * (1.0 + 0.01 * ctrl->tcol_max);
+            ctrl->piv1 = piv;
+            if (fabs(piv) < e5 && !rigorous) ctrl->status = ST_PIVSMALL;
+        }
+    };
+    if (pass == 1) grid_reduce(v, none, scratch, &ctrl->ticket[1], CombRatio1(), fin);
+    else grid_reduce(v, none, scratch, &ctrl->ticket[1], CombRatio2(), fin);
+}
+
+/* chuzc (dual ratio test), lib/glpspx02.js:793-935, one pass per launch.
+   Algorithmic bytes: 21 per examined entry and pass (idx 4, trow 8, stat 1, cbar 8). */
+__global__ void k_ratio_dual(Ctrl *ctrl, int pass, const signed char *__restrict__ stat,
+                             const double *__restrict__ cbar, const double *__restrict__ trow,
+                             const int *__restrict__ ind, int num, double rtol, int rigorous,
+                             Key *scratch)
+{
+    if (ctrl->status != ST_OK) return;
+    if (pass == 2 && ctrl->skip2) return;
+    const double s = (ctrl->delta > 0.0 ? +1.0 : -1.0);
+    const double eps = (ind == nullptr ? ctrl->eps : 0.0);
+    const double tmax = ctrl->tmax;
+    Key none = {DBL_MAX, 0.0, 0.0, INT_MAX, 0};
+    Key v = none;
+    for (int pos = blockIdx.x * blockDim.x + threadIdx.x; pos < num; pos += gridDim.x * blockDim.x) {
+        int j = ind ? ind[pos] : pos;
+        double tr = trow[j];
+        if (tr == 0.0 || fabs(tr) < eps) continue;
+        double alfa = __dmul_rn(s, tr), t;
+        int st = stat[j];
+        if (alfa > 0.0) {
+            if (st == GLP_NL || st == GLP_NF) t = (pass == 1) ? __dadd_rn(cbar[j], rtol) : cbar[j];
+            else continue;
+        } else {
+            if (st == GLP_NU || st == GLP_NF) t = (pass == 1) ? __dsub_rn(cbar[j], rtol) : cbar[j];
+            else continue;
+        }
+        t = __ddiv_rn(t, alfa);
+        if (t < 0.0) t = 0.0;
+        Key c = {t, fabs(alfa), 0.0, pos, 0};
+        if (pass == 1) CombRatio1()(v, c);
+        else if (t <= tmax) CombRatio2()(v, c);
+    }
+    auto fin = [=](const Key &r) {
+        int q = (r.pos == INT_MAX) ? P_NONE : (ind ? ind[r.pos] : r.pos);
+        double teta = r.a;
+        if (pass == 1) {
+            ctrl->skip2 = (rtol == 0.0 || q < 0 || teta == 0.0);
+            ctrl->tmax = teta;
+            if (!ctrl->skip2) { ctrl->q = q; return; }
+        }
+        ctrl->q = q;
+        ctrl->new_dq = __dmul_rn(s, teta);
+        if (q == P_NONE) { ctrl->status = ST_NONE2; return; }
+        double piv = trow[q];
+        double e5 = 1e-5 * (1.0 + 0.01 * ctrl->trow_max);
+        ctrl->piv2 = piv;
+        if (fabs(piv) < e5 && !rigorous) ctrl->status = ST_PIVSMALL;
+    };
+    if (pass == 1) grid_reduce(v, none, scratch, &ctrl->ticket[1], CombRatio1(), fin);
+    else grid_reduce(v, none, scratch, &ctrl->ticket[1], CombRatio2(), fin);
+}
+
+/* ------------------------------------------------------------------ */
+/* sparse passes over A (all gathers: no atomics, deterministic)       */
+/* ------------------------------------------------------------------ */
+
+template <int G> __device__ __forceinline__ double group_sum(double v)
+{
+#pragma unroll
+    for (int off = G / 2; off > 0; off >>= 1) v += __shfl_down_sync(FULLMASK, v, off, G);
+    return v;
+}
+
+/* Pivot row, lib/glpspx01.js:1058-1098 and lib/glpspx02.js:655-693:
+       trow[j] = -rho' N_j   for every non-basic, non-fixed j
+   as dot products over the CSC columns, G lanes per column.  With u != NULL
+   it also returns the PSE inner products s_j = N_j' u of update_gamma
+   (lib/glpspx01.js:1231-1241) from the same pass over A.
+   Algorithmic bytes: 12 per non-zero of a non-basic column + 13 n + 8 m. */
+template <int G>
+__global__ void k_trow(Ctrl *ctrl, int m, int n, const int *__restrict__ a_ptr,
+                       const int *__restrict__ a_ind, const double *__restrict__ a_val,
+                       const int *__restrict__ head, const signed char *__restrict__ stat,
+                       const double *__restrict__ rho, const double *__restrict__ u,
+                       double *__restrict__ trow, double *__restrict__ svec, int want_max)
+{
+    if (ctrl->status != ST_OK) return;
+    const int gid = (blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const int lane = threadIdx.x % G;
+    double t = 0.0, s = 0.0;
+    bool live = (gid < n) && stat[gid] != GLP_NS;
+    if (live) {
+        int k = head[m + gid];
+        if (k < m) {
+            if (lane == 0) { t = -rho[k]; if (u) s = u[k]; }
+        } else {
+            int beg = a_ptr[k - m], end = a_ptr[k - m + 1];
+            for (int ptr = beg + lane; ptr < end; ptr += G) {
+                int r = a_ind[ptr];
+                double a = a_val[ptr];
+                t += rho[r] * a;
+                if (u) s -= a * u[r];
+            }
+        }
+    }
+    t = group_sum<G>(t);
+    if (u) s = group_sum<G>(s);
+    if (gid < n && lane == 0) {
+        trow[gid] = t;
+        if (u) svec[gid] = s;
+    }
+    if (want_max) {
+        /* |trow|_inf: warp max, then one atomic per block (bit pattern of a
+           non-negative double orders like an unsigned integer) */
+        __shared__ double wmax[32];
+        double a = (gid < n && lane == 0) ? fabs(t) : 0.0;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) a = fmax(a, __shfl_down_sync(FULLMASK, a, off));
+        if ((threadIdx.x & 31) == 0) wmax[threadIdx.x >> 5] = a;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            a = (threadIdx.x < (blockDim.x >> 5)) ? wmax[threadIdx.x] : 0.0;
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) a = fmax(a, __shfl_down_sync(FULLMASK, a, off));
+            if (threadIdx.x == 0 && a > 0.0) atomic_max_abs(&ctrl->big, a);
+        }
+    }
+}
+
+/* tail of FTRAN: x[i] for every basic position from y = T * h_N
+   (see glpb_internal.cuh).  One group of G lanes per position, gathering the
+   row of A that belongs to a basic auxiliary variable. */
+template <int G>
+__global__ void k_ftran_tail(Ctrl *ctrl, int m, const int *__restrict__ at_ptr,
+                             const int *__restrict__ at_ind, const double *__restrict__ at_val,
+                             const int *__restrict__ head, const int *__restrict__ bind,
+                             const int *__restrict__ rslot, const double *__restrict__ h,
+                             const double *__restrict__ y, double *__restrict__ x)
+{
+    if (ctrl->status != ST_OK) return;
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const int lane = threadIdx.x % G;
+    double acc = 0.0;
+    int kk = (i < m) ? head[i] : m;
+    if (i < m && kk < m) {
+        int beg = at_ptr[kk], end = at_ptr[kk + 1];
+        for (int ptr = beg + lane; ptr < end; ptr += G) {
+            int pb = bind[m + at_ind[ptr]];
+            if (pb < m) acc += at_val[ptr] * y[rslot[pb]];
+        }
+    }
+    acc = group_sum<G>(acc);
+    if (i < m && lane == 0) x[i] = (kk < m) ? h[kk] + acc : y[rslot[i]];
+}
+
+/* head of BTRAN: w[b] = c[pos_b] + sum_{r in R_B} A[r, j_b] c[bind[r]] */
+template <int G>
+__global__ void k_btran_head(Ctrl *ctrl, int m, const int *__restrict__ a_ptr,
+                             const int *__restrict__ a_ind, const double *__restrict__ a_val,
+                             const int *__restrict__ head, const int *__restrict__ bind,
+                             const int *__restrict__ slot_pos, const double *__restrict__ c,
+                             double *__restrict__ w)
+{
+    if (ctrl->status != ST_OK) return;
+    const int k = ctrl->k;
+    const int b = (blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const int lane = threadIdx.x % G;
+    double acc = 0.0;
+    int i = 0;
+    if (b < k) {
+        i = slot_pos[b];
+        int j = head[i] - m;
+        int beg = a_ptr[j], end = a_ptr[j + 1];
+        for (int ptr = beg + lane; ptr < end; ptr += G) {
+            int pr = bind[a_ind[ptr]];
+            if (pr < m) acc += a_val[ptr] * c[pr];
+        }
+    }
+    acc = group_sum<G>(acc);
+    if (b < k && lane == 0) w[b] = c[i] + acc;
+}
+
+__global__ void k_btran_tail(Ctrl *ctrl, int m, const int *__restrict__ cslot,
+                             const int *__restrict__ bind, const double *__restrict__ c,
+                             const double *__restrict__ zn, double *__restrict__ z)
+{
+    if (ctrl->status != ST_OK) return;
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= m) return;
+    int cs = cslot[r];
+    z[r] = (cs >= 0) ? zn[cs] : c[bind[r]];
+}
+
+/* residual of B x = h (error_ftran, lib/glpspx01.js:219-249), by rows */
+template <int G>
+__global__ void k_resid_ftran(Ctrl *ctrl, int m, const int *__restrict__ at_ptr,
+                              const int *__restrict__ at_ind, const double *__restrict__ at_val,
+                              const int *__restrict__ bind, const double *__restrict__ h,
+                              const double *__restrict__ x, double *__restrict__ r)
+{
+    if (ctrl->status != ST_OK) return;
+    const int row = (blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const int lane = threadIdx.x % G;
+    double acc = 0.0;
+    if (row < m) {
+        for (int ptr = at_ptr[row] + lane; ptr < at_ptr[row + 1]; ptr += G) {
+            int pb = bind[m + at_ind[ptr]];
+            if (pb < m) acc += at_val[ptr] * x[pb];
+        }
+    }
+    acc = group_sum<G>(acc);
+    if (row < m && lane == 0) {
+        int pr = bind[row];
+        r[row] = h[row] - (pr < m ? x[pr] : 0.0) + acc;
+    }
+}
+
+/* residual of B' x = h (error_btran, lib/glpspx01.js:265-293), by columns */
+template <int G>
+__global__ void k_resid_btran(Ctrl *ctrl, int m, const int *__restrict__ a_ptr,
+                              const int *__restrict__ a_ind, const double *__restrict__ a_val,
+                              const int *__restrict__ head, const double *__restrict__ h,
+                              const double *__restrict__ x, double *__restrict__ r)
+{
+    if (ctrl->status != ST_OK) return;
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const int lane = threadIdx.x % G;
+    double acc = 0.0;
+    int k = (i < m) ? head[i] : 0;
+    if (i < m && k >= m) {
+        for (int ptr = a_ptr[k - m] + lane; ptr < a_ptr[k - m + 1]; ptr += G)
+            acc += a_val[ptr] * x[a_ind[ptr]];
+    }
+    acc = group_sum<G>(acc);
+    if (i < m && lane == 0) r[i] = (k < m) ? h[i] - x[k] : h[i] + acc;
+}
+
+/* right-hand side of eval_beta: h = -N xN (lib/glpspx01.js:483-505), by rows */
+template <int G>
+__global__ void k_beta_rhs(Ctrl *ctrl, int m, int n, const int *__restrict__ at_ptr,
+                           const int *__restrict__ at_ind, const double *__restrict__ at_val,
+                           const int *__restrict__ head, const int *__restrict__ bind,
+                           const signed char *__restrict__ stat, const double *__restrict__ lb,
+                           const double *__restrict__ ub, double *__restrict__ h)
+{
+    if (ctrl->status != ST_OK) return;
+    const int row = (blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const int lane = threadIdx.x % G;
+    double acc = 0.0;
+    if (row < m) {
+        for (int ptr = at_ptr[row] + lane; ptr < at_ptr[row + 1]; ptr += G) {
+            int pb = bind[m + at_ind[ptr]];
+            if (pb >= m) acc += at_val[ptr] * get_xN(stat, head, lb, ub, m, pb - m);
+        }
+    }
+    acc = group_sum<G>(acc);
+    if (row < m && lane == 0) {
+        int pr = bind[row];
+        h[row] = acc - (pr >= m ? get_xN(stat, head, lb, ub, m, pr - m) : 0.0);
+    }
+}
+
+/* eval_cbar: d_j = c_k - N_j' pi (lib/glpspx01.js:531-584), by columns */
+template <int G>
+__global__ void k_cbar(Ctrl *ctrl, int m, int n, const int *__restrict__ a_ptr,
+                       const int *__restrict__ a_ind, const double *__restrict__ a_val,
+                       const int *__restrict__ head, const double *__restrict__ coef,
+                       const double *__restrict__ pi, double *__restrict__ cbar)
+{
+    if (ctrl->status != ST_OK) return;
+    const int j = (blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const int lane = threadIdx.x % G;
+    double acc = 0.0;
+    int k = (j < n) ? head[m + j] : 0;
+    if (j < n && k >= m) {
+        for (int ptr = a_ptr[k - m] + lane; ptr < a_ptr[k - m + 1]; ptr += G)
+            acc += a_val[ptr] * pi[a_ind[ptr]];
+    }
+    acc = group_sum<G>(acc);
+    if (j < n && lane == 0) cbar[j] = (k < m) ? coef[k] - pi[k] : coef[k] + acc;
+}
+
+/* dual update_gamma, first half (lib/glpspx02.js:1103-1132): by rows,
+       v[r] = sum_{j in C, non-basic} N_j[r] * trow_j */
+template <int G>
+__global__ void k_dual_gamma_rhs(Ctrl *ctrl, int m, const int *__restrict__ at_ptr,
+                                 const int *__restrict__ at_ind, const double *__restrict__ at_val,
+                                 const int *__restrict__ bind, const signed char *__restrict__ refsp,
+                                 const double *__restrict__ trow, double *__restrict__ v)
+{
+    if (ctrl->status != ST_OK) return;
+    const int row = (blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const int lane = threadIdx.x % G;
+    double acc = 0.0;
+    if (row < m) {
+        for (int ptr = at_ptr[row] + lane; ptr < at_ptr[row + 1]; ptr += G) {
+            int jj = at_ind[ptr];
+            int pb = bind[m + jj];
+            if (pb >= m && refsp[m + jj]) acc -= trow[pb - m] * at_val[ptr];
+        }
+    }
+    acc = group_sum<G>(acc);
+    if (row < m && lane == 0) {
+        int pr = bind[row];
+        v[row] = acc + ((pr >= m && refsp[row]) ? trow[pr - m] : 0.0);
+    }
+}
+
+/* ------------------------------------------------------------------ */
+/* dense work on T                                                    */
+/* ------------------------------------------------------------------ */
+
+#define GEMV_TILE 128
+
+/* y_part[s][b] = sum over a tile of columns  T[b,cs] * h[slot_row[cs]].
+   Columns whose right-hand side is exactly zero are skipped, which makes the
+   same kernel the sparse-rhs FTRAN of eval_tcol.  8 k^2 bytes when h is dense. */
+__global__ void k_gemvN_part(Ctrl *ctrl, const double *__restrict__ T, int ldt,
+                             const double *__restrict__ h, const int *__restrict__ slot_row,
+                             double *__restrict__ part)
+{
+    if (ctrl->status != ST_OK) return;
+    const int k = ctrl->k;
+    const int c0 = blockIdx.y * GEMV_TILE;
+    if (c0 >= k || (int)(blockIdx.x * GEMV_TILE) >= k) return;
+    __shared__ double hs[GEMV_TILE];
+    const int cn = min(GEMV_TILE, k - c0);
+    if ((int)threadIdx.x < cn) hs[threadIdx.x] = h[slot_row[c0 + threadIdx.x]];
+    __syncthreads();
+    const int b = blockIdx.x * GEMV_TILE + threadIdx.x;
+    if (b >= k) return;
+    double acc = 0.0;
+    const double *col = T + (size_t)c0 * ldt + b;
+#pragma unroll 4
+    for (int c = 0; c < cn; c++) {
+        double hv = hs[c];
+        if (hv != 0.0) acc += col[(size_t)c * ldt] * hv;
+    }
+    part[(size_t)blockIdx.y * ldt + b] = acc;
+}
+
+__global__ void k_gemvN_fin(Ctrl *ctrl, int ldt, const double *__restrict__ part,
+                            double *__restrict__ y)
+{
+    if (ctrl->status != ST_OK) return;
+    const int k = ctrl->k;
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= k) return;
+    const int S = (k + GEMV_TILE - 1) / GEMV_TILE;
+    double acc = 0.0;
+    for (int s = 0; s < S; s++) acc += part[(size_t)s * ldt + b];
+    y[b] = acc;
+}
+
+/* zn[cs] = sum_b T[b,cs] * w[b]; one warp per column, coalesced */
+__global__ void k_gemvT(Ctrl *ctrl, const double *__restrict__ T, int ldt,
+                        const double *__restrict__ w, double *__restrict__ zn)
+{
+    if (ctrl->status != ST_OK) return;
+    const int k = ctrl->k;
+    const int cs = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (cs >= k) return;
+    const double *col = T + (size_t)cs * ldt;
+    double acc = 0.0;
+    for (int b = lane; b < k; b += 32) acc += col[b] * w[b];
+    acc = group_sum<32>(acc);
+    if (lane == 0) zn[cs] = acc;
+}
+
+/* rho = row p of inv(B) (eval_rho, lib/glpspx01.js:1030-1042) read straight
+   out of T instead of a BTRAN of e_p */
+__global__ void k_rho(Ctrl *ctrl, int m, const double *__restrict__ T, int ldt,
+                      const int *__restrict__ at_ptr, const int *__restrict__ at_ind,
+                      const double *__restrict__ at_val, const int *__restrict__ head,
+                      const int *__restrict__ bind, const int *__restrict__ rslot,
+                      const int *__restrict__ cslot, double *__restrict__ rho)
+{
+    if (ctrl->status != ST_OK) return;
+    const int p = ctrl->p;
+    if (p < 0) return;
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= m) return;
+    const int cs = cslot[r];
+    if (cs < 0) { rho[r] = (bind[r] == p) ? 1.0 : 0.0; return; }
+    const int kp = head[p];
+    const double *col = T + (size_t)cs * ldt;
+    if (kp >= m) { rho[r] = col[rslot[p]]; return; }
+    double acc = 0.0;
+    for (int ptr = at_ptr[kp]; ptr < at_ptr[kp + 1]; ptr++) {
+        int pb = bind[m + at_ind[ptr]];
+        if (pb < m) acc += at_val[ptr] * col[rslot[pb]];
+    }
+    rho[r] = acc;
+}
+
+/* rank-1 part of a basis change:  inv(B)' = E inv(B)  restricted to T.
+   For b, cs < k:  T[b,cs] -= (tcol[pos_b]/tcol_p) rho[row_cs]   (pos_b != p)
+                   T[b,cs]  = -rho[row_cs]/tcol_p                (pos_b == p)
+   Algorithmic bytes: 16 k^2 (read + write of T). */
+#define UPD_TB 256
+#define UPD_TC 16
+__global__ void k_update_rank1(Ctrl *ctrl, double *__restrict__ T, int ldt,
+                               const double *__restrict__ tcol, const double *__restrict__ rho,
+                               const int *__restrict__ slot_pos, const int *__restrict__ slot_row)
+{
+    if (ctrl->status != ST_OK) return;
+    const int p = ctrl->p;
+    if (p < 0) return;
+    const int k = ctrl->k;
+    const int b = blockIdx.x * UPD_TB + threadIdx.x;
+    const int c0 = blockIdx.y * UPD_TC;
+    if (c0 >= k) return;
+    __shared__ double rs[UPD_TC];
+    const int cn = min(UPD_TC, k - c0);
+    if ((int)threadIdx.x < cn) rs[threadIdx.x] = rho[slot_row[c0 + threadIdx.x]];
+    __syncthreads();
+    if (b >= k) return;
+    const int i = slot_pos[b];
+    const double tp = tcol[p];
+    double *col = T + (size_t)c0 * ldt + b;
+    if (i == p) {
+        const double f = -1.0 / tp;
+#pragma unroll 4
+        for (int c = 0; c < cn; c++) col[(size_t)c * ldt] = rs[c] * f;
+    } else {
+        const double f = tcol[i] / tp;
+        if (f != 0.0) {
+#pragma unroll 4
+            for (int c = 0; c < cn; c++) col[(size_t)c * ldt] -= f * rs[c];
+        }
+    }
+}
+
+/* the O(k) remainder of a basis change: append/remove a row and/or column of
+   T, maintain the slot maps, swap head/bind and set the new non-basic status
+   (change_basis, lib/glpspx01.js:1310-1371 / lib/glpspx02.js:1259-1294).
+   One block. */
+__global__ void k_update_fix(Ctrl *ctrl, int m, double *__restrict__ T, int ldt,
+                             const double *__restrict__ tcol, const double *__restrict__ rho,
+                             int *__restrict__ rslot, int *__restrict__ slot_pos,
+                             int *__restrict__ cslot, int *__restrict__ slot_row,
+                             int *__restrict__ head, int *__restrict__ bind,
+                             signed char *__restrict__ stat, const signed char *__restrict__ type,
+                             int dual)
+{
+    if (ctrl->status != ST_OK) return;
+    const int p = ctrl->p, q = ctrl->q;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    if (p == P_FLIP) {
+        if (tid == 0) stat[q] = (stat[q] == GLP_NL) ? GLP_NU : GLP_NL;
+        return;
+    }
+    const int k = ctrl->k;
+    const int kp = head[p], kq = head[m + q];
+    const bool LS = (kp < m), ES = (kq < m);
+    const double tp = tcol[p];
+    const int csq = ES ? cslot[kq] : -1;
+    const int bp = LS ? -1 : rslot[p];
+    /* 1. new column for row kp (it joins R_N): inv(B)'[i,kp] = -tcol_i/tcol_p,
+          i != p; 1/d_p = -1/tcol_p at i = p */
+    const int ctgt = LS ? (ES ? csq : k) : -1;
+    const int bnew = (LS && !ES) ? k : -1;
+    if (LS) {
+        double *col = T + (size_t)ctgt * ldt;
+        for (int b = tid; b < k; b += nt) col[b] = -tcol[slot_pos[b]] / tp;
+        if (bnew >= 0 && tid == 0) col[bnew] = -1.0 / tp;
+    }
+    /* 2. new row for position p (it joins P_S) */
+    if (bnew >= 0) {
+        for (int cs = tid; cs < k; cs += nt)
+            T[(size_t)cs * ldt + bnew] = -rho[slot_row[cs]] / tp;
+    }
+    __syncthreads();
+    /* 3. removals: the last column/row moves into the hole */
+    int knew = k;
+    if (LS && !ES) knew = k + 1;
+    if (!LS && ES) {
+        knew = k - 1;
+        /* column csq <- column k-1 ; row bp <- row k-1 */
+        if (csq != k - 1) {
+            double *dst = T + (size_t)csq * ldt;
+            const double *src = T + (size_t)(k - 1) * ldt;
+            for (int b = tid; b < k; b += nt) dst[b] = src[b];
+        }
+        __syncthreads();
+        if (bp != k - 1) {
+            for (int cs = tid; cs < k; cs += nt)
+                T[(size_t)cs * ldt + bp] = T[(size_t)cs * ldt + (k - 1)];
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        /* slot maps */
+        if (LS) { cslot[kp] = ctgt; slot_row[ctgt] = kp; }
+        if (ES) {
+            cslot[kq] = -1;
+            if (!LS) {
+                if (csq != k - 1) { int rl = slot_row[k - 1]; slot_row[csq] = rl; cslot[rl] = csq; }
+            }
+        }
+        if (bnew >= 0) { rslot[p] = bnew; slot_pos[bnew] = p; }
+        if (!LS && ES) {
+            rslot[p] = -1;
+            if (bp != k - 1) { int pl = slot_pos[k - 1]; slot_pos[bp] = pl; rslot[pl] = bp; }
+        }
+        ctrl->k = knew;
+        /* basis header */
+        head[p] = kq; head[m + q] = kp;
+        bind[kq] = p; bind[kp] = m + q;
+        if (dual) {
+            if (type[kp] == GLP_FX) stat[q] = GLP_NS;
+            else stat[q] = (ctrl->delta > 0.0) ? GLP_NL : GLP_NU;
+        } else
+            stat[q] = (signed char)ctrl->p_stat;
+    }
+}
+
+/* ------------------------------------------------------------------ */
+/* refactorisation: T = -inv(A[R_N, J_B]) by Gauss-Jordan             */
+/* ------------------------------------------------------------------ */
+
+/* slot maps from head/bind: structural basic positions and non-basic rows in
+   ascending order.  One block of 1024 threads, chunked scan. */
+__global__ void k_build_slots(Ctrl *ctrl, int m, const int *__restrict__ head,
+                              const int *__restrict__ bind, int *__restrict__ rslot,
+                              int *__restrict__ slot_pos, int *__restrict__ cslot,
+                              int *__restrict__ slot_row)
+{
+    __shared__ int cnt_r[1024], cnt_c[1024];
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int chunk = (m + nt - 1) / nt;
+    const int beg = min(m, tid * chunk), end = min(m, beg + chunk);
+    int nr = 0, nc = 0;
+    for (int i = beg; i < end; i++) {
+        if (head[i] >= m) nr++;
+        if (bind[i] >= m) nc++;
+    }
+    cnt_r[tid] = nr; cnt_c[tid] = nc;
+    __syncthreads();
+    if (tid == 0) {
+        int sr = 0, sc = 0;
+        for (int t = 0; t < nt; t++) {
+            int a = cnt_r[t], b = cnt_c[t];
+            cnt_r[t] = sr; cnt_c[t] = sc;
+            sr += a; sc += b;
+        }
+        ctrl->k = sr;
+        ctrl->sing = (sr != sc);
+        ctrl->max_a = 0.0;
+    }
+    __syncthreads();
+    int br = cnt_r[tid], bc = cnt_c[tid];
+    for (int i = beg; i < end; i++) {
+        if (head[i] >= m) { rslot[i] = br; slot_pos[br] = i; br++; } else rslot[i] = -1;
+        if (bind[i] >= m) { cslot[i] = bc; slot_row[bc] = i; bc++; } else cslot[i] = -1;
+    }
+}
+
+/* M[cs, b] = A[row_cs, j_b]; M shares storage with T (column b contiguous) */
+__global__ void k_build_kernel_matrix(Ctrl *ctrl, int m, double *__restrict__ T, int ldt,
+                                      const int *__restrict__ a_ptr, const int *__restrict__ a_ind,
+                                      const double *__restrict__ a_val, const int *__restrict__ head,
+                                      const int *__restrict__ slot_pos, const int *__restrict__ cslot)
+{
+    const int k = ctrl->k;
+    const int b = blockIdx.x;
+    if (b >= k) return;
+    double *col = T + (size_t)b * ldt;
+    for (int cs = threadIdx.x; cs < k; cs += blockDim.x) col[cs] = 0.0;
+    __syncthreads();
+    const int j = head[slot_pos[b]] - m;
+    double mx = 0.0;
+    for (int ptr = a_ptr[j] + threadIdx.x; ptr < a_ptr[j + 1]; ptr += blockDim.x) {
+        int cs = cslot[a_ind[ptr]];
+        if (cs >= 0) { col[cs] = a_val[ptr]; mx = fmax(mx, fabs(a_val[ptr])); }
+    }
+    if (mx > 0.0) atomic_max_abs(&ctrl->max_a, mx);
+}
+
+/* Gauss-Jordan step t, part 1 (one block): partial pivoting in column t over
+   rows >= t, row swap, save the pivot column and the scaled pivot row */
+__global__ void k_gj_pivot(Ctrl *ctrl, int t, double *__restrict__ X, int ldt,
+                           int *__restrict__ piv, double *__restrict__ rowt,
+                           double *__restrict__ colt)
+{
+    if (ctrl->sing) return;
+    const int k = ctrl->k;
+    if (t >= k) return;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    double *ct = X + (size_t)t * ldt;
+    Key none = {-1.0, 0.0, 0.0, INT_MAX, 0};
+    Key v = none;
+    for (int i = t + tid; i < k; i += nt) {
+        Key c = {fabs(ct[i]), 0.0, 0.0, i, 0};
+        CombArgMax()(v, c);
+    }
+    v = block_reduce(v, none, CombArgMax());
+    __shared__ int s_r;
+    __shared__ double s_pv;
+    if (tid == 0) {
+        s_r = v.pos;
+        piv[t] = v.pos;
+        if (!(v.a > 1e-13 * fmax(ctrl->max_a, 1e-300))) { ctrl->sing = 1; s_r = -1; }
+    }
+    __syncthreads();
+    const int r = s_r;
+    if (r < 0) return;
+    if (r != t) {
+        for (int c = tid; c < k; c += nt) {
+            double *pc = X + (size_t)c * ldt;
+            double a = pc[t], b = pc[r];
+            pc[t] = b; pc[r] = a;
+        }
+    }
+    __syncthreads();
+    if (tid == 0) s_pv = ct[t];
+    __syncthreads();
+    const double ipv = 1.0 / s_pv;
+    for (int i = tid; i < k; i += nt) colt[i] = ct[i];
+    for (int c = tid; c < k; c += nt) rowt[c] = (c == t) ? ipv : X[(size_t)c * ldt + t] * ipv;
+}
+
+/* Gauss-Jordan step t, part 2 (grid): in-place elimination */
+__global__ void k_gj_update(Ctrl *ctrl, int t, double *__restrict__ X, int ldt,
+                            const double *__restrict__ rowt, const double *__restrict__ colt)
+{
+    if (ctrl->sing) return;
+    const int k = ctrl->k;
+    const int i = blockIdx.x * UPD_TB + threadIdx.x;
+    const int c0 = blockIdx.y * UPD_TC;
+    if (c0 >= k) return;
+    __shared__ double rs[UPD_TC];
+    const int cn = min(UPD_TC, k - c0);
+    if ((int)threadIdx.x < cn) rs[threadIdx.x] = rowt[c0 + threadIdx.x];
+    __syncthreads();
+    if (i >= k) return;
+    const double f = colt[i];
+    double *col = X + (size_t)c0 * ldt + i;
+    for (int c = 0; c < cn; c++) {
+        const int cc = c0 + c;
+        double *e = col + (size_t)c * ldt;
+        if (i == t) *e = rs[c];
+        else if (cc == t) *e = -f * rs[c];
+        else *e -= f * rs[c];
+    }
+}
+
+/* undo the row pivoting (column swaps in reverse order) and negate: T = -inv(M).
+   One block; swaps are sequential in t, parallel along the column. */
+__global__ void k_gj_finish(Ctrl *ctrl, double *__restrict__ X, int ldt, const int *__restrict__ piv)
+{
+    if (ctrl->sing) return;
+    const int k = ctrl->k;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int t = k - 1; t >= 0; t--) {
+        int r = piv[t];
+        if (r != t) {
+            double *a = X + (size_t)t * ldt, *b = X + (size_t)r * ldt;
+            for (int i = tid; i < k; i += nt) { double x = a[i]; a[i] = b[i]; b[i] = x; }
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void k_negate(Ctrl *ctrl, double *__restrict__ X, int ldt)
+{
+    if (ctrl->sing) return;
+    const int k = ctrl->k;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = blockIdx.y;
+    if (i < k && c < k) X[(size_t)c * ldt + i] = -X[(size_t)c * ldt + i];
+}
+
+/* whole inversion in one block / shared memory for small kernels (k <= 64):
+   B&B node LPs refactorise at every node, launch count matters there */
+#define GJ_SMALL 64
+__global__ void k_gj_small(Ctrl *ctrl, double *__restrict__ X, int ldt)
+{
+    if (ctrl->sing) return;
+    const int k = ctrl->k;
+    if (k == 0 || k > GJ_SMALL) return;
+    extern __shared__ double sm[];          /* k*k matrix + 2k + perm */
+    double *M = sm;                          /* M[i + c*k] */
+    double *rowt = sm + GJ_SMALL * GJ_SMALL, *colt = rowt + GJ_SMALL;
+    __shared__ int perm[GJ_SMALL];
+    __shared__ int s_r;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int e = tid; e < k * k; e += nt) M[e] = X[(size_t)(e / k) * ldt + (e % k)];
+    __syncthreads();
+    for (int t = 0; t < k; t++) {
+        if (tid == 0) {
+            int r = -1; double best = -1.0;
+            for (int i = t; i < k; i++) { double a = fabs(M[i + t * k]); if (a > best) { best = a; r = i; } }
+            if (!(best > 1e-13 * fmax(ctrl->max_a, 1e-300))) { ctrl->sing = 1; r = -1; }
+            s_r = r; perm[t] = r;
+        }
+        __syncthreads();
+        const int r = s_r;
+        if (r < 0) return;
+        if (r != t)
+            for (int c = tid; c < k; c += nt) { double a = M[t + c * k]; M[t + c * k] = M[r + c * k]; M[r + c * k] = a; }
+        __syncthreads();
+        const double ipv = 1.0 / M[t + t * k];
+        __syncthreads();
+        for (int i = tid; i < k; i += nt) colt[i] = M[i + t * k];
+        for (int c = tid; c < k; c += nt) rowt[c] = (c == t) ? ipv : M[t + c * k] * ipv;
+        __syncthreads();
+        for (int e = tid; e < k * k; e += nt) {
+            int i = e % k, c = e / k;
+            if (i == t) M[e] = rowt[c];
+            else if (c == t) M[e] = -colt[i] * rowt[c];
+            else M[e] -= colt[i] * rowt[c];
+        }
+        __syncthreads();
+    }
+    for (int t = k - 1; t >= 0; t--) {
+        int r = perm[t];
+        if (r != t)
+            for (int i = tid; i < k; i += nt) { double a = M[i + t * k]; M[i + t * k] = M[i + r * k]; M[i + r * k] = a; }
+        __syncthreads();
+    }
+    for (int e = tid; e < k * k; e += nt) X[(size_t)(e / k) * ldt + (e % k)] = -M[e];
+}
+
+/* ------------------------------------------------------------------ */
+/* per-iteration scalar logic and vector updates                      */
+/* ------------------------------------------------------------------ */
+
+/* scatter h = -N[q] (lib/glpspx01.js:702-719) into a zeroed dense vector */
+__global__ void k_col_rhs(Ctrl *ctrl, int m, const int *__restrict__ a_ptr,
+                          const int *__restrict__ a_ind, const double *__restrict__ a_val,
+                          const int *__restrict__ head, double *__restrict__ h)
+{
+    if (ctrl->status != ST_OK) return;
+    const int q = ctrl->q;
+    if (q < 0) return;
+    const int k = head[m + q];
+    if (k < m) { if (blockIdx.x == 0 && threadIdx.x == 0) h[k] = -1.0; return; }
+    for (int ptr = a_ptr[k - m] + blockIdx.x * blockDim.x + threadIdx.x; ptr < a_ptr[k - m + 1];
+         ptr += gridDim.x * blockDim.x)
+        h[a_ind[ptr]] = a_val[ptr];
+}
+
+/* primal, after eval_tcol: |tcol|_inf, the recomputed reduced cost d2
+   (reeval_cost, lib/glpspx01.js:1133-1152), the d1/d2 test (:1901-1919), the
+   PSE scalars gamma_q, delta_q and the masked vector v that update_gamma
+   solves with (:1208-1218) */
+__global__ void k_primal_prep(Ctrl *ctrl, int m, const int *__restrict__ head,
+                              const double *__restrict__ coef, const double *__restrict__ tcol,
+                              const signed char *__restrict__ refsp, double *__restrict__ cbar,
+                              double *__restrict__ v, double tol_piv, int cbar_fresh, int rigorous,
+                              int pse, Key *scratch)
+{
+    if (ctrl->status != ST_OK) return;
+    const int q = ctrl->q;
+    Key none = {0.0, 0.0, 0.0, 0, 0};
+    Key acc = none;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
+        double t = tcol[i];
+        int k = head[i];
+        acc.a += coef[k] * t;
+        acc.c = fmax(acc.c, fabs(t));
+        if (pse) {
+            double vv = refsp[k] ? t : 0.0;
+            v[i] = vv;
+            acc.b += vv * vv;
+        }
+    }
+    grid_reduce(acc, none, scratch, &ctrl->ticket[2], CombSum2(), [=](const Key &r) {
+        const int kq = head[m + q];
+        double big = r.c;
+        ctrl->tcol_max = big;
+        ctrl->eps = tol_piv * (1.0 + 0.01 * big);
+        double d1 = cbar[q], d2 = coef[kq] + r.a;
+        ctrl->d2 = d2;
+        double dq = (refsp[kq] ? 1.0 : 0.0);
+        ctrl->delta_q = dq;
+        ctrl->gamma_q = dq + r.b;
+        if (fabs(d1 - d2) > 1e-5 * (1.0 + fabs(d2)) ||
+            !((d1 < 0.0 && d2 < 0.0) || (d1 > 0.0 && d2 > 0.0))) {
+            if (!cbar_fresh || !rigorous) { ctrl->status = ST_D1D2; return; }
+        }
+        if (d1 > 0.0) d1 = (d2 > 0.0 ? d2 : +DBL_EPSILON);
+        else d1 = (d2 < 0.0 ? d2 : -DBL_EPSILON);
+        cbar[q] = d1;
+        ctrl->d1 = d1;
+    });
+}
+
+/* primal, after eval_trow: pivot agreement test (lib/glpspx01.js:1985-2006)
+   and the scalars of update_cbar (:1154-1176).  One thread. */
+__global__ void k_primal_piv(Ctrl *ctrl, int m, const int *__restrict__ head,
+                             double *__restrict__ trow, double *__restrict__ cbar,
+                             double *__restrict__ coef, const double *__restrict__ tcol,
+                             int binv_fresh, int rigorous)
+{
+    if (ctrl->status != ST_OK) return;
+    const int p = ctrl->p, q = ctrl->q;
+    if (p < 0) return;
+    double piv1 = tcol[p], piv2 = trow[q];
+    ctrl->piv1 = piv1; ctrl->piv2 = piv2;
+    if (fabs(piv1 - piv2) > 1e-8 * (1.0 + fabs(piv1)) ||
+        !((piv1 > 0.0 && piv2 > 0.0) || (piv1 < 0.0 && piv2 < 0.0))) {
+        if (!binv_fresh || !rigorous) { ctrl->status = ST_PIV12; return; }
+        trow[q] = piv1;
+        piv2 = piv1;
+    }
+    ctrl->new_dq = cbar[q] / piv2;
+}
+
+/* primal: update_bbar (:1100-1131), update_cbar (:1154-1176), the phase-1
+   cost fix (:2016-2020) and update_gamma's vector part (:1223-1254) */
+__global__ void k_primal_update(Ctrl *ctrl, int m, int n, const int *__restrict__ head,
+                                const signed char *__restrict__ stat,
+                                const signed char *__restrict__ type, const double *__restrict__ lb,
+                                const double *__restrict__ ub, double *__restrict__ coef,
+                                double *__restrict__ bbar, double *__restrict__ cbar,
+                                double *__restrict__ gamma, const signed char *__restrict__ refsp,
+                                const double *__restrict__ tcol, const double *__restrict__ trow,
+                                const double *__restrict__ svec, int do_gamma)
+{
+    if (ctrl->status != ST_OK) return;
+    const int p = ctrl->p, q = ctrl->q;
+    const double teta = ctrl->teta;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < m) {
+        if (t == p) bbar[t] = get_xN(stat, head, lb, ub, m, q) + teta;
+        else if (teta != 0.0) {
+            double tc = tcol[t];
+            if (tc != 0.0) bbar[t] += tc * teta;
+        }
+    }
+    if (p < 0 || t >= n) return;
+    const double new_dq = ctrl->new_dq;
+    const double pivot = trow[q];
+    const int kp = head[p];
+    if (t == q) {
+        double c = new_dq;
+        if (ctrl->phase == 1) { c -= coef[kp]; coef[kp] = 0.0; }
+        cbar[q] = c;
+        if (do_gamma) {
+            double g = 1.0;
+            if (type[kp] != GLP_FX) {
+                g = ctrl->gamma_q / (pivot * pivot);
+                if (g < DBL_EPSILON) g = DBL_EPSILON;
+            }
+            gamma[q] = g;
+        }
+    } else {
+        double tr = trow[t];
+        if (tr != 0.0) {
+            cbar[t] -= tr * new_dq;
+            if (do_gamma) {
+                double tt = tr / pivot;
+                int k = head[m + t];
+                double t1 = gamma[t] + tt * tt * ctrl->gamma_q + 2.0 * tt * svec[t];
+                double t2 = (refsp[k] ? 1.0 : 0.0) + ctrl->delta_q * tt * tt;
+                double g = (t1 >= t2 ? t1 : t2);
+                if (g < DBL_EPSILON) g = DBL_EPSILON;
+                gamma[t] = g;
+            }
+        }
+    }
+}
+
+/* dual, after eval_trow: |trow|_inf -> eps of sort_trow (lib/glpspx02.js:754-791) */
+__global__ void k_dual_rowmax(Ctrl *ctrl, double tol)
+{
+    if (ctrl->status != ST_OK) return;
+    double big = *((volatile double *)&ctrl->big);
+    ctrl->trow_max = big;
+    ctrl->eps = tol * (1.0 + 0.01 * big);
+    ctrl->big = 0.0;
+}
+
+/* dual, after eval_tcol: pivot agreement test (lib/glpspx02.js:1913-1933),
+   objective tracking (:1936-1938), PSE scalars gamma_p, eta_p (:1103-1115) */
+__global__ void k_dual_prep(Ctrl *ctrl, int m, int n, const int *__restrict__ head,
+                            const signed char *__restrict__ refsp, const double *__restrict__ trow,
+                            double *__restrict__ tcol, const double *__restrict__ cbar,
+                            const signed char *__restrict__ stat, double zeta, int binv_fresh,
+                            int rigorous, int pse, Key *scratch)
+{
+    if (ctrl->status != ST_OK) return;
+    const int p = ctrl->p, q = ctrl->q;
+    Key none = {0.0, 0.0, 0.0, 0, 0};
+    Key acc = none;
+    if (pse) {
+        for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+            double t = trow[j];
+            if (t != 0.0 && refsp[head[m + j]]) acc.a += t * t;
+        }
+    }
+    grid_reduce(acc, none, scratch, &ctrl->ticket[2], CombSum2(), [=](const Key &r) {
+        double piv1 = tcol[p], piv2 = trow[q];
+        ctrl->piv1 = piv1; ctrl->piv2 = piv2;
+        if (fabs(piv1 - piv2) > 1e-8 * (1.0 + fabs(piv1)) ||
+            !((piv1 > 0.0 && piv2 > 0.0) || (piv1 < 0.0 && piv2 < 0.0))) {
+            if (!binv_fresh || !rigorous) { ctrl->status = ST_PIV12; return; }
+            tcol[p] = piv2;
+            piv1 = piv2;
+        }
+        double eta = (refsp[head[p]] ? 1.0 : 0.0);
+        ctrl->delta_q = eta;              /* eta_p   */
+        ctrl->gamma_q = eta + r.a;        /* gamma_p */
+        ctrl->teta = ctrl->delta / piv1;
+        if (ctrl->phase == 2) ctrl->obj += (cbar[q] / zeta) * (ctrl->delta / piv1);
+    });
+}
+
+/* dual: update_bbar (:1042-1073), update_cbar (:1020-1040), update_gamma's
+   vector part (:1137-1187) */
+__global__ void k_dual_update(Ctrl *ctrl, int m, int n, const int *__restrict__ head,
+                              const signed char *__restrict__ stat,
+                              const signed char *__restrict__ type, const double *__restrict__ lb,
+                              const double *__restrict__ ub, double *__restrict__ bbar,
+                              double *__restrict__ cbar, double *__restrict__ gamma,
+                              signed char *__restrict__ refsp, const double *__restrict__ tcol,
+                              const double *__restrict__ trow, const double *__restrict__ u,
+                              int do_gamma)
+{
+    if (ctrl->status != ST_OK) return;
+    const int p = ctrl->p, q = ctrl->q;
+    const double teta = ctrl->teta, new_dq = ctrl->new_dq;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int kp = head[p], kq = head[m + q];
+    const double pivot = tcol[p];
+    if (t < n) {
+        if (t == q) cbar[q] = new_dq;
+        else if (new_dq != 0.0) {
+            double tr = trow[t];
+            if (tr != 0.0) cbar[t] -= tr * new_dq;
+        }
+    }
+    if (t < m) {
+        const bool drop = (type[kp] == GLP_FX && refsp[kp]);
+        if (t == p) {
+            bbar[p] = get_xN(stat, head, lb, ub, m, q) + teta;
+            if (do_gamma) {
+                double g = 1.0;
+                if (type[kq] != GLP_FR) {
+                    g = ctrl->gamma_q / (pivot * pivot);
+                    if (g < DBL_EPSILON) g = DBL_EPSILON;
+                    if (drop) {
+                        double tt = 1.0 / pivot;
+                        g -= tt * tt;
+                        if (g < DBL_EPSILON) g = DBL_EPSILON;
+                    }
+                }
+                gamma[p] = g;
+            }
+        } else {
+            double tc = tcol[t];
+            if (tc != 0.0) {
+                if (teta != 0.0) bbar[t] += tc * teta;
+                int k = head[t];
+                if (do_gamma && type[k] != GLP_FR) {
+                    double tt = tc / pivot;
+                    double t1 = gamma[t] + tt * tt * ctrl->gamma_q + 2.0 * tt * u[t];
+                    double t2 = (refsp[k] ? 1.0 : 0.0) + ctrl->delta_q * tt * tt;
+                    double g = (t1 >= t2 ? t1 : t2);
+                    if (g < DBL_EPSILON) g = DBL_EPSILON;
+                    if (drop) {
+                        g -= tt * tt;
+                        if (g < DBL_EPSILON) g = DBL_EPSILON;
+                    }
+                    gamma[t] = g;
+                }
+            }
+        }
+    }
+}
+
+/* second half of the fixed-variable rule of dual update_gamma (:1171-1173):
+   runs after k_dual_update so that no thread still reads refsp[kp] */
+__global__ void k_dual_drop_refsp(Ctrl *ctrl, const int *__restrict__ head,
+                                  const signed char *__restrict__ type, signed char *__restrict__ refsp)
+{
+    if (ctrl->status != ST_OK) return;
+    int kp = head[ctrl->p];
+    if (type[kp] == GLP_FX && refsp[kp]) refsp[kp] = 0;
+}
+
+/* reset_refsp: lib/glpspx01.js:586-601 (primal, dual = 0) / lib/glpspx02.js:497-512 */
+__global__ void k_reset_refsp(int m, int n, const int *__restrict__ head,
+                              signed char *__restrict__ refsp, double *__restrict__ gamma, int dual)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < m + n) {
+        int k = head[t];
+        bool in = dual ? (t < m) : (t >= m);
+        refsp[k] = in ? 1 : 0;
+    }
+    if (dual ? (t < m) : (t < n)) gamma[t] = 1.0;
+}
+
+/* set_aux_obj (lib/glpspx01.js:1373-1414): phase-1 costs; ctrl->cnt = violations */
+__global__ void k_set_aux_obj(Ctrl *ctrl, int m, int n, const int *__restrict__ head,
+                              const signed char *__restrict__ type, const double *__restrict__ lb,
+                              const double *__restrict__ ub, const double *__restrict__ bbar,
+                              double *__restrict__ coef, double tol_bnd)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= m + n) return;
+    const int k = head[t];
+    double c = 0.0;
+    if (t < m) {
+        int tk = type[k];
+        double b = bbar[t];
+        if (tk == GLP_LO || tk == GLP_DB || tk == GLP_FX)
+            if (b < lb[k] - relax(tol_bnd, lb[k])) c = -1.0;
+        if (tk == GLP_UP || tk == GLP_DB || tk == GLP_FX)
+            if (b > ub[k] + relax(tol_bnd, ub[k])) c = +1.0;
+        if (c != 0.0) atomicAdd(&ctrl->cnt, 1);
+    }
+    coef[k] = c;
+}
+
+/* set_orig_obj (lib/glpspx01.js:1416-1427): coef = zeta * obj on structurals */
+__global__ void k_set_orig_obj(int m, int n, const double *__restrict__ obj,
+                               double *__restrict__ coef, double zeta)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= m + n) return;
+    coef[k] = (k < m) ? 0.0 : zeta * obj[1 + (k - m)];
+}
+
+/* primal check_stab (:1429-1481) and check_feas (:1483-1522): ctrl->flag |= 1 */
+__global__ void k_primal_check(Ctrl *ctrl, int m, int mode, int phase, const int *__restrict__ head,
+                               const signed char *__restrict__ type, const double *__restrict__ lb,
+                               const double *__restrict__ ub, const double *__restrict__ coef,
+                               const double *__restrict__ bbar, double tol_bnd)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const int k = head[i];
+    const double b = bbar[i], c = coef[k];
+    const int tk = type[k];
+    bool bad = false;
+    if (mode == 0) { /* check_stab */
+        if (phase == 1 && c < 0.0) bad = b > lb[k] + relax(tol_bnd, lb[k]);
+        else if (phase == 1 && c > 0.0) bad = b < ub[k] - relax(tol_bnd, ub[k]);
+        else {
+            if (tk == GLP_LO || tk == GLP_DB || tk == GLP_FX) bad = b < lb[k] - relax(tol_bnd, lb[k]);
+            if (!bad && (tk == GLP_UP || tk == GLP_DB || tk == GLP_FX))
+                bad = b > ub[k] + relax(tol_bnd, ub[k]);
+        }
+    } else { /* check_feas (phase 1) */
+        if (c < 0.0) bad = b < lb[k] - relax(tol_bnd, lb[k]);
+        else if (c > 0.0) bad = b > ub[k] + relax(tol_bnd, ub[k]);
+    }
+    if (bad) ctrl->flag = 1;
+}
+
+/* dual check_feas (lib/glpspx02.js:1296-1315, mode 1) and check_stab
+   (:1410-1422, mode 0) */
+__global__ void k_dual_check(Ctrl *ctrl, int m, int n, int mode, const int *__restrict__ head,
+                             const signed char *__restrict__ orig_type,
+                             const signed char *__restrict__ stat, const double *__restrict__ cbar,
+                             double tol_dj)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const double d = cbar[j];
+    bool bad = false;
+    if (mode == 1) {
+        int t = orig_type[head[m + j]];
+        if (d < -tol_dj) bad = (t == GLP_LO || t == GLP_FR);
+        if (d > +tol_dj) bad = bad || (t == GLP_UP || t == GLP_FR);
+    } else {
+        int s = stat[j];
+        if (d < -tol_dj) bad = (s == GLP_NL || s == GLP_NF);
+        if (d > +tol_dj) bad = bad || (s == GLP_NU || s == GLP_NF);
+    }
+    if (bad) ctrl->flag = 1;
+}
+
+/* dual set_aux_bnds (:1317-1359, aux = 1) / set_orig_bnds (:1361-1408, aux = 0) */
+__global__ void k_dual_set_bnds(int m, int n, int aux, const int *__restrict__ head,
+                                const int *__restrict__ bind,
+                                const signed char *__restrict__ orig_type,
+                                const double *__restrict__ orig_lb, const double *__restrict__ orig_ub,
+                                signed char *__restrict__ type, double *__restrict__ lb,
+                                double *__restrict__ ub, signed char *__restrict__ stat,
+                                const double *__restrict__ cbar)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= m + n) return;
+    int t;
+    double l, u;
+    if (aux) {
+        switch (orig_type[k]) {
+        case GLP_FR: t = GLP_DB; l = -1e3; u = +1e3; break;
+        case GLP_LO: t = GLP_DB; l = 0.0; u = +1.0; break;
+        case GLP_UP: t = GLP_DB; l = -1.0; u = 0.0; break;
+        default: t = GLP_FX; l = u = 0.0; break;
+        }
+    } else { t = orig_type[k]; l = orig_lb[k]; u = orig_ub[k]; }
+    type[k] = (signed char)t; lb[k] = l; ub[k] = u;
+    const int pos = bind[k];
+    if (pos < m) return;
+    const int j = pos - m;
+    const double d = cbar[j];
+    int s;
+    if (aux) s = (t == GLP_FX) ? GLP_NS : (d >= 0.0 ? GLP_NL : GLP_NU);
+    else {
+        switch (t) {
+        case GLP_FR: s = GLP_NF; break;
+        case GLP_LO: s = GLP_NL; break;
+        case GLP_UP: s = GLP_NU; break;
+        case GLP_DB:
+            if (d >= +DBL_EPSILON) s = GLP_NL;
+            else if (d <= -DBL_EPSILON) s = GLP_NU;
+            else s = (fabs(l) <= fabs(u)) ? GLP_NL : GLP_NU;
+            break;
+        default: s = GLP_NS;
+        }
+    }
+    stat[j] = (signed char)s;
+}
+
+/* eval_obj (lib/glpspx01.js:1524-1548): two-sum reduction over positions */
+__global__ void k_eval_obj(Ctrl *ctrl, int m, int n, const int *__restrict__ head,
+                           const double *__restrict__ obj, const double *__restrict__ bbar,
+                           const signed char *__restrict__ stat, const double *__restrict__ lb,
+                           const double *__restrict__ ub, Key *scratch)
+{
+    Key none = {0.0, 0.0, 0.0, 0, 0};
+    Key acc = none;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < m + n; t += gridDim.x * blockDim.x) {
+        int k = head[t];
+        if (k >= m) {
+            double x = (t < m) ? bbar[t] : get_xN(stat, head, lb, ub, m, t - m);
+            acc.a += obj[1 + (k - m)] * x;
+        }
+    }
+    grid_reduce(acc, none, scratch, &ctrl->ticket[3], CombSum2(),
+                [=](const Key &r) { ctrl->obj = obj[0] + r.a; });
+}
+
+__global__ void k_gather_cB(int m, const int *__restrict__ head, const double *__restrict__ coef,
+                            double *__restrict__ cB)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < m) cB[i] = coef[head[i]];
+}
+
+__global__ void k_axpy1(int m, double *__restrict__ x, const double *__restrict__ d)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < m) x[i] += d[i];
+}
+
+__global__ void k_unit(Ctrl *ctrl, int m, double *__restrict__ e)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < m) e[i] = (i == ctrl->p) ? 1.0 : 0.0;
+}
+
+__global__ void k_clear_ctrl(Ctrl *ctrl, int phase)
+{
+    ctrl->status = ST_OK; ctrl->flag = 0; ctrl->cnt = 0; ctrl->big = 0.0; ctrl->skip2 = 0;
+    ctrl->phase = phase;
+}
+
+#endif /* GLPB_KERNELS_CUH */

@@ -1,0 +1,1210 @@
+/* solver.cu -- host side of libglpb200: device-resident problem handle, basis
+ * solves, refactorisation, and the loop controllers that replay the control
+ * flow of spx_primal (lib/glpspx01.js:1684-2056) and spx_dual
+ * (lib/glpspx02.js:1592-1966) around the kernels in kernels.cuh.
+ *
+ * There is no CPU arithmetic on the solve path: the host only decides which
+ * kernels to enqueue next from the device's status word, exactly where the
+ * reference's loop branches.
+ */
+#include "kernels.cuh"
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+static thread_local char g_err[512] = "";
+
+void glpb_set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+}
+
+static double now_ms()
+{
+    using namespace std::chrono;
+    return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
+
+#define LAUNCH(P, kern, grid, block, smem, ...)                                \
+    do {                                                                       \
+        kern<<<(grid), (block), (smem), (P)->stream>>>(__VA_ARGS__);            \
+        (P)->n_launch++;                                                       \
+    } while (0)
+
+static inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
+
+/* lanes per sparse vector, by average length */
+static inline int pick_group(double avg) { return avg >= 48.0 ? 32 : (avg >= 12.0 ? 8 : 4); }
+
+#define GROUP_DISPATCH(G, CALL)                                                \
+    do {                                                                       \
+        if ((G) == 32) { constexpr int GG = 32; CALL; }                        \
+        else if ((G) == 8) { constexpr int GG = 8; CALL; }                     \
+        else { constexpr int GG = 4; CALL; }                                   \
+    } while (0)
+
+template <class T> static int dalloc(T **p, size_t count)
+{
+    cudaError_t e = cudaMalloc((void **)p, (count ? count : 1) * sizeof(T));
+    if (e != cudaSuccess) { glpb_set_error("cudaMalloc(%zu bytes): %s", count * sizeof(T), cudaGetErrorString(e)); return GLPB_ENOMEM; }
+    return 0;
+}
+
+template <class T> static int h2d(glpb_prob *P, T *dst, const T *src, size_t count)
+{
+    CK(cudaMemcpyAsync(dst, src, count * sizeof(T), cudaMemcpyHostToDevice, P->stream));
+    return 0;
+}
+
+static int sync_ctrl(glpb_prob *P)
+{
+    CK(cudaMemcpyAsync(P->h_ctrl, P->ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, P->stream));
+    CK(cudaStreamSynchronize(P->stream));
+    P->n_sync++;
+    return 0;
+}
+
+/* ------------------------------------------------------------------ */
+/* handle                                                             */
+/* ------------------------------------------------------------------ */
+
+extern "C" int glpb_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+extern "C" const char *glpb_last_error(void) { return g_err; }
+extern "C" const char *glpb_version(void) { return "glpb200 0.1 (sm_100a); GLPK 4.49 semantics"; }
+
+extern "C" void glpb_init_smcp(glpb_smcp *p)
+{
+    p->msg_lev = 3; p->meth = GLP_PRIMAL; p->pricing = GLP_PT_PSE; p->r_test = GLP_RT_HAR;
+    p->tol_bnd = 1e-7; p->tol_dj = 1e-7; p->tol_piv = 1e-10;
+    p->obj_ll = -DBL_MAX; p->obj_ul = +DBL_MAX;
+    p->it_lim = INT_MAX; p->tm_lim = INT_MAX; p->out_frq = 500; p->out_dly = 0; p->presolve = 0;
+}
+
+extern "C" void glpb_init_iocp(glpb_iocp *p)
+{
+    p->msg_lev = 3; p->br_tech = GLP_BR_DTH; p->bt_tech = GLP_BT_BLB;
+    p->tol_int = 1e-5; p->tol_obj = 1e-7; p->tm_lim = INT_MAX; p->out_frq = 5000;
+    p->out_dly = 10000; p->pp_tech = GLP_PP_ALL; p->mip_gap = 0.0; p->presolve = 0;
+    p->node_lim = -1;
+}
+
+extern "C" void glpb_destroy(glpb_prob *P)
+{
+    if (!P) return;
+    cudaSetDevice(P->device);
+    void *ptrs[] = {P->a_ptr, P->a_ind, P->at_ptr, P->at_ind, P->a_val, P->at_val, P->type,
+                    P->orig_type, P->stat, P->refsp, P->lb, P->ub, P->coef, P->orig_lb, P->orig_ub,
+                    P->obj, P->head, P->bind, P->bbar, P->cbar, P->gamma, P->tcol, P->trow, P->rho,
+                    P->svec, P->w1, P->w2, P->w3, P->w4, P->w5, P->yk, P->wk, P->T, P->partial,
+                    P->rslot, P->slot_pos, P->cslot, P->slot_row, P->gj_piv, P->gj_row, P->gj_col,
+                    P->scratch, P->ctrl};
+    for (void *p : ptrs) if (p) cudaFree(p);
+    if (P->h_ctrl) cudaFreeHost(P->h_ctrl);
+    if (P->stream) cudaStreamDestroy(P->stream);
+    delete P;
+}
+
+static int create_device(glpb_prob *P)
+{
+    const int m = P->m, n = P->n, nnz = P->nnz;
+    CK(cudaSetDevice(P->device));
+    CK(cudaStreamCreateWithFlags(&P->stream, cudaStreamNonBlocking));
+    int rc;
+#define DA(ptr, cnt) if ((rc = dalloc(&P->ptr, (size_t)(cnt))) != 0) return rc
+    DA(a_ptr, n + 1); DA(a_ind, nnz); DA(a_val, nnz);
+    DA(at_ptr, m + 1); DA(at_ind, nnz); DA(at_val, nnz);
+    DA(type, m + n); DA(orig_type, m + n); DA(stat, n); DA(refsp, m + n);
+    DA(lb, m + n); DA(ub, m + n); DA(coef, m + n); DA(orig_lb, m + n); DA(orig_ub, m + n);
+    DA(obj, n + 1); DA(head, m + n); DA(bind, m + n);
+    DA(bbar, m); DA(cbar, n); DA(gamma, std::max(m, n));
+    DA(tcol, m); DA(trow, n); DA(rho, m); DA(svec, n);
+    DA(w1, m); DA(w2, m); DA(w3, m); DA(w4, m); DA(w5, m);
+    P->ldt = (m + 7) & ~7;
+    DA(yk, P->ldt); DA(wk, P->ldt);
+    DA(T, (size_t)P->ldt * P->ldt);
+    P->partial_rows = cdiv(P->ldt, GEMV_TILE);
+    DA(partial, (size_t)P->partial_rows * P->ldt);
+    DA(rslot, m); DA(slot_pos, P->ldt); DA(cslot, m); DA(slot_row, P->ldt);
+    DA(gj_piv, P->ldt); DA(gj_row, P->ldt); DA(gj_col, P->ldt);
+    DA(scratch, 4096);
+    DA(ctrl, 1);
+#undef DA
+    CK(cudaMallocHost((void **)&P->h_ctrl, sizeof(Ctrl)));
+    CK(cudaMemsetAsync(P->ctrl, 0, sizeof(Ctrl), P->stream));
+    return 0;
+}
+
+/* scaled copies of A by columns and by rows; the row copy keeps columns in
+   ascending order, which is the row-list order after glp_sort_matrix */
+static int upload_matrix(glpb_prob *P)
+{
+    const int m = P->m, n = P->n, nnz = P->nnz;
+    std::vector<double> sval(nnz);
+    for (int j = 0; j < n; j++)
+        for (int t = P->h_aptr[j]; t < P->h_aptr[j + 1]; t++)
+            sval[t] = P->h_rii[P->h_aind[t]] * P->h_aval[t] * P->h_sjj[j];
+    P->h_atptr.assign(m + 1, 0);
+    for (int t = 0; t < nnz; t++) P->h_atptr[P->h_aind[t] + 1]++;
+    for (int i = 0; i < m; i++) P->h_atptr[i + 1] += P->h_atptr[i];
+    P->h_atind.assign(nnz, 0); P->h_atval.assign(nnz, 0.0);
+    std::vector<double> satval(nnz);
+    std::vector<int> fill(P->h_atptr.begin(), P->h_atptr.end() - 1);
+    for (int j = 0; j < n; j++)
+        for (int t = P->h_aptr[j]; t < P->h_aptr[j + 1]; t++) {
+            int pos = fill[P->h_aind[t]]++;
+            P->h_atind[pos] = j; P->h_atval[pos] = P->h_aval[t]; satval[pos] = sval[t];
+        }
+    int rc;
+    if ((rc = h2d(P, P->a_ptr, P->h_aptr.data(), n + 1))) return rc;
+    if ((rc = h2d(P, P->a_ind, P->h_aind.data(), nnz))) return rc;
+    if ((rc = h2d(P, P->a_val, sval.data(), nnz))) return rc;
+    if ((rc = h2d(P, P->at_ptr, P->h_atptr.data(), m + 1))) return rc;
+    if ((rc = h2d(P, P->at_ind, P->h_atind.data(), nnz))) return rc;
+    if ((rc = h2d(P, P->at_val, satval.data(), nnz))) return rc;
+    CK(cudaStreamSynchronize(P->stream));
+    return 0;
+}
+
+static int default_stat(int type, double lb, double ub, int stat)
+{
+    /* glp_set_row_bnds / glp_set_col_bnds status rule, lib/glpapi01.js:217-281 */
+    if (stat == GLP_BS) return stat;
+    switch (type) {
+    case GLP_FR: return GLP_NF;
+    case GLP_LO: return GLP_NL;
+    case GLP_UP: return GLP_NU;
+    case GLP_DB: return (stat == GLP_NL || stat == GLP_NU) ? stat : (fabs(lb) <= fabs(ub) ? GLP_NL : GLP_NU);
+    default: return GLP_NS;
+    }
+}
+
+extern "C" glpb_prob *glpb_create(int m, int n, int nnz, int dir, double c0, const int *type,
+                                  const double *lb, const double *ub, const double *coef,
+                                  const int *kind, const double *rii, const double *sjj,
+                                  const int *A_ptr, const int *A_ind, const double *A_val, int device)
+{
+    if (m < 1 || n < 1 || nnz < 0 || !type || !lb || !ub || !coef || !A_ptr || (nnz && (!A_ind || !A_val)) ||
+        !(dir == GLP_MIN || dir == GLP_MAX)) {
+        glpb_set_error("glpb_create: invalid argument");
+        return nullptr;
+    }
+    int ndev = glpb_device_count();
+    if (ndev < 1 || device < 0 || device >= ndev) {
+        glpb_set_error("glpb_create: no CUDA device %d (found %d); there is no CPU fallback", device, ndev);
+        return nullptr;
+    }
+    glpb_prob *P = new glpb_prob();
+    P->device = device; P->m = m; P->n = n; P->nnz = nnz; P->dir = dir; P->c0 = c0;
+    P->h_type.assign(type, type + m + n);
+    P->h_lb.assign(lb, lb + m + n); P->h_ub.assign(ub, ub + m + n);
+    P->h_coef.assign(coef, coef + n);
+    if (kind) P->h_kind.assign(kind, kind + n); else P->h_kind.assign(n, GLP_CV);
+    if (rii) P->h_rii.assign(rii, rii + m); else P->h_rii.assign(m, 1.0);
+    if (sjj) P->h_sjj.assign(sjj, sjj + n); else P->h_sjj.assign(n, 1.0);
+    P->h_aptr.assign(A_ptr, A_ptr + n + 1);
+    P->h_aind.assign(A_ind, A_ind + nnz);
+    P->h_aval.assign(A_val, A_val + nnz);
+    for (int t = 0; t < nnz; t++)
+        if (A_ind[t] < 0 || A_ind[t] >= m) { glpb_set_error("glpb_create: row index out of range"); delete P; return nullptr; }
+    /* new rows are basic, new columns non-basic (lib/glpapi01.js:118,166) */
+    P->h_stat.assign(m + n, GLP_BS);
+    for (int j = 0; j < n; j++) P->h_stat[m + j] = default_stat(type[m + j], lb[m + j], ub[m + j], GLP_NS);
+    for (int k = 0; k < m + n; k++) {
+        /* normalise unused bound fields like glp_set_*_bnds does */
+        switch (P->h_type[k]) {
+        case GLP_FR: P->h_lb[k] = P->h_ub[k] = 0.0; break;
+        case GLP_LO: P->h_ub[k] = 0.0; break;
+        case GLP_UP: P->h_lb[k] = 0.0; break;
+        case GLP_FX: P->h_ub[k] = P->h_lb[k]; break;
+        default: break;
+        }
+    }
+    P->h_head.assign(m, 0);
+    P->h_prim.assign(m + n, 0.0); P->h_dual.assign(m + n, 0.0); P->h_mipx.assign(m + n, 0.0);
+    P->trace = getenv("GLPB_TRACE") ? atoi(getenv("GLPB_TRACE")) : 0;
+    if (create_device(P) != 0 || upload_matrix(P) != 0) { glpb_destroy(P); return nullptr; }
+    return P;
+}
+
+extern "C" int glpb_set_bounds(glpb_prob *P, int count, const int *k, const int *type,
+                               const double *lb, const double *ub)
+{
+    if (!P || count < 0) return GLPB_EINVAL;
+    for (int t = 0; t < count; t++) {
+        int kk = k[t] - 1;
+        if (kk < 0 || kk >= P->m + P->n || type[t] < GLP_FR || type[t] > GLP_FX) return GLPB_EINVAL;
+        double l = lb[t], u = ub[t];
+        switch (type[t]) {
+        case GLP_FR: l = u = 0.0; break;
+        case GLP_LO: u = 0.0; break;
+        case GLP_UP: l = 0.0; break;
+        case GLP_FX: u = l; break;
+        default: break;
+        }
+        P->h_type[kk] = type[t]; P->h_lb[kk] = l; P->h_ub[kk] = u;
+        P->h_stat[kk] = default_stat(type[t], l, u, P->h_stat[kk]);
+    }
+    return 0;
+}
+
+extern "C" int glpb_set_basis(glpb_prob *P, const int *stat)
+{
+    if (!P || !stat) return GLPB_EINVAL;
+    for (int k = 0; k < P->m + P->n; k++) {
+        int s = stat[k];
+        if (s < GLP_BS || s > GLP_NS) return GLPB_EINVAL;
+        if (s != GLP_BS) { /* lib/glpapi05.js:9-17 */
+            switch (P->h_type[k]) {
+            case GLP_FR: s = GLP_NF; break;
+            case GLP_LO: s = GLP_NL; break;
+            case GLP_UP: s = GLP_NU; break;
+            case GLP_DB: if (s != GLP_NU) s = GLP_NL; break;
+            default: s = GLP_NS;
+            }
+        }
+        if ((P->h_stat[k] == GLP_BS) != (s == GLP_BS)) P->valid = 0;
+        P->h_stat[k] = s;
+    }
+    return 0;
+}
+
+extern "C" int glpb_std_basis(glpb_prob *P)
+{
+    if (!P) return GLPB_EINVAL;
+    std::vector<int> st(P->m + P->n, GLP_BS);
+    for (int j = 0; j < P->n; j++) {
+        int k = P->m + j;
+        st[k] = (P->h_type[k] == GLP_DB && fabs(P->h_lb[k]) > fabs(P->h_ub[k])) ? GLP_NU : GLP_NL;
+    }
+    return glpb_set_basis(P, st.data());
+}
+
+extern "C" int glpb_set_bfcp(glpb_prob *P, const glpb_bfcp *parm)
+{
+    if (!P) return GLPB_EINVAL;
+    if (!parm) { P->bfcp = {100, 0.10, 1e-6}; return 0; }
+    if (parm->nfs_max < 1 || parm->nfs_max > 32767) return GLPB_EINVAL;
+    P->bfcp = *parm;
+    return 0;
+}
+
+extern "C" int glpb_set_it_cnt(glpb_prob *P, int it_cnt)
+{
+    if (!P) return GLPB_EINVAL;
+    P->it_cnt = it_cnt;
+    return 0;
+}
+
+/* ------------------------------------------------------------------ */
+/* basis solves                                                       */
+/* ------------------------------------------------------------------ */
+
+struct Dev { /* launch geometry derived from the handle */
+    glpb_prob *P;
+    int m, n, gc, gr, k;
+    explicit Dev(glpb_prob *P_) : P(P_), m(P_->m), n(P_->n)
+    {
+        gc = pick_group((double)P->nnz / P->n);
+        gr = pick_group((double)P->nnz / P->m);
+        k = 0;
+    }
+};
+
+/* x = inv(B) h   (bfd_ftran, lib/glpbfd.js:148-157); h and x must differ */
+static void dev_ftran(Dev &D, const double *h, double *x)
+{
+    glpb_prob *P = D.P;
+    if (D.k > 0) {
+        int tl = cdiv(D.k, GEMV_TILE);
+        LAUNCH(P, k_gemvN_part, dim3(tl, tl), GEMV_TILE, 0, P->ctrl, P->T, P->ldt, h, P->slot_row, P->partial);
+        LAUNCH(P, k_gemvN_fin, cdiv(D.k, 256), 256, 0, P->ctrl, P->ldt, P->partial, P->yk);
+    }
+    GROUP_DISPATCH(D.gr, LAUNCH(P, k_ftran_tail<GG>, cdiv((long)D.m * GG, 256), 256, 0, P->ctrl, D.m,
+                                P->at_ptr, P->at_ind, P->at_val, P->head, P->bind, P->rslot, h, P->yk, x));
+}
+
+/* z = inv(B') c  (bfd_btran, lib/glpbfd.js:159-168); c and z must differ */
+static void dev_btran(Dev &D, const double *c, double *z)
+{
+    glpb_prob *P = D.P;
+    if (D.k > 0) {
+        GROUP_DISPATCH(D.gc, LAUNCH(P, k_btran_head<GG>, cdiv((long)D.k * GG, 256), 256, 0, P->ctrl, D.m,
+                                    P->a_ptr, P->a_ind, P->a_val, P->head, P->bind, P->slot_pos, c, P->wk));
+        LAUNCH(P, k_gemvT, cdiv((long)D.k * 32, 256), 256, 0, P->ctrl, P->T, P->ldt, P->wk, P->yk);
+    }
+    LAUNCH(P, k_btran_tail, cdiv(D.m, 256), 256, 0, P->ctrl, D.m, P->cslot, P->bind, c, P->yk, z);
+}
+
+/* refactorisation (invert_B -> bfd_factorize -> luf_factorize in the
+   reference, lib/glpspx01.js:177-181): rebuild T for the current basis header
+   by Gauss-Jordan with partial pivoting on the k x k structural kernel */
+static int dev_refactor(Dev &D)
+{
+    glpb_prob *P = D.P;
+    LAUNCH(P, k_build_slots, 1, 1024, 0, P->ctrl, D.m, P->head, P->bind, P->rslot, P->slot_pos, P->cslot, P->slot_row);
+    int rc = sync_ctrl(P);
+    if (rc) return rc;
+    D.k = P->h_ctrl->k;
+    if (P->h_ctrl->sing) return GLP_EBADB;
+    const int k = D.k;
+    P->n_refac++;
+    if (k > 0) {
+        LAUNCH(P, k_build_kernel_matrix, k, 128, 0, P->ctrl, D.m, P->T, P->ldt, P->a_ptr, P->a_ind,
+               P->a_val, P->head, P->slot_pos, P->cslot);
+        if (k <= GJ_SMALL) {
+            size_t smem = (size_t)(GJ_SMALL * GJ_SMALL + 2 * GJ_SMALL) * sizeof(double);
+            LAUNCH(P, k_gj_small, 1, 256, smem, P->ctrl, P->T, P->ldt);
+        } else {
+            dim3 grid(cdiv(k, UPD_TB), cdiv(k, UPD_TC));
+            for (int t = 0; t < k; t++) {
+                LAUNCH(P, k_gj_pivot, 1, 1024, 0, P->ctrl, t, P->T, P->ldt, P->gj_piv, P->gj_row, P->gj_col);
+                LAUNCH(P, k_gj_update, grid, UPD_TB, 0, P->ctrl, t, P->T, P->ldt, P->gj_row, P->gj_col);
+            }
+            LAUNCH(P, k_gj_finish, 1, 1024, 0, P->ctrl, P->T, P->ldt, P->gj_piv);
+            LAUNCH(P, k_negate, dim3(cdiv(k, 256), k), 256, 0, P->ctrl, P->T, P->ldt);
+        }
+        rc = sync_ctrl(P);
+        if (rc) return rc;
+        if (P->h_ctrl->sing) return GLP_ESING;
+    }
+    return 0;
+}
+
+/* upload the basis header in init_csa order (lib/glpspx01.js:107-129) */
+static int upload_basis(glpb_prob *P)
+{
+    const int m = P->m, n = P->n;
+    std::vector<int> head(m + n), bind(m + n);
+    std::vector<signed char> stat(n);
+    for (int i = 0; i < m; i++) head[i] = P->h_head[i] - 1;
+    int kk = 0;
+    for (int k = 0; k < m + n; k++)
+        if (P->h_stat[k] != GLP_BS) {
+            if (kk >= n) return GLP_EBADB;
+            head[m + kk] = k; stat[kk] = (signed char)P->h_stat[k]; kk++;
+        }
+    if (kk != n) return GLP_EBADB;
+    for (int t = 0; t < m + n; t++) bind[head[t]] = t;
+    int rc;
+    if ((rc = h2d(P, P->head, head.data(), m + n))) return rc;
+    if ((rc = h2d(P, P->bind, bind.data(), m + n))) return rc;
+    if ((rc = h2d(P, P->stat, stat.data(), n))) return rc;
+    CK(cudaStreamSynchronize(P->stream));
+    return 0;
+}
+
+/* glp_factorize, lib/glpapi12.js:5-100 */
+extern "C" int glpb_factorize(glpb_prob *P)
+{
+    if (!P) return GLPB_EINVAL;
+    CK(cudaSetDevice(P->device));
+    const int m = P->m, n = P->n;
+    P->valid = 0;
+    int j = 0;
+    for (int k = 0; k < m + n; k++)
+        if (P->h_stat[k] == GLP_BS) {
+            j++;
+            if (j > m) return GLP_EBADB;
+            P->h_head[j - 1] = k + 1;
+        }
+    if (j < m) return GLP_EBADB;
+    int rc = upload_basis(P);
+    if (rc) return rc;
+    Dev D(P);
+    rc = dev_refactor(D);
+    if (rc) return rc;
+    P->valid = 1;
+    return 0;
+}
+
+/* scaled working copies of bounds and costs (init_csa, lib/glpspx01.js:61-94) */
+static int upload_bounds(glpb_prob *P, bool dual)
+{
+    const int m = P->m, n = P->n;
+    std::vector<signed char> type(m + n);
+    std::vector<double> lb(m + n), ub(m + n), coef(m + n, 0.0), obj(n + 1);
+    for (int i = 0; i < m; i++) {
+        type[i] = (signed char)P->h_type[i];
+        lb[i] = P->h_lb[i] * P->h_rii[i]; ub[i] = P->h_ub[i] * P->h_rii[i];
+    }
+    double cmax = 0.0;
+    obj[0] = P->c0;
+    for (int j = 0; j < n; j++) {
+        type[m + j] = (signed char)P->h_type[m + j];
+        lb[m + j] = P->h_lb[m + j] / P->h_sjj[j]; ub[m + j] = P->h_ub[m + j] / P->h_sjj[j];
+        coef[m + j] = P->h_coef[j] * P->h_sjj[j];
+        obj[1 + j] = coef[m + j];
+        cmax = std::max(cmax, fabs(obj[1 + j]));
+    }
+    if (cmax == 0.0) cmax = 1.0;
+    P->zeta = (P->dir == GLP_MIN ? +1.0 : -1.0) / cmax;
+    if (fabs(P->zeta) < 1.0) P->zeta *= 1000.0;
+    if (dual) for (int j = 0; j < n; j++) coef[m + j] *= P->zeta; /* lib/glpspx02.js:148 */
+    int rc;
+    if ((rc = h2d(P, P->type, type.data(), m + n))) return rc;
+    if ((rc = h2d(P, P->lb, lb.data(), m + n))) return rc;
+    if ((rc = h2d(P, P->ub, ub.data(), m + n))) return rc;
+    if ((rc = h2d(P, P->orig_type, type.data(), m + n))) return rc;
+    if ((rc = h2d(P, P->orig_lb, lb.data(), m + n))) return rc;
+    if ((rc = h2d(P, P->orig_ub, ub.data(), m + n))) return rc;
+    if ((rc = h2d(P, P->coef, coef.data(), m + n))) return rc;
+    if ((rc = h2d(P, P->obj, obj.data(), n + 1))) return rc;
+    CK(cudaMemsetAsync(P->refsp, 0, m + n, P->stream));
+    CK(cudaStreamSynchronize(P->stream));
+    return 0;
+}
+
+/* store_sol, lib/glpspx01.js:1591-1681: bring head/stat/bbar/cbar back and
+   un-scale into the glp_prob fields the getters read */
+static int store_sol(glpb_prob *P, int p_stat, int d_stat, int ray, int it_cnt)
+{
+    const int m = P->m, n = P->n;
+    std::vector<int> head(m + n);
+    std::vector<signed char> stat(n);
+    std::vector<double> bbar(m), cbar(n);
+    CK(cudaMemcpyAsync(head.data(), P->head, (m + n) * sizeof(int), cudaMemcpyDeviceToHost, P->stream));
+    CK(cudaMemcpyAsync(stat.data(), P->stat, n, cudaMemcpyDeviceToHost, P->stream));
+    CK(cudaMemcpyAsync(bbar.data(), P->bbar, m * sizeof(double), cudaMemcpyDeviceToHost, P->stream));
+    CK(cudaMemcpyAsync(cbar.data(), P->cbar, n * sizeof(double), cudaMemcpyDeviceToHost, P->stream));
+    CK(cudaStreamSynchronize(P->stream));
+    P->n_sync++;
+    P->valid = 1;
+    P->pbs_stat = p_stat; P->dbs_stat = d_stat;
+    P->it_cnt = it_cnt;
+    P->some = ray;
+    auto nbval = [&](int k, int st) {
+        switch (st) {
+        case GLP_NL: return P->h_lb[k];
+        case GLP_NU: return P->h_ub[k];
+        case GLP_NF: return 0.0;
+        default: return P->h_lb[k];
+        }
+    };
+    for (int i = 0; i < m; i++) {
+        int k = head[i];
+        P->h_head[i] = k + 1;
+        P->h_stat[k] = GLP_BS;
+        P->h_prim[k] = (k < m) ? bbar[i] / P->h_rii[k] : bbar[i] * P->h_sjj[k - m];
+        P->h_dual[k] = 0.0;
+    }
+    for (int j = 0; j < n; j++) {
+        int k = head[m + j];
+        P->h_stat[k] = stat[j];
+        P->h_prim[k] = nbval(k, stat[j]);
+        P->h_dual[k] = (k < m) ? (cbar[j] * P->h_rii[k]) / P->zeta : (cbar[j] / P->h_sjj[k - m]) / P->zeta;
+    }
+    /* eval_obj, lib/glpspx01.js:1524-1548, in the reference's summation order */
+    double sum = P->c0;
+    for (int i = 0; i < m; i++) {
+        int k = head[i];
+        if (k >= m) sum += (P->h_coef[k - m] * P->h_sjj[k - m]) * bbar[i];
+    }
+    for (int j = 0; j < n; j++) {
+        int k = head[m + j];
+        if (k >= m) {
+            double xs;
+            switch (stat[j]) {
+            case GLP_NL: xs = P->h_lb[k] / P->h_sjj[k - m]; break;
+            case GLP_NU: xs = P->h_ub[k] / P->h_sjj[k - m]; break;
+            case GLP_NF: xs = 0.0; break;
+            default: xs = P->h_lb[k] / P->h_sjj[k - m];
+            }
+            sum += (P->h_coef[k - m] * P->h_sjj[k - m]) * xs;
+        }
+    }
+    P->obj_val = sum;
+    return 0;
+}
+
+static int spx_fail(glpb_prob *P, int it_cnt)
+{
+    P->pbs_stat = P->dbs_stat = GLP_UNDEF;
+    P->obj_val = 0.0;
+    P->it_cnt = it_cnt;
+    P->some = 0;
+    P->valid = 0;
+    return GLP_EFAIL;
+}
+
+/* ------------------------------------------------------------------ */
+/* shared pieces of both loops                                        */
+/* ------------------------------------------------------------------ */
+
+struct Loop : Dev {
+    const glpb_smcp &parm;
+    int phase = 0, binv_st = 2, bbar_st = 0, cbar_st = 0, rigorous = 0;
+    int it_cnt = 0, it_beg = 0, refct = 0, upd_cnt = 0;
+    double tm_beg = 0.0;
+    Loop(glpb_prob *P_, const glpb_smcp &parm_) : Dev(P_), parm(parm_) {}
+
+    int grid1(int len) const { return std::max(1, std::min(cdiv(len, 256), 1184)); }
+
+    void clear_ctrl() { LAUNCH(P, k_clear_ctrl, 1, 1, 0, P->ctrl, phase); }
+
+    /* eval_bbar, lib/glpspx01.js:473-512,560-563 */
+    void eval_bbar()
+    {
+        GROUP_DISPATCH(gr, LAUNCH(P, k_beta_rhs<GG>, cdiv((long)m * GG, 256), 256, 0, P->ctrl, m, n, P->at_ptr,
+                                  P->at_ind, P->at_val, P->head, P->bind, P->stat, P->lb, P->ub, P->w2));
+        dev_ftran(*this, P->w2, P->bbar);
+        GROUP_DISPATCH(gr, LAUNCH(P, k_resid_ftran<GG>, cdiv((long)m * GG, 256), 256, 0, P->ctrl, m, P->at_ptr,
+                                  P->at_ind, P->at_val, P->bind, P->w2, P->bbar, P->w1));
+        dev_ftran(*this, P->w1, P->w3);
+        LAUNCH(P, k_axpy1, cdiv(m, 256), 256, 0, m, P->bbar, P->w3);
+    }
+
+    /* eval_cbar, lib/glpspx01.js:514-584 */
+    void eval_cbar()
+    {
+        LAUNCH(P, k_gather_cB, cdiv(m, 256), 256, 0, m, P->head, P->coef, P->w2);
+        dev_btran(*this, P->w2, P->w3);
+        GROUP_DISPATCH(gc, LAUNCH(P, k_resid_btran<GG>, cdiv((long)m * GG, 256), 256, 0, P->ctrl, m, P->a_ptr,
+                                  P->a_ind, P->a_val, P->head, P->w2, P->w3, P->w1));
+        dev_btran(*this, P->w1, P->w4);
+        LAUNCH(P, k_axpy1, cdiv(m, 256), 256, 0, m, P->w3, P->w4);
+        GROUP_DISPATCH(gc, LAUNCH(P, k_cbar<GG>, cdiv((long)n * GG, 256), 256, 0, P->ctrl, m, n, P->a_ptr,
+                                  P->a_ind, P->a_val, P->head, P->coef, P->w3, P->cbar));
+    }
+
+    /* eval_tcol (+ refine_tcol), lib/glpspx01.js:690-771 */
+    void eval_tcol()
+    {
+        cudaMemsetAsync(P->w5, 0, (size_t)m * sizeof(double), P->stream);
+        LAUNCH(P, k_col_rhs, 4, 256, 0, P->ctrl, m, P->a_ptr, P->a_ind, P->a_val, P->head, P->w5);
+        dev_ftran(*this, P->w5, P->tcol);
+        if (rigorous) {
+            GROUP_DISPATCH(gr, LAUNCH(P, k_resid_ftran<GG>, cdiv((long)m * GG, 256), 256, 0, P->ctrl, m, P->at_ptr,
+                                      P->at_ind, P->at_val, P->bind, P->w5, P->tcol, P->w1));
+            dev_ftran(*this, P->w1, P->w4);
+            LAUNCH(P, k_axpy1, cdiv(m, 256), 256, 0, m, P->tcol, P->w4);
+        }
+    }
+
+    /* eval_rho (+ refine_rho), lib/glpspx01.js:1030-1056 */
+    void eval_rho()
+    {
+        LAUNCH(P, k_rho, cdiv(m, 128), 128, 0, P->ctrl, m, P->T, P->ldt, P->at_ptr, P->at_ind, P->at_val,
+               P->head, P->bind, P->rslot, P->cslot, P->rho);
+        if (rigorous) {
+            LAUNCH(P, k_unit, cdiv(m, 256), 256, 0, P->ctrl, m, P->w2);
+            GROUP_DISPATCH(gc, LAUNCH(P, k_resid_btran<GG>, cdiv((long)m * GG, 256), 256, 0, P->ctrl, m, P->a_ptr,
+                                      P->a_ind, P->a_val, P->head, P->w2, P->rho, P->w1));
+            dev_btran(*this, P->w1, P->w4);
+            LAUNCH(P, k_axpy1, cdiv(m, 256), 256, 0, m, P->rho, P->w4);
+        }
+    }
+
+    void update_basis(int dual)
+    {
+        if (k > 0) {
+            dim3 grid(cdiv(k, UPD_TB), cdiv(k, UPD_TC));
+            LAUNCH(P, k_update_rank1, grid, UPD_TB, 0, P->ctrl, P->T, P->ldt, P->tcol, P->rho, P->slot_pos, P->slot_row);
+        }
+        LAUNCH(P, k_update_fix, 1, 1024, 0, P->ctrl, m, P->T, P->ldt, P->tcol, P->rho, P->rslot, P->slot_pos,
+               P->cslot, P->slot_row, P->head, P->bind, P->stat, P->type, dual);
+    }
+
+    int refactor()
+    {
+        int rc = dev_refactor(*this);
+        upd_cnt = 0;
+        return rc;
+    }
+
+    bool it_limit() const { return parm.it_lim < INT_MAX && it_cnt - it_beg >= parm.it_lim; }
+    bool tm_limit() const { return parm.tm_lim < INT_MAX && (now_ms() - tm_beg) >= parm.tm_lim; }
+
+    void trace_iter(const char *tag)
+    {
+        if (!P->trace) return;
+        const Ctrl &c = *P->h_ctrl;
+        fprintf(stderr, "[glpb %s] it %d ph %d st %d q %d p %d k %d teta %.12g delta %.12g piv1 %.6g piv2 %.6g rig %d\n",
+                tag, it_cnt, phase, c.status, c.q, c.p, c.k, c.teta, c.delta, c.piv1, c.piv2, rigorous);
+    }
+};
+
+/* ------------------------------------------------------------------ */
+/* primal loop controller: lib/glpspx01.js:1684-2056                  */
+/* ------------------------------------------------------------------ */
+
+struct Primal : Loop {
+    using Loop::Loop;
+
+    void chuzc(int set_status)
+    {
+        LAUNCH(P, k_chuzc_primal, grid1(n), 256, 0, P->ctrl, n, P->stat, P->cbar, P->gamma, parm.tol_dj,
+               set_status, P->scratch);
+    }
+
+    int set_aux_obj(int *cnt)
+    {
+        clear_ctrl();
+        LAUNCH(P, k_set_aux_obj, cdiv(m + n, 256), 256, 0, P->ctrl, m, n, P->head, P->type, P->lb, P->ub,
+               P->bbar, P->coef, 0.90 * parm.tol_bnd);
+        int rc = sync_ctrl(P);
+        *cnt = P->h_ctrl->cnt;
+        return rc;
+    }
+
+    void set_orig_obj()
+    {
+        LAUNCH(P, k_set_orig_obj, cdiv(m + n, 256), 256, 0, m, n, P->obj, P->coef, P->zeta);
+    }
+
+    int check(int mode, int *flag)
+    {
+        clear_ctrl();
+        LAUNCH(P, k_primal_check, cdiv(m, 256), 256, 0, P->ctrl, m, mode, phase, P->head, P->type, P->lb,
+               P->ub, P->coef, P->bbar, parm.tol_bnd);
+        int rc = sync_ctrl(P);
+        *flag = P->h_ctrl->flag;
+        return rc;
+    }
+
+    /* returns q != none after the run-out checks of lib/glpspx01.js:1813-1832 */
+    int stop_on_limit(int code)
+    {
+        int p_stat, d_stat;
+        clear_ctrl();
+        if (phase == 1) { p_stat = GLP_INFEAS; set_orig_obj(); eval_cbar(); }
+        else p_stat = GLP_FEAS;
+        chuzc(0);
+        int rc = sync_ctrl(P);
+        if (rc) return rc;
+        d_stat = (P->h_ctrl->q == P_NONE ? GLP_FEAS : GLP_INFEAS);
+        rc = store_sol(P, p_stat, d_stat, 0, it_cnt);
+        return rc ? rc : code;
+    }
+
+    int run()
+    {
+        int rc, flag, cnt;
+        const int pse = (parm.pricing == GLP_PT_PSE);
+        if ((rc = upload_bounds(P, false))) return rc;
+        if ((rc = upload_basis(P))) return rc;
+        {   /* T and its slot maps survive between calls; k is read back once */
+            if ((rc = sync_ctrl(P))) return rc;
+            k = P->h_ctrl->k;
+        }
+        P->valid = 0;
+        it_beg = it_cnt = P->it_cnt;
+        tm_beg = now_ms();
+        refct = 0;
+        LAUNCH(P, k_reset_refsp, cdiv(m + n, 256), 256, 0, m, n, P->head, P->refsp, P->gamma, 0);
+        cudaMemsetAsync(P->refsp, 0, m + n, P->stream);
+        for (;;) {
+            if (binv_st == 0) {
+                rc = refactor();
+                if (rc < 0) return rc;
+                if (rc != 0) return spx_fail(P, it_cnt);
+                binv_st = 1;
+                bbar_st = cbar_st = 0;
+            }
+            if (bbar_st == 0) {
+                clear_ctrl();
+                eval_bbar();
+                bbar_st = 1;
+                if (phase == 0) {
+                    if ((rc = set_aux_obj(&cnt))) return rc;
+                    if (cnt > 0) phase = 1;
+                    else { set_orig_obj(); phase = 2; }
+                    cbar_st = 0;
+                }
+                if ((rc = check(0, &flag))) return rc;
+                if (flag) { phase = 0; binv_st = 0; rigorous = 5; continue; }
+            }
+            if (phase == 1) {
+                if ((rc = check(1, &flag))) return rc;
+                if (!flag) { phase = 2; set_orig_obj(); cbar_st = 0; }
+            }
+            if (cbar_st == 0) { clear_ctrl(); eval_cbar(); cbar_st = 1; }
+            if (pse && refct == 0) {
+                LAUNCH(P, k_reset_refsp, cdiv(m + n, 256), 256, 0, m, n, P->head, P->refsp, P->gamma, 0);
+                refct = 1000;
+            }
+            if (it_limit() || tm_limit()) {
+                int code = it_limit() ? GLP_EITLIM : GLP_ETMLIM;
+                if (bbar_st != 1 || (phase == 2 && cbar_st != 1)) {
+                    if (bbar_st != 1) bbar_st = 0;
+                    if (phase == 2 && cbar_st != 1) cbar_st = 0;
+                    continue;
+                }
+                return stop_on_limit(code);
+            }
+            /* ---- one iteration, enqueued as a whole ---- */
+            const int do_gamma = pse && refct > 0;
+            clear_ctrl();
+            chuzc(1);
+            eval_tcol();
+            LAUNCH(P, k_primal_prep, grid1(m), 256, 0, P->ctrl, m, P->head, P->coef, P->tcol, P->refsp, P->cbar,
+                   P->w3, parm.tol_piv, cbar_st == 1, rigorous, do_gamma, P->scratch);
+            const double rtol = (parm.r_test == GLP_RT_STD ? 0.0 : 0.30 * parm.tol_bnd);
+            for (int pass = 1; pass <= 2; pass++)
+                LAUNCH(P, k_ratio_primal, grid1(m), 256, 0, P->ctrl, pass, m, P->type, P->lb, P->ub, P->coef,
+                       P->head, P->bbar, P->tcol, (const int *)nullptr, m, rtol, rigorous, P->scratch);
+            eval_rho();
+            if (do_gamma) dev_btran(*this, P->w3, P->w2);
+            GROUP_DISPATCH(gc, LAUNCH(P, k_trow<GG>, cdiv((long)n * GG, 256), 256, 0, P->ctrl, m, n, P->a_ptr,
+                                      P->a_ind, P->a_val, P->head, P->stat, P->rho,
+                                      do_gamma ? P->w2 : (const double *)nullptr, P->trow, P->svec, 0));
+            LAUNCH(P, k_primal_piv, 1, 1, 0, P->ctrl, m, P->head, P->trow, P->cbar, P->coef, P->tcol,
+                   binv_st == 1, rigorous);
+            LAUNCH(P, k_primal_update, cdiv(std::max(m, n), 256), 256, 0, P->ctrl, m, n, P->head, P->stat, P->type,
+                   P->lb, P->ub, P->coef, P->bbar, P->cbar, P->gamma, P->refsp, P->tcol, P->trow, P->svec, do_gamma);
+            update_basis(0);
+            if ((rc = sync_ctrl(P))) return rc;
+            trace_iter("primal");
+            const Ctrl &c = *P->h_ctrl;
+            k = c.k;
+            switch (c.status) {
+            case ST_OK:
+                bbar_st = 2;
+                if (c.p >= 0) {
+                    cbar_st = 2;
+                    if (do_gamma) refct--;
+                    binv_st = 2;
+                    upd_cnt++; P->n_update++;
+                    if (upd_cnt >= P->bfcp.nfs_max) binv_st = 0;
+                }
+                it_cnt++; P->n_iter++;
+                if (rigorous > 0) rigorous--;
+                break;
+            case ST_NONE1:
+                if (bbar_st != 1 || cbar_st != 1) {
+                    if (bbar_st != 1) bbar_st = 0;
+                    if (cbar_st != 1) cbar_st = 0;
+                    break;
+                }
+                {
+                    int p_stat, d_stat;
+                    if (phase == 1) {
+                        p_stat = GLP_NOFEAS;
+                        set_orig_obj();
+                        clear_ctrl();
+                        eval_cbar();
+                        chuzc(0);
+                        if ((rc = sync_ctrl(P))) return rc;
+                        d_stat = (P->h_ctrl->q == P_NONE ? GLP_FEAS : GLP_INFEAS);
+                    } else
+                        p_stat = d_stat = GLP_FEAS;
+                    rc = store_sol(P, p_stat, d_stat, 0, it_cnt);
+                    return rc;
+                }
+            case ST_D1D2:
+                if (cbar_st != 1) cbar_st = 0;
+                rigorous = 5;
+                break;
+            case ST_NONE2:
+                if (bbar_st != 1 || cbar_st != 1 || !rigorous) {
+                    if (bbar_st != 1) bbar_st = 0;
+                    if (cbar_st != 1) cbar_st = 0;
+                    rigorous = 1;
+                    break;
+                }
+                if (phase == 1) return spx_fail(P, it_cnt);
+                {
+                    std::vector<int> hq(1);
+                    CK(cudaMemcpy(hq.data(), P->head + m + c.q, sizeof(int), cudaMemcpyDeviceToHost));
+                    rc = store_sol(P, GLP_FEAS, GLP_NOFEAS, hq[0] + 1, it_cnt);
+                    return rc;
+                }
+            case ST_PIVSMALL:
+                rigorous = 5;
+                break;
+            case ST_PIV12:
+                if (binv_st != 1) binv_st = 0;
+                rigorous = 5;
+                break;
+            default:
+                glpb_set_error("primal: unexpected device status %d", c.status);
+                return GLPB_ESTATE;
+            }
+        }
+    }
+};
+
+/* ------------------------------------------------------------------ */
+/* dual loop controller: lib/glpspx02.js:1592-1966                    */
+/* ------------------------------------------------------------------ */
+
+struct Dual : Loop {
+    using Loop::Loop;
+
+    int check(int mode, double tol, int *flag)
+    {
+        clear_ctrl();
+        LAUNCH(P, k_dual_check, cdiv(n, 256), 256, 0, P->ctrl, m, n, mode, P->head, P->orig_type, P->stat,
+               P->cbar, tol);
+        int rc = sync_ctrl(P);
+        *flag = P->h_ctrl->flag;
+        return rc;
+    }
+
+    void set_bnds(int aux)
+    {
+        LAUNCH(P, k_dual_set_bnds, cdiv(m + n, 256), 256, 0, m, n, aux, P->head, P->bind, P->orig_type,
+               P->orig_lb, P->orig_ub, P->type, P->lb, P->ub, P->stat, P->cbar);
+    }
+
+    void eval_obj()
+    {
+        LAUNCH(P, k_eval_obj, grid1(m + n), 256, 0, P->ctrl, m, n, P->head, P->obj, P->bbar, P->stat, P->lb,
+               P->ub, P->scratch);
+    }
+
+    int stop_on_limit(int code)
+    {
+        int d_stat;
+        if (phase == 1) { d_stat = GLP_INFEAS; set_bnds(0); clear_ctrl(); eval_bbar(); }
+        else d_stat = GLP_FEAS;
+        int rc = store_sol(P, GLP_INFEAS, d_stat, 0, it_cnt);
+        return rc ? rc : code;
+    }
+
+    int run()
+    {
+        int rc, flag;
+        const int pse = (parm.pricing == GLP_PT_PSE);
+        double obj_track = 0.0;
+        if ((rc = upload_bounds(P, true))) return rc;
+        if ((rc = upload_basis(P))) return rc;
+        if ((rc = sync_ctrl(P))) return rc;
+        k = P->h_ctrl->k;
+        P->valid = 0;
+        it_beg = it_cnt = P->it_cnt;
+        tm_beg = now_ms();
+        refct = 0;
+        LAUNCH(P, k_reset_refsp, cdiv(m + n, 256), 256, 0, m, n, P->head, P->refsp, P->gamma, 1);
+        cudaMemsetAsync(P->refsp, 0, m + n, P->stream);
+        for (;;) {
+            if (binv_st == 0) {
+                rc = refactor();
+                if (rc < 0) return rc;
+                if (rc != 0) return spx_fail(P, it_cnt);
+                binv_st = 1;
+                bbar_st = cbar_st = 0;
+            }
+            if (cbar_st == 0) {
+                clear_ctrl();
+                eval_cbar();
+                cbar_st = 1;
+                if (phase == 0) {
+                    if ((rc = check(1, 0.90 * parm.tol_dj, &flag))) return rc;
+                    if (flag) { phase = 1; set_bnds(1); }
+                    else { phase = 2; set_bnds(0); }
+                    refct = 0;
+                    bbar_st = 0;
+                }
+                if ((rc = check(0, parm.tol_dj, &flag))) return rc;
+                if (flag) {
+                    if (parm.meth == GLP_DUALP) {
+                        rc = store_sol(P, GLP_UNDEF, GLP_UNDEF, 0, it_cnt);
+                        return rc ? rc : GLP_EFAIL;
+                    }
+                    phase = 0; binv_st = 0; rigorous = 5;
+                    continue;
+                }
+            }
+            if (phase == 1) {
+                if ((rc = check(1, parm.tol_dj, &flag))) return rc;
+                if (!flag) {
+                    phase = 2;
+                    if (cbar_st != 1) { clear_ctrl(); eval_cbar(); cbar_st = 1; }
+                    set_bnds(0);
+                    refct = 0;
+                    bbar_st = 0;
+                }
+            }
+            if (bbar_st == 0) {
+                clear_ctrl();
+                eval_bbar();
+                if (phase == 2) {
+                    eval_obj();
+                    if ((rc = sync_ctrl(P))) return rc;
+                    obj_track = P->h_ctrl->obj;
+                }
+                bbar_st = 1;
+            }
+            if (pse && refct == 0) {
+                LAUNCH(P, k_reset_refsp, cdiv(m + n, 256), 256, 0, m, n, P->head, P->refsp, P->gamma, 1);
+                refct = 1000;
+            }
+            /* objective cut-offs used by branch-and-bound, lib/glpspx02.js:1727-1760 */
+            if (phase == 2 && ((P->zeta < 0.0 && parm.obj_ll > -DBL_MAX && obj_track <= parm.obj_ll) ||
+                               (P->zeta > 0.0 && parm.obj_ul < +DBL_MAX && obj_track >= parm.obj_ul))) {
+                if (bbar_st != 1 || cbar_st != 1) {
+                    if (bbar_st != 1) bbar_st = 0;
+                    if (cbar_st != 1) cbar_st = 0;
+                    continue;
+                }
+                rc = store_sol(P, GLP_INFEAS, GLP_FEAS, 0, it_cnt);
+                return rc ? rc : (P->zeta < 0.0 ? GLP_EOBJLL : GLP_EOBJUL);
+            }
+            if (it_limit() || tm_limit()) {
+                int code = it_limit() ? GLP_EITLIM : GLP_ETMLIM;
+                if ((phase == 2 && bbar_st != 1) || cbar_st != 1) {
+                    if (phase == 2 && bbar_st != 1) bbar_st = 0;
+                    if (cbar_st != 1) cbar_st = 0;
+                    continue;
+                }
+                return stop_on_limit(code);
+            }
+            /* ---- one iteration ---- */
+            const int do_gamma = pse && refct > 0;
+            clear_ctrl();
+            LAUNCH(P, k_chuzr_dual, grid1(m), 256, 0, P->ctrl, m, P->type, P->lb, P->ub, P->head, P->bbar,
+                   P->gamma, parm.tol_bnd, 1, P->scratch);
+            eval_rho();
+            GROUP_DISPATCH(gc, LAUNCH(P, k_trow<GG>, cdiv((long)n * GG, 256), 256, 0, P->ctrl, m, n, P->a_ptr,
+                                      P->a_ind, P->a_val, P->head, P->stat, P->rho, (const double *)nullptr,
+                                      P->trow, P->svec, 1));
+            LAUNCH(P, k_dual_rowmax, 1, 1, 0, P->ctrl, parm.tol_bnd); /* sic: tol_bnd, lib/glpspx02.js:1851 */
+            const double rtol = (parm.r_test == GLP_RT_STD ? 0.0 : 0.30 * parm.tol_dj);
+            for (int pass = 1; pass <= 2; pass++)
+                LAUNCH(P, k_ratio_dual, grid1(n), 256, 0, P->ctrl, pass, P->stat, P->cbar, P->trow,
+                       (const int *)nullptr, n, rtol, rigorous, P->scratch);
+            eval_tcol();
+            LAUNCH(P, k_dual_prep, grid1(n), 256, 0, P->ctrl, m, n, P->head, P->refsp, P->trow, P->tcol, P->cbar,
+                   P->stat, P->zeta, binv_st == 1, rigorous, do_gamma, P->scratch);
+            if (do_gamma) {
+                GROUP_DISPATCH(gr, LAUNCH(P, k_dual_gamma_rhs<GG>, cdiv((long)m * GG, 256), 256, 0, P->ctrl, m,
+                                          P->at_ptr, P->at_ind, P->at_val, P->bind, P->refsp, P->trow, P->w3));
+                dev_ftran(*this, P->w3, P->w2);
+            }
+            LAUNCH(P, k_dual_update, cdiv(std::max(m, n), 256), 256, 0, P->ctrl, m, n, P->head, P->stat, P->type,
+                   P->lb, P->ub, P->bbar, P->cbar, P->gamma, P->refsp, P->tcol, P->trow, P->w2, do_gamma);
+            if (do_gamma) LAUNCH(P, k_dual_drop_refsp, 1, 1, 0, P->ctrl, P->head, P->type, P->refsp);
+            update_basis(1);
+            if ((rc = sync_ctrl(P))) return rc;
+            trace_iter("dual");
+            const Ctrl &c = *P->h_ctrl;
+            k = c.k;
+            switch (c.status) {
+            case ST_OK:
+                bbar_st = 2; cbar_st = 2;
+                obj_track = c.obj;
+                if (do_gamma) refct--;
+                binv_st = 2;
+                upd_cnt++; P->n_update++;
+                if (upd_cnt >= P->bfcp.nfs_max) binv_st = 0;
+                it_cnt++; P->n_iter++;
+                if (rigorous > 0) rigorous--;
+                break;
+            case ST_NONE1:
+                if (bbar_st != 1 || cbar_st != 1) {
+                    if (bbar_st != 1) bbar_st = 0;
+                    if (cbar_st != 1) cbar_st = 0;
+                    break;
+                }
+                {
+                    int p_stat, d_stat;
+                    if (phase == 1) {
+                        set_bnds(0);
+                        clear_ctrl();
+                        eval_bbar();
+                        p_stat = GLP_INFEAS; d_stat = GLP_NOFEAS;
+                    } else
+                        p_stat = d_stat = GLP_FEAS;
+                    return store_sol(P, p_stat, d_stat, 0, it_cnt);
+                }
+            case ST_NONE2:
+                if (bbar_st != 1 || cbar_st != 1 || !rigorous) {
+                    if (bbar_st != 1) bbar_st = 0;
+                    if (cbar_st != 1) cbar_st = 0;
+                    rigorous = 1;
+                    break;
+                }
+                if (phase == 1) return spx_fail(P, it_cnt);
+                {
+                    int hp;
+                    CK(cudaMemcpy(&hp, P->head + c.p, sizeof(int), cudaMemcpyDeviceToHost));
+                    return store_sol(P, GLP_NOFEAS, GLP_FEAS, hp + 1, it_cnt);
+                }
+            case ST_PIVSMALL:
+                rigorous = 5;
+                break;
+            case ST_PIV12:
+                if (binv_st != 1) binv_st = 0;
+                rigorous = 5;
+                break;
+            default:
+                glpb_set_error("dual: unexpected device status %d", c.status);
+                return GLPB_ESTATE;
+            }
+        }
+    }
+};
+
+/* ------------------------------------------------------------------ */
+/* drivers                                                            */
+/* ------------------------------------------------------------------ */
+
+/* trivial_lp, lib/glpapi06.js:149-258 (host: there is no matrix to stream) */
+static void trivial_lp(glpb_prob *P, const glpb_smcp &parm)
+{
+    const int m = P->m, n = P->n;
+    P->valid = 0;
+    P->pbs_stat = P->dbs_stat = GLP_FEAS;
+    P->obj_val = P->c0;
+    P->some = 0;
+    for (int i = 0; i < m; i++) {
+        P->h_stat[i] = GLP_BS; P->h_prim[i] = P->h_dual[i] = 0.0;
+        int t = P->h_type[i];
+        if ((t == GLP_LO || t == GLP_DB || t == GLP_FX) && P->h_lb[i] > +parm.tol_bnd) {
+            P->pbs_stat = GLP_NOFEAS;
+            if (P->some == 0 && parm.meth != GLP_PRIMAL) P->some = i + 1;
+        }
+        if ((t == GLP_UP || t == GLP_DB || t == GLP_FX) && P->h_ub[i] < -parm.tol_bnd) {
+            P->pbs_stat = GLP_NOFEAS;
+            if (P->some == 0 && parm.meth != GLP_PRIMAL) P->some = i + 1;
+        }
+    }
+    double zeta = 1.0;
+    for (int j = 0; j < n; j++) zeta = std::max(zeta, fabs(P->h_coef[j]));
+    zeta = (P->dir == GLP_MIN ? +1.0 : -1.0) / zeta;
+    for (int j = 0; j < n; j++) {
+        int k = m + j, t = P->h_type[k];
+        double c = P->h_coef[j];
+        bool lo;
+        if (t == GLP_FR) { P->h_stat[k] = GLP_NF; P->h_prim[k] = 0.0; }
+        else if (t == GLP_FX) { P->h_stat[k] = GLP_NS; P->h_prim[k] = P->h_lb[k]; }
+        else {
+            if (t == GLP_LO) lo = true;
+            else if (t == GLP_UP) lo = false;
+            else if (zeta * c > 0.0) lo = true;
+            else if (zeta * c < 0.0) lo = false;
+            else lo = fabs(P->h_lb[k]) <= fabs(P->h_ub[k]);
+            P->h_stat[k] = lo ? GLP_NL : GLP_NU;
+            P->h_prim[k] = lo ? P->h_lb[k] : P->h_ub[k];
+        }
+        P->h_dual[k] = c;
+        P->obj_val += c * P->h_prim[k];
+        if ((t == GLP_FR || t == GLP_LO) && zeta * c < -parm.tol_dj) {
+            P->dbs_stat = GLP_NOFEAS;
+            if (P->some == 0 && parm.meth == GLP_PRIMAL) P->some = k + 1;
+        }
+        if ((t == GLP_FR || t == GLP_UP) && zeta * c > +parm.tol_dj) {
+            P->dbs_stat = GLP_NOFEAS;
+            if (P->some == 0 && parm.meth == GLP_PRIMAL) P->some = k + 1;
+        }
+    }
+}
+
+static int check_smcp(const glpb_smcp &p)
+{
+    /* lib/glpapi06.js:271-300 */
+    if (p.msg_lev < 0 || p.msg_lev > 4) return GLPB_EINVAL;
+    if (!(p.meth == GLP_PRIMAL || p.meth == GLP_DUALP || p.meth == GLP_DUAL)) return GLPB_EINVAL;
+    if (!(p.pricing == GLP_PT_STD || p.pricing == GLP_PT_PSE)) return GLPB_EINVAL;
+    if (!(p.r_test == GLP_RT_STD || p.r_test == GLP_RT_HAR)) return GLPB_EINVAL;
+    if (!(0.0 < p.tol_bnd && p.tol_bnd < 1.0)) return GLPB_EINVAL;
+    if (!(0.0 < p.tol_dj && p.tol_dj < 1.0)) return GLPB_EINVAL;
+    if (!(0.0 < p.tol_piv && p.tol_piv < 1.0)) return GLPB_EINVAL;
+    if (p.it_lim < 0 || p.tm_lim < 0 || p.out_frq < 1 || p.out_dly < 0) return GLPB_EINVAL;
+    if (!(p.presolve == 0 || p.presolve == 1)) return GLPB_EINVAL;
+    return 0;
+}
+
+extern "C" int glpb_simplex(glpb_prob *P, const glpb_smcp *parm_)
+{
+    if (!P) return GLPB_EINVAL;
+    glpb_smcp parm;
+    if (parm_) parm = *parm_; else glpb_init_smcp(&parm);
+    int rc = check_smcp(parm);
+    if (rc) { glpb_set_error("glp_simplex: invalid control parameter"); return rc; }
+    if (parm.presolve) { glpb_set_error("glp_simplex: presolve stays in the host binding (SURVEY 8f)"); return GLPB_EINVAL; }
+    CK(cudaSetDevice(P->device));
+    const int m = P->m, n = P->n;
+    P->pbs_stat = P->dbs_stat = GLP_UNDEF;
+    P->obj_val = 0.0;
+    P->some = 0;
+    for (int k = 0; k < m + n; k++)
+        if (P->h_type[k] == GLP_DB && P->h_lb[k] >= P->h_ub[k]) return GLP_EBOUND;
+    if (P->nnz == 0) { trivial_lp(P, parm); return 0; }
+    /* solve_lp, lib/glpapi06.js:3-39 */
+    if (!P->valid) {
+        rc = glpb_factorize(P);
+        if (rc != 0) return rc;
+    }
+    double t0 = now_ms();
+    int ret;
+    if (parm.meth == GLP_PRIMAL) { Primal s(P, parm); ret = s.run(); }
+    else {
+        { Dual s(P, parm); ret = s.run(); }
+        if (parm.meth == GLP_DUALP && ret == GLP_EFAIL && P->valid) { Primal s(P, parm); ret = s.run(); }
+    }
+    P->last_solve_us = (now_ms() - t0) * 1000.0;
+    return ret;
+}
+
+extern "C" int glpb_get_status(glpb_prob *P)
+{
+    if (!P) return GLPB_EINVAL;
+    int status = P->pbs_stat;
+    if (status == GLP_FEAS) {
+        if (P->dbs_stat == GLP_FEAS) status = GLP_OPT;
+        else if (P->dbs_stat == GLP_NOFEAS) status = GLP_UNBND;
+    }
+    return status;
+}
+
+extern "C" int glpb_get_solution(glpb_prob *P, int *stat, double *prim, double *dual, int *head,
+                                 int *pbs_stat, int *dbs_stat, double *obj_val, int *it_cnt, int *some)
+{
+    if (!P) return GLPB_EINVAL;
+    const int m = P->m, n = P->n;
+    if (stat) memcpy(stat, P->h_stat.data(), (m + n) * sizeof(int));
+    if (prim) memcpy(prim, P->h_prim.data(), (m + n) * sizeof(double));
+    if (dual) memcpy(dual, P->h_dual.data(), (m + n) * sizeof(double));
+    if (head) memcpy(head, P->h_head.data(), m * sizeof(int));
+    if (pbs_stat) *pbs_stat = P->pbs_stat;
+    if (dbs_stat) *dbs_stat = P->dbs_stat;
+    if (obj_val) *obj_val = P->obj_val;
+    if (it_cnt) *it_cnt = P->it_cnt;
+    if (some) *some = P->some;
+    return 0;
+}
+
+extern "C" int glpb_get_counters(glpb_prob *P, long *out, int count)
+{
+    if (!P || !out) return GLPB_EINVAL;
+    long v[7] = {P->n_iter, P->n_refac, P->n_launch, P->n_sync, P->n_update,
+                 (long)(P->h_ctrl ? P->h_ctrl->k : 0), (long)P->last_solve_us};
+    for (int i = 0; i < count && i < 7; i++) out[i] = v[i];
+    return 0;
+}
+
+/* bfd_ftran / bfd_btran on the current factorisation (scaled space) */
+static int solve_host_vec(glpb_prob *P, double *x, bool tr)
+{
+    if (!P || !x) return GLPB_EINVAL;
+    if (!P->valid) return GLPB_ESTATE;
+    CK(cudaSetDevice(P->device));
+    const int m = P->m;
+    Dev D(P);
+    int rc = sync_ctrl(P);
+    if (rc) return rc;
+    D.k = P->h_ctrl->k;
+    if ((rc = h2d(P, P->w1, x, m))) return rc;
+    LAUNCH(P, k_clear_ctrl, 1, 1, 0, P->ctrl, 0);
+    if (tr) dev_btran(D, P->w1, P->w2); else dev_ftran(D, P->w1, P->w2);
+    CK(cudaMemcpyAsync(x, P->w2, m * sizeof(double), cudaMemcpyDeviceToHost, P->stream));
+    CK(cudaStreamSynchronize(P->stream));
+    return 0;
+}
+
+extern "C" int glpb_ftran(glpb_prob *P, double *x) { return solve_host_vec(P, x, false); }
+extern "C" int glpb_btran(glpb_prob *P, double *x) { return solve_host_vec(P, x, true); }

@@ -1,0 +1,872 @@
+"""Host-side mirror of the glpk.js API for the simplex path.
+
+Same names, argument meaning, 1-based indexing and error behaviour as the
+reference's JavaScript (``lib/glpapi01.js``, ``glpapi05.js``, ``glpapi06.js``,
+``glpapi09.js``, ``glpcpx.js``): invalid arguments raise (the reference's
+``xerror`` throws), solver conditions are integer return codes.  The problem
+object lives on the host exactly like the reference's ``glp_prob``; the solve
+calls marshal it once into a device-resident handle (``native.Problem``) and
+write the solution back into the same fields the reference's getters read.
+
+What is NOT here on purpose ("out of scope" / "next"): the LP/MIP
+presolver, scaling, MathProg, cut generators.  ``presolve: GLP_ON`` is accepted
+and solved without the presolver (the optimum is the same).
+"""
+import math
+
+import numpy as np
+
+from . import native
+from .native import *  # noqa: F401,F403  (GLP_* constants)
+
+GLP_PROB_MAGIC = 0xD7D9D6C2
+
+
+class GlpkError(Exception):
+    """What xerror() throws in the reference (lib/glpapi.js:26)."""
+
+
+def xerror(msg):
+    raise GlpkError(msg)
+
+
+class SMCP:
+    """lib/glpapi06.js:359-375, including the ``options[k] || default`` quirk:
+    falsy values (0) given to the constructor fall back to the default."""
+
+    _defaults = dict(msg_lev=GLP_MSG_ALL, meth=GLP_PRIMAL, pricing=GLP_PT_PSE, r_test=GLP_RT_HAR,
+                     tol_bnd=1e-7, tol_dj=1e-7, tol_piv=1e-10, obj_ll=-DBL_MAX, obj_ul=+DBL_MAX,
+                     it_lim=INT_MAX, tm_lim=INT_MAX, out_frq=500, out_dly=0, presolve=GLP_OFF)
+
+    def __init__(self, options=None):
+        options = options or {}
+        for k, v in self._defaults.items():
+            setattr(self, k, options.get(k) or v)
+
+
+class IOCP:
+    """lib/glpapi09.js:392-414 (fields of the B&B path only)."""
+
+    _defaults = dict(msg_lev=GLP_MSG_ALL, br_tech=GLP_BR_DTH, bt_tech=GLP_BT_BLB, tol_int=1e-5,
+                     tol_obj=1e-7, tm_lim=INT_MAX, out_frq=5000, out_dly=10000, cb_func=None,
+                     cb_info=None, cb_size=0, pp_tech=GLP_PP_ALL, mip_gap=0.0, mir_cuts=GLP_OFF,
+                     gmi_cuts=GLP_OFF, cov_cuts=GLP_OFF, clq_cuts=GLP_OFF, presolve=GLP_OFF,
+                     binarize=GLP_OFF, fp_heur=GLP_OFF)
+
+    def __init__(self, options=None):
+        options = options or {}
+        for k, v in self._defaults.items():
+            setattr(self, k, options.get(k) or v)
+
+
+class _Row:
+    __slots__ = ("i", "name", "type", "lb", "ub", "rii", "stat", "bind", "prim", "dual", "mipx", "elems")
+
+    def __init__(self, i):
+        self.i, self.name = i, None
+        self.type, self.lb, self.ub = GLP_FR, 0.0, 0.0
+        self.rii = 1.0
+        self.stat, self.bind = GLP_BS, 0
+        self.prim = self.dual = self.mipx = 0.0
+        self.elems = []  # [(j, val)] in list order
+
+
+class _Col:
+    __slots__ = ("j", "name", "kind", "type", "lb", "ub", "coef", "sjj", "stat", "bind", "prim",
+                 "dual", "mipx", "elems")
+
+    def __init__(self, j):
+        self.j, self.name, self.kind = j, None, GLP_CV
+        self.type, self.lb, self.ub, self.coef = GLP_FX, 0.0, 0.0, 0.0
+        self.sjj = 1.0
+        self.stat, self.bind = GLP_NS, 0
+        self.prim = self.dual = self.mipx = 0.0
+        self.elems = []  # [(i, val)] in list order
+
+
+class glp_prob:
+    def __init__(self):
+        self.magic = GLP_PROB_MAGIC
+        self.name = self.obj = None
+        self.dir, self.c0 = GLP_MIN, 0.0
+        self.m = self.n = self.nnz = 0
+        self.row, self.col = [None], [None]
+        self.valid = 0
+        self.head = [0]
+        self.pbs_stat = self.dbs_stat = GLP_UNDEF
+        self.obj_val = 0.0
+        self.it_cnt = self.some = 0
+        self.mip_stat, self.mip_obj = GLP_UNDEF, 0.0
+        self.bfcp = None
+        self._dev = None       # native.Problem
+        self._dirty = True     # matrix / costs changed since the handle was built
+
+
+def glp_create_prob():
+    return glp_prob()
+
+
+def _check(P, who):
+    if P is None or getattr(P, "magic", None) != GLP_PROB_MAGIC:
+        xerror("%s: P = %r; invalid problem object" % (who, P))
+
+
+def glp_set_prob_name(P, name):
+    P.name = name
+
+
+def glp_set_obj_name(P, name):
+    P.obj = name
+
+
+def glp_set_obj_dir(P, dir):
+    if dir not in (GLP_MIN, GLP_MAX):
+        xerror("glp_set_obj_dir: dir = %r; invalid direction flag" % (dir,))
+    P.dir = dir
+    P._dirty = True
+
+
+def glp_add_rows(P, nrs):
+    if nrs < 1:
+        xerror("glp_add_rows: nrs = %d; invalid number of rows" % nrs)
+    for i in range(P.m + 1, P.m + nrs + 1):
+        P.row.append(_Row(i))
+    P.head.extend([0] * nrs)
+    P.m += nrs
+    P.valid = 0
+    P._dirty = True
+    return P.m - nrs + 1
+
+
+def glp_add_cols(P, ncs):
+    if ncs < 1:
+        xerror("glp_add_cols: ncs = %d; invalid number of columns" % ncs)
+    for j in range(P.n + 1, P.n + ncs + 1):
+        P.col.append(_Col(j))
+    P.n += ncs
+    P._dirty = True
+    return P.n - ncs + 1
+
+
+def glp_set_row_name(P, i, name):
+    if not (1 <= i <= P.m):
+        xerror("glp_set_row_name: i = %d; row number out of range" % i)
+    P.row[i].name = name
+
+
+def glp_set_col_name(P, j, name):
+    if not (1 <= j <= P.n):
+        xerror("glp_set_col_name: j = %d; column number out of range" % j)
+    P.col[j].name = name
+
+
+def _set_bnds(x, who, idx, type, lb, ub):
+    # lib/glpapi01.js:217-281
+    x.type = type
+    if type == GLP_FR:
+        x.lb = x.ub = 0.0
+        if x.stat != GLP_BS:
+            x.stat = GLP_NF
+    elif type == GLP_LO:
+        x.lb, x.ub = lb, 0.0
+        if x.stat != GLP_BS:
+            x.stat = GLP_NL
+    elif type == GLP_UP:
+        x.lb, x.ub = 0.0, ub
+        if x.stat != GLP_BS:
+            x.stat = GLP_NU
+    elif type == GLP_DB:
+        x.lb, x.ub = lb, ub
+        if x.stat not in (GLP_BS, GLP_NL, GLP_NU):
+            x.stat = GLP_NL if abs(lb) <= abs(ub) else GLP_NU
+    elif type == GLP_FX:
+        x.lb = x.ub = lb
+        if x.stat != GLP_BS:
+            x.stat = GLP_NS
+    else:
+        xerror("%s: %d; type = %r; invalid type" % (who, idx, type))
+
+
+def glp_set_row_bnds(P, i, type, lb, ub):
+    if not (1 <= i <= P.m):
+        xerror("glp_set_row_bnds: i = %d; row number out of range" % i)
+    _set_bnds(P.row[i], "glp_set_row_bnds: i =", i, type, lb, ub)
+
+
+def glp_set_col_bnds(P, j, type, lb, ub):
+    if not (1 <= j <= P.n):
+        xerror("glp_set_col_bnds: j = %d; column number out of range" % j)
+    _set_bnds(P.col[j], "glp_set_col_bnds: j =", j, type, lb, ub)
+
+
+def glp_set_obj_coef(P, j, coef):
+    if not (0 <= j <= P.n):
+        xerror("glp_set_obj_coef: j = %d; column number out of range" % j)
+    if j == 0:
+        P.c0 = coef
+    else:
+        P.col[j].coef = coef
+    P._dirty = True
+
+
+def glp_set_mat_row(P, i, length, ind, val):
+    """ind/val are 1-based sequences (slot 0 ignored); new elements are
+    prepended to the row and column lists (lib/glpapi01.js:295-378)."""
+    if not (1 <= i <= P.m):
+        xerror("glp_set_mat_row: i = %d; row number out of range" % i)
+    if not (0 <= length <= P.n):
+        xerror("glp_set_mat_row: i = %d; len = %d; invalid row length" % (i, length))
+    row = P.row[i]
+    for (j, _) in row.elems:
+        col = P.col[j]
+        col.elems = [e for e in col.elems if e[0] != i]
+        P.nnz -= 1
+        if col.stat == GLP_BS:
+            P.valid = 0
+    row.elems = []
+    for k in range(1, length + 1):
+        j = ind[k]
+        if not (1 <= j <= P.n):
+            xerror("glp_set_mat_row: i = %d; ind[%d] = %d; column index out of range" % (i, k, j))
+        col = P.col[j]
+        if col.elems and col.elems[0][0] == i:
+            xerror("glp_set_mat_row: i = %d; ind[%d] = %d; duplicate column indices not allowed" % (i, k, j))
+        if val[k] == 0.0:
+            continue
+        row.elems.insert(0, (j, float(val[k])))
+        col.elems.insert(0, (i, float(val[k])))
+        P.nnz += 1
+        if col.stat == GLP_BS:
+            P.valid = 0
+    P._dirty = True
+
+
+def glp_set_mat_col(P, j, length, ind, val):
+    """lib/glpapi01.js:380-462"""
+    if not (1 <= j <= P.n):
+        xerror("glp_set_mat_col: j = %d; column number out of range" % j)
+    if not (0 <= length <= P.m):
+        xerror("glp_set_mat_col: j = %d; len = %d; invalid column length" % (j, length))
+    col = P.col[j]
+    for (i, _) in col.elems:
+        row = P.row[i]
+        row.elems = [e for e in row.elems if e[0] != j]
+        P.nnz -= 1
+    col.elems = []
+    for k in range(1, length + 1):
+        i = ind[k]
+        if not (1 <= i <= P.m):
+            xerror("glp_set_mat_col: j = %d; ind[%d] = %d; row index out of range" % (j, k, i))
+        row = P.row[i]
+        if row.elems and row.elems[0][0] == j:
+            xerror("glp_set_mat_col: j = %d; ind[%d] = %d; duplicate row indices not allowed" % (j, k, i))
+        if val[k] == 0.0:
+            continue
+        col.elems.insert(0, (i, float(val[k])))
+        row.elems.insert(0, (j, float(val[k])))
+        P.nnz += 1
+    if col.stat == GLP_BS:
+        P.valid = 0
+    P._dirty = True
+
+
+def glp_load_matrix(P, ne, ia, ja, ar):
+    """lib/glpapi01.js:464-560: replace the whole matrix by ne triplets (1-based)."""
+    for r in P.row[1:]:
+        r.elems = []
+    for c in P.col[1:]:
+        c.elems = []
+    P.nnz = 0
+    seen = set()
+    for k in range(1, ne + 1):
+        i, j = ia[k], ja[k]
+        if not (1 <= i <= P.m):
+            xerror("glp_load_matrix: ia[%d] = %d; row index out of range" % (k, i))
+        if not (1 <= j <= P.n):
+            xerror("glp_load_matrix: ja[%d] = %d; column index out of range" % (k, j))
+        if (i, j) in seen:
+            xerror("glp_load_matrix: ia[%d] = %d; ja[%d] = %d; duplicate indices not allowed" % (k, i, k, j))
+        seen.add((i, j))
+        if ar[k] == 0.0:
+            continue
+        P.row[i].elems.insert(0, (j, float(ar[k])))
+        P.col[j].elems.insert(0, (i, float(ar[k])))
+        P.nnz += 1
+    P.valid = 0
+    P._dirty = True
+
+
+def glp_sort_matrix(P):
+    """lib/glpapi01.js:620-649"""
+    _check(P, "glp_sort_matrix")
+    for r in P.row[1:]:
+        r.elems.sort(key=lambda e: e[0])
+    for c in P.col[1:]:
+        c.elems.sort(key=lambda e: e[0])
+    P._dirty = True
+
+
+def glp_set_col_kind(P, j, kind):
+    """lib/glpapi09.js:1-38"""
+    if not (1 <= j <= P.n):
+        xerror("glp_set_col_kind: j = %d; column number out of range" % j)
+    col = P.col[j]
+    if kind == GLP_CV:
+        col.kind = GLP_CV
+    elif kind == GLP_IV:
+        col.kind = GLP_IV
+    elif kind == GLP_BV:
+        col.kind = GLP_IV
+        if not (col.type == GLP_DB and col.lb == 0.0 and col.ub == 1.0):
+            glp_set_col_bnds(P, j, GLP_DB, 0.0, 1.0)
+    else:
+        xerror("glp_set_col_kind: j = %d; kind = %r; invalid column kind" % (j, kind))
+    P._dirty = True
+
+
+def glp_get_col_kind(P, j):
+    col = P.col[j]
+    if col.kind == GLP_IV and col.type == GLP_DB and col.lb == 0.0 and col.ub == 1.0:
+        return GLP_BV
+    return col.kind
+
+
+def _norm_stat(x, stat):
+    if stat != GLP_BS:
+        stat = {GLP_FR: GLP_NF, GLP_LO: GLP_NL, GLP_UP: GLP_NU,
+                GLP_DB: (GLP_NU if stat == GLP_NU else GLP_NL), GLP_FX: GLP_NS}[x.type]
+    return stat
+
+
+def glp_set_row_stat(P, i, stat):
+    """lib/glpapi05.js:1-23"""
+    if not (1 <= i <= P.m):
+        xerror("glp_set_row_stat: i = %d; row number out of range" % i)
+    if stat not in (GLP_BS, GLP_NL, GLP_NU, GLP_NF, GLP_NS):
+        xerror("glp_set_row_stat: i = %d; stat = %r; invalid status" % (i, stat))
+    row = P.row[i]
+    stat = _norm_stat(row, stat)
+    if (row.stat == GLP_BS) != (stat == GLP_BS):
+        P.valid = 0
+    row.stat = stat
+
+
+def glp_set_col_stat(P, j, stat):
+    """lib/glpapi05.js:25-47"""
+    if not (1 <= j <= P.n):
+        xerror("glp_set_col_stat: j = %d; column number out of range" % j)
+    if stat not in (GLP_BS, GLP_NL, GLP_NU, GLP_NF, GLP_NS):
+        xerror("glp_set_col_stat: j = %d; stat = %r; invalid status" % (j, stat))
+    col = P.col[j]
+    stat = _norm_stat(col, stat)
+    if (col.stat == GLP_BS) != (stat == GLP_BS):
+        P.valid = 0
+    col.stat = stat
+
+
+def glp_std_basis(P):
+    """lib/glpapi05.js:49-63"""
+    for i in range(1, P.m + 1):
+        glp_set_row_stat(P, i, GLP_BS)
+    for j in range(1, P.n + 1):
+        col = P.col[j]
+        if col.type == GLP_DB and abs(col.lb) > abs(col.ub):
+            glp_set_col_stat(P, j, GLP_NU)
+        else:
+            glp_set_col_stat(P, j, GLP_NL)
+
+
+# ---- getters (lib/glpapi02.js, lib/glpapi06.js:398-482, lib/glpapi09.js:441-459) ----
+def glp_get_num_rows(P): return P.m
+def glp_get_num_cols(P): return P.n
+def glp_get_num_nz(P): return P.nnz
+def glp_get_obj_dir(P): return P.dir
+def glp_get_prob_name(P): return P.name
+def glp_get_row_name(P, i): return P.row[i].name
+def glp_get_col_name(P, j): return P.col[j].name
+def glp_get_num_int(P): return sum(1 for c in P.col[1:] if c.kind == GLP_IV)
+def glp_get_num_bin(P): return sum(1 for c in P.col[1:] if c.kind == GLP_IV and c.type == GLP_DB and c.lb == 0.0 and c.ub == 1.0)
+def glp_get_prim_stat(P): return P.pbs_stat
+def glp_get_dual_stat(P): return P.dbs_stat
+def glp_get_obj_val(P): return P.obj_val
+def glp_mip_status(P): return P.mip_stat
+def glp_mip_obj_val(P): return P.mip_obj
+
+
+def glp_get_status(P):
+    """lib/glpapi06.js:398-427"""
+    status = P.pbs_stat
+    if status == GLP_FEAS:
+        if P.dbs_stat == GLP_FEAS:
+            status = GLP_OPT
+        elif P.dbs_stat == GLP_NOFEAS:
+            status = GLP_UNBND
+    return status
+
+
+def _row(P, i, who):
+    if not (1 <= i <= P.m):
+        xerror("%s: i = %d; row number out of range" % (who, i))
+    return P.row[i]
+
+
+def _col(P, j, who):
+    if not (1 <= j <= P.n):
+        xerror("%s: j = %d; column number out of range" % (who, j))
+    return P.col[j]
+
+
+def glp_get_row_stat(P, i): return _row(P, i, "glp_get_row_stat").stat
+def glp_get_row_prim(P, i): return _row(P, i, "glp_get_row_prim").prim
+def glp_get_row_dual(P, i): return _row(P, i, "glp_get_row_dual").dual
+def glp_get_col_stat(P, j): return _col(P, j, "glp_get_col_stat").stat
+def glp_get_col_prim(P, j): return _col(P, j, "glp_get_col_prim").prim
+def glp_get_col_dual(P, j): return _col(P, j, "glp_get_col_dual").dual
+def glp_mip_row_val(P, i): return _row(P, i, "glp_mip_row_val").mipx
+def glp_mip_col_val(P, j): return _col(P, j, "glp_mip_col_val").mipx
+
+
+def glp_get_unbnd_ray(P):
+    k = P.some
+    return 0 if k > P.m + P.n else k
+
+
+# ---- CPLEX LP format (lib/glpcpx.js:10-753), own recursive-descent reader ----
+_NAME_EXTRA = set("!\"#$%&()/,.;?@_`'{}|~")
+_KEYWORDS = {
+    "minimize": "MIN", "minimum": "MIN", "min": "MIN", "maximize": "MAX", "maximum": "MAX", "max": "MAX",
+    "st": "ST", "s.t.": "ST", "st.": "ST", "bounds": "BOUNDS", "bound": "BOUNDS",
+    "general": "GEN", "generals": "GEN", "gen": "GEN", "integer": "INT", "integers": "INT", "int": "INT",
+    "binary": "BIN", "binaries": "BIN", "bin": "BIN", "end": "END",
+}
+
+
+def _tokenize(text):
+    """Yield (kind, image, value, colon_follows).  Keywords are recognised only
+    for a name that starts a line, as the reference's scanner does."""
+    toks = []
+    for raw in text.replace("\r", "").split("\n"):
+        line = raw.split("\\", 1)[0].replace("\t", " ")
+        i, n, first = 0, len(line), True
+        while i < n:
+            ch = line[i]
+            if ch == " ":
+                i += 1
+                continue
+            if ch.isalpha() or (ch in _NAME_EXTRA and ch != "."):
+                j = i
+                while j < n and (line[j].isalnum() or line[j] in _NAME_EXTRA):
+                    j += 1
+                image = line[i:j]
+                kind = "NAME"
+                if first:
+                    low = image.lower()
+                    if low in ("subject", "such"):
+                        rest = line[j:].lstrip(" ")
+                        want = "to" if low == "subject" else "that"
+                        if rest.lower().startswith(want) and (len(rest) == len(want) or not rest[len(want)].isalnum()):
+                            kind = "ST"
+                            j = n - len(rest) + len(want)
+                    elif low in _KEYWORDS:
+                        kind = _KEYWORDS[low]
+                toks.append((kind, image, 0.0, j < n and line[j] == ":"))
+                i = j
+            elif ch.isdigit() or ch == ".":
+                j = i
+                while j < n and line[j].isdigit():
+                    j += 1
+                if j < n and line[j] == ".":
+                    j += 1
+                    while j < n and line[j].isdigit():
+                        j += 1
+                if j < n and line[j] in "eE":
+                    k = j + 1
+                    if k < n and line[k] in "+-":
+                        k += 1
+                    if k < n and line[k].isdigit():
+                        while k < n and line[k].isdigit():
+                            k += 1
+                        j = k
+                toks.append(("NUM", line[i:j], float(line[i:j]), False))
+                i = j
+            elif ch in "+-:":
+                toks.append(({"+": "PLUS", "-": "MINUS", ":": "COLON"}[ch], ch, 0.0, False))
+                i += 1
+            elif ch in "<>=":
+                j = i + 1
+                if j < n and line[j] in "<>=":
+                    j += 1
+                op = line[i:j]
+                kind = "LE" if "<" in op else ("GE" if ">" in op else "EQ")
+                toks.append((kind, op, 0.0, False))
+                i = j
+            else:
+                xerror("glp_read_lp: character `%s' not recognized" % ch)
+            first = False
+    toks.append(("EOF", "", 0.0, False))
+    return toks
+
+
+def glp_read_lp_from_string(P, parm, text):
+    """lib/glpcpx.js:1000-1010; returns 0 on success, 1 on a syntax error."""
+    _check(P, "glp_read_lp")
+    try:
+        _read_lp(P, text)
+    except GlpkError:
+        fresh = glp_prob()
+        P.__dict__.update(fresh.__dict__)
+        return 1
+    return 0
+
+
+def glp_read_lp(P, parm, callback):
+    """lib/glpcpx.js:10: ``callback()`` returns the next character or a chunk of
+    text and a falsy value at end of input (a plain string is accepted too)."""
+    if isinstance(callback, str):
+        return glp_read_lp_from_string(P, parm, callback)
+    parts = []
+    while True:
+        s = callback()
+        if not s:
+            break
+        parts.append(s)
+    return glp_read_lp_from_string(P, parm, "".join(parts))
+
+
+def _read_lp(P, text):
+    fresh = glp_prob()
+    P.__dict__.update(fresh.__dict__)
+    toks = _tokenize(text)
+    pos = [0]
+    cols, rows, lbs, ubs = {}, {}, {}, {}
+
+    def tok():
+        return toks[pos[0]]
+
+    def adv():
+        pos[0] += 1
+
+    def find_col(name):
+        j = cols.get(name)
+        if j is None:
+            j = glp_add_cols(P, 1)
+            glp_set_col_name(P, j, name)
+            cols[name] = j
+        return j
+
+    def linear_form():
+        ind, val, used = [0], [0.0], set()
+        while True:
+            s, coef = 1.0, 1.0
+            if tok()[0] in ("PLUS", "MINUS"):
+                s = 1.0 if tok()[0] == "PLUS" else -1.0
+                adv()
+            if tok()[0] == "NUM":
+                coef = tok()[2]
+                adv()
+            if tok()[0] != "NAME":
+                xerror("glp_read_lp: missing variable name")
+            j = find_col(tok()[1])
+            if j in used:
+                xerror("glp_read_lp: multiple use of variable `%s' not allowed" % tok()[1])
+            used.add(j)
+            ind.append(j)
+            val.append(s * coef)
+            adv()
+            if tok()[0] not in ("PLUS", "MINUS"):
+                break
+        keep = [(j, v) for j, v in zip(ind[1:], val[1:]) if v != 0.0]
+        return len(keep), [0] + [j for j, _ in keep], [0.0] + [v for _, v in keep]
+
+    def signed_number(what):
+        s = 1.0
+        if tok()[0] in ("PLUS", "MINUS"):
+            s = 1.0 if tok()[0] == "PLUS" else -1.0
+            adv()
+        if tok()[0] != "NUM":
+            xerror("glp_read_lp: missing " + what)
+        v = s * tok()[2]
+        adv()
+        return v
+
+    def bound_value(lower):
+        s, signed = 1.0, False
+        if tok()[0] in ("PLUS", "MINUS"):
+            s, signed = (1.0 if tok()[0] == "PLUS" else -1.0), True
+            adv()
+        if tok()[0] == "NUM":
+            v = s * tok()[2]
+            adv()
+            return v
+        if signed and tok()[0] == "NAME" and tok()[1].lower() in ("infinity", "inf"):
+            if lower and s > 0:
+                xerror("glp_read_lp: invalid use of `+inf' as lower bound")
+            if not lower and s < 0:
+                xerror("glp_read_lp: invalid use of `-inf' as upper bound")
+            adv()
+            return -DBL_MAX if lower else +DBL_MAX
+        xerror("glp_read_lp: missing %s bound" % ("lower" if lower else "upper"))
+
+    if tok()[0] not in ("MIN", "MAX"):
+        xerror("glp_read_lp: `minimize' or `maximize' keyword missing")
+    glp_set_obj_dir(P, GLP_MIN if tok()[0] == "MIN" else GLP_MAX)
+    adv()
+    if tok()[0] == "NAME" and tok()[3]:
+        glp_set_obj_name(P, tok()[1])
+        adv()
+        adv()
+    else:
+        glp_set_obj_name(P, "obj")
+    ln, ind, val = linear_form()
+    for k in range(1, ln + 1):
+        glp_set_obj_coef(P, ind[k], val[k])
+    if tok()[0] != "ST":
+        xerror("glp_read_lp: constraints section missing")
+    adv()
+    while True:
+        i = glp_add_rows(P, 1)
+        if tok()[0] == "NAME" and tok()[3]:
+            if tok()[1] in rows:
+                xerror("glp_read_lp: constraint `%s' multiply defined" % tok()[1])
+            rows[tok()[1]] = i
+            glp_set_row_name(P, i, tok()[1])
+            adv()
+            adv()
+        else:
+            glp_set_row_name(P, i, "r.%d" % i)
+        ln, ind, val = linear_form()
+        glp_set_mat_row(P, i, ln, ind, val)
+        sense = tok()[0]
+        if sense not in ("LE", "GE", "EQ"):
+            xerror("glp_read_lp: missing constraint sense")
+        adv()
+        rhs = signed_number("right-hand side")
+        glp_set_row_bnds(P, i, {"LE": GLP_UP, "GE": GLP_LO, "EQ": GLP_FX}[sense], rhs, rhs)
+        if tok()[0] not in ("PLUS", "MINUS", "NUM", "NAME"):
+            break
+    if tok()[0] == "BOUNDS":
+        adv()
+        while tok()[0] in ("PLUS", "MINUS", "NUM", "NAME"):
+            lb_flag = tok()[0] != "NAME"
+            if lb_flag:
+                lbv = bound_value(True)
+                if tok()[0] != "LE":
+                    xerror("glp_read_lp: missing `<', `<=', or `=<' after lower bound")
+                adv()
+            if tok()[0] != "NAME":
+                xerror("glp_read_lp: missing variable name")
+            j = find_col(tok()[1])
+            if lb_flag:
+                lbs[j] = lbv
+            adv()
+            if tok()[0] == "LE":
+                adv()
+                ubs[j] = bound_value(False)
+            elif tok()[0] == "GE":
+                if lb_flag:
+                    xerror("glp_read_lp: invalid bound definition")
+                adv()
+                lbs[j] = bound_value(True)
+            elif tok()[0] == "EQ":
+                if lb_flag:
+                    xerror("glp_read_lp: invalid bound definition")
+                adv()
+                lbs[j] = ubs[j] = signed_number("fixed value")
+            elif tok()[0] == "NAME" and tok()[1].lower() == "free":
+                if lb_flag:
+                    xerror("glp_read_lp: invalid bound definition")
+                lbs[j], ubs[j] = -DBL_MAX, +DBL_MAX
+                adv()
+            elif not lb_flag:
+                xerror("glp_read_lp: invalid bound definition")
+    while tok()[0] in ("GEN", "INT", "BIN"):
+        binary = tok()[0] == "BIN"
+        adv()
+        while tok()[0] == "NAME":
+            j = find_col(tok()[1])
+            glp_set_col_kind(P, j, GLP_IV)
+            if binary:
+                lbs[j], ubs[j] = 0.0, 1.0
+            adv()
+    if tok()[0] == "END":
+        adv()
+    elif tok()[0] != "EOF":
+        xerror("glp_read_lp: symbol %s in wrong position" % tok()[1])
+    if tok()[0] != "EOF":
+        xerror("glp_read_lp: extra symbol(s) detected beyond `end'")
+    for j in range(1, P.n + 1):  # lib/glpcpx.js:698-717
+        lb, ub = lbs.get(j, 0.0), ubs.get(j, +DBL_MAX)
+        if lb == -DBL_MAX and ub == +DBL_MAX:
+            t = GLP_FR
+        elif ub == +DBL_MAX:
+            t = GLP_LO
+        elif lb == -DBL_MAX:
+            t = GLP_UP
+        elif lb != ub:
+            t = GLP_DB
+        else:
+            t = GLP_FX
+        glp_set_col_bnds(P, j, t, lb, ub)
+    glp_sort_matrix(P)
+
+
+# ---- marshalling to the device handle ----
+def _arrays(P):
+    m, n = P.m, P.n
+    type_ = np.zeros(m + n, np.int32)
+    lb = np.zeros(m + n)
+    ub = np.zeros(m + n)
+    for i in range(1, m + 1):
+        r = P.row[i]
+        type_[i - 1], lb[i - 1], ub[i - 1] = r.type, r.lb, r.ub
+    coef = np.zeros(n)
+    kind = np.zeros(n, np.int32)
+    ptr = np.zeros(n + 1, np.int32)
+    ind, val = [], []
+    for j in range(1, n + 1):
+        c = P.col[j]
+        type_[m + j - 1], lb[m + j - 1], ub[m + j - 1] = c.type, c.lb, c.ub
+        coef[j - 1], kind[j - 1] = c.coef, c.kind
+        ptr[j - 1] = len(ind)
+        for (i, v) in c.elems:
+            ind.append(i - 1)
+            val.append(v)
+    ptr[n] = len(ind)
+    rii = np.array([P.row[i].rii for i in range(1, m + 1)])
+    sjj = np.array([P.col[j].sjj for j in range(1, n + 1)])
+    return dict(m=m, n=n, dir=P.dir, c0=P.c0, type=type_, lb=lb, ub=ub, coef=coef, kind=kind,
+                A_ptr=ptr, A_ind=np.array(ind, np.int32), A_val=np.array(val, np.float64)), rii, sjj
+
+
+def _device(P, device=0):
+    """(Re)build the device handle when the matrix changed; otherwise push only
+    bounds and statuses, which is all glp_set_*_bnds / glp_set_*_stat touch."""
+    d, rii, sjj = _arrays(P)
+    if P._dev is None or P._dirty:
+        if P._dev is not None:
+            P._dev.close()
+        P._dev = native.Problem(d, device=device, rii=rii, sjj=sjj)
+        P._dirty = False
+        P.valid = 0
+    else:
+        k = np.arange(1, P.m + P.n + 1, dtype=np.int32)
+        P._dev.set_bounds(k, d["type"], d["lb"], d["ub"])
+    stat = np.array([P.row[i].stat for i in range(1, P.m + 1)] +
+                    [P.col[j].stat for j in range(1, P.n + 1)], np.int32)
+    if not P.valid:
+        P._dev.set_basis(stat)
+    else:
+        # the basis is unchanged: only non-basic statuses may differ
+        P._dev.set_basis(stat)
+    P._dev.L.glpb_set_it_cnt(P._dev.h, int(P.it_cnt))
+    return P._dev
+
+
+def _pull(P, dev):
+    s = dev.solution()
+    m, n = P.m, P.n
+    P.pbs_stat, P.dbs_stat = s["pbs"], s["dbs"]
+    P.obj_val, P.it_cnt, P.some = s["obj"], s["it_cnt"], s["some"]
+    bind = {int(k): i + 1 for i, k in enumerate(s["head"])}
+    P.head = [0] + [int(k) for k in s["head"]]
+    for i in range(1, m + 1):
+        r = P.row[i]
+        r.stat, r.prim, r.dual = int(s["stat"][i - 1]), float(s["prim"][i - 1]), float(s["dual"][i - 1])
+        r.bind = bind.get(i, 0)
+    for j in range(1, n + 1):
+        c = P.col[j]
+        k = m + j
+        c.stat, c.prim, c.dual = int(s["stat"][k - 1]), float(s["prim"][k - 1]), float(s["dual"][k - 1])
+        c.bind = bind.get(k, 0)
+
+
+def _check_smcp(parm):
+    # lib/glpapi06.js:271-300
+    def bad(name):
+        xerror("glp_simplex: %s = %r; invalid parameter" % (name, getattr(parm, name)))
+    if parm.msg_lev not in (GLP_MSG_OFF, GLP_MSG_ERR, GLP_MSG_ON, GLP_MSG_ALL, GLP_MSG_DBG): bad("msg_lev")
+    if parm.meth not in (GLP_PRIMAL, GLP_DUALP, GLP_DUAL): bad("meth")
+    if parm.pricing not in (GLP_PT_STD, GLP_PT_PSE): bad("pricing")
+    if parm.r_test not in (GLP_RT_STD, GLP_RT_HAR): bad("r_test")
+    if not (0.0 < parm.tol_bnd < 1.0): bad("tol_bnd")
+    if not (0.0 < parm.tol_dj < 1.0): bad("tol_dj")
+    if not (0.0 < parm.tol_piv < 1.0): bad("tol_piv")
+    if parm.it_lim < 0: bad("it_lim")
+    if parm.tm_lim < 0: bad("tm_lim")
+    if parm.out_frq < 1: bad("out_frq")
+    if parm.out_dly < 0: bad("out_dly")
+    if parm.presolve not in (GLP_ON, GLP_OFF): bad("presolve")
+
+
+def glp_simplex(P, parm=None, device=0):
+    """lib/glpapi06.js:261-339"""
+    _check(P, "glp_simplex")
+    if parm is None:
+        parm = SMCP()
+    _check_smcp(parm)
+    P.pbs_stat = P.dbs_stat = GLP_UNDEF
+    P.obj_val, P.some = 0.0, 0
+    for i in range(1, P.m + 1):
+        r = P.row[i]
+        if r.type == GLP_DB and r.lb >= r.ub:
+            return GLP_EBOUND
+    for j in range(1, P.n + 1):
+        c = P.col[j]
+        if c.type == GLP_DB and c.lb >= c.ub:
+            return GLP_EBOUND
+    if P.m == 0 or P.n == 0:
+        xerror("glp_simplex: empty problems are handled by the host binding only")
+    dev = _device(P, device)
+    sp = dev.smcp(msg_lev=parm.msg_lev, meth=parm.meth, pricing=parm.pricing, r_test=parm.r_test,
+                  tol_bnd=parm.tol_bnd, tol_dj=parm.tol_dj, tol_piv=parm.tol_piv, obj_ll=parm.obj_ll,
+                  obj_ul=parm.obj_ul, it_lim=int(parm.it_lim), tm_lim=int(parm.tm_lim),
+                  out_frq=parm.out_frq, out_dly=parm.out_dly, presolve=GLP_OFF)
+    ret = dev.simplex(sp)
+    _pull(P, dev)
+    P.valid = 1 if ret in (0, GLP_EOBJLL, GLP_EOBJUL, GLP_EITLIM, GLP_ETMLIM) else P.valid
+    return ret
+
+
+def glp_intopt(P, parm=None, device=0):
+    """lib/glpapi09.js:61-390 (presolve OFF path: the root LP must be optimal)"""
+    _check(P, "glp_intopt")
+    if parm is None:
+        parm = IOCP()
+    if parm.br_tech not in (GLP_BR_FFV, GLP_BR_LFV, GLP_BR_MFV, GLP_BR_DTH, GLP_BR_PCH):
+        xerror("glp_intopt: br_tech = %r; invalid parameter" % (parm.br_tech,))
+    if parm.bt_tech not in (GLP_BT_DFS, GLP_BT_BFS, GLP_BT_BLB, GLP_BT_BPH):
+        xerror("glp_intopt: bt_tech = %r; invalid parameter" % (parm.bt_tech,))
+    if not (0.0 < parm.tol_int < 1.0):
+        xerror("glp_intopt: tol_int = %r; invalid parameter" % (parm.tol_int,))
+    if not (0.0 < parm.tol_obj < 1.0):
+        xerror("glp_intopt: tol_obj = %r; invalid parameter" % (parm.tol_obj,))
+    P.mip_stat, P.mip_obj = GLP_UNDEF, 0.0
+    for j in range(1, P.n + 1):  # lib/glpapi09.js:337-364
+        c = P.col[j]
+        if c.kind == GLP_IV:
+            if c.type in (GLP_LO, GLP_DB) and c.lb != math.floor(c.lb):
+                return GLP_EBOUND
+            if c.type in (GLP_UP, GLP_DB) and c.ub != math.floor(c.ub):
+                return GLP_EBOUND
+            if c.type == GLP_FX and c.lb != math.floor(c.lb):
+                return GLP_EBOUND
+    if parm.presolve == GLP_ON:
+        ret = glp_simplex(P, SMCP({"msg_lev": parm.msg_lev}), device=device)
+        if ret != 0:
+            return ret
+    if glp_get_status(P) != GLP_OPT:
+        return GLP_EROOT
+    dev = P._dev
+    ip = dev.iocp(msg_lev=parm.msg_lev, br_tech=parm.br_tech, bt_tech=parm.bt_tech,
+                  tol_int=parm.tol_int, tol_obj=parm.tol_obj, tm_lim=int(parm.tm_lim),
+                  out_frq=parm.out_frq, out_dly=parm.out_dly, pp_tech=parm.pp_tech,
+                  mip_gap=parm.mip_gap, presolve=GLP_OFF, node_lim=getattr(parm, "node_lim", -1))
+    ret = dev.intopt(ip)
+    mp = dev.mip()
+    P.mip_stat, P.mip_obj = mp["mip_stat"], mp["mip_obj"]
+    for i in range(1, P.m + 1):
+        P.row[i].mipx = float(mp["mipx"][i - 1])
+    for j in range(1, P.n + 1):
+        P.col[j].mipx = float(mp["mipx"][P.m + j - 1])
+    _pull(P, dev)
+    return ret

@@ -1,0 +1,178 @@
+/* glpb200.h -- C ABI of libglpb200.so, the B200-native (sm_100a) replacement
+ * for the simplex hot path of glpk.js (JavaScript port of GLPK 4.49).
+ *
+ * This is the drop-in boundary.  A host binding (N-API addon,
+ * ctypes, cgo ...) keeps one handle per glp_prob; the handle owns all
+ * device-resident problem data: CSC and CSR copies of the scaled constraint
+ * matrix, bounds, costs, the basis header, steepest-edge weights and the
+ * basis inverse.  Every entry point is blocking, never throws, and retains no
+ * caller pointer after it returns.  There is NO CPU fallback: without a CUDA
+ * device every compute call fails with GLPB_ENODEV.
+ *
+ * Index conventions at this boundary are the reference's: variables are
+ * numbered k = 1..m+n (auxiliary rows first), basis header entries are such
+ * k, statuses/types/return codes are the GLP_* values of lib/glpk.js.
+ * Arrays are plain 0-based C arrays (element [k-1] belongs to variable k)
+ * unless a parameter is documented as "CSA layout" (1-based, slot 0 unused,
+ * exactly as lib/glpspx01.js / lib/glpspx02.js keep them).
+ */
+#ifndef GLPB200_H
+#define GLPB200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- API misuse / environment errors (negative; GLP_* codes are >= 0) ---- */
+#define GLPB_EINVAL  (-1)   /* invalid argument (the JS facade throws)        */
+#define GLPB_ENODEV  (-2)   /* no CUDA device / CUDA runtime error            */
+#define GLPB_ENOMEM  (-3)   /* device allocation failed                      */
+#define GLPB_ESTATE  (-4)   /* call not valid in the handle's current state   */
+
+typedef struct glpb_prob glpb_prob;
+
+/* glp_smcp, field for field: lib/glpapi06.js:359-375 (SMCP constructor) */
+typedef struct glpb_smcp {
+    int msg_lev, meth, pricing, r_test;
+    double tol_bnd, tol_dj, tol_piv, obj_ll, obj_ul;
+    int it_lim, tm_lim, out_frq, out_dly, presolve;
+} glpb_smcp;
+
+/* glp_iocp: lib/glpapi09.js:392-414 (IOCP constructor); node_lim is an
+ * extension used only by throughput benchmarks (-1 = off) */
+typedef struct glpb_iocp {
+    int msg_lev, br_tech, bt_tech;
+    double tol_int, tol_obj;
+    int tm_lim, out_frq, out_dly, pp_tech;
+    double mip_gap;
+    int presolve;
+    long node_lim;
+} glpb_iocp;
+
+/* glp_bfcp subset: lib/glpapi12.js:108-122.  The device keeps an explicit
+ * inverse of the structural kernel of B instead of F*H*V, so only the update
+ * count (nfs_max -> refactorisation period) and the pivot tolerances apply. */
+typedef struct glpb_bfcp {
+    int nfs_max;        /* refactorise after this many updates (default 100) */
+    double piv_tol;     /* relative pivot threshold in the dense inverse      */
+    double upd_tol;     /* reserved                                           */
+} glpb_bfcp;
+
+void glpb_init_smcp(glpb_smcp *parm);   /* replaces: new SMCP()  api06:359 */
+void glpb_init_iocp(glpb_iocp *parm);   /* replaces: new IOCP()  api09:392 */
+
+/* Library / device probes. */
+int glpb_device_count(void);
+const char *glpb_last_error(void);
+const char *glpb_version(void);
+
+/* Create a device-resident problem.  Replaces what alloc_csa/init_csa copy
+ * out of the glp_prob (lib/glpspx01.js:5-145, lib/glpspx02.js:5-190):
+ *   dir GLP_MIN/GLP_MAX, c0 constant term,
+ *   type/lb/ub [m+n] (rows then columns, UNSCALED), coef[n] objective,
+ *   kind[n] GLP_CV/GLP_IV (may be NULL), rii[m], sjj[n] scale factors (NULL=1),
+ *   A in CSC: A_ptr[n+1], A_ind[nnz] 0-based rows, A_val[nnz] UNSCALED, each
+ *   column in the reference's list order (col.ptr -> c_next).
+ * Returns NULL on failure (see glpb_last_error). */
+glpb_prob *glpb_create(int m, int n, int nnz, int dir, double c0,
+                       const int *type, const double *lb, const double *ub,
+                       const double *coef, const int *kind,
+                       const double *rii, const double *sjj,
+                       const int *A_ptr, const int *A_ind, const double *A_val,
+                       int device);
+void glpb_destroy(glpb_prob *P);                     /* idempotent on NULL */
+
+/* glp_set_row_bnds / glp_set_col_bnds for a list of variables k (1..m+n),
+ * api01:217-281: non-basic statuses are re-derived, the basis stays valid. */
+int glpb_set_bounds(glpb_prob *P, int count, const int *k, const int *type,
+                    const double *lb, const double *ub);
+/* glp_set_row_stat / glp_set_col_stat for all variables, api05:1-47 */
+int glpb_set_basis(glpb_prob *P, const int *stat /* [m+n] */);
+int glpb_std_basis(glpb_prob *P);                    /* api05:49-63 */
+int glpb_set_bfcp(glpb_prob *P, const glpb_bfcp *parm);
+int glpb_set_it_cnt(glpb_prob *P, int it_cnt);
+
+/* glp_factorize, api12:5-100: 0 / GLP_EBADB / GLP_ESING / GLP_ECOND */
+int glpb_factorize(glpb_prob *P);
+/* glp_simplex with presolve OFF, api06:261-339 -> solve_lp api06:3-39 ->
+ * spx_primal / spx_dual.  Returns 0 or GLP_EBADB/ESING/ECOND/EBOUND/EFAIL/
+ * EOBJLL/EOBJUL/EITLIM/ETMLIM. */
+int glpb_simplex(glpb_prob *P, const glpb_smcp *parm);
+/* glp_intopt with presolve OFF, api09:61-114 -> ios_driver (ios03:507-951):
+ * 0 / GLP_EROOT / GLP_EFAIL / GLP_EMIPGAP / GLP_ETMLIM / GLP_ESTOP */
+int glpb_intopt(glpb_prob *P, const glpb_iocp *parm);
+
+/* What store_sol writes back (lib/glpspx01.js:1591-1681).  Any pointer may be
+ * NULL.  stat/prim/dual are [m+n]; head is [m] (values k = 1..m+n). */
+int glpb_get_solution(glpb_prob *P, int *stat, double *prim, double *dual,
+                      int *head, int *pbs_stat, int *dbs_stat, double *obj_val,
+                      int *it_cnt, int *some);
+int glpb_get_status(glpb_prob *P);                   /* api06:398-427 */
+/* record_solution (ios03:118-139): mipx is [m+n] */
+int glpb_get_mip(glpb_prob *P, int *mip_stat, double *mip_obj, double *mipx,
+                 long *nodes);
+
+/* Counters for measurement: out[0] iterations, [1] refactorisations,
+ * [2] kernel launches, [3] host<->device syncs, [4] basis updates,
+ * [5] current kernel size k, [6] device microseconds in the last solve. */
+int glpb_get_counters(glpb_prob *P, long *out, int count);
+
+/* Basis solves with the current factorisation, scaled space:
+ * bfd_ftran / bfd_btran (lib/glpbfd.js:148-168); x is [m], in place. */
+int glpb_ftran(glpb_prob *P, double *x);
+int glpb_btran(glpb_prob *P, double *x);
+
+/* ---- kernel-level entry points (parity tests feed them the reference's
+ *      arrays; all arrays CSA layout = 1-based, lengths as in alloc_csa) ---- */
+
+/* chuzc, lib/glpspx01.js:646-688: returns q (0 = none) */
+int glpb_k_chuzc_primal(int n, const signed char *stat, const double *cbar,
+                        const double *gamma, double tol_dj, int *q);
+/* chuzr, lib/glpspx02.js:572-625: returns p (0 = none) and delta */
+int glpb_k_chuzr_dual(int m, int n, const signed char *type, const double *lb,
+                      const double *ub, const int *head, const double *bbar,
+                      const double *gamma, double tol_bnd, int *p,
+                      double *delta);
+/* chuzr, lib/glpspx01.js:808-1028, on the sorted list tcol_ind[1..tcol_num];
+ * p = 0 none, -1 bound flip */
+int glpb_k_ratio_primal(int m, int n, const signed char *type, const double *lb,
+                        const double *ub, const double *coef, const int *head,
+                        int phase, const double *bbar, double cbar_q, int q,
+                        const int *tcol_ind, const double *tcol_vec,
+                        int tcol_num, double rtol, int *p, int *p_stat,
+                        double *teta);
+/* chuzc, lib/glpspx02.js:793-935, on the sorted list trow_ind[1..trow_num] */
+int glpb_k_ratio_dual(int n, const signed char *stat, const double *cbar,
+                      double delta, const int *trow_ind, const double *trow_vec,
+                      int trow_num, double rtol, int *q, double *new_dq);
+/* eval_trow1, lib/glpspx02.js:655-693 (pivot row as column dots).  A in CSA
+ * layout; rho[1..m]; out trow_vec[1..n] */
+int glpb_k_trow(int m, int n, const int *A_ptr, const int *A_ind,
+                const double *A_val, const int *head, const signed char *stat,
+                const double *rho, double *trow_vec);
+
+/* Stand-alone streaming benchmark of the pricing kernel over resident data
+ * (bench.py roofline leg): runs `reps` launches on n columns, returns the
+ * average device time per launch in microseconds. */
+int glpb_bench_kernel(const char *name, int m, int n, int reps, double *usec,
+                      double *bytes);
+
+/* Synthetic problem generators (RNG = lib/glprng01.js restated).
+ * Each allocates with malloc; free with glpb_free_problem. */
+typedef struct glpb_problem_data {
+    int m, n, nnz, dir;
+    double c0;
+    int *type; double *lb, *ub;     /* [m+n] */
+    double *coef; int *kind;        /* [n]   */
+    int *A_ptr, *A_ind; double *A_val;
+} glpb_problem_data;
+int glpb_gen_packing(int m, int n, double density, int seed, glpb_problem_data *out);   /* C2 */
+int glpb_gen_covering(int m, int n, int kmin, int kspan, int seed, glpb_problem_data *out); /* C3 */
+int glpb_gen_mkp(int m, int n, int seed, glpb_problem_data *out);                       /* C5 */
+void glpb_free_problem(glpb_problem_data *d);
+void glpb_rng_fill(int seed, int count, int *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GLPB200_H */

@@ -1,0 +1,145 @@
+"""GPU parity tests, kernel level: every selection kernel is fed the oracle's
+live CSA arrays (the reference's basis, reduced costs and weights) at every
+iteration of real solves and must return the very same index (bit-exact),
+through the C ABI (glpb_k_*)."""
+import numpy as np
+import pytest
+
+import glpk_js_b200 as G
+import oracle_lib as O
+import helpers as H
+
+nat = G.native
+pytestmark = pytest.mark.gpu
+
+
+def problems():
+    yield "gap", H.load_golden("gap")
+    yield "todd", H.load_golden("todd")
+    yield "packing", H.to_oracle(nat.generate("packing", m=60, n=120, density=0.25, seed=3))
+    yield "covering", H.to_oracle(nat.generate("covering", m=120, n=240, kmin=3, kspan=4, seed=4))
+
+
+def boxed(d, seed):
+    """give some columns upper bounds so that DB / bound-flip paths are hit"""
+    rng = np.random.default_rng(seed)
+    d = dict(d)
+    ct, cu = d["c_type"].copy(), d["c_ub"].copy()
+    pick = rng.random(d["n"]) < 0.4
+    ct[pick & (ct == O.GLP_LO)] = O.GLP_DB
+    cu[pick] = np.where(cu[pick] > 0, cu[pick], rng.integers(1, 4, pick.sum()))
+    d["c_type"], d["c_ub"] = ct, cu
+    return d
+
+
+def test_primal_pricing_and_ratio_bit_exact_on_reference_state():
+    checked = {"chuzc": 0, "chuzr": 0, "flip": 0, "phase1": 0}
+    for name, d in problems():
+        for variant in (d, boxed(d, 1)):
+            P = O.Problem.from_arrays(variant)
+
+            def hook(ev, csa):
+                s = O.csa_scalars(csa)
+                m, n = s["m"], s["n"]
+                if ev == O.EV_P_CHUZC:
+                    q = nat.k_chuzc_primal(n, O.csa_get(csa, "stat"), O.csa_get(csa, "cbar"),
+                                           O.csa_get(csa, "gamma"), s["tol"])
+                    assert q == s["q"], (name, s["it_cnt"], q, s["q"])
+                    checked["chuzc"] += 1
+                elif ev == O.EV_P_CHUZR:
+                    cbar = O.csa_get(csa, "cbar")
+                    p, p_stat, teta = nat.k_ratio_primal(
+                        m, n, O.csa_get(csa, "type"), O.csa_get(csa, "lb"), O.csa_get(csa, "ub"),
+                        O.csa_get(csa, "coef"), O.csa_get(csa, "head"), s["phase"], O.csa_get(csa, "bbar"),
+                        float(cbar[s["q"]]), s["q"], O.csa_get(csa, "tcol_ind"), O.csa_get(csa, "tcol_vec"),
+                        s["tcol_num"], s["tol"])
+                    assert (p, teta) == (s["p"], s["teta"]), (name, s["it_cnt"], p, s["p"], teta, s["teta"])
+                    if p != 0:
+                        assert p_stat == s["p_stat"]
+                    checked["chuzr"] += 1
+                    checked["flip"] += p < 0
+                    checked["phase1"] += s["phase"] == 1
+            P.set_hook(hook)
+            assert P.simplex(meth=O.GLP_PRIMAL) == 0
+    assert checked["chuzc"] > 200 and checked["chuzr"] > 200 and checked["flip"] > 0 and checked["phase1"] > 0, checked
+
+
+def test_dual_pricing_and_ratio_bit_exact_on_reference_state():
+    checked = {"chuzr": 0, "chuzc": 0}
+    for name, d in problems():
+        for variant in (d, boxed(d, 2)):
+            P = O.Problem.from_arrays(variant)
+
+            def hook(ev, csa):
+                s = O.csa_scalars(csa)
+                m, n = s["m"], s["n"]
+                if ev == O.EV_D_CHUZR:
+                    p, delta = nat.k_chuzr_dual(m, n, O.csa_get(csa, "type"), O.csa_get(csa, "lb"),
+                                                O.csa_get(csa, "ub"), O.csa_get(csa, "head"),
+                                                O.csa_get(csa, "bbar"), O.csa_get(csa, "gamma"), s["tol"])
+                    assert (p, delta) == (s["p"], s["delta"]), (name, s["it_cnt"])
+                    checked["chuzr"] += 1
+                elif ev == O.EV_D_CHUZC:
+                    q, new_dq = nat.k_ratio_dual(n, O.csa_get(csa, "stat"), O.csa_get(csa, "cbar"), s["delta"],
+                                                 O.csa_get(csa, "trow_ind"), O.csa_get(csa, "trow_vec"),
+                                                 s["trow_num"], s["tol"])
+                    assert (q, new_dq) == (s["q"], s["new_dq"]), (name, s["it_cnt"], q, s["q"])
+                    checked["chuzc"] += 1
+            P.set_hook(hook)
+            assert P.simplex(meth=O.GLP_DUAL) == 0
+    assert checked["chuzr"] > 200 and checked["chuzc"] > 200, checked
+
+
+def test_pricing_ties_break_to_lowest_index():
+    """Exact ties in d^2/gamma and in (ratio, |alfa|): lowest index / first in list."""
+    rng = np.random.default_rng(0)
+    for n in (1, 7, 300, 5000):
+        stat = np.full(1 + n, O.GLP_NL, np.int8)
+        cbar = np.zeros(1 + n)
+        gamma = np.ones(1 + n)
+        vals = rng.choice([-2.0, -1.0, 0.0, 1.0], size=n)
+        cbar[1:] = vals
+        stat[1:][rng.random(n) < 0.2] = O.GLP_NS
+        stat[1:][rng.random(n) < 0.2] = O.GLP_NU
+        stat[1:][rng.random(n) < 0.1] = O.GLP_NF
+        want = O.lib().glpo_chuzc_primal(n, stat.ctypes.data, cbar.ctypes.data, gamma.ctypes.data, 1e-7)
+        assert nat.k_chuzc_primal(n, stat, cbar, gamma, 1e-7) == want
+    # empty / ineligible
+    assert nat.k_chuzc_primal(3, np.full(4, O.GLP_NS, np.int8), -np.ones(4), np.ones(4), 1e-7) == 0
+    # dual ratio test with many exact ties
+    for n in (5, 64, 3000):
+        stat = np.full(1 + n, O.GLP_NL, np.int8)
+        cbar = np.zeros(1 + n)
+        cbar[1:] = rng.choice([0.0, 1.0, 2.0], size=n)
+        trow = np.zeros(1 + n)
+        trow[1:] = rng.choice([0.5, 1.0, 2.0], size=n)
+        ind = np.zeros(1 + n, np.int32)
+        ind[1:] = rng.permutation(n) + 1
+        q = np.zeros(1, np.int32)
+        dq = np.zeros(1)
+        O.lib().glpo_chuzc_dual(stat.ctypes.data, cbar.ctypes.data, 1.0, ind.ctypes.data, trow.ctypes.data, n,
+                                3e-8, q.ctypes.data, dq.ctypes.data)
+        assert nat.k_ratio_dual(n, stat, cbar, 1.0, ind, trow, n, 3e-8) == (int(q[0]), float(dq[0]))
+
+
+def test_pivot_row_spmv_matches_reference_eval_trow():
+    """eval_trow1 (column dots): warp-level summation order differs from the
+    sequential loop, so the tolerance is 1e-12 relative to |rho|.|A_j|."""
+    seen = [0]
+    for name, d in problems():
+        P = O.Problem.from_arrays(d)
+
+        def hook(ev, csa):
+            if ev != O.EV_D_TROW:
+                return
+            s = O.csa_scalars(csa)
+            m, n = s["m"], s["n"]
+            got = nat.k_trow(m, n, O.csa_get(csa, "A_ptr"), O.csa_get(csa, "A_ind"), O.csa_get(csa, "A_val"),
+                             O.csa_get(csa, "head"), O.csa_get(csa, "stat"), O.csa_get(csa, "work4"))
+            ref = O.csa_get(csa, "trow_vec")
+            scale = 1.0 + np.abs(O.csa_get(csa, "work4")).max() * np.abs(O.csa_get(csa, "A_val")).max()
+            assert np.max(np.abs(got[1:] - ref[1:])) <= 1e-12 * scale * 16
+            seen[0] += 1
+        P.set_hook(hook)
+        assert P.simplex(meth=O.GLP_DUAL) == 0
+    assert seen[0] > 100

@@ -1,0 +1,150 @@
+"""GPU parity tests, solver level, through the C ABI: identical status, optimum
+within 1e-9 relative, primal/dual residuals <= 1e-9, against the oracle and the
+golden pins; plus the size-independent properties of the basis solves."""
+import numpy as np
+import pytest
+
+import glpk_js_b200 as G
+import oracle_lib as O
+import helpers as H
+
+nat = G.native
+glpk = G.glpk
+pytestmark = pytest.mark.gpu
+METHS = [nat.GLP_PRIMAL, nat.GLP_DUAL, nat.GLP_DUALP]
+
+
+def solve_both(dn, **kw):
+    P = nat.Problem(dn)
+    rc = P.simplex(**kw)
+    s = P.solution()
+    Q = O.Problem.from_arrays(H.to_oracle(dn))
+    orc = Q.simplex(**kw)
+    o = Q.solution()
+    return P, rc, s, orc, o
+
+
+def assert_parity(dn, rc, s, orc, o, what):
+    assert rc == orc, (what, rc, orc)
+    assert (s["status"], s["pbs"], s["dbs"]) == (o["status"], o["pbs"], o["dbs"]), what
+    if o["status"] == O.GLP_OPT:
+        assert abs(s["obj"] - o["obj"]) <= 1e-9 * max(1.0, abs(o["obj"])), (what, s["obj"], o["obj"])
+        r = H.kkt(dn, s)
+        assert max(r.values()) <= 1e-9, (what, r)
+
+
+@pytest.mark.parametrize("name", ["test", "gap", "todd"])
+@pytest.mark.parametrize("meth", METHS)
+def test_fixtures_match_oracle_and_pins(name, meth):
+    d = H.load_golden(name)
+    dn = H.to_native(d)
+    P, rc, s, orc, o = solve_both(dn, meth=meth)
+    assert_parity(dn, rc, s, orc, o, (name, meth))
+    assert abs(s["obj"] - d["highs_lp_obj"]) <= 1e-9 * max(1.0, abs(d["highs_lp_obj"]))
+    P.close()
+
+
+def test_test_lpt_follows_the_hand_trace():
+    """no ties on this problem, so the device path must take the same two pivots"""
+    d = H.load_golden("test")
+    P = nat.Problem(H.to_native(d))
+    assert P.simplex(meth=nat.GLP_PRIMAL) == 0
+    s = P.solution()
+    assert s["it_cnt"] == 2 and list(s["head"]) == d["hand_trace_primal"]["head_final"]
+    np.testing.assert_allclose(s["prim"][3:], d["highs_lp_x"], atol=1e-9)
+    np.testing.assert_allclose(s["dual"][:3], [10.0 / 3, 2.0 / 3, 0.0], atol=1e-9)
+    P.close()
+
+
+@pytest.mark.parametrize("meth", METHS)
+@pytest.mark.parametrize("pricing", [nat.GLP_PT_PSE, nat.GLP_PT_STD])
+@pytest.mark.parametrize("r_test", [nat.GLP_RT_HAR, nat.GLP_RT_STD])
+def test_synthetic_small(meth, pricing, r_test):
+    for which, kw in (("packing", dict(m=48, n=96, density=0.3, seed=21)),
+                      ("covering", dict(m=96, n=192, kmin=3, kspan=4, seed=22))):
+        dn = nat.generate(which, **kw)
+        P, rc, s, orc, o = solve_both(dn, meth=meth, pricing=pricing, r_test=r_test)
+        assert_parity(dn, rc, s, orc, o, (which, meth, pricing, r_test))
+        P.close()
+
+
+@pytest.mark.parametrize("which,kw,meth", [
+    ("packing", dict(m=256, n=512, density=0.2, seed=20240501), nat.GLP_PRIMAL),
+    ("covering", dict(m=1024, n=2048, kmin=8, kspan=17, seed=20240601), nat.GLP_DUAL),
+])
+def test_synthetic_medium_with_refactorisations(which, kw, meth):
+    dn = nat.generate(which, **kw)
+    P, rc, s, orc, o = solve_both(dn, meth=meth)
+    assert_parity(dn, rc, s, orc, o, which)
+    c = P.counters()
+    assert c["refactorizations"] >= 2 and c["launches"] > 0, c
+    P.close()
+
+
+def test_infeasible_unbounded_and_limits():
+    # infeasible: x1 + x2 <= 1, x1 + x2 >= 3
+    P = glpk.glp_create_prob()
+    txt = "Minimize\n obj: x1 + x2\nSubject To\n a: x1 + x2 <= 1\n b: x1 + x2 >= 3\nEnd\n"
+    assert glpk.glp_read_lp_from_string(P, None, txt) == 0
+    for meth in METHS:
+        Q = O.Problem.from_lp(txt)
+        orc = Q.simplex(meth=meth)
+        parm = glpk.SMCP({"meth": meth})
+        parm.msg_lev = glpk.GLP_MSG_OFF
+        glpk.glp_std_basis(P)
+        assert glpk.glp_simplex(P, parm) == orc
+        assert glpk.glp_get_status(P) == Q.solution()["status"] == glpk.GLP_NOFEAS
+    # unbounded: max x1 + x2 s.t. x1 - x2 <= 1
+    txt = "Maximize\n obj: x1 + x2\nSubject To\n a: x1 - x2 <= 1\nEnd\n"
+    assert glpk.glp_read_lp_from_string(P, None, txt) == 0
+    Q = O.Problem.from_lp(txt)
+    assert Q.simplex(meth=O.GLP_PRIMAL) == 0
+    parm = glpk.SMCP()
+    parm.msg_lev = glpk.GLP_MSG_OFF
+    assert glpk.glp_simplex(P, parm) == 0
+    assert glpk.glp_get_status(P) == Q.solution()["status"] == glpk.GLP_UNBND
+    assert glpk.glp_get_unbnd_ray(P) == Q.solution()["some"]
+    # iteration limit
+    dn = nat.generate("packing", m=48, n=96, density=0.3, seed=21)
+    R = nat.Problem(dn)
+    assert R.simplex(meth=nat.GLP_PRIMAL, it_lim=5) == nat.GLP_EITLIM
+    assert R.solution()["it_cnt"] == 5 and R.solution()["pbs"] == nat.GLP_FEAS
+    assert R.simplex(meth=nat.GLP_PRIMAL) == 0          # warm start from the stored basis
+    Q = O.Problem.from_arrays(H.to_oracle(dn))
+    Q.simplex(meth=O.GLP_PRIMAL)
+    assert abs(R.solution()["obj"] - Q.solution()["obj"]) <= 1e-9 * abs(Q.solution()["obj"])
+    R.close()
+
+
+def test_basis_solves_roundtrip_and_linearity():
+    """ftran/btran against a dense numpy solve with the returned basis header;
+    B * ftran(b) = b, B' * btran(c) = c, and linearity -- at a size where the
+    structural kernel T is a few hundred wide."""
+    dn = nat.generate("packing", m=256, n=512, density=0.2, seed=9)
+    P = nat.Problem(dn)
+    assert P.simplex(meth=nat.GLP_PRIMAL) == 0
+    s = P.solution()
+    B = H.basis_matrix(dn, s["head"])
+    rng = np.random.default_rng(1)
+    b1, b2 = rng.standard_normal(256), rng.standard_normal(256)
+    x1, x2 = P.ftran(b1), P.ftran(b2)
+    assert np.max(np.abs(B @ x1 - b1)) <= 1e-9 * (1 + np.abs(x1).max())
+    np.testing.assert_allclose(P.ftran(2 * b1 - 3 * b2), 2 * x1 - 3 * x2, rtol=0, atol=1e-9 * (1 + np.abs(x1).max()))
+    z = P.btran(b1)
+    assert np.max(np.abs(B.T @ z - b1)) <= 1e-9 * (1 + np.abs(z).max())
+    assert P.counters()["k"] == int((s["stat"][256:] == nat.GLP_BS).sum())
+    P.close()
+
+
+def test_facade_like_reference_test_js():
+    """the flow of the reference's test/test.js cplex(): read LP, simplex, print"""
+    lp = glpk.glp_create_prob()
+    assert glpk.glp_read_lp_from_string(lp, None, H.golden_text("test")) == 0
+    smcp = glpk.SMCP({"presolve": glpk.GLP_OFF})
+    smcp.msg_lev = glpk.GLP_MSG_OFF
+    assert glpk.glp_simplex(lp, smcp) == 0
+    assert glpk.glp_get_status(lp) == glpk.GLP_OPT
+    assert abs(glpk.glp_get_obj_val(lp) - 733.3333333333333) <= 1e-9 * 733.4
+    x = [glpk.glp_get_col_prim(lp, j) for j in range(1, glpk.glp_get_num_cols(lp) + 1)]
+    np.testing.assert_allclose(x, [33.333333333333336, 66.66666666666666, 0.0], atol=1e-9)
+    assert [glpk.glp_get_col_name(lp, j) for j in (1, 2, 3)] == ["x1", "x2", "x3"]

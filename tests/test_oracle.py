@@ -1,0 +1,175 @@
+"""CPU tests: the oracle against the pins, the host logic, the C-ABI surface.
+(No CUDA device is needed; nothing here launches a kernel.)"""
+import re
+import os
+
+import numpy as np
+import pytest
+
+import glpk_js_b200 as G
+import oracle_lib as O
+import helpers as H
+
+nat = G.native
+glpk = G.glpk
+PINS = {"test": 733.3333333333333, "gap": 254.35771655880353, "todd": 4194303.5}
+
+
+@pytest.mark.parametrize("name", ["test", "gap", "todd"])
+@pytest.mark.parametrize("meth", [O.GLP_PRIMAL, O.GLP_DUAL, O.GLP_DUALP])
+def test_oracle_matches_highs_pins(name, meth):
+    d = H.load_golden(name)
+    assert abs(d["highs_lp_obj"] - PINS[name]) <= 1e-9 * max(1, abs(PINS[name]))
+    P = O.Problem.from_arrays(d)
+    assert P.simplex(meth=meth) == 0
+    s = P.solution()
+    assert s["status"] == O.GLP_OPT
+    assert abs(s["obj"] - PINS[name]) <= 1e-9 * max(1.0, abs(PINS[name]))
+    r = H.kkt(H.to_native(d), s)
+    assert max(r.values()) <= 1e-9, r
+
+
+def test_oracle_hand_trace_test_lpt():
+    """pivots (q=1,p=2),(q=2,p=1); cbar/gamma/bbar after iteration 1."""
+    d = H.load_golden("test")
+    tr = d["hand_trace_primal"]
+    P = O.Problem.from_arrays(d)
+    seen = []
+
+    def hook(ev, csa):
+        if ev == O.EV_P_CHUZR:
+            s = O.csa_scalars(csa)
+            seen.append((s["q"], s["p"], O.csa_get(csa, "cbar")[1:].copy(),
+                         O.csa_get(csa, "gamma")[1:].copy(), O.csa_get(csa, "bbar")[1:].copy(),
+                         O.csa_get(csa, "tcol_ind")[1:4].copy()))
+    P.set_hook(hook)
+    assert P.simplex(meth=O.GLP_PRIMAL) == 0
+    assert [[q, p] for q, p, *_ in seen] == tr["pivots"]
+    assert list(seen[0][5]) == [3, 1, 2]          # order left by sort_tcol
+    np.testing.assert_allclose(seen[1][2], tr["cbar_after_1"], rtol=1e-12)
+    np.testing.assert_allclose(seen[1][3], tr["gamma_after_1"], rtol=1e-12)
+    np.testing.assert_allclose(seen[1][4], tr["bbar_after_1"], rtol=1e-12)
+    s = P.solution()
+    assert s["it_cnt"] == tr["it_cnt"] and list(s["head"]) == tr["head_final"]
+    np.testing.assert_allclose(s["prim"][3:], d["highs_lp_x"], atol=1e-9)
+
+
+def test_oracle_invariants_updated_vs_recomputed():
+    """The reference's own self-check (err_in_bbar/cbar, lib/glpspx01.js:1257-1289):
+    updated bbar/cbar must agree with values recomputed from scratch."""
+    d = nat.generate("packing", m=40, n=80, density=0.3, seed=5)
+    P = O.Problem.from_arrays(H.to_oracle(d))
+    A = H.dense_A(d)
+    worst = [0.0]
+
+    def hook(ev, csa):
+        if ev != O.EV_P_ITER:
+            return
+        s = O.csa_scalars(csa)
+        m, n = s["m"], s["n"]
+        head = O.csa_get(csa, "head")
+        stat = O.csa_get(csa, "stat")
+        lb, ub = O.csa_get(csa, "lb"), O.csa_get(csa, "ub")
+        bbar = O.csa_get(csa, "bbar")[1:]
+        full = np.hstack([np.eye(m), -A])
+        B = full[:, head[1:m + 1] - 1]
+        N = full[:, head[m + 1:] - 1]
+        xn = np.array([{2: lb[head[m + j]], 3: ub[head[m + j]], 4: 0.0, 5: lb[head[m + j]]}[int(stat[j])]
+                       for j in range(1, n + 1)])
+        beta = np.linalg.solve(B, -N @ xn)
+        worst[0] = max(worst[0], np.max(np.abs(beta - bbar) / (1 + np.abs(beta))))
+    P.set_hook(hook)
+    assert P.simplex(meth=O.GLP_PRIMAL) == 0
+    assert worst[0] <= 1e-9
+
+
+def test_lp_reader_roundtrip_and_python_reader_agree():
+    for name in ("test", "gap", "todd"):
+        d = H.load_golden(name)
+        text = H.golden_text(name)
+        e = O.Problem.from_lp(text).export()
+        for k in ("r_type", "r_lb", "r_ub", "c_type", "c_lb", "c_ub", "c_coef", "c_kind", "A_ptr", "A_ind", "A_val"):
+            np.testing.assert_array_equal(e[k], d[k], err_msg=name + ":" + k)
+        P = glpk.glp_create_prob()
+        assert glpk.glp_read_lp_from_string(P, None, text) == 0
+        a, _, _ = glpk._arrays(P)
+        n = H.to_native(d)
+        for k in ("type", "lb", "ub", "coef", "kind", "A_ptr", "A_ind", "A_val"):
+            np.testing.assert_array_equal(a[k], n[k], err_msg=name + ":" + k)
+        assert (a["dir"], P.m, P.n, P.nnz) == (d["dir"], d["m"], d["n"], len(d["A_val"]))
+
+
+def test_lp_reader_syntax_error_and_bounds_forms():
+    P = glpk.glp_create_prob()
+    assert glpk.glp_read_lp_from_string(P, None, "Maximize\n obj: x\nEnd\n") == 1   # no constraints
+    txt = ("Minimize\n z: 2 a - b + 0 c\nSubject To\n c1: a + b >= -1.5\n c2: - a + 3 c = 2\n"
+           "Bounds\n -inf <= a <= 4\n b free\n c >= 1\n 0 <= d <= 1\nBinary\n e\nGeneral\n d\nEnd\n")
+    assert glpk.glp_read_lp_from_string(P, None, txt) == 0
+    assert [P.col[j].type for j in range(1, 6)] == [glpk.GLP_UP, glpk.GLP_FR, glpk.GLP_LO, glpk.GLP_DB, glpk.GLP_DB]
+    assert glpk.glp_get_num_int(P) == 2 and glpk.glp_get_num_bin(P) == 2
+    assert P.row[1].type == glpk.GLP_LO and P.row[1].lb == -1.5 and P.row[2].type == glpk.GLP_FX
+    Q = O.Problem.from_lp(txt)
+    e = Q.export()
+    a, _, _ = glpk._arrays(P)
+    np.testing.assert_array_equal(a["type"], np.concatenate([e["r_type"], e["c_type"]]))
+    np.testing.assert_array_equal(a["A_val"], e["A_val"])
+
+
+def test_rng_and_generators_are_deterministic_and_match_oracle_rng():
+    a = nat.rng_fill(20240501, 500)
+    b = np.zeros(500, np.int32)
+    O.lib().glpo_rng_fill(20240501, 500, b.ctypes.data_as(O.C.c_void_p))
+    np.testing.assert_array_equal(a, b)
+    assert a.min() >= 0
+    d1 = nat.generate("covering", m=64, n=128, kmin=4, kspan=3, seed=7)
+    d2 = nat.generate("covering", m=64, n=128, kmin=4, kspan=3, seed=7)
+    np.testing.assert_array_equal(d1["A_ind"], d2["A_ind"])
+    np.testing.assert_array_equal(d1["A_val"], d2["A_val"])
+    rows = np.zeros(64, int)
+    np.add.at(rows, d1["A_ind"], 1)
+    assert rows.min() >= 1                       # every row covered
+    lens = np.diff(d1["A_ptr"])
+    assert lens[1:].min() >= 4 and lens[1:].max() <= 6
+    k = nat.generate("mkp", m=5, n=20, seed=3)
+    assert (k["kind"] == nat.GLP_IV).all() and (k["ub"][5:] == 1).all()
+
+
+def test_c_abi_exports_every_declared_symbol():
+    hdr = open(os.path.join(os.path.dirname(H.HERE), "include", "glpb200.h")).read()
+    declared = set(re.findall(r"\b(glpb_[a-z0-9_]+)\s*\(", hdr))
+    declared -= {"glpb_prob"}
+    lib = nat.load()
+    missing = [s for s in sorted(declared) if not hasattr(lib, s)]
+    assert not missing, missing
+    assert set(nat.SYMBOLS) == declared
+
+
+def test_no_cpu_fallback_without_device():
+    """Without a CUDA device every compute entry point must fail loudly."""
+    lib = nat.load()
+    if lib.glpb_device_count() > 0:
+        pytest.skip("a GPU is present")
+    d = nat.generate("packing", m=4, n=8, density=0.5, seed=1)
+    with pytest.raises(RuntimeError, match="no CUDA device"):
+        nat.Problem(d)
+    with pytest.raises(RuntimeError, match="no CUDA device"):
+        nat.k_chuzc_primal(3, np.zeros(4, np.int8), np.zeros(4), np.ones(4), 1e-7)
+    P = glpk.glp_create_prob()
+    glpk.glp_read_lp_from_string(P, None, H.golden_text("test"))
+    with pytest.raises(RuntimeError):
+        glpk.glp_simplex(P, glpk.SMCP({"msg_lev": glpk.GLP_MSG_ERR}))
+
+
+def test_facade_parameter_checks_and_quirks():
+    s = glpk.SMCP({"msg_lev": 0, "it_lim": 5})
+    assert s.msg_lev == glpk.GLP_MSG_ALL and s.it_lim == 5     # the `|| default` quirk
+    P = glpk.glp_create_prob()
+    glpk.glp_read_lp_from_string(P, None, H.golden_text("test"))
+    bad = glpk.SMCP()
+    bad.tol_bnd = 2.0
+    with pytest.raises(glpk.GlpkError, match="tol_bnd"):
+        glpk.glp_simplex(P, bad)
+    with pytest.raises(glpk.GlpkError, match="out of range"):
+        glpk.glp_get_col_prim(P, 99)
+    glpk.glp_set_col_bnds(P, 1, glpk.GLP_DB, 3.0, 1.0)
+    assert glpk.glp_simplex(P, glpk.SMCP()) == glpk.GLP_EBOUND
