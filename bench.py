@@ -1,0 +1,313 @@
+#!/usr/bin/env python
+"""bench.py -- headline measurement of the simplex hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c2s|c3s]
+    python bench.py --impl reference ...      # the reference's CPU path (oracle port)
+
+A *step* is one complete solve of the workload LP from the standard (all-slack)
+basis to optimality through the C ABI.  Metric = simplex iterations per second
+(BASELINE.json); time-to-optimal is ms_per_step.
+
+  value  problem resident in HBM when the timed region starts (only the basis
+         is reset between steps); timed on the device (CUDA events on the solve
+         stream, max over ranks).
+  e2e    the same metric through the public API with HOST buffers: handle
+         creation (pinned host -> device copy of the problem) + solve + solution
+         read-back, every step.
+  roofline  the kernel with the largest share of device time in an extra
+         profiled step (CUDA events around every launch on the solve stream).
+  cpu_baseline  the oracle (C++ port of the reference, 1 thread) on a bounded
+         sample (iteration limit) of the same LP, rank 0, N=1 only.
+
+Single LPs do not shard ("replicas only"): with --gpus N every rank
+solves its own replica and value is the aggregate.  Workloads: c2 = packing LP
+2048x4096, 20 % dense, primal simplex + projected steepest edge + Harris
+(BASELINE.json configs[1]); c3 = covering LP 16384x32768, ~16 nnz/col, dual
+simplex (configs[2]); c2s/c3s are 1/4-size versions for quick checks.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+WORKLOADS = {
+    "c2": dict(gen="packing", kw=dict(m=2048, n=4096, density=0.20, seed=20240501), meth="primal",
+               cpu_it_lim=600, name="packing LP m=2048 n=4096 20% dense, primal simplex, PSE pricing, Harris ratio test"),
+    "c3": dict(gen="covering", kw=dict(m=16384, n=32768, kmin=8, kspan=17, seed=20240601), meth="dual",
+               cpu_it_lim=1500, name="covering LP m=16384 n=32768 ~16 nnz/col, dual simplex, PSE pricing, Harris ratio test"),
+    "c2s": dict(gen="packing", kw=dict(m=512, n=1024, density=0.20, seed=20240501), meth="primal",
+                cpu_it_lim=600, name="packing LP m=512 n=1024 20% dense (quarter-size check)"),
+    "c3s": dict(gen="covering", kw=dict(m=4096, n=8192, kmin=8, kspan=17, seed=20240601), meth="dual",
+                cpu_it_lim=1500, name="covering LP m=4096 n=8192 (quarter-size check)"),
+}
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi SM clocks and throttle reasons while the timed region runs"""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
+                 "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i] == "Active"})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": reasons}
+
+
+def oracle_problem(d):
+    import oracle_lib as O
+    from helpers import to_oracle
+    return O, O.Problem.from_arrays(to_oracle(d))
+
+
+def meth_code(nat, w):
+    return nat.GLP_PRIMAL if w["meth"] == "primal" else nat.GLP_DUAL
+
+
+def run_reference(args, w, rank, world):
+    """--impl reference: the reference's own CPU implementation of the path.
+    The reference is JavaScript and no JS engine exists in this image, so this
+    arm times the oracle (C++ port, single thread like the reference)."""
+    if rank != 0:
+        return
+    import glpk_js_b200 as G
+    nat = G.native
+    d = nat.generate(w["gen"], **w["kw"])
+    O, _ = oracle_problem(d)
+    it_lim = w["cpu_it_lim"]
+    times, iters = [], []
+    for s in range(args.warmup + args.steps):
+        _, P = oracle_problem(d)
+        t0 = time.perf_counter()
+        P.simplex(meth=meth_code(O, w), it_lim=it_lim)
+        dt = time.perf_counter() - t0
+        if s >= args.warmup:
+            times.append(dt)
+            iters.append(P.solution()["it_cnt"])
+    val = sum(iters) / sum(times)
+    sample = "first %d iterations of the same LP from the standard basis (the full CPU solve takes minutes)" % it_lim
+    line = {"impl": "reference", "metric": "simplex_iterations_per_sec", "value": val, "unit": "iter/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1000.0 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": w["name"], **{k: v for k, v in w["kw"].items()}},
+            "cpu_baseline": {"value": val, "unit": "iter/s", "cores": 1, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "iter/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    w = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, w, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import glpk_js_b200 as G
+    nat = G.native
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    if nat.load().glpb_device_count() < 1:
+        raise SystemExit("bench.py: no CUDA device (there is no CPU fallback)")
+
+    d = nat.generate(w["gen"], **w["kw"])
+    m, n, nnz = d["m"], d["n"], len(d["A_val"])
+    meth = meth_code(nat, w)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def flush_l2():
+        flush_buf.fill_(1)
+        torch.cuda.synchronize()
+
+    # ---- resident leg: value ----
+    P = nat.Problem(d, device=local_rank)
+    sampler = ClockSampler(local_rank)
+    dev_ms, iters, launches0 = [], [], 0
+    for s in range(args.warmup + args.steps):
+        if s == args.warmup:
+            barrier()
+            sampler.start()
+            launches0 = P.counters()["launches"]
+            t_wall0 = time.perf_counter()
+        flush_l2()
+        P.std_basis()
+        rc = P.simplex(meth=meth)
+        c = P.counters()
+        if s >= args.warmup:
+            dev_ms.append(c["solve_us"] / 1000.0)
+            iters.append(P.solution()["it_cnt"])
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop()
+    cnt = P.counters()
+    launches = cnt["launches"] - launches0
+    sol = P.solution()
+    status, obj = sol["status"], sol["obj"]
+
+    my_ms = float(sum(dev_ms))
+    tot_it = float(sum(iters))
+    if world > 1:
+        t = torch.tensor([my_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        it = torch.tensor([tot_it], device="cuda", dtype=torch.float64)
+        dist.all_reduce(it, op=dist.ReduceOp.SUM)
+        max_ms, all_it = float(t.item()), float(it.item())
+    else:
+        max_ms, all_it = my_ms, tot_it
+    value = all_it / (max_ms / 1000.0)
+
+    # ---- profiled extra step: per-kernel device time (CUDA events on the solve stream) ----
+    P.std_basis()
+    P.set_profile(1)
+    P.simplex(meth=meth, it_lim=min(int(iters[-1]), 1500))
+    prof = P.profile()
+    P.set_profile(0)
+    tot_prof_ms = sum(v["ms"] for v in prof.values()) or 1.0
+    with_bytes = {k: v for k, v in prof.items() if v["bytes"] > 0}
+    top = max(with_bytes, key=lambda k: with_bytes[k]["ms"]) if with_bytes else None
+    peak, peak_src = peaks()
+    roofline = None
+    if top:
+        v = prof[top]
+        ach = (v["bytes"] / v["count"]) / (v["ms"] / v["count"] * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": top, "achieved": ach, "peak": peak, "unit": "GB/s",
+                    "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                    "bytes_per_launch": v["bytes"] / v["count"], "us_per_launch": 1000.0 * v["ms"] / v["count"],
+                    "share_of_device_time": v["ms"] / tot_prof_ms,
+                    "kernel_shares": {k: round(x["ms"] / tot_prof_ms, 4) for k, x in
+                                      sorted(prof.items(), key=lambda kv: -kv[1]["ms"])[:8]}}
+    P.close()
+
+    # ---- e2e leg: host buffers every step ----
+    pinned = {}
+    for k_, a in d.items():
+        if isinstance(a, np.ndarray):
+            t_ = torch.from_numpy(a.copy()).pin_memory()
+            pinned[k_] = t_.numpy()
+        else:
+            pinned[k_] = a
+    h2d = int(sum(a.nbytes for a in pinned.values() if isinstance(a, np.ndarray)))
+    d2h = (m + n) * (4 + 8 + 8) + m * 4 + 40
+    e2e_t, e2e_it = [], []
+    for s in range(args.warmup + args.steps):
+        if s == args.warmup:
+            barrier()
+        flush_l2()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        Q = nat.Problem(pinned, device=local_rank)
+        Q.simplex(meth=meth)
+        so = Q.solution()
+        dt = time.perf_counter() - t0
+        Q.close()
+        if s >= args.warmup:
+            e2e_t.append(dt)
+            e2e_it.append(so["it_cnt"])
+    barrier()
+    my_e2e = float(sum(e2e_t))
+    if world > 1:
+        t = torch.tensor([my_e2e], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        it = torch.tensor([float(sum(e2e_it))], device="cuda", dtype=torch.float64)
+        dist.all_reduce(it, op=dist.ReduceOp.SUM)
+        e2e_val = float(it.item()) / float(t.item())
+    else:
+        e2e_val = sum(e2e_it) / my_e2e
+
+    # ---- CPU baseline (rank 0, N=1 only): the oracle on a bounded sample ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        O, Pc = oracle_problem(d)
+        t0 = time.perf_counter()
+        Pc.simplex(meth=meth_code(O, w), it_lim=w["cpu_it_lim"])
+        dt = time.perf_counter() - t0
+        itc = Pc.solution()["it_cnt"]
+        cpu = {"value": itc / dt, "unit": "iter/s", "cores": 1, "kind": "port",
+               "sample": "first %d iterations of the same LP from the standard basis, %.1f s "
+                         "(C++ port of the reference; the JS reference cannot run here)" % (itc, dt)}
+
+    if rank == 0:
+        line = {"metric": "simplex_iterations_per_sec", "value": value, "unit": "iter/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": max_ms / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic",
+                "config": {"workload": w["name"], **w["kw"], "nnz": nnz, "step": "one full solve from the standard basis to optimality",
+                           "parallelism": "replicas only (a single LP does not shard)" if world > 1 else "1 GPU",
+                           "l2": "flushed between steps (256 MiB write); within a solve the working set is L2-resident by design"},
+                "clocks": clocks,
+                "e2e": {"value": e2e_val, "unit": "iter/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "ms_per_step": 1000.0 * my_e2e / args.steps},
+                "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+                "iterations_per_step": tot_it / args.steps, "time_to_optimal_ms": max_ms / args.steps,
+                "status": int(status), "objective": obj, "wall_s_timed_region": t_wall,
+                "refactorizations": cnt["refactorizations"], "kernel_size_k": cnt["k"]}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

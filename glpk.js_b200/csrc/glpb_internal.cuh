@@ -25,6 +25,7 @@
 #include <cfloat>
 #include <climits>
 #include <cstdint>
+#include <map>
 #include <string>
 #include <vector>
 #include "../../include/glpb200.h"
@@ -137,6 +138,14 @@ struct glpb_prob {
     long n_iter = 0, n_refac = 0, n_launch = 0, n_sync = 0, n_update = 0;
     double last_solve_us = 0.0;
     int trace = 0;
+    /* ---- optional per-kernel timing with CUDA events on the solve stream ---- */
+    struct ProfRec { const char *name; cudaEvent_t e0, e1; double bytes; };
+    struct ProfAcc { double ms = 0.0, bytes = 0.0; long count = 0; };
+    int prof = 0;
+    double next_bytes = 0.0;        /* algorithmic bytes of the next launch */
+    std::vector<ProfRec> prof_recs;
+    std::map<std::string, ProfAcc> prof_acc;
+    std::string prof_text;
 };
 
 void glpb_set_error(const char *fmt, ...);

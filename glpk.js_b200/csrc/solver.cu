@@ -32,9 +32,49 @@ static double now_ms()
     return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
 }
 
+#define PROF_MAX_RECS 400000
+
+static inline void prof_begin(glpb_prob *P, const char *name)
+{
+    if (!P->prof || P->prof_recs.size() >= PROF_MAX_RECS) return;
+    glpb_prob::ProfRec r;
+    r.name = name; r.bytes = P->next_bytes;
+    cudaEventCreate(&r.e0); cudaEventCreate(&r.e1);
+    cudaEventRecord(r.e0, P->stream);
+    P->prof_recs.push_back(r);
+}
+
+static inline void prof_end(glpb_prob *P)
+{
+    P->next_bytes = 0.0;
+    if (!P->prof || P->prof_recs.empty() || P->prof_recs.size() > PROF_MAX_RECS) return;
+    cudaEventRecord(P->prof_recs.back().e1, P->stream);
+}
+
+/* fold the recorded event pairs into per-kernel totals (after a sync) */
+static void prof_collect(glpb_prob *P)
+{
+    if (P->prof_recs.empty()) return;
+    cudaStreamSynchronize(P->stream);
+    for (auto &r : P->prof_recs) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess) {
+            std::string nm(r.name);
+            size_t lt = nm.find('<');
+            if (lt != std::string::npos) nm = nm.substr(0, lt);
+            auto &a = P->prof_acc[nm];
+            a.ms += ms; a.bytes += r.bytes; a.count++;
+        }
+        cudaEventDestroy(r.e0); cudaEventDestroy(r.e1);
+    }
+    P->prof_recs.clear();
+}
+
 #define LAUNCH(P, kern, grid, block, smem, ...)                                \
     do {                                                                       \
+        prof_begin((P), #kern);                                                \
         kern<<<(grid), (block), (smem), (P)->stream>>>(__VA_ARGS__);            \
+        prof_end(P);                                                           \
         (P)->n_launch++;                                                       \
     } while (0)
 
@@ -112,6 +152,7 @@ extern "C" void glpb_destroy(glpb_prob *P)
                     P->rslot, P->slot_pos, P->cslot, P->slot_row, P->gj_piv, P->gj_row, P->gj_col,
                     P->scratch, P->ctrl};
     for (void *p : ptrs) if (p) cudaFree(p);
+    P->prof = 0; prof_collect(P);
     if (P->h_ctrl) cudaFreeHost(P->h_ctrl);
     if (P->stream) cudaStreamDestroy(P->stream);
     delete P;
@@ -332,6 +373,7 @@ static void dev_ftran(Dev &D, const double *h, double *x)
         LAUNCH(P, k_gemvN_part, dim3(tl, tl), GEMV_TILE, 0, P->ctrl, P->T, P->ldt, h, P->slot_row, P->partial);
         LAUNCH(P, k_gemvN_fin, cdiv(D.k, 256), 256, 0, P->ctrl, P->ldt, P->partial, P->yk);
     }
+    P->next_bytes = 12.0 * P->nnz * (1.0 - (double)D.k / D.m) + 16.0 * D.m;
     GROUP_DISPATCH(D.gr, LAUNCH(P, k_ftran_tail<GG>, cdiv((long)D.m * GG, 256), 256, 0, P->ctrl, D.m,
                                 P->at_ptr, P->at_ind, P->at_val, P->head, P->bind, P->rslot, h, P->yk, x));
 }
@@ -343,6 +385,7 @@ static void dev_btran(Dev &D, const double *c, double *z)
     if (D.k > 0) {
         GROUP_DISPATCH(D.gc, LAUNCH(P, k_btran_head<GG>, cdiv((long)D.k * GG, 256), 256, 0, P->ctrl, D.m,
                                     P->a_ptr, P->a_ind, P->a_val, P->head, P->bind, P->slot_pos, c, P->wk));
+        P->next_bytes = 8.0 * D.k * (double)D.k;
         LAUNCH(P, k_gemvT, cdiv((long)D.k * 32, 256), 256, 0, P->ctrl, P->T, P->ldt, P->wk, P->yk);
     }
     LAUNCH(P, k_btran_tail, cdiv(D.m, 256), 256, 0, P->ctrl, D.m, P->cslot, P->bind, c, P->yk, z);
@@ -611,6 +654,7 @@ struct Loop : Dev {
     {
         if (k > 0) {
             dim3 grid(cdiv(k, UPD_TB), cdiv(k, UPD_TC));
+            P->next_bytes = 16.0 * k * (double)k;
             LAUNCH(P, k_update_rank1, grid, UPD_TB, 0, P->ctrl, P->T, P->ldt, P->tcol, P->rho, P->slot_pos, P->slot_row);
         }
         LAUNCH(P, k_update_fix, 1, 1024, 0, P->ctrl, m, P->T, P->ldt, P->tcol, P->rho, P->rslot, P->slot_pos,
@@ -645,6 +689,7 @@ struct Primal : Loop {
 
     void chuzc(int set_status)
     {
+        P->next_bytes = 17.0 * n;
         LAUNCH(P, k_chuzc_primal, grid1(n), 256, 0, P->ctrl, n, P->stat, P->cbar, P->gamma, parm.tol_dj,
                set_status, P->scratch);
     }
@@ -752,11 +797,14 @@ struct Primal : Loop {
             LAUNCH(P, k_primal_prep, grid1(m), 256, 0, P->ctrl, m, P->head, P->coef, P->tcol, P->refsp, P->cbar,
                    P->w3, parm.tol_piv, cbar_st == 1, rigorous, do_gamma, P->scratch);
             const double rtol = (parm.r_test == GLP_RT_STD ? 0.0 : 0.30 * parm.tol_bnd);
-            for (int pass = 1; pass <= 2; pass++)
+            for (int pass = 1; pass <= 2; pass++) {
+                P->next_bytes = 45.0 * m;
                 LAUNCH(P, k_ratio_primal, grid1(m), 256, 0, P->ctrl, pass, m, P->type, P->lb, P->ub, P->coef,
                        P->head, P->bbar, P->tcol, (const int *)nullptr, m, rtol, rigorous, P->scratch);
+            }
             eval_rho();
             if (do_gamma) dev_btran(*this, P->w3, P->w2);
+            P->next_bytes = 12.0 * P->nnz * (1.0 - (double)k / n) + 13.0 * n + 8.0 * m;
             GROUP_DISPATCH(gc, LAUNCH(P, k_trow<GG>, cdiv((long)n * GG, 256), 256, 0, P->ctrl, m, n, P->a_ptr,
                                       P->a_ind, P->a_val, P->head, P->stat, P->rho,
                                       do_gamma ? P->w2 : (const double *)nullptr, P->trow, P->svec, 0));
@@ -965,17 +1013,21 @@ struct Dual : Loop {
             /* ---- one iteration ---- */
             const int do_gamma = pse && refct > 0;
             clear_ctrl();
+            P->next_bytes = 37.0 * m;
             LAUNCH(P, k_chuzr_dual, grid1(m), 256, 0, P->ctrl, m, P->type, P->lb, P->ub, P->head, P->bbar,
                    P->gamma, parm.tol_bnd, 1, P->scratch);
             eval_rho();
+            P->next_bytes = 12.0 * P->nnz * (1.0 - (double)k / n) + 13.0 * n + 8.0 * m;
             GROUP_DISPATCH(gc, LAUNCH(P, k_trow<GG>, cdiv((long)n * GG, 256), 256, 0, P->ctrl, m, n, P->a_ptr,
                                       P->a_ind, P->a_val, P->head, P->stat, P->rho, (const double *)nullptr,
                                       P->trow, P->svec, 1));
             LAUNCH(P, k_dual_rowmax, 1, 1, 0, P->ctrl, parm.tol_bnd); /* sic: tol_bnd, lib/glpspx02.js:1851 */
             const double rtol = (parm.r_test == GLP_RT_STD ? 0.0 : 0.30 * parm.tol_dj);
-            for (int pass = 1; pass <= 2; pass++)
+            for (int pass = 1; pass <= 2; pass++) {
+                P->next_bytes = 17.0 * n;
                 LAUNCH(P, k_ratio_dual, grid1(n), 256, 0, P->ctrl, pass, P->stat, P->cbar, P->trow,
                        (const int *)nullptr, n, rtol, rigorous, P->scratch);
+            }
             eval_tcol();
             LAUNCH(P, k_dual_prep, grid1(n), 256, 0, P->ctrl, m, n, P->head, P->refsp, P->trow, P->tcol, P->cbar,
                    P->stat, P->zeta, binv_st == 1, rigorous, do_gamma, P->scratch);
@@ -1139,14 +1191,23 @@ extern "C" int glpb_simplex(glpb_prob *P, const glpb_smcp *parm_)
         rc = glpb_factorize(P);
         if (rc != 0) return rc;
     }
-    double t0 = now_ms();
+    /* device time of the whole solve: CUDA events on the solve stream */
+    cudaEvent_t ev0, ev1;
+    CK(cudaEventCreate(&ev0));
+    CK(cudaEventCreate(&ev1));
+    CK(cudaEventRecord(ev0, P->stream));
     int ret;
     if (parm.meth == GLP_PRIMAL) { Primal s(P, parm); ret = s.run(); }
     else {
         { Dual s(P, parm); ret = s.run(); }
         if (parm.meth == GLP_DUALP && ret == GLP_EFAIL && P->valid) { Primal s(P, parm); ret = s.run(); }
     }
-    P->last_solve_us = (now_ms() - t0) * 1000.0;
+    float ms = 0.f;
+    cudaEventRecord(ev1, P->stream);
+    cudaEventSynchronize(ev1);
+    cudaEventElapsedTime(&ms, ev0, ev1);
+    cudaEventDestroy(ev0); cudaEventDestroy(ev1);
+    P->last_solve_us = ms * 1000.0;
     return ret;
 }
 
@@ -1185,6 +1246,30 @@ extern "C" int glpb_get_counters(glpb_prob *P, long *out, int count)
                  (long)(P->h_ctrl ? P->h_ctrl->k : 0), (long)P->last_solve_us};
     for (int i = 0; i < count && i < 7; i++) out[i] = v[i];
     return 0;
+}
+
+/* per-kernel device time measured with CUDA events on the solve stream;
+   the report is text: one line "name count total_ms algorithmic_bytes" */
+extern "C" int glpb_set_profile(glpb_prob *P, int on)
+{
+    if (!P) return GLPB_EINVAL;
+    prof_collect(P);
+    P->prof = on;
+    if (on) P->prof_acc.clear();
+    return 0;
+}
+
+extern "C" const char *glpb_profile_report(glpb_prob *P)
+{
+    if (!P) return "";
+    prof_collect(P);
+    P->prof_text.clear();
+    char line[256];
+    for (auto &kv : P->prof_acc) {
+        snprintf(line, sizeof line, "%s %ld %.6f %.0f\n", kv.first.c_str(), kv.second.count, kv.second.ms, kv.second.bytes);
+        P->prof_text += line;
+    }
+    return P->prof_text.c_str();
 }
 
 /* bfd_ftran / bfd_btran on the current factorisation (scaled space) */

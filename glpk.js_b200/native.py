@@ -66,6 +66,7 @@ SYMBOLS = [
     "glpb_create", "glpb_destroy", "glpb_set_bounds", "glpb_set_basis", "glpb_std_basis",
     "glpb_set_bfcp", "glpb_set_it_cnt", "glpb_factorize", "glpb_simplex", "glpb_intopt",
     "glpb_get_solution", "glpb_get_status", "glpb_get_mip", "glpb_get_counters", "glpb_ftran",
+    "glpb_set_profile", "glpb_profile_report",
     "glpb_btran", "glpb_k_chuzc_primal", "glpb_k_chuzr_dual", "glpb_k_ratio_primal",
     "glpb_k_ratio_dual", "glpb_k_trow", "glpb_bench_kernel", "glpb_gen_packing",
     "glpb_gen_covering", "glpb_gen_mkp", "glpb_free_problem", "glpb_rng_fill",
@@ -112,6 +113,9 @@ def load():
     L.glpb_get_mip.argtypes = [vp] * 5
     L.glpb_get_counters.argtypes = [vp, vp, ci]
     L.glpb_ftran.argtypes = [vp, vp]
+    L.glpb_set_profile.argtypes = [vp, ci]
+    L.glpb_profile_report.argtypes = [vp]
+    L.glpb_profile_report.restype = C.c_char_p
     L.glpb_btran.argtypes = [vp, vp]
     L.glpb_k_chuzc_primal.argtypes = [ci, vp, vp, vp, cd, vp]
     L.glpb_k_chuzr_dual.argtypes = [ci, ci] + [vp] * 6 + [cd, vp, vp]
@@ -279,6 +283,17 @@ class Problem:
         self.L.glpb_get_counters(self.h, out, 7)
         keys = ["iterations", "refactorizations", "launches", "syncs", "updates", "k", "solve_us"]
         return {k: int(out[i]) for i, k in enumerate(keys)}
+
+    def set_profile(self, on):
+        self.L.glpb_set_profile(self.h, int(on))
+
+    def profile(self):
+        """{kernel: dict(count, ms, bytes)} from CUDA events on the solve stream"""
+        out = {}
+        for line in self.L.glpb_profile_report(self.h).decode().splitlines():
+            name, cnt, ms, nb = line.split()
+            out[name] = dict(count=int(cnt), ms=float(ms), bytes=float(nb))
+        return out
 
     def ftran(self, x):
         x = _f64(x).copy()

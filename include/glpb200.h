@@ -117,6 +117,12 @@ int glpb_get_mip(glpb_prob *P, int *mip_stat, double *mip_obj, double *mipx,
  * [5] current kernel size k, [6] device microseconds in the last solve. */
 int glpb_get_counters(glpb_prob *P, long *out, int count);
 
+/* Per-kernel device time, measured with CUDA events on the handle's stream
+ * (bench.py roofline leg).  The report is text, one line per kernel:
+ * "name launches total_ms algorithmic_bytes". */
+int glpb_set_profile(glpb_prob *P, int on);
+const char *glpb_profile_report(glpb_prob *P);
+
 /* Basis solves with the current factorisation, scaled space:
  * bfd_ftran / bfd_btran (lib/glpbfd.js:148-168); x is [m], in place. */
 int glpb_ftran(glpb_prob *P, double *x);
