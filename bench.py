@@ -194,11 +194,12 @@ def main():
             t_wall0 = time.perf_counter()
         flush_l2()
         P.std_basis()
+        it_before = P.solution()["it_cnt"]      # it_cnt accumulates per handle, like glp_prob.it_cnt
         rc = P.simplex(meth=meth)
         c = P.counters()
         if s >= args.warmup:
             dev_ms.append(c["solve_us"] / 1000.0)
-            iters.append(P.solution()["it_cnt"])
+            iters.append(P.solution()["it_cnt"] - it_before)
     barrier()
     t_wall = time.perf_counter() - t_wall0
     clocks = sampler.stop()
