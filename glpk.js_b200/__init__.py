@@ -19,5 +19,6 @@ CUDA library is present and a device is visible.
 from . import native  # noqa: F401
 from .native import LIB_PATH, load, build  # noqa: F401
 from . import glpk  # noqa: F401
+from . import bnb  # noqa: F401
 
 __all__ = ["native", "glpk", "load", "build", "LIB_PATH"]

@@ -1,0 +1,228 @@
+"""Node-sharded branch-and-bound across the GPUs of one box.
+
+A single LP never spans GPUs; the only part of the path that shards is the
+``ios_driver`` search (lib/glpios03.js:507-951): open nodes are independent
+units.  Every rank owns a device-resident copy of the problem and a local pool
+of open nodes (``glpb_mip_*`` in the C ABI).  The search proceeds in rounds:
+
+1. every rank solves up to ``slice`` node LPs from its own pool;
+2. incumbent exchange: all-reduce (min or max) of the best objective, applied
+   as a cut-off on the ranks that did not find it;
+3. load balancing: pool sizes are all-gathered, every rank derives the same
+   transfer plan, donors export self-contained node records and one padded
+   all-gather moves them (records are ~18(m+n) bytes, so this is latency- not
+   bandwidth-bound even over NCCL/NVLink);
+4. termination when every pool is empty.
+
+Ramp-up is replicated: all ranks run the identical deterministic search until
+there are enough open nodes, then keep every ``world``-th one.  The explored
+tree differs from the serial one, the optimum (an objective *value*) does not.
+
+The communicator is abstract so that the logic runs under ``torch.distributed``
+(NCCL on GPUs, gloo in CPU tests) or in-process (``LocalGroup``) for tests that
+emulate several ranks on one device.
+"""
+import numpy as np
+
+from . import native
+
+MAX_SHIP = 16        # node records a donor ships per round
+
+
+class TorchComm:
+    """torch.distributed adapter (backend nccl on GPUs, gloo on CPU)."""
+
+    def __init__(self, device=None):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.device = device if device is not None else (
+            torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu"))
+
+    def allreduce(self, value, op):
+        t = self.torch.tensor([value], dtype=self.torch.float64, device=self.device)
+        self.dist.all_reduce(t, op={"min": self.dist.ReduceOp.MIN, "max": self.dist.ReduceOp.MAX,
+                                    "sum": self.dist.ReduceOp.SUM}[op])
+        return float(t.item())
+
+    def allgather_ints(self, values):
+        t = self.torch.tensor(list(values), dtype=self.torch.int64, device=self.device)
+        out = [self.torch.empty_like(t) for _ in range(self.world)]
+        self.dist.all_gather(out, t)
+        return [[int(v) for v in o.tolist()] for o in out]
+
+    def allgather_bytes(self, buf, nbytes):
+        t = self.torch.zeros(nbytes, dtype=self.torch.uint8, device=self.device)
+        if len(buf):
+            t[:len(buf)] = self.torch.from_numpy(np.ascontiguousarray(buf)).to(self.device)
+        out = [self.torch.empty_like(t) for _ in range(self.world)]
+        self.dist.all_gather(out, t)
+        return [o.cpu().numpy() for o in out]
+
+
+def transfer_plan(counts, low=1, max_ship=MAX_SHIP):
+    """Deterministic donor -> receiver plan from the gathered pool sizes.
+    Returns {donor: (receiver, n)}; a rank takes part in one transfer a round."""
+    order = sorted(range(len(counts)), key=lambda r: (counts[r], r))
+    plan, lo, hi = {}, 0, len(order) - 1
+    counts = list(counts)
+    while lo < hi:
+        poor, rich = order[lo], order[hi]
+        if counts[poor] > low or counts[rich] - counts[poor] < 2:
+            break
+        n = min(max_ship, (counts[rich] - counts[poor]) // 2)
+        if n > 0:
+            plan[rich] = (poor, n)
+        lo += 1
+        hi -= 1
+    return plan
+
+
+class Worker:
+    """What the driver needs from a rank; the GPU implementation wraps a
+    ``native.Problem``, tests substitute a fake."""
+
+    def __init__(self, prob):
+        self.P = prob
+
+    def begin(self, **iocp):
+        return self.P.mip_begin(**iocp)
+
+    def run(self, max_nodes):
+        return self.P.mip_run(max_nodes)
+
+    def incumbent(self):
+        return self.P.mip_incumbent()
+
+    def set_cutoff(self, obj):
+        self.P.mip_set_cutoff(obj)
+
+    def open_count(self):
+        return self.P.mip_open_count()
+
+    def record_bytes(self):
+        return self.P.L.glpb_mip_record_bytes(self.P.h)
+
+    def export(self, n):
+        return self.P.mip_export(n)
+
+    def import_(self, buf, n):
+        self.P.mip_import(buf, n)
+
+    def end(self, ret):
+        return self.P.mip_end(ret)
+
+    def solution(self):
+        return self.P.mip()
+
+
+def sharded_intopt(worker, comm, minimize, slice_nodes=64, ramp_nodes=None, node_lim=None, **iocp):
+    """Run the sharded search on this rank.  Returns a dict with the global
+    optimum, who holds the solution, node counts and the per-round log."""
+    rank, world = comm.rank, comm.world
+    rc = worker.begin(**iocp)
+    if rc != 0:
+        return dict(ret=rc, obj=None, nodes=0, total_nodes=0, rounds=0)
+    rb = worker.record_bytes()
+    inf = float("inf")
+    my_nodes, rounds, ret = 0, 0, 0
+    # ---- replicated ramp-up ----
+    if world > 1:
+        want = ramp_nodes if ramp_nodes is not None else 4 * world
+        state = 1
+        while state == 1 and worker.open_count() < want:
+            state, solved = worker.run(1)
+            my_nodes += solved
+        if state > 1:
+            ret = state
+        if worker.open_count() > 0 and ret == 0:
+            buf, cnt = worker.export(-(1 << 20))          # pop every open node (same list on all ranks)
+            keep = [i for i in range(cnt) if i % world == rank]
+            if keep:
+                rec = np.concatenate([buf[i * rb:(i + 1) * rb] for i in keep])
+                worker.import_(rec, len(keep))
+        ramp = my_nodes
+    else:
+        ramp = 0
+    # ---- sharded rounds ----
+    while ret == 0:
+        rounds += 1
+        budget = slice_nodes
+        if node_lim is not None:
+            budget = max(0, min(budget, node_lim - my_nodes))
+        state, solved = worker.run(budget) if budget > 0 else (1, 0)
+        my_nodes += solved
+        if state > 1:
+            ret = state
+        has, obj = worker.incumbent()
+        key = obj if minimize else -obj
+        best = comm.allreduce(key if obj not in (inf, -inf) and abs(obj) < 1e300 else inf, "min")
+        if best < inf:
+            worker.set_cutoff(best if minimize else -best)
+        stop = comm.allreduce(float(ret != 0 or (node_lim is not None and my_nodes >= node_lim)), "max")
+        counts = [c[0] for c in comm.allgather_ints([worker.open_count()])]
+        if stop > 0 or sum(counts) == 0:
+            break
+        plan = transfer_plan(counts)
+        ship, dst, n = np.zeros(0, np.uint8), -1, 0
+        if rank in plan:
+            dst, want_n = plan[rank]
+            ship, n = worker.export(want_n)
+        meta = comm.allgather_ints([dst, n])
+        if any(mm[1] > 0 for mm in meta):
+            bufs = comm.allgather_bytes(ship, MAX_SHIP * rb)
+            for src, (d, cnt) in enumerate(meta):
+                if d == rank and cnt > 0:
+                    worker.import_(bufs[src][:cnt * rb], cnt)
+    # ---- wrap up: global optimum and its holder ----
+    has, obj = worker.incumbent()
+    key = (obj if minimize else -obj) if abs(obj) < 1e300 else inf
+    best = comm.allreduce(key, "min")
+    holder = comm.allreduce(float(rank) if (has and key == best) else float(world), "min")
+    total = comm.allreduce(float(my_nodes), "sum")
+    any_err = comm.allreduce(float(ret), "max")
+    worker.end(int(any_err))
+    return dict(ret=int(any_err), obj=(None if best == inf else (best if minimize else -best)),
+                holder=(int(holder) if holder < world else None), nodes=my_nodes,
+                total_nodes=int(total) - ramp * (world - 1), rounds=rounds, ramp_nodes=ramp)
+
+
+# ---- in-process emulation of several ranks (tests; one GPU or none) ----
+class LocalGroup:
+    """Runs ``world`` drivers as cooperative threads with barrier-style
+    collectives, so the N>1 protocol can be exercised without N devices."""
+
+    def __init__(self, world):
+        import threading
+        self.world = world
+        self.barrier = threading.Barrier(world)
+        self.slots = [None] * world
+        self.lock = threading.Lock()
+
+    def comm(self, rank):
+        return _LocalComm(self, rank)
+
+
+class _LocalComm:
+    def __init__(self, group, rank):
+        self.g, self.rank, self.world = group, rank, group.world
+
+    def _exchange(self, value):
+        self.g.slots[self.rank] = value
+        self.g.barrier.wait()
+        out = list(self.g.slots)
+        self.g.barrier.wait()
+        return out
+
+    def allreduce(self, value, op):
+        vals = self._exchange(value)
+        return {"min": min, "max": max, "sum": sum}[op](vals)
+
+    def allgather_ints(self, values):
+        return self._exchange(list(values))
+
+    def allgather_bytes(self, buf, nbytes):
+        b = np.zeros(nbytes, np.uint8)
+        b[:len(buf)] = buf
+        return self._exchange(b)

@@ -89,6 +89,9 @@ struct Key {
     int pos, aux;
 };
 
+struct glpb_mip;
+void glpb_mip_free(glpb_mip *T);
+
 struct glpb_prob {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -146,6 +149,7 @@ struct glpb_prob {
     std::vector<ProfRec> prof_recs;
     std::map<std::string, ProfAcc> prof_acc;
     std::string prof_text;
+    glpb_mip *mip = nullptr;       /* branch-and-bound tree while glp_intopt runs */
 };
 
 void glpb_set_error(const char *fmt, ...);

@@ -153,6 +153,7 @@ extern "C" void glpb_destroy(glpb_prob *P)
                     P->scratch, P->ctrl};
     for (void *p : ptrs) if (p) cudaFree(p);
     P->prof = 0; prof_collect(P);
+    if (P->mip) { glpb_mip_free(P->mip); P->mip = nullptr; }
     if (P->h_ctrl) cudaFreeHost(P->h_ctrl);
     if (P->stream) cudaStreamDestroy(P->stream);
     delete P;

@@ -67,6 +67,8 @@ SYMBOLS = [
     "glpb_set_bfcp", "glpb_set_it_cnt", "glpb_factorize", "glpb_simplex", "glpb_intopt",
     "glpb_get_solution", "glpb_get_status", "glpb_get_mip", "glpb_get_counters", "glpb_ftran",
     "glpb_set_profile", "glpb_profile_report",
+    "glpb_mip_begin", "glpb_mip_run", "glpb_mip_get_incumbent", "glpb_mip_set_cutoff", "glpb_mip_open_count",
+    "glpb_mip_record_bytes", "glpb_mip_export_nodes", "glpb_mip_import_nodes", "glpb_mip_end",
     "glpb_btran", "glpb_k_chuzc_primal", "glpb_k_chuzr_dual", "glpb_k_ratio_primal",
     "glpb_k_ratio_dual", "glpb_k_trow", "glpb_bench_kernel", "glpb_gen_packing",
     "glpb_gen_covering", "glpb_gen_mkp", "glpb_free_problem", "glpb_rng_fill",
@@ -117,6 +119,16 @@ def load():
     L.glpb_profile_report.argtypes = [vp]
     L.glpb_profile_report.restype = C.c_char_p
     L.glpb_btran.argtypes = [vp, vp]
+    L.glpb_mip_begin.argtypes = [vp, vp]
+    L.glpb_mip_run.argtypes = [vp, C.c_long, vp]
+    L.glpb_mip_get_incumbent.argtypes = [vp, vp, vp]
+    L.glpb_mip_set_cutoff.argtypes = [vp, cd]
+    L.glpb_mip_open_count.argtypes = [vp]
+    L.glpb_mip_record_bytes.argtypes = [vp]
+    L.glpb_mip_record_bytes.restype = C.c_long
+    L.glpb_mip_export_nodes.argtypes = [vp, ci, vp, C.c_long, vp]
+    L.glpb_mip_import_nodes.argtypes = [vp, vp, ci]
+    L.glpb_mip_end.argtypes = [vp, ci]
     L.glpb_k_chuzc_primal.argtypes = [ci, vp, vp, vp, cd, vp]
     L.glpb_k_chuzr_dual.argtypes = [ci, ci] + [vp] * 6 + [cd, vp, vp]
     L.glpb_k_ratio_primal.argtypes = [ci, ci] + [vp] * 5 + [ci, vp, cd, ci, vp, vp, ci, cd, vp, vp, vp]
@@ -277,6 +289,50 @@ class Problem:
         x = np.zeros(self.m + self.n)
         self.L.glpb_get_mip(self.h, C.byref(st), C.byref(obj), _p(x), C.byref(nodes))
         return dict(mip_stat=st.value, mip_obj=obj.value, mipx=x, nodes=nodes.value)
+
+    # ---- resumable branch-and-bound (multi-GPU node sharding) ----
+    def mip_begin(self, parm=None, **kw):
+        if parm is None:
+            parm = self.iocp(**kw)
+        return self.L.glpb_mip_begin(self.h, C.byref(parm))
+
+    def mip_run(self, max_nodes=-1):
+        solved = C.c_long()
+        rc = self.L.glpb_mip_run(self.h, max_nodes, C.byref(solved))
+        if rc < 0:
+            raise RuntimeError("glpb_mip_run failed (%d): %s" % (rc, last_error()))
+        return rc, solved.value
+
+    def mip_incumbent(self):
+        has = C.c_int()
+        obj = C.c_double()
+        self.L.glpb_mip_get_incumbent(self.h, C.byref(has), C.byref(obj))
+        return bool(has.value), obj.value
+
+    def mip_set_cutoff(self, obj):
+        return self.L.glpb_mip_set_cutoff(self.h, float(obj))
+
+    def mip_open_count(self):
+        return self.L.glpb_mip_open_count(self.h)
+
+    def mip_export(self, max_count):
+        rb = self.L.glpb_mip_record_bytes(self.h)
+        room = max_count if max_count > 0 else self.mip_open_count()
+        buf = np.zeros(max(1, room) * rb, np.uint8)
+        cnt = C.c_int()
+        rc = self.L.glpb_mip_export_nodes(self.h, max_count, _p(buf), buf.nbytes, C.byref(cnt))
+        if rc != 0:
+            raise RuntimeError("glpb_mip_export_nodes failed (%d)" % rc)
+        return buf[:cnt.value * rb], cnt.value
+
+    def mip_import(self, buf, count):
+        buf = np.ascontiguousarray(buf, dtype=np.uint8)
+        rc = self.L.glpb_mip_import_nodes(self.h, _p(buf), int(count))
+        if rc != 0:
+            raise RuntimeError("glpb_mip_import_nodes failed (%d)" % rc)
+
+    def mip_end(self, ret=0):
+        return self.L.glpb_mip_end(self.h, int(ret))
 
     def counters(self):
         out = (C.c_long * 7)()

@@ -112,6 +112,22 @@ int glpb_get_status(glpb_prob *P);                   /* api06:398-427 */
 int glpb_get_mip(glpb_prob *P, int *mip_stat, double *mip_obj, double *mipx,
                  long *nodes);
 
+/* Resumable branch-and-bound for multi-GPU node sharding.
+ * glpb_intopt == begin + run(-1) + end.  Between slices a host exchanges the
+ * incumbent objective and migrates open nodes between ranks; a node record is
+ * self-contained (glpb_mip_record_bytes bytes: bound, lp_obj, level and the
+ * complete type/stat/lb/ub vectors).
+ *   run:  0 = local pool exhausted, 1 = slice limit reached, GLP_E* = stopped */
+int glpb_mip_begin(glpb_prob *P, const glpb_iocp *parm);
+int glpb_mip_run(glpb_prob *P, long max_nodes, long *solved);
+int glpb_mip_get_incumbent(glpb_prob *P, int *has_solution, double *obj);
+int glpb_mip_set_cutoff(glpb_prob *P, double obj);
+int glpb_mip_open_count(glpb_prob *P);
+long glpb_mip_record_bytes(glpb_prob *P);
+int glpb_mip_export_nodes(glpb_prob *P, int max_count, void *buf, long cap, int *count);
+int glpb_mip_import_nodes(glpb_prob *P, const void *buf, int count);
+int glpb_mip_end(glpb_prob *P, int ret);
+
 /* Counters for measurement: out[0] iterations, [1] refactorisations,
  * [2] kernel launches, [3] host<->device syncs, [4] basis updates,
  * [5] current kernel size k, [6] device microseconds in the last solve. */

@@ -1,0 +1,131 @@
+"""GPU parity tests of the branch-and-bound row (glp_intopt): identical MIP
+optimum and status as the oracle and the HiGHS pins, through the C ABI and the
+facade; resumable slices; node migration between two emulated ranks."""
+import threading
+
+import numpy as np
+import pytest
+
+import glpk_js_b200 as G
+import oracle_lib as O
+import helpers as H
+
+nat, glpk, bnb = G.native, G.glpk, G.bnb
+pytestmark = pytest.mark.gpu
+
+
+def oracle_mip(dn, **kw):
+    Q = O.Problem.from_arrays(H.to_oracle(dn))
+    assert Q.simplex(meth=O.GLP_PRIMAL) == 0
+    ret = Q.intopt(**kw)
+    return ret, Q.mip()
+
+
+@pytest.mark.parametrize("name", ["gap", "todd"])
+def test_fixture_mip_optimum(name):
+    d = H.load_golden(name)
+    dn = H.to_native(d)
+    P = nat.Problem(dn)
+    assert P.simplex(meth=nat.GLP_PRIMAL) == 0
+    assert P.intopt() == 0
+    mp = P.mip()
+    oret, omp = oracle_mip(dn)
+    assert oret == 0 and mp["mip_stat"] == omp["mip_stat"] == nat.GLP_OPT
+    assert mp["mip_obj"] == omp["mip_obj"] == d["highs_mip_obj"]
+    x = mp["mipx"][dn["m"]:]
+    assert np.all(x == np.round(x))
+    assert abs(float(dn["coef"] @ x) + dn["c0"] - mp["mip_obj"]) < 1e-9
+    ax = H.spmv(dn, x)
+    np.testing.assert_allclose(ax, mp["mipx"][:dn["m"]], atol=1e-9)
+    assert mp["nodes"] > 0
+    # the LP relaxation is restored afterwards (ios_delete_tree)
+    assert abs(P.solution()["obj"] - d["highs_lp_obj"]) <= 1e-9 * abs(d["highs_lp_obj"])
+    P.close()
+
+
+@pytest.mark.parametrize("br,bt", [(nat.GLP_BR_DTH, nat.GLP_BT_BLB), (nat.GLP_BR_MFV, nat.GLP_BT_DFS),
+                                   (nat.GLP_BR_FFV, nat.GLP_BT_BFS), (nat.GLP_BR_LFV, nat.GLP_BT_BPH)])
+def test_small_knapsack_all_branching_rules(br, bt):
+    dn = nat.generate("mkp", m=5, n=30, seed=20240701)
+    P = nat.Problem(dn)
+    assert P.simplex(meth=nat.GLP_PRIMAL) == 0
+    assert P.intopt(br_tech=br, bt_tech=bt) == 0
+    oret, omp = oracle_mip(dn, br_tech=br, bt_tech=bt)
+    assert oret == 0 and P.mip()["mip_stat"] == nat.GLP_OPT
+    assert P.mip()["mip_obj"] == omp["mip_obj"]
+    P.close()
+
+
+def test_root_must_be_optimal_and_infeasible_mip():
+    dn = H.to_native(H.load_golden("gap"))
+    P = nat.Problem(dn)
+    assert P.intopt() == nat.GLP_EROOT              # lib/glpapi09.js:67-72
+    P.close()
+    lp = glpk.glp_create_prob()
+    txt = "Maximize\n obj: x + y\nSubject To\n c: 2 x + 2 y = 3\nBounds\n x <= 1\n y <= 1\nGeneral\n x y\nEnd\n"
+    assert glpk.glp_read_lp_from_string(lp, None, txt) == 0
+    s = glpk.SMCP()
+    s.msg_lev = glpk.GLP_MSG_OFF
+    assert glpk.glp_simplex(lp, s) == 0
+    io = glpk.IOCP()
+    io.msg_lev = glpk.GLP_MSG_OFF
+    assert glpk.glp_intopt(lp, io) == 0
+    assert glpk.glp_mip_status(lp) == glpk.GLP_NOFEAS
+    Q = O.Problem.from_lp(txt)
+    Q.simplex(meth=O.GLP_PRIMAL)
+    assert Q.intopt() == 0 and Q.mip()["mip_stat"] == O.GLP_NOFEAS
+
+
+def test_facade_flow_of_reference_test_js_on_gap():
+    lp = glpk.glp_create_prob()
+    assert glpk.glp_read_lp_from_string(lp, None, H.golden_text("gap")) == 0
+    smcp = glpk.SMCP({"presolve": glpk.GLP_ON})
+    smcp.msg_lev = glpk.GLP_MSG_OFF
+    smcp.presolve = glpk.GLP_OFF
+    assert glpk.glp_simplex(lp, smcp) == 0
+    iocp = glpk.IOCP({"presolve": glpk.GLP_ON})
+    iocp.msg_lev = glpk.GLP_MSG_OFF
+    assert glpk.glp_intopt(lp, iocp) == 0
+    assert glpk.glp_mip_status(lp) == glpk.GLP_OPT and glpk.glp_mip_obj_val(lp) == 261.0
+    cols = [glpk.glp_mip_col_val(lp, j) for j in range(1, glpk.glp_get_num_cols(lp) + 1)]
+    assert all(v in (0.0, 1.0) for v in cols) and sum(cols) == 15.0
+
+
+def test_slices_resume_to_the_same_optimum():
+    dn = H.to_native(H.load_golden("todd"))
+    P = nat.Problem(dn)
+    assert P.simplex(meth=nat.GLP_PRIMAL) == 0
+    assert P.mip_begin() == 0
+    total, state = 0, 1
+    while state == 1:
+        state, solved = P.mip_run(50)
+        total += solved
+    assert state == 0 and P.mip_end(0) == 0
+    assert P.mip()["mip_obj"] == 4190215.0 and P.mip()["mip_stat"] == nat.GLP_OPT and total == P.mip()["nodes"]
+    P.close()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_node_sharding_emulated_ranks_same_optimum(world):
+    """several ranks emulated as threads on one GPU, each with its own handle;
+    nodes really migrate through export/import records"""
+    dn = H.to_native(H.load_golden("todd"))
+    group = bnb.LocalGroup(world)
+    results = [None] * world
+    probs = []
+    for r in range(world):
+        P = nat.Problem(dn)
+        assert P.simplex(meth=nat.GLP_PRIMAL) == 0
+        probs.append(P)
+
+    def body(rank):
+        results[rank] = bnb.sharded_intopt(bnb.Worker(probs[rank]), group.comm(rank), minimize=False, slice_nodes=40)
+    ts = [threading.Thread(target=body, args=(r,)) for r in range(world)]
+    [t.start() for t in ts]
+    [t.join(600) for t in ts]
+    assert all(r is not None and r["ret"] == 0 for r in results), results
+    assert all(r["obj"] == 4190215.0 for r in results)
+    holder = results[0]["holder"]
+    assert holder is not None and probs[holder].mip()["mip_obj"] == 4190215.0
+    assert sum(r["nodes"] > r["ramp_nodes"] for r in results) >= 2
+    [P.close() for P in probs]
