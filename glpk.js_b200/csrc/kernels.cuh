@@ -672,6 +672,54 @@ __global__ void k_gemvT(Ctrl *ctrl, const double *__restrict__ T, int ldt,
 
 /* rho = row p of inv(B) (eval_rho, lib/glpspx01.js:1030-1042) read straight
    out of T instead of a BTRAN of e_p */
+/* Fast form: row p of inv(B) restricted to R_N is T' w with
+       w = e_b                       (a structural variable leaves)
+       w[b] = A[kp, j_b]             (the auxiliary variable of row kp leaves)
+   Every block rebuilds the sparse w in shared memory (zero + scatter of one
+   CSR row), then each warp owns one column of T: coalesced dot products
+   instead of a per-thread walk of the CSR row.  Rows whose auxiliary variable
+   is basic are unit entries.  Dynamic shared memory: k doubles.
+   Algorithmic bytes: 8 k^2 + 12 rowlen + 12 m. */
+__global__ void k_rho_fast(Ctrl *ctrl, int m, const double *__restrict__ T, int ldt,
+                           const int *__restrict__ at_ptr, const int *__restrict__ at_ind,
+                           const double *__restrict__ at_val, const int *__restrict__ head,
+                           const int *__restrict__ bind, const int *__restrict__ rslot,
+                           const int *__restrict__ cslot, const int *__restrict__ slot_row,
+                           double *__restrict__ rho)
+{
+    extern __shared__ double w[];
+    if (ctrl->status != ST_OK) return;
+    const int p = ctrl->p;
+    if (p < 0) return;
+    const int k = ctrl->k;
+    const int kp = head[p];
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int gid = blockIdx.x * nt + tid;
+    if (gid < m && cslot[gid] < 0) rho[gid] = (bind[gid] == p) ? 1.0 : 0.0;
+    if ((int)((blockIdx.x * nt) >> 5) >= k) return;      /* no column for this block */
+    for (int b = tid; b < k; b += nt) w[b] = 0.0;
+    __syncthreads();
+    if (kp >= m) { if (tid == 0) w[rslot[p]] = 1.0; }
+    else
+        for (int ptr = at_ptr[kp] + tid; ptr < at_ptr[kp + 1]; ptr += nt) {
+            int pb = bind[m + at_ind[ptr]];
+            if (pb < m) w[rslot[pb]] = at_val[ptr];
+        }
+    __syncthreads();
+    const int cs = gid >> 5, lane = tid & 31;
+    if (cs >= k) return;
+    const double *col = T + (size_t)cs * ldt;
+    double acc = 0.0;
+    for (int b = lane; b < k; b += 32) {
+        double wb = w[b];
+        if (wb != 0.0) acc += col[b] * wb;
+    }
+    acc = group_sum<32>(acc);
+    if (lane == 0) rho[slot_row[cs]] = acc;
+}
+
+/* reference form (one thread per row, sequential walk); kept for kernels
+   larger than the shared-memory budget of k_rho_fast */
 __global__ void k_rho(Ctrl *ctrl, int m, const double *__restrict__ T, int ldt,
                       const int *__restrict__ at_ptr, const int *__restrict__ at_ind,
                       const double *__restrict__ at_val, const int *__restrict__ head,
@@ -945,6 +993,126 @@ __global__ void k_gj_update(Ctrl *ctrl, int t, double *__restrict__ X, int ldt,
         if (i == t) *e = rs[c];
         else if (cc == t) *e = -f * rs[c];
         else *e -= f * rs[c];
+    }
+}
+
+/* ---- blocked Gauss-Jordan: GJ_NB pivots per round, three launches ----------
+   Round over panel columns [c0, c0+nb):
+   1. k_bgj_panel (one CTA): the nb Gauss-Jordan steps (partial pivoting, row
+      swaps, elimination) restricted to the panel columns.  Afterwards the
+      panel holds its final in-place values Pf = G E_P, G = G_nb ... G_1.
+   2. k_bgj_swap: the same row swaps on every other column, and a copy of
+      their pivot-row entries  Xp[t, c] = X[c0+t, c].
+   3. k_bgj_update: G x = x_notP + Pf x_P for every other column, i.e. a
+      rank-nb update  X[i,c] = (i in P ? 0 : X[i,c]) + sum_t Pf[i,t] Xp[t,c].
+   Memory traffic per round is one read+write of X instead of nb of them. */
+#define GJ_NB 32
+
+__global__ void k_bgj_panel(Ctrl *ctrl, int c0, double *__restrict__ X, int ldt,
+                            int *__restrict__ piv, double *__restrict__ rowt,
+                            double *__restrict__ colt)
+{
+    if (ctrl->sing) return;
+    const int k = ctrl->k;
+    if (c0 >= k) return;
+    const int nb = min(GJ_NB, k - c0);
+    const int tid = threadIdx.x, nt = blockDim.x;
+    __shared__ int s_r;
+    __shared__ double s_ipv;
+    __shared__ double s_row[GJ_NB];
+    for (int t = c0; t < c0 + nb; t++) {
+        double *ct = X + (size_t)t * ldt;
+        Key none = {-1.0, 0.0, 0.0, INT_MAX, 0};
+        Key v = none;
+        for (int i = t + tid; i < k; i += nt) {
+            Key c = {fabs(ct[i]), 0.0, 0.0, i, 0};
+            CombArgMax()(v, c);
+        }
+        v = block_reduce(v, none, CombArgMax());
+        if (tid == 0) {
+            s_r = v.pos;
+            piv[t] = v.pos;
+            if (!(v.a > 1e-13 * fmax(ctrl->max_a, 1e-300))) { ctrl->sing = 1; s_r = -1; }
+        }
+        __syncthreads();
+        const int r = s_r;
+        if (r < 0) return;
+        if (r != t && tid < nb) {
+            double *pc = X + (size_t)(c0 + tid) * ldt;
+            double a = pc[t], b = pc[r];
+            pc[t] = b; pc[r] = a;
+        }
+        __syncthreads();
+        if (tid == 0) s_ipv = 1.0 / ct[t];
+        __syncthreads();
+        const double ipv = s_ipv;
+        if (tid < nb) {
+            int c = c0 + tid;
+            s_row[tid] = (c == t) ? ipv : X[(size_t)c * ldt + t] * ipv;
+        }
+        for (int i = tid; i < k; i += nt) colt[i] = ct[i];
+        __syncthreads();
+        for (int e = tid; e < k * nb; e += nt) {
+            const int i = e % k, cc = e / k, c = c0 + cc;
+            double *x = X + (size_t)c * ldt + i;
+            const double f = colt[i];
+            if (i == t) *x = s_row[cc];
+            else if (c == t) *x = -f * s_row[cc];
+            else *x -= f * s_row[cc];
+        }
+        __syncthreads();
+    }
+}
+
+/* one thread per non-panel column: apply the round's row swaps in order and
+   save the pivot-row entries */
+__global__ void k_bgj_swap(Ctrl *ctrl, int c0, double *__restrict__ X, int ldt,
+                           const int *__restrict__ piv, double *__restrict__ Xp)
+{
+    if (ctrl->sing) return;
+    const int k = ctrl->k;
+    if (c0 >= k) return;
+    const int nb = min(GJ_NB, k - c0);
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= k || (c >= c0 && c < c0 + nb)) return;
+    double *col = X + (size_t)c * ldt;
+    for (int t = 0; t < nb; t++) {
+        int r = piv[c0 + t];
+        if (r != c0 + t) { double a = col[c0 + t]; col[c0 + t] = col[r]; col[r] = a; }
+    }
+    for (int t = 0; t < nb; t++) Xp[(size_t)t * ldt + c] = col[c0 + t];
+}
+
+__global__ void k_bgj_update(Ctrl *ctrl, int c0, double *__restrict__ X, int ldt,
+                             const double *__restrict__ Xp)
+{
+    if (ctrl->sing) return;
+    const int k = ctrl->k;
+    if (c0 >= k) return;
+    const int nb = min(GJ_NB, k - c0);
+    const int i = blockIdx.x * UPD_TB + threadIdx.x;
+    const int cc0 = blockIdx.y * UPD_TC;
+    if (cc0 >= k) return;
+    __shared__ double xs[GJ_NB][UPD_TC];
+    const int cn = min(UPD_TC, k - cc0);
+    for (int e = threadIdx.x; e < GJ_NB * UPD_TC; e += blockDim.x) {
+        int t = e / UPD_TC, c = e % UPD_TC;
+        xs[t][c] = (t < nb && c < cn) ? Xp[(size_t)t * ldt + cc0 + c] : 0.0;
+    }
+    __syncthreads();
+    if (i >= k) return;
+    double pf[GJ_NB];
+#pragma unroll
+    for (int t = 0; t < GJ_NB; t++) pf[t] = (t < nb) ? X[(size_t)(c0 + t) * ldt + i] : 0.0;
+    const bool in_p = (i >= c0 && i < c0 + nb);
+    for (int c = 0; c < cn; c++) {
+        const int col = cc0 + c;
+        if (col >= c0 && col < c0 + nb) continue;     /* panel columns are final */
+        double *x = X + (size_t)col * ldt + i;
+        double acc = in_p ? 0.0 : *x;
+#pragma unroll
+        for (int t = 0; t < GJ_NB; t++) acc += pf[t] * xs[t][c];
+        *x = acc;
     }
 }
 

@@ -261,8 +261,7 @@ struct glpb_mip {
         Dev D(P);
         LAUNCH(P, k_clear_ctrl, 1, 1, 0, P->ctrl, 2);
         CK(cudaMemcpyAsync(&P->ctrl->p, &pos, sizeof(int), cudaMemcpyHostToDevice, P->stream));
-        LAUNCH(P, k_rho, cdiv(m, 128), 128, 0, P->ctrl, m, P->T, P->ldt, P->at_ptr, P->at_ind, P->at_val,
-               P->head, P->bind, P->rslot, P->cslot, P->rho);
+        launch_rho(P, P->h_ctrl->k);
         GROUP_DISPATCH(D.gc, LAUNCH(P, k_trow<GG>, cdiv((long)n * GG, 256), 256, 0, P->ctrl, m, n, P->a_ptr,
                                     P->a_ind, P->a_val, P->head, P->stat, P->rho, (const double *)nullptr,
                                     P->trow, P->svec, 0));

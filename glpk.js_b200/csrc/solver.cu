@@ -149,7 +149,7 @@ extern "C" void glpb_destroy(glpb_prob *P)
                     P->orig_type, P->stat, P->refsp, P->lb, P->ub, P->coef, P->orig_lb, P->orig_ub,
                     P->obj, P->head, P->bind, P->bbar, P->cbar, P->gamma, P->tcol, P->trow, P->rho,
                     P->svec, P->w1, P->w2, P->w3, P->w4, P->w5, P->yk, P->wk, P->T, P->partial,
-                    P->rslot, P->slot_pos, P->cslot, P->slot_row, P->gj_piv, P->gj_row, P->gj_col,
+                    P->rslot, P->slot_pos, P->cslot, P->slot_row, P->gj_piv, P->gj_row, P->gj_col, P->gj_xp,
                     P->scratch, P->ctrl};
     for (void *p : ptrs) if (p) cudaFree(p);
     P->prof = 0; prof_collect(P);
@@ -181,6 +181,7 @@ static int create_device(glpb_prob *P)
     DA(partial, (size_t)P->partial_rows * P->ldt);
     DA(rslot, m); DA(slot_pos, P->ldt); DA(cslot, m); DA(slot_row, P->ldt);
     DA(gj_piv, P->ldt); DA(gj_row, P->ldt); DA(gj_col, P->ldt);
+    DA(gj_xp, (size_t)GJ_NB * P->ldt);
     DA(scratch, 4096);
     DA(ctrl, 1);
 #undef DA
@@ -365,6 +366,26 @@ struct Dev { /* launch geometry derived from the handle */
     }
 };
 
+/* rho = row ctrl->p of inv(B); k is the host's view of the kernel size */
+#define RHO_SMEM_MAX (200 * 1024)
+static void launch_rho(glpb_prob *P, int k)
+{
+    const int m = P->m;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_rho_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, RHO_SMEM_MAX);
+        attr_set = true;
+    }
+    size_t smem = (size_t)std::max(k, 1) * sizeof(double);
+    if (smem <= RHO_SMEM_MAX) {
+        P->next_bytes = 8.0 * k * (double)k + 12.0 * m;
+        LAUNCH(P, k_rho_fast, cdiv(std::max((long)k * 32, (long)m), 256), 256, smem, P->ctrl, m, P->T, P->ldt,
+               P->at_ptr, P->at_ind, P->at_val, P->head, P->bind, P->rslot, P->cslot, P->slot_row, P->rho);
+    } else
+        LAUNCH(P, k_rho, cdiv(m, 128), 128, 0, P->ctrl, m, P->T, P->ldt, P->at_ptr, P->at_ind, P->at_val,
+               P->head, P->bind, P->rslot, P->cslot, P->rho);
+}
+
 /* x = inv(B) h   (bfd_ftran, lib/glpbfd.js:148-157); h and x must differ */
 static void dev_ftran(Dev &D, const double *h, double *x)
 {
@@ -413,9 +434,19 @@ static int dev_refactor(Dev &D)
             LAUNCH(P, k_gj_small, 1, 256, smem, P->ctrl, P->T, P->ldt);
         } else {
             dim3 grid(cdiv(k, UPD_TB), cdiv(k, UPD_TC));
-            for (int t = 0; t < k; t++) {
-                LAUNCH(P, k_gj_pivot, 1, 1024, 0, P->ctrl, t, P->T, P->ldt, P->gj_piv, P->gj_row, P->gj_col);
-                LAUNCH(P, k_gj_update, grid, UPD_TB, 0, P->ctrl, t, P->T, P->ldt, P->gj_row, P->gj_col);
+            if (getenv("GLPB_UNBLOCKED_GJ")) {
+                for (int t = 0; t < k; t++) {
+                    LAUNCH(P, k_gj_pivot, 1, 1024, 0, P->ctrl, t, P->T, P->ldt, P->gj_piv, P->gj_row, P->gj_col);
+                    LAUNCH(P, k_gj_update, grid, UPD_TB, 0, P->ctrl, t, P->T, P->ldt, P->gj_row, P->gj_col);
+                }
+            } else {
+                /* blocked: GJ_NB pivots per round, one pass over T per round */
+                for (int c0 = 0; c0 < k; c0 += GJ_NB) {
+                    LAUNCH(P, k_bgj_panel, 1, 1024, 0, P->ctrl, c0, P->T, P->ldt, P->gj_piv, P->gj_row, P->gj_col);
+                    LAUNCH(P, k_bgj_swap, cdiv(k, 256), 256, 0, P->ctrl, c0, P->T, P->ldt, P->gj_piv, P->gj_xp);
+                    P->next_bytes = 16.0 * k * (double)k;
+                    LAUNCH(P, k_bgj_update, grid, UPD_TB, 0, P->ctrl, c0, P->T, P->ldt, P->gj_xp);
+                }
             }
             LAUNCH(P, k_gj_finish, 1, 1024, 0, P->ctrl, P->T, P->ldt, P->gj_piv);
             LAUNCH(P, k_negate, dim3(cdiv(k, 256), k), 256, 0, P->ctrl, P->T, P->ldt);
@@ -640,8 +671,7 @@ struct Loop : Dev {
     /* eval_rho (+ refine_rho), lib/glpspx01.js:1030-1056 */
     void eval_rho()
     {
-        LAUNCH(P, k_rho, cdiv(m, 128), 128, 0, P->ctrl, m, P->T, P->ldt, P->at_ptr, P->at_ind, P->at_val,
-               P->head, P->bind, P->rslot, P->cslot, P->rho);
+        launch_rho(P, k);
         if (rigorous) {
             LAUNCH(P, k_unit, cdiv(m, 256), 256, 0, P->ctrl, m, P->w2);
             GROUP_DISPATCH(gc, LAUNCH(P, k_resid_btran<GG>, cdiv((long)m * GG, 256), 256, 0, P->ctrl, m, P->a_ptr,
@@ -669,6 +699,14 @@ struct Loop : Dev {
         return rc;
     }
 
+    /* refactorisation period: bfcp.nfs_max (the reference's eta-file limit, default 100);
+       the explicit inverse needs a fresh start only for accuracy, so for large
+       kernels the period grows with k unless GLPB_REFAC_AUTO=0 */
+    int refac_period() const
+    {
+        static const bool fixed = getenv("GLPB_REFAC_AUTO") && atoi(getenv("GLPB_REFAC_AUTO")) == 0;
+        return fixed ? P->bfcp.nfs_max : std::max(P->bfcp.nfs_max, k / 8);
+    }
     bool it_limit() const { return parm.it_lim < INT_MAX && it_cnt - it_beg >= parm.it_lim; }
     bool tm_limit() const { return parm.tm_lim < INT_MAX && (now_ms() - tm_beg) >= parm.tm_lim; }
 
@@ -826,7 +864,7 @@ struct Primal : Loop {
                     if (do_gamma) refct--;
                     binv_st = 2;
                     upd_cnt++; P->n_update++;
-                    if (upd_cnt >= P->bfcp.nfs_max) binv_st = 0;
+                    if (upd_cnt >= refac_period()) binv_st = 0;
                 }
                 it_cnt++; P->n_iter++;
                 if (rigorous > 0) rigorous--;
@@ -1052,7 +1090,7 @@ struct Dual : Loop {
                 if (do_gamma) refct--;
                 binv_st = 2;
                 upd_cnt++; P->n_update++;
-                if (upd_cnt >= P->bfcp.nfs_max) binv_st = 0;
+                if (upd_cnt >= refac_period()) binv_st = 0;
                 it_cnt++; P->n_iter++;
                 if (rigorous > 0) rigorous--;
                 break;
