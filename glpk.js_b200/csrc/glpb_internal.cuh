@@ -57,6 +57,11 @@ enum {
     ST_PIVSMALL = 4,   /* pivot below 1e-5(1+0.01 max)                         */
     ST_PIV12 = 5,      /* tcol[p] and trow[q] disagree                         */
     ST_SINGULAR = 6,   /* refactorisation met a zero pivot                     */
+    /* raised at the end of a completed iteration (batch mode) */
+    ST_REFAC = 7,      /* refactorisation period reached                       */
+    ST_LIMIT = 8,      /* iteration limit reached                              */
+    ST_REFSP = 9,      /* reference space must be reset (refct == 0)           */
+    ST_OBJLIM = 10,    /* dual: objective crossed obj_ll / obj_ul              */
 };
 
 #define P_NONE (-1)
@@ -72,7 +77,12 @@ struct Ctrl {
     int cnt;            /* generic counter result (set_aux_obj)               */
     int skip2;          /* ratio test: second pass not needed                 */
     int sing;           /* refactorisation: singular                          */
-    int pad0, pad1;
+    /* loop state kept on the device so that several iterations can be enqueued
+       back to back; the host seeds it at the start of a batch */
+    int it_cnt, it_max, refct, upd_cnt, period, n_done;
+    int rigorous, bbar_fresh, cbar_fresh, binv_fresh, pse;
+    int pad0;
+    double obj_ll, obj_ul, zeta;
     double teta, delta, new_dq, tmax;
     double tcol_max, trow_max, eps;
     double piv1, piv2, d1, d2;

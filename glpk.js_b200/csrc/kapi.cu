@@ -119,13 +119,13 @@ extern "C" int glpb_k_ratio_primal(int m, int n, const signed char *type, const 
     double *d_bbar = t.up(bbar + 1, m), *d_tcol = t.up(tcol_vec + 1, m);
     Ctrl hc;
     memset(&hc, 0, sizeof hc);
-    hc.q = q - 1; hc.phase = phase; hc.d1 = cbar_q;
+    hc.q = q - 1; hc.phase = phase; hc.d1 = cbar_q; hc.rigorous = 1;
     Ctrl *ctrl = t.up(&hc, 1);
     Key *scr = t.zero<Key>(4096);
     if (!t.ok) return GLPB_ENOMEM;
     for (int pass = 1; pass <= 2; pass++)
         k_ratio_primal<<<grid1(tcol_num), 256>>>(ctrl, pass, m, d_type, d_lb, d_ub, d_coef, d_head, d_bbar,
-                                                 d_tcol, d_ind, tcol_num, rtol, 1, scr);
+                                                 d_tcol, d_ind, tcol_num, rtol, scr);
     Ctrl h;
     if ((rc = finish(t, ctrl, &h))) return rc;
     *p = (h.p >= 0) ? h.p + 1 : (h.p == P_FLIP ? -1 : 0);
@@ -148,12 +148,12 @@ extern "C" int glpb_k_ratio_dual(int n, const signed char *stat, const double *c
     int *d_ind = t.up(ind0.data(), trow_num);
     Ctrl hc;
     memset(&hc, 0, sizeof hc);
-    hc.delta = delta;
+    hc.delta = delta; hc.rigorous = 1;
     Ctrl *ctrl = t.up(&hc, 1);
     Key *scr = t.zero<Key>(4096);
     if (!t.ok) return GLPB_ENOMEM;
     for (int pass = 1; pass <= 2; pass++)
-        k_ratio_dual<<<grid1(trow_num), 256>>>(ctrl, pass, d_stat, d_cbar, d_trow, d_ind, trow_num, rtol, 1, scr);
+        k_ratio_dual<<<grid1(trow_num), 256>>>(ctrl, pass, d_stat, d_cbar, d_trow, d_ind, trow_num, rtol, scr);
     Ctrl h;
     if ((rc = finish(t, ctrl, &h))) return rc;
     *q = (h.q >= 0) ? h.q + 1 : 0;

@@ -140,6 +140,34 @@ __device__ __forceinline__ double get_xN(const signed char *stat, const int *hea
     }
 }
 
+__device__ __forceinline__ bool gamma_on(const Ctrl *ctrl) { return ctrl->pse && ctrl->refct > 0; }
+
+/* end-of-iteration bookkeeping (it_cnt++, rigorous--, state flags, refct,
+   update count) and the conditions under which the host must step in before
+   the next iteration; runs in one thread of the last kernel of an iteration */
+__device__ void iter_end(Ctrl *ctrl, bool basis_changed, int dual)
+{
+    ctrl->it_cnt++;
+    ctrl->n_done++;
+    if (ctrl->rigorous > 0) ctrl->rigorous--;
+    ctrl->bbar_fresh = 0;
+    if (basis_changed) {
+        ctrl->cbar_fresh = 0;
+        ctrl->binv_fresh = 0;
+        ctrl->upd_cnt++;
+        if (gamma_on(ctrl)) ctrl->refct--;
+    }
+    ctrl->big = 0.0;
+    ctrl->skip2 = 0;
+    if (basis_changed && ctrl->upd_cnt >= ctrl->period) ctrl->status = ST_REFAC;
+    else if (ctrl->it_cnt >= ctrl->it_max) ctrl->status = ST_LIMIT;
+    else if (ctrl->pse && ctrl->refct == 0) ctrl->status = ST_REFSP;
+    else if (dual && ctrl->phase == 2 &&
+             ((ctrl->zeta < 0.0 && ctrl->obj_ll > -DBL_MAX && ctrl->obj <= ctrl->obj_ll) ||
+              (ctrl->zeta > 0.0 && ctrl->obj_ul < +DBL_MAX && ctrl->obj >= ctrl->obj_ul)))
+        ctrl->status = ST_OBJLIM;
+}
+
 /* ------------------------------------------------------------------ */
 /* pricing                                                            */
 /* ------------------------------------------------------------------ */
@@ -222,14 +250,15 @@ __global__ void k_chuzr_dual(Ctrl *ctrl, int m, const signed char *__restrict__ 
    |tcol| >= ctrl->eps; ind != NULL: the caller's sorted list (kernel parity).
    Ties are broken by list position, as the sequential loop does.
    Algorithmic bytes: 49 per examined entry and pass. */
-__global__ void k_ratio_primal(Ctrl *ctrl, int pass, int m, const signed char *__restrict__ type,
+__device__ __forceinline__ void ratio_primal_body(Ctrl *ctrl, int pass, int m, const signed char *__restrict__ type,
                                const double *__restrict__ lb, const double *__restrict__ ub,
                                const double *__restrict__ coef, const int *__restrict__ head,
                                const double *__restrict__ bbar, const double *__restrict__ tcol,
-                               const int *__restrict__ ind, int num, double rtol, int rigorous,
+                               const int *__restrict__ ind, int num, double rtol,
                                Key *scratch)
 {
     if (ctrl->status != ST_OK) return;
+    const int rigorous = ctrl->rigorous;
     if (pass == 2 && ctrl->skip2) return;
     const int q = ctrl->q, phase = ctrl->phase;
     const double s = (ctrl->d1 > 0.0 ? -1.0 : +1.0); /* d1 holds the (corrected) cbar[q] */
@@ -309,14 +338,29 @@ __global__ void k_ratio_primal(Ctrl *ctrl, int pass, int m, const signed char *_
     else grid_reduce(v, none, scratch, &ctrl->ticket[1], CombRatio2(), fin);
 }
 
+/* pass = 1 or 2: one pass per launch (any grid); pass = 0: both passes in one
+   launch of a single block (vectors up to a few 10^4 entries) */
+__global__ void k_ratio_primal(Ctrl *ctrl, int pass, int m, const signed char *__restrict__ type,
+                               const double *__restrict__ lb, const double *__restrict__ ub,
+                               const double *__restrict__ coef, const int *__restrict__ head,
+                               const double *__restrict__ bbar, const double *__restrict__ tcol,
+                               const int *__restrict__ ind, int num, double rtol, Key *scratch)
+{
+    if (pass != 0) { ratio_primal_body(ctrl, pass, m, type, lb, ub, coef, head, bbar, tcol, ind, num, rtol, scratch); return; }
+    ratio_primal_body(ctrl, 1, m, type, lb, ub, coef, head, bbar, tcol, ind, num, rtol, scratch);
+    __syncthreads();
+    ratio_primal_body(ctrl, 2, m, type, lb, ub, coef, head, bbar, tcol, ind, num, rtol, scratch);
+}
+
 /* chuzc (dual ratio test), lib/glpspx02.js:793-935, one pass per launch.
    Algorithmic bytes: 21 per examined entry and pass (idx 4, trow 8, stat 1, cbar 8). */
-__global__ void k_ratio_dual(Ctrl *ctrl, int pass, const signed char *__restrict__ stat,
+__device__ __forceinline__ void ratio_dual_body(Ctrl *ctrl, int pass, const signed char *__restrict__ stat,
                              const double *__restrict__ cbar, const double *__restrict__ trow,
-                             const int *__restrict__ ind, int num, double rtol, int rigorous,
+                             const int *__restrict__ ind, int num, double rtol,
                              Key *scratch)
 {
     if (ctrl->status != ST_OK) return;
+    const int rigorous = ctrl->rigorous;
     if (pass == 2 && ctrl->skip2) return;
     const double s = (ctrl->delta > 0.0 ? +1.0 : -1.0);
     const double eps = (ind == nullptr ? ctrl->eps : 0.0);
@@ -362,6 +406,16 @@ __global__ void k_ratio_dual(Ctrl *ctrl, int pass, const signed char *__restrict
     else grid_reduce(v, none, scratch, &ctrl->ticket[1], CombRatio2(), fin);
 }
 
+__global__ void k_ratio_dual(Ctrl *ctrl, int pass, const signed char *__restrict__ stat,
+                             const double *__restrict__ cbar, const double *__restrict__ trow,
+                             const int *__restrict__ ind, int num, double rtol, Key *scratch)
+{
+    if (pass != 0) { ratio_dual_body(ctrl, pass, stat, cbar, trow, ind, num, rtol, scratch); return; }
+    ratio_dual_body(ctrl, 1, stat, cbar, trow, ind, num, rtol, scratch);
+    __syncthreads();
+    ratio_dual_body(ctrl, 2, stat, cbar, trow, ind, num, rtol, scratch);
+}
+
 /* ------------------------------------------------------------------ */
 /* sparse passes over A (all gathers: no atomics, deterministic)       */
 /* ------------------------------------------------------------------ */
@@ -383,10 +437,11 @@ template <int G>
 __global__ void k_trow(Ctrl *ctrl, int m, int n, const int *__restrict__ a_ptr,
                        const int *__restrict__ a_ind, const double *__restrict__ a_val,
                        const int *__restrict__ head, const signed char *__restrict__ stat,
-                       const double *__restrict__ rho, const double *__restrict__ u,
+                       const double *__restrict__ rho, const double *u,
                        double *__restrict__ trow, double *__restrict__ svec, int want_max)
 {
     if (ctrl->status != ST_OK) return;
+    if (u != nullptr && !gamma_on(ctrl)) u = nullptr;   /* PSE inner products only while weights are live */
     const int gid = (blockIdx.x * blockDim.x + threadIdx.x) / G;
     const int lane = threadIdx.x % G;
     double t = 0.0, s = 0.0;
@@ -437,9 +492,10 @@ __global__ void k_ftran_tail(Ctrl *ctrl, int m, const int *__restrict__ at_ptr,
                              const int *__restrict__ at_ind, const double *__restrict__ at_val,
                              const int *__restrict__ head, const int *__restrict__ bind,
                              const int *__restrict__ rslot, const double *__restrict__ h,
-                             const double *__restrict__ y, double *__restrict__ x)
+                             const double *__restrict__ y, double *__restrict__ x, int cond)
 {
     if (ctrl->status != ST_OK) return;
+    if (cond && !gamma_on(ctrl)) return;
     const int i = (blockIdx.x * blockDim.x + threadIdx.x) / G;
     const int lane = threadIdx.x % G;
     double acc = 0.0;
@@ -461,9 +517,10 @@ __global__ void k_btran_head(Ctrl *ctrl, int m, const int *__restrict__ a_ptr,
                              const int *__restrict__ a_ind, const double *__restrict__ a_val,
                              const int *__restrict__ head, const int *__restrict__ bind,
                              const int *__restrict__ slot_pos, const double *__restrict__ c,
-                             double *__restrict__ w)
+                             double *__restrict__ w, int cond)
 {
     if (ctrl->status != ST_OK) return;
+    if (cond && !gamma_on(ctrl)) return;
     const int k = ctrl->k;
     const int b = (blockIdx.x * blockDim.x + threadIdx.x) / G;
     const int lane = threadIdx.x % G;
@@ -484,9 +541,10 @@ __global__ void k_btran_head(Ctrl *ctrl, int m, const int *__restrict__ a_ptr,
 
 __global__ void k_btran_tail(Ctrl *ctrl, int m, const int *__restrict__ cslot,
                              const int *__restrict__ bind, const double *__restrict__ c,
-                             const double *__restrict__ zn, double *__restrict__ z)
+                             const double *__restrict__ zn, double *__restrict__ z, int cond)
 {
     if (ctrl->status != ST_OK) return;
+    if (cond && !gamma_on(ctrl)) return;
     int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= m) return;
     int cs = cslot[r];
@@ -588,9 +646,10 @@ template <int G>
 __global__ void k_dual_gamma_rhs(Ctrl *ctrl, int m, const int *__restrict__ at_ptr,
                                  const int *__restrict__ at_ind, const double *__restrict__ at_val,
                                  const int *__restrict__ bind, const signed char *__restrict__ refsp,
-                                 const double *__restrict__ trow, double *__restrict__ v)
+                                 const double *__restrict__ trow, double *__restrict__ v, int cond)
 {
     if (ctrl->status != ST_OK) return;
+    if (cond && !gamma_on(ctrl)) return;
     const int row = (blockIdx.x * blockDim.x + threadIdx.x) / G;
     const int lane = threadIdx.x % G;
     double acc = 0.0;
@@ -619,32 +678,42 @@ __global__ void k_dual_gamma_rhs(Ctrl *ctrl, int m, const int *__restrict__ at_p
    same kernel the sparse-rhs FTRAN of eval_tcol.  8 k^2 bytes when h is dense. */
 __global__ void k_gemvN_part(Ctrl *ctrl, const double *__restrict__ T, int ldt,
                              const double *__restrict__ h, const int *__restrict__ slot_row,
-                             double *__restrict__ part)
+                             double *__restrict__ part, int single, int cond)
 {
     if (ctrl->status != ST_OK) return;
+    if (cond && !gamma_on(ctrl)) return;
     const int k = ctrl->k;
-    const int c0 = blockIdx.y * GEMV_TILE;
-    if (c0 >= k || (int)(blockIdx.x * GEMV_TILE) >= k) return;
+    if ((int)(blockIdx.x * GEMV_TILE) >= k) return;
     __shared__ double hs[GEMV_TILE];
-    const int cn = min(GEMV_TILE, k - c0);
-    if ((int)threadIdx.x < cn) hs[threadIdx.x] = h[slot_row[c0 + threadIdx.x]];
-    __syncthreads();
     const int b = blockIdx.x * GEMV_TILE + threadIdx.x;
-    if (b >= k) return;
+    /* single != 0: one block walks all column tiles and writes y itself
+       (small kernels: saves the second launch); else one tile per block */
+    const int t0 = single ? 0 : blockIdx.y, t1 = single ? (k + GEMV_TILE - 1) / GEMV_TILE : blockIdx.y + 1;
     double acc = 0.0;
-    const double *col = T + (size_t)c0 * ldt + b;
+    for (int tile = t0; tile < t1; tile++) {
+        const int c0 = tile * GEMV_TILE;
+        if (c0 >= k) break;
+        const int cn = min(GEMV_TILE, k - c0);
+        __syncthreads();
+        if ((int)threadIdx.x < cn) hs[threadIdx.x] = h[slot_row[c0 + threadIdx.x]];
+        __syncthreads();
+        if (b < k) {
+            const double *col = T + (size_t)c0 * ldt + b;
 #pragma unroll 4
-    for (int c = 0; c < cn; c++) {
-        double hv = hs[c];
-        if (hv != 0.0) acc += col[(size_t)c * ldt] * hv;
+            for (int c = 0; c < cn; c++) {
+                double hv = hs[c];
+                if (hv != 0.0) acc += col[(size_t)c * ldt] * hv;
+            }
+        }
     }
-    part[(size_t)blockIdx.y * ldt + b] = acc;
+    if (b < k) part[(size_t)(single ? 0 : blockIdx.y) * ldt + b] = acc;
 }
 
 __global__ void k_gemvN_fin(Ctrl *ctrl, int ldt, const double *__restrict__ part,
-                            double *__restrict__ y)
+                            double *__restrict__ y, int cond)
 {
     if (ctrl->status != ST_OK) return;
+    if (cond && !gamma_on(ctrl)) return;
     const int k = ctrl->k;
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= k) return;
@@ -656,9 +725,10 @@ __global__ void k_gemvN_fin(Ctrl *ctrl, int ldt, const double *__restrict__ part
 
 /* zn[cs] = sum_b T[b,cs] * w[b]; one warp per column, coalesced */
 __global__ void k_gemvT(Ctrl *ctrl, const double *__restrict__ T, int ldt,
-                        const double *__restrict__ w, double *__restrict__ zn)
+                        const double *__restrict__ w, double *__restrict__ zn, int cond)
 {
     if (ctrl->status != ST_OK) return;
+    if (cond && !gamma_on(ctrl)) return;
     const int k = ctrl->k;
     const int cs = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -792,13 +862,16 @@ __global__ void k_update_fix(Ctrl *ctrl, int m, double *__restrict__ T, int ldt,
                              int *__restrict__ cslot, int *__restrict__ slot_row,
                              int *__restrict__ head, int *__restrict__ bind,
                              signed char *__restrict__ stat, const signed char *__restrict__ type,
-                             int dual)
+                             signed char *__restrict__ refsp, int dual)
 {
     if (ctrl->status != ST_OK) return;
     const int p = ctrl->p, q = ctrl->q;
     const int tid = threadIdx.x, nt = blockDim.x;
     if (p == P_FLIP) {
-        if (tid == 0) stat[q] = (stat[q] == GLP_NL) ? GLP_NU : GLP_NL;
+        if (tid == 0) {
+            stat[q] = (stat[q] == GLP_NL) ? GLP_NU : GLP_NL;
+            iter_end(ctrl, false, dual);
+        }
         return;
     }
     const int k = ctrl->k;
@@ -863,6 +936,10 @@ __global__ void k_update_fix(Ctrl *ctrl, int m, double *__restrict__ T, int ldt,
             else stat[q] = (ctrl->delta > 0.0) ? GLP_NL : GLP_NU;
         } else
             stat[q] = (signed char)ctrl->p_stat;
+        /* dual update_gamma: a fixed leaving variable drops out of the
+           reference space (lib/glpspx02.js:1171-1173) */
+        if (dual && gamma_on(ctrl) && type[kp] == GLP_FX && refsp[kp]) refsp[kp] = 0;
+        iter_end(ctrl, true, dual);
     }
 }
 
@@ -1219,11 +1296,11 @@ __global__ void k_col_rhs(Ctrl *ctrl, int m, const int *__restrict__ a_ptr,
 __global__ void k_primal_prep(Ctrl *ctrl, int m, const int *__restrict__ head,
                               const double *__restrict__ coef, const double *__restrict__ tcol,
                               const signed char *__restrict__ refsp, double *__restrict__ cbar,
-                              double *__restrict__ v, double tol_piv, int cbar_fresh, int rigorous,
-                              int pse, Key *scratch)
+                              double *__restrict__ v, double tol_piv, Key *scratch)
 {
     if (ctrl->status != ST_OK) return;
     const int q = ctrl->q;
+    const int cbar_fresh = ctrl->cbar_fresh, rigorous = ctrl->rigorous, pse = gamma_on(ctrl);
     Key none = {0.0, 0.0, 0.0, 0, 0};
     Key acc = none;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
@@ -1262,11 +1339,11 @@ __global__ void k_primal_prep(Ctrl *ctrl, int m, const int *__restrict__ head,
    and the scalars of update_cbar (:1154-1176).  One thread. */
 __global__ void k_primal_piv(Ctrl *ctrl, int m, const int *__restrict__ head,
                              double *__restrict__ trow, double *__restrict__ cbar,
-                             double *__restrict__ coef, const double *__restrict__ tcol,
-                             int binv_fresh, int rigorous)
+                             double *__restrict__ coef, const double *__restrict__ tcol)
 {
     if (ctrl->status != ST_OK) return;
     const int p = ctrl->p, q = ctrl->q;
+    const int binv_fresh = ctrl->binv_fresh, rigorous = ctrl->rigorous;
     if (p < 0) return;
     double piv1 = tcol[p], piv2 = trow[q];
     ctrl->piv1 = piv1; ctrl->piv2 = piv2;
@@ -1288,13 +1365,15 @@ __global__ void k_primal_update(Ctrl *ctrl, int m, int n, const int *__restrict_
                                 double *__restrict__ bbar, double *__restrict__ cbar,
                                 double *__restrict__ gamma, const signed char *__restrict__ refsp,
                                 const double *__restrict__ tcol, const double *__restrict__ trow,
-                                const double *__restrict__ svec, int do_gamma)
+                                const double *__restrict__ svec, double *__restrict__ hz)
 {
     if (ctrl->status != ST_OK) return;
     const int p = ctrl->p, q = ctrl->q;
+    const int do_gamma = gamma_on(ctrl);
     const double teta = ctrl->teta;
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t < m) {
+        hz[t] = 0.0;     /* keep the dense right-hand side of eval_tcol all-zero */
         if (t == p) bbar[t] = get_xN(stat, head, lb, ub, m, q) + teta;
         else if (teta != 0.0) {
             double tc = tcol[t];
@@ -1349,11 +1428,11 @@ __global__ void k_dual_rowmax(Ctrl *ctrl, double tol)
 __global__ void k_dual_prep(Ctrl *ctrl, int m, int n, const int *__restrict__ head,
                             const signed char *__restrict__ refsp, const double *__restrict__ trow,
                             double *__restrict__ tcol, const double *__restrict__ cbar,
-                            const signed char *__restrict__ stat, double zeta, int binv_fresh,
-                            int rigorous, int pse, Key *scratch)
+                            const signed char *__restrict__ stat, double zeta, Key *scratch)
 {
     if (ctrl->status != ST_OK) return;
     const int p = ctrl->p, q = ctrl->q;
+    const int binv_fresh = ctrl->binv_fresh, rigorous = ctrl->rigorous, pse = gamma_on(ctrl);
     Key none = {0.0, 0.0, 0.0, 0, 0};
     Key acc = none;
     if (pse) {
@@ -1388,10 +1467,11 @@ __global__ void k_dual_update(Ctrl *ctrl, int m, int n, const int *__restrict__ 
                               double *__restrict__ cbar, double *__restrict__ gamma,
                               signed char *__restrict__ refsp, const double *__restrict__ tcol,
                               const double *__restrict__ trow, const double *__restrict__ u,
-                              int do_gamma)
+                              double *__restrict__ hz)
 {
     if (ctrl->status != ST_OK) return;
     const int p = ctrl->p, q = ctrl->q;
+    const int do_gamma = gamma_on(ctrl);
     const double teta = ctrl->teta, new_dq = ctrl->new_dq;
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int kp = head[p], kq = head[m + q];
@@ -1404,6 +1484,7 @@ __global__ void k_dual_update(Ctrl *ctrl, int m, int n, const int *__restrict__ 
         }
     }
     if (t < m) {
+        hz[t] = 0.0;
         const bool drop = (type[kp] == GLP_FX && refsp[kp]);
         if (t == p) {
             bbar[p] = get_xN(stat, head, lb, ub, m, q) + teta;
@@ -1626,6 +1707,18 @@ __global__ void k_unit(Ctrl *ctrl, int m, double *__restrict__ e)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < m) e[i] = (i == ctrl->p) ? 1.0 : 0.0;
+}
+
+/* seeds the device-resident loop state before a batch of iterations */
+__global__ void k_batch_begin(Ctrl *ctrl, int phase, int it_cnt, int it_max, int refct, int upd_cnt,
+                              int period, int rigorous, int bbar_fresh, int cbar_fresh, int binv_fresh,
+                              int pse, double obj_ll, double obj_ul, double zeta)
+{
+    ctrl->status = ST_OK; ctrl->flag = 0; ctrl->cnt = 0; ctrl->big = 0.0; ctrl->skip2 = 0;
+    ctrl->phase = phase; ctrl->it_cnt = it_cnt; ctrl->it_max = it_max; ctrl->refct = refct;
+    ctrl->upd_cnt = upd_cnt; ctrl->period = period; ctrl->n_done = 0; ctrl->rigorous = rigorous;
+    ctrl->bbar_fresh = bbar_fresh; ctrl->cbar_fresh = cbar_fresh; ctrl->binv_fresh = binv_fresh;
+    ctrl->pse = pse; ctrl->obj_ll = obj_ll; ctrl->obj_ul = obj_ul; ctrl->zeta = zeta;
 }
 
 __global__ void k_clear_ctrl(Ctrl *ctrl, int phase)

@@ -261,7 +261,7 @@ struct glpb_mip {
         Dev D(P);
         LAUNCH(P, k_clear_ctrl, 1, 1, 0, P->ctrl, 2);
         CK(cudaMemcpyAsync(&P->ctrl->p, &pos, sizeof(int), cudaMemcpyHostToDevice, P->stream));
-        launch_rho(P, P->h_ctrl->k);
+        launch_rho(P, P->h_ctrl->k);   /* k_clear_ctrl leaves pse/refct alone: k_trow gets u = NULL anyway */
         GROUP_DISPATCH(D.gc, LAUNCH(P, k_trow<GG>, cdiv((long)n * GG, 256), 256, 0, P->ctrl, m, n, P->a_ptr,
                                     P->a_ind, P->a_val, P->head, P->stat, P->rho, (const double *)nullptr,
                                     P->trow, P->svec, 0));

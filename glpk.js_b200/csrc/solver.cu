@@ -358,6 +358,7 @@ extern "C" int glpb_set_it_cnt(glpb_prob *P, int it_cnt)
 struct Dev { /* launch geometry derived from the handle */
     glpb_prob *P;
     int m, n, gc, gr, k;
+    int kpad = 0;   /* head-room for grids when several iterations are enqueued (k grows by <= 1 each) */
     explicit Dev(glpb_prob *P_) : P(P_), m(P_->m), n(P_->n)
     {
         gc = pick_group((double)P->nnz / P->n);
@@ -386,31 +387,40 @@ static void launch_rho(glpb_prob *P, int k)
                P->head, P->bind, P->rslot, P->cslot, P->rho);
 }
 
-/* x = inv(B) h   (bfd_ftran, lib/glpbfd.js:148-157); h and x must differ */
-static void dev_ftran(Dev &D, const double *h, double *x)
+/* x = inv(B) h   (bfd_ftran, lib/glpbfd.js:148-157); h and x must differ.
+   cond != 0: the kernels run only while PSE weights are live (device flag) */
+static void dev_ftran(Dev &D, const double *h, double *x, int cond = 0)
 {
     glpb_prob *P = D.P;
-    if (D.k > 0) {
-        int tl = cdiv(D.k, GEMV_TILE);
-        LAUNCH(P, k_gemvN_part, dim3(tl, tl), GEMV_TILE, 0, P->ctrl, P->T, P->ldt, h, P->slot_row, P->partial);
-        LAUNCH(P, k_gemvN_fin, cdiv(D.k, 256), 256, 0, P->ctrl, P->ldt, P->partial, P->yk);
+    const int kg = D.k + D.kpad;
+    if (kg > 0) {
+        int tl = cdiv(kg, GEMV_TILE);
+        if (kg <= 2048) {
+            P->next_bytes = 8.0 * D.k * (double)D.k;
+            LAUNCH(P, k_gemvN_part, dim3(tl, 1), GEMV_TILE, 0, P->ctrl, P->T, P->ldt, h, P->slot_row, P->yk, 1, cond);
+        } else {
+            P->next_bytes = 8.0 * D.k * (double)D.k;
+            LAUNCH(P, k_gemvN_part, dim3(tl, tl), GEMV_TILE, 0, P->ctrl, P->T, P->ldt, h, P->slot_row, P->partial, 0, cond);
+            LAUNCH(P, k_gemvN_fin, cdiv(kg, 256), 256, 0, P->ctrl, P->ldt, P->partial, P->yk, cond);
+        }
     }
     P->next_bytes = 12.0 * P->nnz * (1.0 - (double)D.k / D.m) + 16.0 * D.m;
     GROUP_DISPATCH(D.gr, LAUNCH(P, k_ftran_tail<GG>, cdiv((long)D.m * GG, 256), 256, 0, P->ctrl, D.m,
-                                P->at_ptr, P->at_ind, P->at_val, P->head, P->bind, P->rslot, h, P->yk, x));
+                                P->at_ptr, P->at_ind, P->at_val, P->head, P->bind, P->rslot, h, P->yk, x, cond));
 }
 
 /* z = inv(B') c  (bfd_btran, lib/glpbfd.js:159-168); c and z must differ */
-static void dev_btran(Dev &D, const double *c, double *z)
+static void dev_btran(Dev &D, const double *c, double *z, int cond = 0)
 {
     glpb_prob *P = D.P;
-    if (D.k > 0) {
-        GROUP_DISPATCH(D.gc, LAUNCH(P, k_btran_head<GG>, cdiv((long)D.k * GG, 256), 256, 0, P->ctrl, D.m,
-                                    P->a_ptr, P->a_ind, P->a_val, P->head, P->bind, P->slot_pos, c, P->wk));
+    const int kg = D.k + D.kpad;
+    if (kg > 0) {
+        GROUP_DISPATCH(D.gc, LAUNCH(P, k_btran_head<GG>, cdiv((long)kg * GG, 256), 256, 0, P->ctrl, D.m,
+                                    P->a_ptr, P->a_ind, P->a_val, P->head, P->bind, P->slot_pos, c, P->wk, cond));
         P->next_bytes = 8.0 * D.k * (double)D.k;
-        LAUNCH(P, k_gemvT, cdiv((long)D.k * 32, 256), 256, 0, P->ctrl, P->T, P->ldt, P->wk, P->yk);
+        LAUNCH(P, k_gemvT, cdiv((long)kg * 32, 256), 256, 0, P->ctrl, P->T, P->ldt, P->wk, P->yk, cond);
     }
-    LAUNCH(P, k_btran_tail, cdiv(D.m, 256), 256, 0, P->ctrl, D.m, P->cslot, P->bind, c, P->yk, z);
+    LAUNCH(P, k_btran_tail, cdiv(D.m, 256), 256, 0, P->ctrl, D.m, P->cslot, P->bind, c, P->yk, z, cond);
 }
 
 /* refactorisation (invert_B -> bfd_factorize -> luf_factorize in the
@@ -629,6 +639,43 @@ struct Loop : Dev {
 
     void clear_ctrl() { LAUNCH(P, k_clear_ctrl, 1, 1, 0, P->ctrl, phase); }
 
+    /* vectors up to 64k entries are reduced by one block of 1024 threads (no
+       second stage); longer ones by a multi-block two-stage reduction */
+    int red_blocks(int len) const { return len <= 65536 ? 1 : grid1(len); }
+    int red_threads(int len) const { return len <= 65536 ? 1024 : 256; }
+
+    int batch_size() const
+    {
+        static const int env = getenv("GLPB_BATCH") ? std::max(1, atoi(getenv("GLPB_BATCH"))) : 16;
+        return (rigorous > 0 || P->trace) ? 1 : env;
+    }
+
+    /* seed the device-resident loop state; the dense rhs of eval_tcol is
+       cleared here because an aborted iteration may have left a column in it */
+    void batch_begin(int B, double obj_ll, double obj_ul)
+    {
+        kpad = B;
+        const int it_max = parm.it_lim < INT_MAX ? it_beg + parm.it_lim : INT_MAX;
+        cudaMemsetAsync(P->w5, 0, (size_t)m * sizeof(double), P->stream);
+        LAUNCH(P, k_batch_begin, 1, 1, 0, P->ctrl, phase, it_cnt, it_max, refct, upd_cnt, refac_period(),
+               rigorous, bbar_st == 1, cbar_st == 1, binv_st == 1, parm.pricing == GLP_PT_PSE,
+               obj_ll, obj_ul, P->zeta);
+    }
+
+    /* take the loop state back after the batch */
+    void batch_end()
+    {
+        const Ctrl &c = *P->h_ctrl;
+        k = c.k;
+        kpad = 0;
+        P->n_iter += c.n_done;
+        P->n_update += c.upd_cnt - upd_cnt;
+        it_cnt = c.it_cnt; upd_cnt = c.upd_cnt; refct = c.refct; rigorous = c.rigorous;
+        bbar_st = c.bbar_fresh ? 1 : 2;
+        cbar_st = c.cbar_fresh ? 1 : 2;
+        binv_st = c.binv_fresh ? 1 : 2;
+    }
+
     /* eval_bbar, lib/glpspx01.js:473-512,560-563 */
     void eval_bbar()
     {
@@ -657,7 +704,6 @@ struct Loop : Dev {
     /* eval_tcol (+ refine_tcol), lib/glpspx01.js:690-771 */
     void eval_tcol()
     {
-        cudaMemsetAsync(P->w5, 0, (size_t)m * sizeof(double), P->stream);
         LAUNCH(P, k_col_rhs, 4, 256, 0, P->ctrl, m, P->a_ptr, P->a_ind, P->a_val, P->head, P->w5);
         dev_ftran(*this, P->w5, P->tcol);
         if (rigorous) {
@@ -671,7 +717,7 @@ struct Loop : Dev {
     /* eval_rho (+ refine_rho), lib/glpspx01.js:1030-1056 */
     void eval_rho()
     {
-        launch_rho(P, k);
+        launch_rho(P, k + kpad);
         if (rigorous) {
             LAUNCH(P, k_unit, cdiv(m, 256), 256, 0, P->ctrl, m, P->w2);
             GROUP_DISPATCH(gc, LAUNCH(P, k_resid_btran<GG>, cdiv((long)m * GG, 256), 256, 0, P->ctrl, m, P->a_ptr,
@@ -683,13 +729,14 @@ struct Loop : Dev {
 
     void update_basis(int dual)
     {
-        if (k > 0) {
-            dim3 grid(cdiv(k, UPD_TB), cdiv(k, UPD_TC));
+        const int kg = k + kpad;
+        if (kg > 0) {
+            dim3 grid(cdiv(kg, UPD_TB), cdiv(kg, UPD_TC));
             P->next_bytes = 16.0 * k * (double)k;
             LAUNCH(P, k_update_rank1, grid, UPD_TB, 0, P->ctrl, P->T, P->ldt, P->tcol, P->rho, P->slot_pos, P->slot_row);
         }
         LAUNCH(P, k_update_fix, 1, 1024, 0, P->ctrl, m, P->T, P->ldt, P->tcol, P->rho, P->rslot, P->slot_pos,
-               P->cslot, P->slot_row, P->head, P->bind, P->stat, P->type, dual);
+               P->cslot, P->slot_row, P->head, P->bind, P->stat, P->type, P->refsp, dual);
     }
 
     int refactor()
@@ -729,8 +776,8 @@ struct Primal : Loop {
     void chuzc(int set_status)
     {
         P->next_bytes = 17.0 * n;
-        LAUNCH(P, k_chuzc_primal, grid1(n), 256, 0, P->ctrl, n, P->stat, P->cbar, P->gamma, parm.tol_dj,
-               set_status, P->scratch);
+        LAUNCH(P, k_chuzc_primal, red_blocks(n), red_threads(n), 0, P->ctrl, n, P->stat, P->cbar, P->gamma,
+               parm.tol_dj, set_status, P->scratch);
     }
 
     int set_aux_obj(int *cnt)
@@ -828,46 +875,48 @@ struct Primal : Loop {
                 }
                 return stop_on_limit(code);
             }
-            /* ---- one iteration, enqueued as a whole ---- */
-            const int do_gamma = pse && refct > 0;
-            clear_ctrl();
-            chuzc(1);
-            eval_tcol();
-            LAUNCH(P, k_primal_prep, grid1(m), 256, 0, P->ctrl, m, P->head, P->coef, P->tcol, P->refsp, P->cbar,
-                   P->w3, parm.tol_piv, cbar_st == 1, rigorous, do_gamma, P->scratch);
+            /* ---- a batch of iterations, enqueued as a whole; the device keeps the
+                    loop state and turns the rest of the queue into no-ops as soon
+                    as one of the reference's exceptional branches is met ---- */
+            const int B = batch_size();
+            batch_begin(B, -DBL_MAX, +DBL_MAX);
             const double rtol = (parm.r_test == GLP_RT_STD ? 0.0 : 0.30 * parm.tol_bnd);
-            for (int pass = 1; pass <= 2; pass++) {
-                P->next_bytes = 45.0 * m;
-                LAUNCH(P, k_ratio_primal, grid1(m), 256, 0, P->ctrl, pass, m, P->type, P->lb, P->ub, P->coef,
-                       P->head, P->bbar, P->tcol, (const int *)nullptr, m, rtol, rigorous, P->scratch);
+            for (int b = 0; b < B; b++) {
+                chuzc(1);
+                eval_tcol();
+                LAUNCH(P, k_primal_prep, red_blocks(m), red_threads(m), 0, P->ctrl, m, P->head, P->coef, P->tcol,
+                       P->refsp, P->cbar, P->w3, parm.tol_piv, P->scratch);
+                if (red_blocks(m) == 1) {
+                    P->next_bytes = 90.0 * m;
+                    LAUNCH(P, k_ratio_primal, 1, 1024, 0, P->ctrl, 0, m, P->type, P->lb, P->ub, P->coef, P->head,
+                           P->bbar, P->tcol, (const int *)nullptr, m, rtol, P->scratch);
+                } else
+                    for (int pass = 1; pass <= 2; pass++) {
+                        P->next_bytes = 45.0 * m;
+                        LAUNCH(P, k_ratio_primal, grid1(m), 256, 0, P->ctrl, pass, m, P->type, P->lb, P->ub, P->coef,
+                               P->head, P->bbar, P->tcol, (const int *)nullptr, m, rtol, P->scratch);
+                    }
+                eval_rho();
+                if (pse) dev_btran(*this, P->w3, P->w2, 1);
+                P->next_bytes = 12.0 * P->nnz * (1.0 - (double)k / n) + 13.0 * n + 8.0 * m;
+                GROUP_DISPATCH(gc, LAUNCH(P, k_trow<GG>, cdiv((long)n * GG, 256), 256, 0, P->ctrl, m, n, P->a_ptr,
+                                          P->a_ind, P->a_val, P->head, P->stat, P->rho,
+                                          pse ? P->w2 : (const double *)nullptr, P->trow, P->svec, 0));
+                LAUNCH(P, k_primal_piv, 1, 1, 0, P->ctrl, m, P->head, P->trow, P->cbar, P->coef, P->tcol);
+                LAUNCH(P, k_primal_update, cdiv(std::max(m, n), 256), 256, 0, P->ctrl, m, n, P->head, P->stat,
+                       P->type, P->lb, P->ub, P->coef, P->bbar, P->cbar, P->gamma, P->refsp, P->tcol, P->trow,
+                       P->svec, P->w5);
+                update_basis(0);
             }
-            eval_rho();
-            if (do_gamma) dev_btran(*this, P->w3, P->w2);
-            P->next_bytes = 12.0 * P->nnz * (1.0 - (double)k / n) + 13.0 * n + 8.0 * m;
-            GROUP_DISPATCH(gc, LAUNCH(P, k_trow<GG>, cdiv((long)n * GG, 256), 256, 0, P->ctrl, m, n, P->a_ptr,
-                                      P->a_ind, P->a_val, P->head, P->stat, P->rho,
-                                      do_gamma ? P->w2 : (const double *)nullptr, P->trow, P->svec, 0));
-            LAUNCH(P, k_primal_piv, 1, 1, 0, P->ctrl, m, P->head, P->trow, P->cbar, P->coef, P->tcol,
-                   binv_st == 1, rigorous);
-            LAUNCH(P, k_primal_update, cdiv(std::max(m, n), 256), 256, 0, P->ctrl, m, n, P->head, P->stat, P->type,
-                   P->lb, P->ub, P->coef, P->bbar, P->cbar, P->gamma, P->refsp, P->tcol, P->trow, P->svec, do_gamma);
-            update_basis(0);
             if ((rc = sync_ctrl(P))) return rc;
             trace_iter("primal");
             const Ctrl &c = *P->h_ctrl;
-            k = c.k;
+            batch_end();
             switch (c.status) {
-            case ST_OK:
-                bbar_st = 2;
-                if (c.p >= 0) {
-                    cbar_st = 2;
-                    if (do_gamma) refct--;
-                    binv_st = 2;
-                    upd_cnt++; P->n_update++;
-                    if (upd_cnt >= refac_period()) binv_st = 0;
-                }
-                it_cnt++; P->n_iter++;
-                if (rigorous > 0) rigorous--;
+            case ST_OK: case ST_LIMIT: case ST_REFSP:
+                break;
+            case ST_REFAC:
+                binv_st = 0;
                 break;
             case ST_NONE1:
                 if (bbar_st != 1 || cbar_st != 1) {
@@ -1049,50 +1098,52 @@ struct Dual : Loop {
                 }
                 return stop_on_limit(code);
             }
-            /* ---- one iteration ---- */
-            const int do_gamma = pse && refct > 0;
-            clear_ctrl();
-            P->next_bytes = 37.0 * m;
-            LAUNCH(P, k_chuzr_dual, grid1(m), 256, 0, P->ctrl, m, P->type, P->lb, P->ub, P->head, P->bbar,
-                   P->gamma, parm.tol_bnd, 1, P->scratch);
-            eval_rho();
-            P->next_bytes = 12.0 * P->nnz * (1.0 - (double)k / n) + 13.0 * n + 8.0 * m;
-            GROUP_DISPATCH(gc, LAUNCH(P, k_trow<GG>, cdiv((long)n * GG, 256), 256, 0, P->ctrl, m, n, P->a_ptr,
-                                      P->a_ind, P->a_val, P->head, P->stat, P->rho, (const double *)nullptr,
-                                      P->trow, P->svec, 1));
-            LAUNCH(P, k_dual_rowmax, 1, 1, 0, P->ctrl, parm.tol_bnd); /* sic: tol_bnd, lib/glpspx02.js:1851 */
+            /* ---- a batch of iterations (see the primal loop) ---- */
+            const int B = batch_size();
+            batch_begin(B, parm.obj_ll, parm.obj_ul);
             const double rtol = (parm.r_test == GLP_RT_STD ? 0.0 : 0.30 * parm.tol_dj);
-            for (int pass = 1; pass <= 2; pass++) {
-                P->next_bytes = 17.0 * n;
-                LAUNCH(P, k_ratio_dual, grid1(n), 256, 0, P->ctrl, pass, P->stat, P->cbar, P->trow,
-                       (const int *)nullptr, n, rtol, rigorous, P->scratch);
+            for (int b = 0; b < B; b++) {
+                P->next_bytes = 37.0 * m;
+                LAUNCH(P, k_chuzr_dual, red_blocks(m), red_threads(m), 0, P->ctrl, m, P->type, P->lb, P->ub, P->head,
+                       P->bbar, P->gamma, parm.tol_bnd, 1, P->scratch);
+                eval_rho();
+                P->next_bytes = 12.0 * P->nnz * (1.0 - (double)k / n) + 13.0 * n + 8.0 * m;
+                GROUP_DISPATCH(gc, LAUNCH(P, k_trow<GG>, cdiv((long)n * GG, 256), 256, 0, P->ctrl, m, n, P->a_ptr,
+                                          P->a_ind, P->a_val, P->head, P->stat, P->rho, (const double *)nullptr,
+                                          P->trow, P->svec, 1));
+                LAUNCH(P, k_dual_rowmax, 1, 1, 0, P->ctrl, parm.tol_bnd); /* sic: tol_bnd, lib/glpspx02.js:1851 */
+                if (red_blocks(n) == 1) {
+                    P->next_bytes = 34.0 * n;
+                    LAUNCH(P, k_ratio_dual, 1, 1024, 0, P->ctrl, 0, P->stat, P->cbar, P->trow, (const int *)nullptr,
+                           n, rtol, P->scratch);
+                } else
+                    for (int pass = 1; pass <= 2; pass++) {
+                        P->next_bytes = 17.0 * n;
+                        LAUNCH(P, k_ratio_dual, grid1(n), 256, 0, P->ctrl, pass, P->stat, P->cbar, P->trow,
+                               (const int *)nullptr, n, rtol, P->scratch);
+                    }
+                eval_tcol();
+                LAUNCH(P, k_dual_prep, red_blocks(n), red_threads(n), 0, P->ctrl, m, n, P->head, P->refsp, P->trow,
+                       P->tcol, P->cbar, P->stat, P->zeta, P->scratch);
+                if (pse) {
+                    GROUP_DISPATCH(gr, LAUNCH(P, k_dual_gamma_rhs<GG>, cdiv((long)m * GG, 256), 256, 0, P->ctrl, m,
+                                              P->at_ptr, P->at_ind, P->at_val, P->bind, P->refsp, P->trow, P->w3, 1));
+                    dev_ftran(*this, P->w3, P->w2, 1);
+                }
+                LAUNCH(P, k_dual_update, cdiv(std::max(m, n), 256), 256, 0, P->ctrl, m, n, P->head, P->stat, P->type,
+                       P->lb, P->ub, P->bbar, P->cbar, P->gamma, P->refsp, P->tcol, P->trow, P->w2, P->w5);
+                update_basis(1);
             }
-            eval_tcol();
-            LAUNCH(P, k_dual_prep, grid1(n), 256, 0, P->ctrl, m, n, P->head, P->refsp, P->trow, P->tcol, P->cbar,
-                   P->stat, P->zeta, binv_st == 1, rigorous, do_gamma, P->scratch);
-            if (do_gamma) {
-                GROUP_DISPATCH(gr, LAUNCH(P, k_dual_gamma_rhs<GG>, cdiv((long)m * GG, 256), 256, 0, P->ctrl, m,
-                                          P->at_ptr, P->at_ind, P->at_val, P->bind, P->refsp, P->trow, P->w3));
-                dev_ftran(*this, P->w3, P->w2);
-            }
-            LAUNCH(P, k_dual_update, cdiv(std::max(m, n), 256), 256, 0, P->ctrl, m, n, P->head, P->stat, P->type,
-                   P->lb, P->ub, P->bbar, P->cbar, P->gamma, P->refsp, P->tcol, P->trow, P->w2, do_gamma);
-            if (do_gamma) LAUNCH(P, k_dual_drop_refsp, 1, 1, 0, P->ctrl, P->head, P->type, P->refsp);
-            update_basis(1);
             if ((rc = sync_ctrl(P))) return rc;
             trace_iter("dual");
             const Ctrl &c = *P->h_ctrl;
-            k = c.k;
+            batch_end();
+            obj_track = c.obj;
             switch (c.status) {
-            case ST_OK:
-                bbar_st = 2; cbar_st = 2;
-                obj_track = c.obj;
-                if (do_gamma) refct--;
-                binv_st = 2;
-                upd_cnt++; P->n_update++;
-                if (upd_cnt >= refac_period()) binv_st = 0;
-                it_cnt++; P->n_iter++;
-                if (rigorous > 0) rigorous--;
+            case ST_OK: case ST_LIMIT: case ST_REFSP: case ST_OBJLIM:
+                break;
+            case ST_REFAC:
+                binv_st = 0;
                 break;
             case ST_NONE1:
                 if (bbar_st != 1 || cbar_st != 1) {
