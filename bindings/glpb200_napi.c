@@ -1,0 +1,128 @@
+/* glpb200_napi.c -- thin N-API addon over libglpb200.so (include/glpb200.h).
+ *
+ * NOT built or tested in this repository's image (no Node.js, no node_api.h);
+ * it is the binding a glpk.js maintainer would add.  It is written against the
+ * stable N-API C signatures only and contains no logic: typed arrays in, typed
+ * arrays out, one exported function per C-ABI entry point.
+ *
+ *   build:  cc -shared -fPIC glpb200_napi.c -I../include -I$NODE/include/node \
+ *              -L../glpk.js_b200 -lglpb200 -o glpb200.node
+ */
+#include <node_api.h>
+#include <stdlib.h>
+#include "glpb200.h"
+
+#define NAPI_OK(call) do { if ((call) != napi_ok) { napi_throw_error(env, NULL, #call); return NULL; } } while (0)
+
+static void *typed(napi_env env, napi_value v, size_t *len)
+{
+    napi_typedarray_type t; void *data = NULL; napi_value ab; size_t off;
+    bool is = false;
+    if (napi_is_typedarray(env, v, &is) != napi_ok || !is) return NULL;
+    if (napi_get_typedarray_info(env, v, &t, len, &data, &ab, &off) != napi_ok) return NULL;
+    return data;
+}
+
+static void finalize_handle(napi_env env, void *data, void *hint) { (void)env; (void)hint; glpb_destroy((glpb_prob *)data); }
+
+/* create(m, n, dir, c0, Int32 type, F64 lb, F64 ub, F64 coef, Int32 kind, F64 rii, F64 sjj,
+          Int32 A_ptr, Int32 A_ind, F64 A_val, device) -> external handle */
+static napi_value Create(napi_env env, napi_callback_info info)
+{
+    size_t argc = 15; napi_value a[15];
+    NAPI_OK(napi_get_cb_info(env, info, &argc, a, NULL, NULL));
+    int32_t m, n, dir, device; double c0; size_t len, nnz;
+    NAPI_OK(napi_get_value_int32(env, a[0], &m));
+    NAPI_OK(napi_get_value_int32(env, a[1], &n));
+    NAPI_OK(napi_get_value_int32(env, a[2], &dir));
+    NAPI_OK(napi_get_value_double(env, a[3], &c0));
+    NAPI_OK(napi_get_value_int32(env, a[14], &device));
+    int *type = typed(env, a[4], &len); double *lb = typed(env, a[5], &len), *ub = typed(env, a[6], &len);
+    double *coef = typed(env, a[7], &len); int *kind = typed(env, a[8], &len);
+    double *rii = typed(env, a[9], &len), *sjj = typed(env, a[10], &len);
+    int *ptr = typed(env, a[11], &len), *ind = typed(env, a[12], &nnz); double *val = typed(env, a[13], &nnz);
+    glpb_prob *P = glpb_create(m, n, (int)nnz, dir, c0, type, lb, ub, coef, kind, rii, sjj, ptr, ind, val, device);
+    if (!P) { napi_throw_error(env, NULL, glpb_last_error()); return NULL; }
+    napi_value ext;
+    NAPI_OK(napi_create_external(env, P, finalize_handle, NULL, &ext));
+    return ext;
+}
+
+static glpb_prob *handle(napi_env env, napi_value v) { void *p = NULL; napi_get_value_external(env, v, &p); return (glpb_prob *)p; }
+
+static napi_value ret_int(napi_env env, int v) { napi_value r; napi_create_int32(env, v, &r); return r; }
+
+/* setBasis(h, Int32 stat[m+n]) ; setBounds(h, Int32 k, Int32 type, F64 lb, F64 ub) */
+static napi_value SetBasis(napi_env env, napi_callback_info info)
+{
+    size_t argc = 2, len; napi_value a[2];
+    NAPI_OK(napi_get_cb_info(env, info, &argc, a, NULL, NULL));
+    return ret_int(env, glpb_set_basis(handle(env, a[0]), typed(env, a[1], &len)));
+}
+
+static napi_value SetBounds(napi_env env, napi_callback_info info)
+{
+    size_t argc = 5, cnt, len; napi_value a[5];
+    NAPI_OK(napi_get_cb_info(env, info, &argc, a, NULL, NULL));
+    int *k = typed(env, a[1], &cnt);
+    return ret_int(env, glpb_set_bounds(handle(env, a[0]), (int)cnt, k, typed(env, a[2], &len),
+                                        typed(env, a[3], &len), typed(env, a[4], &len)));
+}
+
+/* simplex(h, Int32 ip[9], F64 dp[5]) : the SMCP fields packed by the facade */
+static napi_value Simplex(napi_env env, napi_callback_info info)
+{
+    size_t argc = 3, len; napi_value a[3];
+    NAPI_OK(napi_get_cb_info(env, info, &argc, a, NULL, NULL));
+    int *ip = typed(env, a[1], &len); double *dp = typed(env, a[2], &len);
+    glpb_smcp s = { ip[0], ip[1], ip[2], ip[3], dp[0], dp[1], dp[2], dp[3], dp[4], ip[4], ip[5], ip[6], ip[7], ip[8] };
+    int rc = glpb_simplex(handle(env, a[0]), &s);
+    if (rc < 0) { napi_throw_error(env, NULL, glpb_last_error()); return NULL; }
+    return ret_int(env, rc);
+}
+
+/* intopt(h, Int32 ip[8], F64 dp[3]) */
+static napi_value Intopt(napi_env env, napi_callback_info info)
+{
+    size_t argc = 3, len; napi_value a[3];
+    NAPI_OK(napi_get_cb_info(env, info, &argc, a, NULL, NULL));
+    int *ip = typed(env, a[1], &len); double *dp = typed(env, a[2], &len);
+    glpb_iocp s = { ip[0], ip[1], ip[2], dp[0], dp[1], ip[3], ip[4], ip[5], ip[6], dp[2], ip[7], -1 };
+    int rc = glpb_intopt(handle(env, a[0]), &s);
+    if (rc < 0) { napi_throw_error(env, NULL, glpb_last_error()); return NULL; }
+    return ret_int(env, rc);
+}
+
+/* getSolution(h, Int32 stat, F64 prim, F64 dual, Int32 head, Int32 ints[4], F64 obj[1]) */
+static napi_value GetSolution(napi_env env, napi_callback_info info)
+{
+    size_t argc = 7, len; napi_value a[7];
+    NAPI_OK(napi_get_cb_info(env, info, &argc, a, NULL, NULL));
+    int *ints = typed(env, a[5], &len); double *obj = typed(env, a[6], &len);
+    return ret_int(env, glpb_get_solution(handle(env, a[0]), typed(env, a[1], &len), typed(env, a[2], &len),
+                                          typed(env, a[3], &len), typed(env, a[4], &len), &ints[0], &ints[1], obj,
+                                          &ints[2], &ints[3]));
+}
+
+/* getMip(h, Int32 st[1], F64 obj[1], F64 mipx[m+n]) */
+static napi_value GetMip(napi_env env, napi_callback_info info)
+{
+    size_t argc = 4, len; napi_value a[4];
+    NAPI_OK(napi_get_cb_info(env, info, &argc, a, NULL, NULL));
+    return ret_int(env, glpb_get_mip(handle(env, a[0]), typed(env, a[1], &len), typed(env, a[2], &len),
+                                     typed(env, a[3], &len), NULL));
+}
+
+static napi_value Init(napi_env env, napi_value exports)
+{
+    napi_property_descriptor d[] = {
+        { "create", 0, Create, 0, 0, 0, napi_default, 0 }, { "setBasis", 0, SetBasis, 0, 0, 0, napi_default, 0 },
+        { "setBounds", 0, SetBounds, 0, 0, 0, napi_default, 0 }, { "simplex", 0, Simplex, 0, 0, 0, napi_default, 0 },
+        { "intopt", 0, Intopt, 0, 0, 0, napi_default, 0 }, { "getSolution", 0, GetSolution, 0, 0, 0, napi_default, 0 },
+        { "getMip", 0, GetMip, 0, 0, 0, napi_default, 0 },
+    };
+    napi_define_properties(env, exports, sizeof d / sizeof d[0], d);
+    return exports;
+}
+
+NAPI_MODULE(NODE_GYP_MODULE_NAME, Init)

@@ -1,0 +1,86 @@
+/* glpk_b200.js -- JS facade: keeps glpk.js's public API and its glp_prob object,
+ * and replaces solve_lp / solve_mip (lib/glpapi06.js:3-39, lib/glpapi09.js:62-114)
+ * by calls into the N-API addon.  Everything above those two call sites
+ * (validation, presolve, scaling, getters) stays the reference's JavaScript.
+ * NOT runnable in this repository's image (no Node.js); see INTEGRATION.md.
+ *
+ *   const glpk = require('glpk');              // the reference
+ *   require('./glpk_b200').install(glpk);      // glp_simplex / glp_intopt now run on the GPU
+ */
+'use strict';
+const addon = require('./glpb200.node');
+
+function marshal(glp, P) {
+    const m = glp.glp_get_num_rows(P), n = glp.glp_get_num_cols(P);
+    const type = new Int32Array(m + n), lb = new Float64Array(m + n), ub = new Float64Array(m + n);
+    const coef = new Float64Array(n), kind = new Int32Array(n), rii = new Float64Array(m), sjj = new Float64Array(n);
+    const stat = new Int32Array(m + n);
+    for (let i = 1; i <= m; i++) {
+        type[i - 1] = glp.glp_get_row_type(P, i); lb[i - 1] = P.row[i].lb; ub[i - 1] = P.row[i].ub;
+        rii[i - 1] = glp.glp_get_rii(P, i); stat[i - 1] = glp.glp_get_row_stat(P, i);
+    }
+    const ptr = new Int32Array(n + 1), ind = [], val = [];
+    for (let j = 1; j <= n; j++) {
+        const k = m + j - 1, col = P.col[j];
+        type[k] = col.type; lb[k] = col.lb; ub[k] = col.ub; coef[j - 1] = col.coef;
+        kind[j - 1] = col.kind; sjj[j - 1] = col.sjj; stat[k] = col.stat;
+        ptr[j - 1] = ind.length;
+        for (let a = col.ptr; a != null; a = a.c_next) { ind.push(a.row.i - 1); val.push(a.val); }   // list order
+    }
+    ptr[n] = ind.length;
+    return { m, n, type, lb, ub, coef, kind, rii, sjj, stat, ptr, ind: Int32Array.from(ind), val: Float64Array.from(val) };
+}
+
+function device(glp, P) {
+    const d = marshal(glp, P);
+    if (!P._glpb || P._glpb_nnz !== P.nnz) {          // matrix changed: new handle
+        P._glpb = addon.create(d.m, d.n, P.dir, P.c0, d.type, d.lb, d.ub, d.coef, d.kind, d.rii, d.sjj,
+                               d.ptr, d.ind, d.val, 0);
+        P._glpb_nnz = P.nnz;
+    } else {
+        const k = Int32Array.from({ length: d.m + d.n }, (_, i) => i + 1);
+        addon.setBounds(P._glpb, k, d.type, d.lb, d.ub);
+    }
+    addon.setBasis(P._glpb, d.stat);
+    return d;
+}
+
+function pull(glp, P, d) {
+    const m = d.m, n = d.n;
+    const stat = new Int32Array(m + n), prim = new Float64Array(m + n), dual = new Float64Array(m + n);
+    const head = new Int32Array(m), ints = new Int32Array(4), obj = new Float64Array(1);
+    addon.getSolution(P._glpb, stat, prim, dual, head, ints, obj);
+    P.pbs_stat = ints[0]; P.dbs_stat = ints[1]; P.it_cnt = ints[2]; P.some = ints[3]; P.obj_val = obj[0];
+    for (let i = 1; i <= m; i++) { const r = P.row[i]; r.stat = stat[i - 1]; r.prim = prim[i - 1]; r.dual = dual[i - 1]; r.bind = 0; }
+    for (let j = 1; j <= n; j++) { const c = P.col[j], k = m + j - 1; c.stat = stat[k]; c.prim = prim[k]; c.dual = dual[k]; c.bind = 0; }
+    for (let i = 1; i <= m; i++) { P.head[i] = head[i - 1]; const k = head[i - 1]; if (k <= m) P.row[k].bind = i; else P.col[k - m].bind = i; }
+    P.valid = 1;
+}
+
+exports.install = function (glp) {
+    const simplex0 = glp.glp_simplex, intopt0 = glp.glp_intopt;
+    glp.glp_simplex = function (P, parm) {
+        parm = parm || new glp.SMCP();
+        if (parm.presolve) return simplex0(P, parm);      // the JS presolver calls back into solve_lp
+        const d = device(glp, P);
+        const ret = addon.simplex(P._glpb,
+            Int32Array.from([parm.msg_lev, parm.meth, parm.pricing, parm.r_test, parm.it_lim, parm.tm_lim, parm.out_frq, parm.out_dly, 0]),
+            Float64Array.from([parm.tol_bnd, parm.tol_dj, parm.tol_piv, parm.obj_ll, parm.obj_ul]));
+        pull(glp, P, d);
+        return ret;
+    };
+    glp.glp_intopt = function (P, parm) {
+        parm = parm || new glp.IOCP();
+        if (parm.presolve || parm.cb_func) return intopt0(P, parm);   // callbacks: host-driven reference loop
+        const d = device(glp, P);
+        const ret = addon.intopt(P._glpb,
+            Int32Array.from([parm.msg_lev, parm.br_tech, parm.bt_tech, parm.tm_lim, parm.out_frq, parm.out_dly, parm.pp_tech, 0]),
+            Float64Array.from([parm.tol_int, parm.tol_obj, parm.mip_gap]));
+        const st = new Int32Array(1), obj = new Float64Array(1), x = new Float64Array(d.m + d.n);
+        addon.getMip(P._glpb, st, obj, x);
+        P.mip_stat = st[0]; P.mip_obj = obj[0];
+        for (let i = 1; i <= d.m; i++) P.row[i].mipx = x[i - 1];
+        for (let j = 1; j <= d.n; j++) P.col[j].mipx = x[d.m + j - 1];
+        return ret;
+    };
+};
