@@ -145,6 +145,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-full", action="store_true", help="profile the whole solve, not its first 1500 iterations")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
@@ -220,26 +221,35 @@ def main():
         max_ms, all_it = my_ms, tot_it
     value = all_it / (max_ms / 1000.0)
 
-    # ---- profiled extra step: per-kernel device time (CUDA events on the solve stream) ----
+    # ---- profiled extra step: per-kernel device time (CUDA events on the solve stream) and,
+    #      inside the persistent engine, per-phase time (SM cycle stamps between grid barriers
+    #      scaled to the CUDA-event time of the engine launches) ----
     P.std_basis()
     P.set_profile(1)
-    P.simplex(meth=meth, it_lim=min(int(iters[-1]), 1500))
+    P.simplex(meth=meth, it_lim=int(iters[-1]) if args.profile_full else min(int(iters[-1]), 1500))
     prof = P.profile()
     P.set_profile(0)
-    tot_prof_ms = sum(v["ms"] for v in prof.values()) or 1.0
-    with_bytes = {k: v for k, v in prof.items() if v["bytes"] > 0}
+    units = {k: v for k, v in prof.items() if not k.startswith("k_engine_")}     # engine split into phases
+    tot_prof_ms = sum(v["ms"] for v in units.values()) or 1.0
+    with_bytes = {k: v for k, v in units.items() if v["bytes"] > 0 and v["count"] > 0}
     top = max(with_bytes, key=lambda k: with_bytes[k]["ms"]) if with_bytes else None
     peak, peak_src = peaks()
     roofline = None
     if top:
         v = prof[top]
         ach = (v["bytes"] / v["count"]) / (v["ms"] / v["count"] * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "kernel": top, "achieved": ach, "peak": peak, "unit": "GB/s",
+        eng = "k_engine_primal:" if w["meth"] == "primal" else "k_engine_dual:"
+        roofline = {"bound": "hbm", "kernel": (eng + top[4:]) if top.startswith("eng_") else top,
+                    "achieved": ach, "peak": peak, "unit": "GB/s",
                     "frac": ach / peak, "traffic": None, "peak_source": peak_src,
                     "bytes_per_launch": v["bytes"] / v["count"], "us_per_launch": 1000.0 * v["ms"] / v["count"],
                     "share_of_device_time": v["ms"] / tot_prof_ms,
+                    "note": "eng_* = phases of the persistent engine (one 'launch' = one iteration's phase)",
                     "kernel_shares": {k: round(x["ms"] / tot_prof_ms, 4) for k, x in
-                                      sorted(prof.items(), key=lambda kv: -kv[1]["ms"])[:8]}}
+                                      sorted(units.items(), key=lambda kv: -kv[1]["ms"])[:10]},
+                    "phase_table": {k: {"us": round(1000.0 * x["ms"] / max(1, x["count"]), 3),
+                                        "GBps": round(x["bytes"] / max(1e-9, x["ms"]) / 1e6, 1)}
+                                    for k, x in sorted(units.items()) if k.startswith("eng_")}}
     P.close()
 
     # ---- e2e leg: host buffers every step ----

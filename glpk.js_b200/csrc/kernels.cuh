@@ -172,19 +172,18 @@ __device__ void iter_end(Ctrl *ctrl, bool basis_changed, int dual)
 /* pricing                                                            */
 /* ------------------------------------------------------------------ */
 
-/* chuzc (primal pricing), lib/glpspx01.js:646-688.
-   Algorithmic bytes: 17 per column (stat 1 + cbar 8 + gamma 8). */
-__global__ void k_chuzc_primal(Ctrl *ctrl, int n, const signed char *__restrict__ stat,
-                               const double *__restrict__ cbar, const double *__restrict__ gamma,
-                               double tol_dj, int set_status, Key *scratch)
+/* chuzc (primal pricing), lib/glpspx01.js:646-688: the scan over columns
+   start, start+stride, ...  Shared by the stand-alone kernel and the persistent
+   iteration engine; (jx, stx) overrides the status of one column whose header
+   update is still in flight (engine), jx = -1 otherwise. */
+__device__ __forceinline__ void scan_chuzc_primal(Key &v, int start, int stride, int n,
+                                                  const signed char *stat, const double *cbar,
+                                                  const double *gamma, double tol_dj, int jx, int stx)
 {
-    if (ctrl->status != ST_OK) return;
-    Key none = {0.0, 0.0, 0.0, INT_MAX, 0};
-    Key v = none;
-    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+    for (int j = start; j < n; j += stride) {
         double dj = cbar[j];
         bool ok;
-        switch (stat[j]) {
+        switch (j == jx ? stx : (int)stat[j]) {
         case GLP_NL: ok = !(dj >= -tol_dj); break;
         case GLP_NU: ok = !(dj <= +tol_dj); break;
         case GLP_NF: ok = !(-tol_dj <= dj && dj <= +tol_dj); break;
@@ -195,6 +194,18 @@ __global__ void k_chuzc_primal(Ctrl *ctrl, int n, const signed char *__restrict_
             if (v.a < temp) { v.a = temp; v.pos = j; }
         }
     }
+}
+
+/* Algorithmic bytes: 17 per column (stat 1 + cbar 8 + gamma 8). */
+__global__ void k_chuzc_primal(Ctrl *ctrl, int n, const signed char *__restrict__ stat,
+                               const double *__restrict__ cbar, const double *__restrict__ gamma,
+                               double tol_dj, int set_status, Key *scratch)
+{
+    if (ctrl->status != ST_OK) return;
+    Key none = {0.0, 0.0, 0.0, INT_MAX, 0};
+    Key v = none;
+    scan_chuzc_primal(v, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x, n, stat, cbar, gamma,
+                      tol_dj, -1, 0);
     grid_reduce(v, none, scratch, &ctrl->ticket[0], CombArgMax(), [=](const Key &r) {
         ctrl->q = (r.a > 0.0 && r.pos != INT_MAX) ? r.pos : P_NONE;
         ctrl->big = 0.0;
@@ -202,19 +213,15 @@ __global__ void k_chuzc_primal(Ctrl *ctrl, int n, const signed char *__restrict_
     });
 }
 
-/* chuzr (dual pricing), lib/glpspx02.js:572-625.
-   Algorithmic bytes: 37 per row (head 4, type 1, lb 8, ub 8, bbar 8, gamma 8). */
-__global__ void k_chuzr_dual(Ctrl *ctrl, int m, const signed char *__restrict__ type,
-                             const double *__restrict__ lb, const double *__restrict__ ub,
-                             const int *__restrict__ head, const double *__restrict__ bbar,
-                             const double *__restrict__ gamma, double tol_bnd, int set_status,
-                             Key *scratch)
+/* chuzr (dual pricing), lib/glpspx02.js:572-625: the scan over basic positions.
+   (ix, kx) overrides head[ix] (engine: header update in flight), ix = -1 otherwise. */
+__device__ __forceinline__ void scan_chuzr_dual(Key &v, int start, int stride, int m,
+                                                const signed char *type, const double *lb,
+                                                const double *ub, const int *head, const double *bbar,
+                                                const double *gamma, double tol_bnd, int ix, int kx)
 {
-    if (ctrl->status != ST_OK) return;
-    Key none = {0.0, 0.0, 0.0, INT_MAX, 0};
-    Key v = none;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
-        int k = head[i];
+    for (int i = start; i < m; i += stride) {
+        int k = (i == ix) ? kx : head[i];
         int t = type[k];
         double ri = 0.0, bi = bbar[i];
         if (t == GLP_LO || t == GLP_DB || t == GLP_FX) {
@@ -232,6 +239,20 @@ __global__ void k_chuzr_dual(Ctrl *ctrl, int m, const signed char *__restrict__ 
             if (v.a < temp) { v.a = temp; v.b = ri; v.pos = i; }
         }
     }
+}
+
+/* Algorithmic bytes: 37 per row (head 4, type 1, lb 8, ub 8, bbar 8, gamma 8). */
+__global__ void k_chuzr_dual(Ctrl *ctrl, int m, const signed char *__restrict__ type,
+                             const double *__restrict__ lb, const double *__restrict__ ub,
+                             const int *__restrict__ head, const double *__restrict__ bbar,
+                             const double *__restrict__ gamma, double tol_bnd, int set_status,
+                             Key *scratch)
+{
+    if (ctrl->status != ST_OK) return;
+    Key none = {0.0, 0.0, 0.0, INT_MAX, 0};
+    Key v = none;
+    scan_chuzr_dual(v, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x, m, type, lb, ub, head,
+                    bbar, gamma, tol_bnd, -1, 0);
     grid_reduce(v, none, scratch, &ctrl->ticket[0], CombArgMax(), [=](const Key &r) {
         bool found = (r.a > 0.0 && r.pos != INT_MAX);
         ctrl->p = found ? r.pos : P_NONE;
@@ -245,32 +266,20 @@ __global__ void k_chuzr_dual(Ctrl *ctrl, int m, const signed char *__restrict__ 
 /* ratio tests                                                        */
 /* ------------------------------------------------------------------ */
 
-/* chuzr (primal ratio test), lib/glpspx01.js:808-1028, one pass per launch.
-   ind == NULL: dense mode over positions 0..num-1 with the significance mask
-   |tcol| >= ctrl->eps; ind != NULL: the caller's sorted list (kernel parity).
-   Ties are broken by list position, as the sequential loop does.
+/* chuzr (primal ratio test), lib/glpspx01.js:808-1028: scan of one pass over
+   list positions start, start+stride, ...  ind == NULL: dense mode over
+   positions 0..num-1 with the significance mask |tcol| >= eps; ind != NULL:
+   the caller's sorted list (kernel parity).  Ties are broken by list position,
+   as the sequential loop does.  Shared by the stand-alone kernel and the engine.
    Algorithmic bytes: 49 per examined entry and pass. */
-__device__ __forceinline__ void ratio_primal_body(Ctrl *ctrl, int pass, int m, const signed char *__restrict__ type,
-                               const double *__restrict__ lb, const double *__restrict__ ub,
-                               const double *__restrict__ coef, const int *__restrict__ head,
-                               const double *__restrict__ bbar, const double *__restrict__ tcol,
-                               const int *__restrict__ ind, int num, double rtol,
-                               Key *scratch)
+__device__ __forceinline__ void scan_ratio_primal(Key &v, int start, int stride, int pass, int phase,
+                                                  double s, double eps, double tmax, double rtol,
+                                                  const signed char *type, const double *lb,
+                                                  const double *ub, const double *coef, const int *head,
+                                                  const double *bbar, const double *tcol,
+                                                  const int *ind, int num)
 {
-    if (ctrl->status != ST_OK) return;
-    const int rigorous = ctrl->rigorous;
-    if (pass == 2 && ctrl->skip2) return;
-    const int q = ctrl->q, phase = ctrl->phase;
-    const double s = (ctrl->d1 > 0.0 ? -1.0 : +1.0); /* d1 holds the (corrected) cbar[q] */
-    const double eps = (ind == nullptr ? ctrl->eps : 0.0);
-    const double tmax = ctrl->tmax;
-    const int kq = head[m + q];
-    Key none = {DBL_MAX, 0.0, 0.0, INT_MAX, 0};
-    Key v = none;
-    if (pass == 1 && blockIdx.x == 0 && threadIdx.x == 0 && type[kq] == GLP_DB) {
-        v.a = __dsub_rn(ub[kq], lb[kq]); v.b = 1.0; v.pos = -1; v.aux = 0;
-    }
-    for (int pos = blockIdx.x * blockDim.x + threadIdx.x; pos < num; pos += gridDim.x * blockDim.x) {
+    for (int pos = start; pos < num; pos += stride) {
         int i = ind ? ind[pos] : pos;
         double tc = tcol[i];
         if (tc == 0.0 || fabs(tc) < eps) continue;
@@ -311,29 +320,59 @@ __device__ __forceinline__ void ratio_primal_body(Ctrl *ctrl, int pass, int m, c
         if (pass == 1) CombRatio1()(v, c);
         else if (t <= tmax) CombRatio2()(v, c);
     }
-    auto fin = [=](const Key &r) {
-        int p, p_stat = r.aux;
-        double teta = r.a;
-        if (r.pos == INT_MAX) p = P_NONE;
-        else if (r.pos == -1) p = P_FLIP;
-        else p = ind ? ind[r.pos] : r.pos;
-        if (pass == 1) {
-            ctrl->skip2 = (rtol == 0.0 || p < 0 || teta == 0.0);
-            ctrl->tmax = teta;
-            if (!ctrl->skip2) { ctrl->p = p; return; }
-        }
-        if (p >= 0 && type[head[p]] == GLP_FX) p_stat = GLP_NS;
-        ctrl->p = p;
-        ctrl->p_stat = p_stat;
-        ctrl->teta = __dmul_rn(s, teta);
-        if (p == P_NONE) { ctrl->status = ST_NONE2; return; }
-        if (p >= 0) {
-            double piv = tcol[p];
-            double e5 = 1e-5 * (1.0 + 0.01 * ctrl->tcol_max);
-            ctrl->piv1 = piv;
-            if (fabs(piv) < e5 && !rigorous) ctrl->status = ST_PIVSMALL;
-        }
-    };
+}
+
+/* what the reference does with the winner of a pass (chuzr, :1009-1028, and
+   the pivot-size test of the main loop, :1960-1975) */
+__device__ __forceinline__ void fin_ratio_primal(Ctrl *ctrl, const Key &r, int pass, double s, double rtol,
+                                                 const signed char *type, const int *head,
+                                                 const double *tcol, const int *ind)
+{
+    int p, p_stat = r.aux;
+    double teta = r.a;
+    if (r.pos == INT_MAX) p = P_NONE;
+    else if (r.pos == -1) p = P_FLIP;
+    else p = ind ? ind[r.pos] : r.pos;
+    if (pass == 1) {
+        ctrl->skip2 = (rtol == 0.0 || p < 0 || teta == 0.0);
+        ctrl->tmax = teta;
+        if (!ctrl->skip2) { ctrl->p = p; return; }
+    }
+    if (p >= 0 && type[head[p]] == GLP_FX) p_stat = GLP_NS;
+    ctrl->p = p;
+    ctrl->p_stat = p_stat;
+    ctrl->teta = __dmul_rn(s, teta);
+    if (p == P_NONE) { ctrl->status = ST_NONE2; return; }
+    if (p >= 0) {
+        double piv = tcol[p];
+        double e5 = 1e-5 * (1.0 + 0.01 * ctrl->tcol_max);
+        ctrl->piv1 = piv;
+        if (fabs(piv) < e5 && !ctrl->rigorous) ctrl->status = ST_PIVSMALL;
+    }
+}
+
+__device__ __forceinline__ void ratio_primal_body(Ctrl *ctrl, int pass, int m, const signed char *__restrict__ type,
+                               const double *__restrict__ lb, const double *__restrict__ ub,
+                               const double *__restrict__ coef, const int *__restrict__ head,
+                               const double *__restrict__ bbar, const double *__restrict__ tcol,
+                               const int *__restrict__ ind, int num, double rtol,
+                               Key *scratch)
+{
+    if (ctrl->status != ST_OK) return;
+    if (pass == 2 && ctrl->skip2) return;
+    const int q = ctrl->q, phase = ctrl->phase;
+    const double s = (ctrl->d1 > 0.0 ? -1.0 : +1.0); /* d1 holds the (corrected) cbar[q] */
+    const double eps = (ind == nullptr ? ctrl->eps : 0.0);
+    const double tmax = ctrl->tmax;
+    const int kq = head[m + q];
+    Key none = {DBL_MAX, 0.0, 0.0, INT_MAX, 0};
+    Key v = none;
+    if (pass == 1 && blockIdx.x == 0 && threadIdx.x == 0 && type[kq] == GLP_DB) {
+        v.a = __dsub_rn(ub[kq], lb[kq]); v.b = 1.0; v.pos = -1; v.aux = 0;
+    }
+    scan_ratio_primal(v, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x, pass, phase, s, eps, tmax,
+                      rtol, type, lb, ub, coef, head, bbar, tcol, ind, num);
+    auto fin = [=](const Key &r) { fin_ratio_primal(ctrl, r, pass, s, rtol, type, head, tcol, ind); };
     if (pass == 1) grid_reduce(v, none, scratch, &ctrl->ticket[1], CombRatio1(), fin);
     else grid_reduce(v, none, scratch, &ctrl->ticket[1], CombRatio2(), fin);
 }
@@ -352,22 +391,14 @@ __global__ void k_ratio_primal(Ctrl *ctrl, int pass, int m, const signed char *_
     ratio_primal_body(ctrl, 2, m, type, lb, ub, coef, head, bbar, tcol, ind, num, rtol, scratch);
 }
 
-/* chuzc (dual ratio test), lib/glpspx02.js:793-935, one pass per launch.
+/* chuzc (dual ratio test), lib/glpspx02.js:793-935: scan of one pass.
    Algorithmic bytes: 21 per examined entry and pass (idx 4, trow 8, stat 1, cbar 8). */
-__device__ __forceinline__ void ratio_dual_body(Ctrl *ctrl, int pass, const signed char *__restrict__ stat,
-                             const double *__restrict__ cbar, const double *__restrict__ trow,
-                             const int *__restrict__ ind, int num, double rtol,
-                             Key *scratch)
+__device__ __forceinline__ void scan_ratio_dual(Key &v, int start, int stride, int pass, double s, double eps,
+                                                double tmax, double rtol, const signed char *stat,
+                                                const double *cbar, const double *trow, const int *ind,
+                                                int num)
 {
-    if (ctrl->status != ST_OK) return;
-    const int rigorous = ctrl->rigorous;
-    if (pass == 2 && ctrl->skip2) return;
-    const double s = (ctrl->delta > 0.0 ? +1.0 : -1.0);
-    const double eps = (ind == nullptr ? ctrl->eps : 0.0);
-    const double tmax = ctrl->tmax;
-    Key none = {DBL_MAX, 0.0, 0.0, INT_MAX, 0};
-    Key v = none;
-    for (int pos = blockIdx.x * blockDim.x + threadIdx.x; pos < num; pos += gridDim.x * blockDim.x) {
+    for (int pos = start; pos < num; pos += stride) {
         int j = ind ? ind[pos] : pos;
         double tr = trow[j];
         if (tr == 0.0 || fabs(tr) < eps) continue;
@@ -386,22 +417,42 @@ __device__ __forceinline__ void ratio_dual_body(Ctrl *ctrl, int pass, const sign
         if (pass == 1) CombRatio1()(v, c);
         else if (t <= tmax) CombRatio2()(v, c);
     }
-    auto fin = [=](const Key &r) {
-        int q = (r.pos == INT_MAX) ? P_NONE : (ind ? ind[r.pos] : r.pos);
-        double teta = r.a;
-        if (pass == 1) {
-            ctrl->skip2 = (rtol == 0.0 || q < 0 || teta == 0.0);
-            ctrl->tmax = teta;
-            if (!ctrl->skip2) { ctrl->q = q; return; }
-        }
-        ctrl->q = q;
-        ctrl->new_dq = __dmul_rn(s, teta);
-        if (q == P_NONE) { ctrl->status = ST_NONE2; return; }
-        double piv = trow[q];
-        double e5 = 1e-5 * (1.0 + 0.01 * ctrl->trow_max);
-        ctrl->piv2 = piv;
-        if (fabs(piv) < e5 && !rigorous) ctrl->status = ST_PIVSMALL;
-    };
+}
+
+__device__ __forceinline__ void fin_ratio_dual(Ctrl *ctrl, const Key &r, int pass, double s, double rtol,
+                                               const double *trow, const int *ind)
+{
+    int q = (r.pos == INT_MAX) ? P_NONE : (ind ? ind[r.pos] : r.pos);
+    double teta = r.a;
+    if (pass == 1) {
+        ctrl->skip2 = (rtol == 0.0 || q < 0 || teta == 0.0);
+        ctrl->tmax = teta;
+        if (!ctrl->skip2) { ctrl->q = q; return; }
+    }
+    ctrl->q = q;
+    ctrl->new_dq = __dmul_rn(s, teta);
+    if (q == P_NONE) { ctrl->status = ST_NONE2; return; }
+    double piv = trow[q];
+    double e5 = 1e-5 * (1.0 + 0.01 * ctrl->trow_max);
+    ctrl->piv2 = piv;
+    if (fabs(piv) < e5 && !ctrl->rigorous) ctrl->status = ST_PIVSMALL;
+}
+
+__device__ __forceinline__ void ratio_dual_body(Ctrl *ctrl, int pass, const signed char *__restrict__ stat,
+                             const double *__restrict__ cbar, const double *__restrict__ trow,
+                             const int *__restrict__ ind, int num, double rtol,
+                             Key *scratch)
+{
+    if (ctrl->status != ST_OK) return;
+    if (pass == 2 && ctrl->skip2) return;
+    const double s = (ctrl->delta > 0.0 ? +1.0 : -1.0);
+    const double eps = (ind == nullptr ? ctrl->eps : 0.0);
+    const double tmax = ctrl->tmax;
+    Key none = {DBL_MAX, 0.0, 0.0, INT_MAX, 0};
+    Key v = none;
+    scan_ratio_dual(v, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x, pass, s, eps, tmax, rtol,
+                    stat, cbar, trow, ind, num);
+    auto fin = [=](const Key &r) { fin_ratio_dual(ctrl, r, pass, s, rtol, trow, ind); };
     if (pass == 1) grid_reduce(v, none, scratch, &ctrl->ticket[1], CombRatio1(), fin);
     else grid_reduce(v, none, scratch, &ctrl->ticket[1], CombRatio2(), fin);
 }

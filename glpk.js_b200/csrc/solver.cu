@@ -8,6 +8,7 @@
  * reference's loop branches.
  */
 #include "kernels.cuh"
+#include "engine.cuh"
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -148,7 +149,8 @@ extern "C" void glpb_destroy(glpb_prob *P)
     void *ptrs[] = {P->a_ptr, P->a_ind, P->at_ptr, P->at_ind, P->a_val, P->at_val, P->type,
                     P->orig_type, P->stat, P->refsp, P->lb, P->ub, P->coef, P->orig_lb, P->orig_ub,
                     P->obj, P->head, P->bind, P->bbar, P->cbar, P->gamma, P->tcol, P->trow, P->rho,
-                    P->svec, P->w1, P->w2, P->w3, P->w4, P->w5, P->yk, P->wk, P->T, P->partial,
+                    P->svec, P->w1, P->w2, P->w3, P->w4, P->w5, P->yk, P->wk, P->yk2, P->zn, P->bar,
+                    P->eng_cyc, P->eng_bytes, P->T, P->partial,
                     P->rslot, P->slot_pos, P->cslot, P->slot_row, P->gj_piv, P->gj_row, P->gj_col, P->gj_xp,
                     P->scratch, P->ctrl};
     for (void *p : ptrs) if (p) cudaFree(p);
@@ -175,7 +177,8 @@ static int create_device(glpb_prob *P)
     DA(tcol, m); DA(trow, n); DA(rho, m); DA(svec, n);
     DA(w1, m); DA(w2, m); DA(w3, m); DA(w4, m); DA(w5, m);
     P->ldt = (m + 7) & ~7;
-    DA(yk, P->ldt); DA(wk, P->ldt);
+    DA(yk, P->ldt); DA(wk, P->ldt); DA(yk2, P->ldt); DA(zn, P->ldt);
+    DA(bar, 1); DA(eng_cyc, 16); DA(eng_bytes, 16);
     DA(T, (size_t)P->ldt * P->ldt);
     P->partial_rows = cdiv(P->ldt, GEMV_TILE);
     DA(partial, (size_t)P->partial_rows * P->ldt);
@@ -187,6 +190,26 @@ static int create_device(glpb_prob *P)
 #undef DA
     CK(cudaMallocHost((void **)&P->h_ctrl, sizeof(Ctrl)));
     CK(cudaMemsetAsync(P->ctrl, 0, sizeof(Ctrl), P->stream));
+    CK(cudaMemsetAsync(P->eng_cyc, 0, 16 * sizeof(long long), P->stream));
+    CK(cudaMemsetAsync(P->eng_bytes, 0, 16 * sizeof(double), P->stream));
+    /* persistent engine: one CTA per SM, dynamic shared memory for staging */
+    {
+        int coop = 0, smem_max = 0;
+        CK(cudaDeviceGetAttribute(&P->sm_count, cudaDevAttrMultiProcessorCount, P->device));
+        CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, P->device));
+        CK(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, P->device));
+        int budget = std::min(smem_max, 200 * 1024) - 24 * 1024;      /* static shared of the engine: ~20 KB */
+        int dcap = std::max(ENG_LCAP, std::min(P->ldt, (budget - ENG_LCAP * 4) / 8));
+        P->eng_dcap = dcap;
+        P->eng_smem = dcap * 8 + ENG_LCAP * 4;
+        if (!coop || P->sm_count > ENG_MAXG) { glpb_set_error("device lacks cooperative launch"); return GLPB_ENODEV; }
+        CK(cudaFuncSetAttribute(k_engine_primal, cudaFuncAttributeMaxDynamicSharedMemorySize, P->eng_smem));
+        CK(cudaFuncSetAttribute(k_engine_dual, cudaFuncAttributeMaxDynamicSharedMemorySize, P->eng_smem));
+        int occ = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_engine_dual, ENG_NT, P->eng_smem));
+        if (occ < 1) { glpb_set_error("engine does not fit an SM"); return GLPB_ENODEV; }
+        P->eng_ready = 1;
+    }
     return 0;
 }
 
@@ -662,6 +685,61 @@ struct Loop : Dev {
                obj_ll, obj_ul, P->zeta);
     }
 
+    bool engine_ok() const
+    {
+        static const bool off = getenv("GLPB_ENGINE") && atoi(getenv("GLPB_ENGINE")) == 0;
+        return !off && P->eng_ready && rigorous == 0 && !P->trace;
+    }
+
+    /* grid of the persistent engine: every SM once the problem is big enough to
+       feed them, a single CTA (barriers degrade to __syncthreads) for tiny LPs */
+    int engine_grid() const
+    {
+        static const int env = getenv("GLPB_GRID") ? atoi(getenv("GLPB_GRID")) : 0;
+        if (env > 0) return std::min(env, P->sm_count);
+        double work = (double)P->nnz + (double)k * k + 4.0 * (m + n);
+        if (work <= 32768.0) return 1;
+        return (int)std::min<double>(P->sm_count, std::max(2.0, work / 8192.0));
+    }
+
+    /* run iterations on the device until the engine meets one of the
+       reference's exceptional branches (or max_iters); one host sync */
+    int run_engine(int dual, double rtol, double obj_ll, double obj_ul)
+    {
+        static const int iters = getenv("GLPB_ENG_ITERS") ? std::max(1, atoi(getenv("GLPB_ENG_ITERS"))) : 2000;
+        batch_begin(0, obj_ll, obj_ul);
+        EngArgs A;
+        A.ctrl = P->ctrl; A.m = m; A.n = n; A.ldt = P->ldt; A.max_iters = iters;
+        A.gc = gc; A.gr = gr; A.dcap = P->eng_dcap;
+        A.tol_bnd = parm.tol_bnd; A.tol_dj = parm.tol_dj; A.tol_piv = parm.tol_piv; A.rtol = rtol;
+        A.a_ptr = P->a_ptr; A.a_ind = P->a_ind; A.a_val = P->a_val;
+        A.at_ptr = P->at_ptr; A.at_ind = P->at_ind; A.at_val = P->at_val;
+        A.type = P->type; A.stat = P->stat; A.refsp = P->refsp;
+        A.lb = P->lb; A.ub = P->ub; A.coef = P->coef;
+        A.head = P->head; A.bind = P->bind;
+        A.bbar = P->bbar; A.cbar = P->cbar; A.gamma = P->gamma; A.tcol = P->tcol; A.trow = P->trow;
+        A.rho = P->rho; A.svec = P->svec;
+        A.hz = P->w5; A.v = P->w3; A.u = P->w2;
+        A.yk = P->yk; A.yk2 = P->yk2; A.wk = P->wk; A.zn = P->zn;
+        A.T = P->T;
+        A.rslot = P->rslot; A.slot_pos = P->slot_pos; A.cslot = P->cslot; A.slot_row = P->slot_row;
+        A.scratch = P->scratch; A.bar = P->bar;
+        A.prof_cyc = P->prof ? P->eng_cyc + (dual ? 8 : 0) : nullptr;
+        A.prof_bytes = P->prof ? P->eng_bytes + (dual ? 8 : 0) : nullptr;
+        const int G = engine_grid();
+        CK(cudaMemsetAsync(P->bar, 0, sizeof(unsigned int), P->stream));
+        void *args[] = {&A};
+        prof_begin(P, dual ? "k_engine_dual" : "k_engine_primal");
+        cudaError_t e = cudaLaunchCooperativeKernel(dual ? (const void *)k_engine_dual : (const void *)k_engine_primal,
+                                                    dim3(G), dim3(ENG_NT), args, (size_t)P->eng_smem, P->stream);
+        prof_end(P);
+        if (e != cudaSuccess) { glpb_set_error("engine launch: %s", cudaGetErrorString(e)); return GLPB_ENODEV; }
+        P->n_launch++; P->n_eng_launch++;
+        int rc = sync_ctrl(P);
+        if (rc == 0 && P->prof) P->n_eng_prof_iter[dual ? 1 : 0] += P->h_ctrl->n_done;
+        return rc;
+    }
+
     /* take the loop state back after the batch */
     void batch_end()
     {
@@ -878,9 +956,11 @@ struct Primal : Loop {
             /* ---- a batch of iterations, enqueued as a whole; the device keeps the
                     loop state and turns the rest of the queue into no-ops as soon
                     as one of the reference's exceptional branches is met ---- */
-            const int B = batch_size();
-            batch_begin(B, -DBL_MAX, +DBL_MAX);
             const double rtol = (parm.r_test == GLP_RT_STD ? 0.0 : 0.30 * parm.tol_bnd);
+            const bool eng = engine_ok();
+            if (eng) { if ((rc = run_engine(0, rtol, -DBL_MAX, +DBL_MAX))) return rc; }
+            const int B = eng ? 0 : batch_size();
+            if (!eng) batch_begin(B, -DBL_MAX, +DBL_MAX);
             for (int b = 0; b < B; b++) {
                 chuzc(1);
                 eval_tcol();
@@ -908,7 +988,7 @@ struct Primal : Loop {
                        P->svec, P->w5);
                 update_basis(0);
             }
-            if ((rc = sync_ctrl(P))) return rc;
+            if (!eng && (rc = sync_ctrl(P))) return rc;
             trace_iter("primal");
             const Ctrl &c = *P->h_ctrl;
             batch_end();
@@ -1099,9 +1179,11 @@ struct Dual : Loop {
                 return stop_on_limit(code);
             }
             /* ---- a batch of iterations (see the primal loop) ---- */
-            const int B = batch_size();
-            batch_begin(B, parm.obj_ll, parm.obj_ul);
             const double rtol = (parm.r_test == GLP_RT_STD ? 0.0 : 0.30 * parm.tol_dj);
+            const bool eng = engine_ok();
+            if (eng) { if ((rc = run_engine(1, rtol, parm.obj_ll, parm.obj_ul))) return rc; }
+            const int B = eng ? 0 : batch_size();
+            if (!eng) batch_begin(B, parm.obj_ll, parm.obj_ul);
             for (int b = 0; b < B; b++) {
                 P->next_bytes = 37.0 * m;
                 LAUNCH(P, k_chuzr_dual, red_blocks(m), red_threads(m), 0, P->ctrl, m, P->type, P->lb, P->ub, P->head,
@@ -1134,7 +1216,7 @@ struct Dual : Loop {
                        P->lb, P->ub, P->bbar, P->cbar, P->gamma, P->refsp, P->tcol, P->trow, P->w2, P->w5);
                 update_basis(1);
             }
-            if ((rc = sync_ctrl(P))) return rc;
+            if (!eng && (rc = sync_ctrl(P))) return rc;
             trace_iter("dual");
             const Ctrl &c = *P->h_ctrl;
             batch_end();
@@ -1345,7 +1427,12 @@ extern "C" int glpb_set_profile(glpb_prob *P, int on)
     if (!P) return GLPB_EINVAL;
     prof_collect(P);
     P->prof = on;
-    if (on) P->prof_acc.clear();
+    if (on) {
+        P->prof_acc.clear();
+        P->n_eng_prof_iter[0] = P->n_eng_prof_iter[1] = 0;
+        cudaMemsetAsync(P->eng_cyc, 0, 16 * sizeof(long long), P->stream);
+        cudaMemsetAsync(P->eng_bytes, 0, 16 * sizeof(double), P->stream);
+    }
     return 0;
 }
 
@@ -1358,6 +1445,30 @@ extern "C" const char *glpb_profile_report(glpb_prob *P)
     for (auto &kv : P->prof_acc) {
         snprintf(line, sizeof line, "%s %ld %.6f %.0f\n", kv.first.c_str(), kv.second.count, kv.second.ms, kv.second.bytes);
         P->prof_text += line;
+    }
+    /* phases of the persistent engine: SM cycles of CTA 0 between barriers,
+       scaled to the CUDA-event time of the engine launches; count = iterations */
+    long long cyc[16];
+    double byt[16];
+    if (cudaMemcpy(cyc, P->eng_cyc, sizeof cyc, cudaMemcpyDeviceToHost) == cudaSuccess &&
+        cudaMemcpy(byt, P->eng_bytes, sizeof byt, cudaMemcpyDeviceToHost) == cudaSuccess) {
+        static const char *pn[16] = {"P1_chuzc", "P2_tcol_head", "P3_tcol_tail_prep", "P4_ratio1_btran_head",
+                                     "P5_ratio2_gemvT", "P6_rho_utail", "P7_trow_svec", "P8_update_T",
+                                     "D1_chuzr", "D2_rho", "D3_trow", "D4_ratio1_gamma_rhs", "D5_ratio2_gemvN",
+                                     "D6_tcol_head_utail", "D7_tcol_tail", "D8_update_T"};
+        for (int half = 0; half < 2; half++) {
+            const char *kn = half ? "k_engine_dual" : "k_engine_primal";
+            auto itp = P->prof_acc.find(kn);
+            if (itp == P->prof_acc.end()) continue;
+            long long tot = 0;
+            for (int i = 0; i < 8; i++) tot += cyc[half * 8 + i];
+            if (tot <= 0) continue;
+            for (int i = 0; i < 8; i++) {
+                snprintf(line, sizeof line, "eng_%s %ld %.6f %.0f\n", pn[half * 8 + i], P->n_eng_prof_iter[half],
+                         itp->second.ms * (double)cyc[half * 8 + i] / (double)tot, byt[half * 8 + i]);
+                P->prof_text += line;
+            }
+        }
     }
     return P->prof_text.c_str();
 }
