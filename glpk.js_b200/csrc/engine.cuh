@@ -33,13 +33,22 @@
 #define ENG_NT 1024          /* threads per CTA                                  */
 #define ENG_MAXG 160         /* scratch slot width (>= number of SMs)            */
 #define ENG_LCAP 2048        /* staged entries of one sparse column / row        */
-#define ENG_NSLOT 10
+#define ENG_RING 4           /* rotating barrier slots                           */
+
+/* one 128-byte line per (ring slot, CTA): the arrival flag and the partial
+   result that travels with it.  A line of its own keeps the G pollers of a
+   flag from queueing behind the pollers of its neighbours in one L2 slice. */
+struct __align__(128) EngSlot {
+    Key key;
+    unsigned int flag;
+    unsigned int pad[23];
+};
 
 struct EngArgs {
     Ctrl *ctrl;
     int m, n, ldt, max_iters;
-    int gc, gr;               /* lanes per column / row of A                     */
     int dcap;                 /* doubles of dynamic shared memory for staging    */
+    double avg_col, avg_row;  /* average column / row length of A                */
     double tol_bnd, tol_dj, tol_piv, rtol;
     const int *a_ptr, *a_ind; const double *a_val;
     const int *at_ptr, *at_ind; const double *at_val;
@@ -50,40 +59,92 @@ struct EngArgs {
     double *hz;               /* dense rhs of eval_tcol, all-zero between iterations */
     double *v, *u;            /* PSE work vectors [m]                            */
     double *yk, *yk2, *wk, *zn; /* kernel-space work [ldt]                       */
+    /* copies indexed by structural column / by row, zero where the variable is
+       not in the set: they turn the gathers of the sparse passes into one load */
+    double *ycol, *ycol2;     /* [n] FTRAN results y by basic column (0: non-basic)        */
+    double *vrow;             /* [m] primal: masked tcol by row of a basic auxiliary       */
+    double *trowcol;          /* [n] dual: trow over the reference space by non-basic column */
     double *T;
     int *rslot, *slot_pos, *cslot, *slot_row;
-    Key *scratch;
-    unsigned int *bar;
+    EngSlot *slots;           /* [ENG_RING][ENG_MAXG] arrival flags + CTA partials, zeroed by the host */
     long long *prof_cyc;      /* optional: SM cycles per phase, CTA 0 (NULL = off)  */
     double *prof_bytes;       /* optional: algorithmic bytes per phase              */
 };
 
 struct EngCtx {
-    int G, cta, tid, lane, warp, gtid, gsize, gwarp, nwarp;
-    unsigned int epoch;
+    int G, cta, tid, lane, warp, gtid, gsize;
+    unsigned int seq;         /* barrier sequence number, identical in every thread */
+    unsigned int dseq;        /* sequence number of the header-update hand-off     */
     long long t_last;
     double *sh_d;             /* [dcap] staging values / dense vector            */
     int *sh_i;                /* [ENG_LCAP] staging indices                      */
 };
 
-/* grid-wide barrier: monotone arrival counter, zeroed by the host before the launch */
-__device__ __forceinline__ void eng_bar(EngCtx &X, const EngArgs &A)
+__device__ __forceinline__ unsigned int eng_ld_relaxed(const unsigned int *p)
+{
+    unsigned int v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void eng_st_release(unsigned int *p, unsigned int v)
+{
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void eng_fence_acq() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+
+/* Grid-wide barrier without a shared counter: every CTA publishes the barrier
+   sequence number in its own flag (release), thread i of every CTA polls the
+   flag of CTA i.  No atomic is contended and the critical path is one store
+   becoming visible in L2.  Slots rotate so that a CTA that runs ahead cannot
+   overwrite a flag a slower CTA has not seen yet (it can be at most one
+   barrier ahead). */
+__device__ __forceinline__ void eng_arrive(EngCtx &X, const EngArgs &A)
 {
     __syncthreads();
+    X.seq++;
+    if (X.G > 1 && X.tid == 0) eng_st_release(&A.slots[(X.seq & (ENG_RING - 1)) * ENG_MAXG + X.cta].flag, X.seq);
+}
+__device__ __forceinline__ void eng_wait(EngCtx &X, const EngArgs &A)
+{
     if (X.G > 1) {
-        X.epoch += (unsigned int)X.G;
-        if (X.tid == 0) {
-            __threadfence();
-            atomicAdd(A.bar, 1u);
-            while (*((volatile unsigned int *)A.bar) < X.epoch) { }
-            __threadfence();
+        if (X.tid < X.G) {
+            const unsigned int *f = &A.slots[(X.seq & (ENG_RING - 1)) * ENG_MAXG + X.tid].flag;
+            while (eng_ld_relaxed(f) < X.seq) { }
+            eng_fence_acq();
         }
         __syncthreads();
     }
 }
+__device__ __forceinline__ void eng_bar(EngCtx &X, const EngArgs &A)
+{
+    eng_arrive(X, A);
+    eng_wait(X, A);
+}
+
+/* Hand-off of the O(1) header update (slot maps, head/bind, status of the
+   entering column): CTA 0 performs it once EVERY CTA has arrived at the last
+   barrier of the iteration -- nobody reads the old header any more -- and then
+   raises this flag; nobody reads the new header before seeing it.  Costs one
+   flag round trip instead of a second grid barrier. */
+__device__ __forceinline__ void eng_header_done(EngCtx &X, const EngArgs &A)
+{
+    X.dseq++;
+    if (X.G > 1) {
+        unsigned int *done = &A.slots[ENG_RING * ENG_MAXG].flag;
+        __syncthreads();        /* CTA 0: thread 0's header writes are ordered before the release */
+        if (X.tid == 0) {
+            if (X.cta == 0) eng_st_release(done, X.dseq);
+            else {
+                while (eng_ld_relaxed(done) < X.dseq) { }
+                eng_fence_acq();
+            }
+        }
+    }
+    __syncthreads();
+}
 
 /* phase accounting for bench.py's roofline leg: CTA 0 leaves every barrier
-   last-or-together with the grid, so its cycle stamps bound the phase */
+   together with the grid, so its cycle stamps bound the phase */
 __device__ __forceinline__ void eng_mark(EngCtx &X, const EngArgs &A, int phase, double bytes)
 {
     if (A.prof_cyc != nullptr && X.cta == 0 && X.tid == 0) {
@@ -94,38 +155,135 @@ __device__ __forceinline__ void eng_mark(EngCtx &X, const EngArgs &A, int phase,
     }
 }
 
-/* CTA partial -> slot -> barrier -> every CTA combines the G partials */
+/* Barrier that carries a reduction: the CTA partial travels with the arrival
+   flag; thread i of every CTA picks up partial i as soon as flag i is up and the
+   G partials are combined in index order (deterministic, same in every CTA). */
 template <class Comb>
-__device__ Key eng_allreduce(EngCtx &X, const EngArgs &A, Key v, const Key &none, int slot, Comb comb)
+__device__ Key eng_allreduce(EngCtx &X, const EngArgs &A, Key v, const Key &none, Comb comb)
 {
-    __shared__ Key sh_res;
-    v = block_reduce(v, none, comb);
-    Key *sl = A.scratch + slot * ENG_MAXG;
-    if (X.G > 1) {
-        if (X.tid == 0) sl[X.cta] = v;
-        eng_bar(X, A);
-        if (X.tid < 32) {
-            Key r = none;
-            for (int i = X.tid; i < X.G; i += 32) {
-                Key o;
-                o.a = __ldcg(&sl[i].a); o.b = __ldcg(&sl[i].b); o.c = __ldcg(&sl[i].c);
-                o.pos = __ldcg(&sl[i].pos); o.aux = __ldcg(&sl[i].aux);
-                comb(r, o);
-            }
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) {
-                Key o = key_shfl_down(r, off);
-                comb(r, o);
-            }
-            if (X.tid == 0) sh_res = r;
+    __shared__ Key wres[ENG_MAXG / 32];
+    v = block_reduce(v, none, comb);      /* its __syncthreads also fence this CTA's phase writes */
+    X.seq++;
+    if (X.G == 1) {
+        if (X.tid == 0) wres[0] = v;
+        __syncthreads();
+        Key r = wres[0];
+        __syncthreads();
+        return r;
+    }
+    EngSlot *ring = A.slots + (X.seq & (ENG_RING - 1)) * ENG_MAXG;
+    if (X.tid == 0) {
+        Key *d = &ring[X.cta].key;
+        __stcg(&d->a, v.a); __stcg(&d->b, v.b); __stcg(&d->c, v.c); __stcg(&d->pos, v.pos); __stcg(&d->aux, v.aux);
+        eng_st_release(&ring[X.cta].flag, X.seq);
+    }
+    const int nw = (X.G + 31) >> 5;
+    if (X.warp < nw) {
+        Key r = none;
+        if (X.tid < X.G) {
+            const unsigned int *f = &ring[X.tid].flag;
+            while (eng_ld_relaxed(f) < X.seq) { }
+            eng_fence_acq();
+            const Key *sl = &ring[X.tid].key;
+            r.a = __ldcg(&sl->a); r.b = __ldcg(&sl->b); r.c = __ldcg(&sl->c);
+            r.pos = __ldcg(&sl->pos); r.aux = __ldcg(&sl->aux);
         }
-    } else {
-        if (X.tid == 0) sh_res = v;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            Key o = key_shfl_down(r, off);
+            comb(r, o);
+        }
+        if (X.lane == 0) wres[X.warp] = r;
     }
     __syncthreads();
-    Key r = sh_res;
+    Key r = wres[0];
+    for (int w = 1; w < nw; w++) comb(r, wres[w]);
     __syncthreads();
     return r;
+}
+
+/* lanes per item for the segmented sums below: as many as the grid offers for
+   nitems in ONE round (rounds of the multi-warp form are separated by
+   __syncthreads), but no more than entries, and at least 4 */
+__device__ __forceinline__ int eng_pick_lp(const EngCtx &X, int nitems, double avg_len)
+{
+    int LP = 4;
+    while (LP < 1024 && (long)nitems * LP * 2 <= (long)X.gsize && LP < avg_len) LP <<= 1;
+    return LP;
+}
+
+/* Segmented sums over the grid: item i is summed by LP lanes (a power of two,
+   4..1024).  LP <= 32: sub-warp groups and shuffles; LP > 32: LP/32 warps of one
+   CTA, partial sums meet in shared memory in a fixed order.  body(i, l, LP, a)
+   accumulates lane l's share into a[0..NV); out(i, a) runs in one thread.
+   All threads of the grid must call with identical nitems and LP. */
+template <int NV, class Body, class Out>
+__device__ __forceinline__ void eng_items(const EngCtx &X, int nitems, int LP, Body body, Out out)
+{
+    __shared__ double part[NV][32];
+    if (LP <= 32) {
+        const int ngroups = X.gsize / LP, g = X.gtid / LP, l = X.tid & (LP - 1);
+        for (int i0 = 0; i0 < nitems; i0 += ngroups) {
+            const int item = i0 + g;
+            double a[NV];
+#pragma unroll
+            for (int x = 0; x < NV; x++) a[x] = 0.0;
+            if (item < nitems) body(item, l, LP, a);
+            for (int off = LP >> 1; off > 0; off >>= 1) {
+#pragma unroll
+                for (int x = 0; x < NV; x++) a[x] += __shfl_xor_sync(FULLMASK, a[x], off);
+            }
+            if (item < nitems && l == 0) out(item, a);
+        }
+    } else {
+        const int W = LP >> 5, IPC = 32 / W;
+        const int sub = X.warp / W, prt = X.warp % W;
+        for (int i0 = 0; i0 < nitems; i0 += X.G * IPC) {
+            const int item = i0 + X.cta * IPC + sub;
+            double a[NV];
+#pragma unroll
+            for (int x = 0; x < NV; x++) a[x] = 0.0;
+            if (item < nitems) body(item, prt * 32 + X.lane, LP, a);
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+#pragma unroll
+                for (int x = 0; x < NV; x++) a[x] += __shfl_xor_sync(FULLMASK, a[x], off);
+            }
+            if (X.lane == 0) {
+#pragma unroll
+                for (int x = 0; x < NV; x++) part[x][X.warp] = a[x];
+            }
+            __syncthreads();
+            if (prt == 0 && X.lane == 0 && item < nitems) {
+#pragma unroll
+                for (int x = 0; x < NV; x++) {
+                    double s = 0.0;
+                    for (int w = 0; w < W; w++) s += part[x][sub * W + w];
+                    a[x] = s;
+                }
+                out(item, a);
+            }
+            __syncthreads();
+        }
+    }
+}
+
+/* lane l's share of  sum_ptr val[ptr] * x[ind[ptr]]  over [beg, end); the
+   matrix arrays are immutable (read-only path), x is not */
+__device__ __forceinline__ double eng_spdot(const int *ind, const double *val, int beg, int end, int l, int LP,
+                                            const double *x)
+{
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    int ptr = beg + l;
+    for (; ptr + 3 * LP < end; ptr += 4 * LP) {
+        const int c0 = __ldg(ind + ptr), c1 = __ldg(ind + ptr + LP), c2 = __ldg(ind + ptr + 2 * LP),
+                  c3 = __ldg(ind + ptr + 3 * LP);
+        const double v0 = __ldg(val + ptr), v1 = __ldg(val + ptr + LP), v2 = __ldg(val + ptr + 2 * LP),
+                     v3 = __ldg(val + ptr + 3 * LP);
+        a0 += v0 * x[c0]; a1 += v1 * x[c1]; a2 += v2 * x[c2]; a3 += v3 * x[c3];
+    }
+    for (; ptr < end; ptr += LP) a0 += __ldg(val + ptr) * x[__ldg(ind + ptr)];
+    return (a0 + a1) + (a2 + a3);
 }
 
 /* ordered compaction inside a CTA: returns the position of this thread's
@@ -158,7 +316,7 @@ __device__ __forceinline__ int eng_compact(const EngCtx &X, bool flag, int &tota
    consecutive rows; its 32 warps split the list, partial sums meet in shared
    memory in a fixed order.  Streams 8 L k bytes of T. */
 __device__ void eng_gemv_rows(const EngCtx &X, const EngArgs &A, int k, int L, const int *idx,
-                              const double *val, double *y, bool accumulate)
+                              const double *val, double *y, double *ycol, bool accumulate)
 {
     __shared__ double red[32][33];
     int RB = 8;
@@ -205,7 +363,11 @@ __device__ void eng_gemv_rows(const EngCtx &X, const EngArgs &A, int k, int L, c
 #pragma unroll 8
             for (int w = 0; w < 32; w++) s += red[w][X.tid];
             const int b2 = rb * RB + X.tid;
-            if (b2 < k) y[b2] = accumulate ? y[b2] + s : s;
+            if (b2 < k) {
+                if (accumulate) s += y[b2];
+                y[b2] = s;
+                ycol[A.head[A.slot_pos[b2]] - A.m] = s;      /* the same value by basic column */
+            }
         }
         __syncthreads();
     }
@@ -215,11 +377,10 @@ __device__ void eng_gemv_rows(const EngCtx &X, const EngArgs &A, int k, int L, c
    lib/glpspx01.js:690-727): y = T h_N over the entries of column q that fall
    on rows of R_N.  CTA 0 also scatters h into the dense vector hz that the
    second half reads. */
-__device__ void eng_ftran_head_col(EngCtx &X, const EngArgs &A, int k, int kq, double *y)
+__device__ void eng_ftran_head_col(EngCtx &X, const EngArgs &A, int k, int kq, double *y, double *ycol)
 {
     const int m = A.m;
-    const int RBmin = 8;
-    const bool work = (X.cta * RBmin < k);
+    const bool work = (X.cta * 8 < k);
     if (!work && X.cta != 0) return;
     if (kq < m) {
         if (X.tid == 0) {
@@ -227,7 +388,7 @@ __device__ void eng_ftran_head_col(EngCtx &X, const EngArgs &A, int k, int kq, d
             if (X.cta == 0) A.hz[kq] = -1.0;
         }
         __syncthreads();
-        eng_gemv_rows(X, A, k, 1, X.sh_i, X.sh_d, y, false);
+        eng_gemv_rows(X, A, k, 1, X.sh_i, X.sh_d, y, ycol, false);
         return;
     }
     const int beg = __ldg(A.a_ptr + (kq - m)), end = __ldg(A.a_ptr + (kq - m) + 1);
@@ -250,38 +411,30 @@ __device__ void eng_ftran_head_col(EngCtx &X, const EngArgs &A, int k, int kq, d
             L += tot;
         }
         __syncthreads();
-        eng_gemv_rows(X, A, k, L, X.sh_i, X.sh_d, y, !first);
+        eng_gemv_rows(X, A, k, L, X.sh_i, X.sh_d, y, ycol, !first);
         first = false;
     }
 }
 
-/* FTRAN, second half: x[i] for every basic position from y = T h_N.  One
-   group of GL lanes per position gathers the row of A of a basic auxiliary
-   variable.  PREP (primal): the reductions of k_primal_prep ride along. */
-template <int GL, bool PREP>
+/* FTRAN, second half: x[i] for every basic position from y = T h_N, given by
+   basic column (ycol, zero on non-basic columns): a basic auxiliary variable
+   gathers its row of A, a basic structural one reads its own entry.
+   PREP (primal): the reductions of k_primal_prep ride along. */
+template <bool PREP>
 __device__ __forceinline__ void eng_ftran_tail(const EngCtx &X, const EngArgs &A, const Ctrl &S,
-                                               const double *h, const double *y, double *x, Key &acc)
+                                               const double *h, const double *ycol, double *x, Key &acc)
 {
     const int m = A.m;
-    const int ngroups = X.gsize / GL, g = X.gtid / GL, lane = X.tid % GL;
     const bool pse = PREP && gamma_on(&S);
-    for (int i0 = 0; i0 < m; i0 += ngroups) {
-        const int i = i0 + g;
-        double a = 0.0;
-        int kk = m;
-        if (i < m) {
-            kk = A.head[i];
-            if (kk < m) {
-                const int beg = __ldg(A.at_ptr + kk), end = __ldg(A.at_ptr + kk + 1);
-                for (int ptr = beg + lane; ptr < end; ptr += GL) {
-                    const int pb = A.bind[m + __ldg(A.at_ind + ptr)];
-                    if (pb < m) a += __ldg(A.at_val + ptr) * y[A.rslot[pb]];
-                }
-            }
-        }
-        a = group_sum<GL>(a);
-        if (i < m && lane == 0) {
-            const double t = (kk < m) ? h[kk] + a : y[A.rslot[i]];
+    const int LP = eng_pick_lp(X, m, A.avg_row);
+    eng_items<1>(X, m, LP,
+        [&](int i, int l, int lp, double *a) {
+            const int kk = A.head[i];
+            if (kk < m) a[0] = eng_spdot(A.at_ind, A.at_val, __ldg(A.at_ptr + kk), __ldg(A.at_ptr + kk + 1), l, lp, ycol);
+        },
+        [&](int i, const double *a) {
+            const int kk = A.head[i];
+            const double t = (kk < m) ? h[kk] + a[0] : ycol[kk - m];
             x[i] = t;
             if (PREP) {
                 acc.a += A.coef[kk] * t;
@@ -289,54 +442,45 @@ __device__ __forceinline__ void eng_ftran_tail(const EngCtx &X, const EngArgs &A
                 if (pse) {
                     const double vv = A.refsp[kk] ? t : 0.0;
                     A.v[i] = vv;
+                    if (kk < m) A.vrow[kk] = vv;
                     acc.b += vv * vv;
                 }
             }
-        }
-    }
+        });
 }
 
-/* BTRAN, first half: w[b] = c[pos_b] + sum_{r in R_B} A[r, j_b] c[bind[r]] */
-template <int GL>
-__device__ __forceinline__ void eng_btran_head(const EngCtx &X, const EngArgs &A, int k, const double *c, double *w)
+/* BTRAN, first half: w[b] = c[pos_b] + sum_{r in R_B} A[r, j_b] c[bind[r]],
+   with c given by position (v) and by row of a basic auxiliary (vrow) */
+__device__ __forceinline__ void eng_btran_head(const EngCtx &X, const EngArgs &A, int k)
 {
     const int m = A.m;
-    const int ngroups = X.gsize / GL, g = X.gtid / GL, lane = X.tid % GL;
-    for (int b0 = 0; b0 < k; b0 += ngroups) {
-        const int b = b0 + g;
-        double a = 0.0;
-        int i = 0;
-        if (b < k) {
-            i = A.slot_pos[b];
-            const int j = A.head[i] - m;
-            const int beg = __ldg(A.a_ptr + j), end = __ldg(A.a_ptr + j + 1);
-            for (int ptr = beg + lane; ptr < end; ptr += GL) {
-                const int pr = A.bind[__ldg(A.a_ind + ptr)];
-                if (pr < m) a += __ldg(A.a_val + ptr) * c[pr];
-            }
-        }
-        a = group_sum<GL>(a);
-        if (b < k && lane == 0) w[b] = c[i] + a;
-    }
+    const int LP = eng_pick_lp(X, k, A.avg_col);
+    eng_items<1>(X, k, LP,
+        [&](int b, int l, int lp, double *a) {
+            const int j = A.head[A.slot_pos[b]] - m;
+            a[0] = eng_spdot(A.a_ind, A.a_val, __ldg(A.a_ptr + j), __ldg(A.a_ptr + j + 1), l, lp, A.vrow);
+        },
+        [&](int b, const double *a) { A.wk[b] = A.v[A.slot_pos[b]] + a[0]; });
 }
 
-/* zn[cs] = sum_b T[b, cs] w[b]: one warp per column, coalesced.  8 k^2 bytes. */
+/* zn[cs] = sum_b T[b, cs] w[b]: column dots, coalesced.  8 k^2 bytes. */
 __device__ __forceinline__ void eng_gemvT(const EngCtx &X, const EngArgs &A, int k, const double *w, double *zn)
 {
-    for (int cs = X.gwarp; cs < k; cs += X.nwarp) {
-        const double *col = A.T + (size_t)cs * A.ldt;
-        double a0 = 0.0, a1 = 0.0;
-        int b = X.lane;
-        for (; b + 32 < k; b += 64) {
-            double t0 = __ldcg(col + b), t1 = __ldcg(col + b + 32);
-            a0 += t0 * w[b]; a1 += t1 * w[b + 32];
-        }
-        if (b < k) a0 += __ldcg(col + b) * w[b];
-        double a = a0 + a1;
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) a += __shfl_xor_sync(FULLMASK, a, off);
-        if (X.lane == 0) zn[cs] = a;
-    }
+    const int LP = max(32, eng_pick_lp(X, k, (double)k / 2));
+    eng_items<1>(X, k, LP,
+        [&](int cs, int l, int lp, double *a) {
+            const double *col = A.T + (size_t)cs * A.ldt;
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+            int b = l;
+            for (; b + 3 * lp < k; b += 4 * lp) {
+                const double t0 = __ldcg(col + b), t1 = __ldcg(col + b + lp);
+                const double t2 = __ldcg(col + b + 2 * lp), t3 = __ldcg(col + b + 3 * lp);
+                a0 += t0 * w[b]; a1 += t1 * w[b + lp]; a2 += t2 * w[b + 2 * lp]; a3 += t3 * w[b + 3 * lp];
+            }
+            for (; b < k; b += lp) a0 += __ldcg(col + b) * w[b];
+            a[0] = (a0 + a1) + (a2 + a3);
+        },
+        [&](int cs, const double *a) { zn[cs] = a[0]; });
 }
 
 /* rho = row p of inv(B) (eval_rho, lib/glpspx01.js:1030-1042), read out of T */
@@ -351,7 +495,7 @@ __device__ void eng_rho(EngCtx &X, const EngArgs &A, int k, int p)
         for (int cs = X.gtid; cs < k; cs += X.gsize) A.rho[A.slot_row[cs]] = __ldcg(row + (size_t)cs * A.ldt);
         return;
     }
-    if (X.cta * (ENG_NT / 32) >= k) return;          /* no column of T for this CTA */
+    /* an auxiliary variable leaves: rho_N = w' T with w the basic part of row kp of A */
     const int beg = __ldg(A.at_ptr + kp), end = __ldg(A.at_ptr + kp + 1);
     bool first = true;
     for (int seg = beg; seg < end || first; seg += ENG_LCAP) {
@@ -369,17 +513,24 @@ __device__ void eng_rho(EngCtx &X, const EngArgs &A, int k, int p)
             L += tot;
         }
         __syncthreads();
-        for (int cs = X.gwarp; cs < k; cs += X.nwarp) {
-            const double *col = A.T + (size_t)cs * A.ldt;
-            double a = 0.0;
-            for (int e = X.lane; e < L; e += 32) a += __ldcg(col + X.sh_i[e]) * X.sh_d[e];
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) a += __shfl_xor_sync(FULLMASK, a, off);
-            if (X.lane == 0) {
+        const int LP = eng_pick_lp(X, k, (double)L);
+        const bool acc = !first;
+        eng_items<1>(X, k, LP,
+            [&](int cs, int l, int lp, double *a) {
+                const double *col = A.T + (size_t)cs * A.ldt;
+                double a0 = 0.0, a1 = 0.0;
+                int e = l;
+                for (; e + lp < L; e += 2 * lp) {
+                    const double t0 = __ldcg(col + X.sh_i[e]), t1 = __ldcg(col + X.sh_i[e + lp]);
+                    a0 += t0 * X.sh_d[e]; a1 += t1 * X.sh_d[e + lp];
+                }
+                if (e < L) a0 += __ldcg(col + X.sh_i[e]) * X.sh_d[e];
+                a[0] = a0 + a1;
+            },
+            [&](int cs, const double *a) {
                 const int r = A.slot_row[cs];
-                A.rho[r] = first ? a : A.rho[r] + a;
-            }
-        }
+                A.rho[r] = acc ? A.rho[r] + a[0] : a[0];
+            });
         first = false;
         __syncthreads();
     }
@@ -387,75 +538,78 @@ __device__ void eng_rho(EngCtx &X, const EngArgs &A, int k, int p)
 
 /* pivot row (eval_trow): trow[j] = -rho' N_j for the non-basic non-fixed
    columns; with PSE also s_j = N_j' u (primal update_gamma) from the same pass.
-   acc.c collects |trow|_inf and acc.a the sum of trow_j^2 over the reference
-   space (dual). */
-template <int GL, bool DUAL>
+   Dual: acc.c collects |trow|_inf, acc.a the sum of trow_j^2 over the reference
+   space, and trowcol gets the reference-space part of trow by column. */
+template <bool DUAL>
 __device__ __forceinline__ void eng_trow(const EngCtx &X, const EngArgs &A, const Ctrl &S, Key &acc)
 {
     const int m = A.m, n = A.n;
-    const int ngroups = X.gsize / GL, g = X.gtid / GL, lane = X.tid % GL;
     const bool pse = gamma_on(&S);
     const bool want_s = !DUAL && pse;
-    for (int j0 = 0; j0 < n; j0 += ngroups) {
-        const int j = j0 + g;
-        double t = 0.0, s = 0.0;
-        int k = 0;
-        const bool live = (j < n) && A.stat[j] != GLP_NS;
-        if (live) {
-            k = A.head[m + j];
+    const int LP = eng_pick_lp(X, n, A.avg_col);
+    eng_items<2>(X, n, LP,
+        [&](int j, int l, int lp, double *a) {
+            if (A.stat[j] == GLP_NS) return;
+            const int k = A.head[m + j];
             if (k < m) {
-                if (lane == 0) { t = -A.rho[k]; if (want_s) s = A.u[k]; }
-            } else {
-                const int beg = __ldg(A.a_ptr + (k - m)), end = __ldg(A.a_ptr + (k - m) + 1);
-                for (int ptr = beg + lane; ptr < end; ptr += GL) {
-                    const int r = __ldg(A.a_ind + ptr);
-                    const double a = __ldg(A.a_val + ptr);
-                    t += A.rho[r] * a;
-                    if (want_s) s -= a * A.u[r];
+                if (l == 0) { a[0] = -A.rho[k]; if (want_s) a[1] = A.u[k]; }
+                return;
+            }
+            const int beg = __ldg(A.a_ptr + (k - m)), end = __ldg(A.a_ptr + (k - m) + 1);
+            double t0 = 0.0, t1 = 0.0, s0 = 0.0, s1 = 0.0;
+            int ptr = beg + l;
+            for (; ptr + 3 * lp < end; ptr += 4 * lp) {
+                const int r0 = __ldg(A.a_ind + ptr), r1 = __ldg(A.a_ind + ptr + lp), r2 = __ldg(A.a_ind + ptr + 2 * lp),
+                          r3 = __ldg(A.a_ind + ptr + 3 * lp);
+                const double v0 = __ldg(A.a_val + ptr), v1 = __ldg(A.a_val + ptr + lp),
+                             v2 = __ldg(A.a_val + ptr + 2 * lp), v3 = __ldg(A.a_val + ptr + 3 * lp);
+                const double x0 = A.rho[r0], x1 = A.rho[r1], x2 = A.rho[r2], x3 = A.rho[r3];
+                t0 += x0 * v0; t1 += x1 * v1; t0 += x2 * v2; t1 += x3 * v3;
+                if (want_s) {
+                    const double u0 = A.u[r0], u1 = A.u[r1], u2 = A.u[r2], u3 = A.u[r3];
+                    s0 -= v0 * u0; s1 -= v1 * u1; s0 -= v2 * u2; s1 -= v3 * u3;
                 }
             }
-        }
-        t = group_sum<GL>(t);
-        if (want_s) s = group_sum<GL>(s);
-        if (j < n && lane == 0) {
+            for (; ptr < end; ptr += lp) {
+                const int r0 = __ldg(A.a_ind + ptr);
+                const double v0 = __ldg(A.a_val + ptr);
+                t0 += A.rho[r0] * v0;
+                if (want_s) s0 -= v0 * A.u[r0];
+            }
+            a[0] = t0 + t1; a[1] = s0 + s1;
+        },
+        [&](int j, const double *a) {
+            const double t = a[0];
             A.trow[j] = t;
-            if (want_s) A.svec[j] = s;
+            if (want_s) A.svec[j] = a[1];
             if (DUAL) {
                 acc.c = fmax(acc.c, fabs(t));
-                if (pse && live && t != 0.0 && A.refsp[k]) acc.a += t * t;
+                const int k = A.head[m + j];
+                const bool in = pse && t != 0.0 && A.refsp[k];
+                if (in) acc.a += t * t;
+                if (k >= m) A.trowcol[k - m] = in ? t : 0.0;
             }
-        }
-    }
+        });
 }
 
 /* dual update_gamma, first half (lib/glpspx02.js:1103-1132), by rows:
    v[r] = sum_{j in C, non-basic} N_j[r] trow_j; the entries on rows of R_N are
    also written in kernel order (wk) for the dense product with T */
-template <int GL>
 __device__ __forceinline__ void eng_gamma_rhs(const EngCtx &X, const EngArgs &A)
 {
     const int m = A.m;
-    const int ngroups = X.gsize / GL, g = X.gtid / GL, lane = X.tid % GL;
-    for (int r0 = 0; r0 < m; r0 += ngroups) {
-        const int row = r0 + g;
-        double a = 0.0;
-        if (row < m) {
-            const int beg = __ldg(A.at_ptr + row), end = __ldg(A.at_ptr + row + 1);
-            for (int ptr = beg + lane; ptr < end; ptr += GL) {
-                const int jj = __ldg(A.at_ind + ptr);
-                const int pb = A.bind[m + jj];
-                if (pb >= m && A.refsp[m + jj]) a -= A.trow[pb - m] * __ldg(A.at_val + ptr);
-            }
-        }
-        a = group_sum<GL>(a);
-        if (row < m && lane == 0) {
+    const int LP = eng_pick_lp(X, m, A.avg_row);
+    eng_items<1>(X, m, LP,
+        [&](int row, int l, int lp, double *a) {
+            a[0] = -eng_spdot(A.at_ind, A.at_val, __ldg(A.at_ptr + row), __ldg(A.at_ptr + row + 1), l, lp, A.trowcol);
+        },
+        [&](int row, const double *a) {
             const int pr = A.bind[row];
-            const double val = a + ((pr >= m && A.refsp[row]) ? A.trow[pr - m] : 0.0);
+            const double val = a[0] + ((pr >= m && A.refsp[row]) ? A.trow[pr - m] : 0.0);
             A.v[row] = val;
             const int cs = A.cslot[row];
             if (cs >= 0) A.wk[cs] = val;
-        }
-    }
+        });
 }
 
 /* description of a basis change, identical in every CTA */
@@ -550,26 +704,46 @@ __device__ void eng_bookkeep(const EngArgs &A, const EngChange &C, int new_stat,
     A.bind[C.kq] = C.p; A.bind[C.kp] = m + C.q;
     A.stat[C.q] = (signed char)new_stat;
     if (drop_refsp) A.refsp[C.kp] = 0;
+    /* zero where the variable left the set the copy is indexed over */
+    if (C.LS) A.vrow[C.kp] = 0.0;
+    else { A.ycol[C.kp - m] = 0.0; A.ycol2[C.kp - m] = 0.0; }
+    if (!C.ES) A.trowcol[C.kq - m] = 0.0;
 }
-
-#define ENG_GROUPS(G, CALL)                                                    \
-    do {                                                                       \
-        if ((G) == 32) { constexpr int GG = 32; CALL; }                        \
-        else if ((G) == 8) { constexpr int GG = 8; CALL; }                     \
-        else { constexpr int GG = 4; CALL; }                                   \
-    } while (0)
 
 __device__ __forceinline__ void eng_init(EngCtx &X, const EngArgs &A, double *dyn)
 {
     X.G = gridDim.x; X.cta = blockIdx.x; X.tid = threadIdx.x;
     X.lane = X.tid & 31; X.warp = X.tid >> 5;
     X.gtid = X.cta * ENG_NT + X.tid; X.gsize = X.G * ENG_NT;
-    X.gwarp = X.gtid >> 5; X.nwarp = X.gsize >> 5;
-    X.epoch = 0u;
+    X.seq = 0u;
+    X.dseq = 0u;
     X.t_last = clock64();
     X.sh_d = dyn;
     X.sh_i = (int *)(dyn + A.dcap);
 }
+
+/* block-wide reduction whose result every thread of the CTA gets */
+template <class Comb>
+__device__ Key eng_blockall(const EngCtx &X, Key v, const Key &none, Comb comb)
+{
+    __shared__ Key res;
+    v = block_reduce(v, none, comb);
+    if (X.tid == 0) res = v;
+    __syncthreads();
+    Key r = res;
+    __syncthreads();
+    return r;
+}
+
+/* vectors up to this length are scanned by EVERY CTA on its own (replicated
+   ratio test: two block-wide reductions, no grid barrier); longer ones by the
+   grid with two barrier-reductions */
+#define ENG_LOCAL_MAX 8192
+
+enum { /* phase slots of the cycle accounting (12 per engine) */
+    PP_PRICE0 = 0, PP_A, PP_B, PP_R1, PP_R2, PP_C, PP_D, PP_E, PP_F,
+    PD_PRICE0 = 0, PD_RHO, PD_TROW, PD_R1, PD_R2, PD_X1, PD_TCOL1, PD_TCOL2, PD_UPD
+};
 
 /* ------------------------------------------------------------------ */
 /* primal engine: lib/glpspx01.js:1868-2056                           */
@@ -582,38 +756,42 @@ __global__ void __launch_bounds__(ENG_NT, 1) k_engine_primal(EngArgs A)
     EngCtx X;
     eng_init(X, A, eng_dyn);
     const int m = A.m, n = A.n;
+    const bool local_ratio = (m <= ENG_LOCAL_MAX);
+    const double nnzA = (double)__ldg(A.a_ptr + n);
     if (X.tid == 0) S = *A.ctrl;
     __syncthreads();
-    int qprev = -1, stprev = 0;
+    int qnext = P_NONE;
     for (int it = 0; it < A.max_iters && S.status == ST_OK; it++) {
-        /* ---- P1: chuzc ---- */
-        {
+        /* ---- pricing (chuzc): the first iteration of a launch prices on its own,
+                later ones were priced by the update phase of their predecessor ---- */
+        if (it == 0) {
             Key none = {0.0, 0.0, 0.0, INT_MAX, 0};
             Key v = none;
-            scan_chuzc_primal(v, X.gtid, X.gsize, n, A.stat, A.cbar, A.gamma, A.tol_dj, qprev, stprev);
-            Key r = eng_allreduce(X, A, v, none, 0, CombArgMax());
-            if (X.tid == 0) {
-                S.q = (r.a > 0.0 && r.pos != INT_MAX) ? r.pos : P_NONE;
-                S.big = 0.0;
-                if (S.q == P_NONE) S.status = ST_NONE1;
-            }
-            __syncthreads();
-            eng_mark(X, A, 0, 17.0 * n);
-            if (S.status != ST_OK) break;
+            scan_chuzc_primal(v, X.gtid, X.gsize, n, A.stat, A.cbar, A.gamma, A.tol_dj, -1, 0);
+            Key r = eng_allreduce(X, A, v, none, CombArgMax());
+            qnext = (r.a > 0.0 && r.pos != INT_MAX) ? r.pos : P_NONE;
+            eng_mark(X, A, PP_PRICE0, 17.0 * n);
         }
+        if (X.tid == 0) {
+            S.q = qnext;
+            S.big = 0.0;
+            if (qnext == P_NONE) S.status = ST_NONE1;
+        }
+        __syncthreads();
+        if (S.status != ST_OK) break;
         const int q = S.q;
         const int kq = A.head[m + q];
         const double nnz_q = (kq < m) ? 1.0 : (double)(__ldg(A.a_ptr + (kq - m) + 1) - __ldg(A.a_ptr + (kq - m)));
-        /* ---- P2: tcol, first half ---- */
-        eng_ftran_head_col(X, A, S.k, kq, A.yk);
+        /* ---- A: tcol, first half ---- */
+        eng_ftran_head_col(X, A, S.k, kq, A.yk, A.ycol);
         eng_bar(X, A);
-        eng_mark(X, A, 1, 12.0 * nnz_q + 8.0 * S.k * nnz_q * ((double)S.k / m) + 8.0 * S.k);
-        /* ---- P3: tcol, second half + the reductions of k_primal_prep ---- */
+        eng_mark(X, A, PP_A, 12.0 * nnz_q + 8.0 * S.k * nnz_q * ((double)S.k / m) + 8.0 * S.k);
+        /* ---- B: tcol, second half + the reductions of k_primal_prep ---- */
         {
             Key none = {0.0, 0.0, 0.0, 0, 0};
             Key acc = none;
-            ENG_GROUPS(A.gr, (eng_ftran_tail<GG, true>(X, A, S, A.hz, A.yk, A.tcol, acc)));
-            Key r = eng_allreduce(X, A, acc, none, 1, CombSum2());
+            eng_ftran_tail<true>(X, A, S, A.hz, A.ycol, A.tcol, acc);
+            Key r = eng_allreduce(X, A, acc, none, CombSum2());
             if (X.tid == 0) {
                 const double big = r.c;
                 S.tcol_max = big;
@@ -634,13 +812,34 @@ __global__ void __launch_bounds__(ENG_NT, 1) k_engine_primal(EngArgs A)
                 }
             }
             __syncthreads();
-            eng_mark(X, A, 2, 12.0 * (double)__ldg(A.at_ptr + m) * (1.0 - (double)S.k / m) + 29.0 * m);
-            if (S.status != ST_OK) break;
+            if (S.status != ST_OK) { eng_mark(X, A, PP_B, 0.0); break; }
         }
         const double sgn = (S.d1 > 0.0 ? -1.0 : +1.0);
         const bool pse = gamma_on(&S);
-        /* ---- P4: Harris pass 1 (+ first half of u = inv(B') v) ---- */
-        {
+        bool cbar_q_pending = true;    /* reeval_cost result cbar[q] = d1 (lib/glpspx01.js:1915-1918) not stored yet */
+        /* ---- Harris ratio test (chuzr) ---- */
+        if (local_ratio) {
+            Key none = {DBL_MAX, 0.0, 0.0, INT_MAX, 0};
+            Key v = none;
+            if (X.tid == 0 && A.type[kq] == GLP_DB) {
+                v.a = __dsub_rn(A.ub[kq], A.lb[kq]); v.b = 1.0; v.pos = -1; v.aux = 0;
+            }
+            scan_ratio_primal(v, X.tid, ENG_NT, 1, S.phase, sgn, S.eps, 0.0, A.rtol, A.type, A.lb, A.ub,
+                              A.coef, A.head, A.bbar, A.tcol, nullptr, m);
+            Key r = eng_blockall(X, v, none, CombRatio1());
+            if (X.tid == 0) fin_ratio_primal(&S, r, 1, sgn, A.rtol, A.type, A.head, A.tcol, nullptr);
+            __syncthreads();
+            if (S.status == ST_OK && !S.skip2) {
+                v = none;
+                scan_ratio_primal(v, X.tid, ENG_NT, 2, S.phase, sgn, S.eps, S.tmax, A.rtol, A.type, A.lb, A.ub,
+                                  A.coef, A.head, A.bbar, A.tcol, nullptr, m);
+                r = eng_blockall(X, v, none, CombRatio2());
+                if (X.tid == 0) fin_ratio_primal(&S, r, 2, sgn, A.rtol, A.type, A.head, A.tcol, nullptr);
+                __syncthreads();
+            }
+            eng_mark(X, A, PP_B, 12.0 * (double)__ldg(A.at_ptr + m) * (1.0 - (double)S.k / m) + 29.0 * m + 90.0 * m);
+        } else {
+            eng_mark(X, A, PP_B, 12.0 * (double)__ldg(A.at_ptr + m) * (1.0 - (double)S.k / m) + 29.0 * m);
             Key none = {DBL_MAX, 0.0, 0.0, INT_MAX, 0};
             Key v = none;
             if (X.gtid == 0 && A.type[kq] == GLP_DB) {
@@ -648,48 +847,63 @@ __global__ void __launch_bounds__(ENG_NT, 1) k_engine_primal(EngArgs A)
             }
             scan_ratio_primal(v, X.gtid, X.gsize, 1, S.phase, sgn, S.eps, 0.0, A.rtol, A.type, A.lb, A.ub,
                               A.coef, A.head, A.bbar, A.tcol, nullptr, m);
-            if (pse) ENG_GROUPS(A.gc, (eng_btran_head<GG>(X, A, S.k, A.v, A.wk)));
-            Key r = eng_allreduce(X, A, v, none, 2, CombRatio1());
-            /* reeval_cost result (lib/glpspx01.js:1915-1918); every CTA has read the old value by now */
-            if (X.cta == 0 && X.tid == 0) A.cbar[q] = S.d1;
+            Key r = eng_allreduce(X, A, v, none, CombRatio1());
+            if (X.cta == 0 && X.tid == 0) A.cbar[q] = S.d1;     /* every CTA has read the old value by now */
+            cbar_q_pending = false;
             if (X.tid == 0) fin_ratio_primal(&S, r, 1, sgn, A.rtol, A.type, A.head, A.tcol, nullptr);
             __syncthreads();
-            eng_mark(X, A, 3, 45.0 * m + (pse ? 12.0 * (double)__ldg(A.a_ptr + n) * ((double)S.k / n) + 16.0 * S.k : 0.0));
-            if (S.status != ST_OK) break;
-        }
-        /* ---- P5: Harris pass 2 (+ second half of u) ---- */
-        {
-            const bool pass2 = !S.skip2;
-            Key none = {DBL_MAX, 0.0, 0.0, INT_MAX, 0};
-            Key v = none;
-            if (pass2)
+            eng_mark(X, A, PP_R1, 45.0 * m);
+            if (S.status == ST_OK && !S.skip2) {
+                v = none;
                 scan_ratio_primal(v, X.gtid, X.gsize, 2, S.phase, sgn, S.eps, S.tmax, A.rtol, A.type, A.lb, A.ub,
                                   A.coef, A.head, A.bbar, A.tcol, nullptr, m);
-            if (pse && S.p != P_FLIP) eng_gemvT(X, A, S.k, A.wk, A.zn);
-            if (pass2) {
-                Key r = eng_allreduce(X, A, v, none, 3, CombRatio2());
+                r = eng_allreduce(X, A, v, none, CombRatio2());
                 if (X.tid == 0) fin_ratio_primal(&S, r, 2, sgn, A.rtol, A.type, A.head, A.tcol, nullptr);
                 __syncthreads();
-            } else
-                eng_bar(X, A);
-            eng_mark(X, A, 4, (pass2 ? 45.0 * m : 0.0) + (pse ? 8.0 * S.k * (double)S.k : 0.0));
-            if (S.status != ST_OK) break;
+                eng_mark(X, A, PP_R2, 45.0 * m);
+            }
+        }
+        if (S.status != ST_OK) {
+            /* a slower CTA may still be reading cbar[q] in its own copy of the d1/d2 test:
+               the value stored here makes that test come out the same way */
+            if (cbar_q_pending && X.cta == 0 && X.tid == 0) A.cbar[q] = S.d1;
+            break;
         }
         const int p = S.p;
         if (p >= 0) {
-            /* ---- P6: rho and the tail of u ---- */
+            /* ---- C: rho (+ first half of u = inv(B') v) ---- */
             eng_rho(X, A, S.k, p);
-            if (pse)
-                for (int r = X.gtid; r < m; r += X.gsize) {
-                    const int cs = A.cslot[r];
-                    A.u[r] = (cs >= 0) ? A.zn[cs] : A.v[A.bind[r]];
-                }
+            if (pse) eng_btran_head(X, A, S.k);
             eng_bar(X, A);
-            eng_mark(X, A, 5, 12.0 * m + 8.0 * S.k + (pse ? 20.0 * m : 0.0));
-            /* ---- P7: pivot row and PSE inner products ---- */
+            if (cbar_q_pending && X.cta == 0 && X.tid == 0) A.cbar[q] = S.d1;   /* all CTAs are past the d1/d2 test */
+            eng_mark(X, A, PP_C, 12.0 * m + 8.0 * S.k + (pse ? 12.0 * nnzA * ((double)S.k / n) + 16.0 * S.k : 0.0));
+            /* ---- D: second half of u ---- */
+            if (pse) {
+                const int k = S.k;
+                const int LP = max(32, eng_pick_lp(X, k, (double)k / 2));
+                eng_items<1>(X, k, LP,
+                    [&](int cs, int l, int lp, double *a) {
+                        const double *col = A.T + (size_t)cs * A.ldt;
+                        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+                        int b = l;
+                        for (; b + 3 * lp < k; b += 4 * lp) {
+                            const double t0 = __ldcg(col + b), t1 = __ldcg(col + b + lp);
+                            const double t2 = __ldcg(col + b + 2 * lp), t3 = __ldcg(col + b + 3 * lp);
+                            a0 += t0 * A.wk[b]; a1 += t1 * A.wk[b + lp]; a2 += t2 * A.wk[b + 2 * lp]; a3 += t3 * A.wk[b + 3 * lp];
+                        }
+                        for (; b < k; b += lp) a0 += __ldcg(col + b) * A.wk[b];
+                        a[0] = (a0 + a1) + (a2 + a3);
+                    },
+                    [&](int cs, const double *a) { A.u[A.slot_row[cs]] = a[0]; });
+                for (int r = X.gtid; r < m; r += X.gsize)
+                    if (A.cslot[r] < 0) A.u[r] = A.vrow[r];
+                eng_bar(X, A);
+                eng_mark(X, A, PP_D, 8.0 * S.k * (double)S.k + 20.0 * m);
+            }
+            /* ---- E: pivot row and PSE inner products ---- */
             {
                 Key dummy = {0.0, 0.0, 0.0, 0, 0};
-                ENG_GROUPS(A.gc, (eng_trow<GG, false>(X, A, S, dummy)));
+                eng_trow<false>(X, A, S, dummy);
                 eng_bar(X, A);
                 if (X.tid == 0) {
                     /* k_primal_piv: lib/glpspx01.js:1985-2006 */
@@ -703,47 +917,65 @@ __global__ void __launch_bounds__(ENG_NT, 1) k_engine_primal(EngArgs A)
                     if (S.status == ST_OK) eng_describe_change(A, S, C);
                 }
                 __syncthreads();
-                eng_mark(X, A, 6, 12.0 * (double)__ldg(A.a_ptr + n) * (1.0 - (double)S.k / n) + 13.0 * n + 8.0 * m);
+                eng_mark(X, A, PP_E, 12.0 * nnzA * (1.0 - (double)S.k / n) + 13.0 * n + 8.0 * m);
                 if (S.status != ST_OK) break;
             }
         }
-        /* ---- P8: update_bbar / update_cbar / update_gamma / basis change ---- */
+        else if (local_ratio)
+            eng_bar(X, A);      /* bound flip: phase F rewrites bbar, which slower CTAs may still be scanning */
+        /* ---- F: update_bbar / update_cbar / update_gamma / basis change, and the
+                pricing of the next iteration from the values just written ---- */
         {
             const double teta = S.teta;
             const double xq = get_xN(A.stat, A.head, A.lb, A.ub, m, q);
-            if (p >= 0) {
-                const double new_dq = S.new_dq, pivot = A.trow[q];
-                const int kp = C.kp;
-                const int phase = S.phase;
-                for (int t = X.gtid; t < n; t += X.gsize) {
-                    if (t == q) {
-                        double c = new_dq;
-                        if (phase == 1) c -= A.coef[kp];
-                        A.cbar[q] = c;
-                        if (pse) {
-                            double g = 1.0;
-                            if (A.type[kp] != GLP_FX) {
-                                g = S.gamma_q / (pivot * pivot);
-                                if (g < DBL_EPSILON) g = DBL_EPSILON;
-                            }
-                            A.gamma[q] = g;
+            int new_stat;
+            if (p >= 0) new_stat = S.p_stat;
+            else new_stat = (A.stat[q] == GLP_NL) ? GLP_NU : GLP_NL;
+            const double new_dq = S.new_dq;
+            const double pivot = (p >= 0) ? A.trow[q] : 1.0;
+            const int kp = (p >= 0) ? C.kp : 0;
+            const int phase = S.phase;
+            Key pnone = {0.0, 0.0, 0.0, INT_MAX, 0};
+            Key pv = pnone;
+            for (int t = X.gtid; t < n; t += X.gsize) {
+                double dj, g;
+                int st;
+                if (p < 0) {
+                    dj = A.cbar[t]; g = A.gamma[t]; st = A.stat[t];
+                    if (t == q) { dj = S.d1; A.cbar[q] = dj; st = new_stat; }     /* reeval_cost result */
+                }
+                else if (t == q) {
+                    dj = new_dq;
+                    if (phase == 1) dj -= A.coef[kp];
+                    A.cbar[q] = dj;
+                    g = A.gamma[q];
+                    if (pse) {
+                        g = 1.0;
+                        if (A.type[kp] != GLP_FX) {
+                            g = S.gamma_q / (pivot * pivot);
+                            if (g < DBL_EPSILON) g = DBL_EPSILON;
                         }
-                    } else {
-                        const double tr = A.trow[t];
-                        if (tr != 0.0) {
-                            A.cbar[t] -= tr * new_dq;
-                            if (pse) {
-                                const double tt = tr / pivot;
-                                const int k = A.head[m + t];
-                                const double t1 = A.gamma[t] + tt * tt * S.gamma_q + 2.0 * tt * A.svec[t];
-                                const double t2 = (A.refsp[k] ? 1.0 : 0.0) + S.delta_q * tt * tt;
-                                double g = (t1 >= t2 ? t1 : t2);
-                                if (g < DBL_EPSILON) g = DBL_EPSILON;
-                                A.gamma[t] = g;
-                            }
+                        A.gamma[q] = g;
+                    }
+                    st = new_stat;
+                } else {
+                    const double tr = A.trow[t];
+                    dj = A.cbar[t]; g = A.gamma[t]; st = A.stat[t];
+                    if (tr != 0.0) {
+                        dj -= tr * new_dq;
+                        A.cbar[t] = dj;
+                        if (pse) {
+                            const double tt = tr / pivot;
+                            const int k = A.head[m + t];
+                            const double t1 = g + tt * tt * S.gamma_q + 2.0 * tt * A.svec[t];
+                            const double t2 = (A.refsp[k] ? 1.0 : 0.0) + S.delta_q * tt * tt;
+                            g = (t1 >= t2 ? t1 : t2);
+                            if (g < DBL_EPSILON) g = DBL_EPSILON;
+                            A.gamma[t] = g;
                         }
                     }
                 }
+                price_primal(pv, t, st, dj, g, A.tol_dj);
             }
             for (int t = X.gtid; t < m; t += X.gsize) {
                 if (t == p) A.bbar[t] = xq + teta;
@@ -760,15 +992,13 @@ __global__ void __launch_bounds__(ENG_NT, 1) k_engine_primal(EngArgs A)
                         A.hz[__ldg(A.a_ind + ptr)] = 0.0;
             }
             if (p >= 0 && S.k + (C.bnew >= 0) > 0) eng_update_T(X, A, C);
-            /* the O(1) remainder runs after the barrier; readers of the next phase use (qprev, stprev) */
-            int new_stat;
-            if (p >= 0) new_stat = S.p_stat;
-            else new_stat = (A.stat[q] == GLP_NL) ? GLP_NU : GLP_NL;
-            eng_bar(X, A);
-            eng_mark(X, A, 7, 24.0 * m + (p >= 0 ? 40.0 * n + 16.0 * S.k * (double)S.k : 0.0));
+            Key r = eng_allreduce(X, A, pv, pnone, CombArgMax());
+            qnext = (r.a > 0.0 && r.pos != INT_MAX) ? r.pos : P_NONE;
+            eng_mark(X, A, PP_F, 24.0 * m + 17.0 * n + (p >= 0 ? 40.0 * n + 16.0 * S.k * (double)S.k : 0.0));
+            /* the O(1) remainder: every CTA has arrived, nobody reads the old header any more */
             if (X.cta == 0 && X.tid == 0) {
                 if (p >= 0) {
-                    if (S.phase == 1) A.coef[C.kp] = 0.0;       /* lib/glpspx01.js:2016-2020 */
+                    if (phase == 1) A.coef[C.kp] = 0.0;       /* lib/glpspx01.js:2016-2020 */
                     eng_bookkeep(A, C, new_stat, false);
                 } else
                     A.stat[q] = (signed char)new_stat;
@@ -777,8 +1007,7 @@ __global__ void __launch_bounds__(ENG_NT, 1) k_engine_primal(EngArgs A)
                 if (p >= 0) S.k = C.knew;
                 iter_end(&S, p >= 0, 0);
             }
-            qprev = q; stprev = new_stat;
-            __syncthreads();
+            eng_header_done(X, A);
         }
     }
     if (X.cta == 0 && X.tid == 0) *A.ctrl = S;
@@ -795,102 +1024,116 @@ __global__ void __launch_bounds__(ENG_NT, 1) k_engine_dual(EngArgs A)
     EngCtx X;
     eng_init(X, A, eng_dyn);
     const int m = A.m, n = A.n;
+    const bool local_ratio = (n <= ENG_LOCAL_MAX);
+    const double nnzA = (double)__ldg(A.a_ptr + n);
     if (X.tid == 0) S = *A.ctrl;
     __syncthreads();
-    int pprev = -1, kprev = 0;
+    int pnext = P_NONE;
+    double dnext = 0.0;
     for (int it = 0; it < A.max_iters && S.status == ST_OK; it++) {
-        /* ---- D1: chuzr ---- */
-        {
+        /* ---- pricing (chuzr): see the primal engine ---- */
+        if (it == 0) {
             Key none = {0.0, 0.0, 0.0, INT_MAX, 0};
             Key v = none;
-            scan_chuzr_dual(v, X.gtid, X.gsize, m, A.type, A.lb, A.ub, A.head, A.bbar, A.gamma, A.tol_bnd,
-                            pprev, kprev);
-            Key r = eng_allreduce(X, A, v, none, 0, CombArgMax());
-            if (X.tid == 0) {
-                const bool found = (r.a > 0.0 && r.pos != INT_MAX);
-                S.p = found ? r.pos : P_NONE;
-                S.delta = found ? r.b : 0.0;
-                S.big = 0.0;
-                if (!found) S.status = ST_NONE1;
-            }
-            __syncthreads();
-            eng_mark(X, A, 0, 37.0 * m);
-            if (S.status != ST_OK) break;
+            scan_chuzr_dual(v, X.gtid, X.gsize, m, A.type, A.lb, A.ub, A.head, A.bbar, A.gamma, A.tol_bnd, -1, 0);
+            Key r = eng_allreduce(X, A, v, none, CombArgMax());
+            const bool found = (r.a > 0.0 && r.pos != INT_MAX);
+            pnext = found ? r.pos : P_NONE;
+            dnext = found ? r.b : 0.0;
+            eng_mark(X, A, PD_PRICE0, 37.0 * m);
         }
+        if (X.tid == 0) {
+            S.p = pnext;
+            S.delta = dnext;
+            S.big = 0.0;
+            if (pnext == P_NONE) S.status = ST_NONE1;
+        }
+        __syncthreads();
+        if (S.status != ST_OK) break;
         const int p = S.p;
         const bool pse = gamma_on(&S);
         const double sgn = (S.delta > 0.0 ? +1.0 : -1.0);
-        const double nnzA = (double)__ldg(A.a_ptr + n);
-        /* ---- D2: rho ---- */
+        /* ---- rho ---- */
         eng_rho(X, A, S.k, p);
         eng_bar(X, A);
-        eng_mark(X, A, 1, 12.0 * m + 8.0 * S.k);
-        /* ---- D3: pivot row, |trow|_inf, sum of squares over the reference space ---- */
+        eng_mark(X, A, PD_RHO, 12.0 * m + 8.0 * S.k);
+        /* ---- pivot row, |trow|_inf, sum of squares over the reference space ---- */
         {
             Key none = {0.0, 0.0, 0.0, 0, 0};
             Key acc = none;
-            ENG_GROUPS(A.gc, (eng_trow<GG, true>(X, A, S, acc)));
-            Key r = eng_allreduce(X, A, acc, none, 1, CombSum2());
+            eng_trow<true>(X, A, S, acc);
+            Key r = eng_allreduce(X, A, acc, none, CombSum2());
             if (X.tid == 0) {
                 S.trow_max = r.c;
                 S.eps = A.tol_bnd * (1.0 + 0.01 * r.c);      /* sic: tol_bnd, lib/glpspx02.js:1851 */
                 S.scal = r.a;                                 /* sum of trow_j^2, j in the reference space */
             }
             __syncthreads();
-            eng_mark(X, A, 2, 12.0 * nnzA * (1.0 - (double)S.k / n) + 13.0 * n + 8.0 * m);
+            eng_mark(X, A, PD_TROW, 12.0 * nnzA * (1.0 - (double)S.k / n) + 13.0 * n + 8.0 * m);
         }
-        /* ---- D4: Harris pass 1 (+ right-hand side of update_gamma) ---- */
-        {
+        /* ---- Harris ratio test (chuzc) and the right-hand side of update_gamma ---- */
+        if (local_ratio) {
+            Key none = {DBL_MAX, 0.0, 0.0, INT_MAX, 0};
+            Key v = none;
+            scan_ratio_dual(v, X.tid, ENG_NT, 1, sgn, S.eps, 0.0, A.rtol, A.stat, A.cbar, A.trow, nullptr, n);
+            Key r = eng_blockall(X, v, none, CombRatio1());
+            if (X.tid == 0) fin_ratio_dual(&S, r, 1, sgn, A.rtol, A.trow, nullptr);
+            __syncthreads();
+            if (S.status == ST_OK && !S.skip2) {
+                v = none;
+                scan_ratio_dual(v, X.tid, ENG_NT, 2, sgn, S.eps, S.tmax, A.rtol, A.stat, A.cbar, A.trow, nullptr, n);
+                r = eng_blockall(X, v, none, CombRatio2());
+                if (X.tid == 0) fin_ratio_dual(&S, r, 2, sgn, A.rtol, A.trow, nullptr);
+                __syncthreads();
+            }
+            if (S.status != ST_OK) break;
+            if (pse) {
+                eng_gamma_rhs(X, A);
+                eng_bar(X, A);
+            }
+            eng_mark(X, A, PD_X1, 34.0 * n + (pse ? 17.0 * nnzA + 16.0 * m : 0.0));
+        } else {
             Key none = {DBL_MAX, 0.0, 0.0, INT_MAX, 0};
             Key v = none;
             scan_ratio_dual(v, X.gtid, X.gsize, 1, sgn, S.eps, 0.0, A.rtol, A.stat, A.cbar, A.trow, nullptr, n);
-            if (pse) ENG_GROUPS(A.gr, (eng_gamma_rhs<GG>(X, A)));
-            Key r = eng_allreduce(X, A, v, none, 2, CombRatio1());
+            if (pse) eng_gamma_rhs(X, A);
+            Key r = eng_allreduce(X, A, v, none, CombRatio1());
             if (X.tid == 0) fin_ratio_dual(&S, r, 1, sgn, A.rtol, A.trow, nullptr);
             __syncthreads();
-            eng_mark(X, A, 3, 17.0 * n + (pse ? 17.0 * nnzA + 16.0 * m : 0.0));
+            eng_mark(X, A, PD_R1, 17.0 * n + (pse ? 17.0 * nnzA + 16.0 * m : 0.0));
             if (S.status != ST_OK) break;
-        }
-        /* ---- D5: Harris pass 2 (+ dense product y2 = T v_N of update_gamma) ---- */
-        {
-            const bool pass2 = !S.skip2;
-            Key none = {DBL_MAX, 0.0, 0.0, INT_MAX, 0};
-            Key v = none;
-            if (pass2)
+            if (!S.skip2) {
+                v = none;
                 scan_ratio_dual(v, X.gtid, X.gsize, 2, sgn, S.eps, S.tmax, A.rtol, A.stat, A.cbar, A.trow, nullptr, n);
-            if (pse && S.k > 0) {
-                const int k = S.k;
-                const double *val = A.wk;
-                if (k <= A.dcap && X.cta * 8 < k) {
-                    for (int e = X.tid; e < k; e += ENG_NT) X.sh_d[e] = A.wk[e];
-                    __syncthreads();
-                    val = X.sh_d;
-                }
-                eng_gemv_rows(X, A, k, k, nullptr, val, A.yk2, false);
-            }
-            if (pass2) {
-                Key r = eng_allreduce(X, A, v, none, 3, CombRatio2());
+                r = eng_allreduce(X, A, v, none, CombRatio2());
                 if (X.tid == 0) fin_ratio_dual(&S, r, 2, sgn, A.rtol, A.trow, nullptr);
                 __syncthreads();
-            } else
-                eng_bar(X, A);
-            eng_mark(X, A, 4, (pass2 ? 17.0 * n : 0.0) + (pse ? 8.0 * S.k * (double)S.k + 16.0 * S.k : 0.0));
-            if (S.status != ST_OK) break;
+                eng_mark(X, A, PD_R2, 17.0 * n);
+                if (S.status != ST_OK) break;
+            }
         }
         const int q = S.q;
         const int kq = A.head[m + q];
-        /* ---- D6: tcol, first half (+ tail of u = inv(B) v) ---- */
-        eng_ftran_head_col(X, A, S.k, kq, A.yk);
-        if (pse) {
-            Key dummy = {0.0, 0.0, 0.0, 0, 0};
-            ENG_GROUPS(A.gr, (eng_ftran_tail<GG, false>(X, A, S, A.v, A.yk2, A.u, dummy)));
+        /* ---- tcol, first half, and the dense product y2 = T v_N of update_gamma ---- */
+        if (pse && S.k > 0) {
+            const int k = S.k;
+            const double *val = A.wk;
+            if (k <= A.dcap && X.cta * 8 < k) {
+                for (int e = X.tid; e < k; e += ENG_NT) X.sh_d[e] = A.wk[e];
+                __syncthreads();
+                val = X.sh_d;
+            }
+            eng_gemv_rows(X, A, k, k, nullptr, val, A.yk2, A.ycol2, false);
+            __syncthreads();
         }
+        eng_ftran_head_col(X, A, S.k, kq, A.yk, A.ycol);
         eng_bar(X, A);
-        eng_mark(X, A, 5, (pse ? 12.0 * nnzA * (1.0 - (double)S.k / m) + 16.0 * m : 0.0) + 8.0 * S.k);
-        /* ---- D7: tcol, second half ---- */
+        eng_mark(X, A, PD_TCOL1, (pse ? 8.0 * S.k * (double)S.k + 16.0 * S.k : 0.0) + 8.0 * S.k);
+        /* ---- tcol, second half, and the tail of u = inv(B) v ---- */
         {
             Key dummy = {0.0, 0.0, 0.0, 0, 0};
-            ENG_GROUPS(A.gr, (eng_ftran_tail<GG, false>(X, A, S, A.hz, A.yk, A.tcol, dummy)));
+            if (pse) eng_ftran_tail<false>(X, A, S, A.v, A.ycol2, A.u, dummy);
+            eng_ftran_tail<false>(X, A, S, A.hz, A.ycol, A.tcol, dummy);
             eng_bar(X, A);
             if (X.tid == 0) {
                 /* k_dual_prep: lib/glpspx02.js:1913-1938, :1103-1115 */
@@ -910,10 +1153,11 @@ __global__ void __launch_bounds__(ENG_NT, 1) k_engine_dual(EngArgs A)
                 }
             }
             __syncthreads();
-            eng_mark(X, A, 6, 12.0 * nnzA * (1.0 - (double)S.k / m) + 16.0 * m);
+            eng_mark(X, A, PD_TCOL2, (pse ? 2.0 : 1.0) * (12.0 * nnzA * (1.0 - (double)S.k / m) + 16.0 * m));
             if (S.status != ST_OK) break;
         }
-        /* ---- D8: update_cbar / update_bbar / update_gamma / basis change ---- */
+        /* ---- update_cbar / update_bbar / update_gamma / basis change, and the
+                pricing of the next iteration from the values just written ---- */
         {
             const double teta = S.teta, new_dq = S.new_dq;
             const int kp = C.kp;
@@ -927,11 +1171,17 @@ __global__ void __launch_bounds__(ENG_NT, 1) k_engine_dual(EngArgs A)
                     if (tr != 0.0) A.cbar[t] -= tr * new_dq;
                 }
             }
+            Key pnone = {0.0, 0.0, 0.0, INT_MAX, 0};
+            Key pv = pnone;
             for (int t = X.gtid; t < m; t += X.gsize) {
+                double bi, g = A.gamma[t];
+                int k;
                 if (t == p) {
-                    A.bbar[p] = xq + teta;
+                    k = kq;
+                    bi = xq + teta;
+                    A.bbar[p] = bi;
                     if (pse) {
-                        double g = 1.0;
+                        g = 1.0;
                         if (A.type[kq] != GLP_FR) {
                             g = S.gamma_q / (pivot * pivot);
                             if (g < DBL_EPSILON) g = DBL_EPSILON;
@@ -944,15 +1194,16 @@ __global__ void __launch_bounds__(ENG_NT, 1) k_engine_dual(EngArgs A)
                         A.gamma[p] = g;
                     }
                 } else {
+                    k = A.head[t];
+                    bi = A.bbar[t];
                     const double tc = A.tcol[t];
                     if (tc != 0.0) {
-                        if (teta != 0.0) A.bbar[t] += tc * teta;
-                        const int k = A.head[t];
+                        if (teta != 0.0) { bi += tc * teta; A.bbar[t] = bi; }
                         if (pse && A.type[k] != GLP_FR) {
                             const double tt = tc / pivot;
-                            const double t1 = A.gamma[t] + tt * tt * S.gamma_q + 2.0 * tt * A.u[t];
+                            const double t1 = g + tt * tt * S.gamma_q + 2.0 * tt * A.u[t];
                             const double t2 = (A.refsp[k] ? 1.0 : 0.0) + S.delta_q * tt * tt;
-                            double g = (t1 >= t2 ? t1 : t2);
+                            g = (t1 >= t2 ? t1 : t2);
                             if (g < DBL_EPSILON) g = DBL_EPSILON;
                             if (drop) {
                                 g -= tt * tt;
@@ -962,6 +1213,7 @@ __global__ void __launch_bounds__(ENG_NT, 1) k_engine_dual(EngArgs A)
                         }
                     }
                 }
+                price_dual(pv, t, A.type[k], A.lb[k], A.ub[k], bi, g, A.tol_bnd);
             }
             if (X.cta == 0) {
                 if (kq < m) { if (X.tid == 0) A.hz[kq] = 0.0; }
@@ -970,16 +1222,20 @@ __global__ void __launch_bounds__(ENG_NT, 1) k_engine_dual(EngArgs A)
                         A.hz[__ldg(A.a_ind + ptr)] = 0.0;
             }
             if (S.k + (C.bnew >= 0) > 0) eng_update_T(X, A, C);
-            eng_bar(X, A);
-            eng_mark(X, A, 7, 24.0 * n + 40.0 * m + 16.0 * S.k * (double)S.k);
+            Key r = eng_allreduce(X, A, pv, pnone, CombArgMax());
+            {
+                const bool found = (r.a > 0.0 && r.pos != INT_MAX);
+                pnext = found ? r.pos : P_NONE;
+                dnext = found ? r.b : 0.0;
+            }
+            eng_mark(X, A, PD_UPD, 24.0 * n + 40.0 * m + 37.0 * m + 16.0 * S.k * (double)S.k);
             const int new_stat = (A.type[kp] == GLP_FX) ? GLP_NS : (S.delta > 0.0 ? GLP_NL : GLP_NU);
             if (X.cta == 0 && X.tid == 0) eng_bookkeep(A, C, new_stat, pse && drop);
             if (X.tid == 0) {
                 S.k = C.knew;
                 iter_end(&S, true, 1);
             }
-            pprev = p; kprev = kq;
-            __syncthreads();
+            eng_header_done(X, A);
         }
     }
     if (X.cta == 0 && X.tid == 0) *A.ctrl = S;

@@ -139,12 +139,15 @@ struct glpb_prob {
     double *w1 = nullptr, *w2 = nullptr, *w3 = nullptr, *w4 = nullptr, *w5 = nullptr; /* [m] work */
     double *yk = nullptr, *wk = nullptr;   /* [ldt] work in kernel space */
     double *yk2 = nullptr, *zn = nullptr;  /* [ldt] engine work in kernel space */
-    unsigned int *bar = nullptr;           /* engine: grid barrier counter */
+    struct EngSlot *eng_slots = nullptr;   /* engine: barrier flags + partials [ENG_RING][ENG_MAXG] */
+    double *eng_cols = nullptr;            /* engine: ycol, ycol2, trowcol [3n] and vrow [m] */
     long long *eng_cyc = nullptr;          /* engine: SM cycles per phase [16] */
     double *eng_bytes = nullptr;           /* engine: algorithmic bytes per phase [16] */
     int sm_count = 0, eng_dcap = 0, eng_smem = 0, eng_ready = 0;
     long n_eng_launch = 0, n_eng_prof_iter[2] = {0, 0};
-    double *T = nullptr, *partial = nullptr;
+    double *T = nullptr, *T2 = nullptr, *partial = nullptr;   /* T2: output buffer of the refactorisation */
+    struct RefSlot *ref_slots = nullptr;
+    unsigned int *ref_flags = nullptr;
     int partial_rows = 0;
     int *rslot = nullptr, *slot_pos = nullptr, *cslot = nullptr, *slot_row = nullptr;
     int *gj_piv = nullptr;

@@ -176,24 +176,27 @@ __device__ void iter_end(Ctrl *ctrl, bool basis_changed, int dual)
    start, start+stride, ...  Shared by the stand-alone kernel and the persistent
    iteration engine; (jx, stx) overrides the status of one column whose header
    update is still in flight (engine), jx = -1 otherwise. */
+__device__ __forceinline__ void price_primal(Key &v, int j, int st, double dj, double gam, double tol_dj)
+{
+    bool ok;
+    switch (st) {
+    case GLP_NL: ok = !(dj >= -tol_dj); break;
+    case GLP_NU: ok = !(dj <= +tol_dj); break;
+    case GLP_NF: ok = !(-tol_dj <= dj && dj <= +tol_dj); break;
+    default: ok = false;
+    }
+    if (ok) {
+        double temp = __ddiv_rn(__dmul_rn(dj, dj), gam);
+        if (v.a < temp || (v.a == temp && temp > 0.0 && j < v.pos)) { v.a = temp; v.pos = j; }
+    }
+}
+
 __device__ __forceinline__ void scan_chuzc_primal(Key &v, int start, int stride, int n,
                                                   const signed char *stat, const double *cbar,
                                                   const double *gamma, double tol_dj, int jx, int stx)
 {
-    for (int j = start; j < n; j += stride) {
-        double dj = cbar[j];
-        bool ok;
-        switch (j == jx ? stx : (int)stat[j]) {
-        case GLP_NL: ok = !(dj >= -tol_dj); break;
-        case GLP_NU: ok = !(dj <= +tol_dj); break;
-        case GLP_NF: ok = !(-tol_dj <= dj && dj <= +tol_dj); break;
-        default: ok = false;
-        }
-        if (ok) {
-            double temp = __ddiv_rn(__dmul_rn(dj, dj), gamma[j]);
-            if (v.a < temp) { v.a = temp; v.pos = j; }
-        }
-    }
+    for (int j = start; j < n; j += stride)
+        price_primal(v, j, j == jx ? stx : (int)stat[j], cbar[j], gamma[j], tol_dj);
 }
 
 /* Algorithmic bytes: 17 per column (stat 1 + cbar 8 + gamma 8). */
@@ -215,6 +218,25 @@ __global__ void k_chuzc_primal(Ctrl *ctrl, int n, const signed char *__restrict_
 
 /* chuzr (dual pricing), lib/glpspx02.js:572-625: the scan over basic positions.
    (ix, kx) overrides head[ix] (engine: header update in flight), ix = -1 otherwise. */
+__device__ __forceinline__ void price_dual(Key &v, int i, int t, double l, double u, double bi, double g,
+                                           double tol_bnd)
+{
+    double ri = 0.0;
+    if (t == GLP_LO || t == GLP_DB || t == GLP_FX) {
+        double eps = relax(tol_bnd, l);
+        if (bi < __dsub_rn(l, eps)) ri = __dsub_rn(l, bi);
+    }
+    if (t == GLP_UP || t == GLP_DB || t == GLP_FX) {
+        double eps = relax(tol_bnd, u);
+        if (bi > __dadd_rn(u, eps)) ri = __dsub_rn(u, bi);
+    }
+    if (ri != 0.0) {
+        if (g < DBL_EPSILON) g = DBL_EPSILON;
+        double temp = __ddiv_rn(__dmul_rn(ri, ri), g);
+        if (v.a < temp || (v.a == temp && temp > 0.0 && i < v.pos)) { v.a = temp; v.b = ri; v.pos = i; }
+    }
+}
+
 __device__ __forceinline__ void scan_chuzr_dual(Key &v, int start, int stride, int m,
                                                 const signed char *type, const double *lb,
                                                 const double *ub, const int *head, const double *bbar,
@@ -222,22 +244,7 @@ __device__ __forceinline__ void scan_chuzr_dual(Key &v, int start, int stride, i
 {
     for (int i = start; i < m; i += stride) {
         int k = (i == ix) ? kx : head[i];
-        int t = type[k];
-        double ri = 0.0, bi = bbar[i];
-        if (t == GLP_LO || t == GLP_DB || t == GLP_FX) {
-            double l = lb[k], eps = relax(tol_bnd, l);
-            if (bi < __dsub_rn(l, eps)) ri = __dsub_rn(l, bi);
-        }
-        if (t == GLP_UP || t == GLP_DB || t == GLP_FX) {
-            double u = ub[k], eps = relax(tol_bnd, u);
-            if (bi > __dadd_rn(u, eps)) ri = __dsub_rn(u, bi);
-        }
-        if (ri != 0.0) {
-            double g = gamma[i];
-            if (g < DBL_EPSILON) g = DBL_EPSILON;
-            double temp = __ddiv_rn(__dmul_rn(ri, ri), g);
-            if (v.a < temp) { v.a = temp; v.b = ri; v.pos = i; }
-        }
+        price_dual(v, i, type[k], lb[k], ub[k], bbar[i], gamma[i], tol_bnd);
     }
 }
 

@@ -1,0 +1,328 @@
+/* refactor.cuh -- refactorisation of the basis inverse in ONE cooperative
+ * launch (replaces invert_B -> bfd_factorize -> luf_factorize of the reference,
+ * lib/glpspx01.js:177-181, lib/glpluf.js:1105-1225, for the explicit inverse
+ * T = -inv(A[R_N, J_B]) that libglpb200 keeps; see glpb_internal.cuh).
+ *
+ * Blocked Gauss-Jordan with partial pivoting, NB pivots per round:
+ *   1. panel: the rows of the NB panel columns are distributed over the CTAs
+ *      and live in shared memory for the whole round.  One grid-wide
+ *      arg-reduction per pivot: every CTA publishes its best candidate row
+ *      TOGETHER with that row's panel entries (and the owner of row t publishes
+ *      row t), so that after the reduction every CTA can swap and eliminate its
+ *      own rows without a second exchange.
+ *   2. the round's row swaps on every other column (a gather/scatter over the
+ *      <= 2 NB affected rows, not NB sequential swaps) and a copy of their
+ *      pivot-row entries;
+ *   3. rank-NB update of the other columns  X[i,c] = (i in P ? 0 : X[i,c]) +
+ *      sum_t Pf[i,t] Xp[t,c]  -- one read+write of X per round.
+ * The final column permutation that undoes the row pivoting and the negation
+ * are one out-of-place streaming pass into the second buffer (the handle flips
+ * its T pointers).  Ties in the pivot search go to the lowest row index, so the
+ * result does not depend on the grid size or on scheduling.
+ */
+#ifndef GLPB_REFACTOR_CUH
+#define GLPB_REFACTOR_CUH
+#include "engine.cuh"
+
+#define REF_NT 1024
+#define REF_NB 32            /* pivots per round                              */
+#define REF_CB 16            /* columns per update block                      */
+#define REF_RMAX 256         /* distributed panel: max rows per CTA            */
+
+struct __align__(128) RefSlot {
+    double absval;
+    int row;
+    unsigned int flag;
+    double cand[REF_NB];     /* panel entries of the candidate row            */
+    double rowt[REF_NB];     /* panel entries of row t (owner of t only)      */
+};
+
+struct RefArgs {
+    Ctrl *ctrl;
+    int m, ldt;
+    int nbr;                 /* pivots per round (8, 16 or 32)                */
+    int single;              /* 1: the whole panel lives in CTA 0's shared memory (k nbr 8 bytes fit);
+                                0: its rows are spread over all CTAs          */
+    int *plan;               /* [2 + 4 REF_NB] single mode: naff, sing, aff_row, aff_src published by CTA 0 */
+    double *X;               /* working matrix (in: nothing, built here)      */
+    double *T2;              /* out: T = -inv(M), column-major, ld = ldt      */
+    const int *a_ptr, *a_ind; const double *a_val;
+    const int *head, *slot_pos, *cslot;
+    int *piv;                /* [ldt] pivot rows                              */
+    RefSlot *slots;          /* [ENG_RING][ENG_MAXG], zeroed by the host      */
+    unsigned int *flags;     /* [ENG_RING][ENG_MAXG*32] plain barrier flags, one line each, zeroed */
+};
+
+struct RefCtx {
+    int G, cta, tid, lane, warp;
+    unsigned int seq;
+};
+
+__device__ __forceinline__ void ref_bar(RefCtx &X, const RefArgs &A)
+{
+    __syncthreads();
+    X.seq++;
+    if (X.G > 1) {
+        unsigned int *ring = A.flags + (size_t)(X.seq & (ENG_RING - 1)) * ENG_MAXG * 32;
+        if (X.tid == 0) eng_st_release(ring + X.cta * 32, X.seq);
+        if (X.tid < X.G) {
+            while (eng_ld_relaxed(ring + X.tid * 32) < X.seq) { }
+            eng_fence_acq();
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(REF_NT, 1) k_refactor(RefArgs A)
+{
+    extern __shared__ double ref_dyn[];       /* pan[R][nbr], fcol[R] | later: int map[k], pv[k] */
+    __shared__ double rowR[REF_NB], rowT[REF_NB], srow[REF_NB];
+    __shared__ double xs[REF_NB][REF_CB];
+    __shared__ int s_piv[REF_NB];
+    __shared__ int aff_row[2 * REF_NB], aff_src[2 * REF_NB];
+    __shared__ int s_naff, s_r, s_wc, s_sing;
+    __shared__ Key wres[ENG_MAXG / 32];
+    __shared__ double s_max[32];
+
+    RefCtx X;
+    X.G = gridDim.x; X.cta = blockIdx.x; X.tid = threadIdx.x; X.lane = X.tid & 31; X.warp = X.tid >> 5;
+    X.seq = 0u;
+    const int G = X.G, cta = X.cta, tid = X.tid;
+    const int k = A.ctrl->k;
+    if (A.ctrl->sing || k <= 0) return;
+    const size_t ldt = (size_t)A.ldt;
+    const int m = A.m;
+    double *pan = ref_dyn;
+
+    /* ---- build M[cs, b] = A[row_cs, j_b] (column b contiguous) ---- */
+    {
+        double mx = 0.0;
+        for (int b = cta; b < k; b += G) {
+            double *col = A.X + (size_t)b * ldt;
+            for (int cs = tid; cs < k; cs += REF_NT) col[cs] = 0.0;
+            __syncthreads();
+            const int j = A.head[A.slot_pos[b]] - m;
+            for (int ptr = __ldg(A.a_ptr + j) + tid; ptr < __ldg(A.a_ptr + j + 1); ptr += REF_NT) {
+                const int cs = A.cslot[__ldg(A.a_ind + ptr)];
+                if (cs >= 0) { const double a = __ldg(A.a_val + ptr); col[cs] = a; mx = fmax(mx, fabs(a)); }
+            }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) mx = fmax(mx, __shfl_xor_sync(FULLMASK, mx, off));
+        if (X.lane == 0) s_max[X.warp] = mx;
+        __syncthreads();
+        if (tid == 0) {
+            for (int w = 1; w < 32; w++) mx = fmax(mx, s_max[w]);
+            if (mx > 0.0) atomic_max_abs(&A.ctrl->max_a, mx);
+        }
+    }
+    ref_bar(X, A);
+    const double max_a = __ldcg(&A.ctrl->max_a);
+    const double tiny = 1e-13 * fmax(max_a, 1e-300);
+
+    /* panel ownership: PG CTAs hold R rows each */
+    const int PG = A.single ? 1 : G;
+    const int NBR = A.nbr;
+    const int R = (k + PG - 1) / PG;
+    const int r0 = (cta < PG) ? min(k, cta * R) : k, r1 = min(k, r0 + R);
+    const int nloc = r1 - r0;
+    const int PS = NBR + 1;                   /* odd row stride: column walks are bank-conflict free */
+    double *fcol = pan + (size_t)R * PS;
+
+    for (int c0 = 0; c0 < k; c0 += NBR) {
+        const int nb = min(NBR, k - c0);
+        /* ---- panel into shared memory ---- */
+        for (int e = tid; e < nloc * nb; e += REF_NT) {
+            const int i = e % nloc, cc = e / nloc;
+            pan[i * PS + cc] = A.X[(size_t)(c0 + cc) * ldt + r0 + i];
+        }
+        if (tid < nb) { aff_row[tid] = c0 + tid; aff_src[tid] = c0 + tid; }
+        if (tid == 0) s_naff = nb;
+        __syncthreads();
+        for (int tt = 0; tt < nb && cta < PG; tt++) {
+            const int t = c0 + tt;
+            /* best local candidate among rows >= t */
+            Key none = {-1.0, 0.0, 0.0, INT_MAX, 0};
+            Key v = none;
+            for (int i = tid; i < nloc; i += REF_NT)
+                if (r0 + i >= t) {
+                    Key c = {fabs(pan[i * PS + tt]), 0.0, 0.0, r0 + i, 0};
+                    CombArgMax()(v, c);
+                }
+            v = block_reduce(v, none, CombArgMax());
+            if (tid == 0) s_r = v.pos;
+            __syncthreads();
+            int r, wc;
+            if (PG > 1) {
+                X.seq++;
+                RefSlot *ring = A.slots + (X.seq & (ENG_RING - 1)) * ENG_MAXG;
+                RefSlot *mine = ring + cta;
+                const int lr = s_r;
+                if (tid < nb) {
+                    if (lr != INT_MAX) __stcg(&mine->cand[tid], pan[(lr - r0) * PS + tid]);
+                    if (t >= r0 && t < r1) __stcg(&mine->rowt[tid], pan[(t - r0) * PS + tid]);
+                }
+                if (tid == 0) { __stcg(&mine->absval, v.a); __stcg(&mine->row, v.pos); }
+                __syncthreads();
+                if (tid == 0) eng_st_release(&mine->flag, X.seq);
+                const int nw = (G + 31) >> 5;
+                if (X.warp < nw) {
+                    Key c = none;
+                    if (tid < G) {
+                        while (eng_ld_relaxed(&ring[tid].flag) < X.seq) { }
+                        eng_fence_acq();
+                        c.a = __ldcg(&ring[tid].absval); c.pos = __ldcg(&ring[tid].row); c.aux = tid;
+                    }
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) {
+                        Key o = key_shfl_down(c, off);
+                        CombArgMax()(c, o);
+                    }
+                    if (X.lane == 0) wres[X.warp] = c;
+                }
+                __syncthreads();
+                if (tid == 0) {
+                    Key c = wres[0];
+                    for (int w = 1; w < nw; w++) CombArgMax()(c, wres[w]);
+                    s_r = c.pos; s_wc = c.aux;
+                    s_sing = !(c.a > tiny);
+                }
+                __syncthreads();
+                r = s_r; wc = s_wc;
+                if (s_sing) { if (cta == 0 && tid == 0) A.ctrl->sing = 1; return; }
+                const int ot = min(G - 1, t / R);
+                if (tid < nb) {
+                    rowR[tid] = __ldcg(&ring[wc].cand[tid]);
+                    rowT[tid] = __ldcg(&ring[ot].rowt[tid]);
+                }
+            } else {
+                if (tid == 0) s_sing = !(v.a > tiny);
+                __syncthreads();
+                r = s_r; wc = 0;
+                if (s_sing) break;             /* reported after the round's barrier */
+                if (tid < nb) { rowR[tid] = pan[r * PS + tid]; rowT[tid] = pan[t * PS + tid]; }
+            }
+            __syncthreads();
+            if (tid == 0) s_piv[tt] = r;
+            /* the round's net row permutation, kept as a gather list: slots
+               0..nb-1 are the panel rows, further slots the outside pivot rows */
+            if (X.warp == 0) {
+                int ib;
+                if (r < c0 + nb) ib = r - c0;
+                else {
+                    const int na = s_naff;
+                    const bool hit = (nb + X.lane < na) && (aff_row[nb + X.lane] == r);
+                    const unsigned int bm = __ballot_sync(FULLMASK, hit);
+                    if (bm) ib = nb + __ffs(bm) - 1;
+                    else {
+                        ib = na;
+                        if (X.lane == 0) { aff_row[na] = r; aff_src[na] = r; s_naff = na + 1; }
+                    }
+                    __syncwarp();
+                }
+                if (X.lane == 0 && r != t) { const int tmp = aff_src[tt]; aff_src[tt] = aff_src[ib]; aff_src[ib] = tmp; }
+            }
+            /* swap rows t and r inside the panel */
+            if (r != t && tid < nb) {
+                if (r >= r0 && r < r1) pan[(r - r0) * PS + tid] = rowT[tid];
+                if (t >= r0 && t < r1) pan[(t - r0) * PS + tid] = rowR[tid];
+            }
+            const double ipv = 1.0 / rowR[tt];
+            if (tid < nb) srow[tid] = (tid == tt) ? ipv : rowR[tid] * ipv;
+            __syncthreads();
+            for (int i = tid; i < nloc; i += REF_NT) fcol[i] = pan[i * PS + tt];
+            __syncthreads();
+            for (int e = tid; e < nloc * nb; e += REF_NT) {
+                const int i = e / nb, cc = e - i * nb;
+                double *x = pan + i * PS + cc;
+                const double f = fcol[i];
+                if (r0 + i == t) *x = srow[cc];
+                else if (cc == tt) *x = -f * srow[cc];
+                else *x -= f * srow[cc];
+            }
+            __syncthreads();
+        }
+        /* ---- panel back to memory; the round's row permutation as a gather ---- */
+        for (int e = tid; e < nloc * nb; e += REF_NT) {
+            const int i = e % nloc, cc = e / nloc;
+            A.X[(size_t)(c0 + cc) * ldt + r0 + i] = pan[i * PS + cc];
+        }
+        if (cta == 0 && tid < nb) A.piv[c0 + tid] = s_piv[tid];
+        if (A.single && cta == 0) {
+            /* the other CTAs did not follow the pivots: publish the gather list */
+            if (tid < 2 * REF_NB) { A.plan[2 + tid] = aff_row[tid]; A.plan[2 + 2 * REF_NB + tid] = aff_src[tid]; }
+            if (tid == 0) { A.plan[0] = s_naff; A.plan[1] = s_sing; }
+        }
+        ref_bar(X, A);
+        if (A.single) {
+            if (cta != 0) {
+                if (tid < 2 * REF_NB) { aff_row[tid] = __ldcg(A.plan + 2 + tid); aff_src[tid] = __ldcg(A.plan + 2 + 2 * REF_NB + tid); }
+                if (tid == 0) { s_naff = __ldcg(A.plan + 0); s_sing = __ldcg(A.plan + 1); }
+            }
+            __syncthreads();
+            if (s_sing) { if (cta == 0 && tid == 0) A.ctrl->sing = 1; return; }
+        }
+        /* ---- the other columns: row swaps, pivot rows, rank-nb update ---- */
+        const int naff = s_naff;
+        const int ncb = (k + REF_CB - 1) / REF_CB;
+        for (int cb = cta; cb < ncb; cb += G) {
+            const int cc0 = cb * REF_CB;
+            {
+                const int a = tid / REF_CB, c = tid % REF_CB;
+                const int col = cc0 + c;
+                const bool act = (a < naff) && (col < k) && !(col >= c0 && col < c0 + nb);
+                double val = 0.0;
+                if (act) val = A.X[(size_t)col * ldt + aff_src[a]];
+                __syncthreads();
+                if (act && aff_src[a] != aff_row[a]) A.X[(size_t)col * ldt + aff_row[a]] = val;
+                __syncthreads();
+            }
+            if (tid < REF_NB * REF_CB) {
+                const int t = tid / REF_CB, c = tid % REF_CB;
+                const int col = cc0 + c;
+                const bool act = (t < nb) && (col < k) && !(col >= c0 && col < c0 + nb);
+                xs[t][c] = act ? A.X[(size_t)col * ldt + c0 + t] : 0.0;
+            }
+            __syncthreads();
+            for (int i = tid; i < k; i += REF_NT) {
+                const bool in_p = (i >= c0 && i < c0 + nb);
+                double acc[REF_CB];
+#pragma unroll
+                for (int c = 0; c < REF_CB; c++) {
+                    const int col = cc0 + c;
+                    acc[c] = (col < k && !in_p) ? A.X[(size_t)col * ldt + i] : 0.0;
+                }
+                for (int t = 0; t < nb; t++) {
+                    const double pf = __ldcg(A.X + (size_t)(c0 + t) * ldt + i);
+#pragma unroll
+                    for (int c = 0; c < REF_CB; c++) acc[c] += pf * xs[t][c];
+                }
+#pragma unroll
+                for (int c = 0; c < REF_CB; c++) {
+                    const int col = cc0 + c;
+                    if (col < k && !(col >= c0 && col < c0 + nb)) A.X[(size_t)col * ldt + i] = acc[c];
+                }
+            }
+            __syncthreads();
+        }
+        ref_bar(X, A);
+    }
+    /* ---- undo the row pivoting (a column permutation) and negate, out of place ---- */
+    int *map = (int *)ref_dyn;
+    int *pv = map + k;
+    for (int j = tid; j < k; j += REF_NT) { map[j] = j; pv[j] = A.piv[j]; }
+    __syncthreads();
+    if (tid == 0)
+        for (int t = k - 1; t >= 0; t--) {
+            const int r = pv[t];
+            if (r != t) { const int x = map[t]; map[t] = map[r]; map[r] = x; }
+        }
+    __syncthreads();
+    for (int j = cta; j < k; j += G) {
+        const double *src = A.X + (size_t)map[j] * ldt;
+        double *dst = A.T2 + (size_t)j * ldt;
+        for (int b = tid; b < k; b += REF_NT) dst[b] = -src[b];
+    }
+}
+
+#endif /* GLPB_REFACTOR_CUH */

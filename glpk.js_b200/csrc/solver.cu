@@ -9,6 +9,7 @@
  */
 #include "kernels.cuh"
 #include "engine.cuh"
+#include "refactor.cuh"
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -34,6 +35,7 @@ static double now_ms()
 }
 
 #define PROF_MAX_RECS 400000
+#define REF_SMEM_MAX (200 * 1024)
 
 static inline void prof_begin(glpb_prob *P, const char *name)
 {
@@ -149,8 +151,8 @@ extern "C" void glpb_destroy(glpb_prob *P)
     void *ptrs[] = {P->a_ptr, P->a_ind, P->at_ptr, P->at_ind, P->a_val, P->at_val, P->type,
                     P->orig_type, P->stat, P->refsp, P->lb, P->ub, P->coef, P->orig_lb, P->orig_ub,
                     P->obj, P->head, P->bind, P->bbar, P->cbar, P->gamma, P->tcol, P->trow, P->rho,
-                    P->svec, P->w1, P->w2, P->w3, P->w4, P->w5, P->yk, P->wk, P->yk2, P->zn, P->bar,
-                    P->eng_cyc, P->eng_bytes, P->T, P->partial,
+                    P->svec, P->w1, P->w2, P->w3, P->w4, P->w5, P->yk, P->wk, P->yk2, P->zn, P->eng_slots, P->eng_cols,
+                    P->eng_cyc, P->eng_bytes, P->T, P->T2, P->ref_slots, P->ref_flags, P->partial,
                     P->rslot, P->slot_pos, P->cslot, P->slot_row, P->gj_piv, P->gj_row, P->gj_col, P->gj_xp,
                     P->scratch, P->ctrl};
     for (void *p : ptrs) if (p) cudaFree(p);
@@ -178,8 +180,10 @@ static int create_device(glpb_prob *P)
     DA(w1, m); DA(w2, m); DA(w3, m); DA(w4, m); DA(w5, m);
     P->ldt = (m + 7) & ~7;
     DA(yk, P->ldt); DA(wk, P->ldt); DA(yk2, P->ldt); DA(zn, P->ldt);
-    DA(bar, 1); DA(eng_cyc, 16); DA(eng_bytes, 16);
+    DA(eng_slots, ENG_RING * ENG_MAXG + 1); DA(eng_cols, 3 * (size_t)n + m); DA(eng_cyc, 24); DA(eng_bytes, 24);
     DA(T, (size_t)P->ldt * P->ldt);
+    DA(T2, (size_t)P->ldt * P->ldt);
+    DA(ref_slots, ENG_RING * ENG_MAXG); DA(ref_flags, ENG_RING * ENG_MAXG * 32);
     P->partial_rows = cdiv(P->ldt, GEMV_TILE);
     DA(partial, (size_t)P->partial_rows * P->ldt);
     DA(rslot, m); DA(slot_pos, P->ldt); DA(cslot, m); DA(slot_row, P->ldt);
@@ -190,8 +194,8 @@ static int create_device(glpb_prob *P)
 #undef DA
     CK(cudaMallocHost((void **)&P->h_ctrl, sizeof(Ctrl)));
     CK(cudaMemsetAsync(P->ctrl, 0, sizeof(Ctrl), P->stream));
-    CK(cudaMemsetAsync(P->eng_cyc, 0, 16 * sizeof(long long), P->stream));
-    CK(cudaMemsetAsync(P->eng_bytes, 0, 16 * sizeof(double), P->stream));
+    CK(cudaMemsetAsync(P->eng_cyc, 0, 24 * sizeof(long long), P->stream));
+    CK(cudaMemsetAsync(P->eng_bytes, 0, 24 * sizeof(double), P->stream));
     /* persistent engine: one CTA per SM, dynamic shared memory for staging */
     {
         int coop = 0, smem_max = 0;
@@ -205,6 +209,7 @@ static int create_device(glpb_prob *P)
         if (!coop || P->sm_count > ENG_MAXG) { glpb_set_error("device lacks cooperative launch"); return GLPB_ENODEV; }
         CK(cudaFuncSetAttribute(k_engine_primal, cudaFuncAttributeMaxDynamicSharedMemorySize, P->eng_smem));
         CK(cudaFuncSetAttribute(k_engine_dual, cudaFuncAttributeMaxDynamicSharedMemorySize, P->eng_smem));
+        CK(cudaFuncSetAttribute(k_refactor, cudaFuncAttributeMaxDynamicSharedMemorySize, REF_SMEM_MAX));
         int occ = 0;
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_engine_dual, ENG_NT, P->eng_smem));
         if (occ < 1) { glpb_set_error("engine does not fit an SM"); return GLPB_ENODEV; }
@@ -460,30 +465,40 @@ static int dev_refactor(Dev &D)
     const int k = D.k;
     P->n_refac++;
     if (k > 0) {
-        LAUNCH(P, k_build_kernel_matrix, k, 128, 0, P->ctrl, D.m, P->T, P->ldt, P->a_ptr, P->a_ind,
-               P->a_val, P->head, P->slot_pos, P->cslot);
-        if (k <= GJ_SMALL) {
-            size_t smem = (size_t)(GJ_SMALL * GJ_SMALL + 2 * GJ_SMALL) * sizeof(double);
-            LAUNCH(P, k_gj_small, 1, 256, smem, P->ctrl, P->T, P->ldt);
-        } else {
-            dim3 grid(cdiv(k, UPD_TB), cdiv(k, UPD_TC));
-            if (getenv("GLPB_UNBLOCKED_GJ")) {
-                for (int t = 0; t < k; t++) {
-                    LAUNCH(P, k_gj_pivot, 1, 1024, 0, P->ctrl, t, P->T, P->ldt, P->gj_piv, P->gj_row, P->gj_col);
-                    LAUNCH(P, k_gj_update, grid, UPD_TB, 0, P->ctrl, t, P->T, P->ldt, P->gj_row, P->gj_col);
-                }
-            } else {
-                /* blocked: GJ_NB pivots per round, one pass over T per round */
-                for (int c0 = 0; c0 < k; c0 += GJ_NB) {
-                    LAUNCH(P, k_bgj_panel, 1, 1024, 0, P->ctrl, c0, P->T, P->ldt, P->gj_piv, P->gj_row, P->gj_col);
-                    LAUNCH(P, k_bgj_swap, cdiv(k, 256), 256, 0, P->ctrl, c0, P->T, P->ldt, P->gj_piv, P->gj_xp);
-                    P->next_bytes = 16.0 * k * (double)k;
-                    LAUNCH(P, k_bgj_update, grid, UPD_TB, 0, P->ctrl, c0, P->T, P->ldt, P->gj_xp);
-                }
-            }
-            LAUNCH(P, k_gj_finish, 1, 1024, 0, P->ctrl, P->T, P->ldt, P->gj_piv);
-            LAUNCH(P, k_negate, dim3(cdiv(k, 256), k), 256, 0, P->ctrl, P->T, P->ldt);
+        /* one cooperative launch: rows of the panel are spread over G CTAs */
+        static const int envg = getenv("GLPB_REF_GRID") ? atoi(getenv("GLPB_REF_GRID")) : 0;
+        int G = std::min(P->sm_count, std::max(1, cdiv(k, 16)));
+        if (envg > 0) G = std::min(envg, P->sm_count);
+        /* panel: whole in CTA 0's shared memory while k * nbr doubles fit, else its rows
+           are spread over all CTAs (one grid-wide arg-reduction per pivot) */
+        static const int envs = getenv("GLPB_REF_SINGLE") ? atoi(getenv("GLPB_REF_SINGLE")) : -1;
+        int nbr = 0, single = 0;
+        for (int nb = REF_NB; nb >= 8 && !nbr; nb >>= 1)
+            if ((size_t)k * (nb + 2) * sizeof(double) <= REF_SMEM_MAX) { nbr = nb; single = 1; }
+        if (envs == 0 || !nbr) { nbr = REF_NB; single = 0; }
+        if (!single) G = std::max(G, cdiv(k, REF_RMAX));
+        const int R = single ? k : cdiv(k, G);
+        const size_t smem = std::max((size_t)R * (nbr + 2) * sizeof(double), (size_t)2 * k * sizeof(int));
+        if (G > P->sm_count || smem > REF_SMEM_MAX) {
+            glpb_set_error("refactorisation: kernel of size %d does not fit the device", k);
+            return GLPB_ENOMEM;
         }
+        CK(cudaMemsetAsync(P->ref_slots, 0, ENG_RING * ENG_MAXG * sizeof(RefSlot), P->stream));
+        CK(cudaMemsetAsync(P->ref_flags, 0, ENG_RING * ENG_MAXG * 32 * sizeof(unsigned int), P->stream));
+        RefArgs A;
+        A.ctrl = P->ctrl; A.m = D.m; A.ldt = P->ldt; A.X = P->T; A.T2 = P->T2;
+        A.a_ptr = P->a_ptr; A.a_ind = P->a_ind; A.a_val = P->a_val;
+        A.head = P->head; A.slot_pos = P->slot_pos; A.cslot = P->cslot;
+        A.piv = P->gj_piv; A.slots = P->ref_slots; A.flags = P->ref_flags;
+        A.nbr = nbr; A.single = single; A.plan = (int *)P->gj_row;   /* gj_row: ldt doubles, used as scratch ints */
+        void *args[] = {&A};
+        P->next_bytes = 16.0 * k * (double)k * cdiv(k, REF_NB);
+        prof_begin(P, "k_refactor");
+        cudaError_t e = cudaLaunchCooperativeKernel((const void *)k_refactor, dim3(G), dim3(REF_NT), args, smem, P->stream);
+        prof_end(P);
+        if (e != cudaSuccess) { glpb_set_error("refactor launch: %s", cudaGetErrorString(e)); return GLPB_ENODEV; }
+        P->n_launch++;
+        std::swap(P->T, P->T2);
         rc = sync_ctrl(P);
         if (rc) return rc;
         if (P->h_ctrl->sing) return GLP_ESING;
@@ -710,7 +725,8 @@ struct Loop : Dev {
         batch_begin(0, obj_ll, obj_ul);
         EngArgs A;
         A.ctrl = P->ctrl; A.m = m; A.n = n; A.ldt = P->ldt; A.max_iters = iters;
-        A.gc = gc; A.gr = gr; A.dcap = P->eng_dcap;
+        A.dcap = P->eng_dcap;
+        A.avg_col = (double)P->nnz / n; A.avg_row = (double)P->nnz / m;
         A.tol_bnd = parm.tol_bnd; A.tol_dj = parm.tol_dj; A.tol_piv = parm.tol_piv; A.rtol = rtol;
         A.a_ptr = P->a_ptr; A.a_ind = P->a_ind; A.a_val = P->a_val;
         A.at_ptr = P->at_ptr; A.at_ind = P->at_ind; A.at_val = P->at_val;
@@ -723,11 +739,14 @@ struct Loop : Dev {
         A.yk = P->yk; A.yk2 = P->yk2; A.wk = P->wk; A.zn = P->zn;
         A.T = P->T;
         A.rslot = P->rslot; A.slot_pos = P->slot_pos; A.cslot = P->cslot; A.slot_row = P->slot_row;
-        A.scratch = P->scratch; A.bar = P->bar;
-        A.prof_cyc = P->prof ? P->eng_cyc + (dual ? 8 : 0) : nullptr;
-        A.prof_bytes = P->prof ? P->eng_bytes + (dual ? 8 : 0) : nullptr;
+        A.ycol = P->eng_cols; A.ycol2 = P->eng_cols + n; A.trowcol = P->eng_cols + 2 * (size_t)n;
+        A.vrow = P->eng_cols + 3 * (size_t)n;
+        A.slots = P->eng_slots;
+        A.prof_cyc = P->prof ? P->eng_cyc + (dual ? 12 : 0) : nullptr;
+        A.prof_bytes = P->prof ? P->eng_bytes + (dual ? 12 : 0) : nullptr;
         const int G = engine_grid();
-        CK(cudaMemsetAsync(P->bar, 0, sizeof(unsigned int), P->stream));
+        CK(cudaMemsetAsync(P->eng_slots, 0, (ENG_RING * ENG_MAXG + 1) * sizeof(EngSlot), P->stream));
+        CK(cudaMemsetAsync(P->eng_cols, 0, (3 * (size_t)n + m) * sizeof(double), P->stream));
         void *args[] = {&A};
         prof_begin(P, dual ? "k_engine_dual" : "k_engine_primal");
         cudaError_t e = cudaLaunchCooperativeKernel(dual ? (const void *)k_engine_dual : (const void *)k_engine_primal,
@@ -1430,8 +1449,8 @@ extern "C" int glpb_set_profile(glpb_prob *P, int on)
     if (on) {
         P->prof_acc.clear();
         P->n_eng_prof_iter[0] = P->n_eng_prof_iter[1] = 0;
-        cudaMemsetAsync(P->eng_cyc, 0, 16 * sizeof(long long), P->stream);
-        cudaMemsetAsync(P->eng_bytes, 0, 16 * sizeof(double), P->stream);
+        cudaMemsetAsync(P->eng_cyc, 0, 24 * sizeof(long long), P->stream);
+        cudaMemsetAsync(P->eng_bytes, 0, 24 * sizeof(double), P->stream);
     }
     return 0;
 }
@@ -1448,24 +1467,26 @@ extern "C" const char *glpb_profile_report(glpb_prob *P)
     }
     /* phases of the persistent engine: SM cycles of CTA 0 between barriers,
        scaled to the CUDA-event time of the engine launches; count = iterations */
-    long long cyc[16];
-    double byt[16];
+    long long cyc[24];
+    double byt[24];
     if (cudaMemcpy(cyc, P->eng_cyc, sizeof cyc, cudaMemcpyDeviceToHost) == cudaSuccess &&
         cudaMemcpy(byt, P->eng_bytes, sizeof byt, cudaMemcpyDeviceToHost) == cudaSuccess) {
-        static const char *pn[16] = {"P1_chuzc", "P2_tcol_head", "P3_tcol_tail_prep", "P4_ratio1_btran_head",
-                                     "P5_ratio2_gemvT", "P6_rho_utail", "P7_trow_svec", "P8_update_T",
-                                     "D1_chuzr", "D2_rho", "D3_trow", "D4_ratio1_gamma_rhs", "D5_ratio2_gemvN",
-                                     "D6_tcol_head_utail", "D7_tcol_tail", "D8_update_T"};
+        static const char *pn[24] = {"P0_chuzc_first", "PA_tcol_head", "PB_tcol_tail_prep_ratio", "PR1_ratio1", "PR2_ratio2",
+                                     "PC_rho_btran_head", "PD_gemvT", "PE_trow_svec", "PF_update_T_chuzc", "P9", "P10", "P11",
+                                     "D0_chuzr_first", "D1_rho", "D2_trow", "DR1_ratio1_gamma_rhs", "DR2_ratio2",
+                                     "DX_ratio_local_gamma_rhs", "D3_gemvN_tcol_head", "D4_tcol_tail_utail",
+                                     "D5_update_T_chuzr", "D9", "D10", "D11"};
         for (int half = 0; half < 2; half++) {
             const char *kn = half ? "k_engine_dual" : "k_engine_primal";
             auto itp = P->prof_acc.find(kn);
             if (itp == P->prof_acc.end()) continue;
             long long tot = 0;
-            for (int i = 0; i < 8; i++) tot += cyc[half * 8 + i];
+            for (int i = 0; i < 12; i++) tot += cyc[half * 12 + i];
             if (tot <= 0) continue;
-            for (int i = 0; i < 8; i++) {
-                snprintf(line, sizeof line, "eng_%s %ld %.6f %.0f\n", pn[half * 8 + i], P->n_eng_prof_iter[half],
-                         itp->second.ms * (double)cyc[half * 8 + i] / (double)tot, byt[half * 8 + i]);
+            for (int i = 0; i < 12; i++) {
+                if (cyc[half * 12 + i] == 0) continue;
+                snprintf(line, sizeof line, "eng_%s %ld %.6f %.0f\n", pn[half * 12 + i], P->n_eng_prof_iter[half],
+                         itp->second.ms * (double)cyc[half * 12 + i] / (double)tot, byt[half * 12 + i]);
                 P->prof_text += line;
             }
         }
