@@ -229,7 +229,8 @@ def main():
     P.simplex(meth=meth, it_lim=int(iters[-1]) if args.profile_full else min(int(iters[-1]), 1500))
     prof = P.profile()
     P.set_profile(0)
-    units = {k: v for k, v in prof.items() if not k.startswith("k_engine_")}     # engine split into phases
+    ref_split = {k: v for k, v in prof.items() if k.startswith("ref_")}          # inside k_refactor: informational
+    units = {k: v for k, v in prof.items() if not k.startswith("k_engine_") and not k.startswith("ref_")}
     tot_prof_ms = sum(v["ms"] for v in units.values()) or 1.0
     with_bytes = {k: v for k, v in units.items() if v["bytes"] > 0 and v["count"] > 0}
     top = max(with_bytes, key=lambda k: with_bytes[k]["ms"]) if with_bytes else None
@@ -249,7 +250,8 @@ def main():
                                       sorted(units.items(), key=lambda kv: -kv[1]["ms"])[:10]},
                     "phase_table": {k: {"us": round(1000.0 * x["ms"] / max(1, x["count"]), 3),
                                         "GBps": round(x["bytes"] / max(1e-9, x["ms"]) / 1e6, 1)}
-                                    for k, x in sorted(units.items()) if k.startswith("eng_")}}
+                                    for k, x in sorted(units.items()) if k.startswith("eng_")},
+                    "refactor_split_ms": {k[4:]: round(x["ms"], 2) for k, x in ref_split.items()}}
     P.close()
 
     # ---- e2e leg: host buffers every step ----

@@ -34,6 +34,7 @@
 #define ENG_MAXG 160         /* scratch slot width (>= number of SMs)            */
 #define ENG_LCAP 2048        /* staged entries of one sparse column / row        */
 #define ENG_RING 4           /* rotating barrier slots                           */
+#define ENG_DB 32            /* deferred basis changes before T is rewritten     */
 
 /* one 128-byte line per (ring slot, CTA): the arrival flag and the partial
    result that travels with it.  A line of its own keeps the G pollers of a
@@ -65,6 +66,12 @@ struct EngArgs {
     double *vrow;             /* [m] primal: masked tcol by row of a basic auxiliary       */
     double *trowcol;          /* [n] dual: trow over the reference space by non-basic column */
     double *T;
+    /* deferred basis changes (dual engine, large problems): the kernel in use is
+       T + sum_{j<nd} Fd_j Rd_j', flushed into T every ENG_DB changes */
+    double *Fd, *Rd;          /* [ENG_DB][ldt] each                              */
+    double *zbuf;             /* [ENG_DB] Rd_j' v for the dense product          */
+    int defer;                /* 1: deferral allowed                             */
+    int local_max;            /* ratio tests up to this length are replicated per CTA */
     int *rslot, *slot_pos, *cslot, *slot_row;
     EngSlot *slots;           /* [ENG_RING][ENG_MAXG] arrival flags + CTA partials, zeroed by the host */
     long long *prof_cyc;      /* optional: SM cycles per phase, CTA 0 (NULL = off)  */
@@ -311,25 +318,27 @@ __device__ __forceinline__ int eng_compact(const EngCtx &X, bool flag, int &tota
     return pos;
 }
 
-/* y[b] (+)= sum_e T[b, idx[e]] * val[e], b < k, for the list (idx, val) of L
-   entries (idx == NULL: idx[e] = e, the dense case).  A CTA owns blocks of RB
-   consecutive rows; its 32 warps split the list, partial sums meet in shared
-   memory in a fixed order.  Streams 8 L k bytes of T. */
+/* y[b] (+)= sum_e T[b, idx[e]] * val[e] + sum_{j<nd} Fd_j[b] z[j], b < k, for the
+   list (idx, val) of L entries (idx == NULL: idx[e] = e, the dense case).
+   Every CTA owns one contiguous range of rows (a multiple of 4, i.e. whole 32-byte
+   sectors) and walks it in chunks of RB rows; its 32 warps split the list and
+   the partial sums meet in shared memory in a fixed order.  Streams 8 L k bytes. */
 __device__ void eng_gemv_rows(const EngCtx &X, const EngArgs &A, int k, int L, const int *idx,
-                              const double *val, double *y, double *ycol, bool accumulate)
+                              const double *val, double *y, double *ycol, bool accumulate,
+                              int nd, const double *z)
 {
     __shared__ double red[32][33];
-    int RB = 8;
-    if (k >= 32 * 2 * X.G) RB = 32; else if (k >= 16 * 2 * X.G) RB = 16;
+    const int RPC = (((k + X.G - 1) / X.G) + 3) & ~3;          /* rows per CTA */
+    const int q0 = min(k, X.cta * RPC), q1 = min(k, q0 + RPC);
+    const int RB = (RPC >= 24) ? 32 : (RPC >= 12 ? 16 : 8);
     const int NSUB = 32 / RB;
     const int r = X.lane & (RB - 1), sub = X.lane / RB;
-    const int nrb = (k + RB - 1) / RB;
     const int stride = NSUB * 32;
     const size_t ldt = (size_t)A.ldt;
-    for (int rb = X.cta; rb < nrb; rb += X.G) {
-        const int b = rb * RB + r;
-        const bool inb = b < k;
-        const double *Tb = A.T + (inb ? b : 0);
+    for (int b0 = q0; b0 < q1; b0 += RB) {
+        const int b = b0 + r;
+        const bool inb = b < q1;
+        const double *Tb = A.T + (inb ? b : q0);
         double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
         int e = sub + NSUB * X.warp;
         if (idx) {
@@ -362,8 +371,9 @@ __device__ void eng_gemv_rows(const EngCtx &X, const EngArgs &A, int k, int L, c
             double s = 0.0;
 #pragma unroll 8
             for (int w = 0; w < 32; w++) s += red[w][X.tid];
-            const int b2 = rb * RB + X.tid;
-            if (b2 < k) {
+            const int b2 = b0 + X.tid;
+            if (b2 < q1) {
+                for (int j = 0; j < nd; j++) s += A.Fd[(size_t)j * ldt + b2] * z[j];
                 if (accumulate) s += y[b2];
                 y[b2] = s;
                 ycol[A.head[A.slot_pos[b2]] - A.m] = s;      /* the same value by basic column */
@@ -377,10 +387,12 @@ __device__ void eng_gemv_rows(const EngCtx &X, const EngArgs &A, int k, int L, c
    lib/glpspx01.js:690-727): y = T h_N over the entries of column q that fall
    on rows of R_N.  CTA 0 also scatters h into the dense vector hz that the
    second half reads. */
-__device__ void eng_ftran_head_col(EngCtx &X, const EngArgs &A, int k, int kq, double *y, double *ycol)
+__device__ void eng_ftran_head_col(EngCtx &X, const EngArgs &A, int k, int kq, double *y, double *ycol, int nd)
 {
+    __shared__ double zs[ENG_DB];
     const int m = A.m;
-    const bool work = (X.cta * 8 < k);
+    const int RPC = (((k + X.G - 1) / X.G) + 3) & ~3;
+    const bool work = (X.cta * RPC < k);
     if (!work && X.cta != 0) return;
     if (kq < m) {
         if (X.tid == 0) {
@@ -388,7 +400,9 @@ __device__ void eng_ftran_head_col(EngCtx &X, const EngArgs &A, int k, int kq, d
             if (X.cta == 0) A.hz[kq] = -1.0;
         }
         __syncthreads();
-        eng_gemv_rows(X, A, k, 1, X.sh_i, X.sh_d, y, ycol, false);
+        if (X.tid < nd) zs[X.tid] = -A.Rd[(size_t)X.tid * A.ldt + X.sh_i[0]];
+        __syncthreads();
+        eng_gemv_rows(X, A, k, 1, X.sh_i, X.sh_d, y, ycol, false, nd, zs);
         return;
     }
     const int beg = __ldg(A.a_ptr + (kq - m)), end = __ldg(A.a_ptr + (kq - m) + 1);
@@ -411,7 +425,14 @@ __device__ void eng_ftran_head_col(EngCtx &X, const EngArgs &A, int k, int kq, d
             L += tot;
         }
         __syncthreads();
-        eng_gemv_rows(X, A, k, L, X.sh_i, X.sh_d, y, ycol, !first);
+        if (X.tid < nd) {
+            const double *Rj = A.Rd + (size_t)X.tid * A.ldt;
+            double zz = 0.0;
+            for (int e = 0; e < L; e++) zz += X.sh_d[e] * Rj[X.sh_i[e]];
+            zs[X.tid] = zz;
+        }
+        __syncthreads();
+        eng_gemv_rows(X, A, k, L, X.sh_i, X.sh_d, y, ycol, !first, nd, zs);
         first = false;
     }
 }
@@ -483,16 +504,26 @@ __device__ __forceinline__ void eng_gemvT(const EngCtx &X, const EngArgs &A, int
         [&](int cs, const double *a) { zn[cs] = a[0]; });
 }
 
-/* rho = row p of inv(B) (eval_rho, lib/glpspx01.js:1030-1042), read out of T */
-__device__ void eng_rho(EngCtx &X, const EngArgs &A, int k, int p)
+/* rho = row p of inv(B) (eval_rho, lib/glpspx01.js:1030-1042), read out of T
+   (plus the nd deferred rank-1 terms) */
+__device__ void eng_rho(EngCtx &X, const EngArgs &A, int k, int p, int nd)
 {
+    __shared__ double fs[ENG_DB];
     const int m = A.m;
+    const size_t ldt = (size_t)A.ldt;
     const int kp = A.head[p];
     for (int r = X.gtid; r < m; r += X.gsize)
         if (A.cslot[r] < 0) A.rho[r] = (A.bind[r] == p) ? 1.0 : 0.0;
     if (kp >= m) {
-        const double *row = A.T + A.rslot[p];
-        for (int cs = X.gtid; cs < k; cs += X.gsize) A.rho[A.slot_row[cs]] = __ldcg(row + (size_t)cs * A.ldt);
+        const int bp = A.rslot[p];
+        if (X.tid < nd) fs[X.tid] = A.Fd[(size_t)X.tid * ldt + bp];
+        if (nd > 0) __syncthreads();
+        const double *row = A.T + bp;
+        for (int cs = X.gtid; cs < k; cs += X.gsize) {
+            double a = __ldcg(row + (size_t)cs * ldt);
+            for (int j = 0; j < nd; j++) a += fs[j] * A.Rd[(size_t)j * ldt + cs];
+            A.rho[A.slot_row[cs]] = a;
+        }
         return;
     }
     /* an auxiliary variable leaves: rho_N = w' T with w the basic part of row kp of A */
@@ -513,11 +544,18 @@ __device__ void eng_rho(EngCtx &X, const EngArgs &A, int k, int p)
             L += tot;
         }
         __syncthreads();
+        if (X.tid < nd) {
+            const double *Fj = A.Fd + (size_t)X.tid * ldt;
+            double ww = 0.0;
+            for (int e = 0; e < L; e++) ww += X.sh_d[e] * Fj[X.sh_i[e]];
+            fs[X.tid] = ww;
+        }
+        if (nd > 0) __syncthreads();
         const int LP = eng_pick_lp(X, k, (double)L);
         const bool acc = !first;
         eng_items<1>(X, k, LP,
             [&](int cs, int l, int lp, double *a) {
-                const double *col = A.T + (size_t)cs * A.ldt;
+                const double *col = A.T + (size_t)cs * ldt;
                 double a0 = 0.0, a1 = 0.0;
                 int e = l;
                 for (; e + lp < L; e += 2 * lp) {
@@ -529,7 +567,9 @@ __device__ void eng_rho(EngCtx &X, const EngArgs &A, int k, int p)
             },
             [&](int cs, const double *a) {
                 const int r = A.slot_row[cs];
-                A.rho[r] = acc ? A.rho[r] + a[0] : a[0];
+                double v = a[0];
+                for (int j = 0; j < nd; j++) v += fs[j] * A.Rd[(size_t)j * ldt + cs];
+                A.rho[r] = acc ? A.rho[r] + v : v;
             });
         first = false;
         __syncthreads();
@@ -685,6 +725,109 @@ __device__ void eng_update_T(const EngCtx &X, const EngArgs &A, const EngChange 
     }
 }
 
+/* The basis change in deferred form: instead of rewriting T (16 k^2 bytes) the
+   rank-1 term (g, rho_N) is appended to (Fd, Rd); only the O(k) structural part
+   touches T: a replaced row or column is written directly (and its entries in
+   the earlier terms are zeroed), a leaving row/column is filled from the last
+   one, in T and in every stored term alike. */
+__device__ void eng_defer_apply(const EngCtx &X, const EngArgs &A, const EngChange &C, int nd)
+{
+    const int k = C.k;
+    const size_t ldt = (size_t)A.ldt;
+    const double tp = C.tp;
+    const bool removal = (!C.LS && C.ES);
+    double *Fn = A.Fd + (size_t)nd * ldt, *Rn = A.Rd + (size_t)nd * ldt;
+    /* entries that the structural part below rewrites are left to it (one writer per cell) */
+    const int skipF = removal ? C.bp : -1;
+    const int skipR = (removal || (C.LS && C.ES)) ? C.csq : -1;
+    for (int t = X.gtid; t < k; t += X.gsize) {
+        const int i = A.slot_pos[t];
+        if (t != skipF) Fn[t] = (i == C.p) ? 0.0 : -A.tcol[i] / tp;    /* row of p: replaced below */
+        if (t != skipR) Rn[t] = A.rho[A.slot_row[t]];
+    }
+    if (C.LS && C.ES) {
+        /* column csq is replaced: T[:, csq] = -tcol_S / tp */
+        for (int t = X.gtid; t < k; t += X.gsize) A.T[(size_t)C.csq * ldt + t] = -A.tcol[A.slot_pos[t]] / tp;
+        for (int j = X.gtid; j <= nd; j += X.gsize) A.Rd[(size_t)j * ldt + C.csq] = 0.0;
+    } else if (C.LS && !C.ES) {
+        /* a row and a column join at slot k */
+        for (int t = X.gtid; t < 2 * k + 1; t += X.gsize) {
+            if (t < k) A.T[(size_t)k * ldt + t] = -A.tcol[A.slot_pos[t]] / tp;
+            else if (t < 2 * k) A.T[(size_t)(t - k) * ldt + k] = -A.rho[A.slot_row[t - k]] / tp;
+            else A.T[(size_t)k * ldt + k] = -1.0 / tp;
+        }
+        for (int j = X.gtid; j <= nd; j += X.gsize) { A.Fd[(size_t)j * ldt + k] = 0.0; A.Rd[(size_t)j * ldt + k] = 0.0; }
+    } else if (removal) {
+        /* row bp and column csq leave: the last row/column moves into the hole */
+        for (int t = X.gtid; t < 2 * k; t += X.gsize) {
+            if (t < k) {            /* destination (bp, c = t), c < k - 1 */
+                const int c = t;
+                if (C.bp != k - 1 && c < k - 1) {
+                    const int sc = (c == C.csq) ? k - 1 : c;
+                    A.T[(size_t)c * ldt + C.bp] = __ldcg(A.T + (size_t)sc * ldt + (k - 1));
+                }
+            } else {                /* destination (s = t - k, csq), s < k - 1, s != bp */
+                const int sr = t - k;
+                if (C.csq != k - 1 && sr < k - 1 && sr != C.bp)
+                    A.T[(size_t)C.csq * ldt + sr] = __ldcg(A.T + (size_t)(k - 1) * ldt + sr);
+            }
+        }
+        for (int j = X.gtid; j <= nd; j += X.gsize) {
+            if (C.bp != k - 1) A.Fd[(size_t)j * ldt + C.bp] = (j == nd) ? -A.tcol[A.slot_pos[k - 1]] / tp
+                                                                       : A.Fd[(size_t)j * ldt + (k - 1)];
+            if (C.csq != k - 1) A.Rd[(size_t)j * ldt + C.csq] = (j == nd) ? A.rho[A.slot_row[k - 1]]
+                                                                         : A.Rd[(size_t)j * ldt + (k - 1)];
+        }
+    } else {
+        /* a structural variable replaces a structural one: row bp = -rho_N / tp */
+        for (int c = X.gtid; c < k; c += X.gsize) A.T[(size_t)c * ldt + C.bp] = -A.rho[A.slot_row[c]] / tp;
+        for (int j = X.gtid; j < nd; j += X.gsize) A.Fd[(size_t)j * ldt + C.bp] = 0.0;
+    }
+}
+
+/* T += sum_{j<nd} Fd_j Rd_j' over the k x k kernel: one read+write of T for up
+   to ENG_DB basis changes.  Tiles of 128 rows x 64 columns, the terms staged in
+   shared memory (needs 6144 doubles of dynamic shared memory). */
+__device__ void eng_flush(const EngCtx &X, const EngArgs &A, int k, int nd)
+{
+    if (nd <= 0 || k <= 0) return;
+    const size_t ldt = (size_t)A.ldt;
+    double *Fs = X.sh_d;                 /* [ENG_DB][128] */
+    double *Rs = X.sh_d + ENG_DB * 128;  /* [ENG_DB][64]  */
+    const int r = X.tid & 127, cg = X.tid >> 7;
+    const int nrt = (k + 127) >> 7, nct = (k + 63) >> 6;
+    for (int u = X.cta; u < nrt * nct; u += X.G) {
+        const int i0 = (u / nct) << 7, c0 = (u % nct) << 6;
+        __syncthreads();
+        for (int e = X.tid; e < ENG_DB * 128; e += ENG_NT) {
+            const int j = e >> 7, i = i0 + (e & 127);
+            Fs[e] = (j < nd && i < k) ? A.Fd[(size_t)j * ldt + i] : 0.0;
+        }
+        for (int e = X.tid; e < ENG_DB * 64; e += ENG_NT) {
+            const int j = e >> 6, c = c0 + (e & 63);
+            Rs[e] = (j < nd && c < k) ? A.Rd[(size_t)j * ldt + c] : 0.0;
+        }
+        __syncthreads();
+        const int i = i0 + r;
+        if (i < k) {
+            double acc[8];
+            double *tp = A.T + (size_t)(c0 + cg * 8) * ldt + i;
+#pragma unroll
+            for (int x = 0; x < 8; x++) acc[x] = (c0 + cg * 8 + x < k) ? __ldcg(tp + (size_t)x * ldt) : 0.0;
+            for (int j = 0; j < nd; j++) {
+                const double f = Fs[j * 128 + r];
+                const double *rr = Rs + j * 64 + cg * 8;
+#pragma unroll
+                for (int x = 0; x < 8; x++) acc[x] += f * rr[x];
+            }
+#pragma unroll
+            for (int x = 0; x < 8; x++)
+                if (c0 + cg * 8 + x < k) tp[(size_t)x * ldt] = acc[x];
+        }
+    }
+    __syncthreads();
+}
+
 /* slot maps, basis header and the new non-basic status (change_basis,
    lib/glpspx01.js:1310-1371 / lib/glpspx02.js:1259-1294); one thread */
 __device__ void eng_bookkeep(const EngArgs &A, const EngChange &C, int new_stat, bool drop_refsp)
@@ -742,7 +885,7 @@ __device__ Key eng_blockall(const EngCtx &X, Key v, const Key &none, Comb comb)
 
 enum { /* phase slots of the cycle accounting (12 per engine) */
     PP_PRICE0 = 0, PP_A, PP_B, PP_R1, PP_R2, PP_C, PP_D, PP_E, PP_F,
-    PD_PRICE0 = 0, PD_RHO, PD_TROW, PD_R1, PD_R2, PD_X1, PD_TCOL1, PD_TCOL2, PD_UPD
+    PD_PRICE0 = 0, PD_RHO, PD_TROW, PD_R1, PD_R2, PD_X1, PD_TCOL1, PD_TCOL2, PD_UPD, PD_FLUSH
 };
 
 /* ------------------------------------------------------------------ */
@@ -756,7 +899,7 @@ __global__ void __launch_bounds__(ENG_NT, 1) k_engine_primal(EngArgs A)
     EngCtx X;
     eng_init(X, A, eng_dyn);
     const int m = A.m, n = A.n;
-    const bool local_ratio = (m <= ENG_LOCAL_MAX);
+    const bool local_ratio = (m <= A.local_max);
     const double nnzA = (double)__ldg(A.a_ptr + n);
     if (X.tid == 0) S = *A.ctrl;
     __syncthreads();
@@ -783,7 +926,7 @@ __global__ void __launch_bounds__(ENG_NT, 1) k_engine_primal(EngArgs A)
         const int kq = A.head[m + q];
         const double nnz_q = (kq < m) ? 1.0 : (double)(__ldg(A.a_ptr + (kq - m) + 1) - __ldg(A.a_ptr + (kq - m)));
         /* ---- A: tcol, first half ---- */
-        eng_ftran_head_col(X, A, S.k, kq, A.yk, A.ycol);
+        eng_ftran_head_col(X, A, S.k, kq, A.yk, A.ycol, 0);
         eng_bar(X, A);
         eng_mark(X, A, PP_A, 12.0 * nnz_q + 8.0 * S.k * nnz_q * ((double)S.k / m) + 8.0 * S.k);
         /* ---- B: tcol, second half + the reductions of k_primal_prep ---- */
@@ -872,7 +1015,7 @@ __global__ void __launch_bounds__(ENG_NT, 1) k_engine_primal(EngArgs A)
         const int p = S.p;
         if (p >= 0) {
             /* ---- C: rho (+ first half of u = inv(B') v) ---- */
-            eng_rho(X, A, S.k, p);
+            eng_rho(X, A, S.k, p, 0);
             if (pse) eng_btran_head(X, A, S.k);
             eng_bar(X, A);
             if (cbar_q_pending && X.cta == 0 && X.tid == 0) A.cbar[q] = S.d1;   /* all CTAs are past the d1/d2 test */
@@ -1024,12 +1167,14 @@ __global__ void __launch_bounds__(ENG_NT, 1) k_engine_dual(EngArgs A)
     EngCtx X;
     eng_init(X, A, eng_dyn);
     const int m = A.m, n = A.n;
-    const bool local_ratio = (n <= ENG_LOCAL_MAX);
+    const bool local_ratio = (n <= A.local_max);
+    const bool defer = A.defer && !local_ratio;     /* deferred basis changes need the grid-wide ratio phases */
     const double nnzA = (double)__ldg(A.a_ptr + n);
     if (X.tid == 0) S = *A.ctrl;
     __syncthreads();
     int pnext = P_NONE;
     double dnext = 0.0;
+    int nd = 0;                   /* deferred rank-1 terms on top of T */
     for (int it = 0; it < A.max_iters && S.status == ST_OK; it++) {
         /* ---- pricing (chuzr): see the primal engine ---- */
         if (it == 0) {
@@ -1054,15 +1199,22 @@ __global__ void __launch_bounds__(ENG_NT, 1) k_engine_dual(EngArgs A)
         const bool pse = gamma_on(&S);
         const double sgn = (S.delta > 0.0 ? +1.0 : -1.0);
         /* ---- rho ---- */
-        eng_rho(X, A, S.k, p);
+        eng_rho(X, A, S.k, p, nd);
         eng_bar(X, A);
-        eng_mark(X, A, PD_RHO, 12.0 * m + 8.0 * S.k);
+        eng_mark(X, A, PD_RHO, 12.0 * m + 8.0 * S.k + 8.0 * nd * S.k);
         /* ---- pivot row, |trow|_inf, sum of squares over the reference space ---- */
         {
             Key none = {0.0, 0.0, 0.0, 0, 0};
             Key acc = none;
             eng_trow<true>(X, A, S, acc);
+            const bool flush_now = (nd == ENG_DB);
+            if (flush_now) {
+                /* nothing else touches T in this phase: fold the deferred terms into it */
+                eng_flush(X, A, S.k, nd);
+                nd = 0;
+            }
             Key r = eng_allreduce(X, A, acc, none, CombSum2());
+            if (flush_now) eng_mark(X, A, PD_FLUSH, 16.0 * S.k * (double)S.k);
             if (X.tid == 0) {
                 S.trow_max = r.c;
                 S.eps = A.tol_bnd * (1.0 + 0.01 * r.c);      /* sic: tol_bnd, lib/glpspx02.js:1851 */
@@ -1102,31 +1254,49 @@ __global__ void __launch_bounds__(ENG_NT, 1) k_engine_dual(EngArgs A)
             __syncthreads();
             eng_mark(X, A, PD_R1, 17.0 * n + (pse ? 17.0 * nnzA + 16.0 * m : 0.0));
             if (S.status != ST_OK) break;
+            const bool need_z = pse && nd > 0 && S.k > 0;
+            if (need_z) {
+                /* z_j = Rd_j' v for the dense product below: one CTA per term */
+                for (int j = X.cta; j < nd; j += X.G) {
+                    const double *Rj = A.Rd + (size_t)j * A.ldt;
+                    const Key z0 = {0.0, 0.0, 0.0, 0, 0};
+                    Key zk = z0;
+                    for (int c = X.tid; c < S.k; c += ENG_NT) zk.a += Rj[c] * A.wk[c];
+                    zk = block_reduce(zk, z0, CombSum2());
+                    if (X.tid == 0) A.zbuf[j] = zk.a;
+                    __syncthreads();
+                }
+            }
             if (!S.skip2) {
                 v = none;
                 scan_ratio_dual(v, X.gtid, X.gsize, 2, sgn, S.eps, S.tmax, A.rtol, A.stat, A.cbar, A.trow, nullptr, n);
                 r = eng_allreduce(X, A, v, none, CombRatio2());
                 if (X.tid == 0) fin_ratio_dual(&S, r, 2, sgn, A.rtol, A.trow, nullptr);
                 __syncthreads();
-                eng_mark(X, A, PD_R2, 17.0 * n);
+                eng_mark(X, A, PD_R2, 17.0 * n + (need_z ? 16.0 * nd * S.k : 0.0));
                 if (S.status != ST_OK) break;
+            } else if (need_z) {
+                eng_bar(X, A);
+                eng_mark(X, A, PD_R2, 16.0 * nd * S.k);
             }
         }
         const int q = S.q;
         const int kq = A.head[m + q];
         /* ---- tcol, first half, and the dense product y2 = T v_N of update_gamma ---- */
         if (pse && S.k > 0) {
+            __shared__ double zd[ENG_DB];
             const int k = S.k;
             const double *val = A.wk;
-            if (k <= A.dcap && X.cta * 8 < k) {
+            if (X.tid < nd) zd[X.tid] = __ldcg(A.zbuf + X.tid);
+            if (k <= A.dcap) {
                 for (int e = X.tid; e < k; e += ENG_NT) X.sh_d[e] = A.wk[e];
-                __syncthreads();
                 val = X.sh_d;
             }
-            eng_gemv_rows(X, A, k, k, nullptr, val, A.yk2, A.ycol2, false);
+            __syncthreads();
+            eng_gemv_rows(X, A, k, k, nullptr, val, A.yk2, A.ycol2, false, nd, zd);
             __syncthreads();
         }
-        eng_ftran_head_col(X, A, S.k, kq, A.yk, A.ycol);
+        eng_ftran_head_col(X, A, S.k, kq, A.yk, A.ycol, nd);
         eng_bar(X, A);
         eng_mark(X, A, PD_TCOL1, (pse ? 8.0 * S.k * (double)S.k + 16.0 * S.k : 0.0) + 8.0 * S.k);
         /* ---- tcol, second half, and the tail of u = inv(B) v ---- */
@@ -1221,14 +1391,15 @@ __global__ void __launch_bounds__(ENG_NT, 1) k_engine_dual(EngArgs A)
                     for (int ptr = __ldg(A.a_ptr + (kq - m)) + X.tid; ptr < __ldg(A.a_ptr + (kq - m) + 1); ptr += ENG_NT)
                         A.hz[__ldg(A.a_ind + ptr)] = 0.0;
             }
-            if (S.k + (C.bnew >= 0) > 0) eng_update_T(X, A, C);
+            if (defer) { eng_defer_apply(X, A, C, nd); nd++; }
+            else if (S.k + (C.bnew >= 0) > 0) eng_update_T(X, A, C);
             Key r = eng_allreduce(X, A, pv, pnone, CombArgMax());
             {
                 const bool found = (r.a > 0.0 && r.pos != INT_MAX);
                 pnext = found ? r.pos : P_NONE;
                 dnext = found ? r.b : 0.0;
             }
-            eng_mark(X, A, PD_UPD, 24.0 * n + 40.0 * m + 37.0 * m + 16.0 * S.k * (double)S.k);
+            eng_mark(X, A, PD_UPD, 24.0 * n + 40.0 * m + 37.0 * m + (defer ? 40.0 * S.k : 16.0 * S.k * (double)S.k));
             const int new_stat = (A.type[kp] == GLP_FX) ? GLP_NS : (S.delta > 0.0 ? GLP_NL : GLP_NU);
             if (X.cta == 0 && X.tid == 0) eng_bookkeep(A, C, new_stat, pse && drop);
             if (X.tid == 0) {
@@ -1238,6 +1409,9 @@ __global__ void __launch_bounds__(ENG_NT, 1) k_engine_dual(EngArgs A)
             eng_header_done(X, A);
         }
     }
+    /* the host-side kernels read T itself: fold what is still deferred.  Every exit
+       from the loop follows a grid-wide barrier after the last access to T. */
+    if (nd > 0) eng_flush(X, A, S.k, nd);
     if (X.cta == 0 && X.tid == 0) *A.ctrl = S;
 }
 

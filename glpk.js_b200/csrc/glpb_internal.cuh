@@ -141,6 +141,7 @@ struct glpb_prob {
     double *yk2 = nullptr, *zn = nullptr;  /* [ldt] engine work in kernel space */
     struct EngSlot *eng_slots = nullptr;   /* engine: barrier flags + partials [ENG_RING][ENG_MAXG] */
     double *eng_cols = nullptr;            /* engine: ycol, ycol2, trowcol [3n] and vrow [m] */
+    double *eng_fr = nullptr;              /* engine: deferred terms Fd, Rd [2][ENG_DB][ldt] and zbuf [ENG_DB] */
     long long *eng_cyc = nullptr;          /* engine: SM cycles per phase [16] */
     double *eng_bytes = nullptr;           /* engine: algorithmic bytes per phase [16] */
     int sm_count = 0, eng_dcap = 0, eng_smem = 0, eng_ready = 0;

@@ -44,6 +44,7 @@ struct RefArgs {
     int single;              /* 1: the whole panel lives in CTA 0's shared memory (k nbr 8 bytes fit);
                                 0: its rows are spread over all CTAs          */
     int *plan;               /* [2 + 4 REF_NB] single mode: naff, sing, aff_row, aff_src published by CTA 0 */
+    long long *prof_cyc;     /* optional [8]: SM cycles of CTA 0 per phase (build, panel, panel i/o, wait, swap+update, finish) */
     double *X;               /* working matrix (in: nothing, built here)      */
     double *T2;              /* out: T = -inv(M), column-major, ld = ldt      */
     const int *a_ptr, *a_ind; const double *a_val;
@@ -84,6 +85,15 @@ __global__ void __launch_bounds__(REF_NT, 1) k_refactor(RefArgs A)
     __shared__ Key wres[ENG_MAXG / 32];
     __shared__ double s_max[32];
 
+    long long t_last = clock64();
+#define REF_MARK(ph)                                                           \
+    do {                                                                       \
+        if (A.prof_cyc != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {    \
+            const long long t_now = clock64();                                 \
+            A.prof_cyc[ph] += t_now - t_last;                                  \
+            t_last = t_now;                                                    \
+        }                                                                      \
+    } while (0)
     RefCtx X;
     X.G = gridDim.x; X.cta = blockIdx.x; X.tid = threadIdx.x; X.lane = X.tid & 31; X.warp = X.tid >> 5;
     X.seq = 0u;
@@ -117,6 +127,7 @@ __global__ void __launch_bounds__(REF_NT, 1) k_refactor(RefArgs A)
         }
     }
     ref_bar(X, A);
+    REF_MARK(0);
     const double max_a = __ldcg(&A.ctrl->max_a);
     const double tiny = 1e-13 * fmax(max_a, 1e-300);
 
@@ -137,9 +148,126 @@ __global__ void __launch_bounds__(REF_NT, 1) k_refactor(RefArgs A)
             pan[i * PS + cc] = A.X[(size_t)(c0 + cc) * ldt + r0 + i];
         }
         if (tid < nb) { aff_row[tid] = c0 + tid; aff_src[tid] = c0 + tid; }
-        if (tid == 0) s_naff = nb;
+        if (tid == 0) { s_naff = nb; s_sing = 0; }
         __syncthreads();
-        for (int tt = 0; tt < nb && cta < PG; tt++) {
+        REF_MARK(2);
+        if (A.single && cta == 0) {
+            /* ---- whole panel in this CTA's shared memory, warp-synchronous:
+               every warp owns a contiguous block of rows (lane = panel column), so a
+               pivot needs two block-wide barriers: candidates -> pivot row -> eliminate.
+               Rows do not move inside the panel; the swaps are recorded (piv, gather
+               list) and applied when the panel is written back. ---- */
+            unsigned char *mark = (unsigned char *)(pan + (size_t)R * PS);
+            int *rowdest = (int *)(mark + ((k + 15) & ~15));
+            for (int i = tid; i < k; i += REF_NT) { mark[i] = 0; rowdest[i] = i; }
+            __syncthreads();
+            const int RW = (k + 31) / 32;
+            const int w0 = min(k, X.warp * RW), w1 = min(k, w0 + RW);
+            const int RS = 32 / NBR, sub = X.lane / NBR, cc = X.lane % NBR;
+            /* candidates of the first pivot column; later ones are tracked while eliminating */
+            double bv = -1.0;
+            int bi = INT_MAX;
+            for (int i = w0 + X.lane; i < w1; i += 32)
+                if (i >= c0) {
+                    const double a = fabs(pan[i * PS]);
+                    if (a > bv) { bv = a; bi = i; }
+                }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                const double ov = __shfl_xor_sync(FULLMASK, bv, off);
+                const int oi = __shfl_xor_sync(FULLMASK, bi, off);
+                if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+            }
+            int *s_wi = (int *)&xs[1][0];
+            for (int tt = 0; tt < nb; tt++) {
+                if (X.lane == 0) { s_max[X.warp] = bv; s_wi[X.warp] = bi; }
+                __syncthreads();
+                bv = s_max[X.lane]; bi = s_wi[X.lane];
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) {
+                    const double ov = __shfl_xor_sync(FULLMASK, bv, off);
+                    const int oi = __shfl_xor_sync(FULLMASK, bi, off);
+                    if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+                }
+                REF_MARK(6);
+                if (!(bv > tiny)) { if (tid == 0) s_sing = 1; break; }
+                const int r = bi;
+                const double rr = (X.lane < nb) ? pan[r * PS + X.lane] : 0.0;
+                const double ipv = 1.0 / __shfl_sync(FULLMASK, rr, tt);
+                const double sr = (X.lane == tt) ? ipv : rr * ipv;
+                if (X.warp == 0) {
+                    /* position currently holding physical row r, and the transposition (c0+tt <-> it) */
+                    const int na = s_naff;
+                    const bool h0 = (X.lane < na) && (aff_src[X.lane] == r);
+                    const bool h1 = (32 + X.lane < na) && (aff_src[32 + X.lane] == r);
+                    const unsigned int b0 = __ballot_sync(FULLMASK, h0), b1 = __ballot_sync(FULLMASK, h1);
+                    int ib;
+                    if (b0) ib = __ffs(b0) - 1;
+                    else if (b1) ib = 32 + __ffs(b1) - 1;
+                    else {
+                        ib = na;
+                        if (X.lane == 0) { aff_row[na] = r; aff_src[na] = r; s_naff = na + 1; }
+                    }
+                    __syncwarp();
+                    if (X.lane == 0) {
+                        s_piv[tt] = aff_row[ib];
+                        const int tmp = aff_src[tt]; aff_src[tt] = aff_src[ib]; aff_src[ib] = tmp;
+                        mark[r] = 1;
+                    }
+                }
+                __syncthreads();
+                REF_MARK(7);
+                /* eliminate this warp's rows, four at a time; the lane of column tt+1
+                   keeps the best unpivoted entry of the next pivot column */
+                const double scc = __shfl_sync(FULLMASK, sr, cc);
+                const bool track = (cc == tt + 1) && (tt + 1 < nb);
+                bv = -1.0; bi = INT_MAX;
+                for (int i0 = w0; i0 < w1; i0 += 4 * RS) {          /* uniform trip count per warp */
+                    double f[4], old[4];
+                    bool act[4];
+#pragma unroll
+                    for (int x = 0; x < 4; x++) {
+                        const int i = i0 + x * RS + sub;
+                        act[x] = (i < w1) && (cc < nb);
+                        const double *px = pan + (act[x] ? i : w0) * PS;
+                        f[x] = px[tt]; old[x] = px[act[x] ? cc : 0];
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int x = 0; x < 4; x++) {
+                        const int i = i0 + x * RS + sub;
+                        if (act[x]) {
+                            const double nv = (i == r) ? scc : ((cc == tt) ? -f[x] * scc : old[x] - f[x] * scc);
+                            pan[i * PS + cc] = nv;
+                            if (track && i >= c0 && !mark[i]) {
+                                const double a = fabs(nv);
+                                if (a > bv) { bv = a; bi = i; }
+                            }
+                        }
+                    }
+                }
+                for (int off = NBR; off < 32; off <<= 1) {
+                    const double ov = __shfl_xor_sync(FULLMASK, bv, off);
+                    const int oi = __shfl_xor_sync(FULLMASK, bi, off);
+                    if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+                }
+                /* lane (tt+1) of sub-row 0 holds the warp's candidate: hand it to lane 0 */
+                bv = __shfl_sync(FULLMASK, bv, (tt + 1) & 31);
+                bi = __shfl_sync(FULLMASK, bi, (tt + 1) & 31);
+                __syncwarp();
+                REF_MARK(1);
+            }
+            __syncthreads();
+            REF_MARK(1);
+            /* write back; position aff_row[a] receives physical row aff_src[a] */
+            if (tid < s_naff) rowdest[aff_src[tid]] = aff_row[tid];
+            __syncthreads();
+            for (int e = tid; e < k * nb; e += REF_NT) {
+                const int i = e % k, c = e / k;
+                A.X[(size_t)(c0 + c) * ldt + rowdest[i]] = pan[i * PS + c];
+            }
+        }
+        for (int tt = 0; tt < nb && cta < PG && !A.single; tt++) {
             const int t = c0 + tt;
             /* best local candidate among rows >= t */
             Key none = {-1.0, 0.0, 0.0, INT_MAX, 0};
@@ -242,8 +370,9 @@ __global__ void __launch_bounds__(REF_NT, 1) k_refactor(RefArgs A)
             }
             __syncthreads();
         }
+        if (!A.single) REF_MARK(1);
         /* ---- panel back to memory; the round's row permutation as a gather ---- */
-        for (int e = tid; e < nloc * nb; e += REF_NT) {
+        for (int e = tid; e < nloc * nb && !A.single; e += REF_NT) {
             const int i = e % nloc, cc = e / nloc;
             A.X[(size_t)(c0 + cc) * ldt + r0 + i] = pan[i * PS + cc];
         }
@@ -253,7 +382,9 @@ __global__ void __launch_bounds__(REF_NT, 1) k_refactor(RefArgs A)
             if (tid < 2 * REF_NB) { A.plan[2 + tid] = aff_row[tid]; A.plan[2 + 2 * REF_NB + tid] = aff_src[tid]; }
             if (tid == 0) { A.plan[0] = s_naff; A.plan[1] = s_sing; }
         }
+        REF_MARK(2);
         ref_bar(X, A);
+        REF_MARK(3);
         if (A.single) {
             if (cta != 0) {
                 if (tid < 2 * REF_NB) { aff_row[tid] = __ldcg(A.plan + 2 + tid); aff_src[tid] = __ldcg(A.plan + 2 + 2 * REF_NB + tid); }
@@ -292,10 +423,16 @@ __global__ void __launch_bounds__(REF_NT, 1) k_refactor(RefArgs A)
                     const int col = cc0 + c;
                     acc[c] = (col < k && !in_p) ? A.X[(size_t)col * ldt + i] : 0.0;
                 }
-                for (int t = 0; t < nb; t++) {
-                    const double pf = __ldcg(A.X + (size_t)(c0 + t) * ldt + i);
+                for (int t0 = 0; t0 < nb; t0 += 8) {
+                    double pf[8];
 #pragma unroll
-                    for (int c = 0; c < REF_CB; c++) acc[c] += pf * xs[t][c];
+                    for (int x = 0; x < 8; x++)
+                        pf[x] = (t0 + x < nb) ? __ldcg(A.X + (size_t)(c0 + t0 + x) * ldt + i) : 0.0;
+#pragma unroll
+                    for (int x = 0; x < 8; x++) {
+#pragma unroll
+                        for (int c = 0; c < REF_CB; c++) acc[c] += pf[x] * xs[t0 + x][c];
+                    }
                 }
 #pragma unroll
                 for (int c = 0; c < REF_CB; c++) {
@@ -305,7 +442,9 @@ __global__ void __launch_bounds__(REF_NT, 1) k_refactor(RefArgs A)
             }
             __syncthreads();
         }
+        REF_MARK(4);
         ref_bar(X, A);
+        REF_MARK(3);
     }
     /* ---- undo the row pivoting (a column permutation) and negate, out of place ---- */
     int *map = (int *)ref_dyn;
@@ -323,6 +462,8 @@ __global__ void __launch_bounds__(REF_NT, 1) k_refactor(RefArgs A)
         double *dst = A.T2 + (size_t)j * ldt;
         for (int b = tid; b < k; b += REF_NT) dst[b] = -src[b];
     }
+    REF_MARK(5);
+#undef REF_MARK
 }
 
 #endif /* GLPB_REFACTOR_CUH */

@@ -151,7 +151,7 @@ extern "C" void glpb_destroy(glpb_prob *P)
     void *ptrs[] = {P->a_ptr, P->a_ind, P->at_ptr, P->at_ind, P->a_val, P->at_val, P->type,
                     P->orig_type, P->stat, P->refsp, P->lb, P->ub, P->coef, P->orig_lb, P->orig_ub,
                     P->obj, P->head, P->bind, P->bbar, P->cbar, P->gamma, P->tcol, P->trow, P->rho,
-                    P->svec, P->w1, P->w2, P->w3, P->w4, P->w5, P->yk, P->wk, P->yk2, P->zn, P->eng_slots, P->eng_cols,
+                    P->svec, P->w1, P->w2, P->w3, P->w4, P->w5, P->yk, P->wk, P->yk2, P->zn, P->eng_slots, P->eng_cols, P->eng_fr,
                     P->eng_cyc, P->eng_bytes, P->T, P->T2, P->ref_slots, P->ref_flags, P->partial,
                     P->rslot, P->slot_pos, P->cslot, P->slot_row, P->gj_piv, P->gj_row, P->gj_col, P->gj_xp,
                     P->scratch, P->ctrl};
@@ -180,7 +180,7 @@ static int create_device(glpb_prob *P)
     DA(w1, m); DA(w2, m); DA(w3, m); DA(w4, m); DA(w5, m);
     P->ldt = (m + 7) & ~7;
     DA(yk, P->ldt); DA(wk, P->ldt); DA(yk2, P->ldt); DA(zn, P->ldt);
-    DA(eng_slots, ENG_RING * ENG_MAXG + 1); DA(eng_cols, 3 * (size_t)n + m); DA(eng_cyc, 24); DA(eng_bytes, 24);
+    DA(eng_slots, ENG_RING * ENG_MAXG + 1); DA(eng_cols, 3 * (size_t)n + m); DA(eng_fr, 2 * (size_t)ENG_DB * P->ldt + ENG_DB); DA(eng_cyc, 32); DA(eng_bytes, 24);
     DA(T, (size_t)P->ldt * P->ldt);
     DA(T2, (size_t)P->ldt * P->ldt);
     DA(ref_slots, ENG_RING * ENG_MAXG); DA(ref_flags, ENG_RING * ENG_MAXG * 32);
@@ -194,7 +194,7 @@ static int create_device(glpb_prob *P)
 #undef DA
     CK(cudaMallocHost((void **)&P->h_ctrl, sizeof(Ctrl)));
     CK(cudaMemsetAsync(P->ctrl, 0, sizeof(Ctrl), P->stream));
-    CK(cudaMemsetAsync(P->eng_cyc, 0, 24 * sizeof(long long), P->stream));
+    CK(cudaMemsetAsync(P->eng_cyc, 0, 32 * sizeof(long long), P->stream));
     CK(cudaMemsetAsync(P->eng_bytes, 0, 24 * sizeof(double), P->stream));
     /* persistent engine: one CTA per SM, dynamic shared memory for staging */
     {
@@ -203,7 +203,7 @@ static int create_device(glpb_prob *P)
         CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, P->device));
         CK(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, P->device));
         int budget = std::min(smem_max, 200 * 1024) - 24 * 1024;      /* static shared of the engine: ~20 KB */
-        int dcap = std::max(ENG_LCAP, std::min(P->ldt, (budget - ENG_LCAP * 4) / 8));
+        int dcap = std::max(ENG_DB * 192, std::min(P->ldt, (budget - ENG_LCAP * 4) / 8));   /* >= the staging of eng_flush */
         P->eng_dcap = dcap;
         P->eng_smem = dcap * 8 + ENG_LCAP * 4;
         if (!coop || P->sm_count > ENG_MAXG) { glpb_set_error("device lacks cooperative launch"); return GLPB_ENODEV; }
@@ -474,11 +474,11 @@ static int dev_refactor(Dev &D)
         static const int envs = getenv("GLPB_REF_SINGLE") ? atoi(getenv("GLPB_REF_SINGLE")) : -1;
         int nbr = 0, single = 0;
         for (int nb = REF_NB; nb >= 8 && !nbr; nb >>= 1)
-            if ((size_t)k * (nb + 2) * sizeof(double) <= REF_SMEM_MAX) { nbr = nb; single = 1; }
+            if ((size_t)k * (nb + 2) * sizeof(double) + 64 <= REF_SMEM_MAX) { nbr = nb; single = 1; }
         if (envs == 0 || !nbr) { nbr = REF_NB; single = 0; }
         if (!single) G = std::max(G, cdiv(k, REF_RMAX));
         const int R = single ? k : cdiv(k, G);
-        const size_t smem = std::max((size_t)R * (nbr + 2) * sizeof(double), (size_t)2 * k * sizeof(int));
+        const size_t smem = std::max((size_t)R * (nbr + 2) * sizeof(double) + 64, (size_t)2 * k * sizeof(int));
         if (G > P->sm_count || smem > REF_SMEM_MAX) {
             glpb_set_error("refactorisation: kernel of size %d does not fit the device", k);
             return GLPB_ENOMEM;
@@ -490,6 +490,7 @@ static int dev_refactor(Dev &D)
         A.a_ptr = P->a_ptr; A.a_ind = P->a_ind; A.a_val = P->a_val;
         A.head = P->head; A.slot_pos = P->slot_pos; A.cslot = P->cslot;
         A.piv = P->gj_piv; A.slots = P->ref_slots; A.flags = P->ref_flags;
+        A.prof_cyc = P->prof ? P->eng_cyc + 24 : nullptr;
         A.nbr = nbr; A.single = single; A.plan = (int *)P->gj_row;   /* gj_row: ldt doubles, used as scratch ints */
         void *args[] = {&A};
         P->next_bytes = 16.0 * k * (double)k * cdiv(k, REF_NB);
@@ -742,6 +743,11 @@ struct Loop : Dev {
         A.ycol = P->eng_cols; A.ycol2 = P->eng_cols + n; A.trowcol = P->eng_cols + 2 * (size_t)n;
         A.vrow = P->eng_cols + 3 * (size_t)n;
         A.slots = P->eng_slots;
+        static const int env_defer = getenv("GLPB_DEFER") ? atoi(getenv("GLPB_DEFER")) : 1;
+        static const int env_local = getenv("GLPB_LOCAL_MAX") ? atoi(getenv("GLPB_LOCAL_MAX")) : ENG_LOCAL_MAX;
+        A.Fd = P->eng_fr; A.Rd = P->eng_fr + (size_t)ENG_DB * P->ldt; A.zbuf = P->eng_fr + 2 * (size_t)ENG_DB * P->ldt;
+        A.defer = (env_defer && dual && P->eng_dcap >= ENG_DB * 192) ? 1 : 0;
+        A.local_max = env_local;
         A.prof_cyc = P->prof ? P->eng_cyc + (dual ? 12 : 0) : nullptr;
         A.prof_bytes = P->prof ? P->eng_bytes + (dual ? 12 : 0) : nullptr;
         const int G = engine_grid();
@@ -1449,7 +1455,7 @@ extern "C" int glpb_set_profile(glpb_prob *P, int on)
     if (on) {
         P->prof_acc.clear();
         P->n_eng_prof_iter[0] = P->n_eng_prof_iter[1] = 0;
-        cudaMemsetAsync(P->eng_cyc, 0, 24 * sizeof(long long), P->stream);
+        cudaMemsetAsync(P->eng_cyc, 0, 32 * sizeof(long long), P->stream);
         cudaMemsetAsync(P->eng_bytes, 0, 24 * sizeof(double), P->stream);
     }
     return 0;
@@ -1467,7 +1473,7 @@ extern "C" const char *glpb_profile_report(glpb_prob *P)
     }
     /* phases of the persistent engine: SM cycles of CTA 0 between barriers,
        scaled to the CUDA-event time of the engine launches; count = iterations */
-    long long cyc[24];
+    long long cyc[32];
     double byt[24];
     if (cudaMemcpy(cyc, P->eng_cyc, sizeof cyc, cudaMemcpyDeviceToHost) == cudaSuccess &&
         cudaMemcpy(byt, P->eng_bytes, sizeof byt, cudaMemcpyDeviceToHost) == cudaSuccess) {
@@ -1487,6 +1493,18 @@ extern "C" const char *glpb_profile_report(glpb_prob *P)
                 if (cyc[half * 12 + i] == 0) continue;
                 snprintf(line, sizeof line, "eng_%s %ld %.6f %.0f\n", pn[half * 12 + i], P->n_eng_prof_iter[half],
                          itp->second.ms * (double)cyc[half * 12 + i] / (double)tot, byt[half * 12 + i]);
+                P->prof_text += line;
+            }
+        }
+        /* phases inside k_refactor (CTA 0's view) */
+        auto itr = P->prof_acc.find("k_refactor");
+        if (itr != P->prof_acc.end()) {
+            static const char *rn[8] = {"build", "panel_pivots", "panel_io", "barrier_wait", "swap_update", "finish", "pivot_search", "pivot_bcast"};
+            long long tot = 0;
+            for (int i = 0; i < 8; i++) tot += cyc[24 + i];
+            for (int i = 0; i < 8 && tot > 0; i++) {
+                snprintf(line, sizeof line, "ref_%s %ld %.6f 0\n", rn[i], itr->second.count,
+                         itr->second.ms * (double)cyc[24 + i] / (double)tot);
                 P->prof_text += line;
             }
         }
