@@ -41,11 +41,11 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 WORKLOADS = {
     "c2": dict(gen="packing", kw=dict(m=2048, n=4096, density=0.20, seed=20240501), meth="primal",
-               cpu_it_lim=600, name="packing LP m=2048 n=4096 20% dense, primal simplex, PSE pricing, Harris ratio test"),
+               cpu_it_lim=600, cpu_mid=3000, cpu_mid_lim=150, name="packing LP m=2048 n=4096 20% dense, primal simplex, PSE pricing, Harris ratio test"),
     "c3": dict(gen="covering", kw=dict(m=16384, n=32768, kmin=8, kspan=17, seed=20240601), meth="dual",
                cpu_it_lim=1500, name="covering LP m=16384 n=32768 ~16 nnz/col, dual simplex, PSE pricing, Harris ratio test"),
     "c2s": dict(gen="packing", kw=dict(m=512, n=1024, density=0.20, seed=20240501), meth="primal",
-                cpu_it_lim=600, name="packing LP m=512 n=1024 20% dense (quarter-size check)"),
+                cpu_it_lim=600, cpu_mid=400, cpu_mid_lim=300, name="packing LP m=512 n=1024 20% dense (quarter-size check)"),
     "c3s": dict(gen="covering", kw=dict(m=4096, n=8192, kmin=8, kspan=17, seed=20240601), meth="dual",
                 cpu_it_lim=1500, name="covering LP m=4096 n=8192 (quarter-size check)"),
 }
@@ -105,6 +105,55 @@ def meth_code(nat, w):
     return nat.GLP_PRIMAL if w["meth"] == "primal" else nat.GLP_DUAL
 
 
+class CpuSampler:
+    """The reference's CPU path (the oracle: C++ port, one thread like the
+    reference) on a BOUNDED sample of the workload: window A = the first
+    cpu_it_lim iterations from the standard basis; window B (when the workload
+    defines cpu_mid) = cpu_mid_lim iterations warm-started from the basis the
+    oracle itself reaches after cpu_mid iterations (set-up run, not timed).
+    The iteration rate falls as the basis fills with structural columns, so a
+    start-only window would flatter the CPU."""
+
+    def __init__(self, d, w):
+        import oracle_lib as O
+        from helpers import to_oracle
+        self.O, self.d, self.w, self.od = O, d, w, to_oracle(d)
+        self.meth = O.GLP_PRIMAL if w["meth"] == "primal" else O.GLP_DUAL
+        self.mid_stat = None
+        self.setup_s = 0.0
+        if w.get("cpu_mid"):
+            t0 = time.perf_counter()
+            P = O.Problem.from_arrays(self.od)
+            P.simplex(meth=self.meth, it_lim=w["cpu_mid"])
+            self.mid_stat = P.solution()["stat"].copy()
+            self.setup_s = time.perf_counter() - t0
+
+    def step(self):
+        """one bounded sample; returns (iterations, seconds)"""
+        O, w = self.O, self.w
+        P = O.Problem.from_arrays(self.od)
+        t0 = time.perf_counter()
+        P.simplex(meth=self.meth, it_lim=w["cpu_it_lim"])
+        dt = time.perf_counter() - t0
+        it = P.solution()["it_cnt"]
+        if self.mid_stat is not None:
+            Q = O.Problem.from_arrays(self.od)
+            Q.set_stat(self.mid_stat)
+            t0 = time.perf_counter()
+            Q.simplex(meth=self.meth, it_lim=w["cpu_mid_lim"])
+            dt += time.perf_counter() - t0
+            it += Q.solution()["it_cnt"]
+        return it, dt
+
+    def describe(self):
+        w = self.w
+        s = "first %d iterations of the same LP from the standard basis" % w["cpu_it_lim"]
+        if self.mid_stat is not None:
+            s += " + %d iterations warm-started from the oracle's own basis after %d iterations" % (
+                w["cpu_mid_lim"], w["cpu_mid"])
+        return s + " (C++ port of the reference, single thread; the JS reference cannot run here: no JS engine)"
+
+
 def run_reference(args, w, rank, world):
     """--impl reference: the reference's own CPU implementation of the path.
     The reference is JavaScript and no JS engine exists in this image, so this
@@ -114,25 +163,20 @@ def run_reference(args, w, rank, world):
     import glpk_js_b200 as G
     nat = G.native
     d = nat.generate(w["gen"], **w["kw"])
-    O, _ = oracle_problem(d)
-    it_lim = w["cpu_it_lim"]
+    smp = CpuSampler(d, w)
     times, iters = [], []
     for s in range(args.warmup + args.steps):
-        _, P = oracle_problem(d)
-        t0 = time.perf_counter()
-        P.simplex(meth=meth_code(O, w), it_lim=it_lim)
-        dt = time.perf_counter() - t0
+        it, dt = smp.step()
         if s >= args.warmup:
             times.append(dt)
-            iters.append(P.solution()["it_cnt"])
+            iters.append(it)
     val = sum(iters) / sum(times)
-    sample = "first %d iterations of the same LP from the standard basis (the full CPU solve takes minutes)" % it_lim
     line = {"impl": "reference", "metric": "simplex_iterations_per_sec", "value": val, "unit": "iter/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1000.0 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": w["name"], **{k: v for k, v in w["kw"].items()}},
-            "cpu_baseline": {"value": val, "unit": "iter/s", "cores": 1, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": val, "unit": "iter/s", "cores": 1, "kind": "port", "sample": smp.describe()},
             "e2e": {"value": val, "unit": "iter/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -146,6 +190,9 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-full", action="store_true", help="profile the whole solve, not its first 1500 iterations")
+    ap.add_argument("--no-c3", action="store_true", help="skip the extra full solve of the 16384x32768 LP")
+    ap.add_argument("--c3-mid", type=int, default=60000, help="iteration at which the C3 solve is split for the CPU sample")
+    ap.add_argument("--c3-cpu-mid-lim", type=int, default=100)
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
@@ -226,7 +273,7 @@ def main():
     #      scaled to the CUDA-event time of the engine launches) ----
     P.std_basis()
     P.set_profile(1)
-    P.simplex(meth=meth, it_lim=int(iters[-1]) if args.profile_full else min(int(iters[-1]), 1500))
+    P.simplex(meth=meth, it_lim=int(iters[-1]) if (args.profile_full or iters[-1] <= 20000) else 1500)
     prof = P.profile()
     P.set_profile(0)
     ref_split = {k: v for k, v in prof.items() if k.startswith("ref_")}          # inside k_refactor: informational
@@ -293,14 +340,59 @@ def main():
     # ---- CPU baseline (rank 0, N=1 only): the oracle on a bounded sample ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        O, Pc = oracle_problem(d)
-        t0 = time.perf_counter()
-        Pc.simplex(meth=meth_code(O, w), it_lim=w["cpu_it_lim"])
-        dt = time.perf_counter() - t0
-        itc = Pc.solution()["it_cnt"]
+        smp = CpuSampler(d, w)
+        itc, dt = smp.step()
         cpu = {"value": itc / dt, "unit": "iter/s", "cores": 1, "kind": "port",
-               "sample": "first %d iterations of the same LP from the standard basis, %.1f s "
-                         "(C++ port of the reference; the JS reference cannot run here)" % (itc, dt)}
+               "sample": smp.describe() + "; %d iterations in %.1f s" % (itc, dt)}
+
+    # ---- the north-star shape (BASELINE.json configs[2]): one full dual solve of the
+    #      16384 x 32768 covering LP, device-resident, next to a bounded CPU sample ----
+    c3 = None
+    if rank == 0 and world == 1 and args.workload == "c2" and not args.no_c3:
+        w3 = WORKLOADS["c3"]
+        d3 = nat.generate(w3["gen"], **w3["kw"])
+        P3 = nat.Problem(d3, device=local_rank)
+        P3.set_profile(1)
+        flush_l2()
+        # two calls: the basis at the midpoint seeds the CPU sample below
+        P3.simplex(meth=nat.GLP_DUAL, it_lim=args.c3_mid)
+        us_a = P3.counters()["solve_us"]
+        mid_stat3 = P3.solution()["stat"].copy()
+        rc3 = P3.simplex(meth=nat.GLP_DUAL)
+        c3cnt, s3 = P3.counters(), P3.solution()
+        c3cnt["solve_us"] += us_a
+        prof3 = {k: v for k, v in P3.profile().items() if k.startswith("eng_") and v["count"] > 0 and v["bytes"] > 0}
+        P3.close()
+        top3 = max(prof3, key=lambda k: prof3[k]["ms"]) if prof3 else None
+        c3 = {"workload": w3["name"], "value": s3["it_cnt"] / (c3cnt["solve_us"] * 1e-6), "unit": "iter/s",
+              "time_to_optimal_ms": c3cnt["solve_us"] / 1000.0, "iterations": int(s3["it_cnt"]), "status": int(s3["status"]),
+              "rc": int(rc3), "objective": s3["obj"], "refactorizations": c3cnt["refactorizations"],
+              "kernel_size_k": c3cnt["k"], "note": "single solve, profiling marks on (a few percent slower)"}
+        if top3:
+            v3 = prof3[top3]
+            ach3 = v3["bytes"] / (v3["ms"] * 1e-3) / 1e9
+            c3["roofline"] = {"bound": "hbm", "kernel": "k_engine_dual:" + top3[4:], "achieved": ach3, "peak": peak,
+                              "unit": "GB/s", "frac": ach3 / peak, "us_per_iteration": 1000.0 * v3["ms"] / v3["count"],
+                              "bytes_per_iteration": v3["bytes"] / v3["count"]}
+        if not args.no_cpu_baseline:
+            smp3 = CpuSampler(d3, w3)
+            it3, dt3 = smp3.step()
+            # second window: the same port warm-started from the DEVICE's basis after c3_mid
+            # iterations (reaching it on the CPU would take the better part of an hour)
+            O3 = smp3.O
+            Q3 = O3.Problem.from_arrays(smp3.od)
+            Q3.set_stat(mid_stat3)
+            t0 = time.perf_counter()
+            Q3.simplex(meth=O3.GLP_DUAL, it_lim=args.c3_cpu_mid_lim)
+            dtm = time.perf_counter() - t0
+            itm = Q3.solution()["it_cnt"]
+            c3["cpu_baseline"] = {"value": (it3 + itm) / (dt3 + dtm), "unit": "iter/s", "cores": 1, "kind": "port",
+                                  "start_window": {"iterations": int(it3), "seconds": dt3, "iter_per_s": it3 / dt3},
+                                  "mid_window": {"iterations": int(itm), "seconds": dtm, "iter_per_s": itm / max(dtm, 1e-9),
+                                                 "from": "the device's basis after %d iterations" % args.c3_mid},
+                                  "sample": smp3.describe() + " + %d iterations warm-started from the device's basis "
+                                  "after %d iterations (one refactorisation period, factorisation included)"
+                                  % (itm, args.c3_mid)}
 
     if rank == 0:
         line = {"metric": "simplex_iterations_per_sec", "value": value, "unit": "iter/s", "n_gpus": world,
@@ -316,7 +408,8 @@ def main():
                 "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
                 "iterations_per_step": tot_it / args.steps, "time_to_optimal_ms": max_ms / args.steps,
                 "status": int(status), "objective": obj, "wall_s_timed_region": t_wall,
-                "refactorizations": cnt["refactorizations"], "kernel_size_k": cnt["k"]}
+                "refactorizations": cnt["refactorizations"], "kernel_size_k": cnt["k"],
+                "north_star_c3": c3}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

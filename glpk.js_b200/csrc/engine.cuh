@@ -330,12 +330,15 @@ __device__ void eng_gemv_rows(const EngCtx &X, const EngArgs &A, int k, int L, c
     __shared__ double red[32][33];
     const int RPC = (((k + X.G - 1) / X.G) + 3) & ~3;          /* rows per CTA */
     const int q0 = min(k, X.cta * RPC), q1 = min(k, q0 + RPC);
-    const int RB = (RPC >= 24) ? 32 : (RPC >= 12 ? 16 : 8);
-    const int NSUB = 32 / RB;
-    const int r = X.lane & (RB - 1), sub = X.lane / RB;
-    const int stride = NSUB * 32;
     const size_t ldt = (size_t)A.ldt;
+    int RB = 32;
     for (int b0 = q0; b0 < q1; b0 += RB) {
+        /* chunk height by what is left: a short last chunk puts two or four columns in one warp load */
+        const int rem = q1 - b0;
+        RB = (rem >= 24) ? 32 : (rem >= 12 ? 16 : 8);
+        const int NSUB = 32 / RB;
+        const int r = X.lane & (RB - 1), sub = X.lane / RB;
+        const int stride = NSUB * 32;
         const int b = b0 + r;
         const bool inb = b < q1;
         const double *Tb = A.T + (inb ? b : q0);

@@ -855,7 +855,8 @@ struct Loop : Dev {
     int refac_period() const
     {
         static const bool fixed = getenv("GLPB_REFAC_AUTO") && atoi(getenv("GLPB_REFAC_AUTO")) == 0;
-        return fixed ? P->bfcp.nfs_max : std::max(P->bfcp.nfs_max, k / 8);
+        static const int div = getenv("GLPB_REFAC_DIV") ? std::max(1, atoi(getenv("GLPB_REFAC_DIV"))) : 2;
+        return fixed ? P->bfcp.nfs_max : std::max(P->bfcp.nfs_max, k / div);
     }
     bool it_limit() const { return parm.it_lim < INT_MAX && it_cnt - it_beg >= parm.it_lim; }
     bool tm_limit() const { return parm.tm_lim < INT_MAX && (now_ms() - tm_beg) >= parm.tm_lim; }
