@@ -336,6 +336,51 @@ __device__ void eng_gemv_rows(const EngCtx &X, const EngArgs &A, int k, int L, c
         /* chunk height by what is left: a short last chunk puts two or four columns in one warp load */
         const int rem = q1 - b0;
         RB = (rem >= 24) ? 32 : (rem >= 12 ? 16 : 8);
+        if (idx == nullptr && RB == 32) {
+            /* dense stream, full-height chunk: 16-byte loads (two rows per lane, two
+               columns per warp instruction), eight in flight per thread */
+            const int r2 = X.lane & 15, sub2 = X.lane >> 4;
+            const int ba = b0 + 2 * r2;
+            const bool in0 = ba < q1, in1 = ba + 1 < q1;
+            const double *Tb2 = A.T + (in0 ? ba : q0);
+            double ax0 = 0.0, ay0 = 0.0, ax1 = 0.0, ay1 = 0.0;
+            int e = sub2 + 2 * X.warp;
+            for (; e + 7 * 64 < L; e += 8 * 64) {
+                double2 t[8];
+#pragma unroll
+                for (int x = 0; x < 8; x++) t[x] = __ldcg((const double2 *)(Tb2 + (size_t)(e + x * 64) * ldt));
+#pragma unroll
+                for (int x = 0; x < 8; x += 2) {
+                    const double v0 = val[e + x * 64], v1 = val[e + (x + 1) * 64];
+                    ax0 += t[x].x * v0; ay0 += t[x].y * v0;
+                    ax1 += t[x + 1].x * v1; ay1 += t[x + 1].y * v1;
+                }
+            }
+            for (; e < L; e += 64) {
+                const double2 t0 = __ldcg((const double2 *)(Tb2 + (size_t)e * ldt));
+                const double v0 = val[e];
+                ax0 += t0.x * v0; ay0 += t0.y * v0;
+            }
+            double ax = in0 ? ax0 + ax1 : 0.0, ay = in1 ? ay0 + ay1 : 0.0;
+            ax += __shfl_xor_sync(FULLMASK, ax, 16);
+            ay += __shfl_xor_sync(FULLMASK, ay, 16);
+            if (sub2 == 0) { red[X.warp][2 * r2] = ax; red[X.warp][2 * r2 + 1] = ay; }
+            __syncthreads();
+            if (X.tid < 32) {
+                double s = 0.0;
+#pragma unroll 8
+                for (int w = 0; w < 32; w++) s += red[w][X.tid];
+                const int b2 = b0 + X.tid;
+                if (b2 < q1) {
+                    for (int j = 0; j < nd; j++) s += A.Fd[(size_t)j * ldt + b2] * z[j];
+                    if (accumulate) s += y[b2];
+                    y[b2] = s;
+                    ycol[A.head[A.slot_pos[b2]] - A.m] = s;
+                }
+            }
+            __syncthreads();
+            continue;
+        }
         const int NSUB = 32 / RB;
         const int r = X.lane & (RB - 1), sub = X.lane / RB;
         const int stride = NSUB * 32;
