@@ -1008,8 +1008,9 @@ __global__ void __launch_bounds__(ENG_NT, 1) k_engine_primal(EngArgs A)
         const double sgn = (S.d1 > 0.0 ? -1.0 : +1.0);
         const bool pse = gamma_on(&S);
         bool cbar_q_pending = true;    /* reeval_cost result cbar[q] = d1 (lib/glpspx01.js:1915-1918) not stored yet */
-        /* ---- Harris ratio test (chuzr) ---- */
+        /* ---- Harris ratio test (chuzr); the first half of u = inv(B') v rides along ---- */
         if (local_ratio) {
+            if (pse) eng_btran_head(X, A, S.k);
             Key none = {DBL_MAX, 0.0, 0.0, INT_MAX, 0};
             Key v = none;
             if (X.tid == 0 && A.type[kq] == GLP_DB) {
@@ -1028,7 +1029,11 @@ __global__ void __launch_bounds__(ENG_NT, 1) k_engine_primal(EngArgs A)
                 if (X.tid == 0) fin_ratio_primal(&S, r, 2, sgn, A.rtol, A.type, A.head, A.tcol, nullptr);
                 __syncthreads();
             }
-            eng_mark(X, A, PP_B, 12.0 * (double)__ldg(A.at_ptr + m) * (1.0 - (double)S.k / m) + 29.0 * m + 90.0 * m);
+            /* one barrier: w (first half of u) is complete, and nobody still scans bbar/tcol
+               when the update phase of a bound flip rewrites bbar */
+            eng_bar(X, A);
+            eng_mark(X, A, PP_B, 12.0 * (double)__ldg(A.at_ptr + m) * (1.0 - (double)S.k / m) + 29.0 * m + 90.0 * m +
+                                 (pse ? 12.0 * nnzA * ((double)S.k / n) + 16.0 * S.k : 0.0));
         } else {
             eng_mark(X, A, PP_B, 12.0 * (double)__ldg(A.at_ptr + m) * (1.0 - (double)S.k / m) + 29.0 * m);
             Key none = {DBL_MAX, 0.0, 0.0, INT_MAX, 0};
@@ -1038,6 +1043,7 @@ __global__ void __launch_bounds__(ENG_NT, 1) k_engine_primal(EngArgs A)
             }
             scan_ratio_primal(v, X.gtid, X.gsize, 1, S.phase, sgn, S.eps, 0.0, A.rtol, A.type, A.lb, A.ub,
                               A.coef, A.head, A.bbar, A.tcol, nullptr, m);
+            if (pse) eng_btran_head(X, A, S.k);
             Key r = eng_allreduce(X, A, v, none, CombRatio1());
             if (X.cta == 0 && X.tid == 0) A.cbar[q] = S.d1;     /* every CTA has read the old value by now */
             cbar_q_pending = false;
@@ -1061,14 +1067,10 @@ __global__ void __launch_bounds__(ENG_NT, 1) k_engine_primal(EngArgs A)
             break;
         }
         const int p = S.p;
+        if (cbar_q_pending && X.cta == 0 && X.tid == 0) A.cbar[q] = S.d1;   /* all CTAs are past the d1/d2 test */
         if (p >= 0) {
-            /* ---- C: rho (+ first half of u = inv(B') v) ---- */
+            /* ---- C: rho and the second half of u ---- */
             eng_rho(X, A, S.k, p, 0);
-            if (pse) eng_btran_head(X, A, S.k);
-            eng_bar(X, A);
-            if (cbar_q_pending && X.cta == 0 && X.tid == 0) A.cbar[q] = S.d1;   /* all CTAs are past the d1/d2 test */
-            eng_mark(X, A, PP_C, 12.0 * m + 8.0 * S.k + (pse ? 12.0 * nnzA * ((double)S.k / n) + 16.0 * S.k : 0.0));
-            /* ---- D: second half of u ---- */
             if (pse) {
                 const int k = S.k;
                 const int LP = max(32, eng_pick_lp(X, k, (double)k / 2));
@@ -1088,9 +1090,9 @@ __global__ void __launch_bounds__(ENG_NT, 1) k_engine_primal(EngArgs A)
                     [&](int cs, const double *a) { A.u[A.slot_row[cs]] = a[0]; });
                 for (int r = X.gtid; r < m; r += X.gsize)
                     if (A.cslot[r] < 0) A.u[r] = A.vrow[r];
-                eng_bar(X, A);
-                eng_mark(X, A, PP_D, 8.0 * S.k * (double)S.k + 20.0 * m);
             }
+            eng_bar(X, A);
+            eng_mark(X, A, PP_C, 12.0 * m + 8.0 * S.k + (pse ? 8.0 * S.k * (double)S.k + 20.0 * m : 0.0));
             /* ---- E: pivot row and PSE inner products ---- */
             {
                 Key dummy = {0.0, 0.0, 0.0, 0, 0};
@@ -1112,8 +1114,6 @@ __global__ void __launch_bounds__(ENG_NT, 1) k_engine_primal(EngArgs A)
                 if (S.status != ST_OK) break;
             }
         }
-        else if (local_ratio)
-            eng_bar(X, A);      /* bound flip: phase F rewrites bbar, which slower CTAs may still be scanning */
         /* ---- F: update_bbar / update_cbar / update_gamma / basis change, and the
                 pricing of the next iteration from the values just written ---- */
         {

@@ -1,0 +1,96 @@
+"""GPU tests of the persistent iteration engine and the cooperative
+refactorisation: every execution mode (replicated vs grid-wide ratio test,
+direct vs deferred basis changes, shared-memory vs distributed panel, grid
+sizes, per-kernel path) must reach the same optimum as the oracle, with KKT
+residuals <= 1e-9, and take (nearly) the same number of iterations; plus the
+size-independent properties at BASELINE.json's full sizes."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+import glpk_js_b200 as G
+import oracle_lib as O
+import helpers as H
+
+nat = G.native
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+# objective of C2 (packing LP 2048 x 4096, seed 20240501) from a full solve of the
+# oracle (228 s on the build container); the device must reproduce it to 1e-9
+C2_OBJ = 89464.4101453462
+
+
+def solve_in_subprocess(args, env=None, timeout=600):
+    e = dict(os.environ)
+    e.update(env or {})
+    out = subprocess.run([sys.executable, os.path.join(HERE, "run_solve.py")] + [str(a) for a in args],
+                         env=e, capture_output=True, text=True, timeout=timeout)
+    assert out.returncode == 0, out.stderr[-2000:]
+    return json.loads(out.stdout.strip().splitlines()[-1])
+
+
+MODES = [
+    ("default", {}),
+    ("grid-wide ratio test + deferred basis changes", {"GLPB_LOCAL_MAX": "0"}),
+    ("grid-wide ratio test, direct basis changes", {"GLPB_LOCAL_MAX": "0", "GLPB_DEFER": "0"}),
+    ("three CTAs", {"GLPB_GRID": "3"}),
+    ("one CTA", {"GLPB_GRID": "1"}),
+    ("distributed panel", {"GLPB_REF_SINGLE": "0"}),
+    ("refactorise every nfs_max updates", {"GLPB_REFAC_AUTO": "0"}),
+    ("per-kernel path", {"GLPB_ENGINE": "0"}),
+]
+
+
+@pytest.mark.parametrize("which,m,n", [("covering", 1024, 2048), ("packing", 256, 512)])
+def test_every_mode_reaches_the_oracle_optimum(which, m, n):
+    if which == "packing":
+        d = nat.generate("packing", m=m, n=n, density=0.2, seed=20240501)
+        meth = O.GLP_PRIMAL
+    else:
+        d = nat.generate("covering", m=m, n=n, kmin=8, kspan=17, seed=20240601)
+        meth = O.GLP_DUAL
+    Q = O.Problem.from_arrays(H.to_oracle(d))
+    assert Q.simplex(meth=meth) == 0
+    o = Q.solution()
+    its = {}
+    for name, env in MODES:
+        r = solve_in_subprocess([which, m, n], env)
+        assert (r["rc"], r["status"]) == (0, o["status"]), (name, r)
+        assert abs(r["obj"] - o["obj"]) <= 1e-9 * max(1.0, abs(o["obj"])), (name, r["obj"], o["obj"])
+        assert max(r["kkt"].values()) <= 1e-9, (name, r["kkt"])
+        its[name] = r["it"]
+    # the modes differ from each other only in summation order (same pivots up to the odd
+    # tie); against the oracle the inverse is built in another pivot order, so on these
+    # degenerate LPs ties fall differently now and then: a few percent either way
+    ref = its["default"]
+    for name, it in its.items():
+        assert abs(it - ref) <= 0.02 * ref + 5, (name, its)
+        assert abs(it - o["it_cnt"]) <= 0.10 * o["it_cnt"] + 5, (name, its, o["it_cnt"])
+
+
+def test_c2_full_size_objective_and_kkt():
+    """BASELINE.json configs[1] at full size: optimum pinned by the oracle's full solve"""
+    r = solve_in_subprocess(["packing", 2048, 4096])
+    assert (r["rc"], r["status"]) == (0, O.GLP_OPT)
+    assert abs(r["obj"] - C2_OBJ) <= 1e-9 * C2_OBJ, r["obj"]
+    assert max(r["kkt"].values()) <= 1e-9, r["kkt"]
+    assert r["launches"] < r["it"], "the iterations must run inside the persistent engine"
+
+
+def test_c3_full_size_properties():
+    """BASELINE.json configs[2] at full size (the oracle would need the better part
+    of an hour): optimality through the size-independent properties -- status,
+    primal/dual feasibility and the reduced-cost equation (glp_check_kkt
+    residuals), with the basis changes deferred and the distributed panel in use"""
+    r = solve_in_subprocess(["covering", 16384, 32768], timeout=900)
+    assert (r["rc"], r["status"]) == (0, O.GLP_OPT)
+    assert max(r["kkt"].values()) <= 1e-9, r["kkt"]
+    assert r["k"] > 2560, "kernel larger than the shared-memory panel: distributed mode was exercised"
+    # same optimum whichever way the basis changes are applied
+    r2 = solve_in_subprocess(["covering", 16384, 32768], {"GLPB_DEFER": "0", "GLPB_REFAC_DIV": "4"}, timeout=900)
+    assert (r2["rc"], r2["status"]) == (0, O.GLP_OPT)
+    assert abs(r["obj"] - r2["obj"]) <= 1e-9 * abs(r["obj"]), (r["obj"], r2["obj"])
