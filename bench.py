@@ -46,6 +46,9 @@ WORKLOADS = {
                cpu_it_lim=1500, name="covering LP m=16384 n=32768 ~16 nnz/col, dual simplex, PSE pricing, Harris ratio test"),
     "c2s": dict(gen="packing", kw=dict(m=512, n=1024, density=0.20, seed=20240501), meth="primal",
                 cpu_it_lim=600, cpu_mid=400, cpu_mid_lim=300, name="packing LP m=512 n=1024 20% dense (quarter-size check)"),
+    "mkp": dict(gen="mkp", kw=dict(m=30, n=500, seed=20240701), meth="bnb", node_lim=400,
+                name="multi-dimensional knapsack MIP m=30 n=500 (BASELINE.json configs[4]), branch-and-bound "
+                     "(DTH branching, best-local-bound backtracking), nodes sharded across the ranks"),
     "c3s": dict(gen="covering", kw=dict(m=4096, n=8192, kmin=8, kspan=17, seed=20240601), meth="dual",
                 cpu_it_lim=1500, name="covering LP m=4096 n=8192 (quarter-size check)"),
 }
@@ -181,6 +184,81 @@ def run_reference(args, w, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def run_bnb(args, w, rank, local_rank, world):
+    """--workload mkp: branch-and-bound throughput (nodes/s).  A step = node_lim
+    node LPs per rank (ios_solve_node: warm-started dual simplex + Driebeck-Tomlin
+    branching); nodes are sharded across the ranks (glpk.js_b200/bnb.py: incumbent
+    all-reduce + node migration over NCCL).  Weak scaling: the per-rank node budget
+    is fixed."""
+    import torch
+    import torch.distributed as dist
+    import glpk_js_b200 as G
+    from glpk_js_b200 import bnb
+    nat = G.native
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    d = nat.generate(w["gen"], **w["kw"])
+    node_lim = w["node_lim"]
+    comm = bnb.TorchComm() if world > 1 else bnb.LocalGroup(1).comm(0)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    times, nodes, objs = [], [], []
+    for s in range(args.warmup + args.steps):
+        P = nat.Problem(d, device=local_rank)          # host buffers -> device every step (e2e == value here)
+        assert P.simplex(meth=nat.GLP_PRIMAL) == 0     # root LP, as solve_mip requires (lib/glpapi09.js:67-72)
+        if s == args.warmup:
+            sampler.start()
+        barrier()
+        t0 = time.perf_counter()
+        res = bnb.sharded_intopt(bnb.Worker(P), comm,
+                                 minimize=(d["dir"] == nat.GLP_MIN), node_lim=node_lim, msg_lev=0)
+        barrier()
+        dt = time.perf_counter() - t0
+        P.close()
+        if s >= args.warmup:
+            times.append(dt)
+            nodes.append(res["total_nodes"])
+            objs.append(res["obj"])
+    clocks = sampler.stop()
+    my = float(sum(times))
+    if world > 1:
+        t = torch.tensor([my], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        my = float(t.item())
+    value = sum(nodes) / my
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        import oracle_lib as O
+        from helpers import to_oracle
+        Q = O.Problem.from_arrays(to_oracle(d))
+        Q.simplex(meth=O.GLP_PRIMAL)
+        t0 = time.perf_counter()
+        Q.intopt(node_lim=node_lim)
+        dtc = time.perf_counter() - t0
+        cpu = {"value": Q.mip()["nodes"] / dtc, "unit": "nodes/s", "cores": 1, "kind": "port",
+               "sample": "%d nodes of the same search (node limit), C++ port of the reference, single thread" % Q.mip()["nodes"]}
+    if rank == 0:
+        line = {"metric": "bnb_nodes_per_sec", "value": value, "unit": "nodes/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": 1000.0 * my / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": w["name"], **w["kw"], "node_lim_per_rank": node_lim,
+                           "parallelism": "nodes sharded over %d rank(s)" % world},
+                "clocks": clocks, "e2e": {"value": value, "unit": "nodes/s", "h2d_bytes_per_step": int(sum(
+                    a.nbytes for a in d.values() if isinstance(a, np.ndarray))), "d2h_bytes_per_step": 8 * (d["m"] + d["n"])},
+                "gpu_launches": None, "roofline": None, "cpu_baseline": cpu, "incumbent": objs[-1] if objs else None}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -201,6 +279,9 @@ def main():
 
     if args.impl == "reference":
         run_reference(args, w, rank, world)
+        return
+    if w["meth"] == "bnb":
+        run_bnb(args, w, rank, local_rank, world)
         return
 
     import torch

@@ -85,6 +85,7 @@ struct EngCtx {
     long long t_last;
     double *sh_d;             /* [dcap] staging values / dense vector            */
     int *sh_i;                /* [ENG_LCAP] staging indices                      */
+    double *sh_red2;          /* [32][65] cross-warp sums of the dense T*v stream */
 };
 
 __device__ __forceinline__ unsigned int eng_ld_relaxed(const unsigned int *p)
@@ -336,40 +337,51 @@ __device__ void eng_gemv_rows(const EngCtx &X, const EngArgs &A, int k, int L, c
         /* chunk height by what is left: a short last chunk puts two or four columns in one warp load */
         const int rem = q1 - b0;
         RB = (rem >= 24) ? 32 : (rem >= 12 ? 16 : 8);
-        if (idx == nullptr && RB == 32) {
-            /* dense stream, full-height chunk: 16-byte loads (two rows per lane, two
-               columns per warp instruction), eight in flight per thread */
-            const int r2 = X.lane & 15, sub2 = X.lane >> 4;
+        if (idx == nullptr && rem >= 24) {
+            /* dense stream: 16-byte loads, two rows per lane, eight loads in flight per
+               thread.  Up to 32 rows left: half a warp per column, two columns per warp
+               instruction; 33..64 rows: the whole chunk in ONE pass, a warp per column
+               (each column of T is touched once, in one contiguous piece). */
+            const bool wide = rem > 32;
+            const int CH = wide ? min(rem, 64) : 32;             /* rows of this chunk */
+            const int r2 = wide ? X.lane : (X.lane & 15), sub2 = wide ? 0 : (X.lane >> 4);
+            const int cstep = wide ? 32 : 64, cfirst = wide ? X.warp : sub2 + 2 * X.warp;
             const int ba = b0 + 2 * r2;
-            const bool in0 = ba < q1, in1 = ba + 1 < q1;
+            const int lim = min(b0 + CH, q1);
+            const bool in0 = ba < lim, in1 = ba + 1 < lim;
             const double *Tb2 = A.T + (in0 ? ba : q0);
             double ax0 = 0.0, ay0 = 0.0, ax1 = 0.0, ay1 = 0.0;
-            int e = sub2 + 2 * X.warp;
-            for (; e + 7 * 64 < L; e += 8 * 64) {
-                double2 t[8];
+            int e = cfirst;
+            if (in0) {
+                for (; e + 7 * cstep < L; e += 8 * cstep) {
+                    double2 t[8];
 #pragma unroll
-                for (int x = 0; x < 8; x++) t[x] = __ldcg((const double2 *)(Tb2 + (size_t)(e + x * 64) * ldt));
+                    for (int x = 0; x < 8; x++) t[x] = __ldcg((const double2 *)(Tb2 + (size_t)(e + x * cstep) * ldt));
 #pragma unroll
-                for (int x = 0; x < 8; x += 2) {
-                    const double v0 = val[e + x * 64], v1 = val[e + (x + 1) * 64];
-                    ax0 += t[x].x * v0; ay0 += t[x].y * v0;
-                    ax1 += t[x + 1].x * v1; ay1 += t[x + 1].y * v1;
+                    for (int x = 0; x < 8; x += 2) {
+                        const double v0 = val[e + x * cstep], v1 = val[e + (x + 1) * cstep];
+                        ax0 += t[x].x * v0; ay0 += t[x].y * v0;
+                        ax1 += t[x + 1].x * v1; ay1 += t[x + 1].y * v1;
+                    }
+                }
+                for (; e < L; e += cstep) {
+                    const double2 t0 = __ldcg((const double2 *)(Tb2 + (size_t)e * ldt));
+                    const double v0 = val[e];
+                    ax0 += t0.x * v0; ay0 += t0.y * v0;
                 }
             }
-            for (; e < L; e += 64) {
-                const double2 t0 = __ldcg((const double2 *)(Tb2 + (size_t)e * ldt));
-                const double v0 = val[e];
-                ax0 += t0.x * v0; ay0 += t0.y * v0;
-            }
             double ax = in0 ? ax0 + ax1 : 0.0, ay = in1 ? ay0 + ay1 : 0.0;
-            ax += __shfl_xor_sync(FULLMASK, ax, 16);
-            ay += __shfl_xor_sync(FULLMASK, ay, 16);
-            if (sub2 == 0) { red[X.warp][2 * r2] = ax; red[X.warp][2 * r2 + 1] = ay; }
+            if (!wide) {
+                ax += __shfl_xor_sync(FULLMASK, ax, 16);
+                ay += __shfl_xor_sync(FULLMASK, ay, 16);
+            }
+            double (*red2)[65] = (double (*)[65])X.sh_red2;      /* [32][65] */
+            if (sub2 == 0) { red2[X.warp][2 * r2] = ax; red2[X.warp][2 * r2 + 1] = ay; }
             __syncthreads();
-            if (X.tid < 32) {
+            if (X.tid < CH) {
                 double s = 0.0;
 #pragma unroll 8
-                for (int w = 0; w < 32; w++) s += red[w][X.tid];
+                for (int w = 0; w < 32; w++) s += red2[w][X.tid];
                 const int b2 = b0 + X.tid;
                 if (b2 < q1) {
                     for (int j = 0; j < nd; j++) s += A.Fd[(size_t)j * ldt + b2] * z[j];
@@ -379,6 +391,7 @@ __device__ void eng_gemv_rows(const EngCtx &X, const EngArgs &A, int k, int L, c
                 }
             }
             __syncthreads();
+            RB = CH;
             continue;
         }
         const int NSUB = 32 / RB;
@@ -911,6 +924,7 @@ __device__ __forceinline__ void eng_init(EngCtx &X, const EngArgs &A, double *dy
     X.t_last = clock64();
     X.sh_d = dyn;
     X.sh_i = (int *)(dyn + A.dcap);
+    X.sh_red2 = (double *)(X.sh_i + ENG_LCAP);
 }
 
 /* block-wide reduction whose result every thread of the CTA gets */

@@ -152,7 +152,7 @@ struct glpb_prob {
     int partial_rows = 0;
     int *rslot = nullptr, *slot_pos = nullptr, *cslot = nullptr, *slot_row = nullptr;
     int *gj_piv = nullptr;
-    double *gj_row = nullptr, *gj_col = nullptr, *gj_xp = nullptr;
+    double *gj_row = nullptr;        /* scratch of the refactorisation (gather list) */
     Key *scratch = nullptr;           /* block partials of reductions */
     Ctrl *ctrl = nullptr;             /* device */
     Ctrl *h_ctrl = nullptr;           /* pinned host mirror */

@@ -1002,7 +1002,7 @@ __global__ void k_update_fix(Ctrl *ctrl, int m, double *__restrict__ T, int ldt,
 }
 
 /* ------------------------------------------------------------------ */
-/* refactorisation: T = -inv(A[R_N, J_B]) by Gauss-Jordan             */
+/* refactorisation: slot maps (the inversion is in refactor.cuh)       */
 /* ------------------------------------------------------------------ */
 
 /* slot maps from head/bind: structural basic positions and non-basic rows in
@@ -1042,291 +1042,7 @@ __global__ void k_build_slots(Ctrl *ctrl, int m, const int *__restrict__ head,
     }
 }
 
-/* M[cs, b] = A[row_cs, j_b]; M shares storage with T (column b contiguous) */
-__global__ void k_build_kernel_matrix(Ctrl *ctrl, int m, double *__restrict__ T, int ldt,
-                                      const int *__restrict__ a_ptr, const int *__restrict__ a_ind,
-                                      const double *__restrict__ a_val, const int *__restrict__ head,
-                                      const int *__restrict__ slot_pos, const int *__restrict__ cslot)
-{
-    const int k = ctrl->k;
-    const int b = blockIdx.x;
-    if (b >= k) return;
-    double *col = T + (size_t)b * ldt;
-    for (int cs = threadIdx.x; cs < k; cs += blockDim.x) col[cs] = 0.0;
-    __syncthreads();
-    const int j = head[slot_pos[b]] - m;
-    double mx = 0.0;
-    for (int ptr = a_ptr[j] + threadIdx.x; ptr < a_ptr[j + 1]; ptr += blockDim.x) {
-        int cs = cslot[a_ind[ptr]];
-        if (cs >= 0) { col[cs] = a_val[ptr]; mx = fmax(mx, fabs(a_val[ptr])); }
-    }
-    if (mx > 0.0) atomic_max_abs(&ctrl->max_a, mx);
-}
-
-/* Gauss-Jordan step t, part 1 (one block): partial pivoting in column t over
-   rows >= t, row swap, save the pivot column and the scaled pivot row */
-__global__ void k_gj_pivot(Ctrl *ctrl, int t, double *__restrict__ X, int ldt,
-                           int *__restrict__ piv, double *__restrict__ rowt,
-                           double *__restrict__ colt)
-{
-    if (ctrl->sing) return;
-    const int k = ctrl->k;
-    if (t >= k) return;
-    const int tid = threadIdx.x, nt = blockDim.x;
-    double *ct = X + (size_t)t * ldt;
-    Key none = {-1.0, 0.0, 0.0, INT_MAX, 0};
-    Key v = none;
-    for (int i = t + tid; i < k; i += nt) {
-        Key c = {fabs(ct[i]), 0.0, 0.0, i, 0};
-        CombArgMax()(v, c);
-    }
-    v = block_reduce(v, none, CombArgMax());
-    __shared__ int s_r;
-    __shared__ double s_pv;
-    if (tid == 0) {
-        s_r = v.pos;
-        piv[t] = v.pos;
-        if (!(v.a > 1e-13 * fmax(ctrl->max_a, 1e-300))) { ctrl->sing = 1; s_r = -1; }
-    }
-    __syncthreads();
-    const int r = s_r;
-    if (r < 0) return;
-    if (r != t) {
-        for (int c = tid; c < k; c += nt) {
-            double *pc = X + (size_t)c * ldt;
-            double a = pc[t], b = pc[r];
-            pc[t] = b; pc[r] = a;
-        }
-    }
-    __syncthreads();
-    if (tid == 0) s_pv = ct[t];
-    __syncthreads();
-    const double ipv = 1.0 / s_pv;
-    for (int i = tid; i < k; i += nt) colt[i] = ct[i];
-    for (int c = tid; c < k; c += nt) rowt[c] = (c == t) ? ipv : X[(size_t)c * ldt + t] * ipv;
-}
-
-/* Gauss-Jordan step t, part 2 (grid): in-place elimination */
-__global__ void k_gj_update(Ctrl *ctrl, int t, double *__restrict__ X, int ldt,
-                            const double *__restrict__ rowt, const double *__restrict__ colt)
-{
-    if (ctrl->sing) return;
-    const int k = ctrl->k;
-    const int i = blockIdx.x * UPD_TB + threadIdx.x;
-    const int c0 = blockIdx.y * UPD_TC;
-    if (c0 >= k) return;
-    __shared__ double rs[UPD_TC];
-    const int cn = min(UPD_TC, k - c0);
-    if ((int)threadIdx.x < cn) rs[threadIdx.x] = rowt[c0 + threadIdx.x];
-    __syncthreads();
-    if (i >= k) return;
-    const double f = colt[i];
-    double *col = X + (size_t)c0 * ldt + i;
-    for (int c = 0; c < cn; c++) {
-        const int cc = c0 + c;
-        double *e = col + (size_t)c * ldt;
-        if (i == t) *e = rs[c];
-        else if (cc == t) *e = -f * rs[c];
-        else *e -= f * rs[c];
-    }
-}
-
-/* ---- blocked Gauss-Jordan: GJ_NB pivots per round, three launches ----------
-   Round over panel columns [c0, c0+nb):
-   1. k_bgj_panel (one CTA): the nb Gauss-Jordan steps (partial pivoting, row
-      swaps, elimination) restricted to the panel columns.  Afterwards the
-      panel holds its final in-place values Pf = G E_P, G = G_nb ... G_1.
-   2. k_bgj_swap: the same row swaps on every other column, and a copy of
-      their pivot-row entries  Xp[t, c] = X[c0+t, c].
-   3. k_bgj_update: G x = x_notP + Pf x_P for every other column, i.e. a
-      rank-nb update  X[i,c] = (i in P ? 0 : X[i,c]) + sum_t Pf[i,t] Xp[t,c].
-   Memory traffic per round is one read+write of X instead of nb of them. */
-#define GJ_NB 32
-
-__global__ void k_bgj_panel(Ctrl *ctrl, int c0, double *__restrict__ X, int ldt,
-                            int *__restrict__ piv, double *__restrict__ rowt,
-                            double *__restrict__ colt)
-{
-    if (ctrl->sing) return;
-    const int k = ctrl->k;
-    if (c0 >= k) return;
-    const int nb = min(GJ_NB, k - c0);
-    const int tid = threadIdx.x, nt = blockDim.x;
-    __shared__ int s_r;
-    __shared__ double s_ipv;
-    __shared__ double s_row[GJ_NB];
-    for (int t = c0; t < c0 + nb; t++) {
-        double *ct = X + (size_t)t * ldt;
-        Key none = {-1.0, 0.0, 0.0, INT_MAX, 0};
-        Key v = none;
-        for (int i = t + tid; i < k; i += nt) {
-            Key c = {fabs(ct[i]), 0.0, 0.0, i, 0};
-            CombArgMax()(v, c);
-        }
-        v = block_reduce(v, none, CombArgMax());
-        if (tid == 0) {
-            s_r = v.pos;
-            piv[t] = v.pos;
-            if (!(v.a > 1e-13 * fmax(ctrl->max_a, 1e-300))) { ctrl->sing = 1; s_r = -1; }
-        }
-        __syncthreads();
-        const int r = s_r;
-        if (r < 0) return;
-        if (r != t && tid < nb) {
-            double *pc = X + (size_t)(c0 + tid) * ldt;
-            double a = pc[t], b = pc[r];
-            pc[t] = b; pc[r] = a;
-        }
-        __syncthreads();
-        if (tid == 0) s_ipv = 1.0 / ct[t];
-        __syncthreads();
-        const double ipv = s_ipv;
-        if (tid < nb) {
-            int c = c0 + tid;
-            s_row[tid] = (c == t) ? ipv : X[(size_t)c * ldt + t] * ipv;
-        }
-        for (int i = tid; i < k; i += nt) colt[i] = ct[i];
-        __syncthreads();
-        for (int e = tid; e < k * nb; e += nt) {
-            const int i = e % k, cc = e / k, c = c0 + cc;
-            double *x = X + (size_t)c * ldt + i;
-            const double f = colt[i];
-            if (i == t) *x = s_row[cc];
-            else if (c == t) *x = -f * s_row[cc];
-            else *x -= f * s_row[cc];
-        }
-        __syncthreads();
-    }
-}
-
-/* one thread per non-panel column: apply the round's row swaps in order and
-   save the pivot-row entries */
-__global__ void k_bgj_swap(Ctrl *ctrl, int c0, double *__restrict__ X, int ldt,
-                           const int *__restrict__ piv, double *__restrict__ Xp)
-{
-    if (ctrl->sing) return;
-    const int k = ctrl->k;
-    if (c0 >= k) return;
-    const int nb = min(GJ_NB, k - c0);
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= k || (c >= c0 && c < c0 + nb)) return;
-    double *col = X + (size_t)c * ldt;
-    for (int t = 0; t < nb; t++) {
-        int r = piv[c0 + t];
-        if (r != c0 + t) { double a = col[c0 + t]; col[c0 + t] = col[r]; col[r] = a; }
-    }
-    for (int t = 0; t < nb; t++) Xp[(size_t)t * ldt + c] = col[c0 + t];
-}
-
-__global__ void k_bgj_update(Ctrl *ctrl, int c0, double *__restrict__ X, int ldt,
-                             const double *__restrict__ Xp)
-{
-    if (ctrl->sing) return;
-    const int k = ctrl->k;
-    if (c0 >= k) return;
-    const int nb = min(GJ_NB, k - c0);
-    const int i = blockIdx.x * UPD_TB + threadIdx.x;
-    const int cc0 = blockIdx.y * UPD_TC;
-    if (cc0 >= k) return;
-    __shared__ double xs[GJ_NB][UPD_TC];
-    const int cn = min(UPD_TC, k - cc0);
-    for (int e = threadIdx.x; e < GJ_NB * UPD_TC; e += blockDim.x) {
-        int t = e / UPD_TC, c = e % UPD_TC;
-        xs[t][c] = (t < nb && c < cn) ? Xp[(size_t)t * ldt + cc0 + c] : 0.0;
-    }
-    __syncthreads();
-    if (i >= k) return;
-    double pf[GJ_NB];
-#pragma unroll
-    for (int t = 0; t < GJ_NB; t++) pf[t] = (t < nb) ? X[(size_t)(c0 + t) * ldt + i] : 0.0;
-    const bool in_p = (i >= c0 && i < c0 + nb);
-    for (int c = 0; c < cn; c++) {
-        const int col = cc0 + c;
-        if (col >= c0 && col < c0 + nb) continue;     /* panel columns are final */
-        double *x = X + (size_t)col * ldt + i;
-        double acc = in_p ? 0.0 : *x;
-#pragma unroll
-        for (int t = 0; t < GJ_NB; t++) acc += pf[t] * xs[t][c];
-        *x = acc;
-    }
-}
-
-/* undo the row pivoting (column swaps in reverse order) and negate: T = -inv(M).
-   One block; swaps are sequential in t, parallel along the column. */
-__global__ void k_gj_finish(Ctrl *ctrl, double *__restrict__ X, int ldt, const int *__restrict__ piv)
-{
-    if (ctrl->sing) return;
-    const int k = ctrl->k;
-    const int tid = threadIdx.x, nt = blockDim.x;
-    for (int t = k - 1; t >= 0; t--) {
-        int r = piv[t];
-        if (r != t) {
-            double *a = X + (size_t)t * ldt, *b = X + (size_t)r * ldt;
-            for (int i = tid; i < k; i += nt) { double x = a[i]; a[i] = b[i]; b[i] = x; }
-        }
-        __syncthreads();
-    }
-}
-
-__global__ void k_negate(Ctrl *ctrl, double *__restrict__ X, int ldt)
-{
-    if (ctrl->sing) return;
-    const int k = ctrl->k;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const int c = blockIdx.y;
-    if (i < k && c < k) X[(size_t)c * ldt + i] = -X[(size_t)c * ldt + i];
-}
-
-/* whole inversion in one block / shared memory for small kernels (k <= 64):
-   B&B node LPs refactorise at every node, launch count matters there */
-#define GJ_SMALL 64
-__global__ void k_gj_small(Ctrl *ctrl, double *__restrict__ X, int ldt)
-{
-    if (ctrl->sing) return;
-    const int k = ctrl->k;
-    if (k == 0 || k > GJ_SMALL) return;
-    extern __shared__ double sm[];          /* k*k matrix + 2k + perm */
-    double *M = sm;                          /* M[i + c*k] */
-    double *rowt = sm + GJ_SMALL * GJ_SMALL, *colt = rowt + GJ_SMALL;
-    __shared__ int perm[GJ_SMALL];
-    __shared__ int s_r;
-    const int tid = threadIdx.x, nt = blockDim.x;
-    for (int e = tid; e < k * k; e += nt) M[e] = X[(size_t)(e / k) * ldt + (e % k)];
-    __syncthreads();
-    for (int t = 0; t < k; t++) {
-        if (tid == 0) {
-            int r = -1; double best = -1.0;
-            for (int i = t; i < k; i++) { double a = fabs(M[i + t * k]); if (a > best) { best = a; r = i; } }
-            if (!(best > 1e-13 * fmax(ctrl->max_a, 1e-300))) { ctrl->sing = 1; r = -1; }
-            s_r = r; perm[t] = r;
-        }
-        __syncthreads();
-        const int r = s_r;
-        if (r < 0) return;
-        if (r != t)
-            for (int c = tid; c < k; c += nt) { double a = M[t + c * k]; M[t + c * k] = M[r + c * k]; M[r + c * k] = a; }
-        __syncthreads();
-        const double ipv = 1.0 / M[t + t * k];
-        __syncthreads();
-        for (int i = tid; i < k; i += nt) colt[i] = M[i + t * k];
-        for (int c = tid; c < k; c += nt) rowt[c] = (c == t) ? ipv : M[t + c * k] * ipv;
-        __syncthreads();
-        for (int e = tid; e < k * k; e += nt) {
-            int i = e % k, c = e / k;
-            if (i == t) M[e] = rowt[c];
-            else if (c == t) M[e] = -colt[i] * rowt[c];
-            else M[e] -= colt[i] * rowt[c];
-        }
-        __syncthreads();
-    }
-    for (int t = k - 1; t >= 0; t--) {
-        int r = perm[t];
-        if (r != t)
-            for (int i = tid; i < k; i += nt) { double a = M[i + t * k]; M[i + t * k] = M[i + r * k]; M[i + r * k] = a; }
-        __syncthreads();
-    }
-    for (int e = tid; e < k * k; e += nt) X[(size_t)(e / k) * ldt + (e % k)] = -M[e];
-}
+/* (the inversion itself is k_refactor, refactor.cuh) */
 
 /* ------------------------------------------------------------------ */
 /* per-iteration scalar logic and vector updates                      */

@@ -153,7 +153,7 @@ extern "C" void glpb_destroy(glpb_prob *P)
                     P->obj, P->head, P->bind, P->bbar, P->cbar, P->gamma, P->tcol, P->trow, P->rho,
                     P->svec, P->w1, P->w2, P->w3, P->w4, P->w5, P->yk, P->wk, P->yk2, P->zn, P->eng_slots, P->eng_cols, P->eng_fr,
                     P->eng_cyc, P->eng_bytes, P->T, P->T2, P->ref_slots, P->ref_flags, P->partial,
-                    P->rslot, P->slot_pos, P->cslot, P->slot_row, P->gj_piv, P->gj_row, P->gj_col, P->gj_xp,
+                    P->rslot, P->slot_pos, P->cslot, P->slot_row, P->gj_piv, P->gj_row,
                     P->scratch, P->ctrl};
     for (void *p : ptrs) if (p) cudaFree(p);
     P->prof = 0; prof_collect(P);
@@ -187,8 +187,7 @@ static int create_device(glpb_prob *P)
     P->partial_rows = cdiv(P->ldt, GEMV_TILE);
     DA(partial, (size_t)P->partial_rows * P->ldt);
     DA(rslot, m); DA(slot_pos, P->ldt); DA(cslot, m); DA(slot_row, P->ldt);
-    DA(gj_piv, P->ldt); DA(gj_row, P->ldt); DA(gj_col, P->ldt);
-    DA(gj_xp, (size_t)GJ_NB * P->ldt);
+    DA(gj_piv, P->ldt); DA(gj_row, P->ldt);
     DA(scratch, 4096);
     DA(ctrl, 1);
 #undef DA
@@ -202,10 +201,10 @@ static int create_device(glpb_prob *P)
         CK(cudaDeviceGetAttribute(&P->sm_count, cudaDevAttrMultiProcessorCount, P->device));
         CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, P->device));
         CK(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, P->device));
-        int budget = std::min(smem_max, 200 * 1024) - 24 * 1024;      /* static shared of the engine: ~20 KB */
+        int budget = std::min(smem_max, 200 * 1024) - 42 * 1024;      /* static shared of the engine (~16 KB) + cross-warp sums */
         int dcap = std::max(ENG_DB * 192, std::min(P->ldt, (budget - ENG_LCAP * 4) / 8));   /* >= the staging of eng_flush */
         P->eng_dcap = dcap;
-        P->eng_smem = dcap * 8 + ENG_LCAP * 4;
+        P->eng_smem = dcap * 8 + ENG_LCAP * 4 + 32 * 65 * 8;
         if (!coop || P->sm_count > ENG_MAXG) { glpb_set_error("device lacks cooperative launch"); return GLPB_ENODEV; }
         CK(cudaFuncSetAttribute(k_engine_primal, cudaFuncAttributeMaxDynamicSharedMemorySize, P->eng_smem));
         CK(cudaFuncSetAttribute(k_engine_dual, cudaFuncAttributeMaxDynamicSharedMemorySize, P->eng_smem));
