@@ -846,44 +846,70 @@ __device__ void eng_defer_apply(const EngCtx &X, const EngArgs &A, const EngChan
     }
 }
 
+/* fp64 tensor-core tile product: D(8x8) = A(8x4) B(4x8) + C.  Fragment layout of
+   mma.m8n8k4.f64: a = A[lane/4][lane%4], b = B[lane%4][lane/4],
+   c0,c1 = C[lane/4][2*(lane%4) + {0,1}]. */
+__device__ __forceinline__ void eng_dmma(double &c0, double &c1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
 /* T += sum_{j<nd} Fd_j Rd_j' over the k x k kernel: one read+write of T for up
-   to ENG_DB basis changes.  Tiles of 128 rows x 64 columns, the terms staged in
-   shared memory (needs 6144 doubles of dynamic shared memory). */
+   to ENG_DB basis changes -- the one dense contraction of the iteration loop, so
+   it runs on the fp64 tensor cores (DMMA m8n8k4).  Tiles of 128 rows x 64
+   columns; the terms are staged in shared memory with row strides 132 / 68 that
+   keep the fragment loads bank-conflict free; every warp owns one 8-row block and
+   four 8-column blocks of the tile.  Needs ENG_FLUSH_SMEM doubles of dynamic
+   shared memory. */
+#define ENG_FS 132
+#define ENG_RS 68
+#define ENG_FLUSH_SMEM (ENG_DB * (ENG_FS + ENG_RS))
 __device__ void eng_flush(const EngCtx &X, const EngArgs &A, int k, int nd)
 {
     if (nd <= 0 || k <= 0) return;
     const size_t ldt = (size_t)A.ldt;
-    double *Fs = X.sh_d;                 /* [ENG_DB][128] */
-    double *Rs = X.sh_d + ENG_DB * 128;  /* [ENG_DB][64]  */
-    const int r = X.tid & 127, cg = X.tid >> 7;
+    double *Fs = X.sh_d;                    /* [ENG_DB][ENG_FS]: Fs[j][r] = Fd_j[i0 + r] */
+    double *Rs = X.sh_d + ENG_DB * ENG_FS;  /* [ENG_DB][ENG_RS]: Rs[j][c] = Rd_j[c0 + c] */
+    const int g = X.lane >> 2, t = X.lane & 3;
+    const int rbk = X.warp & 15, cq = X.warp >> 4;           /* row block, column half of the tile */
     const int nrt = (k + 127) >> 7, nct = (k + 63) >> 6;
+    const int ksteps = (nd + 3) >> 2;
     for (int u = X.cta; u < nrt * nct; u += X.G) {
         const int i0 = (u / nct) << 7, c0 = (u % nct) << 6;
         __syncthreads();
         for (int e = X.tid; e < ENG_DB * 128; e += ENG_NT) {
-            const int j = e >> 7, i = i0 + (e & 127);
-            Fs[e] = (j < nd && i < k) ? A.Fd[(size_t)j * ldt + i] : 0.0;
+            const int j = e >> 7, r = e & 127, i = i0 + r;
+            Fs[j * ENG_FS + r] = (j < nd && i < k) ? A.Fd[(size_t)j * ldt + i] : 0.0;
         }
         for (int e = X.tid; e < ENG_DB * 64; e += ENG_NT) {
-            const int j = e >> 6, c = c0 + (e & 63);
-            Rs[e] = (j < nd && c < k) ? A.Rd[(size_t)j * ldt + c] : 0.0;
+            const int j = e >> 6, c = e & 63, cc = c0 + c;
+            Rs[j * ENG_RS + c] = (j < nd && cc < k) ? A.Rd[(size_t)j * ldt + cc] : 0.0;
         }
         __syncthreads();
-        const int i = i0 + r;
-        if (i < k) {
-            double acc[8];
-            double *tp = A.T + (size_t)(c0 + cg * 8) * ldt + i;
+        const int row = i0 + rbk * 8 + g;
+        double acc[4][2];
+        double *tp[4];
 #pragma unroll
-            for (int x = 0; x < 8; x++) acc[x] = (c0 + cg * 8 + x < k) ? __ldcg(tp + (size_t)x * ldt) : 0.0;
-            for (int j = 0; j < nd; j++) {
-                const double f = Fs[j * 128 + r];
-                const double *rr = Rs + j * 64 + cg * 8;
+        for (int x = 0; x < 4; x++) {
+            const int col = c0 + (cq * 4 + x) * 8 + 2 * t;
+            tp[x] = A.T + (size_t)col * ldt + row;
+            acc[x][0] = (row < k && col < k) ? __ldcg(tp[x]) : 0.0;
+            acc[x][1] = (row < k && col + 1 < k) ? __ldcg(tp[x] + ldt) : 0.0;
+        }
+        for (int kk = 0; kk < ksteps; kk++) {
+            const double a = Fs[(4 * kk + t) * ENG_FS + rbk * 8 + g];
 #pragma unroll
-                for (int x = 0; x < 8; x++) acc[x] += f * rr[x];
+            for (int x = 0; x < 4; x++) {
+                const double b = Rs[(4 * kk + t) * ENG_RS + (cq * 4 + x) * 8 + g];
+                eng_dmma(acc[x][0], acc[x][1], a, b);
             }
+        }
 #pragma unroll
-            for (int x = 0; x < 8; x++)
-                if (c0 + cg * 8 + x < k) tp[(size_t)x * ldt] = acc[x];
+        for (int x = 0; x < 4; x++) {
+            const int col = c0 + (cq * 4 + x) * 8 + 2 * t;
+            if (row < k && col < k) tp[x][0] = acc[x][0];
+            if (row < k && col + 1 < k) tp[x][ldt] = acc[x][1];
         }
     }
     __syncthreads();

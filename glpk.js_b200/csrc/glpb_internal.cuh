@@ -156,6 +156,9 @@ struct glpb_prob {
     Key *scratch = nullptr;           /* block partials of reductions */
     Ctrl *ctrl = nullptr;             /* device */
     Ctrl *h_ctrl = nullptr;           /* pinned host mirror */
+    unsigned char *h_stage = nullptr; /* pinned staging for the per-solve uploads / read-backs */
+    size_t stage_bytes = 0;
+    int k_host = 0;                   /* kernel size as of the last read-back of ctrl */
     double zeta = 1.0;
     /* ---- counters ---- */
     long n_iter = 0, n_refac = 0, n_launch = 0, n_sync = 0, n_update = 0;

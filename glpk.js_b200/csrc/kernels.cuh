@@ -1383,7 +1383,7 @@ __global__ void k_primal_check(Ctrl *ctrl, int m, int mode, int phase, const int
 __global__ void k_dual_check(Ctrl *ctrl, int m, int n, int mode, const int *__restrict__ head,
                              const signed char *__restrict__ orig_type,
                              const signed char *__restrict__ stat, const double *__restrict__ cbar,
-                             double tol_dj)
+                             double tol_dj, int to_cnt = 0)
 {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
@@ -1398,11 +1398,11 @@ __global__ void k_dual_check(Ctrl *ctrl, int m, int n, int mode, const int *__re
         if (d < -tol_dj) bad = (s == GLP_NL || s == GLP_NF);
         if (d > +tol_dj) bad = bad || (s == GLP_NU || s == GLP_NF);
     }
-    if (bad) ctrl->flag = 1;
+    if (bad) { if (to_cnt) ctrl->cnt = 1; else ctrl->flag = 1; }
 }
 
 /* dual set_aux_bnds (:1317-1359, aux = 1) / set_orig_bnds (:1361-1408, aux = 0) */
-__global__ void k_dual_set_bnds(int m, int n, int aux, const int *__restrict__ head,
+__global__ void k_dual_set_bnds(const Ctrl *ctrl, int m, int n, int aux, const int *__restrict__ head,
                                 const int *__restrict__ bind,
                                 const signed char *__restrict__ orig_type,
                                 const double *__restrict__ orig_lb, const double *__restrict__ orig_ub,
@@ -1412,6 +1412,7 @@ __global__ void k_dual_set_bnds(int m, int n, int aux, const int *__restrict__ h
 {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= m + n) return;
+    if (aux < 0) aux = ctrl->flag;      /* phase decided on the device by the preceding k_dual_check(mode 1) */
     int t;
     double l, u;
     if (aux) {
@@ -1481,6 +1482,57 @@ __global__ void k_unit(Ctrl *ctrl, int m, double *__restrict__ e)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < m) e[i] = (i == ctrl->p) ? 1.0 : 0.0;
+}
+
+/* Batched glp_eval_tab_row (lib/glpapi12.js:401-453) for branch-and-bound: CTA f
+   evaluates the simplex-table row of the basic variable at position pos[f]:
+   rho_f = row pos[f] of inv(B) (the reference form of k_rho), then
+   trow_f[j] = -rho_f' N_j for every non-basic non-fixed column (k_trow).
+   One launch and one read-back for all fractional variables of a node instead
+   of one round trip each. */
+__global__ void k_tab_rows(const Ctrl *ctrl, int m, int n, const int *__restrict__ pos,
+                           const double *__restrict__ T, int ldt,
+                           const int *__restrict__ a_ptr, const int *__restrict__ a_ind,
+                           const double *__restrict__ a_val, const int *__restrict__ at_ptr,
+                           const int *__restrict__ at_ind, const double *__restrict__ at_val,
+                           const int *__restrict__ head, const int *__restrict__ bind,
+                           const signed char *__restrict__ stat, const int *__restrict__ rslot,
+                           const int *__restrict__ cslot, double *__restrict__ rho_b,
+                           double *__restrict__ trow_b)
+{
+    const int f = blockIdx.x;
+    const int p = pos[f];
+    const int kp = head[p];
+    double *rho = rho_b + (size_t)f * m;
+    double *trow = trow_b + (size_t)f * n;
+    for (int r = threadIdx.x; r < m; r += blockDim.x) {
+        const int cs = cslot[r];
+        double v;
+        if (cs < 0) v = (bind[r] == p) ? 1.0 : 0.0;
+        else {
+            const double *col = T + (size_t)cs * ldt;
+            if (kp >= m) v = col[rslot[p]];
+            else {
+                v = 0.0;
+                for (int ptr = at_ptr[kp]; ptr < at_ptr[kp + 1]; ptr++) {
+                    const int pb = bind[m + at_ind[ptr]];
+                    if (pb < m) v += at_val[ptr] * col[rslot[pb]];
+                }
+            }
+        }
+        rho[r] = v;
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < n; j += blockDim.x) {
+        double t = 0.0;
+        if (stat[j] != GLP_NS) {
+            const int k = head[m + j];
+            if (k < m) t = -rho[k];
+            else
+                for (int ptr = a_ptr[k - m]; ptr < a_ptr[k - m + 1]; ptr++) t += rho[a_ind[ptr]] * a_val[ptr];
+        }
+        trow[j] = t;
+    }
 }
 
 /* seeds the device-resident loop state before a batch of iterations */

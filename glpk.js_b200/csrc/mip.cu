@@ -60,6 +60,18 @@ struct glpb_mip {
     bool have_cut = false;      /* P->mip_obj is a valid incumbent objective   */
     std::vector<double> trow;   /* host copy of a simplex-table row            */
     std::vector<int> dev_head;
+    /* batched table rows of one node (k_tab_rows) */
+    int *d_tab_pos = nullptr;
+    double *d_tab_rho = nullptr, *d_tab_trow = nullptr;
+    int tab_cap = 0;
+    std::vector<int> tab_js;            /* structural j of every cached row, in order */
+    std::vector<double> tab_rows_h;     /* [rows][n] scaled table rows                */
+    ~glpb_mip()
+    {
+        if (d_tab_pos) cudaFree(d_tab_pos);
+        if (d_tab_rho) cudaFree(d_tab_rho);
+        if (d_tab_trow) cudaFree(d_tab_trow);
+    }
 
     explicit glpb_mip(glpb_prob *P_, const glpb_iocp &pr) : P(P_), parm(pr), m(P_->m), n(P_->n) {}
 
@@ -280,6 +292,59 @@ struct glpb_mip {
         return 0;
     }
 
+    /* table rows of all the structural variables js at once: one launch per chunk of
+       tab_cap rows, one read-back; fills tab_rows_h / dev_head */
+    int tab_rows_batch(const std::vector<int> &js)
+    {
+        tab_js = js;
+        const int F = (int)js.size();
+        tab_rows_h.assign((size_t)F * n, 0.0);
+        if (F == 0) return 0;
+        if (!P->valid) return GLPB_ESTATE;
+        if (!d_tab_pos) {
+            tab_cap = std::max(1, std::min(m, 64));
+            if (cudaMalloc((void **)&d_tab_pos, tab_cap * sizeof(int)) != cudaSuccess ||
+                cudaMalloc((void **)&d_tab_rho, (size_t)tab_cap * m * sizeof(double)) != cudaSuccess ||
+                cudaMalloc((void **)&d_tab_trow, (size_t)tab_cap * n * sizeof(double)) != cudaSuccess) {
+                glpb_set_error("branch-and-bound: device allocation failed");
+                return GLPB_ENOMEM;
+            }
+        }
+        std::vector<int> posof(m + n, -1), pos(F);
+        for (int i = 0; i < m; i++) posof[P->h_head[i] - 1] = i;
+        for (int f = 0; f < F; f++) {
+            pos[f] = posof[m + js[f]];
+            if (pos[f] < 0) return GLPB_ESTATE;
+        }
+        for (int f0 = 0; f0 < F; f0 += tab_cap) {
+            const int fc = std::min(tab_cap, F - f0);
+            CK(cudaMemcpyAsync(d_tab_pos, pos.data() + f0, fc * sizeof(int), cudaMemcpyHostToDevice, P->stream));
+            LAUNCH(P, k_tab_rows, fc, 256, 0, P->ctrl, m, n, d_tab_pos, P->T, P->ldt, P->a_ptr, P->a_ind, P->a_val,
+                   P->at_ptr, P->at_ind, P->at_val, P->head, P->bind, P->stat, P->rslot, P->cslot, d_tab_rho,
+                   d_tab_trow);
+            CK(cudaMemcpyAsync(tab_rows_h.data() + (size_t)f0 * n, d_tab_trow, (size_t)fc * n * sizeof(double),
+                               cudaMemcpyDeviceToHost, P->stream));
+        }
+        CK(cudaMemcpyAsync(dev_head.data(), P->head, (m + n) * sizeof(int), cudaMemcpyDeviceToHost, P->stream));
+        CK(cudaStreamSynchronize(P->stream));
+        P->n_sync++;
+        return 0;
+    }
+
+    /* row f of the batch, un-scaled like tab_row does */
+    void cached_row(int f, std::vector<double> &alfa) const
+    {
+        const int k = m + tab_js[f];
+        const double sb = P->h_sjj[k - m];
+        const double *tr = tab_rows_h.data() + (size_t)f * n;
+        std::fill(alfa.begin(), alfa.end(), 0.0);
+        for (int j = 0; j < n; j++) {
+            const int kk = dev_head[m + j];
+            const double sn = (kk < m) ? 1.0 / P->h_rii[kk] : P->h_sjj[kk - m];
+            alfa[kk] = tr[j] * sb / sn;
+        }
+    }
+
     /* glp_dual_rtest, lib/glpapi12.js:687-762, over all non-basic kk in
        ascending order (the order glp_eval_tab_row lists them); returns kk or -1 */
     int dual_rtest(const std::vector<double> &alfa_row, int dirn, double eps) const
@@ -425,11 +490,16 @@ struct glpb_mip {
         std::vector<double> alfa(m + n);
         int jj = -1;
         double degrad = -1.0, dz_dn = 0, dz_up = 0;
+        /* all the fractional variables' table rows in one device round trip */
+        std::vector<int> js;
+        for (int j = 0; j < n; j++) if (non_int[j]) js.push_back(j);
+        int rcb = tab_rows_batch(js);
+        if (rcb) return rcb;
+        int f = -1;
         for (int j = 0; j < n; j++) {
             if (!non_int[j]) continue;
             double x = P->h_prim[m + j];
-            int rc = tab_row(m + j, alfa);
-            if (rc) return rc;
+            cached_row(++f, alfa);
             for (int kase = -1; kase <= +1; kase += 2) {
                 int kk = dual_rtest(alfa, kase, 1e-9);
                 double delta_z;

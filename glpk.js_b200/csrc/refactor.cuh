@@ -28,6 +28,9 @@
 #define REF_NB 32            /* pivots per round                              */
 #define REF_CB 16            /* columns per update block                      */
 #define REF_RMAX 256         /* distributed panel: max rows per CTA            */
+#define REF_PS 132           /* shared row strides of the DMMA operands        */
+#define REF_XS 36
+#define REF_UPD_SMEM ((REF_NB * (REF_PS + REF_XS)) * sizeof(double))
 
 struct __align__(128) RefSlot {
     double absval;
@@ -395,12 +398,19 @@ __global__ void __launch_bounds__(REF_NT, 1) k_refactor(RefArgs A)
         }
         /* ---- the other columns: row swaps, pivot rows, rank-nb update ---- */
         const int naff = s_naff;
-        const int ncb = (k + REF_CB - 1) / REF_CB;
+        /* blocks of 32 columns; the rank-nb update runs on the fp64 tensor cores (DMMA
+           m8n8k4): tiles of 128 rows x 32 columns, Pf staged with row stride 132 and the
+           pivot rows with stride 36 (bank-conflict-free fragment loads); every warp owns
+           one 8-row block and two 8-column blocks of the tile */
+        double *Pfs = ref_dyn;                     /* [REF_NB][REF_PS]: Pfs[t][r] = X[i0 + r, c0 + t] */
+        double *Rs2 = ref_dyn + REF_NB * REF_PS;   /* [REF_NB][REF_XS]: Rs2[t][c] = X[c0 + t, cc0 + c] after the swaps */
+        const int ncb = (k + 31) / 32;
+        const int ksteps = (nb + 3) >> 2;
         for (int cb = cta; cb < ncb; cb += G) {
-            const int cc0 = cb * REF_CB;
-            {
+            const int cc0 = cb * 32;
+            for (int sblk = 0; sblk < 2; sblk++) {
                 const int a = tid / REF_CB, c = tid % REF_CB;
-                const int col = cc0 + c;
+                const int col = cc0 + sblk * REF_CB + c;
                 const bool act = (a < naff) && (col < k) && !(col >= c0 && col < c0 + nb);
                 double val = 0.0;
                 if (act) val = A.X[(size_t)col * ldt + aff_src[a]];
@@ -408,36 +418,48 @@ __global__ void __launch_bounds__(REF_NT, 1) k_refactor(RefArgs A)
                 if (act && aff_src[a] != aff_row[a]) A.X[(size_t)col * ldt + aff_row[a]] = val;
                 __syncthreads();
             }
-            if (tid < REF_NB * REF_CB) {
-                const int t = tid / REF_CB, c = tid % REF_CB;
+            {
+                const int t = tid >> 5, c = tid & 31;
                 const int col = cc0 + c;
                 const bool act = (t < nb) && (col < k) && !(col >= c0 && col < c0 + nb);
-                xs[t][c] = act ? A.X[(size_t)col * ldt + c0 + t] : 0.0;
+                Rs2[t * REF_XS + c] = act ? A.X[(size_t)col * ldt + c0 + t] : 0.0;
             }
-            __syncthreads();
-            for (int i = tid; i < k; i += REF_NT) {
-                const bool in_p = (i >= c0 && i < c0 + nb);
-                double acc[REF_CB];
+            const int g = X.lane >> 2, t4 = X.lane & 3;
+            const int rbk = X.warp & 15, cq = X.warp >> 4;
+            for (int i0 = 0; i0 < k; i0 += 128) {
+                /* the tile's own entries first: their DRAM latency overlaps the staging of Pf */
+                const int row = i0 + rbk * 8 + g;
+                const bool in_p = (row >= c0 && row < c0 + nb);
+                double acc[2][2];
+                double *tp[2];
+                bool ok[2][2];
 #pragma unroll
-                for (int c = 0; c < REF_CB; c++) {
-                    const int col = cc0 + c;
-                    acc[c] = (col < k && !in_p) ? A.X[(size_t)col * ldt + i] : 0.0;
+                for (int x = 0; x < 2; x++) {
+                    const int col = cc0 + (cq * 2 + x) * 8 + 2 * t4;
+                    tp[x] = A.X + (size_t)col * ldt + row;
+                    ok[x][0] = (row < k) && (col < k) && !(col >= c0 && col < c0 + nb);
+                    ok[x][1] = (row < k) && (col + 1 < k) && !(col + 1 >= c0 && col + 1 < c0 + nb);
+                    acc[x][0] = (ok[x][0] && !in_p) ? __ldcg(tp[x]) : 0.0;
+                    acc[x][1] = (ok[x][1] && !in_p) ? __ldcg(tp[x] + ldt) : 0.0;
                 }
-                for (int t0 = 0; t0 < nb; t0 += 8) {
-                    double pf[8];
+                __syncthreads();
+                for (int e = tid; e < REF_NB * 128; e += REF_NT) {
+                    const int t = e >> 7, r = e & 127;
+                    Pfs[t * REF_PS + r] = (t < nb && i0 + r < k) ? __ldcg(A.X + (size_t)(c0 + t) * ldt + i0 + r) : 0.0;
+                }
+                __syncthreads();
+                for (int kk = 0; kk < ksteps; kk++) {
+                    const double a = Pfs[(4 * kk + t4) * REF_PS + rbk * 8 + g];
 #pragma unroll
-                    for (int x = 0; x < 8; x++)
-                        pf[x] = (t0 + x < nb) ? __ldcg(A.X + (size_t)(c0 + t0 + x) * ldt + i) : 0.0;
-#pragma unroll
-                    for (int x = 0; x < 8; x++) {
-#pragma unroll
-                        for (int c = 0; c < REF_CB; c++) acc[c] += pf[x] * xs[t0 + x][c];
+                    for (int x = 0; x < 2; x++) {
+                        const double b = Rs2[(4 * kk + t4) * REF_XS + (cq * 2 + x) * 8 + g];
+                        eng_dmma(acc[x][0], acc[x][1], a, b);
                     }
                 }
 #pragma unroll
-                for (int c = 0; c < REF_CB; c++) {
-                    const int col = cc0 + c;
-                    if (col < k && !(col >= c0 && col < c0 + nb)) A.X[(size_t)col * ldt + i] = acc[c];
+                for (int x = 0; x < 2; x++) {
+                    if (ok[x][0]) tp[x][0] = acc[x][0];
+                    if (ok[x][1]) tp[x][ldt] = acc[x][1];
                 }
             }
             __syncthreads();

@@ -111,6 +111,7 @@ static int sync_ctrl(glpb_prob *P)
     CK(cudaMemcpyAsync(P->h_ctrl, P->ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, P->stream));
     CK(cudaStreamSynchronize(P->stream));
     P->n_sync++;
+    P->k_host = P->h_ctrl->k;
     return 0;
 }
 
@@ -159,6 +160,7 @@ extern "C" void glpb_destroy(glpb_prob *P)
     P->prof = 0; prof_collect(P);
     if (P->mip) { glpb_mip_free(P->mip); P->mip = nullptr; }
     if (P->h_ctrl) cudaFreeHost(P->h_ctrl);
+    if (P->h_stage) cudaFreeHost(P->h_stage);
     if (P->stream) cudaStreamDestroy(P->stream);
     delete P;
 }
@@ -192,6 +194,10 @@ static int create_device(glpb_prob *P)
     DA(ctrl, 1);
 #undef DA
     CK(cudaMallocHost((void **)&P->h_ctrl, sizeof(Ctrl)));
+    /* pinned staging: bounds/costs [6 x (m+n) doubles + n+1], types [2(m+n)], header [2(m+n) ints + n],
+       and the read-back of head/stat/bbar/cbar; all copies of a solve are asynchronous */
+    P->stage_bytes = (size_t)(6 * (m + n) + n + 1 + m + n) * sizeof(double) + (size_t)4 * (m + n) * sizeof(int) + 4 * (size_t)(m + n) + 256;
+    CK(cudaMallocHost((void **)&P->h_stage, P->stage_bytes));
     CK(cudaMemsetAsync(P->ctrl, 0, sizeof(Ctrl), P->stream));
     CK(cudaMemsetAsync(P->eng_cyc, 0, 32 * sizeof(long long), P->stream));
     CK(cudaMemsetAsync(P->eng_bytes, 0, 24 * sizeof(double), P->stream));
@@ -202,7 +208,7 @@ static int create_device(glpb_prob *P)
         CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, P->device));
         CK(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, P->device));
         int budget = std::min(smem_max, 200 * 1024) - 42 * 1024;      /* static shared of the engine (~16 KB) + cross-warp sums */
-        int dcap = std::max(ENG_DB * 192, std::min(P->ldt, (budget - ENG_LCAP * 4) / 8));   /* >= the staging of eng_flush */
+        int dcap = std::max(ENG_FLUSH_SMEM, std::min(P->ldt, (budget - ENG_LCAP * 4) / 8));   /* >= the staging of eng_flush */
         P->eng_dcap = dcap;
         P->eng_smem = dcap * 8 + ENG_LCAP * 4 + 32 * 65 * 8;
         if (!coop || P->sm_count > ENG_MAXG) { glpb_set_error("device lacks cooperative launch"); return GLPB_ENODEV; }
@@ -477,7 +483,7 @@ static int dev_refactor(Dev &D)
         if (envs == 0 || !nbr) { nbr = REF_NB; single = 0; }
         if (!single) G = std::max(G, cdiv(k, REF_RMAX));
         const int R = single ? k : cdiv(k, G);
-        const size_t smem = std::max((size_t)R * (nbr + 2) * sizeof(double) + 64, (size_t)2 * k * sizeof(int));
+        const size_t smem = std::max({(size_t)R * (nbr + 2) * sizeof(double) + 64, (size_t)2 * k * sizeof(int), (size_t)REF_UPD_SMEM});
         if (G > P->sm_count || smem > REF_SMEM_MAX) {
             glpb_set_error("refactorisation: kernel of size %d does not fit the device", k);
             return GLPB_ENOMEM;
@@ -507,11 +513,30 @@ static int dev_refactor(Dev &D)
 }
 
 /* upload the basis header in init_csa order (lib/glpspx01.js:107-129) */
+/* carve typed arrays out of the pinned staging buffer */
+struct Stage {
+    unsigned char *p;
+    explicit Stage(glpb_prob *P, size_t off) : p(P->h_stage + off) {}
+    template <class T> T *take(size_t count)
+    {
+        size_t a = (size_t)p & 7;
+        if (a) p += 8 - a;
+        T *r = (T *)p;
+        p += count * sizeof(T);
+        return r;
+    }
+};
+/* staging layout: [header | bounds]; the two halves are filled by different calls */
+static size_t stage_off_bounds(const glpb_prob *P) { return (size_t)2 * (P->m + P->n) * sizeof(int) + P->n + 64; }
+
 static int upload_basis(glpb_prob *P)
 {
     const int m = P->m, n = P->n;
-    std::vector<int> head(m + n), bind(m + n);
-    std::vector<signed char> stat(n);
+    /* every entry point leaves the stream idle, and the two staging regions are filled
+       at most once per device synchronisation: no copy is in flight from this memory */
+    Stage S(P, 0);
+    int *head = S.take<int>(m + n), *bind = S.take<int>(m + n);
+    signed char *stat = S.take<signed char>(n);
     for (int i = 0; i < m; i++) head[i] = P->h_head[i] - 1;
     int kk = 0;
     for (int k = 0; k < m + n; k++)
@@ -522,10 +547,9 @@ static int upload_basis(glpb_prob *P)
     if (kk != n) return GLP_EBADB;
     for (int t = 0; t < m + n; t++) bind[head[t]] = t;
     int rc;
-    if ((rc = h2d(P, P->head, head.data(), m + n))) return rc;
-    if ((rc = h2d(P, P->bind, bind.data(), m + n))) return rc;
-    if ((rc = h2d(P, P->stat, stat.data(), n))) return rc;
-    CK(cudaStreamSynchronize(P->stream));
+    if ((rc = h2d(P, P->head, head, m + n))) return rc;
+    if ((rc = h2d(P, P->bind, bind, m + n))) return rc;
+    if ((rc = h2d(P, P->stat, stat, n))) return rc;
     return 0;
 }
 
@@ -557,11 +581,14 @@ extern "C" int glpb_factorize(glpb_prob *P)
 static int upload_bounds(glpb_prob *P, bool dual)
 {
     const int m = P->m, n = P->n;
-    std::vector<signed char> type(m + n);
-    std::vector<double> lb(m + n), ub(m + n), coef(m + n, 0.0), obj(n + 1);
+    Stage S(P, stage_off_bounds(P));
+    double *lb = S.take<double>(m + n), *ub = S.take<double>(m + n), *coef = S.take<double>(m + n);
+    double *obj = S.take<double>(n + 1);
+    signed char *type = S.take<signed char>(m + n);
     for (int i = 0; i < m; i++) {
         type[i] = (signed char)P->h_type[i];
         lb[i] = P->h_lb[i] * P->h_rii[i]; ub[i] = P->h_ub[i] * P->h_rii[i];
+        coef[i] = 0.0;
     }
     double cmax = 0.0;
     obj[0] = P->c0;
@@ -577,16 +604,15 @@ static int upload_bounds(glpb_prob *P, bool dual)
     if (fabs(P->zeta) < 1.0) P->zeta *= 1000.0;
     if (dual) for (int j = 0; j < n; j++) coef[m + j] *= P->zeta; /* lib/glpspx02.js:148 */
     int rc;
-    if ((rc = h2d(P, P->type, type.data(), m + n))) return rc;
-    if ((rc = h2d(P, P->lb, lb.data(), m + n))) return rc;
-    if ((rc = h2d(P, P->ub, ub.data(), m + n))) return rc;
-    if ((rc = h2d(P, P->orig_type, type.data(), m + n))) return rc;
-    if ((rc = h2d(P, P->orig_lb, lb.data(), m + n))) return rc;
-    if ((rc = h2d(P, P->orig_ub, ub.data(), m + n))) return rc;
-    if ((rc = h2d(P, P->coef, coef.data(), m + n))) return rc;
-    if ((rc = h2d(P, P->obj, obj.data(), n + 1))) return rc;
+    if ((rc = h2d(P, P->type, type, m + n))) return rc;
+    if ((rc = h2d(P, P->lb, lb, m + n))) return rc;
+    if ((rc = h2d(P, P->ub, ub, m + n))) return rc;
+    if ((rc = h2d(P, P->orig_type, type, m + n))) return rc;
+    if ((rc = h2d(P, P->orig_lb, lb, m + n))) return rc;
+    if ((rc = h2d(P, P->orig_ub, ub, m + n))) return rc;
+    if ((rc = h2d(P, P->coef, coef, m + n))) return rc;
+    if ((rc = h2d(P, P->obj, obj, n + 1))) return rc;
     CK(cudaMemsetAsync(P->refsp, 0, m + n, P->stream));
-    CK(cudaStreamSynchronize(P->stream));
     return 0;
 }
 
@@ -595,13 +621,14 @@ static int upload_bounds(glpb_prob *P, bool dual)
 static int store_sol(glpb_prob *P, int p_stat, int d_stat, int ray, int it_cnt)
 {
     const int m = P->m, n = P->n;
-    std::vector<int> head(m + n);
-    std::vector<signed char> stat(n);
-    std::vector<double> bbar(m), cbar(n);
-    CK(cudaMemcpyAsync(head.data(), P->head, (m + n) * sizeof(int), cudaMemcpyDeviceToHost, P->stream));
-    CK(cudaMemcpyAsync(stat.data(), P->stat, n, cudaMemcpyDeviceToHost, P->stream));
-    CK(cudaMemcpyAsync(bbar.data(), P->bbar, m * sizeof(double), cudaMemcpyDeviceToHost, P->stream));
-    CK(cudaMemcpyAsync(cbar.data(), P->cbar, n * sizeof(double), cudaMemcpyDeviceToHost, P->stream));
+    Stage S(P, 0);                /* the uploads of this solve completed long ago */
+    int *head = S.take<int>(m + n);
+    double *bbar = S.take<double>(m), *cbar = S.take<double>(n);
+    signed char *stat = S.take<signed char>(n);
+    CK(cudaMemcpyAsync(head, P->head, (m + n) * sizeof(int), cudaMemcpyDeviceToHost, P->stream));
+    CK(cudaMemcpyAsync(stat, P->stat, n, cudaMemcpyDeviceToHost, P->stream));
+    CK(cudaMemcpyAsync(bbar, P->bbar, m * sizeof(double), cudaMemcpyDeviceToHost, P->stream));
+    CK(cudaMemcpyAsync(cbar, P->cbar, n * sizeof(double), cudaMemcpyDeviceToHost, P->stream));
     CK(cudaStreamSynchronize(P->stream));
     P->n_sync++;
     P->valid = 1;
@@ -745,7 +772,7 @@ struct Loop : Dev {
         static const int env_defer = getenv("GLPB_DEFER") ? atoi(getenv("GLPB_DEFER")) : 1;
         static const int env_local = getenv("GLPB_LOCAL_MAX") ? atoi(getenv("GLPB_LOCAL_MAX")) : ENG_LOCAL_MAX;
         A.Fd = P->eng_fr; A.Rd = P->eng_fr + (size_t)ENG_DB * P->ldt; A.zbuf = P->eng_fr + 2 * (size_t)ENG_DB * P->ldt;
-        A.defer = (env_defer && dual && P->eng_dcap >= ENG_DB * 192) ? 1 : 0;
+        A.defer = (env_defer && dual && P->eng_dcap >= ENG_FLUSH_SMEM) ? 1 : 0;
         A.local_max = env_local;
         A.prof_cyc = P->prof ? P->eng_cyc + (dual ? 12 : 0) : nullptr;
         A.prof_bytes = P->prof ? P->eng_bytes + (dual ? 12 : 0) : nullptr;
@@ -929,10 +956,7 @@ struct Primal : Loop {
         const int pse = (parm.pricing == GLP_PT_PSE);
         if ((rc = upload_bounds(P, false))) return rc;
         if ((rc = upload_basis(P))) return rc;
-        {   /* T and its slot maps survive between calls; k is read back once */
-            if ((rc = sync_ctrl(P))) return rc;
-            k = P->h_ctrl->k;
-        }
+        k = P->k_host;      /* T and its slot maps survive between calls */
         P->valid = 0;
         it_beg = it_cnt = P->it_cnt;
         tm_beg = now_ms();
@@ -1096,7 +1120,7 @@ struct Dual : Loop {
 
     void set_bnds(int aux)
     {
-        LAUNCH(P, k_dual_set_bnds, cdiv(m + n, 256), 256, 0, m, n, aux, P->head, P->bind, P->orig_type,
+        LAUNCH(P, k_dual_set_bnds, cdiv(m + n, 256), 256, 0, P->ctrl, m, n, aux, P->head, P->bind, P->orig_type,
                P->orig_lb, P->orig_ub, P->type, P->lb, P->ub, P->stat, P->cbar);
     }
 
@@ -1122,8 +1146,7 @@ struct Dual : Loop {
         double obj_track = 0.0;
         if ((rc = upload_bounds(P, true))) return rc;
         if ((rc = upload_basis(P))) return rc;
-        if ((rc = sync_ctrl(P))) return rc;
-        k = P->h_ctrl->k;
+        k = P->k_host;
         P->valid = 0;
         it_beg = it_cnt = P->it_cnt;
         tm_beg = now_ms();
@@ -1137,6 +1160,34 @@ struct Dual : Loop {
                 if (rc != 0) return spx_fail(P, it_cnt);
                 binv_st = 1;
                 bbar_st = cbar_st = 0;
+            }
+            if (cbar_st == 0 && phase == 0) {
+                /* start of a solve: phase decision, stability check, bbar and the objective
+                   are enqueued as a whole (the device selects the bounds from its own
+                   feasibility flag) and read back with ONE synchronisation */
+                clear_ctrl();
+                eval_cbar();
+                cbar_st = 1;
+                LAUNCH(P, k_dual_check, cdiv(n, 256), 256, 0, P->ctrl, m, n, 1, P->head, P->orig_type, P->stat,
+                       P->cbar, 0.90 * parm.tol_dj, 0);
+                set_bnds(-1);
+                LAUNCH(P, k_dual_check, cdiv(n, 256), 256, 0, P->ctrl, m, n, 0, P->head, P->orig_type, P->stat,
+                       P->cbar, parm.tol_dj, 1);
+                eval_bbar();
+                eval_obj();
+                if ((rc = sync_ctrl(P))) return rc;
+                phase = P->h_ctrl->flag ? 1 : 2;
+                refct = 0;
+                if (P->h_ctrl->cnt) {
+                    if (parm.meth == GLP_DUALP) {
+                        rc = store_sol(P, GLP_UNDEF, GLP_UNDEF, 0, it_cnt);
+                        return rc ? rc : GLP_EFAIL;
+                    }
+                    phase = 0; binv_st = 0; rigorous = 5;
+                    continue;
+                }
+                bbar_st = 1;
+                if (phase == 2) obj_track = P->h_ctrl->obj;
             }
             if (cbar_st == 0) {
                 clear_ctrl();
