@@ -201,7 +201,9 @@ def run_bnb(args, w, rank, local_rank, world):
     torch.cuda.set_device(local_rank)
     d = nat.generate(w["gen"], **w["kw"])
     node_lim = w["node_lim"]
-    comm = bnb.TorchComm() if world > 1 else bnb.LocalGroup(1).comm(0)
+    W = max(1, args.bnb_workers)          # worker threads (device handles) per GPU
+    outer = bnb.TorchComm() if world > 1 else None
+    import threading
 
     def barrier():
         torch.cuda.synchronize()
@@ -212,21 +214,38 @@ def run_bnb(args, w, rank, local_rank, world):
     sampler = ClockSampler(local_rank)
     times, nodes, objs = [], [], []
     for s in range(args.warmup + args.steps):
-        P = nat.Problem(d, device=local_rank)          # host buffers -> device every step (e2e == value here)
-        assert P.simplex(meth=nat.GLP_PRIMAL) == 0     # root LP, as solve_mip requires (lib/glpapi09.js:67-72)
+        probs = []
+        for _ in range(W):                              # host buffers -> device every step (e2e == value here)
+            P = nat.Problem(d, device=local_rank)
+            assert P.simplex(meth=nat.GLP_PRIMAL) == 0  # root LP, as solve_mip requires (lib/glpapi09.js:67-72)
+            probs.append(P)
         if s == args.warmup:
             sampler.start()
+        group = bnb.LocalGroup(W)
+        results = [None] * W
+
+        def work(r):
+            torch.cuda.set_device(local_rank)
+            comm = bnb.HybridComm(group, r, outer)
+            results[r] = bnb.sharded_intopt(bnb.Worker(probs[r]), comm, minimize=(d["dir"] == nat.GLP_MIN),
+                                            node_lim=node_lim, msg_lev=0)
+
         barrier()
         t0 = time.perf_counter()
-        res = bnb.sharded_intopt(bnb.Worker(P), comm,
-                                 minimize=(d["dir"] == nat.GLP_MIN), node_lim=node_lim, msg_lev=0)
+        threads = [threading.Thread(target=work, args=(r,)) for r in range(1, W)]
+        for t in threads:
+            t.start()
+        work(0)
+        for t in threads:
+            t.join()
         barrier()
         dt = time.perf_counter() - t0
-        P.close()
+        for P in probs:
+            P.close()
         if s >= args.warmup:
             times.append(dt)
-            nodes.append(res["total_nodes"])
-            objs.append(res["obj"])
+            nodes.append(results[0]["total_nodes"])
+            objs.append(results[0]["obj"])
     clocks = sampler.stop()
     my = float(sum(times))
     if world > 1:
@@ -249,8 +268,9 @@ def run_bnb(args, w, rank, local_rank, world):
         line = {"metric": "bnb_nodes_per_sec", "value": value, "unit": "nodes/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": 1000.0 * my / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": w["name"], **w["kw"], "node_lim_per_rank": node_lim,
-                           "parallelism": "nodes sharded over %d rank(s)" % world},
+                "config": {"workload": w["name"], **w["kw"], "node_lim_per_worker": node_lim,
+                           "workers_per_gpu": W,
+                           "parallelism": "nodes sharded over %d GPU(s) x %d worker handles" % (world, W)},
                 "clocks": clocks, "e2e": {"value": value, "unit": "nodes/s", "h2d_bytes_per_step": int(sum(
                     a.nbytes for a in d.values() if isinstance(a, np.ndarray))), "d2h_bytes_per_step": 8 * (d["m"] + d["n"])},
                 "gpu_launches": None, "roofline": None, "cpu_baseline": cpu, "incumbent": objs[-1] if objs else None}
@@ -271,6 +291,7 @@ def main():
     ap.add_argument("--no-c3", action="store_true", help="skip the extra full solve of the 16384x32768 LP")
     ap.add_argument("--c3-mid", type=int, default=60000, help="iteration at which the C3 solve is split for the CPU sample")
     ap.add_argument("--c3-cpu-mid-lim", type=int, default=100)
+    ap.add_argument("--bnb-workers", type=int, default=8, help="mkp workload: B&B worker handles (threads) per GPU")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))

@@ -226,3 +226,51 @@ class _LocalComm:
         b = np.zeros(nbytes, np.uint8)
         b[:len(buf)] = buf
         return self._exchange(b)
+
+
+class HybridComm:
+    """W worker threads per process (each with its own device handle on the SAME
+    GPU: node LPs of the C4/C5 sizes occupy one SM, so several run concurrently)
+    times P processes (one per GPU, ``torch.distributed``).  Global rank =
+    process rank * W + worker.  Collectives run in two levels: the workers of a
+    process meet in a ``LocalGroup``; worker 0 alone talks to the other
+    processes."""
+
+    def __init__(self, group, local_rank, outer=None):
+        self.g, self.lr, self.outer = group, local_rank, outer
+        self.local = group.comm(local_rank)
+        self.W = group.world
+        self.P = outer.world if outer is not None else 1
+        self.pr = outer.rank if outer is not None else 0
+        self.rank, self.world = self.pr * self.W + local_rank, self.P * self.W
+
+    def allreduce(self, value, op):
+        red = {"min": min, "max": max, "sum": sum}[op]
+        part = red(self.local._exchange(value))
+        if self.outer is None:
+            return part
+        res = self.outer.allreduce(part, op) if self.lr == 0 else None
+        return self.local._exchange(res)[0]
+
+    def allgather_ints(self, values):
+        loc = self.local._exchange(list(values))               # [W][len]
+        if self.outer is None:
+            return loc
+        flat = None
+        if self.lr == 0:
+            got = self.outer.allgather_ints([v for row in loc for v in row])   # [P][W*len]
+            n = len(values)
+            flat = [row[i * n:(i + 1) * n] for row in got for i in range(self.W)]
+        return self.local._exchange(flat)[0]
+
+    def allgather_bytes(self, buf, nbytes):
+        b = np.zeros(nbytes, np.uint8)
+        b[:len(buf)] = buf
+        loc = self.local._exchange(b)                          # [W] arrays
+        if self.outer is None:
+            return loc
+        out = None
+        if self.lr == 0:
+            got = self.outer.allgather_bytes(np.concatenate(loc), nbytes * self.W)   # [P] arrays
+            out = [g[i * nbytes:(i + 1) * nbytes] for g in got for i in range(self.W)]
+        return self.local._exchange(out)[0]

@@ -160,3 +160,33 @@ def test_sharded_search_over_gloo_world_size_2():
     want = brute(w, p, cap)
     assert all(abs(o[1] - want) < 1e-9 and o[2] == 0 for o in out), (want, out)
     assert out[0][3] == out[1][3]
+
+
+@pytest.mark.parametrize("procs,workers", [(1, 3), (2, 2)])
+def test_hybrid_comm_two_level_search_matches_brute_force(procs, workers):
+    """W worker threads per process x P processes (the processes emulated by a
+    second LocalGroup): same optimum, every rank agrees, collectives consistent"""
+    w, p, cap = instance(5)
+    want = brute(w, p, cap)
+    outer_group = bnb.LocalGroup(procs) if procs > 1 else None
+    groups = [bnb.LocalGroup(workers) for _ in range(procs)]
+    results = {}
+
+    def body(pr, lr):
+        outer = outer_group.comm(pr) if outer_group is not None else None
+        comm = bnb.HybridComm(groups[pr], lr, outer)
+        assert comm.world == procs * workers and comm.rank == pr * workers + lr
+        got = comm.allgather_ints([comm.rank, 7])
+        assert [g[0] for g in got] == list(range(comm.world)) and all(g[1] == 7 for g in got)
+        assert comm.allreduce(float(comm.rank), "max") == comm.world - 1
+        bufs = comm.allgather_bytes(np.full(3, comm.rank, np.uint8), 5)
+        assert [int(b[0]) for b in bufs] == list(range(comm.world)) and all(len(b) == 5 for b in bufs)
+        results[(pr, lr)] = bnb.sharded_intopt(KnapsackWorker(w, p, cap), comm, minimize=False,
+                                               slice_nodes=5, ramp_nodes=8)
+
+    threads = [threading.Thread(target=body, args=(pr, lr)) for pr in range(procs) for lr in range(workers)]
+    [t.start() for t in threads]
+    [t.join(60) for t in threads]
+    assert len(results) == procs * workers
+    assert all(abs(r["obj"] - want) < 1e-9 and r["ret"] == 0 for r in results.values()), (want, results)
+    assert len({r["holder"] for r in results.values()}) == 1
