@@ -857,59 +857,66 @@ __device__ __forceinline__ void eng_dmma(double &c0, double &c1, double a, doubl
 
 /* T += sum_{j<nd} Fd_j Rd_j' over the k x k kernel: one read+write of T for up
    to ENG_DB basis changes -- the one dense contraction of the iteration loop, so
-   it runs on the fp64 tensor cores (DMMA m8n8k4).  Tiles of 128 rows x 64
-   columns; the terms are staged in shared memory with row strides 132 / 68 that
-   keep the fragment loads bank-conflict free; every warp owns one 8-row block and
-   four 8-column blocks of the tile.  Needs ENG_FLUSH_SMEM doubles of dynamic
-   shared memory. */
-#define ENG_FS 132
+   it runs on the fp64 tensor cores (DMMA m8n8k4).  A unit is a block of 64
+   columns times a chunk of rows: the 32 x 64 slice of Rd is staged in shared
+   memory (row stride 68: bank-conflict-free fragment loads), then every warp
+   walks its own 8-row blocks with no block-wide barrier, the Fd fragments coming
+   straight from L2, so that the DRAM latency of one warp's tile overlaps the
+   arithmetic of the others. */
 #define ENG_RS 68
-#define ENG_FLUSH_SMEM (ENG_DB * (ENG_FS + ENG_RS))
+#define ENG_FLUSH_SMEM (ENG_DB * ENG_RS)
 __device__ void eng_flush(const EngCtx &X, const EngArgs &A, int k, int nd)
 {
     if (nd <= 0 || k <= 0) return;
     const size_t ldt = (size_t)A.ldt;
-    double *Fs = X.sh_d;                    /* [ENG_DB][ENG_FS]: Fs[j][r] = Fd_j[i0 + r] */
-    double *Rs = X.sh_d + ENG_DB * ENG_FS;  /* [ENG_DB][ENG_RS]: Rs[j][c] = Rd_j[c0 + c] */
+    double *Rs = X.sh_d;                    /* [ENG_DB][ENG_RS]: Rs[j][c] = Rd_j[c0 + c] */
     const int g = X.lane >> 2, t = X.lane & 3;
-    const int rbk = X.warp & 15, cq = X.warp >> 4;           /* row block, column half of the tile */
-    const int nrt = (k + 127) >> 7, nct = (k + 63) >> 6;
+    const int rbk = X.warp & 15, cq = X.warp >> 4;           /* 8-row block of a 128-row step, column half */
+    const int ncb = (k + 63) >> 6;
+    int nrc = (3 * X.G + ncb - 1) / ncb;                      /* row chunks: about three units per CTA */
+    nrc = max(1, min(nrc, (k + 127) >> 7));
+    const int RCH = ((((k + nrc - 1) / nrc) + 127) >> 7) << 7;
     const int ksteps = (nd + 3) >> 2;
-    for (int u = X.cta; u < nrt * nct; u += X.G) {
-        const int i0 = (u / nct) << 7, c0 = (u % nct) << 6;
+    for (int u = X.cta; u < ncb * nrc; u += X.G) {
+        const int c0 = (u % ncb) << 6, r0 = (u / ncb) * RCH, r1 = min(k, r0 + RCH);
         __syncthreads();
-        for (int e = X.tid; e < ENG_DB * 128; e += ENG_NT) {
-            const int j = e >> 7, r = e & 127, i = i0 + r;
-            Fs[j * ENG_FS + r] = (j < nd && i < k) ? A.Fd[(size_t)j * ldt + i] : 0.0;
-        }
         for (int e = X.tid; e < ENG_DB * 64; e += ENG_NT) {
             const int j = e >> 6, c = e & 63, cc = c0 + c;
             Rs[j * ENG_RS + c] = (j < nd && cc < k) ? A.Rd[(size_t)j * ldt + cc] : 0.0;
         }
         __syncthreads();
-        const int row = i0 + rbk * 8 + g;
-        double acc[4][2];
-        double *tp[4];
-#pragma unroll
-        for (int x = 0; x < 4; x++) {
-            const int col = c0 + (cq * 4 + x) * 8 + 2 * t;
-            tp[x] = A.T + (size_t)col * ldt + row;
-            acc[x][0] = (row < k && col < k) ? __ldcg(tp[x]) : 0.0;
-            acc[x][1] = (row < k && col + 1 < k) ? __ldcg(tp[x] + ldt) : 0.0;
-        }
-        for (int kk = 0; kk < ksteps; kk++) {
-            const double a = Fs[(4 * kk + t) * ENG_FS + rbk * 8 + g];
+        for (int i0 = r0; i0 < r1; i0 += 128) {
+            const int row = i0 + rbk * 8 + g;
+            const bool rok = row < r1;
+            double acc[4][2];
+            double *tp[4];
 #pragma unroll
             for (int x = 0; x < 4; x++) {
-                const double b = Rs[(4 * kk + t) * ENG_RS + (cq * 4 + x) * 8 + g];
-                eng_dmma(acc[x][0], acc[x][1], a, b);
+                const int col = c0 + (cq * 4 + x) * 8 + 2 * t;
+                tp[x] = A.T + (size_t)col * ldt + row;
+                acc[x][0] = (rok && col < k) ? __ldcg(tp[x]) : 0.0;
+                acc[x][1] = (rok && col + 1 < k) ? __ldcg(tp[x] + ldt) : 0.0;
             }
-        }
+            double af[8];
 #pragma unroll
-        for (int x = 0; x < 4; x++) {
-            const int col = c0 + (cq * 4 + x) * 8 + 2 * t;
-            if (row < k && col < k) tp[x][0] = acc[x][0];
-            if (row < k && col + 1 < k) tp[x][ldt] = acc[x][1];
+            for (int kk = 0; kk < 8; kk++)
+                af[kk] = (4 * kk + t < nd && rok) ? __ldcg(A.Fd + (size_t)(4 * kk + t) * ldt + row) : 0.0;
+#pragma unroll
+            for (int kk = 0; kk < 8; kk++) {
+                if (kk < ksteps) {
+#pragma unroll
+                    for (int x = 0; x < 4; x++) {
+                        const double b = Rs[(4 * kk + t) * ENG_RS + (cq * 4 + x) * 8 + g];
+                        eng_dmma(acc[x][0], acc[x][1], af[kk], b);
+                    }
+                }
+            }
+#pragma unroll
+            for (int x = 0; x < 4; x++) {
+                const int col = c0 + (cq * 4 + x) * 8 + 2 * t;
+                if (rok && col < k) tp[x][0] = acc[x][0];
+                if (rok && col + 1 < k) tp[x][ldt] = acc[x][1];
+            }
         }
     }
     __syncthreads();

@@ -149,6 +149,7 @@ struct glpb_prob {
     double *T = nullptr, *T2 = nullptr, *partial = nullptr;   /* T2: output buffer of the refactorisation */
     struct RefSlot *ref_slots = nullptr;
     unsigned int *ref_flags = nullptr;
+    double *ref_xp = nullptr;              /* [REF_NB][ldt] pivot rows of a refactorisation round */
     int partial_rows = 0;
     int *rslot = nullptr, *slot_pos = nullptr, *cslot = nullptr, *slot_row = nullptr;
     int *gj_piv = nullptr;

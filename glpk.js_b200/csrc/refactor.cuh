@@ -29,8 +29,8 @@
 #define REF_CB 16            /* columns per update block                      */
 #define REF_RMAX 256         /* distributed panel: max rows per CTA            */
 #define REF_PS 132           /* shared row strides of the DMMA operands        */
-#define REF_XS 36
-#define REF_UPD_SMEM ((REF_NB * (REF_PS + REF_XS)) * sizeof(double))
+#define REF_XS 68
+#define REF_UPD_SMEM ((REF_NB * REF_XS) * sizeof(double))
 
 struct __align__(128) RefSlot {
     double absval;
@@ -46,7 +46,11 @@ struct RefArgs {
     int nbr;                 /* pivots per round (8, 16 or 32)                */
     int single;              /* 1: the whole panel lives in CTA 0's shared memory (k nbr 8 bytes fit);
                                 0: its rows are spread over all CTAs          */
-    int *plan;               /* [2 + 4 REF_NB] single mode: naff, sing, aff_row, aff_src published by CTA 0 */
+    int pg;                  /* distributed mode: CTAs that hold the panel (a few dozen: the per-pivot
+                                exchange gets cheaper with fewer participants)                       */
+    double *xp;              /* [REF_NB][ldt] pivot rows of the round (after the swaps) by column    */
+    int *plan;               /* [2 + 4 REF_NB] naff, sing, aff_row, aff_src published by CTA 0 for the
+                                CTAs that did not follow the pivots                                  */
     long long *prof_cyc;     /* optional [8]: SM cycles of CTA 0 per phase (build, panel, panel i/o, wait, swap+update, finish) */
     double *X;               /* working matrix (in: nothing, built here)      */
     double *T2;              /* out: T = -inv(M), column-major, ld = ldt      */
@@ -59,7 +63,8 @@ struct RefArgs {
 
 struct RefCtx {
     int G, cta, tid, lane, warp;
-    unsigned int seq;
+    unsigned int seq;        /* grid barriers (all CTAs)                         */
+    unsigned int pseq;       /* per-pivot exchanges (panel CTAs only)            */
 };
 
 __device__ __forceinline__ void ref_bar(RefCtx &X, const RefArgs &A)
@@ -99,7 +104,7 @@ __global__ void __launch_bounds__(REF_NT, 1) k_refactor(RefArgs A)
     } while (0)
     RefCtx X;
     X.G = gridDim.x; X.cta = blockIdx.x; X.tid = threadIdx.x; X.lane = X.tid & 31; X.warp = X.tid >> 5;
-    X.seq = 0u;
+    X.seq = 0u; X.pseq = 0u;
     const int G = X.G, cta = X.cta, tid = X.tid;
     const int k = A.ctrl->k;
     if (A.ctrl->sing || k <= 0) return;
@@ -135,7 +140,7 @@ __global__ void __launch_bounds__(REF_NT, 1) k_refactor(RefArgs A)
     const double tiny = 1e-13 * fmax(max_a, 1e-300);
 
     /* panel ownership: PG CTAs hold R rows each */
-    const int PG = A.single ? 1 : G;
+    const int PG = A.single ? 1 : min(G, A.pg);
     const int NBR = A.nbr;
     const int R = (k + PG - 1) / PG;
     const int r0 = (cta < PG) ? min(k, cta * R) : k, r1 = min(k, r0 + R);
@@ -285,8 +290,8 @@ __global__ void __launch_bounds__(REF_NT, 1) k_refactor(RefArgs A)
             __syncthreads();
             int r, wc;
             if (PG > 1) {
-                X.seq++;
-                RefSlot *ring = A.slots + (X.seq & (ENG_RING - 1)) * ENG_MAXG;
+                X.pseq++;
+                RefSlot *ring = A.slots + (X.pseq & (ENG_RING - 1)) * ENG_MAXG;
                 RefSlot *mine = ring + cta;
                 const int lr = s_r;
                 if (tid < nb) {
@@ -295,12 +300,12 @@ __global__ void __launch_bounds__(REF_NT, 1) k_refactor(RefArgs A)
                 }
                 if (tid == 0) { __stcg(&mine->absval, v.a); __stcg(&mine->row, v.pos); }
                 __syncthreads();
-                if (tid == 0) eng_st_release(&mine->flag, X.seq);
-                const int nw = (G + 31) >> 5;
+                if (tid == 0) eng_st_release(&mine->flag, X.pseq);
+                const int nw = (PG + 31) >> 5;
                 if (X.warp < nw) {
                     Key c = none;
-                    if (tid < G) {
-                        while (eng_ld_relaxed(&ring[tid].flag) < X.seq) { }
+                    if (tid < PG) {
+                        while (eng_ld_relaxed(&ring[tid].flag) < X.pseq) { }
                         eng_fence_acq();
                         c.a = __ldcg(&ring[tid].absval); c.pos = __ldcg(&ring[tid].row); c.aux = tid;
                     }
@@ -320,8 +325,8 @@ __global__ void __launch_bounds__(REF_NT, 1) k_refactor(RefArgs A)
                 }
                 __syncthreads();
                 r = s_r; wc = s_wc;
-                if (s_sing) { if (cta == 0 && tid == 0) A.ctrl->sing = 1; return; }
-                const int ot = min(G - 1, t / R);
+                if (s_sing) break;             /* reported after the round's barrier */
+                const int ot = min(PG - 1, t / R);
                 if (tid < nb) {
                     rowR[tid] = __ldcg(&ring[wc].cand[tid]);
                     rowT[tid] = __ldcg(&ring[ot].rowt[tid]);
@@ -380,90 +385,102 @@ __global__ void __launch_bounds__(REF_NT, 1) k_refactor(RefArgs A)
             A.X[(size_t)(c0 + cc) * ldt + r0 + i] = pan[i * PS + cc];
         }
         if (cta == 0 && tid < nb) A.piv[c0 + tid] = s_piv[tid];
-        if (A.single && cta == 0) {
-            /* the other CTAs did not follow the pivots: publish the gather list */
+        if (cta == 0) {
+            /* the CTAs that did not follow the pivots take the gather list from here */
+            __syncthreads();
             if (tid < 2 * REF_NB) { A.plan[2 + tid] = aff_row[tid]; A.plan[2 + 2 * REF_NB + tid] = aff_src[tid]; }
             if (tid == 0) { A.plan[0] = s_naff; A.plan[1] = s_sing; }
         }
         REF_MARK(2);
         ref_bar(X, A);
         REF_MARK(3);
-        if (A.single) {
-            if (cta != 0) {
-                if (tid < 2 * REF_NB) { aff_row[tid] = __ldcg(A.plan + 2 + tid); aff_src[tid] = __ldcg(A.plan + 2 + 2 * REF_NB + tid); }
-                if (tid == 0) { s_naff = __ldcg(A.plan + 0); s_sing = __ldcg(A.plan + 1); }
-            }
-            __syncthreads();
-            if (s_sing) { if (cta == 0 && tid == 0) A.ctrl->sing = 1; return; }
+        if (cta >= PG) {
+            if (tid < 2 * REF_NB) { aff_row[tid] = __ldcg(A.plan + 2 + tid); aff_src[tid] = __ldcg(A.plan + 2 + 2 * REF_NB + tid); }
+            if (tid == 0) { s_naff = __ldcg(A.plan + 0); s_sing = __ldcg(A.plan + 1); }
         }
+        __syncthreads();
+        if (s_sing) { if (cta == 0 && tid == 0) A.ctrl->sing = 1; return; }
         /* ---- the other columns: row swaps, pivot rows, rank-nb update ---- */
         const int naff = s_naff;
-        /* blocks of 32 columns; the rank-nb update runs on the fp64 tensor cores (DMMA
-           m8n8k4): tiles of 128 rows x 32 columns, Pf staged with row stride 132 and the
-           pivot rows with stride 36 (bank-conflict-free fragment loads); every warp owns
-           one 8-row block and two 8-column blocks of the tile */
-        double *Pfs = ref_dyn;                     /* [REF_NB][REF_PS]: Pfs[t][r] = X[i0 + r, c0 + t] */
-        double *Rs2 = ref_dyn + REF_NB * REF_PS;   /* [REF_NB][REF_XS]: Rs2[t][c] = X[c0 + t, cc0 + c] after the swaps */
-        const int ncb = (k + 31) / 32;
+        /* (2) the round's row permutation on the other columns, 16 columns per CTA step;
+               their pivot rows (after the swaps) go to xp[t][col] */
+        for (int cb = cta; cb < (k + REF_CB - 1) / REF_CB; cb += G) {
+            const int a = tid / REF_CB, c = tid % REF_CB;
+            const int col = cb * REF_CB + c;
+            const bool inpanel = (col >= c0 && col < c0 + nb);
+            const bool act = (a < naff) && (col < k) && !inpanel;
+            double val = 0.0;
+            if (act) val = A.X[(size_t)col * ldt + aff_src[a]];
+            __syncthreads();
+            if (act && aff_src[a] != aff_row[a]) A.X[(size_t)col * ldt + aff_row[a]] = val;
+            __syncthreads();
+            if (tid < REF_NB * REF_CB) {
+                const int t = tid / REF_CB;
+                if (col < (int)ldt)
+                    A.xp[(size_t)t * ldt + col] = (t < nb && col < k && !inpanel) ? A.X[(size_t)col * ldt + c0 + t] : 0.0;
+            }
+        }
+        ref_bar(X, A);
+        /* (3) rank-nb update on the fp64 tensor cores (DMMA m8n8k4).  A unit is a block of
+               64 columns times a chunk of rows; the 32 x 64 slice of the pivot rows is staged
+               in shared memory (row stride 68: bank-conflict-free fragment loads), then every
+               warp walks its own 8-row blocks with no block-wide barrier, the Pf fragments
+               coming straight from L2: the DRAM latency of one warp's tile overlaps the
+               arithmetic of the others */
+        double *Rs2 = ref_dyn;                     /* [REF_NB][REF_XS] */
+        const int ncb = (k + 63) >> 6;
+        int nrc = (3 * G + ncb - 1) / ncb;
+        nrc = max(1, min(nrc, (k + 127) >> 7));
+        const int RCH = ((((k + nrc - 1) / nrc) + 127) >> 7) << 7;
         const int ksteps = (nb + 3) >> 2;
-        for (int cb = cta; cb < ncb; cb += G) {
-            const int cc0 = cb * 32;
-            for (int sblk = 0; sblk < 2; sblk++) {
-                const int a = tid / REF_CB, c = tid % REF_CB;
-                const int col = cc0 + sblk * REF_CB + c;
-                const bool act = (a < naff) && (col < k) && !(col >= c0 && col < c0 + nb);
-                double val = 0.0;
-                if (act) val = A.X[(size_t)col * ldt + aff_src[a]];
-                __syncthreads();
-                if (act && aff_src[a] != aff_row[a]) A.X[(size_t)col * ldt + aff_row[a]] = val;
-                __syncthreads();
+        const int g = X.lane >> 2, t4 = X.lane & 3;
+        const int rbk = X.warp & 15, cq = X.warp >> 4;
+        for (int u = cta; u < ncb * nrc; u += G) {
+            const int cc0 = (u % ncb) << 6, q0 = (u / ncb) * RCH, q1 = min(k, q0 + RCH);
+            __syncthreads();
+            for (int e = tid; e < REF_NB * 64; e += REF_NT) {
+                const int t = e >> 6, c = e & 63, col = cc0 + c;
+                Rs2[t * REF_XS + c] = (t < nb && col < k) ? __ldcg(A.xp + (size_t)t * ldt + col) : 0.0;
             }
-            {
-                const int t = tid >> 5, c = tid & 31;
-                const int col = cc0 + c;
-                const bool act = (t < nb) && (col < k) && !(col >= c0 && col < c0 + nb);
-                Rs2[t * REF_XS + c] = act ? A.X[(size_t)col * ldt + c0 + t] : 0.0;
-            }
-            const int g = X.lane >> 2, t4 = X.lane & 3;
-            const int rbk = X.warp & 15, cq = X.warp >> 4;
-            for (int i0 = 0; i0 < k; i0 += 128) {
-                /* the tile's own entries first: their DRAM latency overlaps the staging of Pf */
+            __syncthreads();
+            for (int i0 = q0; i0 < q1; i0 += 128) {
                 const int row = i0 + rbk * 8 + g;
+                const bool rok = row < q1;
                 const bool in_p = (row >= c0 && row < c0 + nb);
-                double acc[2][2];
-                double *tp[2];
-                bool ok[2][2];
+                double acc[4][2];
+                double *tp[4];
+                bool ok[4][2];
 #pragma unroll
-                for (int x = 0; x < 2; x++) {
-                    const int col = cc0 + (cq * 2 + x) * 8 + 2 * t4;
+                for (int x = 0; x < 4; x++) {
+                    const int col = cc0 + (cq * 4 + x) * 8 + 2 * t4;
                     tp[x] = A.X + (size_t)col * ldt + row;
-                    ok[x][0] = (row < k) && (col < k) && !(col >= c0 && col < c0 + nb);
-                    ok[x][1] = (row < k) && (col + 1 < k) && !(col + 1 >= c0 && col + 1 < c0 + nb);
+                    ok[x][0] = rok && (col < k) && !(col >= c0 && col < c0 + nb);
+                    ok[x][1] = rok && (col + 1 < k) && !(col + 1 >= c0 && col + 1 < c0 + nb);
                     acc[x][0] = (ok[x][0] && !in_p) ? __ldcg(tp[x]) : 0.0;
                     acc[x][1] = (ok[x][1] && !in_p) ? __ldcg(tp[x] + ldt) : 0.0;
                 }
-                __syncthreads();
-                for (int e = tid; e < REF_NB * 128; e += REF_NT) {
-                    const int t = e >> 7, r = e & 127;
-                    Pfs[t * REF_PS + r] = (t < nb && i0 + r < k) ? __ldcg(A.X + (size_t)(c0 + t) * ldt + i0 + r) : 0.0;
-                }
-                __syncthreads();
-                for (int kk = 0; kk < ksteps; kk++) {
-                    const double a = Pfs[(4 * kk + t4) * REF_PS + rbk * 8 + g];
+                double af[8];
 #pragma unroll
-                    for (int x = 0; x < 2; x++) {
-                        const double b = Rs2[(4 * kk + t4) * REF_XS + (cq * 2 + x) * 8 + g];
-                        eng_dmma(acc[x][0], acc[x][1], a, b);
+                for (int kk = 0; kk < 8; kk++)
+                    af[kk] = (4 * kk + t4 < nb && rok) ? __ldcg(A.X + (size_t)(c0 + 4 * kk + t4) * ldt + row) : 0.0;
+#pragma unroll
+                for (int kk = 0; kk < 8; kk++) {
+                    if (kk < ksteps) {
+#pragma unroll
+                        for (int x = 0; x < 4; x++) {
+                            const double b = Rs2[(4 * kk + t4) * REF_XS + (cq * 4 + x) * 8 + g];
+                            eng_dmma(acc[x][0], acc[x][1], af[kk], b);
+                        }
                     }
                 }
 #pragma unroll
-                for (int x = 0; x < 2; x++) {
+                for (int x = 0; x < 4; x++) {
                     if (ok[x][0]) tp[x][0] = acc[x][0];
                     if (ok[x][1]) tp[x][ldt] = acc[x][1];
                 }
             }
-            __syncthreads();
         }
+        __syncthreads();
         REF_MARK(4);
         ref_bar(X, A);
         REF_MARK(3);

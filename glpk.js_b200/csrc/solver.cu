@@ -153,7 +153,7 @@ extern "C" void glpb_destroy(glpb_prob *P)
                     P->orig_type, P->stat, P->refsp, P->lb, P->ub, P->coef, P->orig_lb, P->orig_ub,
                     P->obj, P->head, P->bind, P->bbar, P->cbar, P->gamma, P->tcol, P->trow, P->rho,
                     P->svec, P->w1, P->w2, P->w3, P->w4, P->w5, P->yk, P->wk, P->yk2, P->zn, P->eng_slots, P->eng_cols, P->eng_fr,
-                    P->eng_cyc, P->eng_bytes, P->T, P->T2, P->ref_slots, P->ref_flags, P->partial,
+                    P->eng_cyc, P->eng_bytes, P->T, P->T2, P->ref_slots, P->ref_flags, P->ref_xp, P->partial,
                     P->rslot, P->slot_pos, P->cslot, P->slot_row, P->gj_piv, P->gj_row,
                     P->scratch, P->ctrl};
     for (void *p : ptrs) if (p) cudaFree(p);
@@ -185,7 +185,7 @@ static int create_device(glpb_prob *P)
     DA(eng_slots, ENG_RING * ENG_MAXG + 1); DA(eng_cols, 3 * (size_t)n + m); DA(eng_fr, 2 * (size_t)ENG_DB * P->ldt + ENG_DB); DA(eng_cyc, 32); DA(eng_bytes, 24);
     DA(T, (size_t)P->ldt * P->ldt);
     DA(T2, (size_t)P->ldt * P->ldt);
-    DA(ref_slots, ENG_RING * ENG_MAXG); DA(ref_flags, ENG_RING * ENG_MAXG * 32);
+    DA(ref_slots, ENG_RING * ENG_MAXG); DA(ref_flags, ENG_RING * ENG_MAXG * 32); DA(ref_xp, (size_t)REF_NB * P->ldt);
     P->partial_rows = cdiv(P->ldt, GEMV_TILE);
     DA(partial, (size_t)P->partial_rows * P->ldt);
     DA(rslot, m); DA(slot_pos, P->ldt); DA(cslot, m); DA(slot_row, P->ldt);
@@ -208,7 +208,7 @@ static int create_device(glpb_prob *P)
         CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, P->device));
         CK(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, P->device));
         int budget = std::min(smem_max, 200 * 1024) - 42 * 1024;      /* static shared of the engine (~16 KB) + cross-warp sums */
-        int dcap = std::max(ENG_FLUSH_SMEM, std::min(P->ldt, (budget - ENG_LCAP * 4) / 8));   /* >= the staging of eng_flush */
+        int dcap = std::max({ENG_LCAP, ENG_FLUSH_SMEM, std::min(P->ldt, (budget - ENG_LCAP * 4) / 8)});   /* >= the list staging and the staging of eng_flush */
         P->eng_dcap = dcap;
         P->eng_smem = dcap * 8 + ENG_LCAP * 4 + 32 * 65 * 8;
         if (!coop || P->sm_count > ENG_MAXG) { glpb_set_error("device lacks cooperative launch"); return GLPB_ENODEV; }
@@ -481,8 +481,9 @@ static int dev_refactor(Dev &D)
         for (int nb = REF_NB; nb >= 8 && !nbr; nb >>= 1)
             if ((size_t)k * (nb + 2) * sizeof(double) + 64 <= REF_SMEM_MAX) { nbr = nb; single = 1; }
         if (envs == 0 || !nbr) { nbr = REF_NB; single = 0; }
-        if (!single) G = std::max(G, cdiv(k, REF_RMAX));
-        const int R = single ? k : cdiv(k, G);
+        static const int envpg = getenv("GLPB_REF_PG") ? atoi(getenv("GLPB_REF_PG")) : 32;
+        const int pg = std::max(1, std::min(G, std::max(envpg, cdiv(k, 700))));     /* panel CTAs; <= 700 rows each */
+        const int R = single ? k : cdiv(k, pg);
         const size_t smem = std::max({(size_t)R * (nbr + 2) * sizeof(double) + 64, (size_t)2 * k * sizeof(int), (size_t)REF_UPD_SMEM});
         if (G > P->sm_count || smem > REF_SMEM_MAX) {
             glpb_set_error("refactorisation: kernel of size %d does not fit the device", k);
@@ -496,7 +497,7 @@ static int dev_refactor(Dev &D)
         A.head = P->head; A.slot_pos = P->slot_pos; A.cslot = P->cslot;
         A.piv = P->gj_piv; A.slots = P->ref_slots; A.flags = P->ref_flags;
         A.prof_cyc = P->prof ? P->eng_cyc + 24 : nullptr;
-        A.nbr = nbr; A.single = single; A.plan = (int *)P->gj_row;   /* gj_row: ldt doubles, used as scratch ints */
+        A.nbr = nbr; A.single = single; A.pg = pg; A.xp = P->ref_xp; A.plan = (int *)P->gj_row;   /* gj_row: ldt doubles, used as scratch ints */
         void *args[] = {&A};
         P->next_bytes = 16.0 * k * (double)k * cdiv(k, REF_NB);
         prof_begin(P, "k_refactor");

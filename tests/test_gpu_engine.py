@@ -40,6 +40,7 @@ MODES = [
     ("three CTAs", {"GLPB_GRID": "3"}),
     ("one CTA", {"GLPB_GRID": "1"}),
     ("distributed panel", {"GLPB_REF_SINGLE": "0"}),
+    ("distributed panel held by two CTAs", {"GLPB_REF_SINGLE": "0", "GLPB_REF_PG": "2"}),
     ("refactorise every nfs_max updates", {"GLPB_REFAC_AUTO": "0"}),
     ("per-kernel path", {"GLPB_ENGINE": "0"}),
 ]
