@@ -71,6 +71,7 @@ struct EngArgs {
     double *Fd, *Rd;          /* [ENG_DB][ldt] each                              */
     double *zbuf;             /* [ENG_DB] Rd_j' v for the dense product          */
     int defer;                /* 1: deferral allowed                             */
+    int use_tma;              /* 1: TMA-staged dense T*v stream where it applies */
     int local_max;            /* ratio tests up to this length are replicated per CTA */
     int *rslot, *slot_pos, *cslot, *slot_row;
     EngSlot *slots;           /* [ENG_RING][ENG_MAXG] arrival flags + CTA partials, zeroed by the host */
@@ -442,6 +443,135 @@ __device__ void eng_gemv_rows(const EngCtx &X, const EngArgs &A, int k, int L, c
         }
         __syncthreads();
     }
+}
+
+/* ---- TMA (bulk asynchronous copy) + mbarrier helpers ---- */
+__device__ __forceinline__ unsigned int eng_smem_u32(const void *p) { return (unsigned int)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void eng_mbar_init(unsigned long long *bar, unsigned int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(eng_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void eng_mbar_inval(unsigned long long *bar)
+{
+    asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(eng_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void eng_mbar_expect_tx(unsigned long long *bar, unsigned int bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(eng_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void eng_mbar_arrive(unsigned long long *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(eng_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void eng_mbar_wait(unsigned long long *bar, unsigned int parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(eng_smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void eng_bulk_g2s(void *dst, const void *src, unsigned int bytes, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(eng_smem_u32(dst)), "l"(src), "r"(bytes), "r"(eng_smem_u32(bar)) : "memory");
+}
+
+/* The dense stream y = T v (8 k^2 bytes, the dominant pass of large dual
+   problems) with TMA/shared-memory staging of column segments: every CTA owns a
+   contiguous range of <= 64 rows; the piece of each column of T that falls in
+   it (one contiguous run of 16-byte multiples) is brought into shared memory by
+   cp.async.bulk, ENG_TNC columns per stage, ENG_TST stages in flight, completion
+   on an mbarrier per stage -- the bytes in flight no longer depend on registers.
+   The 1024 threads consume a stage as 64 row slots x 16 column groups; a second
+   mbarrier per stage (one arrival per warp) hands the slot back to the producer
+   (warp 0). */
+#define ENG_TNC 64
+#define ENG_TST 4
+#define ENG_TMA_SMEM (ENG_TST * ENG_TNC * 64)       /* doubles */
+__device__ __forceinline__ bool eng_gemv_tma_ok(const EngCtx &X, const EngArgs &A, int k)
+{
+    const int RPC = (((k + X.G - 1) / X.G) + 3) & ~3;
+    return RPC > 16 && RPC <= 64 && A.dcap >= ENG_TMA_SMEM && k >= 4 * ENG_TNC;
+}
+__device__ void eng_gemv_dense_tma(const EngCtx &X, const EngArgs &A, int k, const double *v, double *y, double *ycol,
+                                   int nd, const double *z)
+{
+    __shared__ __align__(8) unsigned long long full_bar[ENG_TST], empty_bar[ENG_TST];
+    const size_t ldt = (size_t)A.ldt;
+    const int RPC = (((k + X.G - 1) / X.G) + 3) & ~3;
+    const int q0 = min(k, X.cta * RPC), q1 = min(k, q0 + RPC);
+    const int rows = q1 - q0;
+    if (rows <= 0) return;                                    /* uniform per CTA: no grid barrier inside */
+    const int rowsp = (rows + 1) & ~1;                         /* 16-byte multiples */
+    const unsigned int rowbytes = (unsigned int)rowsp * 8u;
+    double *stage = X.sh_d;                                    /* [ENG_TST][ENG_TNC][rowsp] */
+    const int ntile = (k + ENG_TNC - 1) / ENG_TNC;
+    if (X.tid == 0) {
+        for (int s = 0; s < ENG_TST; s++) { eng_mbar_init(&full_bar[s], 1u); eng_mbar_init(&empty_bar[s], ENG_NT / 32); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const double *Tq = A.T + q0;
+    /* producer: warp 0 fills one stage */
+    auto fill = [&](int tile) {
+        const int s = tile % ENG_TST;
+        const int c0 = tile * ENG_TNC, nc = min(ENG_TNC, k - c0);
+        if (X.lane == 0) eng_mbar_expect_tx(&full_bar[s], (unsigned int)nc * rowbytes);
+        __syncwarp();
+        double *dst = stage + (size_t)s * ENG_TNC * rowsp;
+        for (int c = X.lane; c < nc; c += 32)
+            eng_bulk_g2s(dst + (size_t)c * rowsp, Tq + (size_t)(c0 + c) * ldt, rowbytes, &full_bar[s]);
+    };
+    if (X.warp == 0) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        for (int t = 0; t < min(ENG_TST, ntile); t++) fill(t);
+    }
+    const int r = X.tid & 63, cg = X.tid >> 6;                 /* 64 row slots x 16 column groups */
+    double acc0 = 0.0, acc1 = 0.0;
+    for (int tile = 0; tile < ntile; tile++) {
+        const int s = tile % ENG_TST;
+        const unsigned int par = (unsigned int)((tile / ENG_TST) & 1);
+        eng_mbar_wait(&full_bar[s], par);
+        const int c0 = tile * ENG_TNC, nc = min(ENG_TNC, k - c0);
+        const double *src = stage + (size_t)s * ENG_TNC * rowsp + r;
+        if (r < rows) {
+            int c = cg;
+            for (; c + 16 < nc; c += 32) {
+                acc0 += src[(size_t)c * rowsp] * v[c0 + c];
+                acc1 += src[(size_t)(c + 16) * rowsp] * v[c0 + c + 16];
+            }
+            if (c < nc) acc0 += src[(size_t)c * rowsp] * v[c0 + c];
+        }
+        __syncwarp();
+        if (X.lane == 0) eng_mbar_arrive(&empty_bar[s]);       /* this warp is done with the slot */
+        if (X.warp == 0 && tile + ENG_TST < ntile) {
+            eng_mbar_wait(&empty_bar[s], par);                 /* every warp is done with it */
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            fill(tile + ENG_TST);
+        }
+    }
+    /* column groups meet in shared memory (fixed order), then the epilogue of eng_gemv_rows */
+    double (*red2)[65] = (double (*)[65])X.sh_red2;            /* [32][65]: 16 groups used */
+    red2[cg][r] = acc0 + acc1;
+    __syncthreads();
+    if (X.tid < rows) {
+        double sum = 0.0;
+#pragma unroll
+        for (int w = 0; w < 16; w++) sum += red2[w][X.tid];
+        const int b2 = q0 + X.tid;
+        for (int j = 0; j < nd; j++) sum += A.Fd[(size_t)j * ldt + b2] * z[j];
+        y[b2] = sum;
+        ycol[A.head[A.slot_pos[b2]] - A.m] = sum;
+    }
+    __syncthreads();
+    if (X.tid == 0)
+        for (int s = 0; s < ENG_TST; s++) { eng_mbar_inval(&full_bar[s]); eng_mbar_inval(&empty_bar[s]); }
+    __syncthreads();
 }
 
 /* FTRAN, first half, for the right-hand side h = -N_q (eval_tcol,
@@ -988,7 +1118,7 @@ enum { /* phase slots of the cycle accounting (12 per engine) */
 /* ------------------------------------------------------------------ */
 __global__ void __launch_bounds__(ENG_NT, 1) k_engine_primal(EngArgs A)
 {
-    extern __shared__ double eng_dyn[];
+    extern __shared__ __align__(128) double eng_dyn[];
     __shared__ Ctrl S;
     __shared__ EngChange C;
     EngCtx X;
@@ -1256,7 +1386,7 @@ __global__ void __launch_bounds__(ENG_NT, 1) k_engine_primal(EngArgs A)
 /* ------------------------------------------------------------------ */
 __global__ void __launch_bounds__(ENG_NT, 1) k_engine_dual(EngArgs A)
 {
-    extern __shared__ double eng_dyn[];
+    extern __shared__ __align__(128) double eng_dyn[];
     __shared__ Ctrl S;
     __shared__ EngChange C;
     EngCtx X;
@@ -1383,12 +1513,14 @@ __global__ void __launch_bounds__(ENG_NT, 1) k_engine_dual(EngArgs A)
             const int k = S.k;
             const double *val = A.wk;
             if (X.tid < nd) zd[X.tid] = __ldcg(A.zbuf + X.tid);
-            if (k <= A.dcap) {
+            const bool tma = A.use_tma && eng_gemv_tma_ok(X, A, k);
+            if (!tma && k <= A.dcap) {
                 for (int e = X.tid; e < k; e += ENG_NT) X.sh_d[e] = A.wk[e];
                 val = X.sh_d;
             }
             __syncthreads();
-            eng_gemv_rows(X, A, k, k, nullptr, val, A.yk2, A.ycol2, false, nd, zd);
+            if (tma) eng_gemv_dense_tma(X, A, k, A.wk, A.yk2, A.ycol2, nd, zd);
+            else eng_gemv_rows(X, A, k, k, nullptr, val, A.yk2, A.ycol2, false, nd, zd);
             __syncthreads();
         }
         eng_ftran_head_col(X, A, S.k, kq, A.yk, A.ycol, nd);

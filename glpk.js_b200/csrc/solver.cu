@@ -208,7 +208,7 @@ static int create_device(glpb_prob *P)
         CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, P->device));
         CK(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, P->device));
         int budget = std::min(smem_max, 200 * 1024) - 42 * 1024;      /* static shared of the engine (~16 KB) + cross-warp sums */
-        int dcap = std::max({ENG_LCAP, ENG_FLUSH_SMEM, std::min(P->ldt, (budget - ENG_LCAP * 4) / 8)});   /* >= the list staging and the staging of eng_flush */
+        int dcap = std::max({ENG_LCAP, ENG_FLUSH_SMEM, ENG_TMA_SMEM, std::min(P->ldt, (budget - ENG_LCAP * 4) / 8)});   /* >= list staging, flush staging, TMA stages */
         P->eng_dcap = dcap;
         P->eng_smem = dcap * 8 + ENG_LCAP * 4 + 32 * 65 * 8;
         if (!coop || P->sm_count > ENG_MAXG) { glpb_set_error("device lacks cooperative launch"); return GLPB_ENODEV; }
@@ -774,6 +774,10 @@ struct Loop : Dev {
         static const int env_local = getenv("GLPB_LOCAL_MAX") ? atoi(getenv("GLPB_LOCAL_MAX")) : ENG_LOCAL_MAX;
         A.Fd = P->eng_fr; A.Rd = P->eng_fr + (size_t)ENG_DB * P->ldt; A.zbuf = P->eng_fr + 2 * (size_t)ENG_DB * P->ldt;
         A.defer = (env_defer && dual && P->eng_dcap >= ENG_FLUSH_SMEM) ? 1 : 0;
+        /* measured on B200 (C3): per-column bulk copies of ~350 bytes are issue-bound (2.2 TB/s) and lose
+           to the register-staged 16-byte loads (3.6 TB/s), so the TMA-staged stream is opt-in */
+        static const int env_tma = getenv("GLPB_TMA") ? atoi(getenv("GLPB_TMA")) : 0;
+        A.use_tma = env_tma;
         A.local_max = env_local;
         A.prof_cyc = P->prof ? P->eng_cyc + (dual ? 12 : 0) : nullptr;
         A.prof_bytes = P->prof ? P->eng_bytes + (dual ? 12 : 0) : nullptr;

@@ -37,6 +37,8 @@ MODES = [
     ("default", {}),
     ("grid-wide ratio test + deferred basis changes", {"GLPB_LOCAL_MAX": "0"}),
     ("grid-wide ratio test, direct basis changes", {"GLPB_LOCAL_MAX": "0", "GLPB_DEFER": "0"}),
+    ("eight CTAs, TMA-staged T*v stream once k >= 256", {"GLPB_GRID": "8", "GLPB_TMA": "1"}),
+    ("eight CTAs, register-staged stream", {"GLPB_GRID": "8"}),
     ("three CTAs", {"GLPB_GRID": "3"}),
     ("one CTA", {"GLPB_GRID": "1"}),
     ("distributed panel", {"GLPB_REF_SINGLE": "0"}),
