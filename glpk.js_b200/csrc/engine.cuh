@@ -284,19 +284,6 @@ __device__ __forceinline__ double eng_spdot(const int *ind, const double *val, i
 {
     double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
     int ptr = beg + l;
-    /* eight independent gathers in flight per lane: the pass is bound by the latency of
-       the dependent pair (index, x[index]), not by bytes */
-    for (; ptr + 7 * LP < end; ptr += 8 * LP) {
-        int c[8];
-        double v[8];
-#pragma unroll
-        for (int u = 0; u < 8; u++) { c[u] = __ldg(ind + ptr + u * LP); v[u] = __ldg(val + ptr + u * LP); }
-        double g[8];
-#pragma unroll
-        for (int u = 0; u < 8; u++) g[u] = x[c[u]];
-        a0 += v[0] * g[0]; a1 += v[1] * g[1]; a2 += v[2] * g[2]; a3 += v[3] * g[3];
-        a0 += v[4] * g[4]; a1 += v[5] * g[5]; a2 += v[6] * g[6]; a3 += v[7] * g[7];
-    }
     for (; ptr + 3 * LP < end; ptr += 4 * LP) {
         const int c0 = __ldg(ind + ptr), c1 = __ldg(ind + ptr + LP), c2 = __ldg(ind + ptr + 2 * LP),
                   c3 = __ldg(ind + ptr + 3 * LP);
