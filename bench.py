@@ -381,25 +381,33 @@ def main():
     ref_split = {k: v for k, v in prof.items() if k.startswith("ref_")}          # inside k_refactor: informational
     units = {k: v for k, v in prof.items() if not k.startswith("k_engine_") and not k.startswith("ref_")}
     tot_prof_ms = sum(v["ms"] for v in units.values()) or 1.0
-    with_bytes = {k: v for k, v in units.items() if v["bytes"] > 0 and v["count"] > 0}
-    top = max(with_bytes, key=lambda k: with_bytes[k]["ms"]) if with_bytes else None
+    # the dominant kernel is the persistent engine: its roofline entry is the sum of the
+    # algorithmic bytes of all its phases over the CUDA-event time of its launches
+    eng_name = "k_engine_primal" if w["meth"] == "primal" else "k_engine_dual"
+    phases = {k: v for k, v in units.items() if k.startswith("eng_")}
+    agg = {"ms": sum(v["ms"] for v in phases.values()), "bytes": sum(v["bytes"] for v in phases.values()),
+           "count": max([v["count"] for v in phases.values()] or [0])}
+    cands = {k: v for k, v in units.items() if not k.startswith("eng_") and v["bytes"] > 0 and v["count"] > 0}
+    if agg["ms"] > 0 and agg["count"] > 0:
+        cands[eng_name] = agg
+    top = max(cands, key=lambda k: cands[k]["ms"]) if cands else None
     peak, peak_src = peaks()
     roofline = None
     if top:
-        v = prof[top]
+        v = cands[top]
         ach = (v["bytes"] / v["count"]) / (v["ms"] / v["count"] * 1e-3) / 1e9
-        eng = "k_engine_primal:" if w["meth"] == "primal" else "k_engine_dual:"
-        roofline = {"bound": "hbm", "kernel": (eng + top[4:]) if top.startswith("eng_") else top,
-                    "achieved": ach, "peak": peak, "unit": "GB/s",
+        shares = {k: x["ms"] for k, x in units.items() if not k.startswith("eng_")}
+        shares[eng_name] = agg["ms"]
+        roofline = {"bound": "hbm", "kernel": top, "achieved": ach, "peak": peak, "unit": "GB/s",
                     "frac": ach / peak, "traffic": None, "peak_source": peak_src,
                     "bytes_per_launch": v["bytes"] / v["count"], "us_per_launch": 1000.0 * v["ms"] / v["count"],
                     "share_of_device_time": v["ms"] / tot_prof_ms,
-                    "note": "eng_* = phases of the persistent engine (one 'launch' = one iteration's phase)",
-                    "kernel_shares": {k: round(x["ms"] / tot_prof_ms, 4) for k, x in
-                                      sorted(units.items(), key=lambda kv: -kv[1]["ms"])[:10]},
-                    "phase_table": {k: {"us": round(1000.0 * x["ms"] / max(1, x["count"]), 3),
-                                        "GBps": round(x["bytes"] / max(1e-9, x["ms"]) / 1e6, 1)}
-                                    for k, x in sorted(units.items()) if k.startswith("eng_")},
+                    "note": "for the persistent engine one 'launch' = one simplex iteration (all phases); "
+                            "phase_table splits it (SM-cycle stamps of CTA 0 between grid barriers)",
+                    "kernel_shares": {k: round(x / tot_prof_ms, 4) for k, x in sorted(shares.items(), key=lambda kv: -kv[1])[:8]},
+                    "phase_table": {k[4:]: {"us": round(1000.0 * x["ms"] / max(1, x["count"]), 3),
+                                            "GBps": round(x["bytes"] / max(1e-9, x["ms"]) / 1e6, 1)}
+                                    for k, x in sorted(phases.items())},
                     "refactor_split_ms": {k[4:]: round(x["ms"], 2) for k, x in ref_split.items()}}
     P.close()
 
@@ -464,6 +472,8 @@ def main():
         c3cnt, s3 = P3.counters(), P3.solution()
         c3cnt["solve_us"] += us_a
         prof3 = {k: v for k, v in P3.profile().items() if k.startswith("eng_") and v["count"] > 0 and v["bytes"] > 0}
+        eng3_ms = sum(v["ms"] for v in prof3.values())
+        eng3_bytes = sum(v["bytes"] for v in prof3.values())
         P3.close()
         top3 = max(prof3, key=lambda k: prof3[k]["ms"]) if prof3 else None
         c3 = {"workload": w3["name"], "value": s3["it_cnt"] / (c3cnt["solve_us"] * 1e-6), "unit": "iter/s",
@@ -475,7 +485,10 @@ def main():
             ach3 = v3["bytes"] / (v3["ms"] * 1e-3) / 1e9
             c3["roofline"] = {"bound": "hbm", "kernel": "k_engine_dual:" + top3[4:], "achieved": ach3, "peak": peak,
                               "unit": "GB/s", "frac": ach3 / peak, "us_per_iteration": 1000.0 * v3["ms"] / v3["count"],
-                              "bytes_per_iteration": v3["bytes"] / v3["count"]}
+                              "bytes_per_iteration": v3["bytes"] / v3["count"],
+                              "whole_engine": {"achieved": eng3_bytes / max(1e-9, eng3_ms) / 1e6, "unit": "GB/s",
+                                               "frac": eng3_bytes / max(1e-9, eng3_ms) / 1e6 / peak,
+                                               "us_per_iteration": 1000.0 * eng3_ms / v3["count"]}}
         if not args.no_cpu_baseline:
             smp3 = CpuSampler(d3, w3)
             it3, dt3 = smp3.step()

@@ -1159,7 +1159,9 @@ __global__ void __launch_bounds__(ENG_NT, 1) k_engine_primal(EngArgs A)
             Key none = {0.0, 0.0, 0.0, 0, 0};
             Key acc = none;
             eng_ftran_tail<true>(X, A, S, A.hz, A.ycol, A.tcol, acc);
+            eng_mark(X, A, 9, 12.0 * (double)__ldg(A.at_ptr + m) * (1.0 - (double)S.k / m) + 29.0 * m);
             Key r = eng_allreduce(X, A, acc, none, CombSum2());
+            eng_mark(X, A, 10, 0.0);
             if (X.tid == 0) {
                 const double big = r.c;
                 S.tcol_max = big;
@@ -1188,31 +1190,62 @@ __global__ void __launch_bounds__(ENG_NT, 1) k_engine_primal(EngArgs A)
         /* ---- Harris ratio test (chuzr); the first half of u = inv(B') v rides along ---- */
         if (local_ratio) {
             if (pse) eng_btran_head(X, A, S.k);
+            eng_mark(X, A, 11, pse ? 12.0 * nnzA * ((double)S.k / n) + 16.0 * S.k : 0.0);
             Key none = {DBL_MAX, 0.0, 0.0, INT_MAX, 0};
             Key v = none;
             if (X.tid == 0 && A.type[kq] == GLP_DB) {
                 v.a = __dsub_rn(A.ub[kq], A.lb[kq]); v.b = 1.0; v.pos = -1; v.aux = 0;
             }
-            scan_ratio_primal(v, X.tid, ENG_NT, 1, S.phase, sgn, S.eps, 0.0, A.rtol, A.type, A.lb, A.ub,
-                              A.coef, A.head, A.bbar, A.tcol, nullptr, m);
-            Key r = eng_blockall(X, v, none, CombRatio1());
-            if (X.tid == 0) fin_ratio_primal(&S, r, 1, sgn, A.rtol, A.type, A.head, A.tcol, nullptr);
-            __syncthreads();
-            if (S.status == ST_OK && !S.skip2) {
-                v = none;
-                scan_ratio_primal(v, X.tid, ENG_NT, 2, S.phase, sgn, S.eps, S.tmax, A.rtol, A.type, A.lb, A.ub,
-                                  A.coef, A.head, A.bbar, A.tcol, nullptr, m);
-                r = eng_blockall(X, v, none, CombRatio2());
-                if (X.tid == 0) fin_ratio_primal(&S, r, 2, sgn, A.rtol, A.type, A.head, A.tcol, nullptr);
+            if (m <= 2 * ENG_NT) {
+                /* both passes from ONE scan of memory: every thread keeps its (at most two)
+                   candidates in registers, exact and relaxed ratio alike */
+                RatioCand cand[2];
+                bool ok[2];
+#pragma unroll
+                for (int x = 0; x < 2; x++) {
+                    const int pos = X.tid + x * ENG_NT;
+                    ok[x] = (pos < m) && ratio_primal_elem(cand[x], pos, S.phase, sgn, S.eps, A.rtol, A.type, A.lb, A.ub,
+                                                           A.coef, A.head, A.bbar, A.tcol);
+                    if (ok[x]) { const Key c = ratio_primal_key(cand[x], 1, pos); CombRatio1()(v, c); }
+                }
+                Key r = eng_blockall(X, v, none, CombRatio1());
+                if (X.tid == 0) fin_ratio_primal(&S, r, 1, sgn, A.rtol, nullptr);
                 __syncthreads();
+                if (S.status == ST_OK && !S.skip2) {
+                    const double tmax = S.tmax;
+                    v = none;
+#pragma unroll
+                    for (int x = 0; x < 2; x++)
+                        if (ok[x] && cand[x].t2 <= tmax) {
+                            const Key c = ratio_primal_key(cand[x], 2, X.tid + x * ENG_NT);
+                            CombRatio2()(v, c);
+                        }
+                    r = eng_blockall(X, v, none, CombRatio2());
+                    if (X.tid == 0) fin_ratio_primal(&S, r, 2, sgn, A.rtol, nullptr);
+                    __syncthreads();
+                }
+            } else {
+                scan_ratio_primal(v, X.tid, ENG_NT, 1, S.phase, sgn, S.eps, 0.0, A.rtol, A.type, A.lb, A.ub,
+                                  A.coef, A.head, A.bbar, A.tcol, nullptr, m);
+                Key r = eng_blockall(X, v, none, CombRatio1());
+                if (X.tid == 0) fin_ratio_primal(&S, r, 1, sgn, A.rtol, nullptr);
+                __syncthreads();
+                if (S.status == ST_OK && !S.skip2) {
+                    v = none;
+                    scan_ratio_primal(v, X.tid, ENG_NT, 2, S.phase, sgn, S.eps, S.tmax, A.rtol, A.type, A.lb, A.ub,
+                                      A.coef, A.head, A.bbar, A.tcol, nullptr, m);
+                    r = eng_blockall(X, v, none, CombRatio2());
+                    if (X.tid == 0) fin_ratio_primal(&S, r, 2, sgn, A.rtol, nullptr);
+                    __syncthreads();
+                }
             }
+            eng_mark(X, A, PP_R1, 45.0 * m * (S.skip2 ? 1.0 : 2.0));
             /* one barrier: w (first half of u) is complete, and nobody still scans bbar/tcol
                when the update phase of a bound flip rewrites bbar */
             eng_bar(X, A);
-            eng_mark(X, A, PP_B, 12.0 * (double)__ldg(A.at_ptr + m) * (1.0 - (double)S.k / m) + 29.0 * m + 90.0 * m +
-                                 (pse ? 12.0 * nnzA * ((double)S.k / n) + 16.0 * S.k : 0.0));
+            eng_mark(X, A, PP_B, 0.0);
         } else {
-            eng_mark(X, A, PP_B, 12.0 * (double)__ldg(A.at_ptr + m) * (1.0 - (double)S.k / m) + 29.0 * m);
+            eng_mark(X, A, PP_B, 0.0);
             Key none = {DBL_MAX, 0.0, 0.0, INT_MAX, 0};
             Key v = none;
             if (X.gtid == 0 && A.type[kq] == GLP_DB) {
@@ -1224,7 +1257,7 @@ __global__ void __launch_bounds__(ENG_NT, 1) k_engine_primal(EngArgs A)
             Key r = eng_allreduce(X, A, v, none, CombRatio1());
             if (X.cta == 0 && X.tid == 0) A.cbar[q] = S.d1;     /* every CTA has read the old value by now */
             cbar_q_pending = false;
-            if (X.tid == 0) fin_ratio_primal(&S, r, 1, sgn, A.rtol, A.type, A.head, A.tcol, nullptr);
+            if (X.tid == 0) fin_ratio_primal(&S, r, 1, sgn, A.rtol, nullptr);
             __syncthreads();
             eng_mark(X, A, PP_R1, 45.0 * m);
             if (S.status == ST_OK && !S.skip2) {
@@ -1232,7 +1265,7 @@ __global__ void __launch_bounds__(ENG_NT, 1) k_engine_primal(EngArgs A)
                 scan_ratio_primal(v, X.gtid, X.gsize, 2, S.phase, sgn, S.eps, S.tmax, A.rtol, A.type, A.lb, A.ub,
                                   A.coef, A.head, A.bbar, A.tcol, nullptr, m);
                 r = eng_allreduce(X, A, v, none, CombRatio2());
-                if (X.tid == 0) fin_ratio_primal(&S, r, 2, sgn, A.rtol, A.type, A.head, A.tcol, nullptr);
+                if (X.tid == 0) fin_ratio_primal(&S, r, 2, sgn, A.rtol, nullptr);
                 __syncthreads();
                 eng_mark(X, A, PP_R2, 45.0 * m);
             }
@@ -1454,13 +1487,13 @@ __global__ void __launch_bounds__(ENG_NT, 1) k_engine_dual(EngArgs A)
             Key v = none;
             scan_ratio_dual(v, X.tid, ENG_NT, 1, sgn, S.eps, 0.0, A.rtol, A.stat, A.cbar, A.trow, nullptr, n);
             Key r = eng_blockall(X, v, none, CombRatio1());
-            if (X.tid == 0) fin_ratio_dual(&S, r, 1, sgn, A.rtol, A.trow, nullptr);
+            if (X.tid == 0) fin_ratio_dual(&S, r, 1, sgn, A.rtol, nullptr);
             __syncthreads();
             if (S.status == ST_OK && !S.skip2) {
                 v = none;
                 scan_ratio_dual(v, X.tid, ENG_NT, 2, sgn, S.eps, S.tmax, A.rtol, A.stat, A.cbar, A.trow, nullptr, n);
                 r = eng_blockall(X, v, none, CombRatio2());
-                if (X.tid == 0) fin_ratio_dual(&S, r, 2, sgn, A.rtol, A.trow, nullptr);
+                if (X.tid == 0) fin_ratio_dual(&S, r, 2, sgn, A.rtol, nullptr);
                 __syncthreads();
             }
             if (S.status != ST_OK) break;
@@ -1475,7 +1508,7 @@ __global__ void __launch_bounds__(ENG_NT, 1) k_engine_dual(EngArgs A)
             scan_ratio_dual(v, X.gtid, X.gsize, 1, sgn, S.eps, 0.0, A.rtol, A.stat, A.cbar, A.trow, nullptr, n);
             if (pse) eng_gamma_rhs(X, A);
             Key r = eng_allreduce(X, A, v, none, CombRatio1());
-            if (X.tid == 0) fin_ratio_dual(&S, r, 1, sgn, A.rtol, A.trow, nullptr);
+            if (X.tid == 0) fin_ratio_dual(&S, r, 1, sgn, A.rtol, nullptr);
             __syncthreads();
             eng_mark(X, A, PD_R1, 17.0 * n + (pse ? 17.0 * nnzA + 16.0 * m : 0.0));
             if (S.status != ST_OK) break;
@@ -1496,7 +1529,7 @@ __global__ void __launch_bounds__(ENG_NT, 1) k_engine_dual(EngArgs A)
                 v = none;
                 scan_ratio_dual(v, X.gtid, X.gsize, 2, sgn, S.eps, S.tmax, A.rtol, A.stat, A.cbar, A.trow, nullptr, n);
                 r = eng_allreduce(X, A, v, none, CombRatio2());
-                if (X.tid == 0) fin_ratio_dual(&S, r, 2, sgn, A.rtol, A.trow, nullptr);
+                if (X.tid == 0) fin_ratio_dual(&S, r, 2, sgn, A.rtol, nullptr);
                 __syncthreads();
                 eng_mark(X, A, PD_R2, 17.0 * n + (need_z ? 16.0 * nd * S.k : 0.0));
                 if (S.status != ST_OK) break;

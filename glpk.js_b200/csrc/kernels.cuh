@@ -279,6 +279,52 @@ __global__ void k_chuzr_dual(Ctrl *ctrl, int m, const signed char *__restrict__ 
    the caller's sorted list (kernel parity).  Ties are broken by list position,
    as the sequential loop does.  Shared by the stand-alone kernel and the engine.
    Algorithmic bytes: 49 per examined entry and pass. */
+/* one candidate of the primal ratio test: both the ratio against the relaxed
+   bound (pass 1) and against the exact bound (pass 2), the pivot |alfa|, the
+   status the leaving variable would take, the signed tcol entry and whether the
+   variable is fixed.  Returns false if position i gives no ratio. */
+struct RatioCand {
+    double t1, t2, aabs, tc;
+    int i_stat, fx;
+};
+__device__ __forceinline__ bool ratio_primal_elem(RatioCand &C, int i, int phase, double s, double eps, double rtol,
+                                                  const signed char *type, const double *lb, const double *ub,
+                                                  const double *coef, const int *head, const double *bbar,
+                                                  const double *tcol)
+{
+    const double tc = tcol[i];
+    if (tc == 0.0 || fabs(tc) < eps) return false;
+    const int k = head[i];
+    const double alfa = __dmul_rn(s, tc), bi = bbar[i];
+    const int tk = type[k];
+    const double ck = (phase == 1 ? coef[k] : 0.0);
+    double b, r1;
+    int i_stat;
+    if (alfa > 0.0) {
+        if (phase == 1 && ck < 0.0) { b = lb[k]; r1 = __dadd_rn(b, relax(rtol, b)); i_stat = GLP_NL; }
+        else if (phase == 1 && ck > 0.0) return false;
+        else if (tk == GLP_UP || tk == GLP_DB || tk == GLP_FX) { b = ub[k]; r1 = __dadd_rn(b, relax(rtol, b)); i_stat = GLP_NU; }
+        else return false;
+    } else {
+        if (phase == 1 && ck > 0.0) { b = ub[k]; r1 = __dsub_rn(b, relax(rtol, b)); i_stat = GLP_NU; }
+        else if (phase == 1 && ck < 0.0) return false;
+        else if (tk == GLP_LO || tk == GLP_DB || tk == GLP_FX) { b = lb[k]; r1 = __dsub_rn(b, relax(rtol, b)); i_stat = GLP_NL; }
+        else return false;
+    }
+    double t1 = __ddiv_rn(__dsub_rn(r1, bi), alfa), t2 = __ddiv_rn(__dsub_rn(b, bi), alfa);
+    if (t1 < 0.0) t1 = 0.0;
+    if (t2 < 0.0) t2 = 0.0;
+    C.t1 = t1; C.t2 = t2; C.aabs = fabs(alfa); C.tc = tc; C.i_stat = i_stat; C.fx = (tk == GLP_FX);
+    return true;
+}
+
+/* key of a candidate: a = ratio, b = |alfa|, c = signed tcol entry, aux = status (+256 if the variable is fixed) */
+__device__ __forceinline__ Key ratio_primal_key(const RatioCand &C, int pass, int pos)
+{
+    Key c = {pass == 1 ? C.t1 : C.t2, C.aabs, C.tc, pos, C.i_stat | (C.fx ? 256 : 0)};
+    return c;
+}
+
 __device__ __forceinline__ void scan_ratio_primal(Key &v, int start, int stride, int pass, int phase,
                                                   double s, double eps, double tmax, double rtol,
                                                   const signed char *type, const double *lb,
@@ -287,55 +333,21 @@ __device__ __forceinline__ void scan_ratio_primal(Key &v, int start, int stride,
                                                   const int *ind, int num)
 {
     for (int pos = start; pos < num; pos += stride) {
-        int i = ind ? ind[pos] : pos;
-        double tc = tcol[i];
-        if (tc == 0.0 || fabs(tc) < eps) continue;
-        int k = head[i];
-        double alfa = __dmul_rn(s, tc), t, bi = bbar[i];
-        int tk = type[k], i_stat;
-        double ck = (phase == 1 ? coef[k] : 0.0);
-        if (alfa > 0.0) {
-            if (phase == 1 && ck < 0.0) {
-                double b = lb[k];
-                t = (pass == 1) ? __dadd_rn(b, relax(rtol, b)) : b;
-                i_stat = GLP_NL;
-            } else if (phase == 1 && ck > 0.0)
-                continue;
-            else if (tk == GLP_UP || tk == GLP_DB || tk == GLP_FX) {
-                double b = ub[k];
-                t = (pass == 1) ? __dadd_rn(b, relax(rtol, b)) : b;
-                i_stat = GLP_NU;
-            } else
-                continue;
-        } else {
-            if (phase == 1 && ck > 0.0) {
-                double b = ub[k];
-                t = (pass == 1) ? __dsub_rn(b, relax(rtol, b)) : b;
-                i_stat = GLP_NU;
-            } else if (phase == 1 && ck < 0.0)
-                continue;
-            else if (tk == GLP_LO || tk == GLP_DB || tk == GLP_FX) {
-                double b = lb[k];
-                t = (pass == 1) ? __dsub_rn(b, relax(rtol, b)) : b;
-                i_stat = GLP_NL;
-            } else
-                continue;
-        }
-        t = __ddiv_rn(__dsub_rn(t, bi), alfa);
-        if (t < 0.0) t = 0.0;
-        Key c = {t, fabs(alfa), 0.0, pos, i_stat};
+        const int i = ind ? ind[pos] : pos;
+        RatioCand C;
+        if (!ratio_primal_elem(C, i, phase, s, eps, rtol, type, lb, ub, coef, head, bbar, tcol)) continue;
+        const Key c = ratio_primal_key(C, pass, pos);
         if (pass == 1) CombRatio1()(v, c);
-        else if (t <= tmax) CombRatio2()(v, c);
+        else if (c.a <= tmax) CombRatio2()(v, c);
     }
 }
 
 /* what the reference does with the winner of a pass (chuzr, :1009-1028, and
    the pivot-size test of the main loop, :1960-1975) */
 __device__ __forceinline__ void fin_ratio_primal(Ctrl *ctrl, const Key &r, int pass, double s, double rtol,
-                                                 const signed char *type, const int *head,
-                                                 const double *tcol, const int *ind)
+                                                 const int *ind)
 {
-    int p, p_stat = r.aux;
+    int p, p_stat = r.aux & 255;
     double teta = r.a;
     if (r.pos == INT_MAX) p = P_NONE;
     else if (r.pos == -1) p = P_FLIP;
@@ -345,13 +357,13 @@ __device__ __forceinline__ void fin_ratio_primal(Ctrl *ctrl, const Key &r, int p
         ctrl->tmax = teta;
         if (!ctrl->skip2) { ctrl->p = p; return; }
     }
-    if (p >= 0 && type[head[p]] == GLP_FX) p_stat = GLP_NS;
+    if (p >= 0 && (r.aux & 256)) p_stat = GLP_NS;        /* a fixed variable leaves: lib/glpspx01.js:1019 */
     ctrl->p = p;
     ctrl->p_stat = p_stat;
     ctrl->teta = __dmul_rn(s, teta);
     if (p == P_NONE) { ctrl->status = ST_NONE2; return; }
     if (p >= 0) {
-        double piv = tcol[p];
+        double piv = r.c;                                  /* tcol[p], carried by the key */
         double e5 = 1e-5 * (1.0 + 0.01 * ctrl->tcol_max);
         ctrl->piv1 = piv;
         if (fabs(piv) < e5 && !ctrl->rigorous) ctrl->status = ST_PIVSMALL;
@@ -379,7 +391,7 @@ __device__ __forceinline__ void ratio_primal_body(Ctrl *ctrl, int pass, int m, c
     }
     scan_ratio_primal(v, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x, pass, phase, s, eps, tmax,
                       rtol, type, lb, ub, coef, head, bbar, tcol, ind, num);
-    auto fin = [=](const Key &r) { fin_ratio_primal(ctrl, r, pass, s, rtol, type, head, tcol, ind); };
+    auto fin = [=](const Key &r) { fin_ratio_primal(ctrl, r, pass, s, rtol, ind); };
     if (pass == 1) grid_reduce(v, none, scratch, &ctrl->ticket[1], CombRatio1(), fin);
     else grid_reduce(v, none, scratch, &ctrl->ticket[1], CombRatio2(), fin);
 }
@@ -400,34 +412,48 @@ __global__ void k_ratio_primal(Ctrl *ctrl, int pass, int m, const signed char *_
 
 /* chuzc (dual ratio test), lib/glpspx02.js:793-935: scan of one pass.
    Algorithmic bytes: 21 per examined entry and pass (idx 4, trow 8, stat 1, cbar 8). */
+struct RatioCandD {
+    double t1, t2, aabs, tr;
+};
+__device__ __forceinline__ bool ratio_dual_elem(RatioCandD &C, int j, double s, double eps, double rtol,
+                                                const signed char *stat, const double *cbar, const double *trow)
+{
+    const double tr = trow[j];
+    if (tr == 0.0 || fabs(tr) < eps) return false;
+    const double alfa = __dmul_rn(s, tr);
+    const int st = stat[j];
+    double d = cbar[j], r1;
+    if (alfa > 0.0) {
+        if (st == GLP_NL || st == GLP_NF) r1 = __dadd_rn(d, rtol);
+        else return false;
+    } else {
+        if (st == GLP_NU || st == GLP_NF) r1 = __dsub_rn(d, rtol);
+        else return false;
+    }
+    double t1 = __ddiv_rn(r1, alfa), t2 = __ddiv_rn(d, alfa);
+    if (t1 < 0.0) t1 = 0.0;
+    if (t2 < 0.0) t2 = 0.0;
+    C.t1 = t1; C.t2 = t2; C.aabs = fabs(alfa); C.tr = tr;
+    return true;
+}
+
 __device__ __forceinline__ void scan_ratio_dual(Key &v, int start, int stride, int pass, double s, double eps,
                                                 double tmax, double rtol, const signed char *stat,
                                                 const double *cbar, const double *trow, const int *ind,
                                                 int num)
 {
     for (int pos = start; pos < num; pos += stride) {
-        int j = ind ? ind[pos] : pos;
-        double tr = trow[j];
-        if (tr == 0.0 || fabs(tr) < eps) continue;
-        double alfa = __dmul_rn(s, tr), t;
-        int st = stat[j];
-        if (alfa > 0.0) {
-            if (st == GLP_NL || st == GLP_NF) t = (pass == 1) ? __dadd_rn(cbar[j], rtol) : cbar[j];
-            else continue;
-        } else {
-            if (st == GLP_NU || st == GLP_NF) t = (pass == 1) ? __dsub_rn(cbar[j], rtol) : cbar[j];
-            else continue;
-        }
-        t = __ddiv_rn(t, alfa);
-        if (t < 0.0) t = 0.0;
-        Key c = {t, fabs(alfa), 0.0, pos, 0};
+        const int j = ind ? ind[pos] : pos;
+        RatioCandD C;
+        if (!ratio_dual_elem(C, j, s, eps, rtol, stat, cbar, trow)) continue;
+        const Key c = {pass == 1 ? C.t1 : C.t2, C.aabs, C.tr, pos, 0};       /* c = signed trow entry */
         if (pass == 1) CombRatio1()(v, c);
-        else if (t <= tmax) CombRatio2()(v, c);
+        else if (c.a <= tmax) CombRatio2()(v, c);
     }
 }
 
 __device__ __forceinline__ void fin_ratio_dual(Ctrl *ctrl, const Key &r, int pass, double s, double rtol,
-                                               const double *trow, const int *ind)
+                                               const int *ind)
 {
     int q = (r.pos == INT_MAX) ? P_NONE : (ind ? ind[r.pos] : r.pos);
     double teta = r.a;
@@ -439,7 +465,7 @@ __device__ __forceinline__ void fin_ratio_dual(Ctrl *ctrl, const Key &r, int pas
     ctrl->q = q;
     ctrl->new_dq = __dmul_rn(s, teta);
     if (q == P_NONE) { ctrl->status = ST_NONE2; return; }
-    double piv = trow[q];
+    double piv = r.c;                                      /* trow[q], carried by the key */
     double e5 = 1e-5 * (1.0 + 0.01 * ctrl->trow_max);
     ctrl->piv2 = piv;
     if (fabs(piv) < e5 && !ctrl->rigorous) ctrl->status = ST_PIVSMALL;
@@ -459,7 +485,7 @@ __device__ __forceinline__ void ratio_dual_body(Ctrl *ctrl, int pass, const sign
     Key v = none;
     scan_ratio_dual(v, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x, pass, s, eps, tmax, rtol,
                     stat, cbar, trow, ind, num);
-    auto fin = [=](const Key &r) { fin_ratio_dual(ctrl, r, pass, s, rtol, trow, ind); };
+    auto fin = [=](const Key &r) { fin_ratio_dual(ctrl, r, pass, s, rtol, ind); };
     if (pass == 1) grid_reduce(v, none, scratch, &ctrl->ticket[1], CombRatio1(), fin);
     else grid_reduce(v, none, scratch, &ctrl->ticket[1], CombRatio2(), fin);
 }

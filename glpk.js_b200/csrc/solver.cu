@@ -1533,8 +1533,8 @@ extern "C" const char *glpb_profile_report(glpb_prob *P)
     double byt[24];
     if (cudaMemcpy(cyc, P->eng_cyc, sizeof cyc, cudaMemcpyDeviceToHost) == cudaSuccess &&
         cudaMemcpy(byt, P->eng_bytes, sizeof byt, cudaMemcpyDeviceToHost) == cudaSuccess) {
-        static const char *pn[24] = {"P0_chuzc_first", "PA_tcol_head", "PB_tcol_tail_prep_ratio", "PR1_ratio1", "PR2_ratio2",
-                                     "PC_rho_btran_head", "PD_gemvT", "PE_trow_svec", "PF_update_T_chuzc", "P9", "P10", "P11",
+        static const char *pn[24] = {"P0_chuzc_first", "PA_tcol_head", "PB5_barrier", "PB4_ratio_local", "PR2_ratio2",
+                                     "PC_rho_gemvT", "PD_unused", "PE_trow_svec", "PF_update_T_chuzc", "PB1_tail", "PB2_allreduce", "PB3_btran_head",
                                      "D0_chuzr_first", "D1_rho", "D2_trow", "DR1_ratio1_gamma_rhs", "DR2_ratio2",
                                      "DX_ratio_local_gamma_rhs", "D3_gemvN_tcol_head", "D4_tcol_tail_utail",
                                      "D5_update_T_chuzr", "D9", "D10", "D11"};
