@@ -72,6 +72,7 @@ struct EngArgs {
     double *zbuf;             /* [ENG_DB] Rd_j' v for the dense product          */
     int defer;                /* 1: deferral allowed                             */
     int use_tma;              /* 1: TMA-staged dense T*v stream where it applies */
+    int hdr_smem;             /* 1: keep per-CTA copies of the basis header in shared memory */
     int local_max;            /* ratio tests up to this length are replicated per CTA */
     int *rslot, *slot_pos, *cslot, *slot_row;
     EngSlot *slots;           /* [ENG_RING][ENG_MAXG] arrival flags + CTA partials, zeroed by the host */
@@ -87,6 +88,13 @@ struct EngCtx {
     double *sh_d;             /* [dcap] staging values / dense vector            */
     int *sh_i;                /* [ENG_LCAP] staging indices                      */
     double *sh_red2;          /* [32][65] cross-warp sums of the dense T*v stream */
+    /* the basis header and the slot maps as the engine reads them: the arrays in
+       global memory, or -- small problems -- per-CTA copies in shared memory that
+       every CTA keeps up to date itself (an index lookup then costs a shared-memory
+       access instead of an L2 round trip inside every dependent-load chain) */
+    int *head, *bind, *rslot, *slot_pos, *cslot, *slot_row;
+    signed char *stat;
+    int hdr_local;            /* 1: the pointers above are this CTA's private copies */
 };
 
 __device__ __forceinline__ unsigned int eng_ld_relaxed(const unsigned int *p)
@@ -138,7 +146,7 @@ __device__ __forceinline__ void eng_bar(EngCtx &X, const EngArgs &A)
 __device__ __forceinline__ void eng_header_done(EngCtx &X, const EngArgs &A)
 {
     X.dseq++;
-    if (X.G > 1) {
+    if (X.G > 1 && !X.hdr_local) {
         unsigned int *done = &A.slots[ENG_RING * ENG_MAXG].flag;
         __syncthreads();        /* CTA 0: thread 0's header writes are ordered before the release */
         if (X.tid == 0) {
@@ -388,7 +396,7 @@ __device__ void eng_gemv_rows(const EngCtx &X, const EngArgs &A, int k, int L, c
                     for (int j = 0; j < nd; j++) s += A.Fd[(size_t)j * ldt + b2] * z[j];
                     if (accumulate) s += y[b2];
                     y[b2] = s;
-                    ycol[A.head[A.slot_pos[b2]] - A.m] = s;
+                    ycol[X.head[X.slot_pos[b2]] - A.m] = s;
                 }
             }
             __syncthreads();
@@ -438,7 +446,7 @@ __device__ void eng_gemv_rows(const EngCtx &X, const EngArgs &A, int k, int L, c
                 for (int j = 0; j < nd; j++) s += A.Fd[(size_t)j * ldt + b2] * z[j];
                 if (accumulate) s += y[b2];
                 y[b2] = s;
-                ycol[A.head[A.slot_pos[b2]] - A.m] = s;      /* the same value by basic column */
+                ycol[X.head[X.slot_pos[b2]] - A.m] = s;      /* the same value by basic column */
             }
         }
         __syncthreads();
@@ -566,7 +574,7 @@ __device__ void eng_gemv_dense_tma(const EngCtx &X, const EngArgs &A, int k, con
         const int b2 = q0 + X.tid;
         for (int j = 0; j < nd; j++) sum += A.Fd[(size_t)j * ldt + b2] * z[j];
         y[b2] = sum;
-        ycol[A.head[A.slot_pos[b2]] - A.m] = sum;
+        ycol[X.head[X.slot_pos[b2]] - A.m] = sum;
     }
     __syncthreads();
     if (X.tid == 0)
@@ -587,7 +595,7 @@ __device__ void eng_ftran_head_col(EngCtx &X, const EngArgs &A, int k, int kq, d
     if (!work && X.cta != 0) return;
     if (kq < m) {
         if (X.tid == 0) {
-            X.sh_i[0] = A.cslot[kq]; X.sh_d[0] = -1.0;
+            X.sh_i[0] = X.cslot[kq]; X.sh_d[0] = -1.0;
             if (X.cta == 0) A.hz[kq] = -1.0;
         }
         __syncthreads();
@@ -607,7 +615,7 @@ __device__ void eng_ftran_head_col(EngCtx &X, const EngArgs &A, int k, int kq, d
             int r = 0, cs = -1;
             double a = 0.0;
             if (valid) {
-                r = __ldg(A.a_ind + e); a = __ldg(A.a_val + e); cs = A.cslot[r];
+                r = __ldg(A.a_ind + e); a = __ldg(A.a_val + e); cs = X.cslot[r];
                 if (X.cta == 0) A.hz[r] = a;
             }
             int tot;
@@ -641,11 +649,11 @@ __device__ __forceinline__ void eng_ftran_tail(const EngCtx &X, const EngArgs &A
     const int LP = eng_pick_lp(X, m, A.avg_row);
     eng_items<1>(X, m, LP,
         [&](int i, int l, int lp, double *a) {
-            const int kk = A.head[i];
+            const int kk = X.head[i];
             if (kk < m) a[0] = eng_spdot(A.at_ind, A.at_val, __ldg(A.at_ptr + kk), __ldg(A.at_ptr + kk + 1), l, lp, ycol);
         },
         [&](int i, const double *a) {
-            const int kk = A.head[i];
+            const int kk = X.head[i];
             const double t = (kk < m) ? h[kk] + a[0] : ycol[kk - m];
             x[i] = t;
             if (PREP) {
@@ -669,10 +677,10 @@ __device__ __forceinline__ void eng_btran_head(const EngCtx &X, const EngArgs &A
     const int LP = eng_pick_lp(X, k, A.avg_col);
     eng_items<1>(X, k, LP,
         [&](int b, int l, int lp, double *a) {
-            const int j = A.head[A.slot_pos[b]] - m;
+            const int j = X.head[X.slot_pos[b]] - m;
             a[0] = eng_spdot(A.a_ind, A.a_val, __ldg(A.a_ptr + j), __ldg(A.a_ptr + j + 1), l, lp, A.vrow);
         },
-        [&](int b, const double *a) { A.wk[b] = A.v[A.slot_pos[b]] + a[0]; });
+        [&](int b, const double *a) { A.wk[b] = A.v[X.slot_pos[b]] + a[0]; });
 }
 
 /* zn[cs] = sum_b T[b, cs] w[b]: column dots, coalesced.  8 k^2 bytes. */
@@ -702,18 +710,18 @@ __device__ void eng_rho(EngCtx &X, const EngArgs &A, int k, int p, int nd)
     __shared__ double fs[ENG_DB];
     const int m = A.m;
     const size_t ldt = (size_t)A.ldt;
-    const int kp = A.head[p];
+    const int kp = X.head[p];
     for (int r = X.gtid; r < m; r += X.gsize)
-        if (A.cslot[r] < 0) A.rho[r] = (A.bind[r] == p) ? 1.0 : 0.0;
+        if (X.cslot[r] < 0) A.rho[r] = (X.bind[r] == p) ? 1.0 : 0.0;
     if (kp >= m) {
-        const int bp = A.rslot[p];
+        const int bp = X.rslot[p];
         if (X.tid < nd) fs[X.tid] = A.Fd[(size_t)X.tid * ldt + bp];
         if (nd > 0) __syncthreads();
         const double *row = A.T + bp;
         for (int cs = X.gtid; cs < k; cs += X.gsize) {
             double a = __ldcg(row + (size_t)cs * ldt);
             for (int j = 0; j < nd; j++) a += fs[j] * A.Rd[(size_t)j * ldt + cs];
-            A.rho[A.slot_row[cs]] = a;
+            A.rho[X.slot_row[cs]] = a;
         }
         return;
     }
@@ -728,10 +736,10 @@ __device__ void eng_rho(EngCtx &X, const EngArgs &A, int k, int p, int nd)
             const bool valid = e < segend;
             int pb = m;
             double a = 0.0;
-            if (valid) { pb = A.bind[m + __ldg(A.at_ind + e)]; a = __ldg(A.at_val + e); }
+            if (valid) { pb = X.bind[m + __ldg(A.at_ind + e)]; a = __ldg(A.at_val + e); }
             int tot;
             const int pos = eng_compact(X, valid && pb < m, tot);
-            if (valid && pb < m) { X.sh_i[L + pos] = A.rslot[pb]; X.sh_d[L + pos] = a; }
+            if (valid && pb < m) { X.sh_i[L + pos] = X.rslot[pb]; X.sh_d[L + pos] = a; }
             L += tot;
         }
         __syncthreads();
@@ -757,7 +765,7 @@ __device__ void eng_rho(EngCtx &X, const EngArgs &A, int k, int p, int nd)
                 a[0] = a0 + a1;
             },
             [&](int cs, const double *a) {
-                const int r = A.slot_row[cs];
+                const int r = X.slot_row[cs];
                 double v = a[0];
                 for (int j = 0; j < nd; j++) v += fs[j] * A.Rd[(size_t)j * ldt + cs];
                 A.rho[r] = acc ? A.rho[r] + v : v;
@@ -780,8 +788,8 @@ __device__ __forceinline__ void eng_trow(const EngCtx &X, const EngArgs &A, cons
     const int LP = eng_pick_lp(X, n, A.avg_col);
     eng_items<2>(X, n, LP,
         [&](int j, int l, int lp, double *a) {
-            if (A.stat[j] == GLP_NS) return;
-            const int k = A.head[m + j];
+            if (X.stat[j] == GLP_NS) return;
+            const int k = X.head[m + j];
             if (k < m) {
                 if (l == 0) { a[0] = -A.rho[k]; if (want_s) a[1] = A.u[k]; }
                 return;
@@ -815,7 +823,7 @@ __device__ __forceinline__ void eng_trow(const EngCtx &X, const EngArgs &A, cons
             if (want_s) A.svec[j] = a[1];
             if (DUAL) {
                 acc.c = fmax(acc.c, fabs(t));
-                const int k = A.head[m + j];
+                const int k = X.head[m + j];
                 const bool in = pse && t != 0.0 && A.refsp[k];
                 if (in) acc.a += t * t;
                 if (k >= m) A.trowcol[k - m] = in ? t : 0.0;
@@ -835,10 +843,10 @@ __device__ __forceinline__ void eng_gamma_rhs(const EngCtx &X, const EngArgs &A)
             a[0] = -eng_spdot(A.at_ind, A.at_val, __ldg(A.at_ptr + row), __ldg(A.at_ptr + row + 1), l, lp, A.trowcol);
         },
         [&](int row, const double *a) {
-            const int pr = A.bind[row];
+            const int pr = X.bind[row];
             const double val = a[0] + ((pr >= m && A.refsp[row]) ? A.trow[pr - m] : 0.0);
             A.v[row] = val;
-            const int cs = A.cslot[row];
+            const int cs = X.cslot[row];
             if (cs >= 0) A.wk[cs] = val;
         });
 }
@@ -849,15 +857,15 @@ struct EngChange {
     double tp;
 };
 
-__device__ __forceinline__ void eng_describe_change(const EngArgs &A, const Ctrl &S, EngChange &C)
+__device__ __forceinline__ void eng_describe_change(const EngCtx &X, const EngArgs &A, const Ctrl &S, EngChange &C)
 {
     const int m = A.m;
     C.p = S.p; C.q = S.q; C.k = S.k;
-    C.kp = A.head[C.p]; C.kq = A.head[m + C.q];
+    C.kp = X.head[C.p]; C.kq = X.head[m + C.q];
     C.LS = (C.kp < m); C.ES = (C.kq < m);
     C.tp = A.tcol[C.p];
-    C.csq = C.ES ? A.cslot[C.kq] : -1;
-    C.bp = C.LS ? -1 : A.rslot[C.p];
+    C.csq = C.ES ? X.cslot[C.kq] : -1;
+    C.bp = C.LS ? -1 : X.rslot[C.p];
     C.ctgt = C.LS ? (C.ES ? C.csq : C.k) : -1;
     C.bnew = (C.LS && !C.ES) ? C.k : -1;
     C.knew = C.k;
@@ -887,7 +895,7 @@ __device__ void eng_update_T(const EngCtx &X, const EngArgs &A, const EngChange 
         const int c0 = (tile / ntr) * ENG_UC;
         if (b >= kd) continue;
         const int sb = (removal && b == C.bp) ? k - 1 : b;
-        const int i = A.slot_pos[sb];
+        const int i = X.slot_pos[sb];
         const bool isp = (i == C.p);
         const double f = isp ? -1.0 / tp : A.tcol[i] / tp;
 #pragma unroll
@@ -897,7 +905,7 @@ __device__ void eng_update_T(const EngCtx &X, const EngArgs &A, const EngChange 
             double *dst = A.T + (size_t)cs * ldt + b;
             if (C.LS && C.ES && cs == C.csq) { *dst = -A.tcol[i] / tp; continue; }
             const int scs = (removal && cs == C.csq) ? k - 1 : cs;
-            const double rs = A.rho[A.slot_row[scs]];
+            const double rs = A.rho[X.slot_row[scs]];
             if (isp) { *dst = rs * f; continue; }
             const bool moved = (sb != b) || (scs != cs);
             if (f != 0.0 || moved) {
@@ -909,8 +917,8 @@ __device__ void eng_update_T(const EngCtx &X, const EngArgs &A, const EngChange 
     if (C.bnew >= 0) {
         /* a row and a column join: column k (rows 0..k) and row k (columns 0..k-1) */
         for (int t = X.gtid; t < 2 * k + 1; t += X.gsize) {
-            if (t < k) A.T[(size_t)k * ldt + t] = -A.tcol[A.slot_pos[t]] / tp;
-            else if (t < 2 * k) A.T[(size_t)(t - k) * ldt + k] = -A.rho[A.slot_row[t - k]] / tp;
+            if (t < k) A.T[(size_t)k * ldt + t] = -A.tcol[X.slot_pos[t]] / tp;
+            else if (t < 2 * k) A.T[(size_t)(t - k) * ldt + k] = -A.rho[X.slot_row[t - k]] / tp;
             else A.T[(size_t)k * ldt + k] = -1.0 / tp;
         }
     }
@@ -932,19 +940,19 @@ __device__ void eng_defer_apply(const EngCtx &X, const EngArgs &A, const EngChan
     const int skipF = removal ? C.bp : -1;
     const int skipR = (removal || (C.LS && C.ES)) ? C.csq : -1;
     for (int t = X.gtid; t < k; t += X.gsize) {
-        const int i = A.slot_pos[t];
+        const int i = X.slot_pos[t];
         if (t != skipF) Fn[t] = (i == C.p) ? 0.0 : -A.tcol[i] / tp;    /* row of p: replaced below */
-        if (t != skipR) Rn[t] = A.rho[A.slot_row[t]];
+        if (t != skipR) Rn[t] = A.rho[X.slot_row[t]];
     }
     if (C.LS && C.ES) {
         /* column csq is replaced: T[:, csq] = -tcol_S / tp */
-        for (int t = X.gtid; t < k; t += X.gsize) A.T[(size_t)C.csq * ldt + t] = -A.tcol[A.slot_pos[t]] / tp;
+        for (int t = X.gtid; t < k; t += X.gsize) A.T[(size_t)C.csq * ldt + t] = -A.tcol[X.slot_pos[t]] / tp;
         for (int j = X.gtid; j <= nd; j += X.gsize) A.Rd[(size_t)j * ldt + C.csq] = 0.0;
     } else if (C.LS && !C.ES) {
         /* a row and a column join at slot k */
         for (int t = X.gtid; t < 2 * k + 1; t += X.gsize) {
-            if (t < k) A.T[(size_t)k * ldt + t] = -A.tcol[A.slot_pos[t]] / tp;
-            else if (t < 2 * k) A.T[(size_t)(t - k) * ldt + k] = -A.rho[A.slot_row[t - k]] / tp;
+            if (t < k) A.T[(size_t)k * ldt + t] = -A.tcol[X.slot_pos[t]] / tp;
+            else if (t < 2 * k) A.T[(size_t)(t - k) * ldt + k] = -A.rho[X.slot_row[t - k]] / tp;
             else A.T[(size_t)k * ldt + k] = -1.0 / tp;
         }
         for (int j = X.gtid; j <= nd; j += X.gsize) { A.Fd[(size_t)j * ldt + k] = 0.0; A.Rd[(size_t)j * ldt + k] = 0.0; }
@@ -964,14 +972,14 @@ __device__ void eng_defer_apply(const EngCtx &X, const EngArgs &A, const EngChan
             }
         }
         for (int j = X.gtid; j <= nd; j += X.gsize) {
-            if (C.bp != k - 1) A.Fd[(size_t)j * ldt + C.bp] = (j == nd) ? -A.tcol[A.slot_pos[k - 1]] / tp
+            if (C.bp != k - 1) A.Fd[(size_t)j * ldt + C.bp] = (j == nd) ? -A.tcol[X.slot_pos[k - 1]] / tp
                                                                        : A.Fd[(size_t)j * ldt + (k - 1)];
-            if (C.csq != k - 1) A.Rd[(size_t)j * ldt + C.csq] = (j == nd) ? A.rho[A.slot_row[k - 1]]
+            if (C.csq != k - 1) A.Rd[(size_t)j * ldt + C.csq] = (j == nd) ? A.rho[X.slot_row[k - 1]]
                                                                          : A.Rd[(size_t)j * ldt + (k - 1)];
         }
     } else {
         /* a structural variable replaces a structural one: row bp = -rho_N / tp */
-        for (int c = X.gtid; c < k; c += X.gsize) A.T[(size_t)c * ldt + C.bp] = -A.rho[A.slot_row[c]] / tp;
+        for (int c = X.gtid; c < k; c += X.gsize) A.T[(size_t)c * ldt + C.bp] = -A.rho[X.slot_row[c]] / tp;
         for (int j = X.gtid; j < nd; j += X.gsize) A.Fd[(size_t)j * ldt + C.bp] = 0.0;
     }
 }
@@ -1053,23 +1061,37 @@ __device__ void eng_flush(const EngCtx &X, const EngArgs &A, int k, int nd)
 }
 
 /* slot maps, basis header and the new non-basic status (change_basis,
-   lib/glpspx01.js:1310-1371 / lib/glpspx02.js:1259-1294); one thread */
-__device__ void eng_bookkeep(const EngArgs &A, const EngChange &C, int new_stat, bool drop_refsp)
+   lib/glpspx01.js:1310-1371 / lib/glpspx02.js:1259-1294) on one copy of the
+   header arrays; one thread */
+__device__ void eng_bookkeep_hdr(int *head, int *bind, int *rslot, int *slot_pos, int *cslot, int *slot_row,
+                                 signed char *stat, int m, const EngChange &C, int new_stat)
 {
-    const int m = A.m, k = C.k;
-    if (C.LS) { A.cslot[C.kp] = C.ctgt; A.slot_row[C.ctgt] = C.kp; }
+    const int k = C.k;
+    if (C.LS) { cslot[C.kp] = C.ctgt; slot_row[C.ctgt] = C.kp; }
     if (C.ES) {
-        A.cslot[C.kq] = -1;
-        if (!C.LS && C.csq != k - 1) { int rl = A.slot_row[k - 1]; A.slot_row[C.csq] = rl; A.cslot[rl] = C.csq; }
+        cslot[C.kq] = -1;
+        if (!C.LS && C.csq != k - 1) { int rl = slot_row[k - 1]; slot_row[C.csq] = rl; cslot[rl] = C.csq; }
     }
-    if (C.bnew >= 0) { A.rslot[C.p] = C.bnew; A.slot_pos[C.bnew] = C.p; }
+    if (C.bnew >= 0) { rslot[C.p] = C.bnew; slot_pos[C.bnew] = C.p; }
     if (!C.LS && C.ES) {
-        A.rslot[C.p] = -1;
-        if (C.bp != k - 1) { int pl = A.slot_pos[k - 1]; A.slot_pos[C.bp] = pl; A.rslot[pl] = C.bp; }
+        rslot[C.p] = -1;
+        if (C.bp != k - 1) { int pl = slot_pos[k - 1]; slot_pos[C.bp] = pl; rslot[pl] = C.bp; }
     }
-    A.head[C.p] = C.kq; A.head[m + C.q] = C.kp;
-    A.bind[C.kq] = C.p; A.bind[C.kp] = m + C.q;
-    A.stat[C.q] = (signed char)new_stat;
+    head[C.p] = C.kq; head[m + C.q] = C.kp;
+    bind[C.kq] = C.p; bind[C.kp] = m + C.q;
+    stat[C.q] = (signed char)new_stat;
+}
+
+/* the whole O(1) remainder of a basis change: thread 0 of every CTA updates its
+   private header (if any), thread 0 of CTA 0 the arrays in global memory and the
+   vectors whose zero pattern follows the basis */
+__device__ void eng_bookkeep(const EngCtx &X, const EngArgs &A, const EngChange &C, int new_stat, bool drop_refsp)
+{
+    const int m = A.m;
+    if (X.hdr_local)
+        eng_bookkeep_hdr(X.head, X.bind, X.rslot, X.slot_pos, X.cslot, X.slot_row, X.stat, m, C, new_stat);
+    if (X.cta != 0) return;
+    eng_bookkeep_hdr(A.head, A.bind, A.rslot, A.slot_pos, A.cslot, A.slot_row, A.stat, m, C, new_stat);
     if (drop_refsp) A.refsp[C.kp] = 0;
     /* zero where the variable left the set the copy is indexed over */
     if (C.LS) A.vrow[C.kp] = 0.0;
@@ -1088,6 +1110,22 @@ __device__ __forceinline__ void eng_init(EngCtx &X, const EngArgs &A, double *dy
     X.sh_d = dyn;
     X.sh_i = (int *)(dyn + A.dcap);
     X.sh_red2 = (double *)(X.sh_i + ENG_LCAP);
+    X.head = A.head; X.bind = A.bind; X.rslot = A.rslot; X.slot_pos = A.slot_pos;
+    X.cslot = A.cslot; X.slot_row = A.slot_row; X.stat = A.stat;
+    X.hdr_local = 0;
+    if (A.hdr_smem) {
+        const int m = A.m, n = A.n, ldt = A.ldt;
+        int *base = (int *)(X.sh_red2 + 32 * 65);
+        X.head = base; X.bind = X.head + (m + n); X.rslot = X.bind + (m + n); X.cslot = X.rslot + m;
+        X.slot_pos = X.cslot + m; X.slot_row = X.slot_pos + ldt;
+        X.stat = (signed char *)(X.slot_row + ldt);
+        for (int t = X.tid; t < m + n; t += ENG_NT) { X.head[t] = A.head[t]; X.bind[t] = A.bind[t]; }
+        for (int t = X.tid; t < m; t += ENG_NT) { X.rslot[t] = A.rslot[t]; X.cslot[t] = A.cslot[t]; }
+        for (int t = X.tid; t < ldt; t += ENG_NT) { X.slot_pos[t] = A.slot_pos[t]; X.slot_row[t] = A.slot_row[t]; }
+        for (int t = X.tid; t < n; t += ENG_NT) X.stat[t] = A.stat[t];
+        X.hdr_local = 1;
+        __syncthreads();
+    }
 }
 
 /* block-wide reduction whose result every thread of the CTA gets */
@@ -1135,7 +1173,7 @@ __global__ void __launch_bounds__(ENG_NT, 1) k_engine_primal(EngArgs A)
         if (it == 0) {
             Key none = {0.0, 0.0, 0.0, INT_MAX, 0};
             Key v = none;
-            scan_chuzc_primal(v, X.gtid, X.gsize, n, A.stat, A.cbar, A.gamma, A.tol_dj, -1, 0);
+            scan_chuzc_primal(v, X.gtid, X.gsize, n, X.stat, A.cbar, A.gamma, A.tol_dj, -1, 0);
             Key r = eng_allreduce(X, A, v, none, CombArgMax());
             qnext = (r.a > 0.0 && r.pos != INT_MAX) ? r.pos : P_NONE;
             eng_mark(X, A, PP_PRICE0, 17.0 * n);
@@ -1148,7 +1186,7 @@ __global__ void __launch_bounds__(ENG_NT, 1) k_engine_primal(EngArgs A)
         __syncthreads();
         if (S.status != ST_OK) break;
         const int q = S.q;
-        const int kq = A.head[m + q];
+        const int kq = X.head[m + q];
         const double nnz_q = (kq < m) ? 1.0 : (double)(__ldg(A.a_ptr + (kq - m) + 1) - __ldg(A.a_ptr + (kq - m)));
         /* ---- A: tcol, first half ---- */
         eng_ftran_head_col(X, A, S.k, kq, A.yk, A.ycol, 0);
@@ -1205,7 +1243,7 @@ __global__ void __launch_bounds__(ENG_NT, 1) k_engine_primal(EngArgs A)
                 for (int x = 0; x < 2; x++) {
                     const int pos = X.tid + x * ENG_NT;
                     ok[x] = (pos < m) && ratio_primal_elem(cand[x], pos, S.phase, sgn, S.eps, A.rtol, A.type, A.lb, A.ub,
-                                                           A.coef, A.head, A.bbar, A.tcol);
+                                                           A.coef, X.head, A.bbar, A.tcol);
                     if (ok[x]) { const Key c = ratio_primal_key(cand[x], 1, pos); CombRatio1()(v, c); }
                 }
                 Key r = eng_blockall(X, v, none, CombRatio1());
@@ -1226,14 +1264,14 @@ __global__ void __launch_bounds__(ENG_NT, 1) k_engine_primal(EngArgs A)
                 }
             } else {
                 scan_ratio_primal(v, X.tid, ENG_NT, 1, S.phase, sgn, S.eps, 0.0, A.rtol, A.type, A.lb, A.ub,
-                                  A.coef, A.head, A.bbar, A.tcol, nullptr, m);
+                                  A.coef, X.head, A.bbar, A.tcol, nullptr, m);
                 Key r = eng_blockall(X, v, none, CombRatio1());
                 if (X.tid == 0) fin_ratio_primal(&S, r, 1, sgn, A.rtol, nullptr);
                 __syncthreads();
                 if (S.status == ST_OK && !S.skip2) {
                     v = none;
                     scan_ratio_primal(v, X.tid, ENG_NT, 2, S.phase, sgn, S.eps, S.tmax, A.rtol, A.type, A.lb, A.ub,
-                                      A.coef, A.head, A.bbar, A.tcol, nullptr, m);
+                                      A.coef, X.head, A.bbar, A.tcol, nullptr, m);
                     r = eng_blockall(X, v, none, CombRatio2());
                     if (X.tid == 0) fin_ratio_primal(&S, r, 2, sgn, A.rtol, nullptr);
                     __syncthreads();
@@ -1252,7 +1290,7 @@ __global__ void __launch_bounds__(ENG_NT, 1) k_engine_primal(EngArgs A)
                 v.a = __dsub_rn(A.ub[kq], A.lb[kq]); v.b = 1.0; v.pos = -1; v.aux = 0;
             }
             scan_ratio_primal(v, X.gtid, X.gsize, 1, S.phase, sgn, S.eps, 0.0, A.rtol, A.type, A.lb, A.ub,
-                              A.coef, A.head, A.bbar, A.tcol, nullptr, m);
+                              A.coef, X.head, A.bbar, A.tcol, nullptr, m);
             if (pse) eng_btran_head(X, A, S.k);
             Key r = eng_allreduce(X, A, v, none, CombRatio1());
             if (X.cta == 0 && X.tid == 0) A.cbar[q] = S.d1;     /* every CTA has read the old value by now */
@@ -1263,7 +1301,7 @@ __global__ void __launch_bounds__(ENG_NT, 1) k_engine_primal(EngArgs A)
             if (S.status == ST_OK && !S.skip2) {
                 v = none;
                 scan_ratio_primal(v, X.gtid, X.gsize, 2, S.phase, sgn, S.eps, S.tmax, A.rtol, A.type, A.lb, A.ub,
-                                  A.coef, A.head, A.bbar, A.tcol, nullptr, m);
+                                  A.coef, X.head, A.bbar, A.tcol, nullptr, m);
                 r = eng_allreduce(X, A, v, none, CombRatio2());
                 if (X.tid == 0) fin_ratio_primal(&S, r, 2, sgn, A.rtol, nullptr);
                 __syncthreads();
@@ -1297,9 +1335,9 @@ __global__ void __launch_bounds__(ENG_NT, 1) k_engine_primal(EngArgs A)
                         for (; b < k; b += lp) a0 += __ldcg(col + b) * A.wk[b];
                         a[0] = (a0 + a1) + (a2 + a3);
                     },
-                    [&](int cs, const double *a) { A.u[A.slot_row[cs]] = a[0]; });
+                    [&](int cs, const double *a) { A.u[X.slot_row[cs]] = a[0]; });
                 for (int r = X.gtid; r < m; r += X.gsize)
-                    if (A.cslot[r] < 0) A.u[r] = A.vrow[r];
+                    if (X.cslot[r] < 0) A.u[r] = A.vrow[r];
             }
             eng_bar(X, A);
             eng_mark(X, A, PP_C, 12.0 * m + 8.0 * S.k + (pse ? 8.0 * S.k * (double)S.k + 20.0 * m : 0.0));
@@ -1317,7 +1355,7 @@ __global__ void __launch_bounds__(ENG_NT, 1) k_engine_primal(EngArgs A)
                         S.status = ST_PIV12;
                     else
                         S.new_dq = S.d1 / piv2;
-                    if (S.status == ST_OK) eng_describe_change(A, S, C);
+                    if (S.status == ST_OK) eng_describe_change(X, A, S, C);
                 }
                 __syncthreads();
                 eng_mark(X, A, PP_E, 12.0 * nnzA * (1.0 - (double)S.k / n) + 13.0 * n + 8.0 * m);
@@ -1328,10 +1366,10 @@ __global__ void __launch_bounds__(ENG_NT, 1) k_engine_primal(EngArgs A)
                 pricing of the next iteration from the values just written ---- */
         {
             const double teta = S.teta;
-            const double xq = get_xN(A.stat, A.head, A.lb, A.ub, m, q);
+            const double xq = get_xN(X.stat, X.head, A.lb, A.ub, m, q);
             int new_stat;
             if (p >= 0) new_stat = S.p_stat;
-            else new_stat = (A.stat[q] == GLP_NL) ? GLP_NU : GLP_NL;
+            else new_stat = (X.stat[q] == GLP_NL) ? GLP_NU : GLP_NL;
             const double new_dq = S.new_dq;
             const double pivot = (p >= 0) ? A.trow[q] : 1.0;
             const int kp = (p >= 0) ? C.kp : 0;
@@ -1342,7 +1380,7 @@ __global__ void __launch_bounds__(ENG_NT, 1) k_engine_primal(EngArgs A)
                 double dj, g;
                 int st;
                 if (p < 0) {
-                    dj = A.cbar[t]; g = A.gamma[t]; st = A.stat[t];
+                    dj = A.cbar[t]; g = A.gamma[t]; st = X.stat[t];
                     if (t == q) { dj = S.d1; A.cbar[q] = dj; st = new_stat; }     /* reeval_cost result */
                 }
                 else if (t == q) {
@@ -1361,13 +1399,13 @@ __global__ void __launch_bounds__(ENG_NT, 1) k_engine_primal(EngArgs A)
                     st = new_stat;
                 } else {
                     const double tr = A.trow[t];
-                    dj = A.cbar[t]; g = A.gamma[t]; st = A.stat[t];
+                    dj = A.cbar[t]; g = A.gamma[t]; st = X.stat[t];
                     if (tr != 0.0) {
                         dj -= tr * new_dq;
                         A.cbar[t] = dj;
                         if (pse) {
                             const double tt = tr / pivot;
-                            const int k = A.head[m + t];
+                            const int k = X.head[m + t];
                             const double t1 = g + tt * tt * S.gamma_q + 2.0 * tt * A.svec[t];
                             const double t2 = (A.refsp[k] ? 1.0 : 0.0) + S.delta_q * tt * tt;
                             g = (t1 >= t2 ? t1 : t2);
@@ -1397,12 +1435,14 @@ __global__ void __launch_bounds__(ENG_NT, 1) k_engine_primal(EngArgs A)
             qnext = (r.a > 0.0 && r.pos != INT_MAX) ? r.pos : P_NONE;
             eng_mark(X, A, PP_F, 24.0 * m + 17.0 * n + (p >= 0 ? 40.0 * n + 16.0 * S.k * (double)S.k : 0.0));
             /* the O(1) remainder: every CTA has arrived, nobody reads the old header any more */
-            if (X.cta == 0 && X.tid == 0) {
+            if (X.tid == 0) {
                 if (p >= 0) {
-                    if (phase == 1) A.coef[C.kp] = 0.0;       /* lib/glpspx01.js:2016-2020 */
-                    eng_bookkeep(A, C, new_stat, false);
-                } else
-                    A.stat[q] = (signed char)new_stat;
+                    if (phase == 1 && X.cta == 0) A.coef[C.kp] = 0.0;       /* lib/glpspx01.js:2016-2020 */
+                    eng_bookkeep(X, A, C, new_stat, false);
+                } else {
+                    if (X.hdr_local) X.stat[q] = (signed char)new_stat;
+                    if (X.cta == 0) A.stat[q] = (signed char)new_stat;
+                }
             }
             if (X.tid == 0) {
                 if (p >= 0) S.k = C.knew;
@@ -1438,7 +1478,7 @@ __global__ void __launch_bounds__(ENG_NT, 1) k_engine_dual(EngArgs A)
         if (it == 0) {
             Key none = {0.0, 0.0, 0.0, INT_MAX, 0};
             Key v = none;
-            scan_chuzr_dual(v, X.gtid, X.gsize, m, A.type, A.lb, A.ub, A.head, A.bbar, A.gamma, A.tol_bnd, -1, 0);
+            scan_chuzr_dual(v, X.gtid, X.gsize, m, A.type, A.lb, A.ub, X.head, A.bbar, A.gamma, A.tol_bnd, -1, 0);
             Key r = eng_allreduce(X, A, v, none, CombArgMax());
             const bool found = (r.a > 0.0 && r.pos != INT_MAX);
             pnext = found ? r.pos : P_NONE;
@@ -1485,13 +1525,13 @@ __global__ void __launch_bounds__(ENG_NT, 1) k_engine_dual(EngArgs A)
         if (local_ratio) {
             Key none = {DBL_MAX, 0.0, 0.0, INT_MAX, 0};
             Key v = none;
-            scan_ratio_dual(v, X.tid, ENG_NT, 1, sgn, S.eps, 0.0, A.rtol, A.stat, A.cbar, A.trow, nullptr, n);
+            scan_ratio_dual(v, X.tid, ENG_NT, 1, sgn, S.eps, 0.0, A.rtol, X.stat, A.cbar, A.trow, nullptr, n);
             Key r = eng_blockall(X, v, none, CombRatio1());
             if (X.tid == 0) fin_ratio_dual(&S, r, 1, sgn, A.rtol, nullptr);
             __syncthreads();
             if (S.status == ST_OK && !S.skip2) {
                 v = none;
-                scan_ratio_dual(v, X.tid, ENG_NT, 2, sgn, S.eps, S.tmax, A.rtol, A.stat, A.cbar, A.trow, nullptr, n);
+                scan_ratio_dual(v, X.tid, ENG_NT, 2, sgn, S.eps, S.tmax, A.rtol, X.stat, A.cbar, A.trow, nullptr, n);
                 r = eng_blockall(X, v, none, CombRatio2());
                 if (X.tid == 0) fin_ratio_dual(&S, r, 2, sgn, A.rtol, nullptr);
                 __syncthreads();
@@ -1505,7 +1545,7 @@ __global__ void __launch_bounds__(ENG_NT, 1) k_engine_dual(EngArgs A)
         } else {
             Key none = {DBL_MAX, 0.0, 0.0, INT_MAX, 0};
             Key v = none;
-            scan_ratio_dual(v, X.gtid, X.gsize, 1, sgn, S.eps, 0.0, A.rtol, A.stat, A.cbar, A.trow, nullptr, n);
+            scan_ratio_dual(v, X.gtid, X.gsize, 1, sgn, S.eps, 0.0, A.rtol, X.stat, A.cbar, A.trow, nullptr, n);
             if (pse) eng_gamma_rhs(X, A);
             Key r = eng_allreduce(X, A, v, none, CombRatio1());
             if (X.tid == 0) fin_ratio_dual(&S, r, 1, sgn, A.rtol, nullptr);
@@ -1527,7 +1567,7 @@ __global__ void __launch_bounds__(ENG_NT, 1) k_engine_dual(EngArgs A)
             }
             if (!S.skip2) {
                 v = none;
-                scan_ratio_dual(v, X.gtid, X.gsize, 2, sgn, S.eps, S.tmax, A.rtol, A.stat, A.cbar, A.trow, nullptr, n);
+                scan_ratio_dual(v, X.gtid, X.gsize, 2, sgn, S.eps, S.tmax, A.rtol, X.stat, A.cbar, A.trow, nullptr, n);
                 r = eng_allreduce(X, A, v, none, CombRatio2());
                 if (X.tid == 0) fin_ratio_dual(&S, r, 2, sgn, A.rtol, nullptr);
                 __syncthreads();
@@ -1539,7 +1579,7 @@ __global__ void __launch_bounds__(ENG_NT, 1) k_engine_dual(EngArgs A)
             }
         }
         const int q = S.q;
-        const int kq = A.head[m + q];
+        const int kq = X.head[m + q];
         /* ---- tcol, first half, and the dense product y2 = T v_N of update_gamma ---- */
         if (pse && S.k > 0) {
             __shared__ double zd[ENG_DB];
@@ -1574,12 +1614,12 @@ __global__ void __launch_bounds__(ENG_NT, 1) k_engine_dual(EngArgs A)
                     !((piv1 > 0.0 && piv2 > 0.0) || (piv1 < 0.0 && piv2 < 0.0)))
                     S.status = ST_PIV12;
                 else {
-                    const double eta = (A.refsp[A.head[p]] ? 1.0 : 0.0);
+                    const double eta = (A.refsp[X.head[p]] ? 1.0 : 0.0);
                     S.delta_q = eta;
                     S.gamma_q = eta + (pse ? S.scal : 0.0);
                     S.teta = S.delta / piv1;
                     if (S.phase == 2) S.obj += (A.cbar[q] / S.zeta) * (S.delta / piv1);
-                    eng_describe_change(A, S, C);
+                    eng_describe_change(X, A, S, C);
                 }
             }
             __syncthreads();
@@ -1592,7 +1632,7 @@ __global__ void __launch_bounds__(ENG_NT, 1) k_engine_dual(EngArgs A)
             const double teta = S.teta, new_dq = S.new_dq;
             const int kp = C.kp;
             const double pivot = C.tp;
-            const double xq = get_xN(A.stat, A.head, A.lb, A.ub, m, q);
+            const double xq = get_xN(X.stat, X.head, A.lb, A.ub, m, q);
             const bool drop = (A.type[kp] == GLP_FX && A.refsp[kp]);
             for (int t = X.gtid; t < n; t += X.gsize) {
                 if (t == q) A.cbar[q] = new_dq;
@@ -1624,7 +1664,7 @@ __global__ void __launch_bounds__(ENG_NT, 1) k_engine_dual(EngArgs A)
                         A.gamma[p] = g;
                     }
                 } else {
-                    k = A.head[t];
+                    k = X.head[t];
                     bi = A.bbar[t];
                     const double tc = A.tcol[t];
                     if (tc != 0.0) {
@@ -1661,7 +1701,7 @@ __global__ void __launch_bounds__(ENG_NT, 1) k_engine_dual(EngArgs A)
             }
             eng_mark(X, A, PD_UPD, 24.0 * n + 40.0 * m + 37.0 * m + (defer ? 40.0 * S.k : 16.0 * S.k * (double)S.k));
             const int new_stat = (A.type[kp] == GLP_FX) ? GLP_NS : (S.delta > 0.0 ? GLP_NL : GLP_NU);
-            if (X.cta == 0 && X.tid == 0) eng_bookkeep(A, C, new_stat, pse && drop);
+            if (X.tid == 0) eng_bookkeep(X, A, C, new_stat, pse && drop);
             if (X.tid == 0) {
                 S.k = C.knew;
                 iter_end(&S, true, 1);

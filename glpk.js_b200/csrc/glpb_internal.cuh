@@ -144,7 +144,7 @@ struct glpb_prob {
     double *eng_fr = nullptr;              /* engine: deferred terms Fd, Rd [2][ENG_DB][ldt] and zbuf [ENG_DB] */
     long long *eng_cyc = nullptr;          /* engine: SM cycles per phase [16] */
     double *eng_bytes = nullptr;           /* engine: algorithmic bytes per phase [16] */
-    int sm_count = 0, eng_dcap = 0, eng_smem = 0, eng_ready = 0;
+    int sm_count = 0, eng_dcap = 0, eng_smem = 0, eng_ready = 0, eng_hdr = 0, eng_tma = 0;
     long n_eng_launch = 0, n_eng_prof_iter[2] = {0, 0};
     double *T = nullptr, *T2 = nullptr, *partial = nullptr;   /* T2: output buffer of the refactorisation */
     struct RefSlot *ref_slots = nullptr;

@@ -207,10 +207,20 @@ static int create_device(glpb_prob *P)
         CK(cudaDeviceGetAttribute(&P->sm_count, cudaDevAttrMultiProcessorCount, P->device));
         CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, P->device));
         CK(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, P->device));
-        int budget = std::min(smem_max, 200 * 1024) - 42 * 1024;      /* static shared of the engine (~16 KB) + cross-warp sums */
-        int dcap = std::max({ENG_LCAP, ENG_FLUSH_SMEM, ENG_TMA_SMEM, std::min(P->ldt, (budget - ENG_LCAP * 4) / 8)});   /* >= list staging, flush staging, TMA stages */
+        /* dynamic shared memory of the engine: [dcap doubles: list / vector / flush staging]
+           [ENG_LCAP ints][32 x 65 doubles][optional private copy of the basis header] */
+        const int want_tma = getenv("GLPB_TMA") ? atoi(getenv("GLPB_TMA")) : 0;
+        const int want_hdr = getenv("GLPB_HDR") ? atoi(getenv("GLPB_HDR")) : 1;
+        const size_t total = (size_t)std::min(smem_max, 200 * 1024) - 18 * 1024;      /* minus the static part */
+        const size_t fixed = (size_t)ENG_LCAP * 4 + 32 * 65 * 8;
+        const size_t hdr = ((size_t)2 * (m + n) + 2 * (size_t)m + 2 * (size_t)P->ldt) * 4 + n + 16;
+        const size_t dmin = std::max({(size_t)ENG_LCAP, (size_t)ENG_FLUSH_SMEM, want_tma ? (size_t)ENG_TMA_SMEM : (size_t)0});
+        P->eng_tma = want_tma;
+        P->eng_hdr = (want_hdr && dmin * 8 + fixed + hdr <= total) ? 1 : 0;
+        const size_t room = total - fixed - (P->eng_hdr ? hdr : 0);
+        int dcap = (int)std::max(dmin, std::min((size_t)P->ldt, room / 8));
         P->eng_dcap = dcap;
-        P->eng_smem = dcap * 8 + ENG_LCAP * 4 + 32 * 65 * 8;
+        P->eng_smem = (int)((size_t)dcap * 8 + fixed + (P->eng_hdr ? hdr : 0));
         if (!coop || P->sm_count > ENG_MAXG) { glpb_set_error("device lacks cooperative launch"); return GLPB_ENODEV; }
         CK(cudaFuncSetAttribute(k_engine_primal, cudaFuncAttributeMaxDynamicSharedMemorySize, P->eng_smem));
         CK(cudaFuncSetAttribute(k_engine_dual, cudaFuncAttributeMaxDynamicSharedMemorySize, P->eng_smem));
@@ -775,9 +785,9 @@ struct Loop : Dev {
         A.Fd = P->eng_fr; A.Rd = P->eng_fr + (size_t)ENG_DB * P->ldt; A.zbuf = P->eng_fr + 2 * (size_t)ENG_DB * P->ldt;
         A.defer = (env_defer && dual && P->eng_dcap >= ENG_FLUSH_SMEM) ? 1 : 0;
         /* measured on B200 (C3): per-column bulk copies of ~350 bytes are issue-bound (2.2 TB/s) and lose
-           to the register-staged 16-byte loads (3.6 TB/s), so the TMA-staged stream is opt-in */
-        static const int env_tma = getenv("GLPB_TMA") ? atoi(getenv("GLPB_TMA")) : 0;
-        A.use_tma = env_tma;
+           to the register-staged 16-byte loads (3.6 TB/s), so the TMA-staged stream is opt-in (GLPB_TMA=1) */
+        A.use_tma = P->eng_tma;
+        A.hdr_smem = P->eng_hdr;
         A.local_max = env_local;
         A.prof_cyc = P->prof ? P->eng_cyc + (dual ? 12 : 0) : nullptr;
         A.prof_bytes = P->prof ? P->eng_bytes + (dual ? 12 : 0) : nullptr;

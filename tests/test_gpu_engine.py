@@ -41,6 +41,7 @@ MODES = [
     ("eight CTAs, register-staged stream", {"GLPB_GRID": "8"}),
     ("three CTAs", {"GLPB_GRID": "3"}),
     ("one CTA", {"GLPB_GRID": "1"}),
+    ("basis header read from global memory (no per-CTA copies)", {"GLPB_HDR": "0"}),
     ("distributed panel", {"GLPB_REF_SINGLE": "0"}),
     ("distributed panel held by two CTAs", {"GLPB_REF_SINGLE": "0", "GLPB_REF_PG": "2"}),
     ("refactorise every nfs_max updates", {"GLPB_REFAC_AUTO": "0"}),
