@@ -36,6 +36,7 @@ static double now_ms()
 
 #define PROF_MAX_RECS 400000
 #define REF_SMEM_MAX (200 * 1024)
+#define RHO_SMEM_MAX (200 * 1024)
 
 static inline void prof_begin(glpb_prob *P, const char *name)
 {
@@ -225,6 +226,7 @@ static int create_device(glpb_prob *P)
         CK(cudaFuncSetAttribute(k_engine_primal, cudaFuncAttributeMaxDynamicSharedMemorySize, P->eng_smem));
         CK(cudaFuncSetAttribute(k_engine_dual, cudaFuncAttributeMaxDynamicSharedMemorySize, P->eng_smem));
         CK(cudaFuncSetAttribute(k_refactor, cudaFuncAttributeMaxDynamicSharedMemorySize, REF_SMEM_MAX));
+        CK(cudaFuncSetAttribute(k_rho_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, RHO_SMEM_MAX));
         int occ = 0;
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_engine_dual, ENG_NT, P->eng_smem));
         if (occ < 1) { glpb_set_error("engine does not fit an SM"); return GLPB_ENODEV; }
@@ -411,15 +413,9 @@ struct Dev { /* launch geometry derived from the handle */
 };
 
 /* rho = row ctrl->p of inv(B); k is the host's view of the kernel size */
-#define RHO_SMEM_MAX (200 * 1024)
 static void launch_rho(glpb_prob *P, int k)
 {
     const int m = P->m;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(k_rho_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, RHO_SMEM_MAX);
-        attr_set = true;
-    }
     size_t smem = (size_t)std::max(k, 1) * sizeof(double);
     if (smem <= RHO_SMEM_MAX) {
         P->next_bytes = 8.0 * k * (double)k + 12.0 * m;
