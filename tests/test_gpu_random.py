@@ -1,0 +1,95 @@
+"""GPU parity on randomised general LPs: mixed row types (<=, >=, ranged,
+equality, free), mixed column types (lower, upper, boxed, free, fixed), feasible,
+infeasible and unbounded instances.  Every method (primal, dual, dual-then-
+primal) must return the oracle's return code and status; at an optimum the
+objective agrees to 1e-9 and the KKT residuals are <= 1e-9.  This walks the
+engine through phase 1 of both algorithms, bound flips, free variables and the
+no-ratio / nothing-to-price exits."""
+import numpy as np
+import pytest
+
+import glpk_js_b200 as G
+import oracle_lib as O
+import helpers as H
+
+nat = G.native
+pytestmark = pytest.mark.gpu
+
+
+def random_lp(seed):
+    rng = np.random.default_rng(seed)
+    m, n = int(rng.integers(4, 36)), int(rng.integers(4, 48))
+    dens = rng.uniform(0.15, 0.6)
+    A = np.where(rng.random((m, n)) < dens, np.round(rng.uniform(-5, 5, (m, n)), 2), 0.0)
+    for j in range(n):                      # no empty columns
+        if not A[:, j].any():
+            A[rng.integers(0, m), j] = float(rng.integers(1, 5))
+    x0 = np.round(rng.uniform(-2, 4, n), 1)  # a point that most rows are built around
+    ax = A @ x0
+    rt = rng.choice([O.GLP_FR, O.GLP_LO, O.GLP_UP, O.GLP_DB, O.GLP_FX], size=m, p=[0.05, 0.3, 0.3, 0.2, 0.15])
+    slack = np.round(rng.uniform(0, 3, m), 1)
+    shift = np.where(rng.random(m) < 0.1, rng.uniform(-6, 6, m), 0.0)     # now and then infeasible
+    rl = np.where(np.isin(rt, (O.GLP_LO, O.GLP_DB, O.GLP_FX)), ax - slack + shift, 0.0)
+    ru = np.where(rt == O.GLP_UP, ax + slack + shift, np.where(rt == O.GLP_DB, rl + 2 * slack + 0.5, np.where(rt == O.GLP_FX, rl, 0.0)))
+    ct = rng.choice([O.GLP_FR, O.GLP_LO, O.GLP_UP, O.GLP_DB, O.GLP_FX], size=n, p=[0.1, 0.45, 0.1, 0.3, 0.05])
+    cl = np.where(np.isin(ct, (O.GLP_LO, O.GLP_DB, O.GLP_FX)), np.round(x0 - rng.uniform(0, 3, n), 1), 0.0)
+    cu = np.where(ct == O.GLP_UP, np.round(x0 + rng.uniform(0, 3, n), 1),
+                  np.where(ct == O.GLP_DB, cl + np.round(rng.uniform(0.5, 6, n), 1), np.where(ct == O.GLP_FX, cl, 0.0)))
+    coef = np.round(rng.uniform(-4, 4, n), 1)
+    ptr, ind, val = [0], [], []
+    for j in range(n):
+        nz = np.nonzero(A[:, j])[0]
+        ind.extend(nz.tolist())
+        val.extend(A[nz, j].tolist())
+        ptr.append(len(ind))
+    return dict(m=m, n=n, dir=int(rng.choice([O.GLP_MIN, O.GLP_MAX])), c0=float(np.round(rng.uniform(-3, 3), 1)),
+                r_type=rt.astype(np.int32), r_lb=rl, r_ub=ru, c_type=ct.astype(np.int32), c_lb=cl, c_ub=cu,
+                c_coef=coef, c_kind=np.full(n, O.GLP_CV, np.int32), A_ptr=np.array(ptr, np.int32),
+                A_ind=np.array(ind, np.int32), A_val=np.array(val, np.float64))
+
+
+@pytest.mark.parametrize("block", range(4))
+def test_random_general_lps_match_the_oracle(block):
+    seen = {}
+    for seed in range(block * 12, block * 12 + 12):
+        d = random_lp(1000 + seed)
+        dn = H.to_native(d)
+        for meth in (nat.GLP_PRIMAL, nat.GLP_DUAL, nat.GLP_DUALP):
+            P = nat.Problem(dn)
+            rc = P.simplex(meth=meth)
+            s = P.solution()
+            Q = O.Problem.from_arrays(d)
+            orc = Q.simplex(meth=meth)
+            o = Q.solution()
+            what = (seed, meth, d["m"], d["n"])
+            assert rc == orc, (what, rc, orc, s["status"], o["status"])
+            assert (s["status"], s["pbs"], s["dbs"]) == (o["status"], o["pbs"], o["dbs"]), what
+            if o["status"] == O.GLP_OPT:
+                assert abs(s["obj"] - o["obj"]) <= 1e-9 * max(1.0, abs(o["obj"])), (what, s["obj"], o["obj"])
+                r = H.kkt(dn, s)
+                assert max(r.values()) <= 1e-9, (what, r)
+            seen[o["status"]] = seen.get(o["status"], 0) + 1
+            P.close()
+    assert sum(seen.values()) == 36
+
+
+@pytest.mark.parametrize("env", [
+    {"GLPB_GRID": "6"},                                   # six CTAs, replicated ratio test, private headers
+    {"GLPB_GRID": "6", "GLPB_LOCAL_MAX": "0"},            # grid-wide ratio test, deferred basis changes
+    {"GLPB_GRID": "5", "GLPB_LOCAL_MAX": "0", "GLPB_HDR": "0", "GLPB_REF_SINGLE": "0", "GLPB_REF_PG": "2"},
+])
+def test_random_general_lps_in_multi_cta_modes(env):
+    """the same randomised LPs with the library forced into its multi-CTA modes
+    (the tuning variables are read once per process, hence the child pytest)"""
+    import os
+    import subprocess
+    import sys
+    if os.environ.get("GLPB_TEST_NESTED"):
+        pytest.skip("nested run")
+    e = dict(os.environ)
+    e.update(env)
+    e["GLPB_TEST_NESTED"] = "1"
+    out = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-m", "gpu", "-x", "-q",
+                          "-k", "match_the_oracle"], env=e, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
+    assert "4 passed" in out.stdout, out.stdout[-500:]
