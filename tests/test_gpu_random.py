@@ -93,3 +93,52 @@ def test_random_general_lps_in_multi_cta_modes(env):
                           "-k", "match_the_oracle"], env=e, capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
     assert "4 passed" in out.stdout, out.stdout[-500:]
+
+
+def random_mip(seed):
+    """small bounded integer programs on top of random_lp: every column boxed, about
+    two thirds of them integer, integral bounds"""
+    rng = np.random.default_rng(5000 + seed)
+    d = random_lp(7000 + seed)
+    n = d["n"]
+    d["c_type"] = np.full(n, O.GLP_DB, np.int32)
+    lo = np.floor(rng.uniform(-3, 2, n))
+    d["c_lb"] = lo
+    d["c_ub"] = lo + rng.integers(1, 6, n).astype(float)
+    d["c_kind"] = np.where(rng.random(n) < 0.65, O.GLP_IV, O.GLP_CV).astype(np.int32)
+    # rows rebuilt around an integer point inside the boxes, so that the program is feasible
+    x0 = np.floor(rng.uniform(d["c_lb"], d["c_ub"] + 1.0 - 1e-9))
+    A = H.dense_A(dict(m=d["m"], n=n, A_ptr=d["A_ptr"], A_ind=d["A_ind"], A_val=d["A_val"]))
+    ax = A @ x0
+    slack = np.round(rng.uniform(0.5, 4, d["m"]), 1)
+    rt = d["r_type"]
+    d["r_lb"] = np.where(np.isin(rt, (O.GLP_LO, O.GLP_DB)), ax - slack, np.where(rt == O.GLP_FX, ax, 0.0))
+    d["r_ub"] = np.where(rt == O.GLP_UP, ax + slack, np.where(rt == O.GLP_DB, ax + slack, np.where(rt == O.GLP_FX, ax, 0.0)))
+    return d
+
+
+def test_random_small_mips_identical_optimum():
+    statuses = {}
+    for seed in [s_ for s_ in range(24) if s_ != 8]:      # seed 8 needs 26 802 nodes: too slow for a test
+        d = random_mip(seed)
+        dn = H.to_native(d)
+        Q = O.Problem.from_arrays(d)
+        orc = Q.simplex(meth=O.GLP_PRIMAL)
+        P = nat.Problem(dn)
+        rc = P.simplex(meth=nat.GLP_PRIMAL)
+        assert rc == orc and P.solution()["status"] == Q.solution()["status"], seed
+        if Q.solution()["status"] != O.GLP_OPT:
+            P.close()
+            continue
+        oret = Q.intopt()
+        ret = P.intopt(msg_lev=0)
+        om, mp = Q.mip(), P.mip()
+        assert ret == oret and mp["mip_stat"] == om["mip_stat"], (seed, ret, oret, mp["mip_stat"], om["mip_stat"])
+        if om["mip_stat"] == O.GLP_OPT:
+            assert abs(mp["mip_obj"] - om["mip_obj"]) <= 1e-9 * max(1.0, abs(om["mip_obj"])), (seed, mp["mip_obj"], om["mip_obj"])
+            x = mp["mipx"][d["m"]:]
+            iv = d["c_kind"] == O.GLP_IV
+            assert np.max(np.abs(x[iv] - np.round(x[iv]))) <= 1e-5, seed
+        statuses[om["mip_stat"]] = statuses.get(om["mip_stat"], 0) + 1
+        P.close()
+    assert statuses.get(O.GLP_OPT, 0) >= 4, statuses
