@@ -117,6 +117,7 @@ struct glpb_prob {
     std::vector<double> h_atval;
     std::vector<int> h_head;                     /* [m], values k+1 */
     int valid = 0;
+    int t_ok = 0;                /* the device's T / slot maps are consistent with h_head */
     int pbs_stat = GLP_UNDEF, dbs_stat = GLP_UNDEF;
     double obj_val = 0.0;
     int it_cnt = 0, some = 0;

@@ -567,6 +567,7 @@ extern "C" int glpb_factorize(glpb_prob *P)
     CK(cudaSetDevice(P->device));
     const int m = P->m, n = P->n;
     P->valid = 0;
+    P->t_ok = 0;
     int j = 0;
     for (int k = 0; k < m + n; k++)
         if (P->h_stat[k] == GLP_BS) {
@@ -581,6 +582,7 @@ extern "C" int glpb_factorize(glpb_prob *P)
     rc = dev_refactor(D);
     if (rc) return rc;
     P->valid = 1;
+    P->t_ok = 1;
     return 0;
 }
 
@@ -639,6 +641,7 @@ static int store_sol(glpb_prob *P, int p_stat, int d_stat, int ray, int it_cnt)
     CK(cudaStreamSynchronize(P->stream));
     P->n_sync++;
     P->valid = 1;
+    P->t_ok = 1;
     P->pbs_stat = p_stat; P->dbs_stat = d_stat;
     P->it_cnt = it_cnt;
     P->some = ray;
@@ -693,6 +696,7 @@ static int spx_fail(glpb_prob *P, int it_cnt)
     P->it_cnt = it_cnt;
     P->some = 0;
     P->valid = 0;
+    P->t_ok = 0;
     return GLP_EFAIL;
 }
 
@@ -969,6 +973,7 @@ struct Primal : Loop {
         if ((rc = upload_basis(P))) return rc;
         k = P->k_host;      /* T and its slot maps survive between calls */
         P->valid = 0;
+        P->t_ok = 0;         /* the device state is in motion until store_sol */
         it_beg = it_cnt = P->it_cnt;
         tm_beg = now_ms();
         refct = 0;
@@ -1159,6 +1164,7 @@ struct Dual : Loop {
         if ((rc = upload_basis(P))) return rc;
         k = P->k_host;
         P->valid = 0;
+        P->t_ok = 0;         /* the device state is in motion until store_sol */
         it_beg = it_cnt = P->it_cnt;
         tm_beg = now_ms();
         refct = 0;
@@ -1445,7 +1451,17 @@ extern "C" int glpb_simplex(glpb_prob *P, const glpb_smcp *parm_)
     for (int k = 0; k < m + n; k++)
         if (P->h_type[k] == GLP_DB && P->h_lb[k] >= P->h_ub[k]) return GLP_EBOUND;
     if (P->nnz == 0) { trivial_lp(P, parm); return 0; }
-    /* solve_lp, lib/glpapi06.js:3-39 */
+    /* solve_lp, lib/glpapi06.js:3-39.  glp_set_*_stat clears `valid` on any basic <-> non-basic
+       flip, also when a sequence of them (branch-and-bound: restore the root statuses, then
+       apply the node's) ends in the very set of basic variables the device inverse was left
+       with; that inverse is then still the inverse of this basis */
+    if (!P->valid && P->t_ok) {
+        int nbs = 0;
+        for (int k = 0; k < m + n; k++) nbs += (P->h_stat[k] == GLP_BS);
+        bool same = (nbs == m);
+        for (int i = 0; i < m && same; i++) same = (P->h_stat[P->h_head[i] - 1] == GLP_BS);
+        if (same) P->valid = 1;
+    }
     if (!P->valid) {
         rc = glpb_factorize(P);
         if (rc != 0) return rc;
