@@ -799,6 +799,13 @@ struct Loop : Dev {
         cudaError_t e = cudaLaunchCooperativeKernel(dual ? (const void *)k_engine_dual : (const void *)k_engine_primal,
                                                     dim3(G), dim3(ENG_NT), args, (size_t)P->eng_smem, P->stream);
         prof_end(P);
+        if (e == cudaErrorCooperativeLaunchTooLarge) {
+            /* the SMs are shared with somebody else right now: this handle goes on with the
+               per-kernel path (same kernels' arithmetic, host-enqueued) */
+            cudaGetLastError();
+            P->eng_ready = 0;
+            return sync_ctrl(P);        /* status is ST_OK with n_done = 0: the caller loops */
+        }
         if (e != cudaSuccess) { glpb_set_error("engine launch: %s", cudaGetErrorString(e)); return GLPB_ENODEV; }
         P->n_launch++; P->n_eng_launch++;
         int rc = sync_ctrl(P);
