@@ -201,7 +201,9 @@ def run_bnb(args, w, rank, local_rank, world):
     torch.cuda.set_device(local_rank)
     d = nat.generate(w["gen"], **w["kw"])
     node_lim = w["node_lim"]
-    W = max(1, args.bnb_workers)          # worker threads (device handles) per GPU
+    # worker threads (device handles) per GPU; every node costs host work (set-up, tree), so the
+    # useful number is bounded by the host cores this rank can count on
+    W = args.bnb_workers if args.bnb_workers > 0 else max(1, min(8, ((os.cpu_count() or 8) - 2) // world))
     outer = bnb.TorchComm() if world > 1 else None
     import threading
 
@@ -291,7 +293,8 @@ def main():
     ap.add_argument("--no-c3", action="store_true", help="skip the extra full solve of the 16384x32768 LP")
     ap.add_argument("--c3-mid", type=int, default=60000, help="iteration at which the C3 solve is split for the CPU sample")
     ap.add_argument("--c3-cpu-mid-lim", type=int, default=100)
-    ap.add_argument("--bnb-workers", type=int, default=8, help="mkp workload: B&B worker handles (threads) per GPU")
+    ap.add_argument("--bnb-workers", type=int, default=0,
+                    help="mkp workload: B&B worker handles (threads) per GPU; 0 = min(8, (host cores - 2) / ranks)")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
