@@ -1147,7 +1147,7 @@ __device__ Key eng_blockall(const EngCtx &X, Key v, const Key &none, Comb comb)
 #define ENG_LOCAL_MAX 8192
 
 enum { /* phase slots of the cycle accounting (12 per engine) */
-    PP_PRICE0 = 0, PP_A, PP_B, PP_R1, PP_R2, PP_C, PP_D, PP_E, PP_F,
+    PP_PRICE0 = 0, PP_A, PP_B, PP_R1, PP_R2, PP_C, PP_D, PP_E, PP_F, PP_B_TAIL, PP_B_REDUCE, PP_B_BTRAN,
     PD_PRICE0 = 0, PD_RHO, PD_TROW, PD_R1, PD_R2, PD_X1, PD_TCOL1, PD_TCOL2, PD_UPD, PD_FLUSH
 };
 
@@ -1197,9 +1197,9 @@ __global__ void __launch_bounds__(ENG_NT, 1) k_engine_primal(EngArgs A)
             Key none = {0.0, 0.0, 0.0, 0, 0};
             Key acc = none;
             eng_ftran_tail<true>(X, A, S, A.hz, A.ycol, A.tcol, acc);
-            eng_mark(X, A, 9, 12.0 * (double)__ldg(A.at_ptr + m) * (1.0 - (double)S.k / m) + 29.0 * m);
+            eng_mark(X, A, PP_B_TAIL, 12.0 * (double)__ldg(A.at_ptr + m) * (1.0 - (double)S.k / m) + 29.0 * m);
             Key r = eng_allreduce(X, A, acc, none, CombSum2());
-            eng_mark(X, A, 10, 0.0);
+            eng_mark(X, A, PP_B_REDUCE, 0.0);
             if (X.tid == 0) {
                 const double big = r.c;
                 S.tcol_max = big;
@@ -1228,7 +1228,7 @@ __global__ void __launch_bounds__(ENG_NT, 1) k_engine_primal(EngArgs A)
         /* ---- Harris ratio test (chuzr); the first half of u = inv(B') v rides along ---- */
         if (local_ratio) {
             if (pse) eng_btran_head(X, A, S.k);
-            eng_mark(X, A, 11, pse ? 12.0 * nnzA * ((double)S.k / n) + 16.0 * S.k : 0.0);
+            eng_mark(X, A, PP_B_BTRAN, pse ? 12.0 * nnzA * ((double)S.k / n) + 16.0 * S.k : 0.0);
             Key none = {DBL_MAX, 0.0, 0.0, INT_MAX, 0};
             Key v = none;
             if (X.tid == 0 && A.type[kq] == GLP_DB) {
