@@ -8,9 +8,15 @@ object lives on the host exactly like the reference's ``glp_prob``; the solve
 calls marshal it once into a device-resident handle (``native.Problem``) and
 write the solution back into the same fields the reference's getters read.
 
+Scaling (``glp_scale_prob``, lib/glpscl.js) and the triangular crash basis
+(``glp_adv_basis``, lib/glpini01.js) run in the native library's host code
+(``glpb_scale_prob`` / ``glpb_adv_basis``); they prepare inputs of the path.
+
 What is NOT here on purpose ("out of scope" / "next"): the LP/MIP
-presolver, scaling, MathProg, cut generators.  ``presolve: GLP_ON`` is accepted
-and solved without the presolver (the optimum is the same).
+presolver's transformations (``glpnpp*.js``), MathProg, cut generators.
+``presolve: GLP_ON`` runs the reference's flow around an identity presolve:
+copy of the problem, ``glp_scale_prob``, ``glp_adv_basis``, solve, solution
+stored back the way ``npp_unload_sol`` does.
 """
 import math
 
@@ -28,6 +34,40 @@ class GlpkError(Exception):
 
 def xerror(msg):
     raise GlpkError(msg)
+
+
+_print_func = None
+
+
+def glp_set_print_func(value):
+    """lib/glpapi.js:33 -- the default hook prints nothing (:28-30)."""
+    global _print_func
+    _print_func = value
+
+
+def glp_get_print_func():
+    return _print_func
+
+
+def xprintf(data):
+    if _print_func is not None:
+        _print_func(data)
+
+
+def _num(x):
+    """A number the way JavaScript's string concatenation shows it."""
+    x = float(x)
+    if x != x:
+        return "NaN"
+    if x in (math.inf, -math.inf):
+        return "Infinity" if x > 0 else "-Infinity"
+    if x == math.floor(x) and abs(x) < 1e21:
+        return "%d" % x
+    r = repr(x)
+    if "e" in r:
+        mant, ex = r.split("e")
+        r = "%se%s%d" % (mant, "+" if int(ex) >= 0 else "-", abs(int(ex)))
+    return r
 
 
 class SMCP:
@@ -374,6 +414,127 @@ def glp_std_basis(P):
             glp_set_col_stat(P, j, GLP_NU)
         else:
             glp_set_col_stat(P, j, GLP_NL)
+
+
+# ---- scale factors, scaling, crash basis (lib/glpapi04.js, glpscl.js, glpini01.js) ----
+def glp_set_rii(P, i, rii):
+    """lib/glpapi04.js:1-16"""
+    if not (1 <= i <= P.m):
+        xerror("glp_set_rii: i = %d; row number out of range" % i)
+    if rii <= 0.0:
+        xerror("glp_set_rii: i = %d; rii = %s; invalid scale factor" % (i, _num(rii)))
+    row = P.row[i]
+    if row.rii != rii:
+        if P.valid and any(P.col[j].stat == GLP_BS for (j, _) in row.elems):
+            P.valid = 0
+        P._dirty = True   # the handle holds rii*a*sjj
+    row.rii = float(rii)
+
+
+def glp_set_sjj(P, j, sjj):
+    """lib/glpapi04.js:18-28"""
+    if not (1 <= j <= P.n):
+        xerror("glp_set_sjj: j = %d; column number out of range" % j)
+    if sjj <= 0.0:
+        xerror("glp_set_sjj: j = %d; sjj = %s; invalid scale factor" % (j, _num(sjj)))
+    col = P.col[j]
+    if col.sjj != sjj:
+        if P.valid and col.stat == GLP_BS:
+            P.valid = 0
+        P._dirty = True
+    col.sjj = float(sjj)
+
+
+def glp_get_rii(P, i):
+    if not (1 <= i <= P.m):
+        xerror("glp_get_rii: i = %d; row number out of range" % i)
+    return P.row[i].rii
+
+
+def glp_get_sjj(P, j):
+    if not (1 <= j <= P.n):
+        xerror("glp_get_sjj: j = %d; column number out of range" % j)
+    return P.col[j].sjj
+
+
+def glp_unscale_prob(P):
+    """lib/glpapi04.js:44-50"""
+    for i in range(1, P.m + 1):
+        glp_set_rii(P, i, 1.0)
+    for j in range(1, P.n + 1):
+        glp_set_sjj(P, j, 1.0)
+
+
+def _csc(P):
+    """Columns of A in list order: (ptr[n+1], 0-based row index, value)."""
+    ptr = np.zeros(P.n + 1, np.int32)
+    ind, val = [], []
+    for j in range(1, P.n + 1):
+        for (i, v) in P.col[j].elems:
+            ind.append(i - 1)
+            val.append(v)
+        ptr[j] = len(ind)
+    return ptr, np.array(ind, np.int32), np.array(val, np.float64)
+
+
+def _csr(P):
+    """Rows of A in list order: (ptr[m+1], 0-based column index, value)."""
+    ptr = np.zeros(P.m + 1, np.int32)
+    ind, val = [], []
+    for i in range(1, P.m + 1):
+        for (j, v) in P.row[i].elems:
+            ind.append(j - 1)
+            val.append(v)
+        ptr[i] = len(ind)
+    return ptr, np.array(ind, np.int32), np.array(val, np.float64)
+
+
+def glp_scale_prob(P, flags=None):
+    """lib/glpscl.js:216-225.  The min/max sweeps run in the native library
+    (``glpb_scale_prob``); the messages are the reference's.  ``flags`` left out
+    behaves like JavaScript's ``undefined``: every ``flags & X`` is 0, so the
+    call only cancels the current scaling (that is what test/test.js:76 does)."""
+    _check(P, "glp_scale_prob")
+    flags = 0 if flags is None else int(flags)
+    if flags & ~(GLP_SF_GM | GLP_SF_EQ | GLP_SF_2N | GLP_SF_SKIP | GLP_SF_AUTO):
+        xerror("glp_scale_prob: flags = %d; invalid scaling options" % flags)
+    ptr, ind, val = _csc(P)
+    rii, sjj, rep = native.scale_prob(P.m, P.n, ptr, ind, val, flags)
+    xprintf("Scaling...")
+    for tag in ("A", "GM", "EQ", "2N"):
+        if tag in rep:
+            lo, hi, ratio = rep[tag]
+            xprintf("%2s: min|aij| = %s  max|aij| = %s  ratio = %s" % (tag, _num(lo), _num(hi), _num(ratio)))
+            if tag == "A" and lo >= 0.10 and hi <= 10.0:
+                xprintf("Problem data seem to be well scaled")
+    for i in range(1, P.m + 1):
+        glp_set_rii(P, i, float(rii[i - 1]))
+    for j in range(1, P.n + 1):
+        glp_set_sjj(P, j, float(sjj[j - 1]))
+
+
+def glp_adv_basis(P, flags=0):
+    """lib/glpini01.js:355-363; the triangularisation runs in the native library
+    (``glpb_adv_basis``)."""
+    _check(P, "glp_adv_basis")
+    if flags != 0:
+        xerror("glp_adv_basis: flags = %r; invalid flags" % (flags,))
+    if P.m == 0 or P.n == 0:
+        glp_std_basis(P)
+        return
+    xprintf("Constructing initial basis...")
+    m, n = P.m, P.n
+    cptr, cind, _ = _csc(P)
+    rptr, rind, _ = _csr(P)
+    type_ = np.array([P.row[i].type for i in range(1, m + 1)] + [P.col[j].type for j in range(1, n + 1)], np.int32)
+    lb = np.array([P.row[i].lb for i in range(1, m + 1)] + [P.col[j].lb for j in range(1, n + 1)])
+    ub = np.array([P.row[i].ub for i in range(1, m + 1)] + [P.col[j].ub for j in range(1, n + 1)])
+    stat, size = native.adv_basis(m, n, cptr, cind, rptr, rind, type_, lb, ub)
+    P.tri_size = size
+    for i in range(1, m + 1):
+        glp_set_row_stat(P, i, int(stat[i - 1]))
+    for j in range(1, n + 1):
+        glp_set_col_stat(P, j, int(stat[m + j - 1]))
 
 
 # ---- getters (lib/glpapi02.js, lib/glpapi06.js:398-482, lib/glpapi09.js:441-459) ----

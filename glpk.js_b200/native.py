@@ -28,6 +28,7 @@ GLP_BR_FFV, GLP_BR_LFV, GLP_BR_MFV, GLP_BR_DTH, GLP_BR_PCH = 1, 2, 3, 4, 5
 GLP_BT_DFS, GLP_BT_BFS, GLP_BT_BLB, GLP_BT_BPH = 1, 2, 3, 4
 GLP_PP_NONE, GLP_PP_ROOT, GLP_PP_ALL = 0, 1, 2
 GLP_ON, GLP_OFF = 1, 0
+GLP_SF_GM, GLP_SF_EQ, GLP_SF_2N, GLP_SF_SKIP, GLP_SF_AUTO = 0x01, 0x10, 0x20, 0x40, 0x80
 (GLP_EBADB, GLP_ESING, GLP_ECOND, GLP_EBOUND, GLP_EFAIL, GLP_EOBJLL, GLP_EOBJUL, GLP_EITLIM,
  GLP_ETMLIM, GLP_ENOPFS, GLP_ENODFS, GLP_EROOT, GLP_ESTOP, GLP_EMIPGAP) = range(1, 15)
 GLPB_EINVAL, GLPB_ENODEV, GLPB_ENOMEM, GLPB_ESTATE = -1, -2, -3, -4
@@ -72,6 +73,7 @@ SYMBOLS = [
     "glpb_btran", "glpb_k_chuzc_primal", "glpb_k_chuzr_dual", "glpb_k_ratio_primal",
     "glpb_k_ratio_dual", "glpb_k_trow", "glpb_bench_kernel", "glpb_gen_packing",
     "glpb_gen_covering", "glpb_gen_mkp", "glpb_free_problem", "glpb_rng_fill",
+    "glpb_scale_prob", "glpb_adv_basis",
 ]
 
 _lib = None
@@ -140,6 +142,8 @@ def load():
     L.glpb_gen_mkp.argtypes = [ci, ci, ci, vp]
     L.glpb_free_problem.argtypes = [vp]
     L.glpb_rng_fill.argtypes = [ci, ci, vp]
+    L.glpb_scale_prob.argtypes = [ci, ci, vp, vp, vp, ci, vp, vp, vp]
+    L.glpb_adv_basis.argtypes = [ci, ci] + [vp] * 9
     _lib = L
     return L
 
@@ -190,6 +194,37 @@ def generate(which, **kw):
              A_ind=arr(pd.A_ind, nnz, np.int32), A_val=arr(pd.A_val, nnz, np.float64))
     L.glpb_free_problem(C.byref(pd))
     return d
+
+
+def scale_prob(m, n, A_ptr, A_ind, A_val, flags):
+    """glpb_scale_prob: scale factors (rii[m], sjj[n]) and the per-stage report
+    {stage: (min|aij|, max|aij|, ratio)} of lib/glpscl.js scale_prob.  Host only."""
+    L = load()
+    A_ptr, A_ind, A_val = _i32(A_ptr), _i32(A_ind), _f64(A_val)
+    rii, sjj, rep = np.ones(m), np.ones(n), np.zeros(13)
+    rc = L.glpb_scale_prob(m, n, _p(A_ptr), _p(A_ind), _p(A_val), int(flags), _p(rii), _p(sjj), _p(rep))
+    if rc != 0:
+        raise ValueError("glpb_scale_prob: invalid arguments (rc=%d)" % rc)
+    mask = int(rep[0])
+    report = {name: tuple(rep[1 + 3 * s:4 + 3 * s]) for s, name in enumerate(("A", "GM", "EQ", "2N"))
+              if mask & (1 << s)}
+    report["skipped"] = bool(mask & 16)
+    return rii, sjj, report
+
+
+def adv_basis(m, n, A_ptr, A_ind, R_ptr, R_ind, type_, lb, ub):
+    """glpb_adv_basis: statuses [m+n] of the triangular crash basis and the size
+    of the triangular part (lib/glpini01.js).  Host only."""
+    L = load()
+    A_ptr, A_ind, R_ptr, R_ind = _i32(A_ptr), _i32(A_ind), _i32(R_ptr), _i32(R_ind)
+    type_, lb, ub = _i32(type_), _f64(lb), _f64(ub)
+    stat = np.zeros(m + n, np.int32)
+    size = C.c_int(0)
+    rc = L.glpb_adv_basis(m, n, _p(A_ptr), _p(A_ind), _p(R_ptr), _p(R_ind), _p(type_), _p(lb), _p(ub),
+                          _p(stat), C.byref(size))
+    if rc != 0:
+        raise ValueError("glpb_adv_basis: invalid arguments (rc=%d)" % rc)
+    return stat, size.value
 
 
 class Problem:

@@ -194,6 +194,37 @@ int glpb_gen_mkp(int m, int n, int seed, glpb_problem_data *out);               
 void glpb_free_problem(glpb_problem_data *d);
 void glpb_rng_fill(int seed, int count, int *out);
 
+/* ---- Host-side preparation of the path's inputs --------
+ * No device involved; O(nnz) work done once per solve on the caller thread.
+ *
+ * glpb_scale_prob replaces glp_scale_prob(lp, flags) (lib/glpscl.js:216-225,
+ * scale_prob :167-214): cancels the current scaling, then geometric-mean
+ * iterations (15 x, tau 0.90), equilibration and rounding to powers of two as
+ * `flags` (GLP_SF_* of lib/glpk.js:30-34) ask.  A in CSC (0-based rows, any
+ * order within a column); rii[m], sjj[n] are OUTPUT and are exactly what
+ * glpb_create takes.  report (optional, 13 doubles): [0] = bit mask of the
+ * stages reported (1 A, 2 GM, 4 EQ, 8 2N, +16 "well scaled, skipped"), then
+ * (min|aij|, max|aij|, ratio) per stage -- the numbers the reference prints. */
+#define GLPB_SF_GM   0x01
+#define GLPB_SF_EQ   0x10
+#define GLPB_SF_2N   0x20
+#define GLPB_SF_SKIP 0x40
+#define GLPB_SF_AUTO 0x80
+int glpb_scale_prob(int m, int n, const int *A_ptr, const int *A_ind, const double *A_val,
+                    int flags, double *rii, double *sjj, double *report);
+
+/* glpb_adv_basis replaces glp_adv_basis(lp, 0) (lib/glpini01.js:281-363): the
+ * maximal triangular part of (I | -A) without fixed columns becomes the
+ * initial basis.  Columns (A_ptr/A_ind) and rows (R_ptr/R_ind, 0-based column
+ * indices) must be given in the reference's LIST order (the order
+ * glp_get_mat_col / glp_get_mat_row return): ties between rows are broken by
+ * the order in which the column patterns are walked.  type/lb/ub [m+n] as for
+ * glpb_create; stat[m+n] is OUTPUT (GLP_BS/NL/NU/NF/NS) and is what
+ * glpb_set_basis takes; tri_size (optional) = size of the triangular part. */
+int glpb_adv_basis(int m, int n, const int *A_ptr, const int *A_ind, const int *R_ptr,
+                   const int *R_ind, const int *type, const double *lb, const double *ub,
+                   int *stat, int *tri_size);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,287 @@
+"""CPU tests of the host-side preparation steps:
+``glpb_scale_prob`` / ``glpb_adv_basis`` (csrc/hostprep.cpp, through the C ABI
+and through the facade's ``glp_scale_prob`` / ``glp_adv_basis``) against the
+plain-Python restatement of lib/glpscl.js and lib/glpini01.js in
+oracle/hostprep.py -- bit-exact scale factors, identical statuses -- plus the
+properties the algorithms guarantee.  No device is needed."""
+import importlib.util
+import math
+import os
+import random
+
+import numpy as np
+import pytest
+
+import glpk_js_b200 as G
+import helpers as H
+
+nat = G.native
+glpk = G.glpk
+
+_spec = importlib.util.spec_from_file_location(
+    "oracle_hostprep", os.path.join(H.HERE, "..", "oracle", "hostprep.py"))
+OH = importlib.util.module_from_spec(_spec)
+_spec.loader.exec_module(OH)
+
+ALL_FLAGS = [0, nat.GLP_SF_GM, nat.GLP_SF_EQ, nat.GLP_SF_2N, nat.GLP_SF_GM | nat.GLP_SF_EQ,
+             nat.GLP_SF_GM | nat.GLP_SF_EQ | nat.GLP_SF_2N | nat.GLP_SF_SKIP, nat.GLP_SF_AUTO,
+             nat.GLP_SF_EQ | nat.GLP_SF_2N, nat.GLP_SF_GM | nat.GLP_SF_SKIP]
+
+
+def lists_of(P):
+    """rows/cols of a facade problem in the reference's list order, 1-based"""
+    rows = [None] + [list(P.row[i].elems) for i in range(1, P.m + 1)]
+    cols = [None] + [list(P.col[j].elems) for j in range(1, P.n + 1)]
+    return rows, cols
+
+
+def read_fixture(name):
+    P = glpk.glp_create_prob()
+    glpk.glp_read_lp_from_string(P, None, H.golden_text(name))
+    return P
+
+
+def random_problem(seed, m, n, density, wide=False):
+    """Facade problem with mixed row/column types (fixed, free, empty rows and
+    columns included), values over many orders of magnitude when ``wide``."""
+    rnd = random.Random(seed)
+    P = glpk.glp_create_prob()
+    glpk.glp_add_rows(P, m)
+    glpk.glp_add_cols(P, n)
+    types = [glpk.GLP_FR, glpk.GLP_LO, glpk.GLP_UP, glpk.GLP_DB, glpk.GLP_FX]
+    for i in range(1, m + 1):
+        t = rnd.choice(types)
+        lb = rnd.uniform(-5, 5)
+        glpk.glp_set_row_bnds(P, i, t, lb, lb + rnd.uniform(0.5, 4))
+    for j in range(1, n + 1):
+        t = rnd.choice(types)
+        lb = rnd.uniform(-5, 5)
+        glpk.glp_set_col_bnds(P, j, t, lb, lb + rnd.uniform(0.5, 4))
+        glpk.glp_set_obj_coef(P, j, rnd.uniform(-3, 3))
+    for j in range(1, n + 1):
+        if rnd.random() < 0.05:
+            continue  # empty column
+        rows = [i for i in range(1, m + 1) if rnd.random() < density]
+        rnd.shuffle(rows)
+        vals = [(rnd.choice((-1, 1)) * (10.0 ** rnd.uniform(-4, 4) if wide else rnd.uniform(0.1, 3)))
+                for _ in rows]
+        glpk.glp_set_mat_col(P, j, len(rows), [0] + rows, [0.0] + vals)
+    return P
+
+
+def product_scale(P, flags):
+    ptr, ind, val = glpk._csc(P)
+    return nat.scale_prob(P.m, P.n, ptr, ind, val, flags)
+
+
+def check_scale_parity(P, flags):
+    rows, cols = lists_of(P)
+    rii, sjj, rep = product_scale(P, flags)
+    o_rii, o_sjj, o_rep = OH.scale_prob(P.m, P.n, rows, cols, flags)
+    assert rii.tolist() == o_rii[1:], "rii differs (flags=%#x)" % flags     # bit-exact
+    assert sjj.tolist() == o_sjj[1:], "sjj differs (flags=%#x)" % flags
+    for ent in o_rep:
+        if ent[0] == "skipped":
+            assert rep["skipped"]
+        else:
+            assert rep[ent[0]] == tuple(ent[1:])
+    assert rep["skipped"] == any(e[0] == "skipped" for e in o_rep)
+    return rii, sjj, rep
+
+
+def test_round2n_and_hand_case():
+    """3x3 case worked by hand: A = diag-ish with entries 4, 1/4 ... ; one GM
+    sweep on a matrix whose rows/cols each hold one entry makes every scaled
+    entry exactly 1."""
+    assert [OH.round2n(x) for x in (1.0, 0.75, 0.76, 1.5, 1.51, 3.0, 0.1)] == [1.0, 0.5, 1.0, 1.0, 2.0, 2.0, 0.125]
+    P = glpk.glp_create_prob()
+    glpk.glp_add_rows(P, 3)
+    glpk.glp_add_cols(P, 3)
+    for k, v in ((1, 4.0), (2, 0.25), (3, 64.0)):
+        glpk.glp_set_mat_col(P, k, 1, [0, k], [0.0, v])
+    rii, sjj, rep = check_scale_parity(P, nat.GLP_SF_GM)
+    # rows and columns tie (ratio 1 each) -> rows first: rii = 1/|a|, then columns see 1
+    assert rii.tolist() == [0.25, 4.0, 1.0 / 64.0] and sjj.tolist() == [1.0, 1.0, 1.0]
+    assert rep["A"] == (0.25, 64.0, 256.0) and rep["GM"] == (1.0, 1.0, 1.0)
+
+
+@pytest.mark.parametrize("name", ["test", "gap", "todd"])
+def test_scale_fixtures_bit_exact(name):
+    P = read_fixture(name)
+    for flags in ALL_FLAGS:
+        check_scale_parity(P, flags)
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_scale_random_bit_exact(seed):
+    P = random_problem(100 + seed, m=7 + 3 * seed, n=9 + 4 * seed, density=0.3, wide=True)
+    for flags in ALL_FLAGS:
+        check_scale_parity(P, flags)
+
+
+def test_scale_properties():
+    P = random_problem(7, m=40, n=60, density=0.2, wide=True)
+    ptr, ind, val = glpk._csc(P)
+    cols = np.repeat(np.arange(P.n), np.diff(ptr))
+
+    def scaled(rii, sjj):
+        return np.abs(val) * rii[ind] * sjj[cols]
+
+    rii, sjj, rep = product_scale(P, nat.GLP_SF_GM | nat.GLP_SF_EQ)
+    s = scaled(rii, sjj)
+    assert rep["GM"][2] < rep["A"][2]               # geometric mean scaling shrinks the spread
+    assert s.max() <= 1.0 + 1e-12                    # equilibration: largest entry 1 ...
+    colmax = np.zeros(P.n)
+    np.maximum.at(colmax, cols, s)
+    rowmax = np.zeros(P.m)
+    np.maximum.at(rowmax, ind, s)
+    # ... and the lines of the second pass all reach it
+    assert (np.allclose(colmax[colmax > 0], 1.0, rtol=1e-12) or
+            np.allclose(rowmax[rowmax > 0], 1.0, rtol=1e-12))
+    rii2, sjj2, _ = product_scale(P, nat.GLP_SF_GM | nat.GLP_SF_EQ | nat.GLP_SF_2N)
+    for x in list(rii2) + list(sjj2):
+        mant, _ = math.frexp(x)
+        assert mant == 0.5                           # exact powers of two
+    assert np.all(rii2 / rii < 4.0 / 3 + 1e-12) and np.all(rii2 / rii >= 2.0 / 3 - 1e-12)
+    # well-scaled data + SKIP: nothing changes
+    Q = random_problem(8, m=20, n=30, density=0.3, wide=False)
+    r, s_, rep = product_scale(Q, nat.GLP_SF_AUTO)
+    assert rep["skipped"] and np.all(r == 1.0) and np.all(s_ == 1.0)
+
+
+def test_scale_rejects_bad_arguments():
+    ptr = np.array([0, 1], np.int32)
+    with pytest.raises(ValueError):
+        nat.scale_prob(1, 1, ptr, np.array([0], np.int32), np.array([1.0]), 0x02)   # unknown flag
+    with pytest.raises(ValueError):
+        nat.scale_prob(1, 1, ptr, np.array([3], np.int32), np.array([1.0]), 0)      # row out of range
+    P = read_fixture("test")
+    with pytest.raises(glpk.GlpkError):
+        glpk.glp_scale_prob(P, 0x02)
+    with pytest.raises(glpk.GlpkError):
+        glpk.glp_set_rii(P, 1, 0.0)
+    with pytest.raises(glpk.GlpkError):
+        glpk.glp_adv_basis(P, 1)
+
+
+def oracle_adv(P):
+    rows, cols = lists_of(P)
+    m, n = P.m, P.n
+    return OH.adv_basis(
+        m, n, rows, cols,
+        [0] + [P.row[i].type for i in range(1, m + 1)], [0] + [P.row[i].lb for i in range(1, m + 1)],
+        [0] + [P.row[i].ub for i in range(1, m + 1)],
+        [0] + [P.col[j].type for j in range(1, n + 1)], [0] + [P.col[j].lb for j in range(1, n + 1)],
+        [0] + [P.col[j].ub for j in range(1, n + 1)])
+
+
+def check_adv_parity(P):
+    tagx, size = oracle_adv(P)   # its own asserts check the triangular form
+    glpk.glp_adv_basis(P, 0)
+    got = [P.row[i].stat for i in range(1, P.m + 1)] + [P.col[j].stat for j in range(1, P.n + 1)]
+    assert got == tagx[1:]
+    assert P.tri_size == size
+    assert sum(1 for s in got if s == glpk.GLP_BS) == P.m
+    return got, size
+
+
+@pytest.mark.parametrize("name", ["test", "gap", "todd"])
+def test_adv_basis_fixtures(name):
+    P = read_fixture(name)
+    got, size = check_adv_parity(P)
+    assert size == P.m   # every fixture row has a slack or a singleton: full triangle
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_adv_basis_random(seed):
+    P = random_problem(300 + seed, m=5 + 4 * seed, n=6 + 5 * seed, density=0.25)
+    if seed % 3 == 0:
+        glpk.glp_sort_matrix(P)   # another list order, another tie-breaking
+    got, size = check_adv_parity(P)
+    # the basis is non-singular: permuted lower triangular with non-zero diagonal
+    m, n = P.m, P.n
+    A = np.zeros((m, n))
+    for j in range(1, n + 1):
+        for (i, v) in P.col[j].elems:
+            A[i - 1, j - 1] = v
+    B = np.zeros((m, m))
+    c = 0
+    for k, s in enumerate(got):
+        if s == glpk.GLP_BS:
+            if k < m:
+                B[k, c] = 1.0
+            else:
+                B[:, c] = -A[:, k - m]
+            c += 1
+    assert np.linalg.matrix_rank(B) == m
+    # fixed variables never enter the triangular part; they may only be basic as slacks of leftover rows
+    for j in range(1, n + 1):
+        if P.col[j].type == glpk.GLP_FX:
+            assert P.col[j].stat == glpk.GLP_NS
+
+
+def test_adv_basis_all_rows_fixed_takes_structurals():
+    """Equality rows have no usable slack: the triangle must be built from
+    structural columns (a bidiagonal system has a full one)."""
+    m = 6
+    P = glpk.glp_create_prob()
+    glpk.glp_add_rows(P, m)
+    glpk.glp_add_cols(P, m)
+    for i in range(1, m + 1):
+        glpk.glp_set_row_bnds(P, i, glpk.GLP_FX, 1.0, 1.0)
+        glpk.glp_set_col_bnds(P, i, glpk.GLP_LO, 0.0, 0.0)
+    for j in range(1, m + 1):
+        rows = [j] + ([j + 1] if j < m else [])
+        glpk.glp_set_mat_col(P, j, len(rows), [0] + rows, [0.0] + [1.0] * len(rows))
+    got, size = check_adv_parity(P)
+    assert size == m
+    assert all(P.col[j].stat == glpk.GLP_BS for j in range(1, m + 1))
+    assert all(P.row[i].stat == glpk.GLP_NS for i in range(1, m + 1))
+
+
+def test_facade_scaling_state():
+    """glp_scale_prob writes the factors, marks the device copy stale and
+    invalidates the factorisation only when a basic column is touched
+    (lib/glpapi04.js:5-13,22-26); no flags = unscale only (test/test.js:76)."""
+    P = read_fixture("gap")
+    msgs = []
+    glpk.glp_set_print_func(msgs.append)
+    try:
+        glpk.glp_scale_prob(P, glpk.GLP_SF_GM | glpk.GLP_SF_EQ)
+    finally:
+        glpk.glp_set_print_func(None)
+    assert msgs[0] == "Scaling..." and msgs[1].startswith(" A: min|aij| = ") and any(s.startswith("EQ:") for s in msgs)
+    assert any(glpk.glp_get_rii(P, i) != 1.0 for i in range(1, P.m + 1))
+    assert P._dirty
+    P.valid = 1   # all structurals are non-basic after reading: column factors do not matter
+    P._dirty = False
+    glpk.glp_set_sjj(P, 1, 3.0)
+    assert P.valid == 1 and P._dirty
+    glpk.glp_set_rii(P, 1, 5.0)
+    assert P.valid == 1
+    glpk.glp_set_col_stat(P, 1, glpk.GLP_BS)
+    P.valid = 1
+    glpk.glp_set_sjj(P, 1, 2.0)
+    assert P.valid == 0
+    glpk.glp_scale_prob(P)
+    assert all(glpk.glp_get_rii(P, i) == 1.0 for i in range(1, P.m + 1))
+    assert all(glpk.glp_get_sjj(P, j) == 1.0 for j in range(1, P.n + 1))
+
+
+def test_hostprep_large_is_linear_time():
+    """C3-sized covering LP: both steps finish in seconds (O(nnz))."""
+    import time
+    d = nat.generate("covering", m=16384, n=32768)
+    t0 = time.time()
+    rii, sjj, rep = nat.scale_prob(d["m"], d["n"], d["A_ptr"], d["A_ind"], d["A_val"],
+                                   nat.GLP_SF_GM | nat.GLP_SF_EQ | nat.GLP_SF_2N)
+    # rows in index order from the CSC
+    order = np.argsort(d["A_ind"], kind="stable")
+    cols = np.repeat(np.arange(d["n"]), np.diff(d["A_ptr"])).astype(np.int32)
+    R_ptr = np.zeros(d["m"] + 1, np.int32)
+    np.cumsum(np.bincount(d["A_ind"], minlength=d["m"]), out=R_ptr[1:])
+    stat, size = nat.adv_basis(d["m"], d["n"], d["A_ptr"], d["A_ind"], R_ptr, cols[order],
+                               d["type"], d["lb"], d["ub"])
+    assert time.time() - t0 < 20.0
+    assert rep["2N"][2] <= rep["A"][2] * 4
+    assert size == d["m"] and int((stat == nat.GLP_BS).sum()) == d["m"]
