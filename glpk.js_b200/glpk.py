@@ -959,24 +959,109 @@ def _check_smcp(parm):
     if parm.presolve not in (GLP_ON, GLP_OFF): bad("presolve")
 
 
-def glp_simplex(P, parm=None, device=0):
-    """lib/glpapi06.js:261-339"""
-    _check(P, "glp_simplex")
-    if parm is None:
-        parm = SMCP()
-    _check_smcp(parm)
-    P.pbs_stat = P.dbs_stat = GLP_UNDEF
-    P.obj_val, P.some = 0.0, 0
+def _plural(k, word):
+    return "%d %s%s" % (k, word, "" if k == 1 else "s")
+
+
+def _size_line(P):
+    return "%s, %s, %s" % (_plural(P.m, "row"), _plural(P.n, "column"), _plural(P.nnz, "non-zero"))
+
+
+def _check_db_bounds(P, who, msg_lev):
     for i in range(1, P.m + 1):
         r = P.row[i]
         if r.type == GLP_DB and r.lb >= r.ub:
+            if msg_lev >= GLP_MSG_ERR:
+                xprintf("%s: row %d: lb = %s, ub = %s; incorrect bounds" % (who, i, _num(r.lb), _num(r.ub)))
             return GLP_EBOUND
     for j in range(1, P.n + 1):
         c = P.col[j]
         if c.type == GLP_DB and c.lb >= c.ub:
+            if msg_lev >= GLP_MSG_ERR:
+                xprintf("%s: column %d: lb = %s, ub = %s; incorrect bounds" % (who, j, _num(c.lb), _num(c.ub)))
             return GLP_EBOUND
-    if P.m == 0 or P.n == 0:
-        xerror("glp_simplex: empty problems are handled by the host binding only")
+    return 0
+
+
+def _trivial_lp(P, parm):
+    """lib/glpapi06.js:148-255: LP with an empty constraint matrix, solved on the
+    host (there is nothing to launch)."""
+    P.valid = 0
+    P.pbs_stat = P.dbs_stat = GLP_FEAS
+    P.obj_val = P.c0
+    P.some = 0
+    p_infeas = d_infeas = 0.0
+    for i in range(1, P.m + 1):
+        row = P.row[i]
+        row.stat = GLP_BS
+        row.prim = row.dual = 0.0
+        if row.type in (GLP_LO, GLP_DB, GLP_FX):
+            if row.lb > +parm.tol_bnd:
+                P.pbs_stat = GLP_NOFEAS
+                if P.some == 0 and parm.meth != GLP_PRIMAL:
+                    P.some = i
+            if p_infeas < +row.lb:
+                p_infeas = +row.lb
+        if row.type in (GLP_UP, GLP_DB, GLP_FX):
+            if row.ub < -parm.tol_bnd:
+                P.pbs_stat = GLP_NOFEAS
+                if P.some == 0 and parm.meth != GLP_PRIMAL:
+                    P.some = i
+            if p_infeas < -row.ub:
+                p_infeas = -row.ub
+    zeta = 1.0
+    for j in range(1, P.n + 1):
+        zeta = max(zeta, abs(P.col[j].coef))
+    zeta = (+1.0 if P.dir == GLP_MIN else -1.0) / zeta
+    for j in range(1, P.n + 1):
+        col = P.col[j]
+        if col.type == GLP_FR:
+            col.stat, col.prim = GLP_NF, 0.0
+        elif col.type == GLP_FX:
+            col.stat, col.prim = GLP_NS, col.lb
+        else:
+            if col.type == GLP_LO:
+                at_lower = True
+            elif col.type == GLP_UP:
+                at_lower = False
+            elif zeta * col.coef > 0.0:
+                at_lower = True
+            elif zeta * col.coef < 0.0:
+                at_lower = False
+            else:
+                at_lower = abs(col.lb) <= abs(col.ub)
+            col.stat, col.prim = (GLP_NL, col.lb) if at_lower else (GLP_NU, col.ub)
+        col.dual = col.coef
+        P.obj_val += col.coef * col.prim
+        if col.type in (GLP_FR, GLP_LO):
+            if zeta * col.dual < -parm.tol_dj:
+                P.dbs_stat = GLP_NOFEAS
+                if P.some == 0 and parm.meth == GLP_PRIMAL:
+                    P.some = P.m + j
+            d_infeas = max(d_infeas, -zeta * col.dual)
+        if col.type in (GLP_FR, GLP_UP):
+            if zeta * col.dual > +parm.tol_dj:
+                P.dbs_stat = GLP_NOFEAS
+                if P.some == 0 and parm.meth == GLP_PRIMAL:
+                    P.some = P.m + j
+            d_infeas = max(d_infeas, +zeta * col.dual)
+    if parm.msg_lev >= GLP_MSG_ON and parm.out_dly == 0:
+        xprintf("~%d: obj = %s  infeas = %s" % (P.it_cnt, _num(P.obj_val),
+                                                _num(p_infeas if parm.meth == GLP_PRIMAL else d_infeas)))
+    if parm.msg_lev >= GLP_MSG_ALL and parm.out_dly == 0:
+        if P.pbs_stat == GLP_FEAS and P.dbs_stat == GLP_FEAS:
+            xprintf("OPTIMAL SOLUTION FOUND")
+        elif P.pbs_stat == GLP_NOFEAS:
+            xprintf("PROBLEM HAS NO FEASIBLE SOLUTION")
+        elif parm.meth == GLP_PRIMAL:
+            xprintf("PROBLEM HAS UNBOUNDED SOLUTION")
+        else:
+            xprintf("PROBLEM HAS NO DUAL FEASIBLE SOLUTION")
+
+
+def _solve_lp(P, parm, device):
+    """lib/glpapi06.js:3-39 -- the drop-in boundary: glp_factorize + spx_primal /
+    spx_dual run behind glpb_simplex on the device-resident handle."""
     dev = _device(P, device)
     sp = dev.smcp(msg_lev=parm.msg_lev, meth=parm.meth, pricing=parm.pricing, r_test=parm.r_test,
                   tol_bnd=parm.tol_bnd, tol_dj=parm.tol_dj, tol_piv=parm.tol_piv, obj_ll=parm.obj_ll,
@@ -988,35 +1073,173 @@ def glp_simplex(P, parm=None, device=0):
     return ret
 
 
-def glp_intopt(P, parm=None, device=0):
-    """lib/glpapi09.js:61-390 (presolve OFF path: the root LP must be optimal)"""
-    _check(P, "glp_intopt")
+def _clone(P):
+    """What npp_load_prob + npp_build_prob leave when no transformation applies:
+    a fresh problem with the same rows, columns and coefficients, unit scale
+    factors and the default statuses of new rows/columns."""
+    Q = glp_prob()
+    Q.name, Q.obj, Q.dir, Q.c0 = P.name, P.obj, P.dir, P.c0
+    Q.m, Q.n, Q.nnz = P.m, P.n, P.nnz
+    for i in range(1, P.m + 1):
+        r, q = P.row[i], _Row(i)
+        q.name, q.type, q.lb, q.ub, q.elems = r.name, r.type, r.lb, r.ub, list(r.elems)
+        Q.row.append(q)
+    for j in range(1, P.n + 1):
+        c, q = P.col[j], _Col(j)
+        q.name, q.kind, q.type, q.lb, q.ub, q.coef = c.name, c.kind, c.type, c.lb, c.ub, c.coef
+        q.elems = list(c.elems)
+        Q.col.append(q)
+    Q.bfcp = P.bfcp
+    return Q
+
+
+def _quiet(msg_lev, fn, *args):
+    """The reference mutes the terminal around scaling / crash basis unless
+    msg_lev >= GLP_MSG_ALL (lib/glpapi06.js:107-128)."""
+    global _print_func
+    saved = _print_func
+    if msg_lev < GLP_MSG_ALL:
+        _print_func = None
+    try:
+        return fn(*args)
+    finally:
+        _print_func = saved
+
+
+def _bound_value(x):
+    return {GLP_NL: x.lb, GLP_NU: x.ub, GLP_NF: 0.0, GLP_NS: x.lb}[x.stat]
+
+
+def _unload_basic(P, lp):
+    """npp_unload_sol, basic solution (lib/glpnpp01.js:589-682) with identity
+    recovery: statuses and the free values come from the solved copy, the rest
+    is recomputed from the ORIGINAL coefficients."""
+    P.valid = 0
+    P.pbs_stat, P.dbs_stat = lp.pbs_stat, lp.dbs_stat
+    P.obj_val = P.c0
+    P.some = 0
+    for i in range(1, P.m + 1):
+        row, src = P.row[i], lp.row[i]
+        row.stat = src.stat
+        row.dual = src.dual
+        if row.stat == GLP_BS:
+            row.dual = 0.0
+        else:
+            row.prim = _bound_value(row)
+    for j in range(1, P.n + 1):
+        col, src = P.col[j], lp.col[j]
+        col.stat = src.stat
+        col.prim = src.prim
+        if col.stat == GLP_BS:
+            col.dual = 0.0
+        else:
+            col.prim = _bound_value(col)
+        P.obj_val += col.coef * col.prim
+    for i in range(1, P.m + 1):
+        row = P.row[i]
+        if row.stat == GLP_BS:
+            temp = 0.0
+            for (j, v) in row.elems:
+                temp += v * P.col[j].prim
+            row.prim = temp
+    for j in range(1, P.n + 1):
+        col = P.col[j]
+        if col.stat != GLP_BS:
+            temp = col.coef
+            for (i, v) in col.elems:
+                temp -= v * P.row[i].dual
+            col.dual = temp
+
+
+def _unload_mip(P, mip):
+    """npp_unload_sol, MIP solution (lib/glpnpp01.js:734-756)"""
+    P.mip_stat = mip.mip_stat
+    P.mip_obj = P.c0
+    for j in range(1, P.n + 1):
+        col = P.col[j]
+        col.mipx = mip.col[j].mipx
+        P.mip_obj += col.coef * col.mipx
+    for i in range(1, P.m + 1):
+        temp = 0.0
+        for (j, v) in P.row[i].elems:
+            temp += v * P.col[j].mipx
+        P.row[i].mipx = temp
+
+
+def _drop_device(P):
+    if P._dev is not None:
+        P._dev.close()
+        P._dev = None
+
+
+def _preprocess_and_solve_lp(P, parm, device):
+    """lib/glpapi06.js:40-146 around an identity presolve (the transformations of
+    glpnpp*.js are not built): working copy, automatic scaling, triangular crash
+    basis, solve on the device, solution stored back as npp_unload_sol does."""
+    if parm.msg_lev >= GLP_MSG_ALL:
+        xprintf("Preprocessing...")
+    lp = _clone(P)
+    if parm.msg_lev >= GLP_MSG_ALL:
+        xprintf(_size_line(lp))
+    try:
+        _quiet(parm.msg_lev, glp_scale_prob, lp, GLP_SF_AUTO)
+        _quiet(parm.msg_lev, glp_adv_basis, lp, 0)
+        lp.it_cnt = P.it_cnt
+        ret = _solve_lp(lp, parm, device)
+        P.it_cnt = lp.it_cnt
+    finally:
+        _drop_device(lp)
+    if not (ret == 0 and lp.pbs_stat == GLP_FEAS and lp.dbs_stat == GLP_FEAS):
+        if parm.msg_lev >= GLP_MSG_ERR:
+            xprintf("glp_simplex: unable to recover undefined or non-optimal solution")
+        if ret == 0:
+            if lp.pbs_stat == GLP_NOFEAS:
+                ret = GLP_ENOPFS
+            elif lp.dbs_stat == GLP_NOFEAS:
+                ret = GLP_ENODFS
+        return ret
+    _unload_basic(P, lp)
+    return 0
+
+
+def glp_simplex(P, parm=None, device=0):
+    """lib/glpapi06.js:261-339"""
+    _check(P, "glp_simplex")
     if parm is None:
-        parm = IOCP()
-    if parm.br_tech not in (GLP_BR_FFV, GLP_BR_LFV, GLP_BR_MFV, GLP_BR_DTH, GLP_BR_PCH):
-        xerror("glp_intopt: br_tech = %r; invalid parameter" % (parm.br_tech,))
-    if parm.bt_tech not in (GLP_BT_DFS, GLP_BT_BFS, GLP_BT_BLB, GLP_BT_BPH):
-        xerror("glp_intopt: bt_tech = %r; invalid parameter" % (parm.bt_tech,))
-    if not (0.0 < parm.tol_int < 1.0):
-        xerror("glp_intopt: tol_int = %r; invalid parameter" % (parm.tol_int,))
-    if not (0.0 < parm.tol_obj < 1.0):
-        xerror("glp_intopt: tol_obj = %r; invalid parameter" % (parm.tol_obj,))
-    P.mip_stat, P.mip_obj = GLP_UNDEF, 0.0
-    for j in range(1, P.n + 1):  # lib/glpapi09.js:337-364
-        c = P.col[j]
-        if c.kind == GLP_IV:
-            if c.type in (GLP_LO, GLP_DB) and c.lb != math.floor(c.lb):
-                return GLP_EBOUND
-            if c.type in (GLP_UP, GLP_DB) and c.ub != math.floor(c.ub):
-                return GLP_EBOUND
-            if c.type == GLP_FX and c.lb != math.floor(c.lb):
-                return GLP_EBOUND
-    if parm.presolve == GLP_ON:
-        ret = glp_simplex(P, SMCP({"msg_lev": parm.msg_lev}), device=device)
-        if ret != 0:
-            return ret
+        parm = SMCP()
+    _check_smcp(parm)
+    P.pbs_stat = P.dbs_stat = GLP_UNDEF
+    P.obj_val, P.some = 0.0, 0
+    ret = _check_db_bounds(P, "glp_simplex", parm.msg_lev)
+    if ret != 0:
+        return ret
+    if parm.msg_lev >= GLP_MSG_ALL:
+        xprintf("GLPK Simplex Optimizer, v4.49")
+        xprintf(_size_line(P))
+    if P.nnz == 0:
+        _trivial_lp(P, parm)
+        return 0
+    if not parm.presolve:
+        return _solve_lp(P, parm, device)
+    return _preprocess_and_solve_lp(P, parm, device)
+
+
+def _solve_mip(P, parm, device):
+    """lib/glpapi09.js:62-114 -- the root LP must be optimal; the tree runs
+    behind glpb_intopt on the handle that solved the relaxation."""
     if glp_get_status(P) != GLP_OPT:
+        if parm.msg_lev >= GLP_MSG_ERR:
+            xprintf("glp_intopt: optimal basis to initial LP relaxation not provided")
         return GLP_EROOT
+    if P._dev is None or P._dirty or not P.valid:
+        # the optimal basis was found elsewhere (e.g. by a presolve:ON solve, which
+        # leaves P.valid = 0): give the handle that basis; the reference's
+        # ios_driver re-solves the root from it in the same way (glpios03.js:567)
+        quiet = SMCP()
+        quiet.msg_lev = GLP_MSG_OFF
+        ret = _solve_lp(P, quiet, device)
+        if ret != 0 or glp_get_status(P) != GLP_OPT:
+            return GLP_EROOT
     dev = P._dev
     ip = dev.iocp(msg_lev=parm.msg_lev, br_tech=parm.br_tech, bt_tech=parm.bt_tech,
                   tol_int=parm.tol_int, tol_obj=parm.tol_obj, tm_lim=int(parm.tm_lim),
@@ -1031,3 +1254,116 @@ def glp_intopt(P, parm=None, device=0):
         P.col[j].mipx = float(mp["mipx"][P.m + j - 1])
     _pull(P, dev)
     return ret
+
+
+def _int_stats_line(P):
+    ni, nb = glp_get_num_int(P), glp_get_num_bin(P)
+    if nb == 0:
+        s = "none of"
+    elif ni == 1 and nb == 1:
+        s = ""
+    elif nb == 1:
+        s = "one of"
+    elif nb == ni:
+        s = "all of"
+    else:
+        s = "%d of" % nb
+    return "%s, %s which %s binary" % (_plural(ni, "integer variable"), s, "is" if nb == 1 else "are")
+
+
+def _preprocess_and_solve_mip(P, parm, device):
+    """lib/glpapi09.js:116-256 around an identity presolve (see
+    _preprocess_and_solve_lp): copy, scaling GM|EQ|2N|SKIP, crash basis, LP
+    relaxation, branch-and-bound on the device, MIP solution stored back."""
+    if parm.msg_lev >= GLP_MSG_ALL:
+        xprintf("Preprocessing...")
+    mip = _clone(P)
+    if parm.msg_lev >= GLP_MSG_ALL:
+        xprintf(_size_line(mip))
+        xprintf(_int_stats_line(mip))
+    try:
+        _quiet(parm.msg_lev, glp_scale_prob, mip, GLP_SF_GM | GLP_SF_EQ | GLP_SF_2N | GLP_SF_SKIP)
+        _quiet(parm.msg_lev, glp_adv_basis, mip, 0)
+        if parm.msg_lev >= GLP_MSG_ALL:
+            xprintf("Solving LP relaxation...")
+        smcp = SMCP()
+        smcp.msg_lev = parm.msg_lev
+        mip.it_cnt = P.it_cnt
+        ret = glp_simplex(mip, smcp, device=device)
+        P.it_cnt = mip.it_cnt
+        if ret != 0:
+            if parm.msg_lev >= GLP_MSG_ERR:
+                xprintf("glp_intopt: cannot solve LP relaxation")
+            return GLP_EFAIL
+        ret = glp_get_status(mip)
+        if ret == GLP_OPT:
+            ret = 0
+        elif ret == GLP_NOFEAS:
+            ret = GLP_ENOPFS
+        elif ret == GLP_UNBND:
+            ret = GLP_ENODFS
+        if ret != 0:
+            return ret
+        mip.it_cnt = P.it_cnt
+        ret = _solve_mip(mip, parm, device)
+        P.it_cnt = mip.it_cnt
+    finally:
+        _drop_device(mip)
+    if mip.mip_stat not in (GLP_OPT, GLP_FEAS):
+        P.mip_stat = mip.mip_stat
+        return ret
+    _unload_mip(P, mip)
+    return ret
+
+
+def _check_iocp(parm):
+    # lib/glpapi09.js:265-315
+    def bad(name):
+        xerror("glp_intopt: %s = %r; invalid parameter" % (name, getattr(parm, name)))
+    if parm.msg_lev not in (GLP_MSG_OFF, GLP_MSG_ERR, GLP_MSG_ON, GLP_MSG_ALL, GLP_MSG_DBG): bad("msg_lev")
+    if parm.br_tech not in (GLP_BR_FFV, GLP_BR_LFV, GLP_BR_MFV, GLP_BR_DTH, GLP_BR_PCH): bad("br_tech")
+    if parm.bt_tech not in (GLP_BT_DFS, GLP_BT_BFS, GLP_BT_BLB, GLP_BT_BPH): bad("bt_tech")
+    if not (0.0 < parm.tol_int < 1.0): bad("tol_int")
+    if not (0.0 < parm.tol_obj < 1.0): bad("tol_obj")
+    if parm.tm_lim < 0: bad("tm_lim")
+    if parm.out_frq < 0: bad("out_frq")
+    if parm.out_dly < 0: bad("out_dly")
+    if not (0 <= parm.cb_size <= 256): bad("cb_size")
+    if parm.pp_tech not in (GLP_PP_NONE, GLP_PP_ROOT, GLP_PP_ALL): bad("pp_tech")
+    if parm.mip_gap < 0.0: bad("mip_gap")
+    for name in ("mir_cuts", "gmi_cuts", "cov_cuts", "clq_cuts", "presolve", "binarize", "fp_heur"):
+        if getattr(parm, name) not in (GLP_ON, GLP_OFF): bad(name)
+
+
+def glp_intopt(P, parm=None, device=0):
+    """lib/glpapi09.js:258-390"""
+    _check(P, "glp_intopt")
+    if parm is None:
+        parm = IOCP()
+    _check_iocp(parm)
+    P.mip_stat, P.mip_obj = GLP_UNDEF, 0.0
+    ret = _check_db_bounds(P, "glp_intopt", parm.msg_lev)
+    if ret != 0:
+        return ret
+    for j in range(1, P.n + 1):  # lib/glpapi09.js:337-364
+        c = P.col[j]
+        if c.kind != GLP_IV:
+            continue
+        what = None
+        if c.type in (GLP_LO, GLP_DB) and c.lb != math.floor(c.lb):
+            what = "lower bound %s" % _num(c.lb)
+        elif c.type in (GLP_UP, GLP_DB) and c.ub != math.floor(c.ub):
+            what = "upper bound %s" % _num(c.ub)
+        elif c.type == GLP_FX and c.lb != math.floor(c.lb):
+            what = "fixed value %s" % _num(c.lb)
+        if what:
+            if parm.msg_lev >= GLP_MSG_ERR:
+                xprintf("glp_intopt: integer column %d has non-integer %s" % (j, what))
+            return GLP_EBOUND
+    if parm.msg_lev >= GLP_MSG_ALL:
+        xprintf("GLPK Integer Optimizer, v4.49")
+        xprintf(_size_line(P))
+        xprintf(_int_stats_line(P))
+    if not parm.presolve:
+        return _solve_mip(P, parm, device)
+    return _preprocess_and_solve_mip(P, parm, device)

@@ -148,3 +148,69 @@ def test_facade_like_reference_test_js():
     x = [glpk.glp_get_col_prim(lp, j) for j in range(1, glpk.glp_get_num_cols(lp) + 1)]
     np.testing.assert_allclose(x, [33.333333333333336, 66.66666666666666, 0.0], atol=1e-9)
     assert [glpk.glp_get_col_name(lp, j) for j in (1, 2, 3)] == ["x1", "x2", "x3"]
+
+
+@pytest.mark.parametrize("name", ["test", "gap", "todd"])
+@pytest.mark.parametrize("flags", [glpk.GLP_SF_AUTO, glpk.GLP_SF_GM | glpk.GLP_SF_EQ | glpk.GLP_SF_2N,
+                                   glpk.GLP_SF_EQ])
+def test_scaled_problem_and_crash_basis_reach_the_same_optimum(name, flags):
+    """glp_scale_prob + glp_adv_basis feed the path (rii/sjj into glpb_create,
+    statuses into glpb_set_basis); the un-scaled solution must satisfy the KKT
+    conditions of the ORIGINAL problem and match the pins."""
+    d = H.load_golden(name)
+    lp = glpk.glp_create_prob()
+    assert glpk.glp_read_lp_from_string(lp, None, H.golden_text(name)) == 0
+    glpk.glp_scale_prob(lp, flags)
+    glpk.glp_adv_basis(lp, 0)
+    parm = glpk.SMCP()
+    parm.msg_lev = glpk.GLP_MSG_OFF
+    for meth in (glpk.GLP_PRIMAL, glpk.GLP_DUALP):
+        parm.meth = meth
+        assert glpk.glp_simplex(lp, parm) == 0
+        assert glpk.glp_get_status(lp) == glpk.GLP_OPT
+        assert abs(glpk.glp_get_obj_val(lp) - d["highs_lp_obj"]) <= 1e-9 * max(1.0, abs(d["highs_lp_obj"]))
+        m, n = lp.m, lp.n
+        sol = dict(prim=np.array([lp.row[i].prim for i in range(1, m + 1)] + [lp.col[j].prim for j in range(1, n + 1)]),
+                   dual=np.array([lp.row[i].dual for i in range(1, m + 1)] + [lp.col[j].dual for j in range(1, n + 1)]),
+                   stat=np.array([lp.row[i].stat for i in range(1, m + 1)] + [lp.col[j].stat for j in range(1, n + 1)]))
+        arrays, _, _ = glpk._arrays(lp)
+        r = H.kkt(arrays, sol)
+        assert max(r.values()) <= 1e-9, r
+
+
+@pytest.mark.parametrize("name", ["test", "gap", "todd"])
+def test_presolve_on_flow_of_test_js(name):
+    """test/test.js cplex(): glp_simplex with presolve ON, then glp_intopt with
+    presolve ON (copy, scaling, crash basis, solve, solution stored back)."""
+    d = H.load_golden(name)
+    lp = glpk.glp_create_prob()
+    assert glpk.glp_read_lp_from_string(lp, None, H.golden_text(name)) == 0
+    msgs = []
+    glpk.glp_set_print_func(msgs.append)
+    try:
+        assert glpk.glp_simplex(lp, glpk.SMCP({"presolve": glpk.GLP_ON})) == 0
+    finally:
+        glpk.glp_set_print_func(None)
+    assert msgs[0].startswith("GLPK Simplex Optimizer") and "Preprocessing..." in msgs and "Scaling..." in msgs
+    assert "Constructing initial basis..." in msgs
+    assert lp.valid == 0 and glpk.glp_get_status(lp) == glpk.GLP_OPT
+    assert abs(glpk.glp_get_obj_val(lp) - d["highs_lp_obj"]) <= 1e-9 * max(1.0, abs(d["highs_lp_obj"]))
+    assert all(glpk.glp_get_rii(lp, i) == 1.0 for i in range(1, lp.m + 1))   # the original stays unscaled
+    m, n = lp.m, lp.n
+    sol = dict(prim=np.array([lp.row[i].prim for i in range(1, m + 1)] + [lp.col[j].prim for j in range(1, n + 1)]),
+               dual=np.array([lp.row[i].dual for i in range(1, m + 1)] + [lp.col[j].dual for j in range(1, n + 1)]),
+               stat=np.array([lp.row[i].stat for i in range(1, m + 1)] + [lp.col[j].stat for j in range(1, n + 1)]))
+    arrays, _, _ = glpk._arrays(lp)
+    r = H.kkt(arrays, sol)
+    assert max(r.values()) <= 1e-9, r
+    if "highs_mip_obj" in d and d["highs_mip_obj"] is not None:
+        iocp = glpk.IOCP({"presolve": glpk.GLP_ON})
+        iocp.msg_lev = glpk.GLP_MSG_OFF
+        assert glpk.glp_intopt(lp, iocp) == 0
+        assert glpk.glp_mip_status(lp) == glpk.GLP_OPT
+        assert glpk.glp_mip_obj_val(lp) == d["highs_mip_obj"]
+        # and B&B without the presolver from the optimal basis a presolve:ON solve left (valid = 0)
+        iocp2 = glpk.IOCP()
+        iocp2.msg_lev = glpk.GLP_MSG_OFF
+        assert glpk.glp_intopt(lp, iocp2) == 0
+        assert glpk.glp_mip_obj_val(lp) == d["highs_mip_obj"]

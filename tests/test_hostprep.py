@@ -285,3 +285,82 @@ def test_hostprep_large_is_linear_time():
     assert time.time() - t0 < 20.0
     assert rep["2N"][2] <= rep["A"][2] * 4
     assert size == d["m"] and int((stat == nat.GLP_BS).sum()) == d["m"]
+
+
+# ---- glp_simplex on an LP without constraint coefficients (lib/glpapi06.js:148-255):
+# ---- solved on the host, no device involved
+def _trivial(dir_, cols, rows=(), meth=None):
+    P = glpk.glp_create_prob()
+    glpk.glp_set_obj_dir(P, dir_)
+    if rows:
+        glpk.glp_add_rows(P, len(rows))
+        for i, (t, lb, ub) in enumerate(rows, 1):
+            glpk.glp_set_row_bnds(P, i, t, lb, ub)
+    glpk.glp_add_cols(P, len(cols))
+    for j, (t, lb, ub, c) in enumerate(cols, 1):
+        glpk.glp_set_col_bnds(P, j, t, lb, ub)
+        glpk.glp_set_obj_coef(P, j, c)
+    parm = glpk.SMCP()
+    if meth:
+        parm.meth = meth
+    msgs = []
+    glpk.glp_set_print_func(msgs.append)
+    try:
+        ret = glpk.glp_simplex(P, parm)
+    finally:
+        glpk.glp_set_print_func(None)
+    return P, ret, msgs
+
+
+def test_trivial_lp_optimal():
+    P, ret, msgs = _trivial(glpk.GLP_MIN,
+                            [(glpk.GLP_LO, 1.0, 0.0, 2.0), (glpk.GLP_UP, 0.0, 4.0, -3.0),
+                             (glpk.GLP_DB, -1.0, 5.0, 1.0), (glpk.GLP_DB, -1.0, 5.0, -1.0),
+                             (glpk.GLP_DB, -1.0, 5.0, 0.0), (glpk.GLP_DB, -7.0, 5.0, 0.0),
+                             (glpk.GLP_FX, 2.5, 2.5, 4.0), (glpk.GLP_FR, 0.0, 0.0, 0.0)],
+                            rows=[(glpk.GLP_UP, 0.0, 3.0), (glpk.GLP_FR, 0.0, 0.0)])
+    assert ret == 0 and glpk.glp_get_status(P) == glpk.GLP_OPT
+    assert [P.col[j].stat for j in range(1, 9)] == [glpk.GLP_NL, glpk.GLP_NU, glpk.GLP_NL, glpk.GLP_NU,
+                                                    glpk.GLP_NL, glpk.GLP_NU, glpk.GLP_NS, glpk.GLP_NF]
+    assert [P.col[j].prim for j in range(1, 9)] == [1.0, 4.0, -1.0, 5.0, -1.0, 5.0, 2.5, 0.0]
+    assert glpk.glp_get_obj_val(P) == 2.0 - 12.0 - 1.0 - 5.0 + 10.0
+    assert [P.col[j].dual for j in range(1, 9)] == [2.0, -3.0, 1.0, -1.0, 0.0, 0.0, 4.0, 0.0]
+    assert all(P.row[i].stat == glpk.GLP_BS and P.row[i].prim == 0.0 for i in (1, 2))
+    assert msgs == ["GLPK Simplex Optimizer, v4.49", "2 rows, 8 columns, 0 non-zeros",
+                    "~0: obj = -6  infeas = 0", "OPTIMAL SOLUTION FOUND"]
+    assert P.valid == 0
+
+
+def test_trivial_lp_unbounded_and_infeasible():
+    # min -x, x >= 0: dual infeasible; with the primal method `some` names the ray
+    P, ret, msgs = _trivial(glpk.GLP_MIN, [(glpk.GLP_LO, 0.0, 0.0, -1.0)])
+    assert ret == 0 and glpk.glp_get_status(P) == glpk.GLP_UNBND and glpk.glp_get_unbnd_ray(P) == 1
+    assert msgs[-1] == "PROBLEM HAS UNBOUNDED SOLUTION" and msgs[-2] == "~0: obj = 0  infeas = 0"
+    P, ret, msgs = _trivial(glpk.GLP_MAX, [(glpk.GLP_UP, 0.0, 0.0, -2.0)], meth=glpk.GLP_DUAL)
+    assert glpk.glp_get_dual_stat(P) == glpk.GLP_NOFEAS and P.some == 0
+    assert msgs[-1] == "PROBLEM HAS NO DUAL FEASIBLE SOLUTION" and msgs[-2] == "~0: obj = 0  infeas = 1"
+    # a row 0 >= 2 cannot hold
+    P, ret, msgs = _trivial(glpk.GLP_MIN, [(glpk.GLP_LO, 0.0, 0.0, 1.0)], rows=[(glpk.GLP_LO, 2.0, 0.0)],
+                            meth=glpk.GLP_DUAL)
+    assert ret == 0 and glpk.glp_get_prim_stat(P) == glpk.GLP_NOFEAS and P.some == 1
+    assert msgs[-1] == "PROBLEM HAS NO FEASIBLE SOLUTION"
+
+
+def test_incorrect_bounds_and_parameter_checks():
+    P = read_fixture("test")
+    glpk.glp_set_col_bnds(P, 1, glpk.GLP_DB, 0.0, 1.0)
+    P.col[1].ub = -1.0
+    msgs = []
+    glpk.glp_set_print_func(msgs.append)
+    try:
+        assert glpk.glp_simplex(P, glpk.SMCP()) == glpk.GLP_EBOUND
+        assert glpk.glp_intopt(P, glpk.IOCP()) == glpk.GLP_EBOUND
+    finally:
+        glpk.glp_set_print_func(None)
+    assert msgs == ["glp_simplex: column 1: lb = 0, ub = -1; incorrect bounds",
+                    "glp_intopt: column 1: lb = 0, ub = -1; incorrect bounds"]
+    bad = glpk.IOCP()
+    bad.pp_tech = 7
+    with pytest.raises(glpk.GlpkError):
+        glpk.glp_intopt(P, bad)
+    assert glpk._num(1e-7) == "1e-7" and glpk._num(2.5e+30) == "2.5e+30" and glpk._num(3.0) == "3"
