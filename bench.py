@@ -157,6 +157,56 @@ class CpuSampler:
         return s + " (C++ port of the reference, single thread; the JS reference cannot run here: no JS engine)"
 
 
+# DRAM traffic of the dominant kernels from the committed `ncu --set full` captures (never
+# measured inside a bench run): whole-launch sums, one launch = several hundred iterations
+TRAFFIC_EVIDENCE = {
+    "primal": {"file": "profiles/r01j_ncu_full_engine_primal.csv", "kernel": "k_engine_primal",
+               "dram_read_bytes_per_launch": 41.924864e6, "dram_write_bytes_per_launch": 2.069248e6,
+               "launch_ms_under_ncu": 16.451,
+               "reading": "C2 is L2-resident: ~0.1 MB of DRAM traffic per iteration against 45.8 MB of "
+                          "algorithmic bytes -- the iteration is latency-bound, not bandwidth-bound"},
+    "dual": {"file": "profiles/r01h_ncu_full_prof44_engine_dual.csv", "kernel": "k_engine_dual",
+             "dram_read_bytes_per_launch": 285.441696e9, "dram_write_bytes_per_launch": 13.03564e9,
+             "launch_ms_under_ncu": 158.701,
+             "reading": "C3, k ~ 5000, ~1000 iterations in the launch: DRAM read = 8 k^2 bytes x iterations, "
+                        "i.e. traffic = algorithmic bytes of the dense T*v stream, no re-reads"},
+}
+
+
+def roofline_from_profile(prof, eng_name, peak, peak_src, evidence=None):
+    """roofline object from a glpb_profile_report: per-kernel CUDA-event time and algorithmic
+    bytes; the phases of the persistent engine (eng_*) are summed into one unit `eng_name`."""
+    ref_split = {k: v for k, v in prof.items() if k.startswith("ref_")}          # inside k_refactor: informational
+    units = {k: v for k, v in prof.items() if not k.startswith("k_engine_") and not k.startswith("ref_")}
+    tot_prof_ms = sum(v["ms"] for v in units.values()) or 1.0
+    # the dominant kernel is the persistent engine: its roofline entry is the sum of the
+    # algorithmic bytes of all its phases over the CUDA-event time of its launches
+    phases = {k: v for k, v in units.items() if k.startswith("eng_")}
+    agg = {"ms": sum(v["ms"] for v in phases.values()), "bytes": sum(v["bytes"] for v in phases.values()),
+           "count": max([v["count"] for v in phases.values()] or [0])}
+    cands = {k: v for k, v in units.items() if not k.startswith("eng_") and v["bytes"] > 0 and v["count"] > 0}
+    if agg["ms"] > 0 and agg["count"] > 0:
+        cands[eng_name] = agg
+    top = max(cands, key=lambda k: cands[k]["ms"]) if cands else None
+    if not top:
+        return None
+    v = cands[top]
+    ach = (v["bytes"] / v["count"]) / (v["ms"] / v["count"] * 1e-3) / 1e9
+    shares = {k: x["ms"] for k, x in units.items() if not k.startswith("eng_")}
+    shares[eng_name] = agg["ms"]
+    return {"bound": "hbm", "kernel": top, "achieved": ach, "peak": peak, "unit": "GB/s",
+            "frac": ach / peak, "traffic": None, "traffic_evidence": evidence, "peak_source": peak_src,
+            "bytes_per_launch": v["bytes"] / v["count"], "us_per_launch": 1000.0 * v["ms"] / v["count"],
+            "share_of_device_time": v["ms"] / tot_prof_ms,
+            "note": "for the persistent engine one 'launch' = one simplex iteration (all phases); "
+                    "phase_table splits it (SM-cycle stamps of CTA 0 between grid barriers)",
+            "kernel_shares": {k: round(x / tot_prof_ms, 4) for k, x in sorted(shares.items(), key=lambda kv: -kv[1])[:8]},
+            "phase_table": {k[4:]: {"us": round(1000.0 * x["ms"] / max(1, x["count"]), 3),
+                                    "GBps": round(x["bytes"] / max(1e-9, x["ms"]) / 1e6, 1)}
+                            for k, x in sorted(phases.items())},
+            "refactor_split_ms": {k[4:]: round(x["ms"], 2) for k, x in ref_split.items()}}
+
+
 def run_reference(args, w, rank, world):
     """--impl reference: the reference's own CPU implementation of the path.
     The reference is JavaScript and no JS engine exists in this image, so this
@@ -215,6 +265,7 @@ def run_bnb(args, w, rank, local_rank, world):
 
     sampler = ClockSampler(local_rank)
     times, nodes, objs = [], [], []
+    acct = {"launches": 0, "syncs": 0, "iterations": 0, "refactorizations": 0}
     for s in range(args.warmup + args.steps):
         probs = []
         for _ in range(W):                              # host buffers -> device every step (e2e == value here)
@@ -233,6 +284,7 @@ def run_bnb(args, w, rank, local_rank, world):
                                             node_lim=node_lim, msg_lev=0)
 
         barrier()
+        c0 = [P.counters() for P in probs]
         t0 = time.perf_counter()
         threads = [threading.Thread(target=work, args=(r,)) for r in range(1, W)]
         for t in threads:
@@ -242,9 +294,12 @@ def run_bnb(args, w, rank, local_rank, world):
             t.join()
         barrier()
         dt = time.perf_counter() - t0
+        c1 = [P.counters() for P in probs]
         for P in probs:
             P.close()
         if s >= args.warmup:
+            for key in acct:
+                acct[key] += sum(b[key] - a[key] for a, b in zip(c0, c1))
             times.append(dt)
             nodes.append(results[0]["total_nodes"])
             objs.append(results[0]["obj"])
@@ -255,6 +310,26 @@ def run_bnb(args, w, rank, local_rank, world):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         my = float(t.item())
     value = sum(nodes) / my
+    # per-kernel device time of one worker's search (CUDA events on its stream; separate,
+    # untimed pass): which kernel the node time goes to and its algorithmic bytes
+    roofline, node_acct = None, None
+    if rank == 0:
+        Pp = nat.Problem(d, device=local_rank)
+        assert Pp.simplex(meth=nat.GLP_PRIMAL) == 0
+        Pp.set_profile(1)
+        rp = bnb.sharded_intopt(bnb.Worker(Pp), bnb.HybridComm(bnb.LocalGroup(1), 0, None),
+                                minimize=(d["dir"] == nat.GLP_MIN), node_lim=node_lim, msg_lev=0)
+        prof = Pp.profile()
+        Pp.close()
+        peak, peak_src = peaks()
+        roofline = roofline_from_profile(prof, "k_engine_dual", peak, peak_src)
+        if roofline:
+            roofline["note"] = ("one worker handle, %d nodes, profiling pass outside the timed region; node LPs "
+                                "(m=30) run in a ONE-CTA engine out of shared memory/L2, so the HBM fraction is "
+                                "low by construction: node time is launch + synchronisation latency"
+                                % rp["total_nodes"])
+        local_nodes = max(1, sum(nodes) // world)      # acct covers this rank's handles only
+        node_acct = {k + "_per_node": round(v / local_nodes, 2) for k, v in acct.items()}
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         import oracle_lib as O
@@ -275,7 +350,8 @@ def run_bnb(args, w, rank, local_rank, world):
                            "parallelism": "nodes sharded over %d GPU(s) x %d worker handles" % (world, W)},
                 "clocks": clocks, "e2e": {"value": value, "unit": "nodes/s", "h2d_bytes_per_step": int(sum(
                     a.nbytes for a in d.values() if isinstance(a, np.ndarray))), "d2h_bytes_per_step": 8 * (d["m"] + d["n"])},
-                "gpu_launches": None, "roofline": None, "cpu_baseline": cpu, "incumbent": objs[-1] if objs else None}
+                "gpu_launches": int(acct["launches"]) * world, "roofline": roofline, "cpu_baseline": cpu,
+                "per_node": node_acct, "incumbent": objs[-1] if objs else None}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -381,37 +457,9 @@ def main():
     P.simplex(meth=meth, it_lim=int(iters[-1]) if (args.profile_full or iters[-1] <= 20000) else 1500)
     prof = P.profile()
     P.set_profile(0)
-    ref_split = {k: v for k, v in prof.items() if k.startswith("ref_")}          # inside k_refactor: informational
-    units = {k: v for k, v in prof.items() if not k.startswith("k_engine_") and not k.startswith("ref_")}
-    tot_prof_ms = sum(v["ms"] for v in units.values()) or 1.0
-    # the dominant kernel is the persistent engine: its roofline entry is the sum of the
-    # algorithmic bytes of all its phases over the CUDA-event time of its launches
-    eng_name = "k_engine_primal" if w["meth"] == "primal" else "k_engine_dual"
-    phases = {k: v for k, v in units.items() if k.startswith("eng_")}
-    agg = {"ms": sum(v["ms"] for v in phases.values()), "bytes": sum(v["bytes"] for v in phases.values()),
-           "count": max([v["count"] for v in phases.values()] or [0])}
-    cands = {k: v for k, v in units.items() if not k.startswith("eng_") and v["bytes"] > 0 and v["count"] > 0}
-    if agg["ms"] > 0 and agg["count"] > 0:
-        cands[eng_name] = agg
-    top = max(cands, key=lambda k: cands[k]["ms"]) if cands else None
     peak, peak_src = peaks()
-    roofline = None
-    if top:
-        v = cands[top]
-        ach = (v["bytes"] / v["count"]) / (v["ms"] / v["count"] * 1e-3) / 1e9
-        shares = {k: x["ms"] for k, x in units.items() if not k.startswith("eng_")}
-        shares[eng_name] = agg["ms"]
-        roofline = {"bound": "hbm", "kernel": top, "achieved": ach, "peak": peak, "unit": "GB/s",
-                    "frac": ach / peak, "traffic": None, "peak_source": peak_src,
-                    "bytes_per_launch": v["bytes"] / v["count"], "us_per_launch": 1000.0 * v["ms"] / v["count"],
-                    "share_of_device_time": v["ms"] / tot_prof_ms,
-                    "note": "for the persistent engine one 'launch' = one simplex iteration (all phases); "
-                            "phase_table splits it (SM-cycle stamps of CTA 0 between grid barriers)",
-                    "kernel_shares": {k: round(x / tot_prof_ms, 4) for k, x in sorted(shares.items(), key=lambda kv: -kv[1])[:8]},
-                    "phase_table": {k[4:]: {"us": round(1000.0 * x["ms"] / max(1, x["count"]), 3),
-                                            "GBps": round(x["bytes"] / max(1e-9, x["ms"]) / 1e6, 1)}
-                                    for k, x in sorted(phases.items())},
-                    "refactor_split_ms": {k[4:]: round(x["ms"], 2) for k, x in ref_split.items()}}
+    roofline = roofline_from_profile(prof, "k_engine_primal" if w["meth"] == "primal" else "k_engine_dual",
+                                     peak, peak_src, TRAFFIC_EVIDENCE.get(w["meth"]))
     P.close()
 
     # ---- e2e leg: host buffers every step ----
@@ -487,7 +535,9 @@ def main():
             v3 = prof3[top3]
             ach3 = v3["bytes"] / (v3["ms"] * 1e-3) / 1e9
             c3["roofline"] = {"bound": "hbm", "kernel": "k_engine_dual:" + top3[4:], "achieved": ach3, "peak": peak,
-                              "unit": "GB/s", "frac": ach3 / peak, "us_per_iteration": 1000.0 * v3["ms"] / v3["count"],
+                              "unit": "GB/s", "frac": ach3 / peak, "traffic": None,
+                              "traffic_evidence": TRAFFIC_EVIDENCE["dual"],
+                              "us_per_iteration": 1000.0 * v3["ms"] / v3["count"],
                               "bytes_per_iteration": v3["bytes"] / v3["count"],
                               "whole_engine": {"achieved": eng3_bytes / max(1e-9, eng3_ms) / 1e6, "unit": "GB/s",
                                                "frac": eng3_bytes / max(1e-9, eng3_ms) / 1e6 / peak,

@@ -113,6 +113,30 @@ static napi_value GetMip(napi_env env, napi_callback_info info)
                                      typed(env, a[3], &len), NULL));
 }
 
+/* scaleProb(m, n, Int32 A_ptr, Int32 A_ind, F64 A_val, flags, F64 rii[m], F64 sjj[n], F64 report[13])
+   -- glp_scale_prob (lib/glpscl.js) on flat arrays; host only */
+static napi_value ScaleProb(napi_env env, napi_callback_info info)
+{
+    size_t argc = 9, len; napi_value a[9]; int m, n, flags;
+    NAPI_OK(napi_get_cb_info(env, info, &argc, a, NULL, NULL));
+    NAPI_OK(napi_get_value_int32(env, a[0], &m)); NAPI_OK(napi_get_value_int32(env, a[1], &n));
+    NAPI_OK(napi_get_value_int32(env, a[5], &flags));
+    return ret_int(env, glpb_scale_prob(m, n, typed(env, a[2], &len), typed(env, a[3], &len), typed(env, a[4], &len),
+                                        flags, typed(env, a[6], &len), typed(env, a[7], &len), typed(env, a[8], &len)));
+}
+
+/* advBasis(m, n, Int32 A_ptr, Int32 A_ind, Int32 R_ptr, Int32 R_ind, Int32 type, F64 lb, F64 ub,
+            Int32 stat[m+n], Int32 size[1]) -- glp_adv_basis (lib/glpini01.js); host only */
+static napi_value AdvBasis(napi_env env, napi_callback_info info)
+{
+    size_t argc = 11, len; napi_value a[11]; int m, n;
+    NAPI_OK(napi_get_cb_info(env, info, &argc, a, NULL, NULL));
+    NAPI_OK(napi_get_value_int32(env, a[0], &m)); NAPI_OK(napi_get_value_int32(env, a[1], &n));
+    return ret_int(env, glpb_adv_basis(m, n, typed(env, a[2], &len), typed(env, a[3], &len), typed(env, a[4], &len),
+                                       typed(env, a[5], &len), typed(env, a[6], &len), typed(env, a[7], &len),
+                                       typed(env, a[8], &len), typed(env, a[9], &len), typed(env, a[10], &len)));
+}
+
 static napi_value Init(napi_env env, napi_value exports)
 {
     napi_property_descriptor d[] = {
@@ -120,6 +144,7 @@ static napi_value Init(napi_env env, napi_value exports)
         { "setBounds", 0, SetBounds, 0, 0, 0, napi_default, 0 }, { "simplex", 0, Simplex, 0, 0, 0, napi_default, 0 },
         { "intopt", 0, Intopt, 0, 0, 0, napi_default, 0 }, { "getSolution", 0, GetSolution, 0, 0, 0, napi_default, 0 },
         { "getMip", 0, GetMip, 0, 0, 0, napi_default, 0 },
+        { "scaleProb", 0, ScaleProb, 0, 0, 0, napi_default, 0 }, { "advBasis", 0, AdvBasis, 0, 0, 0, napi_default, 0 },
     };
     napi_define_properties(env, exports, sizeof d / sizeof d[0], d);
     return exports;

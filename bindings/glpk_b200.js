@@ -57,8 +57,36 @@ function pull(glp, P, d) {
     P.valid = 1;
 }
 
+/* rows of A in list order (row.ptr -> r_next), 0-based column indices */
+function rowsOf(P, m) {
+    const ptr = new Int32Array(m + 1), ind = [];
+    for (let i = 1; i <= m; i++) {
+        for (let a = P.row[i].ptr; a != null; a = a.r_next) ind.push(a.col.j - 1);
+        ptr[i] = ind.length;
+    }
+    return { ptr, ind: Int32Array.from(ind) };
+}
+
 exports.install = function (glp) {
     const simplex0 = glp.glp_simplex, intopt0 = glp.glp_intopt;
+    /* glp_scale_prob / glp_adv_basis (lib/glpscl.js, lib/glpini01.js): O(nnz) host work in the
+       native library instead of linked-list walks; same factors, same statuses */
+    glp.glp_scale_prob = function (P, flags) {
+        const d = marshal(glp, P), rep = new Float64Array(13);
+        if (addon.scaleProb(d.m, d.n, d.ptr, d.ind, d.val, flags | 0, d.rii, d.sjj, rep) !== 0)
+            throw new Error('glp_scale_prob: flags = ' + flags + '; invalid scaling options');
+        for (let i = 1; i <= d.m; i++) glp.glp_set_rii(P, i, d.rii[i - 1]);
+        for (let j = 1; j <= d.n; j++) glp.glp_set_sjj(P, j, d.sjj[j - 1]);
+    };
+    glp.glp_adv_basis = function (P, flags) {
+        if (flags) throw new Error('glp_adv_basis: flags = ' + flags + '; invalid flags');
+        const d = marshal(glp, P);
+        if (d.m === 0 || d.n === 0) return glp.glp_std_basis(P);
+        const r = rowsOf(P, d.m), stat = new Int32Array(d.m + d.n), size = new Int32Array(1);
+        addon.advBasis(d.m, d.n, d.ptr, d.ind, r.ptr, r.ind, d.type, d.lb, d.ub, stat, size);
+        for (let i = 1; i <= d.m; i++) glp.glp_set_row_stat(P, i, stat[i - 1]);
+        for (let j = 1; j <= d.n; j++) glp.glp_set_col_stat(P, j, stat[d.m + j - 1]);
+    };
     glp.glp_simplex = function (P, parm) {
         parm = parm || new glp.SMCP();
         if (parm.presolve) return simplex0(P, parm);      // the JS presolver calls back into solve_lp

@@ -175,6 +175,16 @@ struct glpb_prob {
     std::map<std::string, ProfAcc> prof_acc;
     std::string prof_text;
     glpb_mip *mip = nullptr;       /* branch-and-bound tree while glp_intopt runs */
+    /* ---- replayed launch sequences (small LPs: the node LPs of branch-and-bound).
+       The fresh recomputations of bbar / cbar and the start-of-solve block of the dual
+       loop are fixed sequences of 7-22 tiny kernels whose arguments never change for
+       a handle except the T/T2 flip; they are captured once into CUDA graphs and
+       replayed with one call (host launch cost, not arithmetic, is the node time). */
+    struct GraphSlot { cudaGraphExec_t exec = nullptr; const void *T = nullptr; double key = 0.0; int launches = 0; };
+    enum { GK_BBAR = 0, GK_CBAR = 1, GK_DSTART = 2, GK_KINDS = 3 };
+    GraphSlot graphs[GK_KINDS][2];
+    int graph_ok = 0, capturing = 0;
+    long n_graph = 0;
 };
 
 void glpb_set_error(const char *fmt, ...);

@@ -159,6 +159,8 @@ extern "C" void glpb_destroy(glpb_prob *P)
                     P->scratch, P->ctrl};
     for (void *p : ptrs) if (p) cudaFree(p);
     P->prof = 0; prof_collect(P);
+    for (auto &kind : P->graphs)
+        for (auto &g : kind) if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
     if (P->mip) { glpb_mip_free(P->mip); P->mip = nullptr; }
     if (P->h_ctrl) cudaFreeHost(P->h_ctrl);
     if (P->h_stage) cudaFreeHost(P->h_stage);
@@ -231,6 +233,12 @@ static int create_device(glpb_prob *P)
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_engine_dual, ENG_NT, P->eng_smem));
         if (occ < 1) { glpb_set_error("engine does not fit an SM"); return GLPB_ENODEV; }
         P->eng_ready = 1;
+    }
+    {
+        /* replayed launch sequences (Loop::graphed) for LPs small enough that launch cost,
+           not arithmetic, is the time of a recomputation; GLPB_GRAPH=0 turns them off */
+        const int want = getenv("GLPB_GRAPH") ? atoi(getenv("GLPB_GRAPH")) : 1;
+        P->graph_ok = (want && m <= 512 && n <= 8192) ? 1 : 0;
     }
     return 0;
 }
@@ -715,6 +723,49 @@ struct Loop : Dev {
 
     void clear_ctrl() { LAUNCH(P, k_clear_ctrl, 1, 1, 0, P->ctrl, phase); }
 
+    /* Run `body` (kernel launches only, no host decision inside) through a CUDA graph
+       captured on first use.  Grids are sized for the largest kernel (k = m): every kernel
+       takes the live k from the device control block, so one capture serves all bases.
+       The graph is keyed by the T pointer (the refactorisation flips T/T2) and one scalar. */
+    template <class F> void graphed(int kind, double key, F body)
+    {
+        if (!P->graph_ok || P->prof || P->capturing || P->trace) { body(); return; }
+        glpb_prob::GraphSlot *s = nullptr;
+        for (auto &g : P->graphs[kind]) if (g.exec && g.T == (const void *)P->T && g.key == key) s = &g;
+        if (!s) {
+            for (auto &g : P->graphs[kind]) if (!g.exec) { s = &g; break; }
+            if (!s) { s = &P->graphs[kind][0]; cudaGraphExecDestroy(s->exec); s->exec = nullptr; }
+            const int k_save = k, kpad_save = kpad;
+            const long l0 = P->n_launch;
+            cudaGraph_t g = nullptr;
+            k = m; kpad = 0;
+            P->capturing = 1;
+            cudaError_t e = cudaStreamBeginCapture(P->stream, cudaStreamCaptureModeThreadLocal);
+            if (e == cudaSuccess) {
+                body();
+                e = cudaStreamEndCapture(P->stream, &g);
+            }
+            P->capturing = 0;
+            k = k_save; kpad = kpad_save;
+            s->launches = (int)(P->n_launch - l0);
+            P->n_launch = l0;
+            if (e == cudaSuccess) e = cudaGraphInstantiate(&s->exec, g, 0);
+            if (g) cudaGraphDestroy(g);
+            if (e != cudaSuccess) {         /* no graphs on this handle: plain launches from now on */
+                cudaGetLastError();
+                s->exec = nullptr;
+                P->graph_ok = 0;
+                body();
+                return;
+            }
+            s->T = (const void *)P->T;
+            s->key = key;
+        }
+        if (cudaGraphLaunch(s->exec, P->stream) != cudaSuccess) { cudaGetLastError(); P->graph_ok = 0; body(); return; }
+        P->n_launch += s->launches;
+        P->n_graph++;
+    }
+
     /* vectors up to 64k entries are reduced by one block of 1024 threads (no
        second stage); longer ones by a multi-block two-stage reduction */
     int red_blocks(int len) const { return len <= 65536 ? 1 : grid1(len); }
@@ -828,7 +879,8 @@ struct Loop : Dev {
     }
 
     /* eval_bbar, lib/glpspx01.js:473-512,560-563 */
-    void eval_bbar()
+    void eval_bbar() { graphed(glpb_prob::GK_BBAR, 0.0, [&] { eval_bbar_launches(); }); }
+    void eval_bbar_launches()
     {
         GROUP_DISPATCH(gr, LAUNCH(P, k_beta_rhs<GG>, cdiv((long)m * GG, 256), 256, 0, P->ctrl, m, n, P->at_ptr,
                                   P->at_ind, P->at_val, P->head, P->bind, P->stat, P->lb, P->ub, P->w2));
@@ -840,7 +892,8 @@ struct Loop : Dev {
     }
 
     /* eval_cbar, lib/glpspx01.js:514-584 */
-    void eval_cbar()
+    void eval_cbar() { graphed(glpb_prob::GK_CBAR, 0.0, [&] { eval_cbar_launches(); }); }
+    void eval_cbar_launches()
     {
         LAUNCH(P, k_gather_cB, cdiv(m, 256), 256, 0, m, P->head, P->coef, P->w2);
         dev_btran(*this, P->w2, P->w3);
@@ -1189,16 +1242,18 @@ struct Dual : Loop {
                 /* start of a solve: phase decision, stability check, bbar and the objective
                    are enqueued as a whole (the device selects the bounds from its own
                    feasibility flag) and read back with ONE synchronisation */
-                clear_ctrl();
-                eval_cbar();
+                graphed(glpb_prob::GK_DSTART, parm.tol_dj, [&] {
+                    clear_ctrl();
+                    eval_cbar();
+                    LAUNCH(P, k_dual_check, cdiv(n, 256), 256, 0, P->ctrl, m, n, 1, P->head, P->orig_type, P->stat,
+                           P->cbar, 0.90 * parm.tol_dj, 0);
+                    set_bnds(-1);
+                    LAUNCH(P, k_dual_check, cdiv(n, 256), 256, 0, P->ctrl, m, n, 0, P->head, P->orig_type, P->stat,
+                           P->cbar, parm.tol_dj, 1);
+                    eval_bbar();
+                    eval_obj();
+                });
                 cbar_st = 1;
-                LAUNCH(P, k_dual_check, cdiv(n, 256), 256, 0, P->ctrl, m, n, 1, P->head, P->orig_type, P->stat,
-                       P->cbar, 0.90 * parm.tol_dj, 0);
-                set_bnds(-1);
-                LAUNCH(P, k_dual_check, cdiv(n, 256), 256, 0, P->ctrl, m, n, 0, P->head, P->orig_type, P->stat,
-                       P->cbar, parm.tol_dj, 1);
-                eval_bbar();
-                eval_obj();
                 if ((rc = sync_ctrl(P))) return rc;
                 phase = P->h_ctrl->flag ? 1 : 2;
                 refct = 0;
@@ -1524,9 +1579,9 @@ extern "C" int glpb_get_solution(glpb_prob *P, int *stat, double *prim, double *
 extern "C" int glpb_get_counters(glpb_prob *P, long *out, int count)
 {
     if (!P || !out) return GLPB_EINVAL;
-    long v[7] = {P->n_iter, P->n_refac, P->n_launch, P->n_sync, P->n_update,
-                 (long)(P->h_ctrl ? P->h_ctrl->k : 0), (long)P->last_solve_us};
-    for (int i = 0; i < count && i < 7; i++) out[i] = v[i];
+    long v[8] = {P->n_iter, P->n_refac, P->n_launch, P->n_sync, P->n_update,
+                 (long)(P->h_ctrl ? P->h_ctrl->k : 0), (long)P->last_solve_us, P->n_graph};
+    for (int i = 0; i < count && i < 8; i++) out[i] = v[i];
     return 0;
 }
 

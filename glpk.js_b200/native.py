@@ -370,9 +370,9 @@ class Problem:
         return self.L.glpb_mip_end(self.h, int(ret))
 
     def counters(self):
-        out = (C.c_long * 7)()
-        self.L.glpb_get_counters(self.h, out, 7)
-        keys = ["iterations", "refactorizations", "launches", "syncs", "updates", "k", "solve_us"]
+        out = (C.c_long * 8)()
+        self.L.glpb_get_counters(self.h, out, 8)
+        keys = ["iterations", "refactorizations", "launches", "syncs", "updates", "k", "solve_us", "graph_launches"]
         return {k: int(out[i]) for i, k in enumerate(keys)}
 
     def set_profile(self, on):

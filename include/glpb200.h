@@ -130,7 +130,9 @@ int glpb_mip_end(glpb_prob *P, int ret);
 
 /* Counters for measurement: out[0] iterations, [1] refactorisations,
  * [2] kernel launches, [3] host<->device syncs, [4] basis updates,
- * [5] current kernel size k, [6] device microseconds in the last solve. */
+ * [5] current kernel size k, [6] device microseconds in the last solve,
+ * [7] CUDA-graph replays (fixed launch sequences of small LPs; their kernels
+ * are counted in [2]). */
 int glpb_get_counters(glpb_prob *P, long *out, int count);
 
 /* Per-kernel device time, measured with CUDA events on the handle's stream
