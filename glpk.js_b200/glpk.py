@@ -587,6 +587,59 @@ def glp_mip_row_val(P, i): return _row(P, i, "glp_mip_row_val").mipx
 def glp_mip_col_val(P, j): return _col(P, j, "glp_mip_col_val").mipx
 
 
+def glp_get_obj_name(P): return P.obj
+def glp_get_row_type(P, i): return _row(P, i, "glp_get_row_type").type
+def glp_get_col_type(P, j): return _col(P, j, "glp_get_col_type").type
+
+
+def glp_get_row_lb(P, i):
+    """lib/glpapi02.js:36-52: -DBL_MAX when the row has no lower bound"""
+    r = _row(P, i, "glp_get_row_lb")
+    return -DBL_MAX if r.type in (GLP_FR, GLP_UP) else r.lb
+
+
+def glp_get_row_ub(P, i):
+    r = _row(P, i, "glp_get_row_ub")
+    return +DBL_MAX if r.type in (GLP_FR, GLP_LO) else r.ub
+
+
+def glp_get_col_lb(P, j):
+    c = _col(P, j, "glp_get_col_lb")
+    return -DBL_MAX if c.type in (GLP_FR, GLP_UP) else c.lb
+
+
+def glp_get_col_ub(P, j):
+    c = _col(P, j, "glp_get_col_ub")
+    return +DBL_MAX if c.type in (GLP_FR, GLP_LO) else c.ub
+
+
+def glp_get_obj_coef(P, j):
+    if not (0 <= j <= P.n):
+        xerror("glp_get_obj_coef: j = %d; column number out of range" % j)
+    return P.c0 if j == 0 else P.col[j].coef
+
+
+def glp_get_mat_row(P, i, ind=None, val=None):
+    """lib/glpapi02.js:127-140: fills ind[1..len] / val[1..len] in list order"""
+    r = _row(P, i, "glp_get_mat_row")
+    for t, (j, v) in enumerate(r.elems, 1):
+        if ind is not None:
+            ind[t] = j
+        if val is not None:
+            val[t] = v
+    return len(r.elems)
+
+
+def glp_get_mat_col(P, j, ind=None, val=None):
+    c = _col(P, j, "glp_get_mat_col")
+    for t, (i, v) in enumerate(c.elems, 1):
+        if ind is not None:
+            ind[t] = i
+        if val is not None:
+            val[t] = v
+    return len(c.elems)
+
+
 def glp_get_unbnd_ray(P):
     k = P.some
     return 0 if k > P.m + P.n else k
@@ -688,7 +741,7 @@ def glp_read_lp(P, parm, callback):
     parts = []
     while True:
         s = callback()
-        if not s:
+        if not s or s == -1:      # XEOF = -1 (lib/glpapi.js:21), what test/test.js returns
             break
         parts.append(s)
     return glp_read_lp_from_string(P, parm, "".join(parts))
@@ -872,6 +925,140 @@ def _read_lp(P, text):
 
 
 # ---- marshalling to the device handle ----
+def glp_write_lp(P, parm, callback):
+    """lib/glpcpx.js:755-998: CPLEX LP text, one ``callback(line)`` per line.
+    (The reference's adjust_name assigns into an immutable string and so changes
+    nothing: a name with a blank or a dash is replaced by r_i / x_j.)"""
+    _check(P, "glp_write_lp")
+
+    def valid(name):
+        if name is None or name == "" or name[0] == "." or name[0].isdigit():
+            return False
+        return all((ch.isalnum() and ch.isascii()) or ch in _NAME_EXTRA for ch in name)
+
+    def row_name(i):
+        name = P.obj if i == 0 else P.row[i].name
+        return name if valid(name) else ("obj" if i == 0 else "r_%d" % i)
+
+    def col_name(j):
+        name = P.col[j].name
+        return name if valid(name) else "x_%d" % j
+
+    count = [0]
+
+    def out(line):
+        callback(line)
+        count[0] += 1
+
+    def finish():
+        out("End")
+        xprintf("%d lines were written" % count[0])
+        return 0
+
+    class Line:
+        def __init__(self, text):
+            self.text = text
+
+        def add(self, term):
+            if len(self.text) + len(term) > 72:
+                out(self.text)
+                self.text = ""
+            self.text += term
+
+    def signed_term(v, name):
+        if v == +1.0:
+            return " + " + name
+        if v == -1.0:
+            return " - " + name
+        if v > 0.0:
+            return " + %s %s" % (_num(v), name)
+        return " - %s %s" % (_num(-v), name)
+
+    xprintf("Writing problem data")
+    out("\\* Problem: %s *\\" % ("Unknown" if P.name is None else P.name))
+    out("")
+    if not (P.m > 0 and P.n > 0):
+        xprintf("Warning: problem has no rows/columns")
+        out("\\* WARNING: PROBLEM HAS NO ROWS/COLUMNS *\\")
+        out("")
+        return finish()
+    out("Minimize" if P.dir == GLP_MIN else "Maximize")
+    line = Line(" " + row_name(0) + ":")
+    terms = 0
+    for j in range(1, P.n + 1):
+        col = P.col[j]
+        if col.coef != 0.0 or not col.elems:
+            terms += 1
+            line.add((" + 0 " + col_name(j)) if col.coef == 0.0 else signed_term(col.coef, col_name(j)))
+    if terms == 0:
+        line.text += " 0 " + col_name(1)
+    out(line.text)
+    if P.c0 != 0.0:
+        out("\\* constant term = %s *\\" % _num(P.c0))
+    out("")
+    out("Subject To")
+    for i in range(1, P.m + 1):
+        row = P.row[i]
+        if row.type == GLP_FR:
+            continue
+        line = Line(" " + row_name(i) + ":")
+        for (j, v) in row.elems:
+            line.add(signed_term(v, col_name(j)))
+        if row.type == GLP_DB:
+            line.add(" - ~r_%d" % i)
+        elif not row.elems:
+            line.text += " 0 " + col_name(1)
+        if row.type == GLP_LO:
+            line.add(" >= " + _num(row.lb))
+        elif row.type == GLP_UP:
+            line.add(" <= " + _num(row.ub))
+        else:
+            line.add(" = " + _num(row.lb))
+        out(line.text)
+    out("")
+    flag = False
+    for i in range(1, P.m + 1):
+        row = P.row[i]
+        if row.type != GLP_DB:
+            continue
+        if not flag:
+            out("Bounds")
+            flag = True
+        out(" 0 <= ~r_%d <= %s" % (i, _num(row.ub - row.lb)))
+    for j in range(1, P.n + 1):
+        col = P.col[j]
+        if col.type == GLP_LO and col.lb == 0.0:
+            continue
+        if not flag:
+            out("Bounds")
+            flag = True
+        name = col_name(j)
+        if col.type == GLP_FR:
+            out(" %s free" % name)
+        elif col.type == GLP_LO:
+            out(" %s >= %s" % (name, _num(col.lb)))
+        elif col.type == GLP_UP:
+            out(" -Inf <= %s <= %s" % (name, _num(col.ub)))
+        elif col.type == GLP_DB:
+            out(" %s <= %s <= %s" % (_num(col.lb), name, _num(col.ub)))
+        else:
+            out(" %s = %s" % (name, _num(col.lb)))
+    if flag:
+        callback("")
+    count[0] += 1
+    flag = False
+    for j in range(1, P.n + 1):
+        if P.col[j].kind == GLP_CV:
+            continue
+        if not flag:
+            out("Generals")
+            flag = True
+        out(" " + col_name(j))
+    if flag:
+        out("")
+    return finish()
+
+
 def _arrays(P):
     m, n = P.m, P.n
     type_ = np.zeros(m + n, np.int32)

@@ -364,3 +364,81 @@ def test_incorrect_bounds_and_parameter_checks():
     with pytest.raises(glpk.GlpkError):
         glpk.glp_intopt(P, bad)
     assert glpk._num(1e-7) == "1e-7" and glpk._num(2.5e+30) == "2.5e+30" and glpk._num(3.0) == "3"
+
+
+# ---- glp_write_lp (lib/glpcpx.js:755-998) and the reader, round trip
+def _same_problem(P, Q):
+    assert (P.m, P.n, P.nnz, P.dir) == (Q.m, Q.n, Q.nnz, Q.dir)
+    for i in range(1, P.m + 1):
+        a, b = P.row[i], Q.row[i]
+        assert a.type == b.type and glpk.glp_get_row_lb(P, i) == glpk.glp_get_row_lb(Q, i)
+        assert glpk.glp_get_row_ub(P, i) == glpk.glp_get_row_ub(Q, i)
+        assert sorted(a.elems) == sorted(b.elems)
+    for j in range(1, P.n + 1):
+        a, b = P.col[j], Q.col[j]
+        assert (a.type, a.kind, a.coef) == (b.type, b.kind, b.coef)
+        assert glpk.glp_get_col_lb(P, j) == glpk.glp_get_col_lb(Q, j)
+        assert glpk.glp_get_col_ub(P, j) == glpk.glp_get_col_ub(Q, j)
+
+
+@pytest.mark.parametrize("name", ["test", "gap", "todd"])
+def test_write_lp_round_trip_fixtures(name):
+    P = read_fixture(name)
+    lines = []
+    assert glpk.glp_write_lp(P, None, lines.append) == 0
+    assert lines[0] == "\\* Problem: Unknown *\\" and lines[-1] == "End"
+    assert all(len(s) <= 72 for s in lines)
+    Q = glpk.glp_create_prob()
+    # the reference's callback convention: one character per call, -1 at the end (test/test.js:36-43)
+    text, pos = "\n".join(lines) + "\n", [0]
+
+    def getc():
+        if pos[0] < len(text):
+            pos[0] += 1
+            return text[pos[0] - 1]
+        return -1
+
+    assert glpk.glp_read_lp(Q, None, getc) == 0
+    _same_problem(P, Q)
+    assert ([glpk.glp_get_col_name(Q, j) for j in range(1, Q.n + 1)] ==
+            [glpk.glp_get_col_name(P, j) for j in range(1, P.n + 1)])
+    again = []
+    glpk.glp_write_lp(Q, None, again.append)
+    assert again == lines                      # write(read(write(P))) is a fixed point
+
+
+def test_write_lp_round_trip_random_and_special_rows():
+    P = random_problem(41, m=12, n=15, density=0.3)
+    for i in range(1, P.m + 1):                # ranged rows become an extra column: tested below
+        if P.row[i].type in (glpk.GLP_DB, glpk.GLP_FR):
+            glpk.glp_set_row_bnds(P, i, glpk.GLP_UP, 0.0, 3.5)
+    glpk.glp_set_col_kind(P, 2, glpk.GLP_IV)
+    glpk.glp_set_col_name(P, 3, "has blank")   # invalid in LP format -> x_3
+    glpk.glp_set_obj_coef(P, 0, 12.5)
+    lines = []
+    glpk.glp_write_lp(P, None, lines.append)
+    assert "\\* constant term = 12.5 *\\" in lines and " x_2" in lines and "Generals" in lines
+    Q = glpk.glp_create_prob()
+    assert glpk.glp_read_lp_from_string(Q, None, "\n".join(lines)) == 0
+    # columns are numbered in order of first appearance when read back: compare by name
+    name_p = {("x_%d" % j): j for j in range(1, P.n + 1)}
+    assert Q.m == P.m and Q.n == P.n and Q.nnz == P.nnz
+    for jq in range(1, Q.n + 1):
+        jp = name_p[glpk.glp_get_col_name(Q, jq)]
+        a, b = P.col[jp], Q.col[jq]
+        assert (a.type, a.kind, a.coef) == (b.type, b.kind, b.coef)
+        assert glpk.glp_get_col_lb(P, jp) == glpk.glp_get_col_lb(Q, jq)
+        assert glpk.glp_get_col_ub(P, jp) == glpk.glp_get_col_ub(Q, jq)
+        assert sorted(a.elems) == sorted(b.elems)
+    # a ranged row -> "... - ~r_i = lb" plus "0 <= ~r_i <= ub - lb"; a free row is dropped
+    R = read_fixture("test")
+    glpk.glp_set_row_bnds(R, 1, glpk.GLP_DB, 10.0, 100.0)
+    glpk.glp_set_row_bnds(R, 3, glpk.GLP_FR, 0.0, 0.0)
+    lines = []
+    glpk.glp_write_lp(R, None, lines.append)
+    assert " p: + x1 + x2 + x3 - ~r_1 = 10" in lines and " 0 <= ~r_1 <= 90" in lines
+    assert not any(s.startswith(" r:") for s in lines)
+    E = glpk.glp_create_prob()
+    lines = []
+    glpk.glp_write_lp(E, None, lines.append)
+    assert lines == ["\\* Problem: Unknown *\\", "", "\\* WARNING: PROBLEM HAS NO ROWS/COLUMNS *\\", "", "End"]
