@@ -265,7 +265,7 @@ def run_bnb(args, w, rank, local_rank, world):
 
     sampler = ClockSampler(local_rank)
     times, nodes, objs = [], [], []
-    acct = {"launches": 0, "syncs": 0, "iterations": 0, "refactorizations": 0}
+    acct = {"launches": 0, "graph_launches": 0, "syncs": 0, "iterations": 0, "refactorizations": 0}
     for s in range(args.warmup + args.steps):
         probs = []
         for _ in range(W):                              # host buffers -> device every step (e2e == value here)
