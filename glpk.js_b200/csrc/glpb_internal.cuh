@@ -181,7 +181,7 @@ struct glpb_prob {
        a handle except the T/T2 flip; they are captured once into CUDA graphs and
        replayed with one call (host launch cost, not arithmetic, is the node time). */
     struct GraphSlot { cudaGraphExec_t exec = nullptr; const void *T = nullptr; double key = 0.0; int launches = 0; };
-    enum { GK_BBAR = 0, GK_CBAR = 1, GK_DSTART = 2, GK_KINDS = 3 };
+    enum { GK_BBAR = 0, GK_CBAR = 1, GK_DSTART = 2, GK_DFINAL = 3, GK_KINDS = 4 };
     GraphSlot graphs[GK_KINDS][2];
     int graph_ok = 0, capturing = 0;
     long n_graph = 0;

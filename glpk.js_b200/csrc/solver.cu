@@ -1220,6 +1220,9 @@ struct Dual : Loop {
         int rc, flag;
         const int pse = (parm.pricing == GLP_PT_PSE);
         double obj_track = 0.0;
+        /* GLPB_FINAL=0: the last round of a solve goes through the generic loop (two
+           synchronisations and one more engine launch) */
+        static const bool final_round = !(getenv("GLPB_FINAL") && atoi(getenv("GLPB_FINAL")) == 0);
         if ((rc = upload_bounds(P, true))) return rc;
         if ((rc = upload_basis(P))) return rc;
         k = P->k_host;
@@ -1383,6 +1386,43 @@ struct Dual : Loop {
                 binv_st = 0;
                 break;
             case ST_NONE1:
+                if (phase == 2 && bbar_st != 1 && cbar_st != 1 && final_round) {
+                    /* Nothing to price, but bbar and cbar are updated, not freshly computed
+                       vectors: the reference recomputes both and goes round its loop once more
+                       (lib/glpspx02.js:1660-1760,1802-1812).  That round -- eval_cbar, stability
+                       check, eval_bbar, objective, pricing -- is enqueued as a whole and read back
+                       with ONE synchronisation; the decisions below are taken in the loop's order. */
+                    graphed(glpb_prob::GK_DFINAL, parm.tol_dj, [&] {
+                        clear_ctrl();
+                        eval_cbar();
+                        LAUNCH(P, k_dual_check, cdiv(n, 256), 256, 0, P->ctrl, m, n, 0, P->head, P->orig_type,
+                               P->stat, P->cbar, parm.tol_dj, 0);
+                        eval_bbar();
+                        eval_obj();
+                    });
+                    P->next_bytes = 37.0 * m;
+                    LAUNCH(P, k_chuzr_dual, red_blocks(m), red_threads(m), 0, P->ctrl, m, P->type, P->lb, P->ub,
+                           P->head, P->bbar, P->gamma, parm.tol_bnd, 1, P->scratch);
+                    if ((rc = sync_ctrl(P))) return rc;
+                    bbar_st = cbar_st = 1;
+                    obj_track = P->h_ctrl->obj;
+                    if (P->h_ctrl->flag) {              /* dual feasibility lost: as at the top of the loop */
+                        if (parm.meth == GLP_DUALP) {
+                            rc = store_sol(P, GLP_UNDEF, GLP_UNDEF, 0, it_cnt);
+                            return rc ? rc : GLP_EFAIL;
+                        }
+                        phase = 0; binv_st = 0; rigorous = 5;
+                        break;
+                    }
+                    if (P->h_ctrl->status != ST_NONE1) break;   /* something to price after all */
+                    if ((P->zeta < 0.0 && parm.obj_ll > -DBL_MAX && obj_track <= parm.obj_ll) ||
+                        (P->zeta > 0.0 && parm.obj_ul < +DBL_MAX && obj_track >= parm.obj_ul)) {
+                        rc = store_sol(P, GLP_INFEAS, GLP_FEAS, 0, it_cnt);
+                        return rc ? rc : (P->zeta < 0.0 ? GLP_EOBJLL : GLP_EOBJUL);
+                    }
+                    if (it_limit() || tm_limit()) return stop_on_limit(it_limit() ? GLP_EITLIM : GLP_ETMLIM);
+                    return store_sol(P, GLP_FEAS, GLP_FEAS, 0, it_cnt);
+                }
                 if (bbar_st != 1 || cbar_st != 1) {
                     if (bbar_st != 1) bbar_st = 0;
                     if (cbar_st != 1) cbar_st = 0;
