@@ -635,10 +635,12 @@ static int upload_bounds(glpb_prob *P, bool dual)
 
 /* store_sol, lib/glpspx01.js:1591-1681: bring head/stat/bbar/cbar back and
    un-scale into the glp_prob fields the getters read */
-static int store_sol(glpb_prob *P, int p_stat, int d_stat, int ray, int it_cnt)
+/* read-back of store_sol enqueued ahead of a synchronisation the caller is about to make
+   anyway (speculative: the caller may find that the solve goes on and drop it) */
+static int store_sol_prefetch(glpb_prob *P)
 {
     const int m = P->m, n = P->n;
-    Stage S(P, 0);                /* the uploads of this solve completed long ago */
+    Stage S(P, 0);                /* same layout as store_sol */
     int *head = S.take<int>(m + n);
     double *bbar = S.take<double>(m), *cbar = S.take<double>(n);
     signed char *stat = S.take<signed char>(n);
@@ -646,8 +648,24 @@ static int store_sol(glpb_prob *P, int p_stat, int d_stat, int ray, int it_cnt)
     CK(cudaMemcpyAsync(stat, P->stat, n, cudaMemcpyDeviceToHost, P->stream));
     CK(cudaMemcpyAsync(bbar, P->bbar, m * sizeof(double), cudaMemcpyDeviceToHost, P->stream));
     CK(cudaMemcpyAsync(cbar, P->cbar, n * sizeof(double), cudaMemcpyDeviceToHost, P->stream));
-    CK(cudaStreamSynchronize(P->stream));
-    P->n_sync++;
+    return 0;
+}
+
+static int store_sol(glpb_prob *P, int p_stat, int d_stat, int ray, int it_cnt, bool prefetched = false)
+{
+    const int m = P->m, n = P->n;
+    Stage S(P, 0);                /* the uploads of this solve completed long ago */
+    int *head = S.take<int>(m + n);
+    double *bbar = S.take<double>(m), *cbar = S.take<double>(n);
+    signed char *stat = S.take<signed char>(n);
+    if (!prefetched) {
+        CK(cudaMemcpyAsync(head, P->head, (m + n) * sizeof(int), cudaMemcpyDeviceToHost, P->stream));
+        CK(cudaMemcpyAsync(stat, P->stat, n, cudaMemcpyDeviceToHost, P->stream));
+        CK(cudaMemcpyAsync(bbar, P->bbar, m * sizeof(double), cudaMemcpyDeviceToHost, P->stream));
+        CK(cudaMemcpyAsync(cbar, P->cbar, n * sizeof(double), cudaMemcpyDeviceToHost, P->stream));
+        CK(cudaStreamSynchronize(P->stream));
+        P->n_sync++;
+    }
     P->valid = 1;
     P->t_ok = 1;
     P->pbs_stat = p_stat; P->dbs_stat = d_stat;
@@ -1403,6 +1421,7 @@ struct Dual : Loop {
                     P->next_bytes = 37.0 * m;
                     LAUNCH(P, k_chuzr_dual, red_blocks(m), red_threads(m), 0, P->ctrl, m, P->type, P->lb, P->ub,
                            P->head, P->bbar, P->gamma, parm.tol_bnd, 1, P->scratch);
+                    if ((rc = store_sol_prefetch(P))) return rc;   /* the solution rides on the same sync */
                     if ((rc = sync_ctrl(P))) return rc;
                     bbar_st = cbar_st = 1;
                     obj_track = P->h_ctrl->obj;
@@ -1417,11 +1436,11 @@ struct Dual : Loop {
                     if (P->h_ctrl->status != ST_NONE1) break;   /* something to price after all */
                     if ((P->zeta < 0.0 && parm.obj_ll > -DBL_MAX && obj_track <= parm.obj_ll) ||
                         (P->zeta > 0.0 && parm.obj_ul < +DBL_MAX && obj_track >= parm.obj_ul)) {
-                        rc = store_sol(P, GLP_INFEAS, GLP_FEAS, 0, it_cnt);
+                        rc = store_sol(P, GLP_INFEAS, GLP_FEAS, 0, it_cnt, true);
                         return rc ? rc : (P->zeta < 0.0 ? GLP_EOBJLL : GLP_EOBJUL);
                     }
                     if (it_limit() || tm_limit()) return stop_on_limit(it_limit() ? GLP_EITLIM : GLP_ETMLIM);
-                    return store_sol(P, GLP_FEAS, GLP_FEAS, 0, it_cnt);
+                    return store_sol(P, GLP_FEAS, GLP_FEAS, 0, it_cnt, true);
                 }
                 if (bbar_st != 1 || cbar_st != 1) {
                     if (bbar_st != 1) bbar_st = 0;
