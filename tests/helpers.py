@@ -112,3 +112,58 @@ def basis_matrix(d, head):
         else:
             B[:, i] = -A[:, k - m - 1]
     return B
+
+
+# ---- randomised general LPs / small MIPs (shared by the GPU parity tests and the HiGHS pins) ----
+def random_lp(seed):
+    rng = np.random.default_rng(seed)
+    m, n = int(rng.integers(4, 36)), int(rng.integers(4, 48))
+    dens = rng.uniform(0.15, 0.6)
+    A = np.where(rng.random((m, n)) < dens, np.round(rng.uniform(-5, 5, (m, n)), 2), 0.0)
+    for j in range(n):                      # no empty columns
+        if not A[:, j].any():
+            A[rng.integers(0, m), j] = float(rng.integers(1, 5))
+    x0 = np.round(rng.uniform(-2, 4, n), 1)  # a point that most rows are built around
+    ax = A @ x0
+    rt = rng.choice([O.GLP_FR, O.GLP_LO, O.GLP_UP, O.GLP_DB, O.GLP_FX], size=m, p=[0.05, 0.3, 0.3, 0.2, 0.15])
+    slack = np.round(rng.uniform(0, 3, m), 1)
+    shift = np.where(rng.random(m) < 0.1, rng.uniform(-6, 6, m), 0.0)     # now and then infeasible
+    rl = np.where(np.isin(rt, (O.GLP_LO, O.GLP_DB, O.GLP_FX)), ax - slack + shift, 0.0)
+    ru = np.where(rt == O.GLP_UP, ax + slack + shift, np.where(rt == O.GLP_DB, rl + 2 * slack + 0.5, np.where(rt == O.GLP_FX, rl, 0.0)))
+    ct = rng.choice([O.GLP_FR, O.GLP_LO, O.GLP_UP, O.GLP_DB, O.GLP_FX], size=n, p=[0.1, 0.45, 0.1, 0.3, 0.05])
+    cl = np.where(np.isin(ct, (O.GLP_LO, O.GLP_DB, O.GLP_FX)), np.round(x0 - rng.uniform(0, 3, n), 1), 0.0)
+    cu = np.where(ct == O.GLP_UP, np.round(x0 + rng.uniform(0, 3, n), 1),
+                  np.where(ct == O.GLP_DB, cl + np.round(rng.uniform(0.5, 6, n), 1), np.where(ct == O.GLP_FX, cl, 0.0)))
+    coef = np.round(rng.uniform(-4, 4, n), 1)
+    ptr, ind, val = [0], [], []
+    for j in range(n):
+        nz = np.nonzero(A[:, j])[0]
+        ind.extend(nz.tolist())
+        val.extend(A[nz, j].tolist())
+        ptr.append(len(ind))
+    return dict(m=m, n=n, dir=int(rng.choice([O.GLP_MIN, O.GLP_MAX])), c0=float(np.round(rng.uniform(-3, 3), 1)),
+                r_type=rt.astype(np.int32), r_lb=rl, r_ub=ru, c_type=ct.astype(np.int32), c_lb=cl, c_ub=cu,
+                c_coef=coef, c_kind=np.full(n, O.GLP_CV, np.int32), A_ptr=np.array(ptr, np.int32),
+                A_ind=np.array(ind, np.int32), A_val=np.array(val, np.float64))
+
+
+def random_mip(seed):
+    """small bounded integer programs on top of random_lp: every column boxed, about
+    two thirds of them integer, integral bounds"""
+    rng = np.random.default_rng(5000 + seed)
+    d = random_lp(7000 + seed)
+    n = d["n"]
+    d["c_type"] = np.full(n, O.GLP_DB, np.int32)
+    lo = np.floor(rng.uniform(-3, 2, n))
+    d["c_lb"] = lo
+    d["c_ub"] = lo + rng.integers(1, 6, n).astype(float)
+    d["c_kind"] = np.where(rng.random(n) < 0.65, O.GLP_IV, O.GLP_CV).astype(np.int32)
+    # rows rebuilt around an integer point inside the boxes, so that the program is feasible
+    x0 = np.floor(rng.uniform(d["c_lb"], d["c_ub"] + 1.0 - 1e-9))
+    A = dense_A(dict(m=d["m"], n=n, A_ptr=d["A_ptr"], A_ind=d["A_ind"], A_val=d["A_val"]))
+    ax = A @ x0
+    slack = np.round(rng.uniform(0.5, 4, d["m"]), 1)
+    rt = d["r_type"]
+    d["r_lb"] = np.where(np.isin(rt, (O.GLP_LO, O.GLP_DB)), ax - slack, np.where(rt == O.GLP_FX, ax, 0.0))
+    d["r_ub"] = np.where(rt == O.GLP_UP, ax + slack, np.where(rt == O.GLP_DB, ax + slack, np.where(rt == O.GLP_FX, ax, 0.0)))
+    return d
