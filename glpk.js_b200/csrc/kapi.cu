@@ -234,6 +234,56 @@ extern "C" int glpb_bench_kernel(const char *name, int m, int n, int reps, doubl
         for (int r = 0; r < reps; r++) k_update_rank1<<<grid, UPD_TB>>>(ctrl, T, ld, tc, rh, sp, sr);
         cudaEventRecord(e1);
         *bytes = 16.0 * k * (double)k;
+    } else if (nm == "chuzr_dual") {
+        /* 37 B per row: head, then type/lb/ub gathered through it, bbar, gamma; m rows,
+           every basic variable a structural one of an n = m column problem */
+        const int copies = 4;
+        std::vector<signed char> ty(2 * (size_t)m);
+        std::vector<double> lo(2 * (size_t)m), hi(2 * (size_t)m), bb(m), ga(m);
+        std::vector<int> hd(m);
+        for (int i = 0; i < m; i++) {
+            hd[i] = m + (int)(((unsigned)i * 2654435761u) % (unsigned)m);      /* scattered gather */
+            bb[i] = ((i * 40503u) % 2001) / 1000.0 - 1.0; ga[i] = 1.0 + (i % 5);
+        }
+        for (size_t k = 0; k < 2 * (size_t)m; k++) { ty[k] = (signed char)(k % 3 == 0 ? GLP_DB : GLP_LO); lo[k] = -0.5; hi[k] = 0.5; }
+        std::vector<signed char *> dt(copies); std::vector<double *> dl(copies), du(copies), db(copies), dg(copies);
+        std::vector<int *> dh(copies);
+        for (int c = 0; c < copies; c++) {
+            dt[c] = t.up(ty.data(), ty.size()); dl[c] = t.up(lo.data(), lo.size()); du[c] = t.up(hi.data(), hi.size());
+            db[c] = t.up(bb.data(), m); dg[c] = t.up(ga.data(), m); dh[c] = t.up(hd.data(), m);
+        }
+        if (!t.ok) return GLPB_ENOMEM;
+        const int g = m <= 65536 ? 1 : grid1(m), th = m <= 65536 ? 1024 : 256;
+        for (int r = 0; r < 3; r++) k_chuzr_dual<<<g, th>>>(ctrl, m, dt[0], dl[0], du[0], dh[0], db[0], dg[0], 1e-7, 0, scr);
+        cudaEventRecord(e0);
+        for (int r = 0; r < reps; r++) { int c = r % copies; k_chuzr_dual<<<g, th>>>(ctrl, m, dt[c], dl[c], du[c], dh[c], db[c], dg[c], 1e-7, 0, scr); }
+        cudaEventRecord(e1);
+        *bytes = 37.0 * m;
+    } else if (nm == "trow") {
+        /* pivot-row SpMV over n non-basic structural columns of 16 non-zeros each
+           (the C3 shape), rows scattered; 12 B per non-zero + 13 n + 8 m */
+        const int per = 16, copies = 2;
+        const size_t nnz = (size_t)n * per;
+        if (m < per || nnz > 0x7fffffffu) { cudaEventDestroy(e0); cudaEventDestroy(e1); return GLPB_EINVAL; }
+        std::vector<int> ptr(n + 1), ind(nnz), hd((size_t)m + n);
+        std::vector<double> val(nnz), rho(m);
+        std::vector<signed char> st(n, (signed char)GLP_NL);
+        for (int j = 0; j <= n; j++) ptr[j] = j * per;
+        for (size_t e = 0; e < nnz; e++) { ind[e] = (int)((e * 2654435761ull + (e >> 4)) % (unsigned)m); val[e] = 0.1 + (e % 9) * 0.1; }
+        for (int i = 0; i < m; i++) { hd[i] = i; rho[i] = (i % 5 == 0) ? 0.0 : 1.0 / (1 + i % 7); }
+        for (int j = 0; j < n; j++) hd[(size_t)m + j] = m + j;
+        std::vector<int *> dp(copies), di(copies); std::vector<double *> dv(copies);
+        for (int c = 0; c < copies; c++) { dp[c] = t.up(ptr.data(), ptr.size()); di[c] = t.up(ind.data(), nnz); dv[c] = t.up(val.data(), nnz); }
+        int *dh = t.up(hd.data(), hd.size());
+        signed char *ds = t.up(st.data(), n);
+        double *dr = t.up(rho.data(), m), *dtr = t.zero<double>(n), *dsv = t.zero<double>(n);
+        if (!t.ok) return GLPB_ENOMEM;
+        const int g = (int)(((long)n * 8 + 255) / 256);
+        for (int r = 0; r < 3; r++) k_trow<8><<<g, 256>>>(ctrl, m, n, dp[0], di[0], dv[0], dh, ds, dr, nullptr, dtr, dsv, 1);
+        cudaEventRecord(e0);
+        for (int r = 0; r < reps; r++) { int c = r % copies; k_trow<8><<<g, 256>>>(ctrl, m, n, dp[c], di[c], dv[c], dh, ds, dr, nullptr, dtr, dsv, 1); }
+        cudaEventRecord(e1);
+        *bytes = 12.0 * (double)nnz + 13.0 * n + 8.0 * m;
     } else {
         cudaEventDestroy(e0); cudaEventDestroy(e1);
         return GLPB_EINVAL;
