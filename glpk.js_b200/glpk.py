@@ -1096,6 +1096,8 @@ def _device(P, device=0):
         P._dev = native.Problem(d, device=device, rii=rii, sjj=sjj)
         P._dirty = False
         P.valid = 0
+        if P.bfcp is not None:
+            _push_bfcp(P)
     else:
         k = np.arange(1, P.m + P.n + 1, dtype=np.int32)
         P._dev.set_bounds(k, d["type"], d["lb"], d["ub"])
@@ -1144,6 +1146,146 @@ def _check_smcp(parm):
     if parm.out_frq < 1: bad("out_frq")
     if parm.out_dly < 0: bad("out_dly")
     if parm.presolve not in (GLP_ON, GLP_OFF): bad("presolve")
+
+
+# ---- basis factorisation interface (lib/glpapi12.js:1-244) ----
+GLP_BF_FT, GLP_BF_BG, GLP_BF_GR = 1, 2, 3
+_BFCP_DEFAULTS = dict(type=GLP_BF_FT, lu_size=0, piv_tol=0.10, piv_lim=4, suhl=GLP_ON, eps_tol=1e-15,
+                      max_gro=1e+10, nfs_max=100, upd_tol=1e-6, nrs_max=100, rs_size=0)
+
+
+def glp_bf_exists(P):
+    """lib/glpapi12.js:1-3"""
+    return bool(P.m == 0 or P.valid)
+
+
+def glp_get_bfcp(P, parm):
+    """lib/glpapi12.js:108-126: fills the dict ``parm``"""
+    parm.update(_BFCP_DEFAULTS if P.bfcp is None else P.bfcp)
+
+
+def glp_set_bfcp(P, parm):
+    """lib/glpapi12.js:134-176.  The device keeps an explicit inverse of the
+    structural kernel of B, so of these only nfs_max (refactorisation period),
+    piv_tol and upd_tol reach it (glpb_set_bfcp); the rest is validated and kept."""
+    if parm is None:
+        P.bfcp = None
+    else:
+        bfcp = dict(_BFCP_DEFAULTS if P.bfcp is None else P.bfcp)
+        bfcp.update(parm)
+
+        def bad(name):
+            xerror("glp_set_bfcp: %s = %s; invalid parameter" % (name, _num(bfcp[name])))
+        if bfcp["type"] not in (GLP_BF_FT, GLP_BF_BG, GLP_BF_GR): bad("type")
+        if bfcp["lu_size"] < 0: bad("lu_size")
+        if not (0.0 < bfcp["piv_tol"] < 1.0): bad("piv_tol")
+        if bfcp["piv_lim"] < 1: bad("piv_lim")
+        if bfcp["suhl"] not in (GLP_ON, GLP_OFF): bad("suhl")
+        if not (0.0 <= bfcp["eps_tol"] <= 1e-6): bad("eps_tol")
+        if bfcp["max_gro"] < 1.0: bad("max_gro")
+        if not (1 <= bfcp["nfs_max"] <= 32767): bad("nfs_max")
+        if not (0.0 < bfcp["upd_tol"] < 1.0): bad("upd_tol")
+        if not (1 <= bfcp["nrs_max"] <= 32767): bad("nrs_max")
+        if bfcp["rs_size"] < 0: bad("rs_size")
+        if bfcp["rs_size"] == 0:
+            bfcp["rs_size"] = 20 * bfcp["nrs_max"]
+        P.bfcp = bfcp
+    if P._dev is not None:
+        _push_bfcp(P)
+
+
+def _push_bfcp(P):
+    b = _BFCP_DEFAULTS if P.bfcp is None else P.bfcp
+    P._dev.set_bfcp(nfs_max=int(b["nfs_max"]), piv_tol=float(b["piv_tol"]), upd_tol=float(b["upd_tol"]))
+
+
+def glp_factorize(P, device=0):
+    """lib/glpapi12.js:5-100: basis header from the statuses (basic variables in
+    the order k = 1..m+n), then the factorisation -- glpb_factorize on the handle."""
+    _check(P, "glp_factorize")
+    m, n = P.m, P.n
+    P.valid = 0
+    head = [0] * (1 + m)
+    j = 0
+    for k in range(1, m + n + 1):
+        x = P.row[k] if k <= m else P.col[k - m]
+        x.bind = 0
+        if x.stat == GLP_BS:
+            j += 1
+            if j > m:
+                return GLP_EBADB
+            head[j] = k
+            x.bind = j
+    if j < m:
+        return GLP_EBADB
+    P.head = head
+    if m > 0:
+        if n == 0 or P.nnz == 0:
+            xerror("glp_factorize: problems without constraint coefficients are handled by the host binding only")
+        dev = _device(P, device)
+        ret = dev.factorize()
+        if ret < 0:
+            xerror("glp_factorize: device error %d: %s" % (ret, native.last_error()))
+        if ret != 0:
+            return ret          # GLP_EBADB / GLP_ESING / GLP_ECOND
+        P.valid = 1
+    return 0
+
+
+def _need_bf(P, who):
+    if not (P.m == 0 or P.valid):
+        xerror("%s: basis factorization does not exist" % who)
+
+
+def glp_get_bhead(P, k):
+    _need_bf(P, "glp_get_bhead")
+    if not (1 <= k <= P.m):
+        xerror("glp_get_bhead: k = %d; index out of range" % k)
+    return P.head[k]
+
+
+def glp_get_row_bind(P, i):
+    _need_bf(P, "glp_get_row_bind")
+    return _row(P, i, "glp_get_row_bind").bind
+
+
+def glp_get_col_bind(P, j):
+    _need_bf(P, "glp_get_col_bind")
+    return _col(P, j, "glp_get_col_bind").bind
+
+
+def _basis_scale(P):
+    """SB of lib/glpapi12.js:178-220: 1/rii for a basic auxiliary variable, sjj for a
+    basic structural one, by basis position"""
+    m = P.m
+    return np.array([(1.0 / P.row[k].rii) if k <= m else P.col[k - m].sjj for k in P.head[1:m + 1]])
+
+
+def glp_ftran(P, x):
+    """lib/glpapi12.js:178-199: solves B x = b in place (x[1..m], slot 0 unused);
+    the scaled solve inv(R B SB) runs on the device (glpb_ftran)."""
+    _need_bf(P, "glp_ftran")
+    m = P.m
+    if m == 0:
+        return
+    rii = np.array([P.row[i].rii for i in range(1, m + 1)])
+    b = np.array([float(x[i]) for i in range(1, m + 1)]) * rii
+    y = P._dev.ftran(b) * _basis_scale(P)
+    for i in range(1, m + 1):
+        x[i] = float(y[i - 1])
+
+
+def glp_btran(P, x):
+    """lib/glpapi12.js:201-222: solves B' x = b in place"""
+    _need_bf(P, "glp_btran")
+    m = P.m
+    if m == 0:
+        return
+    rii = np.array([P.row[i].rii for i in range(1, m + 1)])
+    b = np.array([float(x[i]) for i in range(1, m + 1)]) * _basis_scale(P)
+    y = P._dev.btran(b) * rii
+    for i in range(1, m + 1):
+        x[i] = float(y[i - 1])
 
 
 def _plural(k, word):
@@ -1276,7 +1418,7 @@ def _clone(P):
         q.name, q.kind, q.type, q.lb, q.ub, q.coef = c.name, c.kind, c.type, c.lb, c.ub, c.coef
         q.elems = list(c.elems)
         Q.col.append(q)
-    Q.bfcp = P.bfcp
+    Q.bfcp = None if P.bfcp is None else dict(P.bfcp)   # inherited (lib/glpapi06.js:103-105)
     return Q
 
 

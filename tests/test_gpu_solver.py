@@ -214,3 +214,50 @@ def test_presolve_on_flow_of_test_js(name):
         iocp2.msg_lev = glpk.GLP_MSG_OFF
         assert glpk.glp_intopt(lp, iocp2) == 0
         assert glpk.glp_mip_obj_val(lp) == d["highs_mip_obj"]
+
+
+def test_facade_factorize_ftran_btran_in_unscaled_space():
+    """glp_factorize / glp_ftran / glp_btran (lib/glpapi12.js:5-222) on a SCALED problem:
+    the facade applies R and SB around the device's scaled solves, so B x = b and
+    B' y = b must hold for the unscaled basis matrix -- for the crash basis and for
+    the optimal basis the simplex leaves."""
+    lp = glpk.glp_create_prob()
+    assert glpk.glp_read_lp_from_string(lp, None, H.golden_text("gap")) == 0
+    glpk.glp_scale_prob(lp, glpk.GLP_SF_GM | glpk.GLP_SF_EQ)
+    glpk.glp_adv_basis(lp, 0)
+    arrays, _, _ = glpk._arrays(lp)
+    rng = np.random.default_rng(5)
+    m = lp.m
+
+    def check():
+        assert glpk.glp_bf_exists(lp)
+        head = [glpk.glp_get_bhead(lp, i) for i in range(1, m + 1)]
+        for i, k in enumerate(head, 1):
+            assert (glpk.glp_get_row_bind(lp, k) if k <= m else glpk.glp_get_col_bind(lp, k - m)) == i
+        B = H.basis_matrix(arrays, head)
+        b = rng.uniform(-2, 2, m)
+        x = [0.0] + b.tolist()
+        glpk.glp_ftran(lp, x)
+        np.testing.assert_allclose(B @ np.array(x[1:]), b, atol=1e-9)
+        y = [0.0] + b.tolist()
+        glpk.glp_btran(lp, y)
+        np.testing.assert_allclose(B.T @ np.array(y[1:]), b, atol=1e-9)
+
+    assert glpk.glp_factorize(lp) == 0
+    check()
+    parm = glpk.SMCP()
+    parm.msg_lev = glpk.GLP_MSG_OFF
+    assert glpk.glp_simplex(lp, parm) == 0 and glpk.glp_get_status(lp) == glpk.GLP_OPT
+    check()
+    # a singular basis: two identical structural columns cannot both be basic
+    sp = glpk.glp_create_prob()
+    glpk.glp_add_rows(sp, 2)
+    glpk.glp_add_cols(sp, 2)
+    for j in (1, 2):
+        glpk.glp_set_mat_col(sp, j, 2, [0, 1, 2], [0.0, 1.0, 2.0])
+        glpk.glp_set_col_bnds(sp, j, glpk.GLP_LO, 0.0, 0.0)
+        glpk.glp_set_col_stat(sp, j, glpk.GLP_BS)
+    for i in (1, 2):
+        glpk.glp_set_row_bnds(sp, i, glpk.GLP_UP, 0.0, 4.0)
+        glpk.glp_set_row_stat(sp, i, glpk.GLP_NU)
+    assert glpk.glp_factorize(sp) in (glpk.GLP_ESING, glpk.GLP_ECOND) and not glpk.glp_bf_exists(sp)

@@ -442,3 +442,31 @@ def test_write_lp_round_trip_random_and_special_rows():
     lines = []
     glpk.glp_write_lp(E, None, lines.append)
     assert lines == ["\\* Problem: Unknown *\\", "", "\\* WARNING: PROBLEM HAS NO ROWS/COLUMNS *\\", "", "End"]
+
+
+# ---- basis factorisation interface, host-side behaviour (lib/glpapi12.js:1-176)
+def test_factorize_host_checks_and_bfcp():
+    P = read_fixture("test")
+    assert not glpk.glp_bf_exists(P)
+    for who in (lambda: glpk.glp_get_bhead(P, 1), lambda: glpk.glp_get_row_bind(P, 1),
+                lambda: glpk.glp_ftran(P, [0.0] * 4), lambda: glpk.glp_btran(P, [0.0] * 4)):
+        with pytest.raises(glpk.GlpkError, match="basis factorization does not exist"):
+            who()
+    glpk.glp_set_col_stat(P, 1, glpk.GLP_BS)            # four basic variables for three rows
+    assert glpk.glp_factorize(P) == glpk.GLP_EBADB
+    for i in (1, 2):
+        glpk.glp_set_row_stat(P, i, glpk.GLP_NU)        # two basic variables
+    assert glpk.glp_factorize(P) == glpk.GLP_EBADB and P.valid == 0
+    parm = {}
+    glpk.glp_get_bfcp(P, parm)
+    assert parm["nfs_max"] == 100 and parm["piv_tol"] == 0.10 and parm["type"] == glpk.GLP_BF_FT
+    glpk.glp_set_bfcp(P, {"nfs_max": 50})
+    glpk.glp_get_bfcp(P, parm)
+    assert parm["nfs_max"] == 50 and parm["rs_size"] == 2000
+    with pytest.raises(glpk.GlpkError, match="nfs_max = 0; invalid parameter"):
+        glpk.glp_set_bfcp(P, {"nfs_max": 0})
+    with pytest.raises(glpk.GlpkError, match="piv_tol"):
+        glpk.glp_set_bfcp(P, {"piv_tol": 1.5})
+    glpk.glp_set_bfcp(P, None)
+    glpk.glp_get_bfcp(P, parm)
+    assert parm["nfs_max"] == 100
