@@ -10,6 +10,7 @@
  */
 #include <node_api.h>
 #include <stdlib.h>
+#include <string.h>
 #include "glpb200.h"
 
 #define NAPI_OK(call) do { if ((call) != napi_ok) { napi_throw_error(env, NULL, #call); return NULL; } } while (0)
@@ -137,6 +138,34 @@ static napi_value AdvBasis(napi_env env, napi_callback_info info)
                                        typed(env, a[8], &len), typed(env, a[9], &len), typed(env, a[10], &len)));
 }
 
+/* readLp(text) -> { m, n, dir, type, lb, ub, coef, kind, ptr, ind, val, names } -- glp_read_lp
+   (lib/glpcpx.js) on a string held in memory; throws the reader's message on a syntax error */
+static napi_value ReadLp(napi_env env, napi_callback_info info)
+{
+    size_t argc = 1, len = 0; napi_value a[1], r, v; glpb_problem_data d; char *names = NULL; long nlen = 0; void *p;
+    NAPI_OK(napi_get_cb_info(env, info, &argc, a, NULL, NULL));
+    NAPI_OK(napi_get_value_string_utf8(env, a[0], NULL, 0, &len));
+    char *text = (char *)malloc(len + 1);
+    NAPI_OK(napi_get_value_string_utf8(env, a[0], text, len + 1, &len));
+    int rc = glpb_read_lp(text, (long)len, &d, &names, &nlen);
+    free(text);
+    if (rc != 0) { napi_throw_error(env, NULL, glpb_last_error()); return NULL; }
+    NAPI_OK(napi_create_object(env, &r));
+#define PUT_INT(key, x) do { napi_create_int32(env, (x), &v); napi_set_named_property(env, r, key, v); } while (0)
+#define PUT_ARR(key, type, src, count, bytes) do { napi_value ab; napi_create_arraybuffer(env, (count) * (bytes), &p, &ab); \
+        memcpy(p, (src), (count) * (bytes)); napi_create_typedarray(env, type, (count), ab, 0, &v); \
+        napi_set_named_property(env, r, key, v); } while (0)
+    PUT_INT("m", d.m); PUT_INT("n", d.n); PUT_INT("dir", d.dir);
+    PUT_ARR("type", napi_int32_array, d.type, (size_t)(d.m + d.n), 4); PUT_ARR("lb", napi_float64_array, d.lb, (size_t)(d.m + d.n), 8);
+    PUT_ARR("ub", napi_float64_array, d.ub, (size_t)(d.m + d.n), 8); PUT_ARR("coef", napi_float64_array, d.coef, (size_t)d.n, 8);
+    PUT_ARR("kind", napi_int32_array, d.kind, (size_t)d.n, 4); PUT_ARR("ptr", napi_int32_array, d.A_ptr, (size_t)d.n + 1, 4);
+    PUT_ARR("ind", napi_int32_array, d.A_ind, (size_t)d.nnz, 4); PUT_ARR("val", napi_float64_array, d.A_val, (size_t)d.nnz, 8);
+    napi_create_string_utf8(env, names, (size_t)nlen, &v);       /* NUL-separated: obj, rows, columns */
+    napi_set_named_property(env, r, "names", v);
+    glpb_free_names(names); glpb_free_problem(&d);
+    return r;
+}
+
 static napi_value Init(napi_env env, napi_value exports)
 {
     napi_property_descriptor d[] = {
@@ -145,6 +174,7 @@ static napi_value Init(napi_env env, napi_value exports)
         { "intopt", 0, Intopt, 0, 0, 0, napi_default, 0 }, { "getSolution", 0, GetSolution, 0, 0, 0, napi_default, 0 },
         { "getMip", 0, GetMip, 0, 0, 0, napi_default, 0 },
         { "scaleProb", 0, ScaleProb, 0, 0, 0, napi_default, 0 }, { "advBasis", 0, AdvBasis, 0, 0, 0, napi_default, 0 },
+        { "readLp", 0, ReadLp, 0, 0, 0, napi_default, 0 },
     };
     napi_define_properties(env, exports, sizeof d / sizeof d[0], d);
     return exports;

@@ -73,7 +73,7 @@ SYMBOLS = [
     "glpb_btran", "glpb_k_chuzc_primal", "glpb_k_chuzr_dual", "glpb_k_ratio_primal",
     "glpb_k_ratio_dual", "glpb_k_trow", "glpb_bench_kernel", "glpb_gen_packing",
     "glpb_gen_covering", "glpb_gen_mkp", "glpb_free_problem", "glpb_rng_fill",
-    "glpb_scale_prob", "glpb_adv_basis",
+    "glpb_scale_prob", "glpb_adv_basis", "glpb_read_lp", "glpb_free_names",
 ]
 
 _lib = None
@@ -144,6 +144,8 @@ def load():
     L.glpb_rng_fill.argtypes = [ci, ci, vp]
     L.glpb_scale_prob.argtypes = [ci, ci, vp, vp, vp, ci, vp, vp, vp]
     L.glpb_adv_basis.argtypes = [ci, ci] + [vp] * 9
+    L.glpb_read_lp.argtypes = [C.c_char_p, C.c_long, vp, vp, vp]
+    L.glpb_free_names.argtypes = [vp]
     _lib = L
     return L
 
@@ -194,6 +196,35 @@ def generate(which, **kw):
              A_ind=arr(pd.A_ind, nnz, np.int32), A_val=arr(pd.A_val, nnz, np.float64))
     L.glpb_free_problem(C.byref(pd))
     return d
+
+
+def _problem_arrays(pd):
+    m, n, nnz = pd.m, pd.n, pd.nnz
+    arr = lambda p, k, dt: np.ctypeslib.as_array(p, shape=(max(k, 1),))[:k].astype(dt).copy()
+    return dict(m=m, n=n, nnz=nnz, dir=pd.dir, c0=pd.c0,
+                type=arr(pd.type, m + n, np.int32), lb=arr(pd.lb, m + n, np.float64),
+                ub=arr(pd.ub, m + n, np.float64), coef=arr(pd.coef, n, np.float64),
+                kind=arr(pd.kind, n, np.int32), A_ptr=arr(pd.A_ptr, n + 1, np.int32),
+                A_ind=arr(pd.A_ind, nnz, np.int32), A_val=arr(pd.A_val, nnz, np.float64))
+
+
+def read_lp(text):
+    """glpb_read_lp: CPLEX LP text -> (arrays in the layout glpb_create takes, names) where
+    names = dict(obj=..., rows=[...], cols=[...]).  Raises ValueError with the reader's
+    message (line number included) on a syntax error.  Host only."""
+    L = load()
+    raw = text.encode() if isinstance(text, str) else bytes(text)
+    pd = glpb_problem_data()
+    names, nlen = C.c_void_p(), C.c_long()
+    rc = L.glpb_read_lp(raw, len(raw), C.byref(pd), C.byref(names), C.byref(nlen))
+    if rc != 0:
+        raise ValueError(last_error() if rc == 1 else "glpb_read_lp failed (%d)" % rc)
+    d = _problem_arrays(pd)
+    blob = C.string_at(names, nlen.value).decode()
+    L.glpb_free_names(names)
+    L.glpb_free_problem(C.byref(pd))
+    parts = blob.split("\0")[:-1]
+    return d, dict(obj=parts[0], rows=parts[1:1 + d["m"]], cols=parts[1 + d["m"]:1 + d["m"] + d["n"]])
 
 
 def scale_prob(m, n, A_ptr, A_ind, A_val, flags):

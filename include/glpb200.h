@@ -227,6 +227,18 @@ int glpb_adv_basis(int m, int n, const int *A_ptr, const int *A_ind, const int *
                    const int *R_ind, const int *type, const double *lb, const double *ub,
                    int *stat, int *tri_size);
 
+/* glpb_read_lp replaces glp_read_lp (lib/glpcpx.js:10-753) for a text held in
+ * memory: CPLEX LP format -> the arrays glpb_create takes (columns with ascending
+ * row indices, i.e. the state after the reference's final glp_sort_matrix; rows
+ * and columns numbered in order of first appearance; c0 = 0).  names (optional)
+ * receives one malloc'ed block of NUL-terminated strings: the objective name, the
+ * m row names ("r.<i>" where the text gives none), the n column names; release it
+ * with glpb_free_names and the arrays with glpb_free_problem.  Returns 0, 1 on a
+ * syntax error (the reference's return value; text in glpb_last_error, with the
+ * line number), GLPB_EINVAL / GLPB_ENOMEM. */
+int glpb_read_lp(const char *text, long len, glpb_problem_data *out, char **names, long *names_len);
+void glpb_free_names(char *names);
+
 #ifdef __cplusplus
 }
 #endif

@@ -470,3 +470,102 @@ def test_factorize_host_checks_and_bfcp():
     glpk.glp_set_bfcp(P, None)
     glpk.glp_get_bfcp(P, parm)
     assert parm["nfs_max"] == 100
+
+
+# ---- native LP reader (glpb_read_lp, csrc/lpformat.cpp) against the facade's reader
+def _facade_arrays(text):
+    P = glpk.glp_create_prob()
+    assert glpk.glp_read_lp_from_string(P, None, text) == 0
+    d, _, _ = glpk._arrays(P)
+    names = dict(obj=P.obj, rows=[P.row[i].name for i in range(1, P.m + 1)],
+                 cols=[P.col[j].name for j in range(1, P.n + 1)])
+    return d, names
+
+
+def _same_arrays(a, b):
+    assert (a["m"], a["n"], a["dir"], a["c0"]) == (b["m"], b["n"], b["dir"], b["c0"])
+    for k in ("type", "lb", "ub", "coef", "kind", "A_ptr", "A_ind", "A_val"):
+        assert np.array_equal(np.asarray(a[k]), np.asarray(b[k])), k
+
+
+TRICKY_LP = """\\ a comment line
+MAXIMIZE
+ profit: 3 x + 2.5e0 y - z + 0 w
+Subject To
+ c1: x + y + z <= 10
+ - x + 2 y =< 1.5E+1       \\ trailing comment
+ c3: x - y => -4
+ end_like: 2 end + x = 3
+ x + .5 bin >= 0
+such that
+Bounds
+ -inf <= y <= 8
+ z free
+ -3 <= w <= 3
+ x <= 40
+ 1 <= end
+ 2 <= bin <= 2
+Generals
+ x z
+Binaries
+ b1 b2
+End
+"""
+
+
+def test_native_lp_reader_matches_the_facade_reader():
+    for name in ("test", "gap", "todd"):
+        text = H.golden_text(name)
+        d, names = nat.read_lp(text)
+        fd, fnames = _facade_arrays(text)
+        _same_arrays(d, fd)
+        assert names == fnames
+    # the "such that" on its own line is a second constraints keyword in the wrong place: a syntax error for both
+    bad = TRICKY_LP
+    P = glpk.glp_create_prob()
+    assert glpk.glp_read_lp_from_string(P, None, bad) == 1
+    with pytest.raises(ValueError, match="line 10: symbol such in wrong position"):
+        nat.read_lp(bad)
+    good = TRICKY_LP.replace("such that\n", "")
+    d, names = nat.read_lp(good)
+    fd, fnames = _facade_arrays(good)
+    _same_arrays(d, fd)
+    assert names == fnames
+    assert names["cols"] == ["x", "y", "z", "w", "end", "bin", "b1", "b2"] and names["rows"][1] == "r.2"
+    t = dict(zip(names["cols"], d["type"][d["m"]:].tolist()))
+    assert t == {"x": glpk.GLP_DB, "y": glpk.GLP_UP, "z": glpk.GLP_FR, "w": glpk.GLP_DB, "end": glpk.GLP_LO,
+                 "bin": glpk.GLP_FX, "b1": glpk.GLP_DB, "b2": glpk.GLP_DB}
+    assert d["kind"].tolist() == [2, 1, 2, 1, 1, 1, 2, 2] and d["dir"] == glpk.GLP_MAX
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_native_lp_reader_on_written_random_problems(seed):
+    P = random_problem(500 + seed, m=6 + 5 * seed, n=8 + 6 * seed, density=0.3, wide=(seed % 2 == 1))
+    glpk.glp_set_col_kind(P, 1, glpk.GLP_IV)
+    glpk.glp_set_obj_dir(P, glpk.GLP_MAX if seed % 2 else glpk.GLP_MIN)
+    lines = []
+    glpk.glp_write_lp(P, None, lines.append)
+    text = "\n".join(lines) + "\n"
+    d, names = nat.read_lp(text)
+    fd, fnames = _facade_arrays(text)
+    _same_arrays(d, fd)
+    assert names == fnames
+
+
+@pytest.mark.parametrize("text,what", [
+    ("x + y\nst\n c: x <= 1\nend\n", "keyword missing"),
+    ("min\n x\n", "constraints section missing"),
+    ("min\n x + x\nst\n c: x <= 1\nend\n", "multiple use"),
+    ("min\n x\nst\n c: x <= 1\n c: x >= 0\nend\n", "multiply defined"),
+    ("min\n x\nst\n c: x 1\nend\n", "missing constraint sense"),
+    ("min\n x\nst\n c: x <= y\nend\n", "missing right-hand side"),
+    ("min\n x\nst\n c: x <= 1\nbounds\n +inf <= x\nend\n", "invalid use of `\\+inf'"),
+    ("min\n x\nst\n c: x <= 1\nbounds\n 1 <= x >= 2\nend\n", "invalid bound definition"),
+    ("min\n x\nst\n c: x <= 1\nend\n extra\n", "beyond `end'"),
+    ("min\n x ^ 2\nst\n c: x <= 1\nend\n", "not recognized"),
+])
+def test_native_lp_reader_errors_like_the_facade(text, what):
+    P = glpk.glp_create_prob()
+    assert glpk.glp_read_lp_from_string(P, None, text) == 1
+    with pytest.raises(ValueError, match=what):
+        nat.read_lp(text)
