@@ -1553,6 +1553,59 @@ def glp_simplex(P, parm=None, device=0):
     return _preprocess_and_solve_lp(P, parm, device)
 
 
+# ---- user callback of the branch-and-cut driver (lib/glpapi13.js:1-7, glpios03.js:533-537) ----
+(GLP_IROWGEN, GLP_IBINGO, GLP_IHEUR, GLP_ICUTGEN, GLP_IBRANCH, GLP_ISELECT, GLP_IPREPRO) = range(1, 8)
+
+
+class _Tree:
+    """What a callback can reach through the two ios routines the reference exports
+    (``glp_ios_reason``, ``glp_ios_get_prob``)."""
+    __slots__ = ("reason", "mip")
+
+    def __init__(self, mip):
+        self.reason, self.mip = 0, mip
+
+
+def glp_ios_reason(tree):
+    return tree.reason
+
+
+def glp_ios_get_prob(tree):
+    return tree.mip
+
+
+def _run_mip_with_callbacks(P, parm, dev, ip):
+    """``cb_func != null``: the search runs on the device in slices of ONE node
+    (glpb_mip_begin / glpb_mip_run(1) / glpb_mip_end) and the host calls back between
+    slices, as SURVEY 8b prescribes.  Emulated reasons: GLP_ISELECT before a node is
+    picked and GLP_IBINGO when the incumbent improved (``glp_mip_obj_val`` of
+    ``glp_ios_get_prob(tree)`` then gives the new value, which is all the reference's
+    test/test.js does).  The other reasons (row/cut generation, heuristics, branching,
+    preprocessing requests) belong to features that are off on this path and are not
+    raised."""
+    rc = dev.mip_begin(ip)
+    if rc != 0:
+        return rc
+    tree = _Tree(P)
+    best = None
+    while True:
+        if dev.mip_open_count() > 0:
+            tree.reason = GLP_ISELECT
+            parm.cb_func(tree, parm.cb_info)
+            tree.reason = 0
+        state, _ = dev.mip_run(1)
+        has, obj = dev.mip_incumbent()
+        if has and (best is None or obj != best):
+            best = obj
+            P.mip_stat, P.mip_obj = GLP_FEAS, obj
+            tree.reason = GLP_IBINGO
+            parm.cb_func(tree, parm.cb_info)
+            tree.reason = 0
+        if state != 1:          # 0 = tree exhausted, GLP_E* = stopped; 1 = slice limit reached
+            break
+    return dev.mip_end(state)
+
+
 def _solve_mip(P, parm, device):
     """lib/glpapi09.js:62-114 -- the root LP must be optimal; the tree runs
     behind glpb_intopt on the handle that solved the relaxation."""
@@ -1574,7 +1627,7 @@ def _solve_mip(P, parm, device):
                   tol_int=parm.tol_int, tol_obj=parm.tol_obj, tm_lim=int(parm.tm_lim),
                   out_frq=parm.out_frq, out_dly=parm.out_dly, pp_tech=parm.pp_tech,
                   mip_gap=parm.mip_gap, presolve=GLP_OFF, node_lim=getattr(parm, "node_lim", -1))
-    ret = dev.intopt(ip)
+    ret = dev.intopt(ip) if parm.cb_func is None else _run_mip_with_callbacks(P, parm, dev, ip)
     mp = dev.mip()
     P.mip_stat, P.mip_obj = mp["mip_stat"], mp["mip_obj"]
     for i in range(1, P.m + 1):

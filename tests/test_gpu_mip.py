@@ -129,3 +129,27 @@ def test_node_sharding_emulated_ranks_same_optimum(world):
     assert holder is not None and probs[holder].mip()["mip_obj"] == 4190215.0
     assert sum(r["nodes"] > r["ramp_nodes"] for r in results) >= 2
     [P.close() for P in probs]
+
+
+def test_facade_intopt_with_user_callback():
+    """cb_func != null (what test/test.js passes): the search runs in one-node slices on the
+    device, the callback sees GLP_IBINGO with the improving incumbent; same optimum."""
+    lp = glpk.glp_create_prob()
+    assert glpk.glp_read_lp_from_string(lp, None, H.golden_text("gap")) == 0
+    smcp = glpk.SMCP()
+    smcp.msg_lev = glpk.GLP_MSG_OFF
+    assert glpk.glp_simplex(lp, smcp) == 0
+    bingo, selects = [], [0]
+
+    def cb(tree, info):
+        if glpk.glp_ios_reason(tree) == glpk.GLP_IBINGO:
+            bingo.append(glpk.glp_mip_obj_val(glpk.glp_ios_get_prob(tree)))
+        elif glpk.glp_ios_reason(tree) == glpk.GLP_ISELECT:
+            selects[0] += 1
+
+    iocp = glpk.IOCP({"cb_func": cb})
+    iocp.msg_lev = glpk.GLP_MSG_OFF
+    assert glpk.glp_intopt(lp, iocp) == 0
+    assert glpk.glp_mip_status(lp) == glpk.GLP_OPT and glpk.glp_mip_obj_val(lp) == 261.0
+    assert bingo and bingo[-1] == 261.0 and all(a > b for a, b in zip(bingo, bingo[1:]))   # minimisation
+    assert selects[0] >= len(bingo)

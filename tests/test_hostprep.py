@@ -569,3 +569,67 @@ def test_native_lp_reader_errors_like_the_facade(text, what):
     assert glpk.glp_read_lp_from_string(P, None, text) == 1
     with pytest.raises(ValueError, match=what):
         nat.read_lp(text)
+
+
+# ---- glp_intopt with a user callback: host-driven slices (no device: a scripted stand-in)
+class _ScriptedDevice:
+    """the slice interface of native.Problem, replaying a search of five nodes in which
+    the incumbent improves after nodes 2 and 4"""
+    m, n = 3, 3
+
+    def __init__(self):
+        self.node, self.log = 0, []
+        self.script = [(False, 0.0), (True, 700.0), (True, 700.0), (True, 720.0), (True, 720.0)]
+
+    def iocp(self, **kw):
+        return kw
+
+    def mip_begin(self, ip):
+        self.log.append("begin")
+        return 0
+
+    def mip_open_count(self):
+        return 5 - self.node
+
+    def mip_run(self, k):
+        assert k == 1
+        self.node += 1
+        return (1 if self.node < 5 else 0), 1
+
+    def mip_incumbent(self):
+        return self.script[self.node - 1]
+
+    def mip_end(self, ret):
+        self.log.append("end %d" % ret)
+        return ret
+
+    def intopt(self, ip):
+        raise AssertionError("one-call search must not be used when a callback is given")
+
+    def mip(self):
+        return dict(mip_stat=glpk.GLP_OPT, mip_obj=720.0, mipx=np.array([100.0, 600.0, 300.0, 30.0, 70.0, 0.0]), nodes=5)
+
+    def solution(self):
+        return dict(pbs=glpk.GLP_FEAS, dbs=glpk.GLP_FEAS, obj=733.0, it_cnt=9, some=0, head=np.array([4, 5, 3]),
+                    stat=np.array([3, 3, 1, 1, 1, 2]), prim=np.zeros(6), dual=np.zeros(6))
+
+
+def test_intopt_callback_slices():
+    P = read_fixture("test")
+    P._dev, P._dirty, P.valid = _ScriptedDevice(), False, 1
+    P.pbs_stat = P.dbs_stat = glpk.GLP_FEAS
+    seen = []
+
+    def cb(tree, info):
+        assert info == "ctx" and glpk.glp_ios_get_prob(tree) is P
+        seen.append((glpk.glp_ios_reason(tree), glpk.glp_mip_obj_val(glpk.glp_ios_get_prob(tree))))
+
+    parm = glpk.IOCP({"cb_func": cb, "cb_info": "ctx"})
+    parm.msg_lev = glpk.GLP_MSG_OFF
+    assert glpk.glp_intopt(P, parm) == 0
+    bingo = [(r, v) for r, v in seen if r == glpk.GLP_IBINGO]
+    assert bingo == [(glpk.GLP_IBINGO, 700.0), (glpk.GLP_IBINGO, 720.0)]
+    assert sum(1 for r, _ in seen if r == glpk.GLP_ISELECT) == 5
+    assert P._dev.log == ["begin", "end 0"]
+    assert glpk.glp_mip_status(P) == glpk.GLP_OPT and glpk.glp_mip_obj_val(P) == 720.0
+    assert glpk.glp_mip_col_val(P, 1) == 30.0
