@@ -722,14 +722,40 @@ def _tokenize(text):
 
 
 def glp_read_lp_from_string(P, parm, text):
-    """lib/glpcpx.js:1000-1010; returns 0 on success, 1 on a syntax error."""
+    """lib/glpcpx.js:1000-1010; returns 0 on success, 1 on a syntax error (the
+    problem object is then erased, :745-748).  The text is parsed by the native
+    reader (``glpb_read_lp``); ``_read_lp`` below is the same grammar in Python,
+    kept as its cross-check (tests/test_hostprep.py)."""
     _check(P, "glp_read_lp")
+    fresh = glp_prob()
+    P.__dict__.update(fresh.__dict__)
+    xprintf("Reading problem data")
     try:
-        _read_lp(P, text)
-    except GlpkError:
-        fresh = glp_prob()
-        P.__dict__.update(fresh.__dict__)
+        d, names = native.read_lp(text)
+    except ValueError as e:
+        xprintf(str(e))
         return 1
+    m, n = d["m"], d["n"]
+    P.dir, P.obj = d["dir"], names["obj"]
+    P.m, P.n, P.nnz = m, n, d["nnz"]
+    for i in range(1, m + 1):
+        r = _Row(i)
+        r.name, r.type, r.lb, r.ub = names["rows"][i - 1], int(d["type"][i - 1]), float(d["lb"][i - 1]), float(d["ub"][i - 1])
+        r.stat = GLP_BS
+        P.row.append(r)
+    ptr, ind, val = d["A_ptr"], d["A_ind"], d["A_val"]
+    for j in range(1, n + 1):
+        c = _Col(j)
+        k = m + j - 1
+        c.name = names["cols"][j - 1]
+        _set_bnds(c, "glp_set_col_bnds: j =", j, int(d["type"][k]), float(d["lb"][k]), float(d["ub"][k]))
+        c.coef, c.kind = float(d["coef"][j - 1]), int(d["kind"][j - 1])
+        for t in range(ptr[j - 1], ptr[j]):
+            i, v = int(ind[t]) + 1, float(val[t])
+            c.elems.append((i, v))            # ascending rows: the state after glp_sort_matrix
+            P.row[i].elems.append((j, v))     # columns arrive in ascending order too
+        P.col.append(c)
+    xprintf("%s" % _size_line(P))
     return 0
 
 

@@ -474,8 +474,17 @@ def test_factorize_host_checks_and_bfcp():
 
 # ---- native LP reader (glpb_read_lp, csrc/lpformat.cpp) against the facade's reader
 def _facade_arrays(text):
+    """the Python restatement of the reader (glpk._read_lp), the native reader's cross-check"""
     P = glpk.glp_create_prob()
-    assert glpk.glp_read_lp_from_string(P, None, text) == 0
+    glpk._read_lp(P, text)
+    Q = glpk.glp_create_prob()                     # and the facade entry point (native reader inside)
+    assert glpk.glp_read_lp_from_string(Q, None, text) == 0
+    _same_problem(P, Q)
+    assert [(r.name, r.stat) for r in P.row[1:]] == [(r.name, r.stat) for r in Q.row[1:]]
+    assert [(c.name, c.stat, c.lb, c.ub) for c in P.col[1:]] == [(c.name, c.stat, c.lb, c.ub) for c in Q.col[1:]]
+    assert [r.elems for r in P.row[1:]] == [r.elems for r in Q.row[1:]]
+    assert [c.elems for c in P.col[1:]] == [c.elems for c in Q.col[1:]]
+    assert P.obj == Q.obj and Q.valid == 0 and Q._dirty
     d, _, _ = glpk._arrays(P)
     names = dict(obj=P.obj, rows=[P.row[i].name for i in range(1, P.m + 1)],
                  cols=[P.col[j].name for j in range(1, P.n + 1)])
@@ -523,7 +532,15 @@ def test_native_lp_reader_matches_the_facade_reader():
     # the "such that" on its own line is a second constraints keyword in the wrong place: a syntax error for both
     bad = TRICKY_LP
     P = glpk.glp_create_prob()
-    assert glpk.glp_read_lp_from_string(P, None, bad) == 1
+    with pytest.raises(glpk.GlpkError):
+        glpk._read_lp(P, bad)
+    msgs = []
+    glpk.glp_set_print_func(msgs.append)
+    try:
+        assert glpk.glp_read_lp_from_string(P, None, bad) == 1 and P.m == 0 and P.n == 0
+    finally:
+        glpk.glp_set_print_func(None)
+    assert msgs == ["Reading problem data", "glp_read_lp: line 10: symbol such in wrong position"]
     with pytest.raises(ValueError, match="line 10: symbol such in wrong position"):
         nat.read_lp(bad)
     good = TRICKY_LP.replace("such that\n", "")
@@ -566,6 +583,8 @@ def test_native_lp_reader_on_written_random_problems(seed):
 ])
 def test_native_lp_reader_errors_like_the_facade(text, what):
     P = glpk.glp_create_prob()
+    with pytest.raises(glpk.GlpkError):
+        glpk._read_lp(P, text)
     assert glpk.glp_read_lp_from_string(P, None, text) == 1
     with pytest.raises(ValueError, match=what):
         nat.read_lp(text)
