@@ -234,21 +234,25 @@ def run_reference(args, w, rank, world):
     print(json.dumps(line), flush=True)
 
 
-def run_bnb(args, w, rank, local_rank, world):
+def run_bnb(args, w, rank, local_rank, world, embedded=False):
     """--workload mkp: branch-and-bound throughput (nodes/s).  A step = node_lim
     node LPs per rank (ios_solve_node: warm-started dual simplex + Driebeck-Tomlin
     branching); nodes are sharded across the ranks (glpk.js_b200/bnb.py: incumbent
     all-reduce + node migration over NCCL).  Weak scaling: the per-rank node budget
-    is fixed."""
+    is fixed.  embedded: called from the default run (process group and device already
+    set up); returns the line (rank 0) instead of printing it."""
     import torch
     import torch.distributed as dist
     import glpk_js_b200 as G
     from glpk_js_b200 import bnb
     nat = G.native
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    torch.cuda.set_device(local_rank)
+    if not embedded:
+        if world > 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        torch.cuda.set_device(local_rank)
+    n_steps = min(args.steps, 3) if embedded else args.steps
+    n_warm = min(args.warmup, 3) if embedded else args.warmup
     d = nat.generate(w["gen"], **w["kw"])
     node_lim = w["node_lim"]
     # worker threads (device handles) per GPU; every node costs host work (set-up, tree), so the
@@ -266,13 +270,13 @@ def run_bnb(args, w, rank, local_rank, world):
     sampler = ClockSampler(local_rank)
     times, nodes, objs = [], [], []
     acct = {"launches": 0, "graph_launches": 0, "syncs": 0, "iterations": 0, "refactorizations": 0}
-    for s in range(args.warmup + args.steps):
+    for s in range(n_warm + n_steps):
         probs = []
         for _ in range(W):                              # host buffers -> device every step (e2e == value here)
             P = nat.Problem(d, device=local_rank)
             assert P.simplex(meth=nat.GLP_PRIMAL) == 0  # root LP, as solve_mip requires (lib/glpapi09.js:67-72)
             probs.append(P)
-        if s == args.warmup:
+        if s == n_warm:
             sampler.start()
         group = bnb.LocalGroup(W)
         results = [None] * W
@@ -297,7 +301,7 @@ def run_bnb(args, w, rank, local_rank, world):
         c1 = [P.counters() for P in probs]
         for P in probs:
             P.close()
-        if s >= args.warmup:
+        if s >= n_warm:
             for key in acct:
                 acct[key] += sum(b[key] - a[key] for a, b in zip(c0, c1))
             times.append(dt)
@@ -342,8 +346,8 @@ def run_bnb(args, w, rank, local_rank, world):
         cpu = {"value": Q.mip()["nodes"] / dtc, "unit": "nodes/s", "cores": 1, "kind": "port",
                "sample": "%d nodes of the same search (node limit), C++ port of the reference, single thread" % Q.mip()["nodes"]}
     if rank == 0:
-        line = {"metric": "bnb_nodes_per_sec", "value": value, "unit": "nodes/s", "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": 1000.0 * my / args.steps, "higher_is_better": True,
+        line = {"metric": "bnb_nodes_per_sec", "value": value, "unit": "nodes/s", "n_gpus": world, "steps": n_steps,
+                "warmup": n_warm, "ms_per_step": 1000.0 * my / n_steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": w["name"], **w["kw"], "node_lim_per_worker": node_lim,
                            "workers_per_gpu": W,
@@ -352,9 +356,12 @@ def run_bnb(args, w, rank, local_rank, world):
                     a.nbytes for a in d.values() if isinstance(a, np.ndarray))), "d2h_bytes_per_step": 8 * (d["m"] + d["n"])},
                 "gpu_launches": int(acct["launches"]) * world, "roofline": roofline, "cpu_baseline": cpu,
                 "per_node": node_acct, "incumbent": objs[-1] if objs else None}
+        if embedded:
+            return line
         print(json.dumps(line), flush=True)
-    if world > 1:
+    if world > 1 and not embedded:
         dist.destroy_process_group()
+    return None
 
 
 def main():
@@ -367,6 +374,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-full", action="store_true", help="profile the whole solve, not its first 1500 iterations")
     ap.add_argument("--no-c3", action="store_true", help="skip the extra full solve of the 16384x32768 LP")
+    ap.add_argument("--no-bnb", action="store_true", help="skip the branch-and-bound block (nodes/s, C5) of the default line")
     ap.add_argument("--c3-mid", type=int, default=60000, help="iteration at which the C3 solve is split for the CPU sample")
     ap.add_argument("--c3-cpu-mid-lim", type=int, default=100)
     ap.add_argument("--bnb-workers", type=int, default=0,
@@ -562,6 +570,15 @@ def main():
                                   "after %d iterations (one refactorisation period, factorisation included)"
                                   % (itm, args.c3_mid)}
 
+    # ---- the multi-GPU part of BASELINE.json's metric: branch-and-bound nodes/s on C5 (configs[4]),
+    #      nodes sharded across all ranks of this run; same code as --workload mkp, fewer steps ----
+    bnb_block = None
+    if args.workload == "c2" and not args.no_bnb:
+        try:
+            bnb_block = run_bnb(args, WORKLOADS["mkp"], rank, local_rank, world, embedded=True)
+        except Exception as e:      # the headline line must not depend on the extra block
+            bnb_block = {"error": repr(e)}
+
     if rank == 0:
         line = {"metric": "simplex_iterations_per_sec", "value": value, "unit": "iter/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": max_ms / args.steps,
@@ -577,7 +594,7 @@ def main():
                 "iterations_per_step": tot_it / args.steps, "time_to_optimal_ms": max_ms / args.steps,
                 "status": int(status), "objective": obj, "wall_s_timed_region": t_wall,
                 "refactorizations": cnt["refactorizations"], "kernel_size_k": cnt["k"],
-                "north_star_c3": c3}
+                "north_star_c3": c3, "bnb": bnb_block}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
