@@ -281,11 +281,20 @@ def run_bnb(args, w, rank, local_rank, world, embedded=False):
         group = bnb.LocalGroup(W)
         results = [None] * W
 
+        errors = []
+
         def work(r):
-            torch.cuda.set_device(local_rank)
-            comm = bnb.HybridComm(group, r, outer)
-            results[r] = bnb.sharded_intopt(bnb.Worker(probs[r]), comm, minimize=(d["dir"] == nat.GLP_MIN),
-                                            node_lim=node_lim, msg_lev=0)
+            try:
+                torch.cuda.set_device(local_rank)
+                comm = bnb.HybridComm(group, r, outer)
+                results[r] = bnb.sharded_intopt(bnb.Worker(probs[r]), comm, minimize=(d["dir"] == nat.GLP_MIN),
+                                                node_lim=node_lim, msg_lev=0)
+            except BaseException as e:       # a dead worker must not leave the others waiting at the barrier
+                errors.append(e)
+                try:
+                    group.barrier.abort()
+                except Exception:
+                    pass
 
         barrier()
         c0 = [P.counters() for P in probs]
@@ -296,6 +305,10 @@ def run_bnb(args, w, rank, local_rank, world, embedded=False):
         work(0)
         for t in threads:
             t.join()
+        if errors:
+            for P in probs:
+                P.close()
+            raise RuntimeError("branch-and-bound worker failed: %r" % (errors[0],))
         barrier()
         dt = time.perf_counter() - t0
         c1 = [P.counters() for P in probs]

@@ -189,3 +189,16 @@ def test_default_line_carries_the_bnb_block(stubbed, monkeypatch):
     monkeypatch.setattr(G.bnb, "sharded_intopt", lambda *a, **k: (_ for _ in ()).throw(RuntimeError("boom")))
     d = run(["--bnb-workers", "1"])
     assert "boom" in d["bnb"]["error"] and d["value"] > 0
+
+
+def test_bnb_leg_worker_failure_is_raised_not_hung(stubbed, monkeypatch):
+    """a worker thread that dies aborts the group's barrier and the leg raises in the main thread"""
+    def search(worker, comm, minimize, node_lim=None, **kw):
+        if comm.lr == 1:
+            raise RuntimeError("worker 1 died")
+        comm.g.barrier.wait(timeout=20)          # what the real driver does between slices
+        return dict(total_nodes=node_lim, obj=0.0)
+
+    monkeypatch.setattr(G.bnb, "sharded_intopt", search)
+    with pytest.raises(RuntimeError, match="worker failed"):
+        stubbed.run_bnb(_args(steps=1, warmup=0, bnb_workers=3), stubbed.WORKLOADS["mkp"], 0, 0, 1, embedded=True)
