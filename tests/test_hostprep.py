@@ -652,3 +652,38 @@ def test_intopt_callback_slices():
     assert P._dev.log == ["begin", "end 0"]
     assert glpk.glp_mip_status(P) == glpk.GLP_OPT and glpk.glp_mip_obj_val(P) == 720.0
     assert glpk.glp_mip_col_val(P, 1) == 30.0
+
+
+# ---- the prepared inputs are good inputs: oracle solves from the product's scale factors and
+# ---- crash basis reach the HiGHS-pinned optimum on the random LPs of the GPU tests
+def test_scaled_crash_started_oracle_solves_reach_the_pins():
+    import json
+    import ctypes as C
+    import oracle_lib as O
+    with open(os.path.join(H.GOLDEN, "random_pins.json")) as f:
+        pins = [p for p in json.load(f)["lp"] if p["highs"] == "optimal"]
+    assert len(pins) >= 15
+    for pin in pins:
+        d = H.random_lp(pin["seed"])
+        m, n = d["m"], d["n"]
+        rii, sjj, rep = nat.scale_prob(m, n, d["A_ptr"], d["A_ind"], d["A_val"],
+                                       nat.GLP_SF_GM | nat.GLP_SF_EQ | nat.GLP_SF_2N)
+        # rows of A (ascending columns) for the crash basis
+        cols = np.repeat(np.arange(n), np.diff(d["A_ptr"])).astype(np.int32)
+        order = np.argsort(d["A_ind"], kind="stable")
+        R_ptr = np.zeros(m + 1, np.int32)
+        np.cumsum(np.bincount(d["A_ind"], minlength=m), out=R_ptr[1:])
+        dn = H.to_native(d)
+        stat, size = nat.adv_basis(m, n, d["A_ptr"], d["A_ind"], R_ptr, cols[order], dn["type"], dn["lb"], dn["ub"])
+        assert int((stat == nat.GLP_BS).sum()) == m and 0 < size <= m
+        for meth in (O.GLP_PRIMAL, O.GLP_DUALP):
+            Q = O.Problem.from_arrays(d)
+            Q.L.glpo_set_scale.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+            Q.L.glpo_set_scale(Q.h, rii.ctypes.data_as(C.c_void_p), sjj.ctypes.data_as(C.c_void_p))
+            Q.set_stat(stat)
+            assert Q.simplex(meth=meth) == 0, (pin["seed"], meth)
+            s = Q.solution()
+            assert s["status"] == O.GLP_OPT
+            assert abs(s["obj"] - pin["obj"]) <= 1e-9 * max(1.0, abs(pin["obj"])), (pin["seed"], s["obj"], pin["obj"])
+            r = H.kkt(dn, s)                  # un-scaled solution against the ORIGINAL problem
+            assert max(r.values()) <= 1e-9, (pin["seed"], r)
