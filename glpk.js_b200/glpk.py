@@ -138,6 +138,7 @@ class glp_prob:
         self.it_cnt = self.some = 0
         self.mip_stat, self.mip_obj = GLP_UNDEF, 0.0
         self.bfcp = None
+        self.r_tree = self.c_tree = None   # name indices (glp_create_index)
         self._dev = None       # native.Problem
         self._dirty = True     # matrix / costs changed since the handle was built
 
@@ -189,15 +190,29 @@ def glp_add_cols(P, ncs):
 
 
 def glp_set_row_name(P, i, name):
+    """lib/glpapi01.js:60-84 (the name index, when it exists, follows the change)"""
     if not (1 <= i <= P.m):
         xerror("glp_set_row_name: i = %d; row number out of range" % i)
-    P.row[i].name = name
+    row = P.row[i]
+    r_tree = getattr(P, "r_tree", None)
+    if row.name is not None and r_tree is not None:
+        r_tree.pop(row.name, None)
+    row.name = name
+    if name is not None and r_tree is not None:
+        r_tree[name] = row
 
 
 def glp_set_col_name(P, j, name):
+    """lib/glpapi01.js:86-110"""
     if not (1 <= j <= P.n):
         xerror("glp_set_col_name: j = %d; column number out of range" % j)
-    P.col[j].name = name
+    col = P.col[j]
+    c_tree = getattr(P, "c_tree", None)
+    if col.name is not None and c_tree is not None:
+        c_tree.pop(col.name, None)
+    col.name = name
+    if name is not None and c_tree is not None:
+        c_tree[name] = col
 
 
 def _set_bnds(x, who, idx, type, lb, ub):
@@ -414,6 +429,182 @@ def glp_std_basis(P):
             glp_set_col_stat(P, j, GLP_NU)
         else:
             glp_set_col_stat(P, j, GLP_NL)
+
+
+# ---- problem-object housekeeping (lib/glpapi01.js:559-618,651-860, lib/glpapi03.js, lib/glpapi.js:76) ----
+def glp_version():
+    return "4.49"
+
+
+def glp_check_dup(m, n, ne, ia, ja):
+    """lib/glpapi01.js:559-618: 0 = no duplicates, -k = ia[k]/ja[k] out of range,
+    +k = element k duplicates an earlier one (1-based triplets)"""
+    if m < 0:
+        xerror("glp_check_dup: m = %d; invalid parameter" % m)
+    if n < 0:
+        xerror("glp_check_dup: n = %d; invalid parameter" % n)
+    if ne < 0:
+        xerror("glp_check_dup: ne = %d; invalid parameter" % ne)
+    if ne > 0 and ia is None:
+        xerror("glp_check_dup: ia = %r; invalid parameter" % (ia,))
+    if ne > 0 and ja is None:
+        xerror("glp_check_dup: ja = %r; invalid parameter" % (ja,))
+    for k in range(1, ne + 1):
+        if not (1 <= ia[k] <= m and 1 <= ja[k] <= n):
+            return -k
+    if m == 0 or n == 0:
+        return 0
+    # the reference walks the rows in order, each row's elements from the last to the first,
+    # and reports the SECOND occurrence (in input order) of the first pair it meets twice
+    by_row = {}
+    for k in range(1, ne + 1):
+        by_row.setdefault(ia[k], []).append(k)
+    for i in sorted(by_row):
+        seen = set()
+        for k in reversed(by_row[i]):
+            j = ja[k]
+            if j in seen:
+                hits = [t for t in by_row[i] if ja[t] == j]
+                return hits[1]
+            seen.add(j)
+    return 0
+
+
+def glp_create_index(P):
+    """lib/glpapi03.js:1-25"""
+    if getattr(P, "r_tree", None) is None:
+        P.r_tree = {r.name: r for r in P.row[1:] if r.name is not None}
+    if getattr(P, "c_tree", None) is None:
+        P.c_tree = {c.name: c for c in P.col[1:] if c.name is not None}
+
+
+def glp_find_row(P, name):
+    if getattr(P, "r_tree", None) is None:
+        xerror("glp_find_row: row name index does not exist")
+    row = P.r_tree.get(name)
+    return row.i if row is not None else 0
+
+
+def glp_find_col(P, name):
+    if getattr(P, "c_tree", None) is None:
+        xerror("glp_find_col: column name index does not exist")
+    col = P.c_tree.get(name)
+    return col.j if col is not None else 0
+
+
+def glp_delete_index(P):
+    """lib/glpapi03.js:45-48 -- as written there only the ROW index goes
+    (``lp.r_tree = null`` twice); the column index survives."""
+    P.r_tree = None
+
+
+def glp_del_rows(P, nrs, num):
+    """lib/glpapi01.js:651-703 (num[1..nrs]); remaining rows are renumbered"""
+    if not (1 <= nrs <= P.m):
+        xerror("glp_del_rows: nrs = %d; invalid number of rows" % nrs)
+    for k in range(1, nrs + 1):
+        i = num[k]
+        if not (1 <= i <= P.m):
+            xerror("glp_del_rows: num[%d] = %d; row number out of range" % (k, i))
+        row = P.row[i]
+        if row.i == 0:
+            xerror("glp_del_rows: num[%d] = %d; duplicate row numbers not allowed" % (k, i))
+        glp_set_row_name(P, i, None)
+        glp_set_mat_row(P, i, 0, None, None)
+        row.i = 0
+    remap, kept = {}, [None]
+    for i in range(1, P.m + 1):
+        row = P.row[i]
+        if row.i != 0:
+            kept.append(row)
+            remap[i] = row.i = len(kept) - 1
+    P.row, P.m = kept, len(kept) - 1
+    for col in P.col[1:]:
+        col.elems = [(remap[i], v) for (i, v) in col.elems]
+    P.head = P.head[:P.m + 1]
+    P.valid = 0
+    P._dirty = True
+
+
+def glp_del_cols(P, ncs, num):
+    """lib/glpapi01.js:705-761"""
+    if not (1 <= ncs <= P.n):
+        xerror("glp_del_cols: ncs = %d; invalid number of columns" % ncs)
+    for k in range(1, ncs + 1):
+        j = num[k]
+        if not (1 <= j <= P.n):
+            xerror("glp_del_cols: num[%d] = %d; column number out of range" % (k, j))
+        col = P.col[j]
+        if col.j == 0:
+            xerror("glp_del_cols: num[%d] = %d; duplicate column numbers not allowed" % (k, j))
+        glp_set_col_name(P, j, None)
+        glp_set_mat_col(P, j, 0, None, None)
+        col.j = 0
+        if col.stat == GLP_BS:
+            P.valid = 0
+    remap, kept = {}, [None]
+    for j in range(1, P.n + 1):
+        col = P.col[j]
+        if col.j != 0:
+            kept.append(col)
+            remap[j] = col.j = len(kept) - 1
+    P.col, P.n = kept, len(kept) - 1
+    for row in P.row[1:]:
+        row.elems = [(remap[j], v) for (j, v) in row.elems]
+    if P.valid:
+        for j in range(1, P.n + 1):
+            k = P.col[j].bind
+            if k != 0:
+                P.head[k] = P.m + j
+    P._dirty = True
+
+
+def glp_erase_prob(P):
+    """lib/glpapi01.js:836-842: back to the state glp_create_prob leaves"""
+    _check(P, "glp_erase_prob")
+    _drop_device(P)
+    fresh = glp_prob()
+    P.__dict__.clear()
+    P.__dict__.update(fresh.__dict__)
+
+
+def glp_copy_prob(dest, prob, names):
+    """lib/glpapi01.js:763-834.  Columns are copied through glp_set_mat_col, so the
+    copy's lists are in the order that call leaves (each list reversed)."""
+    _check(dest, "glp_copy_prob")
+    _check(prob, "glp_copy_prob")
+    if dest is prob:
+        xerror("glp_copy_prob: copying problem object to itself not allowed")
+    if names not in (GLP_ON, GLP_OFF):
+        xerror("glp_copy_prob: names = %r; invalid parameter" % (names,))
+    glp_erase_prob(dest)
+    if names and prob.name is not None:
+        glp_set_prob_name(dest, prob.name)
+    if names and prob.obj is not None:
+        glp_set_obj_name(dest, prob.obj)
+    dest.dir, dest.c0 = prob.dir, prob.c0
+    if prob.m > 0:
+        glp_add_rows(dest, prob.m)
+    if prob.n > 0:
+        glp_add_cols(dest, prob.n)
+    dest.bfcp = None if prob.bfcp is None else dict(prob.bfcp)
+    dest.pbs_stat, dest.dbs_stat, dest.obj_val, dest.some = prob.pbs_stat, prob.dbs_stat, prob.obj_val, prob.some
+    dest.mip_stat, dest.mip_obj = prob.mip_stat, prob.mip_obj
+    for i in range(1, prob.m + 1):
+        to, src = dest.row[i], prob.row[i]
+        if names and src.name is not None:
+            glp_set_row_name(dest, i, src.name)
+        to.type, to.lb, to.ub, to.rii = src.type, src.lb, src.ub, src.rii
+        to.stat, to.prim, to.dual, to.mipx = src.stat, src.prim, src.dual, src.mipx
+    for j in range(1, prob.n + 1):
+        to, src = dest.col[j], prob.col[j]
+        if names and src.name is not None:
+            glp_set_col_name(dest, j, src.name)
+        to.kind, to.type, to.lb, to.ub, to.coef = src.kind, src.type, src.lb, src.ub, src.coef
+        ln = len(src.elems)
+        glp_set_mat_col(dest, j, ln, [0] + [i for (i, _) in src.elems], [0.0] + [v for (_, v) in src.elems])
+        to.sjj = src.sjj
+        to.stat, to.prim, to.dual, to.mipx = src.stat, src.prim, src.dual, src.mipx
 
 
 # ---- scale factors, scaling, crash basis (lib/glpapi04.js, glpscl.js, glpini01.js) ----

@@ -687,3 +687,90 @@ def test_scaled_crash_started_oracle_solves_reach_the_pins():
             assert abs(s["obj"] - pin["obj"]) <= 1e-9 * max(1.0, abs(pin["obj"])), (pin["seed"], s["obj"], pin["obj"])
             r = H.kkt(dn, s)                  # un-scaled solution against the ORIGINAL problem
             assert max(r.values()) <= 1e-9, (pin["seed"], r)
+
+
+# ---- problem-object housekeeping (lib/glpapi01.js, lib/glpapi03.js)
+def test_check_dup_and_name_index():
+    ia, ja = [0, 1, 2, 2, 1, 2], [0, 1, 3, 2, 1, 3]
+    assert glpk.glp_check_dup(2, 3, 3, ia, ja) == 0
+    assert glpk.glp_check_dup(2, 3, 4, ia, ja) == 4          # (1,1) again at k = 4
+    assert glpk.glp_check_dup(2, 3, 5, ia, ja) == 4          # row 1 is examined first
+    assert glpk.glp_check_dup(2, 2, 3, ia, ja) == -2         # column 3 out of range
+    assert glpk.glp_check_dup(0, 0, 0, None, None) == 0
+    with pytest.raises(glpk.GlpkError):
+        glpk.glp_check_dup(-1, 0, 0, None, None)
+    assert glpk.glp_version() == "4.49"
+    P = read_fixture("test")
+    with pytest.raises(glpk.GlpkError, match="row name index does not exist"):
+        glpk.glp_find_row(P, "p")
+    glpk.glp_create_index(P)
+    assert glpk.glp_find_row(P, "q") == 2 and glpk.glp_find_col(P, "x3") == 3 and glpk.glp_find_col(P, "nope") == 0
+    glpk.glp_set_col_name(P, 3, "z")                         # the index follows a rename
+    assert glpk.glp_find_col(P, "x3") == 0 and glpk.glp_find_col(P, "z") == 3
+    glpk.glp_delete_index(P)
+    with pytest.raises(glpk.GlpkError):
+        glpk.glp_find_row(P, "p")
+    assert glpk.glp_find_col(P, "z") == 3                    # the reference only drops the row index
+
+
+def test_del_rows_del_cols_renumber_consistently():
+    P = read_fixture("gap")
+    m, n, nnz = P.m, P.n, P.nnz
+    dense = np.zeros((m + 1, n + 1))
+    for j in range(1, n + 1):
+        for (i, v) in P.col[j].elems:
+            dense[i, j] = v
+    names_r = [None] + [P.row[i].name for i in range(1, m + 1)]
+    names_c = [None] + [P.col[j].name for j in range(1, n + 1)]
+    glpk.glp_create_index(P)
+    P.valid = 1
+    glpk.glp_del_rows(P, 2, [0, 3, 7])
+    keep_r = [i for i in range(1, m + 1) if i not in (3, 7)]
+    assert P.m == m - 2 and P.valid == 0 and [P.row[t].name for t in range(1, P.m + 1)] == [names_r[i] for i in keep_r]
+    assert glpk.glp_find_row(P, names_r[3]) == 0 and glpk.glp_find_row(P, names_r[8]) == 6
+    glpk.glp_del_cols(P, 3, [0, 1, 10, n])
+    keep_c = [j for j in range(1, n + 1) if j not in (1, 10, n)]
+    assert P.n == n - 3 and [P.col[t].name for t in range(1, P.n + 1)] == [names_c[j] for j in keep_c]
+    # both copies of the matrix describe the remaining sub-matrix, with the new numbers
+    got = np.zeros((P.m + 1, P.n + 1))
+    for j in range(1, P.n + 1):
+        assert P.col[j].j == j
+        for (i, v) in P.col[j].elems:
+            got[i, j] = v
+    got_r = np.zeros_like(got)
+    for i in range(1, P.m + 1):
+        assert P.row[i].i == i
+        for (j, v) in P.row[i].elems:
+            got_r[i, j] = v
+    want = dense[np.ix_([0] + keep_r, [0] + keep_c)]
+    assert np.array_equal(got, want) and np.array_equal(got_r, want)
+    assert P.nnz == int(np.count_nonzero(want)) and P._dirty
+    with pytest.raises(glpk.GlpkError, match="duplicate row numbers"):
+        glpk.glp_del_rows(P, 2, [0, 2, 2])
+    with pytest.raises(glpk.GlpkError, match="out of range"):
+        glpk.glp_del_cols(P, 1, [0, 999])
+
+
+def test_copy_and_erase_prob():
+    P = read_fixture("gap")
+    glpk.glp_scale_prob(P, glpk.GLP_SF_EQ)
+    glpk.glp_set_bfcp(P, {"nfs_max": 77})
+    Q = glpk.glp_create_prob()
+    glpk.glp_copy_prob(Q, P, glpk.GLP_ON)
+    _same_problem(P, Q)
+    assert [c.name for c in Q.col[1:]] == [c.name for c in P.col[1:]] and Q.obj == P.obj
+    assert [r.rii for r in Q.row[1:]] == [r.rii for r in P.row[1:]] and [c.sjj for c in Q.col[1:]] == [c.sjj for c in P.col[1:]]
+    assert [c.kind for c in Q.col[1:]] == [c.kind for c in P.col[1:]]
+    assert Q.col[1].elems == list(reversed(P.col[1].elems))   # glp_set_mat_col prepends
+    parm = {}
+    glpk.glp_get_bfcp(Q, parm)
+    assert parm["nfs_max"] == 77
+    R = glpk.glp_create_prob()
+    glpk.glp_copy_prob(R, P, glpk.GLP_OFF)
+    assert all(c.name is None for c in R.col[1:]) and R.obj is None
+    with pytest.raises(glpk.GlpkError, match="itself"):
+        glpk.glp_copy_prob(P, P, glpk.GLP_ON)
+    glpk.glp_erase_prob(Q)
+    assert (Q.m, Q.n, Q.nnz, Q.dir, Q.c0) == (0, 0, 0, glpk.GLP_MIN, 0.0) and Q.row == [None] and Q._dev is None
+    glpk.glp_add_rows(Q, 1)                                   # still a usable problem object
+    assert Q.m == 1
