@@ -1505,6 +1505,280 @@ def glp_btran(P, x):
         x[i] = float(y[i - 1])
 
 
+def glp_warm_up(P, device=0):
+    """lib/glpapi12.js:244-398: primal and dual values of the CURRENT basis, without
+    iterating: x_B = -inv(B) N x_N, pi = inv(B') c_B, d_N = c_N - N' pi; the two solves
+    are glp_ftran / glp_btran on the device's factorisation."""
+    _check(P, "glp_warm_up")
+    m, n = P.m, P.n
+    P.pbs_stat = P.dbs_stat = GLP_UNDEF
+    P.obj_val, P.some = 0.0, 0
+    for x in P.row[1:] + P.col[1:]:
+        x.prim = x.dual = 0.0
+    if not glp_bf_exists(P):
+        ret = glp_factorize(P, device)
+        if ret != 0:
+            return ret
+    work = [0.0] * (1 + m)
+    for i in range(1, m + 1):
+        row = P.row[i]
+        if row.stat == GLP_BS:
+            continue
+        row.prim = _bound_value(row)
+        work[i] -= row.prim
+    for j in range(1, n + 1):
+        col = P.col[j]
+        if col.stat == GLP_BS:
+            continue
+        col.prim = _bound_value(col)
+        if col.prim != 0.0:
+            for (i, v) in col.elems:
+                work[i] += v * col.prim
+    glp_ftran(P, work)
+    P.pbs_stat = GLP_FEAS
+    for x in P.row[1:] + P.col[1:]:
+        if x.stat != GLP_BS:
+            continue
+        x.prim = work[x.bind]
+        if x.type in (GLP_LO, GLP_DB, GLP_FX) and x.prim < x.lb - (1e-6 + 1e-9 * abs(x.lb)):
+            P.pbs_stat = GLP_INFEAS
+        if x.type in (GLP_UP, GLP_DB, GLP_FX) and x.prim > x.ub + (1e-6 + 1e-9 * abs(x.ub)):
+            P.pbs_stat = GLP_INFEAS
+    P.obj_val = P.c0
+    for col in P.col[1:]:
+        P.obj_val += col.coef * col.prim
+    work = [0.0] * (1 + m)
+    for col in P.col[1:]:
+        if col.stat == GLP_BS:
+            work[col.bind] = col.coef
+    glp_btran(P, work)
+    P.dbs_stat = GLP_FEAS
+
+    def dual_ok(x):
+        temp = +x.dual if P.dir == GLP_MIN else -x.dual
+        if (x.stat in (GLP_NF, GLP_NL) and temp < -1e-5) or (x.stat in (GLP_NF, GLP_NU) and temp > +1e-5):
+            P.dbs_stat = GLP_INFEAS
+
+    for i in range(1, m + 1):
+        row = P.row[i]
+        if row.stat == GLP_BS:
+            row.dual = 0.0
+            continue
+        row.dual = -work[i]
+        dual_ok(row)
+    for col in P.col[1:]:
+        if col.stat == GLP_BS:
+            col.dual = 0.0
+            continue
+        col.dual = col.coef
+        for (i, v) in col.elems:
+            col.dual += v * work[i]
+        dual_ok(col)
+    return 0
+
+
+def glp_eval_tab_row(P, k, ind, val):
+    """lib/glpapi12.js:401-453: row of the simplex table of basic x[k] (ind/val 1-based out)"""
+    m, n = P.m, P.n
+    _need_bf(P, "glp_eval_tab_row")
+    if not (1 <= k <= m + n):
+        xerror("glp_eval_tab_row: k = %d; variable number out of range" % k)
+    i = glp_get_row_bind(P, k) if k <= m else glp_get_col_bind(P, k - m)
+    if i == 0:
+        xerror("glp_eval_tab_row: k = %d; variable must be basic" % k)
+    rho = [0.0] * (1 + m)
+    rho[i] = 1.0
+    glp_btran(P, rho)
+    ln = 0
+    for kk in range(1, m + n + 1):
+        if kk <= m:
+            if P.row[kk].stat == GLP_BS:
+                continue
+            alfa = -rho[kk]
+        else:
+            col = P.col[kk - m]
+            if col.stat == GLP_BS:
+                continue
+            alfa = 0.0
+            for (r, v) in col.elems:
+                alfa += rho[r] * v
+        if alfa != 0.0:
+            ln += 1
+            ind[ln], val[ln] = kk, alfa
+    return ln
+
+
+def glp_eval_tab_col(P, k, ind, val):
+    """lib/glpapi12.js:455-497: column of the simplex table of non-basic x[k]"""
+    m, n = P.m, P.n
+    _need_bf(P, "glp_eval_tab_col")
+    if not (1 <= k <= m + n):
+        xerror("glp_eval_tab_col: k = %d; variable number out of range" % k)
+    stat = P.row[k].stat if k <= m else P.col[k - m].stat
+    if stat == GLP_BS:
+        xerror("glp_eval_tab_col: k = %d; variable must be non-basic" % k)
+    col = [0.0] * (1 + m)
+    if k <= m:
+        col[k] = -1.0
+    else:
+        for (r, v) in P.col[k - m].elems:
+            col[r] = v
+    glp_ftran(P, col)
+    ln = 0
+    for t in range(1, m + 1):
+        if col[t] != 0.0:
+            ln += 1
+            ind[ln], val[ln] = P.head[t], col[t]
+    return ln
+
+
+def glp_transform_row(P, length, ind, val):
+    """lib/glpapi12.js:499-556: an explicit row sum a_j x_j expressed in the non-basic variables"""
+    _need_bf(P, "glp_transform_row")
+    m, n = P.m, P.n
+    if not (0 <= length <= n):
+        xerror("glp_transform_row: len = %d; invalid row length" % length)
+    a = [0.0] * (1 + n)
+    for t in range(1, length + 1):
+        j = ind[t]
+        if not (1 <= j <= n):
+            xerror("glp_transform_row: ind[%d] = %d; column index out of range" % (t, j))
+        if val[t] == 0.0:
+            xerror("glp_transform_row: val[%d] = 0; zero coefficient not allowed" % t)
+        if a[j] != 0.0:
+            xerror("glp_transform_row: ind[%d] = %d; duplicate column indices not allowed" % (t, j))
+        a[j] = val[t]
+    rho = [0.0] * (1 + m)
+    for i in range(1, m + 1):
+        k = P.head[i]
+        rho[i] = 0.0 if k <= m else a[k - m]
+    glp_btran(P, rho)
+    ln = 0
+    for i in range(1, m + 1):
+        if P.row[i].stat != GLP_BS:
+            alfa = -rho[i]
+            if alfa != 0.0:
+                ln += 1
+                ind[ln], val[ln] = i, alfa
+    for j in range(1, n + 1):
+        col = P.col[j]
+        if col.stat != GLP_BS:
+            alfa = a[j]
+            for (r, v) in col.elems:
+                alfa += v * rho[r]
+            if alfa != 0.0:
+                ln += 1
+                ind[ln], val[ln] = m + j, alfa
+    return ln
+
+
+def glp_transform_col(P, length, ind, val):
+    """lib/glpapi12.js:558-591: an explicit column expressed in the basic variables"""
+    _need_bf(P, "glp_transform_col")
+    m = P.m
+    if not (0 <= length <= m):
+        xerror("glp_transform_col: len = %d; invalid column length" % length)
+    a = [0.0] * (1 + m)
+    for t in range(1, length + 1):
+        i = ind[t]
+        if not (1 <= i <= m):
+            xerror("glp_transform_col: ind[%d] = %d; row index out of range" % (t, i))
+        if val[t] == 0.0:
+            xerror("glp_transform_col: val[%d] = 0; zero coefficient not allowed" % t)
+        if a[i] != 0.0:
+            xerror("glp_transform_col: ind[%d] = %d; duplicate row indices not allowed" % (t, i))
+        a[i] = val[t]
+    glp_ftran(P, a)
+    ln = 0
+    for i in range(1, m + 1):
+        if a[i] != 0.0:
+            ln += 1
+            ind[ln], val[ln] = P.head[i], a[i]
+    return ln
+
+
+def _var(P, k):
+    return P.row[k] if k <= P.m else P.col[k - P.m]
+
+
+def glp_prim_rtest(P, length, ind, val, dir, eps):
+    """lib/glpapi12.js:593-685: textbook primal ratio test over an explicit column;
+    returns the position t of the pivot in ind/val or 0"""
+    if glp_get_prim_stat(P) != GLP_FEAS:
+        xerror("glp_prim_rtest: basic solution is not primal feasible ")
+    if dir not in (+1, -1):
+        xerror("glp_prim_rtest: dir = %r; invalid parameter" % (dir,))
+    if not (0.0 < eps < 1.0):
+        xerror("glp_prim_rtest: eps = %s; invalid parameter" % _num(eps))
+    piv, teta, big = 0, DBL_MAX, 0.0
+    for t in range(1, length + 1):
+        k = ind[t]
+        if not (1 <= k <= P.m + P.n):
+            xerror("glp_prim_rtest: ind[%d] = %d; variable number out of range" % (t, k))
+        x = _var(P, k)
+        if x.stat != GLP_BS:
+            xerror("glp_prim_rtest: ind[%d] = %d; non-basic variable not allowed" % (t, k))
+        alfa = +val[t] if dir > 0 else -val[t]
+        if x.type == GLP_FR:
+            continue
+        elif x.type == GLP_LO or (x.type == GLP_DB and alfa < 0.0):
+            if alfa > -eps:
+                continue
+            temp = (x.lb - x.prim) / alfa
+        elif x.type == GLP_UP or x.type == GLP_DB:
+            if alfa < +eps:
+                continue
+            temp = (x.ub - x.prim) / alfa
+        else:
+            if -eps < alfa < +eps:
+                continue
+            temp = 0.0
+        if temp < 0.0:
+            temp = 0.0
+        if teta > temp or (teta == temp and big < abs(alfa)):
+            piv, teta, big = t, temp, abs(alfa)
+    return piv
+
+
+def glp_dual_rtest(P, length, ind, val, dir, eps):
+    """lib/glpapi12.js:687-762: textbook dual ratio test over an explicit row"""
+    if glp_get_dual_stat(P) != GLP_FEAS:
+        xerror("glp_dual_rtest: basic solution is not dual feasible")
+    if dir not in (+1, -1):
+        xerror("glp_dual_rtest: dir = %r; invalid parameter" % (dir,))
+    if not (0.0 < eps < 1.0):
+        xerror("glp_dual_rtest: eps = %s; invalid parameter" % _num(eps))
+    obj = +1.0 if P.dir == GLP_MIN else -1.0
+    piv, teta, big = 0, DBL_MAX, 0.0
+    for t in range(1, length + 1):
+        k = ind[t]
+        if not (1 <= k <= P.m + P.n):
+            xerror("glp_dual_rtest: ind[%d] = %d; variable number out of range" % (t, k))
+        x = _var(P, k)
+        if x.stat == GLP_BS:
+            xerror("glp_dual_rtest: ind[%d] = %d; basic variable not allowed" % (t, k))
+        alfa = +val[t] if dir > 0 else -val[t]
+        if x.stat == GLP_NL:
+            if alfa < +eps:
+                continue
+            temp = (obj * x.dual) / alfa
+        elif x.stat == GLP_NU:
+            if alfa > -eps:
+                continue
+            temp = (obj * x.dual) / alfa
+        elif x.stat == GLP_NF:
+            if -eps < alfa < +eps:
+                continue
+            temp = 0.0
+        else:
+            continue
+        if temp < 0.0:
+            temp = 0.0
+        if teta > temp or (teta == temp and big < abs(alfa)):
+            piv, teta, big = t, temp, abs(alfa)
+    return piv
+
+
 def _plural(k, word):
     return "%d %s%s" % (k, word, "" if k == 1 else "s")
 

@@ -774,3 +774,164 @@ def test_copy_and_erase_prob():
     assert (Q.m, Q.n, Q.nnz, Q.dir, Q.c0) == (0, 0, 0, glpk.GLP_MIN, 0.0) and Q.row == [None] and Q._dev is None
     glpk.glp_add_rows(Q, 1)                                   # still a usable problem object
     assert Q.m == 1
+
+
+# ---- glp_warm_up, simplex-table rows/columns, textbook ratio tests (lib/glpapi12.js:244-762):
+# ---- facade logic over glp_ftran / glp_btran, checked with a dense stand-in for the device's solves
+class _DenseDevice:
+    """what glpb_factorize / glpb_ftran / glpb_btran do, in the SCALED space, by dense LU"""
+
+    def __init__(self, P):
+        import types
+        self.P, self.h = P, None
+        self.L = types.SimpleNamespace(glpb_set_it_cnt=lambda h, it: 0)
+
+    def set_bounds(self, *a):
+        return 0
+
+    def set_basis(self, stat):
+        return 0
+
+    def factorize(self):
+        P, m = self.P, self.P.m
+        B = np.zeros((m, m))
+        for pos in range(1, m + 1):
+            k = P.head[pos]
+            if k <= m:
+                B[k - 1, pos - 1] = 1.0
+            else:
+                col = P.col[k - m]
+                for (i, v) in col.elems:
+                    B[i - 1, pos - 1] = -P.row[i].rii * v * col.sjj
+        if abs(np.linalg.det(B)) < 1e-12:
+            return glpk.GLP_ESING
+        self.B = B
+        return 0
+
+    def ftran(self, b):
+        return np.linalg.solve(self.B, np.asarray(b, float))
+
+    def btran(self, b):
+        return np.linalg.solve(self.B.T, np.asarray(b, float))
+
+
+def _solved_with_oracle(seed):
+    import oracle_lib as O
+    d = H.random_lp(seed)
+    Q = O.Problem.from_arrays(d)
+    assert Q.simplex(meth=O.GLP_PRIMAL) == 0
+    sol = Q.solution()
+    assert sol["status"] == O.GLP_OPT
+    P = glpk.glp_create_prob()
+    m, n = d["m"], d["n"]
+    glpk.glp_add_rows(P, m)
+    glpk.glp_add_cols(P, n)
+    glpk.glp_set_obj_dir(P, d["dir"])
+    glpk.glp_set_obj_coef(P, 0, d["c0"])
+    for i in range(1, m + 1):
+        glpk.glp_set_row_bnds(P, i, int(d["r_type"][i - 1]), float(d["r_lb"][i - 1]), float(d["r_ub"][i - 1]))
+    for j in range(1, n + 1):
+        glpk.glp_set_col_bnds(P, j, int(d["c_type"][j - 1]), float(d["c_lb"][j - 1]), float(d["c_ub"][j - 1]))
+        glpk.glp_set_obj_coef(P, j, float(d["c_coef"][j - 1]))
+        a, b = d["A_ptr"][j - 1], d["A_ptr"][j]
+        glpk.glp_set_mat_col(P, j, b - a, [0] + (d["A_ind"][a:b] + 1).tolist(), [0.0] + d["A_val"][a:b].tolist())
+    glpk.glp_scale_prob(P, glpk.GLP_SF_GM | glpk.GLP_SF_EQ)
+    for i in range(1, m + 1):
+        glpk.glp_set_row_stat(P, i, int(sol["stat"][i - 1]))
+    for j in range(1, n + 1):
+        glpk.glp_set_col_stat(P, j, int(sol["stat"][m + j - 1]))
+    P._dev, P._dirty = _DenseDevice(P), False
+    return P, d, sol
+
+
+def test_warm_up_reproduces_the_solution_of_the_basis():
+    import json
+    with open(os.path.join(H.GOLDEN, "random_pins.json")) as f:
+        pins = [p for p in json.load(f)["lp"] if p["highs"] == "optimal"][:8]
+    for pin in pins:
+        P, d, sol = _solved_with_oracle(pin["seed"])
+        assert glpk.glp_warm_up(P) == 0
+        assert glpk.glp_get_prim_stat(P) == glpk.GLP_FEAS and glpk.glp_get_dual_stat(P) == glpk.GLP_FEAS
+        assert abs(glpk.glp_get_obj_val(P) - pin["obj"]) <= 1e-9 * max(1.0, abs(pin["obj"]))
+        m, n = P.m, P.n
+        prim = np.array([P.row[i].prim for i in range(1, m + 1)] + [P.col[j].prim for j in range(1, n + 1)])
+        dual = np.array([P.row[i].dual for i in range(1, m + 1)] + [P.col[j].dual for j in range(1, n + 1)])
+        np.testing.assert_allclose(prim, sol["prim"], rtol=0, atol=1e-8)
+        np.testing.assert_allclose(dual, sol["dual"], rtol=0, atol=1e-8)
+    # a basis that is not primal feasible is reported as such
+    P, d, sol = _solved_with_oracle(pins[0]["seed"])
+    for j in range(1, P.n + 1):
+        c = P.col[j]
+        if c.stat == glpk.GLP_NL and c.type == glpk.GLP_DB:
+            glpk.glp_set_col_stat(P, j, glpk.GLP_NU)
+    P.valid = 0
+    assert glpk.glp_warm_up(P) == 0 and glpk.glp_get_dual_stat(P) in (glpk.GLP_FEAS, glpk.GLP_INFEAS)
+
+
+def test_simplex_table_rows_columns_and_ratio_tests():
+    import json
+    with open(os.path.join(H.GOLDEN, "random_pins.json")) as f:
+        seed = next(p["seed"] for p in json.load(f)["lp"] if p["highs"] == "optimal" and p["m"] >= 10 and p["n"] >= 12)
+    P, d, sol = _solved_with_oracle(seed)
+    assert glpk.glp_warm_up(P) == 0
+    m, n = P.m, P.n
+    A = H.dense_A(d)
+    full = np.hstack([np.eye(m), -A])                       # (I | -A), unscaled
+    head = [glpk.glp_get_bhead(P, i) for i in range(1, m + 1)]
+    nonbasic = [k for k in range(1, m + n + 1) if k not in head]
+    T = -np.linalg.solve(full[:, [k - 1 for k in head]], full[:, [k - 1 for k in nonbasic]])   # x_B = T x_N
+    ind, val = [0] * (1 + m + n), [0.0] * (1 + m + n)
+    for pos in (1, m // 2 + 1, m):
+        ln = glpk.glp_eval_tab_row(P, head[pos - 1], ind, val)
+        row = np.zeros(m + n + 1)
+        row[ind[1:ln + 1]] = val[1:ln + 1]
+        np.testing.assert_allclose(row[nonbasic], T[pos - 1], atol=1e-9)
+        # dual ratio test on that row against a direct evaluation
+        for direction in (+1, -1):
+            piv = glpk.glp_dual_rtest(P, ln, ind, val, direction, 1e-9)
+            obj = 1.0 if P.dir == glpk.GLP_MIN else -1.0
+            best = None
+            for t in range(1, ln + 1):
+                x = P.row[ind[t]] if ind[t] <= m else P.col[ind[t] - m]
+                alfa = direction * val[t]
+                if (x.stat == glpk.GLP_NL and alfa >= 1e-9) or (x.stat == glpk.GLP_NU and alfa <= -1e-9):
+                    ratio = max(0.0, obj * x.dual / alfa)
+                elif x.stat == glpk.GLP_NF and abs(alfa) >= 1e-9:
+                    ratio = 0.0
+                else:
+                    continue
+                if best is None or ratio < best[0] or (ratio == best[0] and abs(alfa) > best[1]):
+                    best = (ratio, abs(alfa), t)
+            assert piv == (best[2] if best else 0)
+    for k in nonbasic[:3] + nonbasic[-2:]:
+        ln = glpk.glp_eval_tab_col(P, k, ind, val)
+        col = np.zeros(m + n + 1)
+        col[ind[1:ln + 1]] = val[1:ln + 1]
+        np.testing.assert_allclose(col[head], T[:, nonbasic.index(k)], atol=1e-9)
+        piv = glpk.glp_prim_rtest(P, ln, ind, val, +1, 1e-9)
+        assert 0 <= piv <= ln
+        if piv:                                              # the chosen variable really blocks the increase
+            x = P.row[ind[piv]] if ind[piv] <= m else P.col[ind[piv] - m]
+            assert x.stat == glpk.GLP_BS and x.type != glpk.GLP_FR
+    # transform_row of an original row reproduces the table row of its auxiliary variable when that is basic
+    for i in range(1, m + 1):
+        if P.row[i].stat == glpk.GLP_BS:
+            ln0 = len(P.row[i].elems)
+            ri, rv = [0] + [j for (j, _) in P.row[i].elems] + [0] * (m + n), [0.0] + [v for (_, v) in P.row[i].elems] + [0.0] * (m + n)
+            ln = glpk.glp_transform_row(P, ln0, ri, rv)
+            a = np.zeros(m + n + 1)
+            a[ri[1:ln + 1]] = rv[1:ln + 1]
+            np.testing.assert_allclose(a[nonbasic], T[head.index(i)], atol=1e-9)
+            break
+    # transform_col of an original column = table column of that (non-basic) variable, sign as in N = -A
+    j = next(k - m for k in nonbasic if k > m)
+    ci = [0] + [i for (i, _) in P.col[j].elems] + [0] * m
+    cv = [0.0] + [v for (_, v) in P.col[j].elems] + [0.0] * m
+    ln = glpk.glp_transform_col(P, len(P.col[j].elems), ci, cv)
+    c = np.zeros(m + n + 1)
+    c[ci[1:ln + 1]] = cv[1:ln + 1]
+    np.testing.assert_allclose(c[head], T[:, nonbasic.index(m + j)], atol=1e-9)
+    with pytest.raises(glpk.GlpkError, match="must be basic"):
+        glpk.glp_eval_tab_row(P, nonbasic[0], ind, val)
+    with pytest.raises(glpk.GlpkError, match="must be non-basic"):
+        glpk.glp_eval_tab_col(P, head[0], ind, val)
