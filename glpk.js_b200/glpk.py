@@ -8,9 +8,15 @@ object lives on the host exactly like the reference's ``glp_prob``; the solve
 calls marshal it once into a device-resident handle (``native.Problem``) and
 write the solution back into the same fields the reference's getters read.
 
-Scaling (``glp_scale_prob``, lib/glpscl.js) and the triangular crash basis
-(``glp_adv_basis``, lib/glpini01.js) run in the native library's host code
-(``glpb_scale_prob`` / ``glpb_adv_basis``); they prepare inputs of the path.
+Scaling (``glp_scale_prob``, lib/glpscl.js), the triangular crash basis
+(``glp_adv_basis``, lib/glpini01.js) and the LP-format reader (``glp_read_lp``,
+lib/glpcpx.js) run in the native library's host code (``glpb_scale_prob`` /
+``glpb_adv_basis`` / ``glpb_read_lp``); they prepare inputs of the path.  The
+basis-factorisation interface of lib/glpapi12.js (``glp_factorize``,
+``glp_ftran/btran``, ``glp_warm_up``, simplex-table rows/columns, textbook ratio
+tests) sits on the device's two basis solves.  Of the functions the reference
+exports from glpapi01-09/12, glpcpx and glpscl only ``glp_bf_updated`` and the
+sensitivity analysis (``glp_analyze_bound/coef``) are not mirrored.
 
 What is NOT here on purpose ("out of scope" / "next"): the LP/MIP
 presolver's transformations (``glpnpp*.js``), MathProg, cut generators.
