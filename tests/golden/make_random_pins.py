@@ -29,7 +29,7 @@ def checksum(d):
                  + np.sum(d["r_ub"]) + np.sum(d["c_lb"]) + np.sum(d["c_ub"]))
 
 
-def highs(d, integer):
+def highs(d, integer, presolve=False):
     from scipy.optimize import milp, LinearConstraint, Bounds
     from scipy.sparse import csc_matrix
     m, n = d["m"], d["n"]
@@ -44,7 +44,7 @@ def highs(d, integer):
     cl, cu = bnd(d["c_type"], d["c_lb"], d["c_ub"])
     integrality = (d["c_kind"] == O.GLP_IV).astype(int) if integer else np.zeros(n, int)
     res = milp(sgn * d["c_coef"], constraints=LinearConstraint(A, rl, ru), bounds=Bounds(cl, cu),
-               integrality=integrality, options=dict(mip_rel_gap=0.0, presolve=False))
+               integrality=integrality, options=dict(mip_rel_gap=0.0, presolve=presolve, time_limit=120.0))
     # scipy: 0 optimal, 2 infeasible, 3 unbounded, 4 other (HiGHS "unbounded or infeasible")
     kind = {0: "optimal", 2: "infeasible", 3: "unbounded"}.get(res.status, "other")
     obj = float(sgn * res.fun + d["c0"]) if res.status == 0 else None
@@ -63,6 +63,14 @@ def main():
         lkind, lobj = highs(d, False)
         out["mip"].append(dict(seed=seed, m=d["m"], n=d["n"], checksum=checksum(d), highs=kind, obj=obj,
                                lp_highs=lkind, lp_obj=lobj))
+    # the knapsack instances of the branch-and-bound tests (generator = glpb_gen_mkp, C5 family)
+    import glpk_js_b200 as G
+    out["mkp"] = []
+    for (m, n, seed) in ((5, 30, 20240701), (5, 30, 20240702), (8, 40, 20240702)):
+        d = H.to_oracle(G.native.generate("mkp", m=m, n=n, seed=seed))
+        kind, obj = highs(d, True, presolve=True)
+        lkind, lobj = highs(d, False)
+        out["mkp"].append(dict(m=m, n=n, seed=seed, checksum=checksum(d), highs=kind, obj=obj, lp_obj=lobj))
     with open(os.path.join(HERE, "random_pins.json"), "w") as f:
         json.dump(out, f, indent=1)
     print({k: {s: sum(1 for e in v if e["highs"] == s) for s in ("optimal", "infeasible", "unbounded", "other")}

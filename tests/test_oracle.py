@@ -236,3 +236,16 @@ def test_oracle_matches_highs_on_random_mips():
         assert abs(mp["mip_obj"] - pin["obj"]) <= 1e-9 * max(1.0, abs(pin["obj"])), (pin["seed"], mp["mip_obj"], pin["obj"])
         n_opt += 1
     assert n_opt == 23
+
+
+def test_oracle_matches_highs_on_knapsack_mips():
+    """the C5 family (glpb_gen_mkp) at sizes the oracle's branch-and-bound finishes in seconds;
+    the 5x30 instance is the one the GPU branching-rule tests use"""
+    for pin in _pins()["mkp"]:
+        d = H.to_oracle(nat.generate("mkp", m=pin["m"], n=pin["n"], seed=pin["seed"]))
+        assert abs(_checksum(d) - pin["checksum"]) < 1e-9
+        Q = O.Problem.from_arrays(d)
+        assert Q.simplex(meth=O.GLP_PRIMAL) == 0
+        assert abs(Q.solution()["obj"] - pin["lp_obj"]) <= 1e-9 * abs(pin["lp_obj"])
+        assert Q.intopt() == 0 and Q.mip()["mip_stat"] == O.GLP_OPT
+        assert abs(Q.mip()["mip_obj"] - pin["obj"]) <= 1e-9 * abs(pin["obj"]), (pin, Q.mip()["mip_obj"])
