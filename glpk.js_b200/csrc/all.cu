@@ -3,3 +3,4 @@
 #include "solver.cu"
 #include "kapi.cu"
 #include "mip.cu"
+#include "bnbpool.cu"

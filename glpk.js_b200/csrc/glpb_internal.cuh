@@ -101,6 +101,8 @@ struct Key {
 
 struct glpb_mip;
 void glpb_mip_free(glpb_mip *T);
+struct glpb_bnb;
+void glpb_bnb_free(glpb_bnb *T);
 
 struct glpb_prob {
     int device = 0;
@@ -175,6 +177,7 @@ struct glpb_prob {
     std::map<std::string, ProfAcc> prof_acc;
     std::string prof_text;
     glpb_mip *mip = nullptr;       /* branch-and-bound tree while glp_intopt runs */
+    glpb_bnb *bnb = nullptr;       /* batched branch-and-bound (bnbpool.cuh) while it runs */
     /* ---- replayed launch sequences (small LPs: the node LPs of branch-and-bound).
        The fresh recomputations of bbar / cbar and the start-of-solve block of the dual
        loop are fixed sequences of 7-22 tiny kernels whose arguments never change for

@@ -1025,8 +1025,16 @@ extern "C" int glpb_mip_end(glpb_prob *P, int ret)
     return ret;
 }
 
+static bool bnb_batched(const glpb_prob *P, const glpb_iocp &parm);
+static int bnb_intopt_batched(glpb_prob *P, const glpb_iocp *parm);
+
 extern "C" int glpb_intopt(glpb_prob *P, const glpb_iocp *parm)
 {
+    if (P) {
+        glpb_iocp pr;
+        if (parm) pr = *parm; else glpb_init_iocp(&pr);
+        if (bnb_batched(P, pr)) return bnb_intopt_batched(P, parm);
+    }
     int rc = glpb_mip_begin(P, parm);
     if (rc) return rc;
     int ret = glpb_mip_run(P, -1, nullptr);

@@ -162,6 +162,7 @@ extern "C" void glpb_destroy(glpb_prob *P)
     for (auto &kind : P->graphs)
         for (auto &g : kind) if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
     if (P->mip) { glpb_mip_free(P->mip); P->mip = nullptr; }
+    if (P->bnb) { glpb_bnb_free(P->bnb); P->bnb = nullptr; }
     if (P->h_ctrl) cudaFreeHost(P->h_ctrl);
     if (P->h_stage) cudaFreeHost(P->h_stage);
     if (P->stream) cudaStreamDestroy(P->stream);

@@ -74,6 +74,8 @@ SYMBOLS = [
     "glpb_k_ratio_dual", "glpb_k_trow", "glpb_bench_kernel", "glpb_gen_packing",
     "glpb_gen_covering", "glpb_gen_mkp", "glpb_free_problem", "glpb_rng_fill",
     "glpb_scale_prob", "glpb_adv_basis", "glpb_read_lp", "glpb_free_names",
+    "glpb_bnb_begin", "glpb_bnb_round", "glpb_bnb_open_count", "glpb_bnb_get_incumbent", "glpb_bnb_set_cutoff", "glpb_bnb_clear",
+    "glpb_bnb_record_bytes", "glpb_bnb_export_nodes", "glpb_bnb_import_nodes", "glpb_bnb_stats", "glpb_bnb_end",
 ]
 
 _lib = None
@@ -146,6 +148,18 @@ def load():
     L.glpb_adv_basis.argtypes = [ci, ci] + [vp] * 9
     L.glpb_read_lp.argtypes = [C.c_char_p, C.c_long, vp, vp, vp]
     L.glpb_free_names.argtypes = [vp]
+    L.glpb_bnb_begin.argtypes = [vp, vp, ci, ci]
+    L.glpb_bnb_round.argtypes = [vp, C.c_long, vp]
+    L.glpb_bnb_open_count.argtypes = [vp]
+    L.glpb_bnb_get_incumbent.argtypes = [vp, vp, vp]
+    L.glpb_bnb_set_cutoff.argtypes = [vp, cd]
+    L.glpb_bnb_clear.argtypes = [vp]
+    L.glpb_bnb_record_bytes.argtypes = [vp]
+    L.glpb_bnb_record_bytes.restype = C.c_long
+    L.glpb_bnb_export_nodes.argtypes = [vp, ci, vp, vp]
+    L.glpb_bnb_import_nodes.argtypes = [vp, vp, ci]
+    L.glpb_bnb_stats.argtypes = [vp, vp, ci]
+    L.glpb_bnb_end.argtypes = [vp, ci]
     _lib = L
     return L
 
@@ -399,6 +413,61 @@ class Problem:
 
     def mip_end(self, ret=0):
         return self.L.glpb_mip_end(self.h, int(ret))
+
+    # ---- batched, device-resident branch-and-bound (one CTA per node) ----
+    def bnb_begin(self, parm=None, batch=0, slab_nodes=0, **kw):
+        if parm is None:
+            parm = self.iocp(**kw)
+        rc = self.L.glpb_bnb_begin(self.h, C.byref(parm), int(batch), int(slab_nodes))
+        if rc < 0:
+            raise RuntimeError("glpb_bnb_begin failed (%d): %s" % (rc, last_error()))
+        return rc
+
+    def bnb_round(self, max_tasks=-1):
+        done = C.c_long()
+        rc = self.L.glpb_bnb_round(self.h, max_tasks, C.byref(done))
+        if rc < 0:
+            raise RuntimeError("glpb_bnb_round failed (%d): %s" % (rc, last_error()))
+        return rc, done.value
+
+    def bnb_open_count(self):
+        return self.L.glpb_bnb_open_count(self.h)
+
+    def bnb_incumbent(self):
+        has, obj = C.c_int(), C.c_double()
+        self.L.glpb_bnb_get_incumbent(self.h, C.byref(has), C.byref(obj))
+        return bool(has.value), obj.value
+
+    def bnb_set_cutoff(self, obj):
+        return self.L.glpb_bnb_set_cutoff(self.h, float(obj))
+
+    def bnb_clear(self):
+        return self.L.glpb_bnb_clear(self.h)
+
+    def bnb_record_bytes(self):
+        return int(self.L.glpb_bnb_record_bytes(self.h))
+
+    def bnb_export(self, max_count, dev_ptr):
+        """pack up to max_count open nodes into DEVICE memory at dev_ptr; returns the count"""
+        cnt = C.c_int()
+        rc = self.L.glpb_bnb_export_nodes(self.h, int(max_count), C.c_void_p(dev_ptr), C.byref(cnt))
+        if rc != 0:
+            raise RuntimeError("glpb_bnb_export_nodes failed (%d): %s" % (rc, last_error()))
+        return cnt.value
+
+    def bnb_import(self, dev_ptr, count):
+        rc = self.L.glpb_bnb_import_nodes(self.h, C.c_void_p(dev_ptr), int(count))
+        if rc != 0:
+            raise RuntimeError("glpb_bnb_import_nodes failed (%d): %s" % (rc, last_error()))
+
+    def bnb_stats(self):
+        out = (C.c_long * 8)()
+        self.L.glpb_bnb_stats(self.h, out, 8)
+        keys = ["solved", "tasks", "rounds", "iters", "refacs", "open", "smem_bytes", "a_in_smem"]
+        return {k: int(out[i]) for i, k in enumerate(keys)}
+
+    def bnb_end(self, ret=0):
+        return self.L.glpb_bnb_end(self.h, int(ret))
 
     def counters(self):
         out = (C.c_long * 8)()

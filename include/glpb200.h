@@ -128,6 +128,39 @@ int glpb_mip_export_nodes(glpb_prob *P, int max_count, void *buf, long cap, int 
 int glpb_mip_import_nodes(glpb_prob *P, const void *buf, int count);
 int glpb_mip_end(glpb_prob *P, int ret);
 
+/* Batched, device-resident branch-and-bound (replaces the serial
+ * ios_driver loop, lib/glpios03.js:507-951, for problems whose node LP fits one
+ * CTA: m <= 64, n <= 1024).  The open nodes' states live in a device slab; one
+ * round = ONE kernel launch that takes up to `batch` open nodes, one CTA each,
+ * through ios_preprocess_node, ios_solve_node (warm-started dual simplex out of
+ * shared memory), ios_round_bound, check_integrality, fix_by_red_cost, the
+ * Driebeck-Tomlin choice and branch_on; the host only keeps the tree.
+ * glpb_intopt takes this path by itself for eligible problems (environment
+ * GLPB_BNB=serial keeps the one-LP-at-a-time driver).
+ *   begin:  batch <= 0 -> 4 x SM count (GLPB_BNB_BATCH), slab_nodes <= 0 ->
+ *           262144 (GLPB_BNB_SLAB); the root LP must be solved (GLP_EROOT).
+ *   round:  1 = a round was run (*done nodes), 0 = local pool empty,
+ *           GLP_ETMLIM / GLP_ESTOP (node_lim) / GLP_EMIPGAP / GLP_EFAIL.
+ *   export/import: self-contained node records in DEVICE memory of the
+ *           handle's GPU (glpb_bnb_record_bytes each) for migration between
+ *           ranks, e.g. through an NCCL all-gather; set_cutoff installs an
+ *           incumbent objective found elsewhere.
+ *   stats:  [0] node LPs solved (= ios_solve_node calls), [1] nodes processed,
+ *           [2] rounds, [3] dual simplex iterations, [4] basis inversions,
+ *           [5] open nodes, [6] shared-memory bytes per CTA, [7] matrix in smem.
+ *   end:    solve_mip's status mapping (lib/glpapi09.js:82-112); returns ret. */
+int glpb_bnb_begin(glpb_prob *P, const glpb_iocp *parm, int batch, int slab_nodes);
+int glpb_bnb_round(glpb_prob *P, long max_tasks, long *done);
+int glpb_bnb_open_count(glpb_prob *P);
+int glpb_bnb_get_incumbent(glpb_prob *P, int *has_solution, double *obj);
+int glpb_bnb_set_cutoff(glpb_prob *P, double obj);
+int glpb_bnb_clear(glpb_prob *P);     /* drop all open nodes: a rank that starts empty and is fed by migration */
+long glpb_bnb_record_bytes(glpb_prob *P);
+int glpb_bnb_export_nodes(glpb_prob *P, int max_count, void *dev_buf, int *count);
+int glpb_bnb_import_nodes(glpb_prob *P, const void *dev_buf, int count);
+int glpb_bnb_stats(glpb_prob *P, long *out, int count);
+int glpb_bnb_end(glpb_prob *P, int ret);
+
 /* Counters for measurement: out[0] iterations, [1] refactorisations,
  * [2] kernel launches, [3] host<->device syncs, [4] basis updates,
  * [5] current kernel size k, [6] device microseconds in the last solve,

@@ -294,6 +294,18 @@ API int glpo_csa_get(void *csa, const char *name, void *out, int cap_bytes)
     return -1;
 }
 
+/* size of the factors the oracle's basis code holds right now (called from a
+   hook): out = {nnz_f, nnz_v, nnz_h, hh_nfs, luf.n}; SURVEY 8d counts the bytes
+   of FTRAN/BTRAN as 12*(nnz_f + nnz_h + nnz_v) + 16 m */
+API void glpo_csa_lu_stats(void *csa, long *out5)
+{
+    CSA &c = *(CSA *)csa;
+    out5[0] = out5[1] = out5[2] = out5[3] = out5[4] = 0;
+    if (!c.bfd) return;
+    out5[0] = c.bfd->luf.nnz_f; out5[1] = c.bfd->luf.nnz_v; out5[2] = c.bfd->nnz_h;
+    out5[3] = c.bfd->hh_nfs; out5[4] = c.bfd->luf.n;
+}
+
 /* ---- stateless selection routines, CSA layout ---- */
 API int glpo_chuzc_primal(int n, const signed char *stat, const double *cbar,
                           const double *gamma, double tol_dj)

@@ -123,6 +123,47 @@ def csa_scalars(csa):
     return d
 
 
+def generate(which, **kw):
+    """The synthetic problems of SURVEY 8d built by the ORACLE's own generator
+    (oracle/gen.cpp) -- same dict layout as glpk_js_b200.native.generate
+    (type/lb/ub are [m+n], rows first), without loading the product library."""
+    L = lib()
+    L.glpo_gen_packing.argtypes = [C.c_int, C.c_int, C.c_double, C.c_int]
+    L.glpo_gen_covering.argtypes = [C.c_int] * 5
+    L.glpo_gen_mkp.argtypes = [C.c_int] * 3
+    L.glpo_gen_fetch.argtypes = [C.c_void_p] * 12
+    if which == "packing":
+        m, n = kw.get("m", 2048), kw.get("n", 4096)
+        nnz = L.glpo_gen_packing(m, n, kw.get("density", 0.20), kw.get("seed", 20240501))
+    elif which == "covering":
+        m, n = kw.get("m", 16384), kw.get("n", 32768)
+        nnz = L.glpo_gen_covering(m, n, kw.get("kmin", 8), kw.get("kspan", 17), kw.get("seed", 20240601))
+    elif which == "mkp":
+        m, n = kw.get("m", 30), kw.get("n", 500)
+        nnz = L.glpo_gen_mkp(m, n, kw.get("seed", 20240701))
+    else:
+        raise ValueError(which)
+    i32, f64 = (lambda k: np.zeros(k, np.int32)), (lambda k: np.zeros(k, np.float64))
+    r_type, r_lb, r_ub = i32(m), f64(m), f64(m)
+    c_type, c_lb, c_ub, c_coef, c_kind = i32(n), f64(n), f64(n), f64(n), i32(n)
+    A_ptr, A_ind, A_val = i32(n + 1), i32(nnz), f64(nnz)
+    dr = C.c_int()
+    L.glpo_gen_fetch(C.byref(dr), *[_p(a) for a in (r_type, r_lb, r_ub, c_type, c_lb, c_ub, c_coef, c_kind,
+                                                    A_ptr, A_ind, A_val)])
+    return dict(m=m, n=n, nnz=nnz, dir=dr.value, c0=0.0, type=np.concatenate([r_type, c_type]),
+                lb=np.concatenate([r_lb, c_lb]), ub=np.concatenate([r_ub, c_ub]), coef=c_coef, kind=c_kind,
+                A_ptr=A_ptr, A_ind=A_ind, A_val=A_val)
+
+
+def csa_lu_stats(csa):
+    """nnz of the oracle's F, V, H factors right now (inside a hook)"""
+    out = (C.c_long * 5)()
+    L = lib()
+    L.glpo_csa_lu_stats.argtypes = [C.c_void_p, C.c_void_p]
+    L.glpo_csa_lu_stats(csa, out)
+    return dict(nnz_f=out[0], nnz_v=out[1], nnz_h=out[2], hh_nfs=out[3], n=out[4])
+
+
 class Problem:
     """A problem held by the oracle."""
 
