@@ -274,3 +274,202 @@ class HybridComm:
             got = self.outer.allgather_bytes(np.concatenate(loc), nbytes * self.W)   # [P] arrays
             out = [g[i * nbytes:(i + 1) * nbytes] for g in got for i in range(self.W)]
         return self.local._exchange(out)[0]
+
+
+# ======================================================================
+# Batched engine (glpb_bnb_*: one CTA per node, node states device-resident)
+# ======================================================================
+HDR_DOUBLES = 8          # [key, open, stop, solved, n_ship, dst, has_sol, spare]
+
+
+class BatchWorker:
+    """Adapter over ``native.Problem.bnb_*``; tests substitute the host
+    emulation of the same engine (tests/ne_emul.py)."""
+
+    def __init__(self, prob):
+        self.P = prob
+
+    def begin(self, batch=0, slab_nodes=0, **iocp):
+        return self.P.bnb_begin(batch=batch, slab_nodes=slab_nodes, **iocp)
+
+    def clear(self):
+        self.P.bnb_clear()
+
+    def round(self, max_tasks=-1):
+        return self.P.bnb_round(max_tasks)
+
+    def incumbent(self):
+        return self.P.bnb_incumbent()
+
+    def set_cutoff(self, obj):
+        self.P.bnb_set_cutoff(obj)
+
+    def open_count(self):
+        return self.P.bnb_open_count()
+
+    def record_bytes(self):
+        return self.P.bnb_record_bytes()
+
+    def export_to(self, ptr, n):
+        return self.P.bnb_export(n, ptr)
+
+    def import_from(self, ptr, n):
+        self.P.bnb_import(ptr, n)
+
+    def solved(self):
+        return self.P.bnb_stats()["solved"]
+
+    def end(self, ret):
+        return self.P.bnb_end(ret)
+
+
+class TensorComm:
+    """One fused all-gather per exchange over torch.distributed (NCCL: the node
+    payload goes device -> NVLink -> device; gloo in CPU tests).  ``world`` 1
+    needs no process group."""
+
+    def __init__(self, device=None):
+        import torch
+        self.torch = torch
+        try:
+            import torch.distributed as dist
+            self.dist = dist if dist.is_available() and dist.is_initialized() else None
+        except Exception:
+            self.dist = None
+        self.rank = self.dist.get_rank() if self.dist else 0
+        self.world = self.dist.get_world_size() if self.dist else 1
+        if device is None:
+            device = (torch.device("cuda", torch.cuda.current_device())
+                      if (self.dist and self.dist.get_backend() == "nccl") or (not self.dist and torch.cuda.is_available())
+                      else torch.device("cpu"))
+        self.device = device
+
+    def buffers(self, nbytes):
+        t = self.torch
+        send = t.zeros(nbytes, dtype=t.uint8, device=self.device)
+        recv = t.zeros(nbytes * self.world, dtype=t.uint8, device=self.device)
+        return send, recv
+
+    def write_header(self, send, values):
+        t = self.torch
+        h = t.tensor(values, dtype=t.float64).view(t.uint8)
+        send[:h.numel()].copy_(h)
+
+    def allgather(self, send, recv):
+        if self.dist:
+            self.dist.all_gather_into_tensor(recv, send)
+        else:
+            recv.copy_(send)
+
+    def read_headers(self, recv, nbytes):
+        t = self.torch
+        rows = recv.view(self.world, nbytes)[:, :8 * HDR_DOUBLES].contiguous().cpu()      # the one host sync of an exchange
+        return rows.view(t.float64).view(self.world, HDR_DOUBLES).tolist()
+
+    def sync(self):
+        if self.device.type == "cuda":
+            self.torch.cuda.synchronize(self.device)
+
+
+def sharded_bnb_batched(worker, comm, minimize, batch=0, slab_nodes=0, node_lim=None, max_ship=64,
+                        exchange_every=1, max_rounds=None, **iocp):
+    """The sharded search on this rank with the batched engine.
+
+    Rank 0 starts from the root, the others start empty and are fed by
+    migration.  A *round* is one launch of the node kernel over up to ``batch``
+    open nodes of the local pool.  Every ``exchange_every`` rounds the ranks meet
+    in ONE all-gather of [header | up to max_ship node records]: the header
+    carries the incumbent objective, the pool size, stop flags and the number of
+    records shipped to which rank.  The transfer plan is derived by every rank
+    from the same gathered pool sizes and executed with the next exchange.
+    ``node_lim`` is a per-rank budget of node LPs (weak scaling).  Returns the
+    global optimum value, who holds the solution vector, and node counts."""
+    rank, world = comm.rank, comm.world
+    rc = worker.begin(batch=batch, slab_nodes=slab_nodes, **iocp)
+    if rc != 0:
+        return dict(ret=rc, obj=None, nodes=0, total_nodes=0, rounds=0, exchanges=0)
+    if rank != 0:
+        worker.clear()
+    rb = worker.record_bytes()
+    hdr_bytes = 8 * HDR_DOUBLES
+    nbytes = hdr_bytes + max_ship * rb
+    send, recv = comm.buffers(nbytes)
+    inf = float("inf")
+    rounds = exchanges = 0
+    ret = 0
+    my_plan = None                      # (dst, n) decided at the previous exchange
+    moved_in = moved_out = 0
+    while True:
+        # ---- local work ----
+        for _ in range(exchange_every):
+            if ret != 0:
+                break
+            left = -1
+            if node_lim is not None:
+                left = node_lim - worker.solved()
+                if left <= 0:
+                    break
+            state, done = worker.round(left)
+            if state == 1:
+                rounds += 1
+            elif state == 0:
+                break                   # local pool empty
+            else:
+                ret = state
+        if world == 1 and node_lim is None and ret == 0 and worker.open_count() > 0 and (max_rounds is None or rounds < max_rounds):
+            continue                    # nothing to exchange with
+        # ---- one fused exchange ----
+        has, obj = worker.incumbent()
+        key = (obj if minimize else -obj) if abs(obj) < 1e300 else inf
+        n_ship, dst = 0, -1
+        if my_plan is not None and ret == 0:
+            dst, want = my_plan
+            want = min(want, max_ship, max(0, worker.open_count() - 1))
+            if want > 0:
+                n_ship = worker.export_to(send.data_ptr() + hdr_bytes, want)
+            if n_ship == 0:
+                dst = -1
+        solved = worker.solved()
+        at_limit = node_lim is not None and solved >= node_lim
+        stop = 1.0 if (ret != 0 or (max_rounds is not None and rounds >= max_rounds)) else 0.0
+        comm.write_header(send, [key, float(worker.open_count()), stop, float(solved), float(n_ship), float(dst),
+                                 1.0 if has else 0.0, 1.0 if at_limit else 0.0])
+        comm.allgather(send, recv)
+        hdrs = comm.read_headers(recv, nbytes)
+        exchanges += 1
+        moved_out += n_ship
+        for src, h in enumerate(hdrs):
+            if int(h[5]) == rank and int(h[4]) > 0 and src != rank:
+                worker.import_from(recv.data_ptr() + src * nbytes + hdr_bytes, int(h[4]))
+                moved_in += int(h[4])
+        best = min(h[0] for h in hdrs)
+        if best < inf:
+            worker.set_cutoff(best if minimize else -best)
+        counts = [int(h[1]) for h in hdrs]
+        counts[rank] = worker.open_count()
+        in_flight = sum(int(h[4]) for h in hdrs)
+        any_stop = any(h[2] > 0 for h in hdrs)
+        all_limit = all(h[7] > 0 for h in hdrs)
+        if any_stop or all_limit:
+            break
+        if sum(int(h[1]) for h in hdrs) == 0 and in_flight == 0:
+            break
+        # every rank derives the same plan from the same numbers (its own count as gathered)
+        plan = transfer_plan([int(h[1]) for h in hdrs], low=max(1, (batch or 1)), max_ship=max_ship)
+        my_plan = plan.get(rank)
+    # ---- wrap up: optimum and its holder ----
+    has, obj = worker.incumbent()
+    key = (obj if minimize else -obj) if abs(obj) < 1e300 else inf
+    solved = worker.solved()
+    comm.write_header(send, [key, float(worker.open_count()), float(ret), float(solved), 0.0, -1.0, 1.0 if has else 0.0, 0.0])
+    comm.allgather(send, recv)
+    hdrs = comm.read_headers(recv, nbytes)
+    best = min(h[0] for h in hdrs)
+    holder = next((r for r, h in enumerate(hdrs) if h[6] > 0 and h[0] == best), None)
+    total = int(sum(h[3] for h in hdrs))
+    err = int(max(h[2] for h in hdrs))
+    open_left = int(sum(h[1] for h in hdrs))
+    worker.end(err)
+    return dict(ret=err, obj=(None if best == inf else (best if minimize else -best)), holder=holder, nodes=solved,
+                total_nodes=total, rounds=rounds, exchanges=exchanges, moved_in=moved_in, moved_out=moved_out,
+                open_left=open_left)

@@ -90,7 +90,11 @@ struct Ctrl {
     double obj;         /* dual: tracked objective (bbar[0] in the reference)  */
     double big, scal;   /* scratch scalars                                    */
     double max_a;       /* largest |a| seen when building the kernel matrix   */
-    unsigned int ticket[16];
+    /* optional pivot log (parity tests): entry it = (q, p) of iteration it, 0-based
+       positions (p = P_FLIP for a bound flip); written by iter_end on every path */
+    int *piv_log;
+    int piv_cap, piv_pad;
+    unsigned int ticket[12];
 };
 
 /* key used by every arg-reduction */
@@ -176,6 +180,8 @@ struct glpb_prob {
     std::vector<ProfRec> prof_recs;
     std::map<std::string, ProfAcc> prof_acc;
     std::string prof_text;
+    int *piv_log = nullptr;        /* device pivot log (glpb_set_pivot_log) */
+    int piv_cap = 0;
     glpb_mip *mip = nullptr;       /* branch-and-bound tree while glp_intopt runs */
     glpb_bnb *bnb = nullptr;       /* batched branch-and-bound (bnbpool.cuh) while it runs */
     /* ---- replayed launch sequences (small LPs: the node LPs of branch-and-bound).

@@ -147,6 +147,10 @@ __device__ __forceinline__ bool gamma_on(const Ctrl *ctrl) { return ctrl->pse &&
    the next iteration; runs in one thread of the last kernel of an iteration */
 __device__ void iter_end(Ctrl *ctrl, bool basis_changed, int dual)
 {
+    if (ctrl->piv_log && ctrl->it_cnt >= 0 && ctrl->it_cnt < ctrl->piv_cap) {
+        ctrl->piv_log[2 * ctrl->it_cnt] = ctrl->q;
+        ctrl->piv_log[2 * ctrl->it_cnt + 1] = ctrl->p;
+    }
     ctrl->it_cnt++;
     ctrl->n_done++;
     if (ctrl->rigorous > 0) ctrl->rigorous--;

@@ -161,6 +161,7 @@ extern "C" void glpb_destroy(glpb_prob *P)
     P->prof = 0; prof_collect(P);
     for (auto &kind : P->graphs)
         for (auto &g : kind) if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
+    if (P->piv_log) { cudaFree(P->piv_log); P->piv_log = nullptr; }
     if (P->mip) { glpb_mip_free(P->mip); P->mip = nullptr; }
     if (P->bnb) { glpb_bnb_free(P->bnb); P->bnb = nullptr; }
     if (P->h_ctrl) cudaFreeHost(P->h_ctrl);
@@ -1606,6 +1607,44 @@ extern "C" int glpb_simplex(glpb_prob *P, const glpb_smcp *parm_)
     cudaEventDestroy(ev0); cudaEventDestroy(ev1);
     P->last_solve_us = ms * 1000.0;
     return ret;
+}
+
+/* Pivot log for parity tests: the (q, p) pair of every iteration whose number
+   (the handle's it_cnt before the iteration) is below `cap`; q = 1..n position
+   in the non-basic list, p = 1..m position in the basis header, p = -1 for a
+   bound flip (the reference's csa.q / csa.p, lib/glpspx01.js:30-32). */
+extern "C" int glpb_set_pivot_log(glpb_prob *P, int cap)
+{
+    if (!P || cap < 0) return GLPB_EINVAL;
+    CK(cudaSetDevice(P->device));
+    CK(cudaStreamSynchronize(P->stream));
+    if (P->piv_log) { cudaFree(P->piv_log); P->piv_log = nullptr; }
+    P->piv_cap = cap;
+    if (cap > 0) {
+        CK(cudaMalloc((void **)&P->piv_log, (size_t)2 * cap * sizeof(int)));
+        CK(cudaMemset(P->piv_log, 0xFF, (size_t)2 * cap * sizeof(int)));
+    }
+    int *ptr = P->piv_log;
+    int capv[2] = {cap, 0};
+    CK(cudaMemcpy(&P->ctrl->piv_log, &ptr, sizeof ptr, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(&P->ctrl->piv_cap, capv, sizeof capv, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+extern "C" int glpb_get_pivot_log(glpb_prob *P, int *qp, int cap, int *count)
+{
+    if (!P || !qp || !count) return GLPB_EINVAL;
+    CK(cudaSetDevice(P->device));
+    CK(cudaStreamSynchronize(P->stream));
+    int n = std::min(std::min(cap, P->piv_cap), P->it_cnt);
+    if (n < 0) n = 0;
+    if (n > 0) CK(cudaMemcpy(qp, P->piv_log, (size_t)2 * n * sizeof(int), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < n; i++) {
+        qp[2 * i] += 1;
+        qp[2 * i + 1] = (qp[2 * i + 1] == P_FLIP) ? -1 : qp[2 * i + 1] + 1;
+    }
+    *count = n;
+    return 0;
 }
 
 extern "C" int glpb_get_status(glpb_prob *P)

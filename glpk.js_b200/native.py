@@ -74,7 +74,7 @@ SYMBOLS = [
     "glpb_k_ratio_dual", "glpb_k_trow", "glpb_bench_kernel", "glpb_gen_packing",
     "glpb_gen_covering", "glpb_gen_mkp", "glpb_free_problem", "glpb_rng_fill",
     "glpb_scale_prob", "glpb_adv_basis", "glpb_read_lp", "glpb_free_names",
-    "glpb_bnb_begin", "glpb_bnb_round", "glpb_bnb_open_count", "glpb_bnb_get_incumbent", "glpb_bnb_set_cutoff", "glpb_bnb_clear",
+    "glpb_set_pivot_log", "glpb_get_pivot_log", "glpb_bnb_begin", "glpb_bnb_round", "glpb_bnb_open_count", "glpb_bnb_get_incumbent", "glpb_bnb_set_cutoff", "glpb_bnb_clear",
     "glpb_bnb_record_bytes", "glpb_bnb_export_nodes", "glpb_bnb_import_nodes", "glpb_bnb_stats", "glpb_bnb_end",
 ]
 
@@ -148,6 +148,8 @@ def load():
     L.glpb_adv_basis.argtypes = [ci, ci] + [vp] * 9
     L.glpb_read_lp.argtypes = [C.c_char_p, C.c_long, vp, vp, vp]
     L.glpb_free_names.argtypes = [vp]
+    L.glpb_set_pivot_log.argtypes = [vp, ci]
+    L.glpb_get_pivot_log.argtypes = [vp, vp, ci, vp]
     L.glpb_bnb_begin.argtypes = [vp, vp, ci, ci]
     L.glpb_bnb_round.argtypes = [vp, C.c_long, vp]
     L.glpb_bnb_open_count.argtypes = [vp]
@@ -468,6 +470,20 @@ class Problem:
 
     def bnb_end(self, ret=0):
         return self.L.glpb_bnb_end(self.h, int(ret))
+
+    def set_pivot_log(self, cap):
+        rc = self.L.glpb_set_pivot_log(self.h, int(cap))
+        if rc != 0:
+            raise RuntimeError("glpb_set_pivot_log failed (%d): %s" % (rc, last_error()))
+
+    def pivot_log(self, cap):
+        """[(q, p)] of the first iterations as the reference numbers them (p = -1: bound flip)"""
+        qp = np.zeros(2 * max(1, cap), np.int32)
+        cnt = C.c_int()
+        rc = self.L.glpb_get_pivot_log(self.h, _p(qp), int(cap), C.byref(cnt))
+        if rc != 0:
+            raise RuntimeError("glpb_get_pivot_log failed (%d): %s" % (rc, last_error()))
+        return [(int(qp[2 * i]), int(qp[2 * i + 1])) for i in range(cnt.value)]
 
     def counters(self):
         out = (C.c_long * 8)()

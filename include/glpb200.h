@@ -174,6 +174,14 @@ int glpb_get_counters(glpb_prob *P, long *out, int count);
 int glpb_set_profile(glpb_prob *P, int on);
 const char *glpb_profile_report(glpb_prob *P);
 
+/* Pivot log (parity tests of the iteration engine): after glpb_set_pivot_log(P, cap)
+ * every simplex iteration whose number is below cap records the entering / leaving
+ * pair the reference keeps in csa.q / csa.p (lib/glpspx01.js:30-32: q = 1..n in the
+ * non-basic list, p = 1..m in the basis header, p = -1 for a bound flip).
+ * glpb_get_pivot_log copies min(cap, iterations done) pairs: qp[2 it] = q, qp[2 it + 1] = p. */
+int glpb_set_pivot_log(glpb_prob *P, int cap);
+int glpb_get_pivot_log(glpb_prob *P, int *qp, int cap, int *count);
+
 /* Basis solves with the current factorisation, scaled space:
  * bfd_ftran / bfd_btran (lib/glpbfd.js:148-168); x is [m], in place. */
 int glpb_ftran(glpb_prob *P, double *x);

@@ -6,6 +6,7 @@ committed as tests/golden/lp_pins.json, c3_mid_basis.npz, c3_oracle_run.json.
   python tests/golden/make_c3_pins.py highs          # independent optima (scipy/HiGHS)
   python tests/golden/make_c3_pins.py oracle-c3      # the oracle's own uninterrupted C3 solve (hours, 1 thread)
   python tests/golden/make_c3_pins.py oracle-c2      # the oracle's C2 solve (minutes)
+  python tests/golden/make_c3_pins.py highs-mkp      # HiGHS MIP optima of the knapsacks solved to completion
 
 Problems come from the ORACLE's generator (oracle/gen.cpp); nothing of the
 product library is loaded here.
@@ -118,6 +119,22 @@ if __name__ == "__main__":
             pins.setdefault(name, {})["config"] = dict(cfg["kw"], gen=cfg["which"], nnz=int(d["nnz"]))
             pins[name]["highs"] = highs(d)
             print(name, pins[name]["highs"], flush=True)
+            save_pins(pins)
+    elif what == "highs-mkp":
+        # independent MIP optima (scipy.optimize.milp = HiGHS) of the C5-family knapsacks the bench and the
+        # tests solve to completion; 30x100 does not finish within 600 s in HiGHS and stays unproven
+        from scipy.optimize import milp, LinearConstraint, Bounds
+        from scipy.sparse import csc_matrix
+        pins = load_pins()
+        out = pins.setdefault("mkp", {})
+        for (m, n, seed) in ((30, 60, 20240701), (30, 100, 20240701), (10, 40, 3)):
+            d = O.generate("mkp", m=m, n=n, seed=seed)
+            A = csc_matrix((d["A_val"], d["A_ind"], d["A_ptr"]), shape=(m, n))
+            t0 = time.time()
+            r = milp(-d["coef"], constraints=LinearConstraint(A, -np.inf, d["ub"][:m]), integrality=np.ones(n),
+                     bounds=Bounds(0, 1), options=dict(mip_rel_gap=0.0, time_limit=600))
+            out["mkp_%dx%d_seed%d" % (m, n, seed)] = dict(m=m, n=n, seed=seed, highs_status=int(r.status),
+                                                          highs_obj=float(-r.fun), seconds=round(time.time() - t0, 2))
             save_pins(pins)
     elif what == "oracle-c3":
         oracle_run(C3, "c3", O.GLP_DUAL, 5000, 60000)

@@ -113,7 +113,63 @@ class Pool:
         buf = np.ascontiguousarray(buf, dtype=np.uint8)
         assert self.L.ne_emul_import(self.h, _p(buf), count) == 0
 
+    # ---- pointer-based migration, the interface of glpk_js_b200.bnb.BatchWorker ----
+    def export_to(self, ptr, n):
+        cnt = C.c_int()
+        assert self.L.ne_emul_export(self.h, int(n), C.c_void_p(ptr), C.byref(cnt)) == 0
+        return cnt.value
+
+    def import_from(self, ptr, n):
+        assert self.L.ne_emul_import(self.h, C.c_void_p(ptr), int(n)) == 0
+
     def stats(self):
         out = (C.c_long * 5)()
         self.L.ne_emul_stats(self.h, out)
         return dict(solved=out[0], tasks=out[1], rounds=out[2], iters=out[3], refacs=out[4])
+
+
+class EmulWorker:
+    """glpk_js_b200.bnb.BatchWorker over the host emulation (CPU tests of the
+    sharding protocol, gloo world-size 2)"""
+
+    def __init__(self, d, stat, **kw):
+        self.d, self.stat, self.kw, self.pool = d, stat, kw, None
+
+    def begin(self, batch=0, slab_nodes=0, **iocp):
+        kw = dict(self.kw)
+        kw.update(iocp)
+        self.pool = Pool(self.d, self.stat, batch=batch or 8, cap=slab_nodes or 16384, **kw)
+        return 0
+
+    def clear(self):
+        self.pool.clear()
+
+    def round(self, max_tasks=-1):
+        return self.pool.round(max_tasks)
+
+    def incumbent(self):
+        inc = self.pool.incumbent()
+        big = 1.7976931348623157e308
+        return inc["have_sol"], (inc["obj"] if inc["have_cut"] else (big if self.pool.dir == 1 else -big))
+
+    def set_cutoff(self, obj):
+        self.pool.set_cutoff(obj)
+
+    def open_count(self):
+        return self.pool.open_count()
+
+    def record_bytes(self):
+        return self.pool.record_bytes()
+
+    def export_to(self, ptr, n):
+        return self.pool.export_to(ptr, n)
+
+    def import_from(self, ptr, n):
+        self.pool.import_from(ptr, n)
+
+    def solved(self):
+        return self.pool.stats()["solved"]
+
+    def end(self, ret):
+        self.final = self.pool.incumbent()
+        return ret

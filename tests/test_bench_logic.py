@@ -1,12 +1,15 @@
-"""CPU test of bench.py's branch-and-bound leg (control flow, JSON contract) with the
-device replaced by a scripted stand-in: the default line embeds this leg as its `bnb`
-block, so an exception there would cost the headline line on the GPU box."""
+"""CPU tests of bench.py's host logic: the reference arm's contract (and that it
+loads nothing of the product), identical `config` in both arms, the roofline
+object, and the branch-and-bound block with the device replaced by a scripted
+stand-in (an exception there would cost the headline line on the GPU box)."""
 import argparse
+import contextlib
 import importlib.util
 import io
 import json
 import os
-import contextlib
+import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -14,191 +17,116 @@ import pytest
 import glpk_js_b200 as G
 import helpers as H
 
-_spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(H.HERE, "..", "bench.py"))
+ROOT = os.path.abspath(os.path.join(H.HERE, ".."))
+_spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
 bench = importlib.util.module_from_spec(_spec)
 _spec.loader.exec_module(bench)
 
 
-class _FakeProblem:
-    created = 0
+def test_reference_arm_contract_and_no_product_library():
+    """--impl reference in a fresh interpreter: one JSON line, impl/cpu_baseline/e2e keys, zero copies,
+    and neither the product package nor its .so loaded (the problem comes from the oracle's generator)"""
+    code = ("import runpy, sys, json\n"
+            "sys.argv = ['bench.py', '--impl', 'reference', '--workload', 'c2s', '--steps', '1', '--warmup', '0']\n"
+            "runpy.run_path(%r, run_name='__main__')\n"
+            "maps = open('/proc/self/maps').read()\n"
+            "print(json.dumps({'product_module': any(m.startswith('glpk_js_b200') or m.startswith('glpk.js_b200') for m in sys.modules),"
+            " 'product_so': 'libglpb200' in maps, 'oracle_so': 'libglpo' in maps}))\n" % os.path.join(ROOT, "bench.py"))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 2
+    d, probe = json.loads(lines[0]), json.loads(lines[1])
+    assert probe == {"product_module": False, "product_so": False, "oracle_so": True}
+    assert d["impl"] == "reference" and d["unit"] == "iter/s" and d["value"] > 0 and d["higher_is_better"] is True
+    assert d["e2e"] == {"value": d["value"], "unit": "iter/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] == 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["config"] == bench.config_of(bench.WORKLOADS["c2s"])
 
+
+def test_reference_arm_other_ranks_do_nothing():
+    out = io.StringIO()
+    with contextlib.redirect_stdout(out):
+        bench.run_reference(argparse.Namespace(gpus=2, steps=1, warmup=0), bench.WORKLOADS["c2s"], 1)
+    assert out.getvalue() == ""
+
+
+def test_config_is_identical_in_both_arms_and_names_the_workload():
+    for name, w in bench.WORKLOADS.items():
+        c = bench.config_of(w)
+        assert c["workload"] == w["name"] and set(c) == {"workload"} | set(w["kw"])
+        json.dumps(c)
+    assert bench.WORKLOADS["c3"]["kw"] == dict(m=16384, n=32768, kmin=8, kspan=17, seed=20240601)
+
+
+def test_oracle_generator_equals_product_generator():
+    """bench's CPU legs build their problems with oracle/gen.cpp; the GPU legs with csrc/gen.cpp"""
+    import oracle_lib as O
+    for which, kw in (("packing", dict(m=64, n=96, density=0.2, seed=5)), ("covering", dict(m=128, n=256, kmin=8, kspan=17, seed=7)),
+                      ("mkp", dict(m=30, n=500, seed=20240701))):
+        a, b = O.generate(which, **kw), G.native.generate(which, **kw)
+        for k in a:
+            assert (np.array_equal(a[k], b[k]) if isinstance(a[k], np.ndarray) else a[k] == b[k]), (which, k)
+
+
+def test_roofline_object_from_a_profile():
+    prof = {"k_engine_dual": dict(count=2, ms=0.3, bytes=0.0), "eng_D2_trow": dict(count=8, ms=0.05, bytes=4.0e5),
+            "eng_D4_tcol": dict(count=8, ms=0.10, bytes=3.2e6), "k_beta_rhs": dict(count=2, ms=0.04, bytes=3.0e5),
+            "ref_build": dict(count=1, ms=0.01, bytes=0.0)}
+    roof, detail = bench.roofline_of(prof, "k_engine_dual", 6453.1, "measured", {"dram_bytes_per_iteration": 1.5e5, "source": "x"})
+    assert roof["bound"] == "hbm" and roof["kernel"] == "k_engine_dual" and roof["unit"] == "GB/s"
+    assert abs(roof["achieved"] - 3.6e6 / 0.15e-3 / 1e9) < 1e-9 and abs(roof["frac"] - roof["achieved"] / 6453.1) < 1e-12
+    assert roof["traffic"] == 1.5e5 and roof["top_phase"]["name"] == "D4_tcol"
+    assert abs(roof["bytes_per_launch"] - 3.6e6 / 8) < 1e-9 and abs(roof["us_per_launch"] - 150.0 / 8) < 1e-9
+    assert set(detail["phase_table"]) == {"D2_trow", "D4_tcol"} and "build" in detail["refactor_split_ms"]
+    assert bench.roofline_of({"k_x": dict(count=1, ms=1.0, bytes=1.0)}, "k_engine_dual", 1.0, "", {}) == (None, None)
+    json.dumps(roof)
+
+
+class _FakeProblem:
     def __init__(self, d, device=0, rii=None, sjj=None):
-        type(self).created += 1
-        self.m, self.n = d["m"], d["n"]
-        self.c = dict(iterations=0, refactorizations=0, launches=0, syncs=0, updates=0, k=0, solve_us=0, graph_launches=0)
-        self.prof = False
+        self.m, self.n, self.launches = d["m"], d["n"], 0
 
     def simplex(self, **kw):
-        self.c["launches"] += 40
         return 0
 
     def counters(self):
-        return dict(self.c)
+        return dict(launches=self.launches)
 
-    def set_profile(self, on):
-        self.prof = bool(on)
-
-    def profile(self):
-        return {"k_engine_dual": dict(count=2, ms=0.3, bytes=0.0), "eng_D2_trow": dict(count=8, ms=0.05, bytes=4.0e5),
-                "eng_D3_gemvN_tcol_head": dict(count=8, ms=0.06, bytes=1.0e4), "k_beta_rhs": dict(count=2, ms=0.04, bytes=3.0e5),
-                "ref_build": dict(count=1, ms=0.01, bytes=0.0)}
+    def mip(self):
+        x = np.zeros(self.m + self.n)
+        return dict(mip_stat=5, mip_obj=0.0, mipx=x, nodes=1)
 
     def close(self):
         pass
 
 
-@pytest.fixture
-def stubbed(monkeypatch):
+def test_bnb_block_with_a_scripted_device(monkeypatch):
     import torch
     monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
-    monkeypatch.setattr(torch.cuda, "set_device", lambda *a, **k: None)
     monkeypatch.setattr(G.native, "Problem", _FakeProblem)
 
-    def fake_search(worker, comm, minimize, node_lim=None, **kw):
-        worker.P.c["launches"] += 50 * node_lim
-        worker.P.c["graph_launches"] += 2 * node_lim
-        worker.P.c["syncs"] += 5 * node_lim
-        worker.P.c["iterations"] += 8 * node_lim
-        return dict(total_nodes=node_lim * comm.world, obj=123.0)      # the driver reports the global node count
+    class Comm:
+        rank, world = 0, 1
 
-    monkeypatch.setattr(G.bnb, "sharded_intopt", fake_search)
-    monkeypatch.setattr(bench.ClockSampler, "start", lambda self: None)
-    _FakeProblem.created = 0
-    return bench
+    monkeypatch.setattr(G.bnb, "TensorComm", lambda: Comm())
+    calls = []
 
+    def fake_search(worker, comm, minimize, batch=0, node_lim=None, **kw):
+        calls.append(node_lim)
+        worker.P.launches += 10
+        if node_lim is None:       # the completion run
+            return dict(ret=0, obj=25038.0, holder=0, nodes=1000, total_nodes=1000, rounds=5, exchanges=5, moved_in=0,
+                        moved_out=0, open_left=0)
+        return dict(ret=0, obj=None, holder=None, nodes=node_lim, total_nodes=node_lim, rounds=7, exchanges=7, moved_in=0,
+                    moved_out=0, open_left=99)
 
-def _args(**kw):
-    a = argparse.Namespace(gpus=1, steps=3, warmup=3, bnb_workers=2, no_cpu_baseline=True)
-    a.__dict__.update(kw)
-    return a
-
-
-def test_bnb_leg_embedded_returns_the_block(stubbed):
-    line = stubbed.run_bnb(_args(steps=5, warmup=4), stubbed.WORKLOADS["mkp"], 0, 0, 1, embedded=True)
-    assert line["metric"] == "bnb_nodes_per_sec" and line["unit"] == "nodes/s" and line["n_gpus"] == 1
-    assert line["steps"] == 3 and line["warmup"] == 3                  # capped inside the default line
-    assert line["value"] > 0 and line["config"]["workers_per_gpu"] == 2
-    assert line["gpu_launches"] == 3 * 2 * 50 * 400                     # timed steps x handles x launches
-    assert line["per_node"]["syncs_per_node"] == 5.0 and line["per_node"]["graph_launches_per_node"] == 2.0
-    assert line["roofline"]["kernel"] == "k_engine_dual" and line["roofline"]["bound"] == "hbm"
-    assert line["cpu_baseline"] is None and line["incumbent"] == 123.0
-    json.dumps(line)                                                    # serialisable
-    assert _FakeProblem.created == 6 * 2 + 1                            # (warm-up + steps) x handles + profiling pass
-
-
-def test_bnb_leg_standalone_prints_one_json_line(stubbed):
-    out = io.StringIO()
-    with contextlib.redirect_stdout(out):
-        ret = stubbed.run_bnb(_args(steps=2, warmup=1, no_cpu_baseline=False), stubbed.WORKLOADS["mkp"], 0, 0, 1)
-    assert ret is None
-    lines = [l for l in out.getvalue().splitlines() if l.strip()]
-    assert len(lines) == 1
-    d = json.loads(lines[0])
-    assert d["steps"] == 2 and d["warmup"] == 1 and d["metric"] == "bnb_nodes_per_sec"
-    # the CPU leg is the real oracle: 400 nodes of the same search
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] == 1 and d["cpu_baseline"]["value"] > 0
-
-
-def test_reference_arm_contract():
-    """--impl reference: the oracle timed on a bounded sample; line carries impl, cpu_baseline, e2e with zero copies"""
-    out = io.StringIO()
-    a = argparse.Namespace(gpus=1, steps=1, warmup=0)
-    w = dict(bench.WORKLOADS["c2s"])
-    w["cpu_it_lim"], w["cpu_mid"], w["cpu_mid_lim"] = 60, 80, 20
-    with contextlib.redirect_stdout(out):
-        bench.run_reference(a, w, 0, 1)
-    d = json.loads(out.getvalue().strip())
-    assert d["impl"] == "reference" and d["unit"] == "iter/s" and d["value"] > 0
-    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] == d["value"]
-    with contextlib.redirect_stdout(io.StringIO()) as other:
-        bench.run_reference(a, w, 1, 2)                                 # other ranks: no work, no output
-    assert other.getvalue() == ""
-
-
-def test_default_line_carries_the_bnb_block(stubbed, monkeypatch):
-    """main() end to end with the device stubbed out: one JSON line with every key of the
-    contract, the `bnb` block embedded, and a failure inside that block contained."""
-    import sys
-    import torch
-
-    class FakeLP(_FakeProblem):
-        def __init__(self, d, device=0, rii=None, sjj=None):
-            super().__init__(d, device, rii, sjj)
-            self.it = 0
-
-        def std_basis(self):
-            return 0
-
-        def simplex(self, meth=None, it_lim=None, **kw):
-            self.it += 100
-            self.c.update(launches=self.c["launches"] + 30, solve_us=50000, refactorizations=3, k=17)
-            return 0
-
-        def solution(self):
-            return dict(it_cnt=self.it, status=5, obj=1.5, stat=np.zeros(self.m + self.n, np.int32))
-
-        def profile(self):
-            return {"k_engine_primal": dict(count=1, ms=40.0, bytes=0.0), "eng_PA_tcol_head": dict(count=100, ms=10.0, bytes=5.0e7),
-                    "eng_PE_trow_svec": dict(count=100, ms=20.0, bytes=2.0e9), "k_refactor": dict(count=3, ms=5.0, bytes=1.0e8),
-                    "ref_build": dict(count=3, ms=0.5, bytes=0.0)}
-
-    real_empty = torch.empty
-    monkeypatch.setattr(torch, "empty", lambda *a, **k: real_empty(16, dtype=k.get("dtype", torch.uint8)))
-    monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self: self)
-    monkeypatch.setattr(G.native, "Problem", FakeLP)
-
-    real_lib = G.native.load()
-
-    class FakeLib:
-        """the real library (generators, host code) that claims one device"""
-        def __getattr__(self, name):
-            return getattr(real_lib, name)
-
-        @staticmethod
-        def glpb_device_count():
-            return 1
-    fake_lib = FakeLib()
-    monkeypatch.setattr(G.native, "load", lambda: fake_lib)
-    monkeypatch.setattr(bench.ClockSampler, "stop", lambda self: {"sm_mhz": 1965.0, "sm_max_mhz": 1965.0, "samples": 3, "reasons": []})
-    for env in ("RANK", "LOCAL_RANK", "WORLD_SIZE"):
-        monkeypatch.delenv(env, raising=False)
-
-    def run(extra=()):
-        monkeypatch.setattr(sys, "argv", ["bench.py", "--no-c3", "--no-cpu-baseline", "--steps", "2", "--warmup", "3",
-                                          "--bnb-workers", "2", *extra])
-        out = io.StringIO()
-        with contextlib.redirect_stdout(out):
-            bench.main()
-        lines = [l for l in out.getvalue().splitlines() if l.strip()]
-        assert len(lines) == 1
-        return json.loads(lines[0])
-
-    d = run()
-    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
-                "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline"):
-        assert key in d, key
-    assert d["metric"] == "simplex_iterations_per_sec" and d["dtype"] == "f64" and d["vs_baseline"] is None
-    assert d["steps"] == 2 and d["warmup"] == 3 and d["gpu_launches"] > 0 and "workload" in d["config"]
-    assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["value"] > 0
-    assert d["roofline"]["kernel"] == "k_engine_primal" and d["roofline"]["traffic_evidence"]["file"].startswith("profiles/")
-    assert 0 < d["roofline"]["frac"] < 1 and d["roofline"]["unit"] == "GB/s"
-    assert d["bnb"]["metric"] == "bnb_nodes_per_sec" and d["bnb"]["steps"] == 2 and d["bnb"]["value"] > 0
-    assert run(["--no-bnb"])["bnb"] is None
-    # a failure inside the block is reported there; the headline line survives
-    monkeypatch.setattr(G.bnb, "sharded_intopt", lambda *a, **k: (_ for _ in ()).throw(RuntimeError("boom")))
-    d = run(["--bnb-workers", "1"])
-    assert "boom" in d["bnb"]["error"] and d["value"] > 0
-
-
-def test_bnb_leg_worker_failure_is_raised_not_hung(stubbed, monkeypatch):
-    """a worker thread that dies aborts the group's barrier and the leg raises in the main thread"""
-    def search(worker, comm, minimize, node_lim=None, **kw):
-        if comm.lr == 1:
-            raise RuntimeError("worker 1 died")
-        comm.g.barrier.wait(timeout=20)          # what the real driver does between slices
-        return dict(total_nodes=node_lim, obj=0.0)
-
-    monkeypatch.setattr(G.bnb, "sharded_intopt", search)
-    with pytest.raises(RuntimeError, match="worker failed"):
-        stubbed.run_bnb(_args(steps=1, warmup=0, bnb_workers=3), stubbed.WORKLOADS["mkp"], 0, 0, 1, embedded=True)
+    monkeypatch.setattr(G.bnb, "sharded_bnb_batched", fake_search)
+    args = argparse.Namespace(bnb_nodes=1234, bnb_batch=0)
+    blk = bench.bnb_block(args, 0, 0, 1, 3, 2)
+    assert blk["metric"] == "bnb_nodes_per_sec" and blk["unit"] == "nodes/s" and blk["value"] > 0 and blk["n_gpus"] == 1
+    assert blk["steps"] == 3 and blk["warmup"] == 2 and blk["nodes_per_step"] == 1234 and blk["gpu_launches"] == 30
+    assert calls == [1234] * 5 + [None]
+    oc = blk["optimum_check"]
+    assert oc["optimum"] == 25038.0 and oc["expected"] == pytest.approx(25038.0) and blk["optimum_ok"] is True
+    json.dumps(blk)

@@ -150,3 +150,56 @@ def test_migration_between_two_pools_keeps_the_optimum():
     assert moved > 0
     objs = [x["obj"] for x in (A.incumbent(), B.incumbent()) if x["have_sol"]]
     assert objs and max(objs) == omp["mip_obj"]
+
+
+# ---- the sharding protocol of glpk_js_b200.bnb.sharded_bnb_batched over the emulated engine ----
+def _mkp_case():
+    dn = O.generate("mkp", m=10, n=40, seed=3)
+    _, omp, root = oracle_root_and_mip(dn)
+    return dn, root["stat"], omp["mip_obj"]
+
+
+def test_sharded_batched_single_rank_and_node_limit():
+    import glpk_js_b200 as G
+    dn, stat, want = _mkp_case()
+    w = NE.EmulWorker(dn, stat)
+    res = G.bnb.sharded_bnb_batched(w, G.bnb.TensorComm(), minimize=False, batch=16, slab_nodes=32768)
+    assert res["ret"] == 0 and res["obj"] == want and res["holder"] == 0 and res["open_left"] == 0
+    assert w.final["have_sol"] and w.final["obj"] == want
+    w2 = NE.EmulWorker(dn, stat)
+    res2 = G.bnb.sharded_bnb_batched(w2, G.bnb.TensorComm(), minimize=False, batch=16, slab_nodes=32768, node_lim=200)
+    assert res2["ret"] == 0 and 200 <= res2["total_nodes"] <= 200 + 16 * 3 and res2["open_left"] > 0
+
+
+def _gloo_batched_rank(rank, world, port, q):
+    import torch.distributed as dist
+    import glpk_js_b200 as G
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    dn, stat, want = _mkp_case()
+    w = NE.EmulWorker(dn, stat)
+    res = G.bnb.sharded_bnb_batched(w, G.bnb.TensorComm(), minimize=False, batch=8, slab_nodes=32768, max_ship=16)
+    q.put((rank, res["obj"], res["ret"], res["holder"], res["nodes"], res["moved_in"], res["moved_out"], res["open_left"],
+           w.final["have_sol"], w.final["obj"], want))
+    dist.destroy_process_group()
+
+
+def test_sharded_batched_over_gloo_world_size_2():
+    """two processes, torch.distributed gloo: rank 1 starts empty and is fed by migration through the
+    fused all-gather; both end with the serial optimum and agree on who holds the solution"""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 23500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gloo_batched_rank, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    out = sorted(q.get(timeout=300) for _ in range(2))
+    [p.join(30) for p in procs]
+    want = out[0][10]
+    assert all(o[1] == want and o[2] == 0 and o[7] == 0 for o in out), out
+    assert out[0][3] == out[1][3] and out[0][3] in (0, 1)
+    holder = out[0][3]
+    assert out[holder][8] and out[holder][9] == want            # the holder really has the solution vector
+    assert out[1][5] > 0 and out[0][6] > 0                     # nodes moved from rank 0 to rank 1
+    assert out[0][4] > 0 and out[1][4] > 0                     # both ranks solved node LPs
