@@ -113,13 +113,16 @@ extern "C" int glpb_bnb_import_nodes(glpb_prob *P, const void *dev_buf, int coun
 
 /* out[0] node LPs solved, [1] nodes processed, [2] rounds (= launches),
    [3] dual simplex iterations, [4] basis inversions, [5] open nodes,
-   [6] bytes of shared memory per CTA, [7] matrix resident in shared memory */
+   [6] bytes of shared memory per CTA, [7] matrix resident in shared memory,
+   [8..13] SM cycles summed over the nodes (thread 0 of every CTA): preprocessing, basis
+   inversions, fresh bbar/cbar, simplex iterations, integrality + branching, node state I/O */
 extern "C" int glpb_bnb_stats(glpb_prob *P, long *out, int count)
 {
     if (!P || !P->bnb || !out) return GLPB_ESTATE;
     glpb_bnb &T = *P->bnb;
-    long v[8] = {T.solved, T.tasks_done, T.rounds, T.iters, T.refacs, (long)T.open_count(), (long)T.smem_bytes, (long)T.np.a_in_smem};
-    for (int i = 0; i < count && i < 8; i++) out[i] = v[i];
+    long v[14] = {T.solved, T.tasks_done, T.rounds, T.iters, T.refacs, (long)T.open_count(), (long)T.smem_bytes, (long)T.np.a_in_smem,
+                  (long)T.cyc[0], (long)T.cyc[1], (long)T.cyc[2], (long)T.cyc[3], (long)T.cyc[4], (long)T.cyc[5]};
+    for (int i = 0; i < count && i < 14; i++) out[i] = v[i];
     return 0;
 }
 

@@ -31,7 +31,7 @@ __global__ void __launch_bounds__(NE_NT, 1)
 k_bnb_nodes(NeProb P, const NeTask *tasks, NeResult *res, double *xbuf)
 {
     extern __shared__ __align__(16) unsigned char ne_smem[];
-    NeT t = {(int)threadIdx.x, (int)blockDim.x, (int)(threadIdx.x & 31), (int)(threadIdx.x >> 5), (int)(blockDim.x >> 5), 32};
+    NeT t = {(int)threadIdx.x, (int)blockDim.x, (int)(threadIdx.x & 31), (int)(threadIdx.x >> 5), (int)(blockDim.x >> 5), 32, 0};
     NeS S;
     ne_carve(S, ne_smem, P.m, P.n, P.ldb);
     if (P.a_in_smem) {
@@ -75,6 +75,7 @@ struct glpb_bnb {
     double mip_obj = 0.0;
     std::vector<double> mipx;
     long solved = 0, tasks_done = 0, rounds = 0, iters = 0, refacs = 0;
+    long long cyc[6] = {0, 0, 0, 0, 0, 0};
     double tm_beg = 0.0;
     int fail_code = 0;
 
@@ -93,7 +94,7 @@ struct glpb_bnb {
     {
         std::vector<unsigned char> buf(ne_state_bytes(m, n, np.ldb) + 64);
         for (int b = 0; b < nt; b++) {
-            NeT t = {0, 1, 0, 0, 1, 1};
+            NeT t = {0, 1, 0, 0, 1, 1, 0};
             NeS S;
             ne_carve(S, buf.data(), m, n, np.ldb);
             S.A = np.As;
@@ -119,7 +120,7 @@ struct glpb_bnb {
     ~glpb_bnb()
     {
         dfree(d_As); dfree(d_cw); dfree(d_obj); dfree(d_ucoef); dfree(d_rii); dfree(d_sjj); dfree(d_kind);
-        dfree(np.slab_lb); dfree(np.slab_ub); dfree(np.slab_type); dfree(np.slab_stat);
+        dfree(np.slab_lb); dfree(np.slab_ub); dfree(np.slab_type); dfree(np.slab_stat); dfree(np.slab_bi); dfree(np.slab_upd); dfree(np.slab_head);
         dfree(d_x); dfree(d_inc); dfree(d_inc_have); dfree(d_tasks); dfree(d_res);
     }
 
@@ -149,6 +150,9 @@ struct glpb_bnb {
         double zeta = (P->dir == GLP_MIN ? +1.0 : -1.0) / cmax;
         if (fabs(zeta) < 1.0) zeta *= 1000.0;
         np.zeta = zeta;
+        np.unit_scale = 1;
+        for (int i = 0; i < m; i++) if (P->h_rii[i] != 1.0) np.unit_scale = 0;
+        for (int j = 0; j < n; j++) if (P->h_sjj[j] != 1.0) np.unit_scale = 0;
         for (int j = 0; j < n; j++) cw[j] = ob[j] * zeta;
         np.tol_bnd = 1e-7; np.tol_dj = 1e-7; np.tol_piv = 1e-10;       /* glp_init_smcp defaults, lib/glpios01.js:874-891 */
         np.tol_int = parm.tol_int; np.tol_obj = parm.tol_obj;
@@ -171,6 +175,7 @@ struct glpb_bnb {
         bad |= dalloc((void **)&d_kind, n);
         bad |= dalloc((void **)&np.slab_lb, (size_t)cap * mn * 8); bad |= dalloc((void **)&np.slab_ub, (size_t)cap * mn * 8);
         bad |= dalloc((void **)&np.slab_type, (size_t)cap * mn); bad |= dalloc((void **)&np.slab_stat, (size_t)cap * mn);
+        bad |= dalloc((void **)&np.slab_bi, (size_t)cap * m * np.ldb * 8); bad |= dalloc((void **)&np.slab_upd, (size_t)cap * 4); bad |= dalloc((void **)&np.slab_head, (size_t)cap * m * 4);
         bad |= dalloc((void **)&d_x, (size_t)batch * mn * 8);
         bad |= dalloc((void **)&d_inc, 16); bad |= dalloc((void **)&d_inc_have, 16);
         bad |= dalloc((void **)&d_tasks, batch * sizeof(NeTask)); bad |= dalloc((void **)&d_res, batch * sizeof(NeResult));
@@ -191,10 +196,18 @@ struct glpb_bnb {
         for (int k = 0; k < mn; k++) { ty[k] = (signed char)P->h_type[k]; st[k] = (signed char)P->h_stat[k]; }
         h2d(np.slab_lb + (size_t)root * mn, P->h_lb.data(), mn * 8); h2d(np.slab_ub + (size_t)root * mn, P->h_ub.data(), mn * 8);
         h2d(np.slab_type + (size_t)root * mn, ty.data(), mn); h2d(np.slab_stat + (size_t)root * mn, st.data(), mn);
+        set_no_inverse(root);
         if (dsync()) { glpb_set_error("branch-and-bound: upload failed"); return GLPB_ENODEV; }
         double inf = (P->dir == GLP_MIN ? -DBL_MAX : +DBL_MAX);
         insert(BnbOpen{root, 0, inf, inf, 0.0, 0});
         return 0;
+    }
+
+    /* the node in `slot` carries no basis inverse (root, imported nodes): the engine inverts afresh */
+    int set_no_inverse(int slot)
+    {
+        static const int minus1 = -1;
+        return h2d(np.slab_upd + slot, &minus1, 4);
     }
 
     void insert(BnbOpen nd)
@@ -324,6 +337,7 @@ struct glpb_bnb {
             const NeResult &r = h_res[b];
             const NeTask &tk = h_tasks[b];
             solved += r.solves; iters += r.iters; refacs += r.refacs; tasks_done++;
+            for (int c = 0; c < 6; c++) cyc[c] += r.cyc[c];
             if (r.code == NE_R_BRANCH) {
                 BnbOpen dn{tk.node, tk.level + 1, r.bound, r.dn_lp, r.ii_sum, 0};
                 BnbOpen up{tk.child, tk.level + 1, r.bound, r.up_lp, r.ii_sum, 0};
@@ -391,6 +405,7 @@ struct glpb_bnb {
             bad |= d2d(np.slab_ub + (size_t)slot * mn, rec + 32 + (size_t)mn * 8, (size_t)mn * 8);
             bad |= d2d(np.slab_type + (size_t)slot * mn, rec + 32 + (size_t)mn * 16, mn);
             bad |= d2d(np.slab_stat + (size_t)slot * mn, rec + 32 + (size_t)mn * 17, mn);
+            bad |= set_no_inverse(slot);
             if (bad) return GLPB_ENODEV;
             insert(BnbOpen{slot, (int)hdr[2], hdr[0], hdr[1], hdr[3], 0});
         }

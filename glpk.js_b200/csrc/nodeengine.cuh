@@ -97,9 +97,13 @@ struct NeProb {
     const signed char *kind;    /* [n] 1 = integer column                                */
     double tol_bnd, tol_dj, tol_piv, tol_int, tol_obj;
     int pp_tech, br_tech, it_max, refac_period;
+    int unit_scale, pad1;       /* 1: rii = sjj = 1 (no division in the preprocessing) */
     /* node slab */
     double *slab_lb, *slab_ub;          /* [cap][mn]  */
     signed char *slab_type, *slab_stat; /* [cap][mn]  */
+    double *slab_bi;                    /* [cap][m*ldb] inverse of the node's starting basis (= the parent's final one) */
+    int *slab_upd;                      /* [cap] updates that inverse has seen since it was computed afresh; -1: none stored */
+    int *slab_head;                     /* [cap][m] basis header (variable per position) the stored inverse belongs to */
     /* incumbent shared by the CTAs of a launch: inc[0] objective, inc_have flag */
     double *inc;
     int *inc_have;
@@ -116,9 +120,19 @@ struct NeResult {
     double obj, bound, ii_sum;
     double dn_lp, dn_bnd, up_lp, up_bnd;
     double x_jv;
+    long long cyc[6];    /* SM cycles of thread 0: preprocessing, basis set-up, fresh vectors, iterations, branching, state I/O */
 };
 
-struct NeT { int tid, nt, lane, warp, nwarps, wsize; };
+struct NeT { int tid, nt, lane, warp, nwarps, wsize; mutable int rc; };
+
+NE_D long long ne_clock()
+{
+#ifdef NE_EMUL
+    return 0;
+#else
+    return clock64();
+#endif
+}
 
 /* ------------------------------------------------------------------ */
 /* reductions                                                         */
@@ -159,12 +173,26 @@ template <class K, class Op> NE_D K ne_block_reduce(const NeT &t, K v, Op op, K 
         K o = ne_shfl_down(v, off);
         if (t.lane + off < 32) v = op(v, o);
     }
-    if (t.lane == 0) scratch[t.warp] = v;
+    /* two scratch halves used alternately: a half is rewritten only after the barrier of
+       the next reduction, which every thread passes after it has read this one */
+    K *buf = (K *)((unsigned char *)scratch + (t.rc & 1) * 16 * 32);
+    t.rc++;
+    if (t.lane == 0) buf[t.warp] = v;
     __syncthreads();
-    K r = scratch[0];
-    for (int w = 1; w < t.nwarps; w++) r = op(r, scratch[w]);
-    __syncthreads();
+    K r = buf[0];
+    for (int w = 1; w < t.nwarps; w++) r = op(r, buf[w]);
     return r;
+#endif
+}
+
+/* block-wide OR of a predicate: one barrier */
+NE_D int ne_block_or(const NeT &t, int v)
+{
+#ifdef NE_EMUL
+    (void)t;
+    return v;
+#else
+    return __syncthreads_or(v);
 #endif
 }
 
@@ -207,7 +235,7 @@ struct NeS {
     signed char *nstat;         /* [n] status by non-basic position                 */
     signed char *flag;          /* [max(n, m+1)] scratch flags                      */
     signed char *mark, *pass;   /* [m+1] */
-    NeKey *red;                 /* [nwarps] reduction scratch                       */
+    NeKey *red;                 /* 2 x 16 x 32 bytes: reduction scratch, two halves (<= 16 warps, keys <= 32 B) */
     double *sc;                 /* [16] broadcast scalars                           */
     int *si;                    /* [16] broadcast ints                              */
 };
@@ -231,7 +259,7 @@ NE_HD size_t ne_state_bytes(int m, int n, int ldb)
     b += ne_align((size_t)n);
     b += ne_align((size_t)(n > m + 1 ? n : m + 1));
     b += 2 * ne_align((size_t)(m + 1));
-    b += ne_align(32 * sizeof(NeKey));
+    b += ne_align(2 * 16 * 32);
     b += ne_align(16 * 8) + ne_align(16 * 4);
     return b;
 }
@@ -257,7 +285,7 @@ NE_D void ne_carve(NeS &S, unsigned char *p, int m, int n, int ldb)
     S.nstat = (signed char *)take(n);
     S.flag = (signed char *)take(n > m + 1 ? n : m + 1);
     S.mark = (signed char *)take(m + 1); S.pass = (signed char *)take(m + 1);
-    S.red = (NeKey *)take(32 * sizeof(NeKey));
+    S.red = (NeKey *)take(2 * 16 * 32);
     S.sc = (double *)take(16 * 8); S.si = (int *)take(16 * 4);
 }
 
@@ -340,16 +368,17 @@ NE_D int ne_preprocess(const NeT &t, const NeProb &P, NeS &S, int max_pass, int 
     while (size > 0) {
         const int i = S.list[size - 1];
         size--;
-        NE_SYNC();                       /* everybody has read list[size] */
-        if (t.tid == 0) { S.mark[i] = 0; S.pass[i]++; }
+        if (t.tid == 0) { S.mark[i] = 0; S.pass[i]++; }       /* only thread 0 reads mark / pass */
         const double Li0 = L[i], Ui0 = U[i];
-        if (Li0 == -DBL_MAX && Ui0 == +DBL_MAX) { NE_SYNC(); continue; }
+        if (Li0 == -DBL_MAX && Ui0 == +DBL_MAX) continue;
+        for (int r = t.tid; r <= m; r += t.nt) S.flag[r] = 0;   /* visible after the barrier of the reduction below */
         /* prepare_row_info: sums over the finite terms, number and first
            index of the infinite ones */
         NeRowAcc acc = {0.0, 0.0, 0, 0, INT_MAX, INT_MAX};
         for (int j = t.tid; j < n; j += t.nt) {
-            double a = (i == 0) ? P.ucoef[j] : S.A[(size_t)(i - 1) * P.lda + j] / (P.rii[i - 1] * P.sjj[j]);
+            double a = (i == 0) ? P.ucoef[j] : S.A[(size_t)(i - 1) * P.lda + j];
             if (a == 0.0) continue;
+            if (i != 0 && !P.unit_scale) a /= (P.rii[i - 1] * P.sjj[j]);
             double bmin = a > 0.0 ? l[j] : u[j], bmax = a > 0.0 ? u[j] : l[j];
             if (bmin == (a > 0.0 ? -DBL_MAX : +DBL_MAX)) { acc.nmin++; if (j < acc.jmin) acc.jmin = j; }
             else acc.fmin += a * bmin;
@@ -371,14 +400,13 @@ NE_D int ne_preprocess(const NeT &t, const NeProb &P, NeS &S, int max_pass, int 
             if (Ui != +DBL_MAX && UU < Ui + 1e-12 * (1.0 + fabs(Ui))) Ui = +DBL_MAX;
         }
         if (t.tid == 0) { L[i] = Li; U[i] = Ui; }
-        for (int r = t.tid; r <= m; r += t.nt) S.flag[r] = 0;
-        NE_SYNC();
-        if (Li == -DBL_MAX && Ui == +DBL_MAX) continue;
+        if (Li == -DBL_MAX && Ui == +DBL_MAX) { NE_SYNC(); continue; }
         /* columns of the row: check_col_bounds + check_efficiency */
         int bad = 0;
         for (int j = t.tid; j < n; j += t.nt) {
-            double a = (i == 0) ? P.ucoef[j] : S.A[(size_t)(i - 1) * P.lda + j] / (P.rii[i - 1] * P.sjj[j]);
+            double a = (i == 0) ? P.ucoef[j] : S.A[(size_t)(i - 1) * P.lda + j];
             if (a == 0.0) continue;
+            if (i != 0 && !P.unit_scale) a /= (P.rii[i - 1] * P.sjj[j]);
             const double lj0 = l[j], uj0 = u[j];
             double ilb, iub, ll, uu;
             if (Li == -DBL_MAX || f_max == +DBL_MAX) ilb = -DBL_MAX;
@@ -426,7 +454,7 @@ NE_D int ne_preprocess(const NeT &t, const NeProb &P, NeS &S, int max_pass, int 
                 for (int r = 0; r < m; r++)
                     if (S.A[(size_t)r * P.lda + j] != 0.0) S.flag[r + 1] = 1;   /* benign race: all write 1 */
         }
-        bad = ne_block_reduce(t, bad, NeOrI(), (int *)S.red);
+        bad = ne_block_or(t, bad);
         if (bad) { infeasible = 1; break; }
         /* rows touched by an efficient change go back on the list (ascending) */
         if (t.tid == 0) {
@@ -440,8 +468,7 @@ NE_D int ne_preprocess(const NeT &t, const NeProb &P, NeS &S, int max_pass, int 
             S.si[0] = sz;
         }
         NE_SYNC();
-        size = S.si[0];
-        NE_SYNC();
+        size = S.si[0];          /* rewritten only after the barriers of the next row */
     }
     NE_SYNC();
     if (infeasible) return 1;
@@ -474,21 +501,43 @@ NE_D int ne_preprocess(const NeT &t, const NeProb &P, NeS &S, int max_pass, int 
    (glp_factorize, lib/glpapi12.js:44-67), non-basic rows then columns
    (init_csa, lib/glpspx02.js:160-175).  Returns 0, or 1 if the number of
    basic variables is not m (GLP_EBADB). */
-NE_D int ne_build_head(const NeT &t, const NeProb &P, NeS &S)
+NE_D int ne_build_head(const NeT &t, const NeProb &P, NeS &S, int keep_basic_order)
 {
     const int m = P.m, n = P.n, mn = m + n;
-    if (t.tid == 0) {
-        int nb = 0, nn = 0;
-        for (int k = 0; k < mn; k++) {
-            if (S.kstat[k] == NE_BS) { if (nb < m) { S.head[nb] = k; S.bind[k] = nb; } nb++; }
-            else { if (nn < n) { S.head[m + nn] = k; S.bind[k] = m + nn; S.nstat[nn] = S.kstat[k]; } nn++; }
-        }
-        S.si[0] = (nb == m) ? 0 : 1;
+    /* keep_basic_order: S.head[0..m) already lists the basic variables in the order the
+       inherited inverse was built for (the statuses must agree with it) */
+    if (keep_basic_order) {
+        int bad = 0;
+        for (int i = t.tid; i < m; i += t.nt) { int k = S.head[i]; if (k < 0 || k >= mn || S.kstat[k] != NE_BS) bad = 1; else S.bind[k] = i; }
+        if (ne_block_or(t, bad)) return 1;
     }
-    NE_SYNC();
-    int bad = S.si[0];
-    NE_SYNC();
-    return bad;
+#ifdef NE_EMUL
+    int nb = 0, nn = 0;
+    for (int k = 0; k < mn; k++) {
+        if (S.kstat[k] == NE_BS) { if (!keep_basic_order && nb < m) { S.head[nb] = k; S.bind[k] = nb; } nb++; }
+        else { if (nn < n) { S.head[m + nn] = k; S.bind[k] = m + nn; S.nstat[nn] = S.kstat[k]; } nn++; }
+    }
+    return (nb == m) ? 0 : 1;
+#else
+    if (t.warp == 0) {           /* ordered compaction of both lists by ballots */
+        int nb = 0, nn = 0;
+        for (int base = 0; base < mn; base += 32) {
+            const int k = base + t.lane;
+            const int st = (k < mn) ? S.kstat[k] : 0;
+            const unsigned mb = __ballot_sync(0xffffffffu, st == NE_BS);
+            const unsigned mnb = __ballot_sync(0xffffffffu, st != NE_BS && k < mn);
+            const unsigned lt = (1u << t.lane) - 1u;
+            if (k < mn) {
+                if (st == NE_BS) { int o = nb + __popc(mb & lt); if (o < m && !keep_basic_order) { S.head[o] = k; S.bind[k] = o; } }
+                else { int o = nn + __popc(mnb & lt); if (o < n) { S.head[m + o] = k; S.bind[k] = m + o; S.nstat[o] = (signed char)st; } }
+            }
+            nb += __popc(mb); nn += __popc(mnb);
+        }
+        if (t.lane == 0) S.si[0] = (nb == m) ? 0 : 1;
+    }
+    __syncthreads();
+    return S.si[0];              /* si[0] is next written after at least one more barrier */
+#endif
 }
 
 /* scaled working bounds from the node bounds (lib/glpspx02.js:112-131) */
@@ -680,7 +729,7 @@ NE_D int ne_check_feas(const NeT &t, const NeProb &P, NeS &S, double tol_dj)
         if (S.cbar[j] < -tol_dj && (ty == NE_LO || ty == NE_FR)) bad = 1;
         if (S.cbar[j] > +tol_dj && (ty == NE_UP || ty == NE_FR)) bad = 1;
     }
-    return ne_block_reduce(t, bad, NeOrI(), (int *)S.red);
+    return ne_block_or(t, bad);
 }
 
 /* check_stab: lib/glpspx02.js:1410-1422 */
@@ -692,7 +741,7 @@ NE_D int ne_check_stab(const NeT &t, const NeProb &P, NeS &S, double tol_dj)
         if (S.cbar[j] < -tol_dj && (st == NE_NL || st == NE_NF)) bad = 1;
         if (S.cbar[j] > +tol_dj && (st == NE_NU || st == NE_NF)) bad = 1;
     }
-    return ne_block_reduce(t, bad, NeOrI(), (int *)S.red);
+    return ne_block_or(t, bad);
 }
 
 /* set_aux_bnds: lib/glpspx02.js:1317-1359 */
@@ -793,22 +842,31 @@ struct NeLpOut { int ret, pbs, dbs, iters, refacs; double obj; };
    lib/glpios01.js:866-910, lib/glpapi06.js:3-39, lib/glpspx02.js:1592-1966.
    The primal fall-back of solve_lp is not built here: a failing dual solve
    ends the task with NE_R_FAIL. */
-NE_D void ne_solve_lp(const NeT &t, const NeProb &P, NeS &S, double obj_ll, double obj_ul, NeLpOut &out)
+NE_D void ne_solve_lp(const NeT &t, const NeProb &P, NeS &S, double obj_ll, double obj_ul, NeLpOut &out,
+                      int &bi_upd, long long *cyc)
 {
     const int m = P.m, n = P.n, ldb = P.ldb;
-    int binv_st = 0, bbar_st = 0, cbar_st = 0, rigorous = 0, phase = 0, refct = 0, upd = 0;
+    /* bi_upd >= 0: S.Bi already holds the inverse of this basis (the parent's final one, or
+       the one the previous solve of this node ended with) after bi_upd updates: the solve
+       starts like the reference's with a valid factorisation (binv_st = 2) */
+    int binv_st = (bi_upd >= 0) ? 2 : 0, bbar_st = 0, cbar_st = 0, rigorous = 0, phase = 0, refct = 0;
+    int upd = (bi_upd >= 0) ? bi_upd : 0;
     int it = 0, refacs = 0;
     double objt = 0.0;
+    long long c0 = ne_clock();
     out.ret = 0; out.pbs = out.dbs = NE_UNDEF; out.obj = 0.0;
-    if (ne_build_head(t, P, S)) { out.ret = NE_EFAIL; out.iters = 0; out.refacs = 0; return; }
+    bi_upd = -1;
+    if (ne_build_head(t, P, S, binv_st == 2)) { out.ret = NE_EFAIL; out.iters = 0; out.refacs = 0; return; }
     ne_orig_bounds(t, P, S);
     for (int i = t.tid; i < m; i += t.nt) S.gamma[i] = 1.0;
     NE_SYNC();
     for (;;) {
         if (binv_st == 0) {
+            long long c1 = ne_clock();
             if (ne_invert(t, P, S)) { NE_TRACE("  lp: singular basis\n"); out.ret = NE_EFAIL; break; }
             refacs++;
             binv_st = 1; bbar_st = cbar_st = 0; upd = 0;
+            if (cyc) { long long c2 = ne_clock(); cyc[1] += c2 - c1; c0 += c2 - c1; }
         }
         if (cbar_st == 0) {
             ne_eval_cbar(t, P, S);
@@ -853,6 +911,7 @@ NE_D void ne_solve_lp(const NeT &t, const NeProb &P, NeS &S, double obj_ll, doub
             break;
         }
         if (it >= P.it_max) { out.ret = NE_EITLIM; break; }
+        if (cyc && it == 0 && bbar_st == 1 && cbar_st == 1) { long long c2 = ne_clock(); cyc[2] += c2 - c0; c0 = c2; }
         NE_TRACE("  lp: it %d phase %d obj %.10g st %d%d%d\n", it, phase, objt, binv_st, bbar_st, cbar_st);
         /* chuzr: lib/glpspx02.js:572-625 */
         NeKey kp = {0.0, 0.0, INT_MAX, 0};
@@ -1093,8 +1152,10 @@ NE_D void ne_solve_lp(const NeT &t, const NeProb &P, NeS &S, double obj_ll, doub
     if (out.ret != NE_EFAIL && out.ret != NE_EITLIM) {
         out.obj = ne_eval_obj(t, P, S);
         ne_store_sol(t, P, S);
+        if (binv_st != 0) bi_upd = upd;       /* S.Bi is the inverse of the final basis */
     }
     out.iters = it; out.refacs = refacs;
+    if (cyc) cyc[3] += ne_clock() - c0;
 }
 
 /* ------------------------------------------------------------------ */
@@ -1345,12 +1406,23 @@ NE_D void ne_store_state(const NeT &t, const NeProb &P, const NeS &S, int slot)
 NE_D void ne_process_node(const NeT &t, const NeProb &P, NeS &S, const NeTask &task, NeResult &res, double *xout)
 {
     const int m = P.m, n = P.n, mn = m + n;
+    const long long ck0 = ne_clock();
     {
         const double *lb = P.slab_lb + (size_t)task.node * mn, *ub = P.slab_ub + (size_t)task.node * mn;
         const signed char *ty = P.slab_type + (size_t)task.node * mn, *st = P.slab_stat + (size_t)task.node * mn;
         for (int k = t.tid; k < mn; k += t.nt) { S.lb[k] = lb[k]; S.ub[k] = ub[k]; S.type[k] = ty[k]; S.kstat[k] = st[k]; }
     }
+    int bi_upd = P.slab_upd[task.node];
+    if (bi_upd >= 0) {
+        const double *bi = P.slab_bi + (size_t)task.node * m * P.ldb;
+        for (int e = t.tid; e < m * P.ldb; e += t.nt) S.Bi[e] = bi[e];
+        const int *hd = P.slab_head + (size_t)task.node * m;
+        for (int i = t.tid; i < m; i += t.nt) S.head[i] = hd[i];
+    }
     NE_SYNC();
+    long long cyc[6] = {0, 0, 0, 0, 0, 0};
+    long long ck = ne_clock();
+    cyc[5] += ck - ck0;
     double bound = task.bound, lp_obj = task.lp_obj;
     int code = 0, jv = -1, next = NE_NO_BRNCH, ii_cnt = 0, iters = 0, solves = 0, refacs = 0, lpret = 0;
     double ii_sum = 0.0, dn_lp = 0.0, dn_bnd = 0.0, up_lp = 0.0, up_bnd = 0.0, x_jv = 0.0, obj_val = 0.0;
@@ -1358,15 +1430,19 @@ NE_D void ne_process_node(const NeT &t, const NeProb &P, NeS &S, const NeTask &t
     for (;;) {
         int have_inc; double mip_obj;
         ne_read_incumbent(t, P, S, have_inc, mip_obj);
+        ck = ne_clock();
         if (P.pp_tech == NE_PP_ALL || (P.pp_tech == NE_PP_ROOT && task.level == 0)) {
-            if (ne_preprocess(t, P, S, task.level == 0 ? 100 : 10, have_inc, mip_obj)) { code = NE_R_FATHOM; break; }
+            int inf_ = ne_preprocess(t, P, S, task.level == 0 ? 100 : 10, have_inc, mip_obj);
+            cyc[0] += ne_clock() - ck;
+            if (inf_) { code = NE_R_FATHOM; break; }
         }
         if (!ne_is_hopeful(P, have_inc, mip_obj, bound)) { code = NE_R_FATHOM; break; }
         /* ios_solve_node */
         NeLpOut lp;
         double obj_ll = -DBL_MAX, obj_ul = +DBL_MAX;
         if (have_inc) { if (P.dir == NE_MIN) obj_ul = mip_obj; else obj_ll = mip_obj; }
-        ne_solve_lp(t, P, S, obj_ll, obj_ul, lp);
+        ne_solve_lp(t, P, S, obj_ll, obj_ul, lp, bi_upd, cyc);
+        ck = ne_clock();
         NE_TRACE("node %d lvl %d: lp ret %d pbs %d dbs %d obj %.10g it %d\n", task.node, task.level, lp.ret, lp.pbs, lp.dbs, lp.obj, lp.iters);
         solves++; iters += lp.iters; refacs += lp.refacs; lpret = lp.ret;
         if (!(lp.ret == 0 || lp.ret == NE_EOBJLL || lp.ret == NE_EOBJUL)) { code = NE_R_FAIL; break; }
@@ -1381,29 +1457,47 @@ NE_D void ne_process_node(const NeT &t, const NeProb &P, NeS &S, const NeTask &t
         improve(bound, ne_round_bound(P, rb, obj_val));
         if (!ne_is_hopeful(P, have_inc, mip_obj, bound)) { code = NE_R_FATHOM; break; }
         /* check_integrality: lib/glpios03.js:56-116 */
-        NeIntAcc ia = {0, 0, 0.0};
-        for (int j = t.tid; j < n; j += t.nt) {
-            int k = m + j;
-            S.flag[j] = 0;
-            if (!P.kind[j] || S.kstat[k] != NE_BS) continue;
-            int ty = S.type[k];
-            double l = S.lb[k], u = S.ub[k], x = S.prim[k];
-            if (ty == NE_LO || ty == NE_DB || ty == NE_FX) {
-                if (l - P.tol_int <= x && x <= l + P.tol_int) continue;
-                if (x < l) continue;
+        auto integrality = [&]() {
+            NeIntAcc a = {0, 0, 0.0};
+            for (int j = t.tid; j < n; j += t.nt) {
+                int k = m + j;
+                S.flag[j] = 0;
+                if (!P.kind[j] || S.kstat[k] != NE_BS) continue;
+                int ty = S.type[k];
+                double l = S.lb[k], u = S.ub[k], x = S.prim[k];
+                if (ty == NE_LO || ty == NE_DB || ty == NE_FX) {
+                    if (l - P.tol_int <= x && x <= l + P.tol_int) continue;
+                    if (x < l) continue;
+                }
+                if (ty == NE_UP || ty == NE_DB || ty == NE_FX) {
+                    if (u - P.tol_int <= x && x <= u + P.tol_int) continue;
+                    if (x > u) continue;
+                }
+                double r = floor(x + 0.5);
+                if (r - P.tol_int <= x && x <= r + P.tol_int) continue;
+                S.flag[j] = 1;
+                a.cnt++;
+                double t1 = x - floor(x), t2 = ceil(x) - x;
+                a.sum += (t1 <= t2 ? t1 : t2);
             }
-            if (ty == NE_UP || ty == NE_DB || ty == NE_FX) {
-                if (u - P.tol_int <= x && x <= u + P.tol_int) continue;
-                if (x > u) continue;
-            }
-            double r = floor(x + 0.5);
-            if (r - P.tol_int <= x && x <= r + P.tol_int) continue;
-            S.flag[j] = 1;
-            ia.cnt++;
-            double t1 = x - floor(x), t2 = ceil(x) - x;
-            ia.sum += (t1 <= t2 ? t1 : t2);
+            return ne_block_reduce(t, a, NeIntOp(), (NeIntAcc *)S.red);
+        };
+        NeIntAcc ia = integrality();
+        if (ia.cnt == 0 && lp.refacs == 0) {
+            /* an incumbent candidate whose values come from an inherited inverse: recompute them
+               from a fresh one, as the reference's per-node glp_factorize would (lib/glpapi06.js:6-7) */
+            NE_SYNC();
+            if (!ne_invert(t, P, S)) {
+                refacs++;
+                ne_eval_cbar(t, P, S);
+                ne_eval_bbar(t, P, S);
+                obj_val = ne_eval_obj(t, P, S);
+                ne_store_sol(t, P, S);
+                lp_obj = obj_val;
+                bi_upd = 0;
+                ia = integrality();
+            } else bi_upd = -1;
         }
-        ia = ne_block_reduce(t, ia, NeIntOp(), (NeIntAcc *)S.red);
         ii_cnt = ia.cnt; ii_sum = ia.sum;
         if (ii_cnt == 0) {
             /* record_solution: lib/glpios03.js:118-139 */
@@ -1498,8 +1592,11 @@ NE_D void ne_process_node(const NeT &t, const NeProb &P, NeS &S, const NeTask &t
             NE_SYNC();
             continue;                       /* `more` again with the tightened bound */
         }
-        /* two children: the frozen node state plus one bound each */
+        /* two children: the frozen node state plus one bound each, and the inverse of
+           the basis both start from */
         NE_SYNC();
+        cyc[4] += ne_clock() - ck;
+        ck = ne_clock();
         if (t.tid == 0) ne_set_bnds(S, k, dn_type, l, new_ub);
         NE_SYNC();
         ne_store_state(t, P, S, task.node);
@@ -1507,10 +1604,21 @@ NE_D void ne_process_node(const NeT &t, const NeProb &P, NeS &S, const NeTask &t
         if (t.tid == 0) ne_set_bnds(S, k, up_type, new_lb, u);
         NE_SYNC();
         ne_store_state(t, P, S, task.child);
+        if (bi_upd >= 0) {
+            double *b1 = P.slab_bi + (size_t)task.node * m * P.ldb, *b2 = P.slab_bi + (size_t)task.child * m * P.ldb;
+            for (int e = t.tid; e < m * P.ldb; e += t.nt) { double v = S.Bi[e]; b1[e] = v; b2[e] = v; }
+            int *h1 = P.slab_head + (size_t)task.node * m, *h2 = P.slab_head + (size_t)task.child * m;
+            for (int i = t.tid; i < m; i += t.nt) { h1[i] = S.head[i]; h2[i] = S.head[i]; }
+        }
+        if (t.tid == 0) { P.slab_upd[task.node] = bi_upd; P.slab_upd[task.child] = bi_upd; }
+        cyc[5] += ne_clock() - ck;
+        ck = ne_clock();
         code = NE_R_BRANCH;
         break;
     }
+    if (code != NE_R_BRANCH) cyc[4] += ne_clock() - ck;
     if (t.tid == 0) {
+        for (int c = 0; c < 6; c++) res.cyc[c] = cyc[c];
         res.code = code; res.jv = jv; res.next = next; res.ii_cnt = ii_cnt;
         res.iters = iters; res.solves = solves; res.refacs = refacs; res.ret = lpret;
         res.obj = (code == NE_R_INTEGRAL) ? obj_val : lp_obj;

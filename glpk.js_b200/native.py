@@ -463,9 +463,10 @@ class Problem:
             raise RuntimeError("glpb_bnb_import_nodes failed (%d): %s" % (rc, last_error()))
 
     def bnb_stats(self):
-        out = (C.c_long * 8)()
-        self.L.glpb_bnb_stats(self.h, out, 8)
-        keys = ["solved", "tasks", "rounds", "iters", "refacs", "open", "smem_bytes", "a_in_smem"]
+        out = (C.c_long * 14)()
+        self.L.glpb_bnb_stats(self.h, out, 14)
+        keys = ["solved", "tasks", "rounds", "iters", "refacs", "open", "smem_bytes", "a_in_smem",
+                "cyc_preprocess", "cyc_invert", "cyc_fresh", "cyc_iterate", "cyc_branch", "cyc_state_io"]
         return {k: int(out[i]) for i, k in enumerate(keys)}
 
     def bnb_end(self, ret=0):
