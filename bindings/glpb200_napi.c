@@ -1,9 +1,12 @@
 /* glpb200_napi.c -- thin N-API addon over libglpb200.so (include/glpb200.h).
  *
- * NOT built or tested in this repository's image (no Node.js, no node_api.h);
- * it is the binding a glpk.js maintainer would add.  It is written against the
- * stable N-API C signatures only and contains no logic: typed arrays in, typed
- * arrays out, one exported function per C-ABI entry point.
+ * Not loadable in this repository's image (no Node.js, no node_api.h); it is the
+ * binding a glpk.js maintainer would add.  It is written against the stable
+ * N-API C signatures only; tests/ compile it against a declarations-only stub of
+ * node_api.h (tests/napi_stub) so that it at least stays well-formed C.  Its only
+ * logic is validation: every typed array is checked for element type and length
+ * against m, n, nnz BEFORE a pointer crosses the C ABI (a short buffer would be a
+ * heap overflow inside the library), arguments of the wrong kind throw TypeError.
  *
  *   build:  cc -shared -fPIC glpb200_napi.c -I../include -I$NODE/include/node \
  *              -L../glpk.js_b200 -lglpb200 -o glpb200.node
@@ -15,69 +18,124 @@
 
 #define NAPI_OK(call) do { if ((call) != napi_ok) { napi_throw_error(env, NULL, #call); return NULL; } } while (0)
 
-static void *typed(napi_env env, napi_value v, size_t *len)
+/* A typed array argument of the given element type with at least `need` elements.
+   Returns its data pointer, or NULL after throwing a TypeError: nothing reaches the
+   C ABI unchecked (the library reads type/lb/ub[m+n], A_ptr[n+1], ... and writes
+   stat/prim/dual[m+n] into the caller's buffers). */
+static void *typed_n(napi_env env, napi_value v, napi_typedarray_type want, size_t need, const char *what, size_t *len_out)
 {
-    napi_typedarray_type t; void *data = NULL; napi_value ab; size_t off;
+    napi_typedarray_type t; void *data = NULL; napi_value ab; size_t off = 0, len = 0;
     bool is = false;
-    if (napi_is_typedarray(env, v, &is) != napi_ok || !is) return NULL;
-    if (napi_get_typedarray_info(env, v, &t, len, &data, &ab, &off) != napi_ok) return NULL;
+    if (napi_is_typedarray(env, v, &is) != napi_ok || !is ||
+        napi_get_typedarray_info(env, v, &t, &len, &data, &ab, &off) != napi_ok || t != want || len < need ||
+        (data == NULL && need > 0)) {
+        napi_throw_type_error(env, NULL, what);
+        return NULL;
+    }
+    if (len_out) *len_out = len;
     return data;
+}
+#define I32(v, need, what) ((int *)typed_n(env, (v), napi_int32_array, (need), "glpb200: " what ": Int32Array too short or of the wrong type", NULL))
+#define F64(v, need, what) ((double *)typed_n(env, (v), napi_float64_array, (need), "glpb200: " what ": Float64Array too short or of the wrong type", NULL))
+
+static bool is_nullish(napi_env env, napi_value v)
+{
+    napi_valuetype t;
+    return napi_typeof(env, v, &t) == napi_ok && (t == napi_undefined || t == napi_null);
 }
 
 static void finalize_handle(napi_env env, void *data, void *hint) { (void)env; (void)hint; glpb_destroy((glpb_prob *)data); }
 
-/* create(m, n, dir, c0, Int32 type, F64 lb, F64 ub, F64 coef, Int32 kind, F64 rii, F64 sjj,
+/* the handle and its dimensions (kept next to it so that every later call can size-check its arrays) */
+typedef struct { glpb_prob *P; int m, n; } shim_handle;
+static void finalize_shim(napi_env env, void *data, void *hint) { shim_handle *h = (shim_handle *)data; (void)env; (void)hint; glpb_destroy(h->P); free(h); }
+
+static shim_handle *handle(napi_env env, napi_value v)
+{
+    void *p = NULL;
+    if (napi_get_value_external(env, v, &p) != napi_ok || !p) { napi_throw_type_error(env, NULL, "glpb200: not a problem handle"); return NULL; }
+    return (shim_handle *)p;
+}
+
+static napi_value ret_int(napi_env env, int v) { napi_value r; napi_create_int32(env, v, &r); return r; }
+
+/* create(m, n, dir, c0, Int32 type, F64 lb, F64 ub, F64 coef, Int32 kind|null, F64 rii|null, F64 sjj|null,
           Int32 A_ptr, Int32 A_ind, F64 A_val, device) -> external handle */
 static napi_value Create(napi_env env, napi_callback_info info)
 {
     size_t argc = 15; napi_value a[15];
     NAPI_OK(napi_get_cb_info(env, info, &argc, a, NULL, NULL));
-    int32_t m, n, dir, device; double c0; size_t len, nnz;
+    if (argc < 15) { napi_throw_type_error(env, NULL, "glpb200.create: 15 arguments expected"); return NULL; }
+    int32_t m, n, dir, device; double c0;
     NAPI_OK(napi_get_value_int32(env, a[0], &m));
     NAPI_OK(napi_get_value_int32(env, a[1], &n));
     NAPI_OK(napi_get_value_int32(env, a[2], &dir));
     NAPI_OK(napi_get_value_double(env, a[3], &c0));
     NAPI_OK(napi_get_value_int32(env, a[14], &device));
-    int *type = typed(env, a[4], &len); double *lb = typed(env, a[5], &len), *ub = typed(env, a[6], &len);
-    double *coef = typed(env, a[7], &len); int *kind = typed(env, a[8], &len);
-    double *rii = typed(env, a[9], &len), *sjj = typed(env, a[10], &len);
-    int *ptr = typed(env, a[11], &len), *ind = typed(env, a[12], &nnz); double *val = typed(env, a[13], &nnz);
-    glpb_prob *P = glpb_create(m, n, (int)nnz, dir, c0, type, lb, ub, coef, kind, rii, sjj, ptr, ind, val, device);
-    if (!P) { napi_throw_error(env, NULL, glpb_last_error()); return NULL; }
+    if (m < 1 || n < 1) { napi_throw_range_error(env, NULL, "glpb200.create: m, n must be positive"); return NULL; }
+    const size_t mn = (size_t)m + (size_t)n;
+    int *type = I32(a[4], mn, "type"); if (!type) return NULL;
+    double *lb = F64(a[5], mn, "lb"); if (!lb) return NULL;
+    double *ub = F64(a[6], mn, "ub"); if (!ub) return NULL;
+    double *coef = F64(a[7], (size_t)n, "coef"); if (!coef) return NULL;
+    int *kind = NULL; double *rii = NULL, *sjj = NULL;
+    if (!is_nullish(env, a[8])) { kind = I32(a[8], (size_t)n, "kind"); if (!kind) return NULL; }
+    if (!is_nullish(env, a[9])) { rii = F64(a[9], (size_t)m, "rii"); if (!rii) return NULL; }
+    if (!is_nullish(env, a[10])) { sjj = F64(a[10], (size_t)n, "sjj"); if (!sjj) return NULL; }
+    int *ptr = I32(a[11], (size_t)n + 1, "A_ptr"); if (!ptr) return NULL;
+    /* A_ptr must be a monotone 0-based column pointer; its last entry is nnz */
+    if (ptr[0] != 0) { napi_throw_range_error(env, NULL, "glpb200.create: A_ptr[0] must be 0"); return NULL; }
+    for (int j = 0; j < n; j++)
+        if (ptr[j + 1] < ptr[j]) { napi_throw_range_error(env, NULL, "glpb200.create: A_ptr is not monotone"); return NULL; }
+    const size_t nnz = (size_t)ptr[n];
+    int *ind = I32(a[12], nnz, "A_ind"); if (!ind && nnz) return NULL;
+    double *val = F64(a[13], nnz, "A_val"); if (!val && nnz) return NULL;
+    for (size_t t = 0; t < nnz; t++)
+        if (ind[t] < 0 || ind[t] >= m) { napi_throw_range_error(env, NULL, "glpb200.create: row index out of range"); return NULL; }
+    shim_handle *h = (shim_handle *)calloc(1, sizeof *h);
+    if (!h) { napi_throw_error(env, NULL, "glpb200.create: out of memory"); return NULL; }
+    h->P = glpb_create(m, n, (int)nnz, dir, c0, type, lb, ub, coef, kind, rii, sjj, ptr, ind, val, device);
+    h->m = m; h->n = n;
+    if (!h->P) { free(h); napi_throw_error(env, NULL, glpb_last_error()); return NULL; }
     napi_value ext;
-    NAPI_OK(napi_create_external(env, P, finalize_handle, NULL, &ext));
+    if (napi_create_external(env, h, finalize_shim, NULL, &ext) != napi_ok) { finalize_shim(env, h, NULL); napi_throw_error(env, NULL, "napi_create_external"); return NULL; }
     return ext;
 }
 
-static glpb_prob *handle(napi_env env, napi_value v) { void *p = NULL; napi_get_value_external(env, v, &p); return (glpb_prob *)p; }
-
-static napi_value ret_int(napi_env env, int v) { napi_value r; napi_create_int32(env, v, &r); return r; }
-
-/* setBasis(h, Int32 stat[m+n]) ; setBounds(h, Int32 k, Int32 type, F64 lb, F64 ub) */
+/* setBasis(h, Int32 stat[m+n]) ; setBounds(h, Int32 k[cnt], Int32 type[cnt], F64 lb[cnt], F64 ub[cnt]) */
 static napi_value SetBasis(napi_env env, napi_callback_info info)
 {
-    size_t argc = 2, len; napi_value a[2];
+    size_t argc = 2; napi_value a[2];
     NAPI_OK(napi_get_cb_info(env, info, &argc, a, NULL, NULL));
-    return ret_int(env, glpb_set_basis(handle(env, a[0]), typed(env, a[1], &len)));
+    shim_handle *h = handle(env, a[0]); if (!h) return NULL;
+    int *stat = I32(a[1], (size_t)h->m + h->n, "stat"); if (!stat) return NULL;
+    return ret_int(env, glpb_set_basis(h->P, stat));
 }
 
 static napi_value SetBounds(napi_env env, napi_callback_info info)
 {
-    size_t argc = 5, cnt, len; napi_value a[5];
+    size_t argc = 5, cnt = 0; napi_value a[5];
     NAPI_OK(napi_get_cb_info(env, info, &argc, a, NULL, NULL));
-    int *k = typed(env, a[1], &cnt);
-    return ret_int(env, glpb_set_bounds(handle(env, a[0]), (int)cnt, k, typed(env, a[2], &len),
-                                        typed(env, a[3], &len), typed(env, a[4], &len)));
+    shim_handle *h = handle(env, a[0]); if (!h) return NULL;
+    int *k = (int *)typed_n(env, a[1], napi_int32_array, 0, "glpb200: k: Int32Array expected", &cnt);
+    if (!k && cnt) return NULL;
+    if (cnt == 0) return ret_int(env, 0);
+    int *type = I32(a[2], cnt, "type"); if (!type) return NULL;
+    double *lb = F64(a[3], cnt, "lb"); if (!lb) return NULL;
+    double *ub = F64(a[4], cnt, "ub"); if (!ub) return NULL;
+    return ret_int(env, glpb_set_bounds(h->P, (int)cnt, k, type, lb, ub));
 }
 
 /* simplex(h, Int32 ip[9], F64 dp[5]) : the SMCP fields packed by the facade */
 static napi_value Simplex(napi_env env, napi_callback_info info)
 {
-    size_t argc = 3, len; napi_value a[3];
+    size_t argc = 3; napi_value a[3];
     NAPI_OK(napi_get_cb_info(env, info, &argc, a, NULL, NULL));
-    int *ip = typed(env, a[1], &len); double *dp = typed(env, a[2], &len);
+    shim_handle *h = handle(env, a[0]); if (!h) return NULL;
+    int *ip = I32(a[1], 9, "smcp integers"); if (!ip) return NULL;
+    double *dp = F64(a[2], 5, "smcp doubles"); if (!dp) return NULL;
     glpb_smcp s = { ip[0], ip[1], ip[2], ip[3], dp[0], dp[1], dp[2], dp[3], dp[4], ip[4], ip[5], ip[6], ip[7], ip[8] };
-    int rc = glpb_simplex(handle(env, a[0]), &s);
+    int rc = glpb_simplex(h->P, &s);
     if (rc < 0) { napi_throw_error(env, NULL, glpb_last_error()); return NULL; }
     return ret_int(env, rc);
 }
@@ -85,33 +143,43 @@ static napi_value Simplex(napi_env env, napi_callback_info info)
 /* intopt(h, Int32 ip[8], F64 dp[3]) */
 static napi_value Intopt(napi_env env, napi_callback_info info)
 {
-    size_t argc = 3, len; napi_value a[3];
+    size_t argc = 3; napi_value a[3];
     NAPI_OK(napi_get_cb_info(env, info, &argc, a, NULL, NULL));
-    int *ip = typed(env, a[1], &len); double *dp = typed(env, a[2], &len);
+    shim_handle *h = handle(env, a[0]); if (!h) return NULL;
+    int *ip = I32(a[1], 8, "iocp integers"); if (!ip) return NULL;
+    double *dp = F64(a[2], 3, "iocp doubles"); if (!dp) return NULL;
     glpb_iocp s = { ip[0], ip[1], ip[2], dp[0], dp[1], ip[3], ip[4], ip[5], ip[6], dp[2], ip[7], -1 };
-    int rc = glpb_intopt(handle(env, a[0]), &s);
+    int rc = glpb_intopt(h->P, &s);
     if (rc < 0) { napi_throw_error(env, NULL, glpb_last_error()); return NULL; }
     return ret_int(env, rc);
 }
 
-/* getSolution(h, Int32 stat, F64 prim, F64 dual, Int32 head, Int32 ints[4], F64 obj[1]) */
+/* getSolution(h, Int32 stat[m+n], F64 prim[m+n], F64 dual[m+n], Int32 head[m], Int32 ints[4], F64 obj[1]) */
 static napi_value GetSolution(napi_env env, napi_callback_info info)
 {
-    size_t argc = 7, len; napi_value a[7];
+    size_t argc = 7; napi_value a[7];
     NAPI_OK(napi_get_cb_info(env, info, &argc, a, NULL, NULL));
-    int *ints = typed(env, a[5], &len); double *obj = typed(env, a[6], &len);
-    return ret_int(env, glpb_get_solution(handle(env, a[0]), typed(env, a[1], &len), typed(env, a[2], &len),
-                                          typed(env, a[3], &len), typed(env, a[4], &len), &ints[0], &ints[1], obj,
-                                          &ints[2], &ints[3]));
+    shim_handle *h = handle(env, a[0]); if (!h) return NULL;
+    const size_t mn = (size_t)h->m + h->n;
+    int *stat = I32(a[1], mn, "stat"); if (!stat) return NULL;
+    double *prim = F64(a[2], mn, "prim"); if (!prim) return NULL;
+    double *dual = F64(a[3], mn, "dual"); if (!dual) return NULL;
+    int *head = I32(a[4], (size_t)h->m, "head"); if (!head) return NULL;
+    int *ints = I32(a[5], 4, "ints"); if (!ints) return NULL;
+    double *obj = F64(a[6], 1, "obj"); if (!obj) return NULL;
+    return ret_int(env, glpb_get_solution(h->P, stat, prim, dual, head, &ints[0], &ints[1], obj, &ints[2], &ints[3]));
 }
 
 /* getMip(h, Int32 st[1], F64 obj[1], F64 mipx[m+n]) */
 static napi_value GetMip(napi_env env, napi_callback_info info)
 {
-    size_t argc = 4, len; napi_value a[4];
+    size_t argc = 4; napi_value a[4];
     NAPI_OK(napi_get_cb_info(env, info, &argc, a, NULL, NULL));
-    return ret_int(env, glpb_get_mip(handle(env, a[0]), typed(env, a[1], &len), typed(env, a[2], &len),
-                                     typed(env, a[3], &len), NULL));
+    shim_handle *h = handle(env, a[0]); if (!h) return NULL;
+    int *st = I32(a[1], 1, "mip status"); if (!st) return NULL;
+    double *obj = F64(a[2], 1, "mip objective"); if (!obj) return NULL;
+    double *x = F64(a[3], (size_t)h->m + h->n, "mipx"); if (!x) return NULL;
+    return ret_int(env, glpb_get_mip(h->P, st, obj, x, NULL));
 }
 
 /* scaleProb(m, n, Int32 A_ptr, Int32 A_ind, F64 A_val, flags, F64 rii[m], F64 sjj[n], F64 report[13])
@@ -122,8 +190,17 @@ static napi_value ScaleProb(napi_env env, napi_callback_info info)
     NAPI_OK(napi_get_cb_info(env, info, &argc, a, NULL, NULL));
     NAPI_OK(napi_get_value_int32(env, a[0], &m)); NAPI_OK(napi_get_value_int32(env, a[1], &n));
     NAPI_OK(napi_get_value_int32(env, a[5], &flags));
-    return ret_int(env, glpb_scale_prob(m, n, typed(env, a[2], &len), typed(env, a[3], &len), typed(env, a[4], &len),
-                                        flags, typed(env, a[6], &len), typed(env, a[7], &len), typed(env, a[8], &len)));
+    if (m < 1 || n < 1) { napi_throw_range_error(env, NULL, "glpb200.scaleProb: m, n must be positive"); return NULL; }
+    int *ptr = I32(a[2], (size_t)n + 1, "A_ptr"); if (!ptr) return NULL;
+    if (ptr[0] != 0 || ptr[n] < 0) { napi_throw_range_error(env, NULL, "glpb200.scaleProb: bad A_ptr"); return NULL; }
+    int *ind = I32(a[3], (size_t)ptr[n], "A_ind"); if (!ind && ptr[n]) return NULL;
+    double *val = F64(a[4], (size_t)ptr[n], "A_val"); if (!val && ptr[n]) return NULL;
+    double *rii = F64(a[6], (size_t)m, "rii"); if (!rii) return NULL;
+    double *sjj = F64(a[7], (size_t)n, "sjj"); if (!sjj) return NULL;
+    double *rep = NULL;
+    if (!is_nullish(env, a[8])) { rep = F64(a[8], 13, "report"); if (!rep) return NULL; }
+    (void)len;
+    return ret_int(env, glpb_scale_prob(m, n, ptr, ind, val, flags, rii, sjj, rep));
 }
 
 /* advBasis(m, n, Int32 A_ptr, Int32 A_ind, Int32 R_ptr, Int32 R_ind, Int32 type, F64 lb, F64 ub,
@@ -133,9 +210,21 @@ static napi_value AdvBasis(napi_env env, napi_callback_info info)
     size_t argc = 11, len; napi_value a[11]; int m, n;
     NAPI_OK(napi_get_cb_info(env, info, &argc, a, NULL, NULL));
     NAPI_OK(napi_get_value_int32(env, a[0], &m)); NAPI_OK(napi_get_value_int32(env, a[1], &n));
-    return ret_int(env, glpb_adv_basis(m, n, typed(env, a[2], &len), typed(env, a[3], &len), typed(env, a[4], &len),
-                                       typed(env, a[5], &len), typed(env, a[6], &len), typed(env, a[7], &len),
-                                       typed(env, a[8], &len), typed(env, a[9], &len), typed(env, a[10], &len)));
+    if (m < 1 || n < 1) { napi_throw_range_error(env, NULL, "glpb200.advBasis: m, n must be positive"); return NULL; }
+    const size_t mn = (size_t)m + (size_t)n;
+    int *ptr = I32(a[2], (size_t)n + 1, "A_ptr"); if (!ptr) return NULL;
+    int *rptr = I32(a[4], (size_t)m + 1, "R_ptr"); if (!rptr) return NULL;
+    if (ptr[0] != 0 || rptr[0] != 0 || ptr[n] < 0 || rptr[m] != ptr[n]) { napi_throw_range_error(env, NULL, "glpb200.advBasis: bad A_ptr / R_ptr"); return NULL; }
+    int *ind = I32(a[3], (size_t)ptr[n], "A_ind"); if (!ind && ptr[n]) return NULL;
+    int *rind = I32(a[5], (size_t)ptr[n], "R_ind"); if (!rind && ptr[n]) return NULL;
+    int *type = I32(a[6], mn, "type"); if (!type) return NULL;
+    double *lb = F64(a[7], mn, "lb"); if (!lb) return NULL;
+    double *ub = F64(a[8], mn, "ub"); if (!ub) return NULL;
+    int *stat = I32(a[9], mn, "stat"); if (!stat) return NULL;
+    int *size = NULL;
+    if (!is_nullish(env, a[10])) { size = I32(a[10], 1, "size"); if (!size) return NULL; }
+    (void)len;
+    return ret_int(env, glpb_adv_basis(m, n, ptr, ind, rptr, rind, type, lb, ub, stat, size));
 }
 
 /* readLp(text) -> { m, n, dir, type, lb, ub, coef, kind, ptr, ind, val, names } -- glp_read_lp
@@ -146,11 +235,16 @@ static napi_value ReadLp(napi_env env, napi_callback_info info)
     NAPI_OK(napi_get_cb_info(env, info, &argc, a, NULL, NULL));
     NAPI_OK(napi_get_value_string_utf8(env, a[0], NULL, 0, &len));
     char *text = (char *)malloc(len + 1);
-    NAPI_OK(napi_get_value_string_utf8(env, a[0], text, len + 1, &len));
+    if (!text) { napi_throw_error(env, NULL, "glpb200.readLp: out of memory"); return NULL; }
+    if (napi_get_value_string_utf8(env, a[0], text, len + 1, &len) != napi_ok) {
+        free(text);                                  /* no leak on the error path */
+        napi_throw_error(env, NULL, "glpb200.readLp: argument is not a string");
+        return NULL;
+    }
     int rc = glpb_read_lp(text, (long)len, &d, &names, &nlen);
     free(text);
     if (rc != 0) { napi_throw_error(env, NULL, glpb_last_error()); return NULL; }
-    NAPI_OK(napi_create_object(env, &r));
+    if (napi_create_object(env, &r) != napi_ok) { glpb_free_names(names); glpb_free_problem(&d); napi_throw_error(env, NULL, "napi_create_object"); return NULL; }
 #define PUT_INT(key, x) do { napi_create_int32(env, (x), &v); napi_set_named_property(env, r, key, v); } while (0)
 #define PUT_ARR(key, type, src, count, bytes) do { napi_value ab; napi_create_arraybuffer(env, (count) * (bytes), &p, &ab); \
         memcpy(p, (src), (count) * (bytes)); napi_create_typedarray(env, type, (count), ab, 0, &v); \

@@ -14,7 +14,11 @@
  *   bounds     = [sign] (number|inf) <= name [<= [sign] (number|inf)]
  *              | name (<=|>=|=) value | name free
  *   generals / integers / binaries = lists of names
- * Keywords are recognised only at the start of a line; '\' starts a comment.
+ * Keywords are recognised only when a letter stands in column 0 of a line (the
+ * reference looks for them right after a newline, lib/glpcpx.js:187-192); a name
+ * is followed by a colon if ':' is the next non-blank character of its line; the
+ * right-hand side must end its line (not even a comment may follow); unnamed rows
+ * are called "r.<line number>"; '\' starts a comment.
  */
 #include "../../include/glpb200.h"
 #include <cctype>
@@ -38,8 +42,10 @@ struct Token {
     Kind kind;
     std::string image;
     double value;
-    bool colon; /* a ':' follows immediately (names only) */
+    bool colon; /* a ':' is the next significant character on the same line (the reference tests
+                   csa.c after scan_token has skipped the blanks behind the token, lib/glpcpx.js:256-257) */
     int line;
+    bool eol;   /* nothing but blanks follows on the line -- not even a comment (lib/glpcpx.js:431-433) */
 };
 
 struct SyntaxError {
@@ -81,13 +87,15 @@ std::vector<Token> tokenize(const char *text, long len)
         lineno++;
         std::string line(text + pos, (size_t)(eol - pos));
         pos = eol + 1;
-        size_t cut = line.find('\\');
-        if (cut != std::string::npos) line.resize(cut);
         for (char &c : line)
-            if (c == '\t' || c == '\r') c = ' ';
-        const size_t n = line.size();
+            if (c == '\t' || c == '\r' || c == '\v' || c == '\f') c = ' ';
+        const size_t full = line.size();                 /* the comment stays for the end-of-line tests */
+        size_t cut = line.find('\\');
+        const size_t n = (cut != std::string::npos) ? cut : full;
+        /* next significant position on the RAW line (a comment counts: after it the reference's
+           current character is '\\', not the end of the line) */
+        auto rest = [&](size_t j) { while (j < full && line[j] == ' ') j++; return j; };
         size_t i = 0;
-        bool first = true;
         while (i < n) {
             unsigned char ch = (unsigned char)line[i];
             if (ch == ' ') { i++; continue; }
@@ -96,7 +104,7 @@ std::vector<Token> tokenize(const char *text, long len)
                 while (j < n && name_char((unsigned char)line[j])) j++;
                 std::string image = line.substr(i, j - i);
                 Kind kind = T_NAME;
-                if (first) {
+                if (i == 0 && isalpha(ch)) {             /* keywords: a letter in column 0 (lib/glpcpx.js:187-192) */
                     std::string low = lower(image);
                     if (low == "subject" || low == "such") {
                         /* "subject to" / "such that": the second word must follow on the same line */
@@ -111,46 +119,46 @@ std::vector<Token> tokenize(const char *text, long len)
                     } else
                         kind = keyword(low);
                 }
-                toks.push_back({kind, image, 0.0, j < n && line[j] == ':', lineno});
+                { size_t r = rest(j); toks.push_back({kind, image, 0.0, r < full && line[r] == ':', lineno, r >= full}); }
                 i = j;
             } else if (isdigit(ch) || ch == '.') {
                 size_t j = i;
                 while (j < n && isdigit((unsigned char)line[j])) j++;
                 if (j < n && line[j] == '.') {
                     j++;
+                    if (j - i == 1 && !(j < n && isdigit((unsigned char)line[j])))
+                        throw SyntaxError{"invalid use of decimal point", lineno};
                     while (j < n && isdigit((unsigned char)line[j])) j++;
                 }
                 if (j < n && (line[j] == 'e' || line[j] == 'E')) {
-                    size_t k = j + 1;
-                    if (k < n && (line[k] == '+' || line[k] == '-')) k++;
-                    if (k < n && isdigit((unsigned char)line[k])) {
-                        while (k < n && isdigit((unsigned char)line[k])) k++;
-                        j = k;
-                    }
+                    j++;
+                    if (j < n && (line[j] == '+' || line[j] == '-')) j++;
+                    if (!(j < n && isdigit((unsigned char)line[j])))       /* lib/glpcpx.js:214-218 */
+                        throw SyntaxError{"numeric constant `" + line.substr(i, j - i) + "' incomplete", lineno};
+                    while (j < n && isdigit((unsigned char)line[j])) j++;
                 }
                 std::string image = line.substr(i, j - i);
                 char *endp = nullptr;
                 double v = strtod(image.c_str(), &endp);
                 if (endp == image.c_str() || *endp != '\0')
                     throw SyntaxError{"numeric constant `" + image + "' not recognized", lineno};
-                toks.push_back({T_NUM, image, v, false, lineno});
+                toks.push_back({T_NUM, image, v, false, lineno, rest(j) >= full});
                 i = j;
             } else if (ch == '+' || ch == '-' || ch == ':') {
-                toks.push_back({ch == '+' ? T_PLUS : (ch == '-' ? T_MINUS : T_COLON), std::string(1, (char)ch), 0.0, false, lineno});
+                toks.push_back({ch == '+' ? T_PLUS : (ch == '-' ? T_MINUS : T_COLON), std::string(1, (char)ch), 0.0, false, lineno, rest(i + 1) >= full});
                 i++;
             } else if (ch == '<' || ch == '>' || ch == '=') {
                 size_t j = i + 1;
                 if (j < n && (line[j] == '<' || line[j] == '>' || line[j] == '=')) j++;
                 std::string op = line.substr(i, j - i);
                 Kind kind = op.find('<') != std::string::npos ? T_LE : (op.find('>') != std::string::npos ? T_GE : T_EQ);
-                toks.push_back({kind, op, 0.0, false, lineno});
+                toks.push_back({kind, op, 0.0, false, lineno, rest(j) >= full});
                 i = j;
             } else
                 throw SyntaxError{std::string("character `") + (char)ch + "' not recognized", lineno};
-            first = false;
         }
     }
-    toks.push_back({T_EOF, "", 0.0, false, lineno});
+    toks.push_back({T_EOF, "", 0.0, false, lineno, true});
     return toks;
 }
 
@@ -252,12 +260,19 @@ struct Reader {
                 row_name.push_back(tok().image);
                 adv(); adv();
             } else
-                row_name.push_back("r." + std::to_string(i + 1));
+                row_name.push_back("r." + std::to_string(tok().line));     /* "r." + csa.count: the LINE number, lib/glpcpx.js:395 */
             rows.push_back(linear_form());
             Kind sense = tok().kind;
             if (sense != T_LE && sense != T_GE && sense != T_EQ) fail("missing constraint sense");
             adv();
-            r_bnd.push_back(signed_number("right-hand side"));
+            {
+                double sgn = 1.0;
+                if (is_sign()) { sgn = tok().kind == T_PLUS ? 1.0 : -1.0; adv(); }
+                if (tok().kind != T_NUM) fail("missing right-hand side");
+                r_bnd.push_back(sgn * tok().value);
+                if (!tok().eol) fail("invalid symbol(s) beyond right-hand side");   /* lib/glpcpx.js:431-433 */
+                adv();
+            }
             r_type.push_back(sense == T_LE ? 3 : (sense == T_GE ? 2 : 5)); /* GLP_UP / GLP_LO / GLP_FX */
             if (!(is_sign() || tok().kind == T_NUM || tok().kind == T_NAME)) break;
         }

@@ -797,6 +797,13 @@ struct glpb_mip {
             if (state == S_MORE) {
                 if (parm.node_lim >= 0 && solved >= parm.node_lim) return GLP_ESTOP;
                 if (parm.tm_lim < INT_MAX && (parm.tm_lim - 1) <= (now_ms() - tm_beg)) return GLP_ETMLIM;
+                /* ios_relative_gap <= mip_gap: lib/glpios03.js:615-625, lib/glpios01.js:821-864 */
+                if (feas() && parm.mip_gap > 0.0) {
+                    double best = pool[curr].bound;
+                    for (int t = head; t >= 0; t = pool[t].next)
+                        if (dir() == GLP_MIN ? pool[t].bound < best : pool[t].bound > best) best = pool[t].bound;
+                    if (fabs(P->mip_obj - best) / (fabs(P->mip_obj) + DBL_EPSILON) <= parm.mip_gap) return GLP_EMIPGAP;
+                }
                 int lvl = pool[curr].level;
                 if (parm.pp_tech == GLP_PP_ROOT) { if (lvl == 0 && preprocess_node(100)) { state = S_FATH; continue; } }
                 else if (parm.pp_tech == GLP_PP_ALL) { if (preprocess_node(lvl == 0 ? 100 : 10)) { state = S_FATH; continue; } }

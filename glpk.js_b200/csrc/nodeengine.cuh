@@ -289,6 +289,17 @@ NE_D void ne_carve(NeS &S, unsigned char *p, int m, int n, int ldb)
     S.sc = (double *)take(16 * 8); S.si = (int *)take(16 * 4);
 }
 
+/* sum_i x[i] * A[i][col] over the m rows of the dense matrix (row stride lda) */
+NE_D double ne_coldot(const double *A, int lda, int m, int col, const double *x)
+{
+    const double *a = A + col;
+    double s0 = 0.0, s1 = 0.0;
+    int i = 0;
+    for (; i + 1 < m; i += 2) { s0 += x[i] * a[(size_t)i * lda]; s1 += x[i + 1] * a[(size_t)(i + 1) * lda]; }
+    if (i < m) s0 += x[i] * a[(size_t)i * lda];
+    return s0 + s1;
+}
+
 /* scale of variable k: unscaled value = scaled value * ne_scale(k)
    (rows: 1/rii, columns: sjj; lib/glpspx01.js:61-75, 1629-1678) */
 NE_D double ne_scale(const NeProb &P, int k) { return k < P.m ? 1.0 / P.rii[k] : P.sjj[k - P.m]; }
@@ -695,8 +706,7 @@ NE_D void ne_eval_cbar(const NeT &t, const NeProb &P, NeS &S)
         double d;
         if (k < m) d = -pi[k];
         else {
-            d = P.cw[k - m];
-            for (int i = 0; i < m; i++) d += S.A[(size_t)i * P.lda + (k - m)] * pi[i];
+            d = P.cw[k - m] + ne_coldot(S.A, P.lda, m, k - m, pi);
         }
         S.cbar[j] = d;
     }
@@ -959,7 +969,7 @@ NE_D void ne_solve_lp(const NeT &t, const NeProb &P, NeS &S, double obj_ll, doub
             if (S.nstat[j] != NE_NS) {
                 int k = S.head[m + j];
                 if (k < m) v = -S.rho[k];
-                else for (int i = 0; i < m; i++) v += S.rho[i] * S.A[(size_t)i * P.lda + (k - m)];
+                else v = ne_coldot(S.A, P.lda, m, k - m, S.rho);
             }
             S.trow[j] = v;
             if (fabs(v) > big) big = fabs(v);
@@ -1284,8 +1294,8 @@ NE_D void ne_tab_estimates(const NeT &t, const NeProb &P, NeS &S, int nfrac, dou
             if (!(st == NE_NL || st == NE_NU || st == NE_NF)) continue;
             double v = 0.0;
             if (kk < m) v = -rho[kk];
-            else for (int i = 0; i < m; i++) v += rho[i] * S.A[(size_t)i * P.lda + (kk - m)];
-            v = v * sb / ne_scale(P, kk);
+            else v = ne_coldot(S.A, P.lda, m, kk - m, rho);
+            if (!P.unit_scale) v = v * sb / ne_scale(P, kk);
             if (v == 0.0) continue;
             const double cost = S.dual[kk];
             for (int kase = 0; kase < 2; kase++) {

@@ -299,6 +299,10 @@ extern "C" glpb_prob *glpb_create(int m, int n, int nnz, int dir, double c0, con
         glpb_set_error("glpb_create: invalid argument");
         return nullptr;
     }
+    /* the column pointer must be a monotone 0-based prefix sum that ends at nnz, row indices in range */
+    if (A_ptr[0] != 0 || A_ptr[n] != nnz) { glpb_set_error("glpb_create: A_ptr[0] must be 0 and A_ptr[n] must equal nnz"); return nullptr; }
+    for (int j = 0; j < n; j++)
+        if (A_ptr[j + 1] < A_ptr[j]) { glpb_set_error("glpb_create: A_ptr is not monotone at column %d", j + 1); return nullptr; }
     int ndev = glpb_device_count();
     if (ndev < 1 || device < 0 || device >= ndev) {
         glpb_set_error("glpb_create: no CUDA device %d (found %d); there is no CPU fallback", device, ndev);
@@ -340,7 +344,7 @@ extern "C" glpb_prob *glpb_create(int m, int n, int nnz, int dir, double c0, con
 extern "C" int glpb_set_bounds(glpb_prob *P, int count, const int *k, const int *type,
                                const double *lb, const double *ub)
 {
-    if (!P || count < 0) return GLPB_EINVAL;
+    if (!P || count < 0 || (count > 0 && (!k || !type || !lb || !ub))) return GLPB_EINVAL;
     for (int t = 0; t < count; t++) {
         int kk = k[t] - 1;
         if (kk < 0 || kk >= P->m + P->n || type[t] < GLP_FR || type[t] > GLP_FX) return GLPB_EINVAL;
@@ -1629,6 +1633,40 @@ extern "C" int glpb_set_pivot_log(glpb_prob *P, int cap)
     CK(cudaMemcpy(&P->ctrl->piv_log, &ptr, sizeof ptr, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(&P->ctrl->piv_cap, capv, sizeof capv, cudaMemcpyHostToDevice));
     return 0;
+}
+
+/* Live device vectors for parity tests, CSA layout of the reference (lib/glpspx01.js:13-38):
+   "gamma" (primal: [n] by non-basic position, dual: [m] by basic position), "cbar" [n], "bbar" [m],
+   "head" [m+n] as 1-based variable numbers, "stat" [n].  out receives `count` doubles. */
+extern "C" int glpb_debug_get(glpb_prob *P, const char *name, double *out, int count)
+{
+    if (!P || !name || !out || count < 0) return GLPB_EINVAL;
+    CK(cudaSetDevice(P->device));
+    CK(cudaStreamSynchronize(P->stream));
+    const int m = P->m, n = P->n;
+    std::string s(name);
+    if (s == "gamma" || s == "cbar" || s == "bbar") {
+        const double *src = (s == "gamma") ? P->gamma : (s == "cbar" ? P->cbar : P->bbar);
+        const int len = (s == "gamma") ? std::max(m, n) : (s == "cbar" ? n : m);
+        if (count > len) return GLPB_EINVAL;
+        CK(cudaMemcpy(out, src, (size_t)count * sizeof(double), cudaMemcpyDeviceToHost));
+        return 0;
+    }
+    if (s == "head") {
+        if (count > m + n) return GLPB_EINVAL;
+        std::vector<int> h(count);
+        CK(cudaMemcpy(h.data(), P->head, (size_t)count * sizeof(int), cudaMemcpyDeviceToHost));
+        for (int i = 0; i < count; i++) out[i] = h[i] + 1;
+        return 0;
+    }
+    if (s == "stat") {
+        if (count > n) return GLPB_EINVAL;
+        std::vector<signed char> h(count);
+        CK(cudaMemcpy(h.data(), P->stat, (size_t)count, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < count; i++) out[i] = h[i];
+        return 0;
+    }
+    return GLPB_EINVAL;
 }
 
 extern "C" int glpb_get_pivot_log(glpb_prob *P, int *qp, int cap, int *count)

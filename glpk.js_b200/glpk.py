@@ -853,12 +853,24 @@ _KEYWORDS = {
 
 
 def _tokenize(text):
-    """Yield (kind, image, value, colon_follows).  Keywords are recognised only
-    for a name that starts a line, as the reference's scanner does."""
+    """[(kind, image, value, colon_follows, line, end_of_line)].  As the reference's scanner
+    (lib/glpcpx.js:79-258): keywords only for a letter in column 0; a name is followed by a
+    colon if ':' is the next non-blank character of its line; end_of_line = nothing but blanks
+    follows (a comment counts as something)."""
     toks = []
-    for raw in text.replace("\r", "").split("\n"):
-        line = raw.split("\\", 1)[0].replace("\t", " ")
-        i, n, first = 0, len(line), True
+    lineno = 0
+    for raw in text.split("\n"):
+        lineno += 1
+        full = "".join(" " if c in "\t\r\v\f" else c for c in raw)
+        n = full.find("\\")
+        n = len(full) if n < 0 else n
+        line = full
+
+        def rest(j):
+            while j < len(full) and full[j] == " ":
+                j += 1
+            return j
+        i = 0
         while i < n:
             ch = line[i]
             if ch == " ":
@@ -870,17 +882,18 @@ def _tokenize(text):
                     j += 1
                 image = line[i:j]
                 kind = "NAME"
-                if first:
+                if i == 0 and ch.isalpha():
                     low = image.lower()
                     if low in ("subject", "such"):
-                        rest = line[j:].lstrip(" ")
+                        rst = line[j:n].lstrip(" ")
                         want = "to" if low == "subject" else "that"
-                        if rest.lower().startswith(want) and (len(rest) == len(want) or not rest[len(want)].isalnum()):
+                        if rst.lower().startswith(want) and (len(rst) == len(want) or not rst[len(want)].isalnum()):
                             kind = "ST"
-                            j = n - len(rest) + len(want)
+                            j = n - len(rst) + len(want)
                     elif low in _KEYWORDS:
                         kind = _KEYWORDS[low]
-                toks.append((kind, image, 0.0, j < n and line[j] == ":"))
+                r = rest(j)
+                toks.append((kind, image, 0.0, r < len(full) and full[r] == ":", lineno, r >= len(full)))
                 i = j
             elif ch.isdigit() or ch == ".":
                 j = i
@@ -888,20 +901,22 @@ def _tokenize(text):
                     j += 1
                 if j < n and line[j] == ".":
                     j += 1
+                    if j - i == 1 and not (j < n and line[j].isdigit()):
+                        xerror("glp_read_lp: line %d: invalid use of decimal point" % lineno)
                     while j < n and line[j].isdigit():
                         j += 1
                 if j < n and line[j] in "eE":
-                    k = j + 1
-                    if k < n and line[k] in "+-":
-                        k += 1
-                    if k < n and line[k].isdigit():
-                        while k < n and line[k].isdigit():
-                            k += 1
-                        j = k
-                toks.append(("NUM", line[i:j], float(line[i:j]), False))
+                    j += 1
+                    if j < n and line[j] in "+-":
+                        j += 1
+                    if not (j < n and line[j].isdigit()):
+                        xerror("glp_read_lp: line %d: numeric constant `%s' incomplete" % (lineno, line[i:j]))
+                    while j < n and line[j].isdigit():
+                        j += 1
+                toks.append(("NUM", line[i:j], float(line[i:j]), False, lineno, rest(j) >= len(full)))
                 i = j
             elif ch in "+-:":
-                toks.append(({"+": "PLUS", "-": "MINUS", ":": "COLON"}[ch], ch, 0.0, False))
+                toks.append(({"+": "PLUS", "-": "MINUS", ":": "COLON"}[ch], ch, 0.0, False, lineno, rest(i + 1) >= len(full)))
                 i += 1
             elif ch in "<>=":
                 j = i + 1
@@ -909,12 +924,11 @@ def _tokenize(text):
                     j += 1
                 op = line[i:j]
                 kind = "LE" if "<" in op else ("GE" if ">" in op else "EQ")
-                toks.append((kind, op, 0.0, False))
+                toks.append((kind, op, 0.0, False, lineno, rest(j) >= len(full)))
                 i = j
             else:
-                xerror("glp_read_lp: character `%s' not recognized" % ch)
-            first = False
-    toks.append(("EOF", "", 0.0, False))
+                xerror("glp_read_lp: line %d: character `%s' not recognized" % (lineno, ch))
+    toks.append(("EOF", "", 0.0, False, lineno, True))
     return toks
 
 
@@ -1070,14 +1084,23 @@ def _read_lp(P, text):
             adv()
             adv()
         else:
-            glp_set_row_name(P, i, "r.%d" % i)
+            glp_set_row_name(P, i, "r.%d" % tok()[4])        # "r." + csa.count: the line number (lib/glpcpx.js:395)
         ln, ind, val = linear_form()
         glp_set_mat_row(P, i, ln, ind, val)
         sense = tok()[0]
         if sense not in ("LE", "GE", "EQ"):
             xerror("glp_read_lp: missing constraint sense")
         adv()
-        rhs = signed_number("right-hand side")
+        sgn = 1.0
+        if tok()[0] in ("PLUS", "MINUS"):
+            sgn = 1.0 if tok()[0] == "PLUS" else -1.0
+            adv()
+        if tok()[0] != "NUM":
+            xerror("glp_read_lp: missing right-hand side")
+        rhs = sgn * tok()[2]
+        if not tok()[5]:                                   # lib/glpcpx.js:431-433
+            xerror("glp_read_lp: line %d: invalid symbol(s) beyond right-hand side" % tok()[4])
+        adv()
         glp_set_row_bnds(P, i, {"LE": GLP_UP, "GE": GLP_LO, "EQ": GLP_FX}[sense], rhs, rhs)
         if tok()[0] not in ("PLUS", "MINUS", "NUM", "NAME"):
             break

@@ -74,7 +74,7 @@ SYMBOLS = [
     "glpb_k_ratio_dual", "glpb_k_trow", "glpb_bench_kernel", "glpb_gen_packing",
     "glpb_gen_covering", "glpb_gen_mkp", "glpb_free_problem", "glpb_rng_fill",
     "glpb_scale_prob", "glpb_adv_basis", "glpb_read_lp", "glpb_free_names",
-    "glpb_set_pivot_log", "glpb_get_pivot_log", "glpb_bnb_begin", "glpb_bnb_round", "glpb_bnb_open_count", "glpb_bnb_get_incumbent", "glpb_bnb_set_cutoff", "glpb_bnb_clear",
+    "glpb_set_pivot_log", "glpb_get_pivot_log", "glpb_debug_get", "glpb_bnb_begin", "glpb_bnb_round", "glpb_bnb_open_count", "glpb_bnb_get_incumbent", "glpb_bnb_set_cutoff", "glpb_bnb_clear",
     "glpb_bnb_record_bytes", "glpb_bnb_export_nodes", "glpb_bnb_import_nodes", "glpb_bnb_stats", "glpb_bnb_end",
 ]
 
@@ -150,6 +150,7 @@ def load():
     L.glpb_free_names.argtypes = [vp]
     L.glpb_set_pivot_log.argtypes = [vp, ci]
     L.glpb_get_pivot_log.argtypes = [vp, vp, ci, vp]
+    L.glpb_debug_get.argtypes = [vp, C.c_char_p, vp, ci]
     L.glpb_bnb_begin.argtypes = [vp, vp, ci, ci]
     L.glpb_bnb_round.argtypes = [vp, C.c_long, vp]
     L.glpb_bnb_open_count.argtypes = [vp]
@@ -471,6 +472,13 @@ class Problem:
 
     def bnb_end(self, ret=0):
         return self.L.glpb_bnb_end(self.h, int(ret))
+
+    def debug_get(self, name, count):
+        out = np.zeros(max(1, count))
+        rc = self.L.glpb_debug_get(self.h, name.encode(), _p(out), int(count))
+        if rc != 0:
+            raise RuntimeError("glpb_debug_get(%s) failed (%d)" % (name, rc))
+        return out[:count]
 
     def set_pivot_log(self, cap):
         rc = self.L.glpb_set_pivot_log(self.h, int(cap))

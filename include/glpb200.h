@@ -181,6 +181,11 @@ const char *glpb_profile_report(glpb_prob *P);
  * glpb_get_pivot_log copies min(cap, iterations done) pairs: qp[2 it] = q, qp[2 it + 1] = p. */
 int glpb_set_pivot_log(glpb_prob *P, int cap);
 int glpb_get_pivot_log(glpb_prob *P, int *qp, int cap, int *count);
+/* Live device vectors for parity tests (what update_gamma / update_cbar / update_bbar left,
+ * lib/glpspx01.js:1100-1255, lib/glpspx02.js:1020-1188): name = "gamma" (primal [n] by non-basic
+ * position, dual [m] by basic position), "cbar" [n], "bbar" [m], "head" [m+n] (1-based variable
+ * numbers), "stat" [n]; 0-based arrays of `count` doubles. */
+int glpb_debug_get(glpb_prob *P, const char *name, double *out, int count);
 
 /* Basis solves with the current factorisation, scaled space:
  * bfd_ftran / bfd_btran (lib/glpbfd.js:148-168); x is [m], in place. */

@@ -98,3 +98,29 @@ def test_c3_full_size_properties():
     r2 = solve_in_subprocess(["covering", 16384, 32768], {"GLPB_DEFER": "0", "GLPB_REFAC_DIV": "4"}, timeout=900)
     assert (r2["rc"], r2["status"]) == (0, O.GLP_OPT)
     assert abs(r["obj"] - r2["obj"]) <= 1e-9 * abs(r["obj"]), (r["obj"], r2["obj"])
+
+
+# ---- engine wiring: the (q, p) sequence of whole solves against THE REFERENCE'S own pivot sequence ----
+@pytest.mark.parametrize("engine", ["1", "0"])
+def test_pivot_sequence_equals_the_references(engine):
+    """glpb_simplex with the pivot log on (tests/run_pivots.py, fresh process): the entering / leaving pair
+    of every iteration equals the one lib/glpspx01.js / glpspx02.js chose on the same LP
+    (tests/golden/ref_runs.json, generated by running the reference), for the persistent engine
+    (GLPB_ENGINE=1) and the per-kernel path (=0).  Problems with continuous random data: no exact ties,
+    so the order left by sort_tcol / sort_trow cannot matter."""
+    e = dict(os.environ)
+    e["GLPB_ENGINE"] = engine
+    out = subprocess.run([sys.executable, os.path.join(HERE, "run_pivots.py")], capture_output=True, text=True, env=e, timeout=600)
+    assert out.returncode == 0, out.stderr[-3000:]
+    res = json.loads(out.stdout.strip().splitlines()[-1])
+    assert len(res) >= 12
+    bad = [r for r in res if not (r["rc_ok"] and r["obj_ok"])]
+    assert not bad, bad
+    differ = [r for r in res if not r["same_sequence"]]
+    assert len(differ) <= 1, differ                 # identical pivots, iteration for iteration
+    assert sum(r["iterations"] for r in res) >= 400
+    # update_gamma (lib/glpspx01.js:1178-1255, lib/glpspx02.js:1075-1188): the projected steepest edge weights the
+    # device holds after K iterations equal the ones the reference held at the same point, basis header included
+    w = [x for r in res for x in r["weights"]]
+    assert len(w) >= 20 and all(x["same_head"] for x in w), [x for x in w if not x["same_head"]][:3]
+    assert max(x["gamma_rel_err"] for x in w) <= 1e-9, sorted(w, key=lambda x: -x["gamma_rel_err"])[:3]

@@ -143,3 +143,64 @@ def test_pivot_row_spmv_matches_reference_eval_trow():
         P.set_hook(hook)
         assert P.simplex(meth=O.GLP_DUAL) == 0
     assert seen[0] > 100
+
+
+# ======================================================================
+# the same kernels fed THE REFERENCE'S OWN arrays (tests/golden/ref_vectors.npz:
+# captured from lib/glpspx01.js / lib/glpspx02.js running in the minijs
+# interpreter, oracle/jsref/make_ref_golden.py)
+# ======================================================================
+import os  # noqa: E402
+
+VEC = np.load(os.path.join(H.GOLDEN, "ref_vectors.npz"))
+
+
+def _group(prefix):
+    p = prefix + "/"
+    return {k[len(p):]: VEC[k] for k in VEC.files if k.startswith(p)}
+
+
+def _groups(kind):
+    return sorted({k.rsplit("/", 1)[0] for k in VEC.files if k.split("/")[1].startswith(kind + "_")})
+
+
+def test_selection_kernels_bit_exact_on_the_references_arrays():
+    n_checked = 0
+    for g in _groups("p_chuzc"):
+        v = _group(g)
+        assert nat.k_chuzc_primal(int(v["n"]), v["stat"], v["cbar"], v["gamma"], float(v["tol"])) == int(v["q"]), g
+        n_checked += 1
+    for g in _groups("d_chuzr"):
+        v = _group(g)
+        p, delta = nat.k_chuzr_dual(int(v["m"]), int(v["n"]), v["type"], v["lb"], v["ub"], v["head"], v["bbar"], v["gamma"],
+                                    float(v["tol"]))
+        assert (p, delta) == (int(v["p"]), float(v["delta"])), g
+        n_checked += 1
+    for g in _groups("p_chuzr"):
+        v = _group(g)
+        q = int(v["q"])
+        p, p_stat, teta = nat.k_ratio_primal(int(v["m"]), int(v["n"]), v["type"], v["lb"], v["ub"], v["coef"], v["head"],
+                                             int(v["phase"]), v["bbar"], float(v["cbar"][q]), q, v["tcol_ind"], v["tcol_vec"],
+                                             int(v["tcol_num"]), float(v["rtol"]))
+        assert (p, teta) == (int(v["p"]), float(v["teta"])), g
+        if p != 0:
+            assert p_stat == int(v["p_stat"]), g
+        n_checked += 1
+    for g in _groups("d_chuzc"):
+        v = _group(g)
+        q, new_dq = nat.k_ratio_dual(int(v["n"]), v["stat"], v["cbar"], float(v["delta"]), v["trow_ind"], v["trow_vec"],
+                                     int(v["trow_num"]), float(v["rtol"]))
+        assert (q, new_dq) == (int(v["q"]), float(v["new_dq"])), g
+        n_checked += 1
+    assert n_checked >= 150
+
+
+def test_pivot_row_kernel_on_the_references_rho():
+    n_checked = 0
+    for g in _groups("d_trow"):
+        v = _group(g)
+        got = nat.k_trow(int(v["m"]), int(v["n"]), v["A_ptr"], v["A_ind"], v["A_val"], v["head"], v["stat"], v["rho"])
+        scale = 1.0 + np.abs(v["rho"]).max() * np.abs(v["A_val"]).max()
+        assert np.max(np.abs(got[1:] - v["trow_vec"][1:])) <= 1e-12 * scale * 16, g
+        n_checked += 1
+    assert n_checked >= 20

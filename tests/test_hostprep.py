@@ -502,7 +502,7 @@ MAXIMIZE
  profit: 3 x + 2.5e0 y - z + 0 w
 Subject To
  c1: x + y + z <= 10
- - x + 2 y =< 1.5E+1       \\ trailing comment
+ - x + 2 y =< 1.5E+1
  c3: x - y => -4
  end_like: 2 end + x = 3
  x + .5 bin >= 0
@@ -548,7 +548,7 @@ def test_native_lp_reader_matches_the_facade_reader():
     fd, fnames = _facade_arrays(good)
     _same_arrays(d, fd)
     assert names == fnames
-    assert names["cols"] == ["x", "y", "z", "w", "end", "bin", "b1", "b2"] and names["rows"][1] == "r.2"
+    assert names["cols"] == ["x", "y", "z", "w", "end", "bin", "b1", "b2"] and names["rows"][1] == "r.6"   # "r." + line number
     t = dict(zip(names["cols"], d["type"][d["m"]:].tolist()))
     assert t == {"x": glpk.GLP_DB, "y": glpk.GLP_UP, "z": glpk.GLP_FR, "w": glpk.GLP_DB, "end": glpk.GLP_LO,
                  "bin": glpk.GLP_FX, "b1": glpk.GLP_DB, "b2": glpk.GLP_DB}
@@ -935,3 +935,46 @@ def test_simplex_table_rows_columns_and_ratio_tests():
         glpk.glp_eval_tab_row(P, nonbasic[0], ind, val)
     with pytest.raises(glpk.GlpkError, match="must be non-basic"):
         glpk.glp_eval_tab_col(P, head[0], ind, val)
+
+
+# ---- glpb_read_lp against the REFERENCE'S OWN reader (tests/golden/ref_reader_cases.json: lib/glpcpx.js
+#      executed by minijs, oracle/jsref/make_reader_golden.py) ----
+def _reader_cases():
+    import json
+    import os
+    with open(os.path.join(H.GOLDEN, "ref_reader_cases.json")) as f:
+        return json.load(f)
+
+
+@pytest.mark.parametrize("name", sorted(_reader_cases()))
+def test_native_reader_equals_the_references_reader(name):
+    rec = _reader_cases()[name]
+    if rec["rc"] != 0:
+        # same message; the reference prefixes the line number ("4: invalid symbol(s) ...")
+        line, msg = rec["error"].split(": ", 1)
+        with pytest.raises(ValueError) as ei:
+            nat.read_lp(rec["text"])
+        got = str(ei.value)
+        assert msg in got, (got, rec["error"])
+        if name not in ("missing_sense", "missing_rhs", "row_twice", "extra_after_end", "plus_inf_lower"):
+            assert ("line %s:" % line) in got, (got, rec["error"])      # errors raised while scanning: same line
+        return
+    d, names = nat.read_lp(rec["text"])
+    m, n = rec["m"], rec["n"]
+    assert (d["m"], d["n"], d["dir"]) == (m, n, rec["dir"]) and names["obj"] == rec["obj_name"]
+    assert names["rows"] == [r["name"] for r in rec["rows"]] and names["cols"] == [c["name"] for c in rec["cols"]]
+    assert d["type"][:m].tolist() == [r["type"] for r in rec["rows"]]
+    assert d["type"][m:].tolist() == [c["type"] for c in rec["cols"]]
+    assert d["lb"][:m].tolist() == [r["lb"] for r in rec["rows"]] and d["ub"][:m].tolist() == [r["ub"] for r in rec["rows"]]
+    assert d["lb"][m:].tolist() == [c["lb"] for c in rec["cols"]] and d["ub"][m:].tolist() == [c["ub"] for c in rec["cols"]]
+    assert d["coef"].tolist() == [c["coef"] for c in rec["cols"]]
+    # glp_get_col_kind reports GLP_BV (3) for an integer column with bounds [0, 1]; the stored kind is GLP_IV
+    assert d["kind"].tolist() == [2 if c["kind"] == 3 else c["kind"] for c in rec["cols"]]
+    for j in range(n):
+        a, b = d["A_ptr"][j], d["A_ptr"][j + 1]
+        got = [[int(i) + 1, float(v)] for i, v in zip(d["A_ind"][a:b], d["A_val"][a:b])]
+        assert got == rec["columns"][j], (j, got, rec["columns"][j])
+    # the facade goes through the same reader
+    P = glpk.glp_create_prob()
+    assert glpk.glp_read_lp_from_string(P, None, rec["text"]) == 0
+    assert [P.row[i].name for i in range(1, P.m + 1)] == names["rows"]

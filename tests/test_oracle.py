@@ -249,3 +249,28 @@ def test_oracle_matches_highs_on_knapsack_mips():
         assert abs(Q.solution()["obj"] - pin["lp_obj"]) <= 1e-9 * abs(pin["lp_obj"])
         assert Q.intopt() == 0 and Q.mip()["mip_stat"] == O.GLP_OPT
         assert abs(Q.mip()["mip_obj"] - pin["obj"]) <= 1e-9 * abs(pin["obj"]), (pin, Q.mip()["mip_obj"])
+
+
+def test_napi_shim_is_well_formed_c_and_create_validates_the_column_pointer():
+    """bindings/glpb200_napi.c cannot be loaded here (no Node.js): it is compiled against a
+    declarations-only stub of node_api.h so that it stays valid C; the C ABI itself rejects a
+    column pointer that is not a monotone prefix sum ending at nnz (no device needed for that)."""
+    import subprocess
+    root = os.path.abspath(os.path.join(H.HERE, ".."))
+    out = subprocess.run(["gcc", "-fsyntax-only", "-Wall", "-Werror", "-Wno-unused-function", "-I" + os.path.join(root, "tests", "napi_stub"),
+                          "-I" + os.path.join(root, "include"), os.path.join(root, "bindings", "glpb200_napi.c")],
+                         capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    src = open(os.path.join(root, "bindings", "glpb200_napi.c")).read()
+    for entry in ("Create", "SetBasis", "SetBounds", "Simplex", "Intopt", "GetSolution", "GetMip", "ScaleProb", "AdvBasis", "ReadLp"):
+        assert ("static napi_value %s(" % entry) in src
+    assert src.count("typed_n(") >= 3 and "typed(env" not in src          # every array goes through the checked accessor
+    import ctypes as C
+    L = nat.load()
+    t = np.array([3, 2, 2], np.int32)
+    z = np.zeros(3)
+    for bad_ptr in ([0, 2, 1], [1, 1, 2], [0, 1, 3]):
+        ptr = np.array(bad_ptr, np.int32)
+        h = L.glpb_create(1, 2, 2, 1, 0.0, t.ctypes.data, z.ctypes.data, z.ctypes.data, z[:2].ctypes.data, None, None, None,
+                          ptr.ctypes.data, np.zeros(2, np.int32).ctypes.data, np.ones(2).ctypes.data, 0)
+        assert not h and "A_ptr" in nat.last_error()
