@@ -51,7 +51,7 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 WORKLOADS = {
     "c3": dict(gen="covering", kw=dict(m=16384, n=32768, kmin=8, kspan=17, seed=20240601), meth="dual", pin="c3",
-               cpu_it_lim=1500, cpu_mid_lim=40, mid_basis="c3_mid_basis.npz",
+               cpu_it_lim=30, cpu_mid_lim=30, mid_basis="c3_mid_basis.npz",
                name="covering LP m=16384 n=32768 ~16 nnz/col, dual simplex, PSE pricing, Harris ratio test"),
     "c2": dict(gen="packing", kw=dict(m=2048, n=4096, density=0.20, seed=20240501), meth="primal", pin="c2",
                cpu_it_lim=600, cpu_mid=3000, cpu_mid_lim=150,
@@ -124,6 +124,24 @@ class ClockSampler:
                 "samples": len(sm), "reasons": reasons}
 
 
+def oracle_run_record(w):
+    """what the oracle's own uninterrupted solve of this workload in the build container has logged
+    (tests/golden/<pin>_oracle_run.json, written by tests/golden/make_c3_pins.py while it runs)"""
+    try:
+        with open(os.path.join(GOLDEN, w.get("pin", "-") + "_oracle_run.json")) as f:
+            r = json.load(f)
+        last = r["log"][-1]
+        out = {"complete": not r.get("partial", True), "iterations": int(r.get("it_cnt", last["it"])),
+               "seconds": round(float(r.get("seconds", last["seconds"])), 1), "cores": 1,
+               "where": "build container (not this box), one thread; tests/golden/make_c3_pins.py"}
+        out["iter_per_s"] = out["iterations"] / max(1e-9, out["seconds"])
+        if not out["complete"]:
+            out["note"] = "still running when committed: iterations done so far, the rate keeps falling"
+        return out
+    except Exception:
+        return None
+
+
 def to_oracle(d):
     m = d["m"]
     return dict(m=m, n=d["n"], dir=d["dir"], c0=d["c0"], r_type=d["type"][:m], r_lb=d["lb"][:m],
@@ -136,11 +154,17 @@ class CpuSampler:
     reference) on a BOUNDED sample of the workload, nothing of the product
     library involved: window A = the first cpu_it_lim iterations from the
     standard basis; window B = cpu_mid_lim iterations warm-started from a basis
-    deep inside the solve -- the oracle's own basis after 60000 iterations
-    (committed fixture, tests/golden/make_c3_pins.py) or, for the small
-    workloads, the basis the oracle reaches in an untimed set-up run.  The
-    iteration rate falls by orders of magnitude as the basis fills with
-    structural columns, so a start-only window would flatter the CPU."""
+    deep inside the solve -- the oracle's own basis after 60000 of the ~120000
+    iterations (committed fixture, tests/golden/make_c3_pins.py) or, for the
+    small workloads, the basis the oracle reaches in an untimed set-up run.
+    The time per iteration grows by three orders of magnitude as the basis
+    fills with structural columns (C3: 1200 it/s at the start, ~3 it/s at the
+    midpoint; tests/golden/c3_oracle_run.json), so for C3 both windows have the
+    SAME number of iterations: iterations / seconds over both is then the
+    inverse of the mean time per iteration at the two points, an estimate of
+    the full-solve rate; a start-only window would flatter the CPU a
+    hundredfold.  The oracle's own uninterrupted solve in the build container
+    is reported next to it as `full_solve` when it exists."""
 
     def __init__(self, w):
         import oracle_lib as O
@@ -211,12 +235,9 @@ def run_reference(args, w, rank):
             "cpu_baseline": {"value": val, "unit": "iter/s", "cores": 1, "kind": "port", "sample": smp.describe(),
                              "windows": smp.windows},
             "e2e": {"value": val, "unit": "iter/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    full = load_pins().get(w.get("pin", "-"), {}).get("oracle")
-    if full:
-        line["cpu_baseline"]["full_solve"] = {"iterations": full["it_cnt"], "seconds": round(full["seconds"], 1),
-                                              "iter_per_s": full["it_cnt"] / full["seconds"],
-                                              "where": "the oracle's own uninterrupted solve in the build container "
-                                                       "(tests/golden/make_c3_pins.py), not timed on this box"}
+    rec = oracle_run_record(w)
+    if rec:
+        line["cpu_baseline"]["oracle_run"] = rec
     print(json.dumps(line), flush=True)
 
 
@@ -296,7 +317,7 @@ def bnb_block(args, rank, local_rank, world, n_steps, n_warm):
     expected = pin.get("highs_obj")
     blk = {"metric": "bnb_nodes_per_sec", "value": value, "unit": "nodes/s", "n_gpus": world, "steps": n_steps,
            "warmup": n_warm, "ms_per_step": 1000.0 * my / max(1, n_steps), "scaling": "weak",
-           "node_lim_per_gpu": node_lim, "batch_per_gpu": args.bnb_batch or "4 x SM count", "host_threads_per_gpu": 1,
+           "node_lim_per_gpu": node_lim, "batch_per_gpu": args.bnb_batch or "16 x SM count", "host_threads_per_gpu": 1,
            "nodes_per_step": sum(nodes) / max(1, n_steps), "gpu_launches": int(launches) * world,
            "rounds_per_step": rounds / max(1, n_steps),
            "workload": w["name"],
@@ -445,7 +466,7 @@ def main():
     ap.add_argument("--no-c2", action="store_true", help="skip the nested solve of the 2048x4096 packing LP")
     ap.add_argument("--no-bnb", action="store_true", help="skip the branch-and-bound block")
     ap.add_argument("--bnb-nodes", type=int, default=0, help="node LPs per GPU and step of the bnb block (0 = 150000)")
-    ap.add_argument("--bnb-batch", type=int, default=0, help="open nodes per launch and GPU (0 = 4 x SM count)")
+    ap.add_argument("--bnb-batch", type=int, default=0, help="open nodes per launch and GPU (0 = 16 x SM count)")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
@@ -544,10 +565,9 @@ def main():
         smp = CpuSampler(w)
         itc, dt = smp.step()
         cpu = {"value": itc / dt, "unit": "iter/s", "cores": 1, "kind": "port", "sample": smp.describe(), "windows": smp.windows}
-        if pins.get("oracle"):
-            cpu["full_solve"] = {"iterations": pins["oracle"]["it_cnt"], "seconds": round(pins["oracle"]["seconds"], 1),
-                                 "iter_per_s": pins["oracle"]["it_cnt"] / pins["oracle"]["seconds"],
-                                 "where": "the oracle's own uninterrupted solve in the build container, not timed on this box"}
+        rec = oracle_run_record(w)
+        if rec:
+            cpu["oracle_run"] = rec
 
     # ---- nested: BASELINE.json configs[1], one step (rank 0, N=1) ----
     c2 = None

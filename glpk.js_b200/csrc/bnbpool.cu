@@ -48,7 +48,7 @@ extern "C" int glpb_bnb_begin(glpb_prob *P, const glpb_iocp *parm_, int batch, i
     if (P->bnb) { glpb_bnb_free(P->bnb); P->bnb = nullptr; }
     glpb_bnb *T = new glpb_bnb();
     T->tm_beg = now_ms();
-    if (batch <= 0) batch = env_int("GLPB_BNB_BATCH", 4 * (P->sm_count > 0 ? P->sm_count : 148));
+    if (batch <= 0) batch = env_int("GLPB_BNB_BATCH", 16 * (P->sm_count > 0 ? P->sm_count : 148));
     if (slab_nodes <= 0) slab_nodes = env_int("GLPB_BNB_SLAB", 262144);
     rc = T->init(P, parm, batch, slab_nodes);
     if (rc) { delete T; return rc; }

@@ -30,7 +30,9 @@
 #define GLPB_ENGINE_CUH
 #include "kernels.cuh"
 
+#ifndef ENG_NT
 #define ENG_NT 1024          /* threads per CTA                                  */
+#endif
 #define ENG_MAXG 160         /* scratch slot width (>= number of SMs)            */
 #define ENG_LCAP 2048        /* staged entries of one sparse column / row        */
 #define ENG_RING 4           /* rotating barrier slots                           */

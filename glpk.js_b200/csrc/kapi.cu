@@ -234,7 +234,8 @@ extern "C" int glpb_bench_kernel(const char *name, int m, int n, int reps, doubl
         for (int r = 0; r < reps; r++) k_update_rank1<<<grid, UPD_TB>>>(ctrl, T, ld, tc, rh, sp, sr);
         cudaEventRecord(e1);
         *bytes = 16.0 * k * (double)k;
-    } else if (nm == "chuzr_dual") {
+    } else if (nm == "chuzr_dual" || nm == "chuzr_dual_seq") {
+        const bool seq = (nm == "chuzr_dual_seq");     /* header in ascending order, as glp_factorize leaves it */
         /* 37 B per row: head, then type/lb/ub gathered through it, bbar, gamma; m rows,
            every basic variable a structural one of an n = m column problem */
         const int copies = 4;
@@ -242,7 +243,7 @@ extern "C" int glpb_bench_kernel(const char *name, int m, int n, int reps, doubl
         std::vector<double> lo(2 * (size_t)m), hi(2 * (size_t)m), bb(m), ga(m);
         std::vector<int> hd(m);
         for (int i = 0; i < m; i++) {
-            hd[i] = m + (int)(((unsigned)i * 2654435761u) % (unsigned)m);      /* scattered gather */
+            hd[i] = seq ? m + i : m + (int)(((unsigned)i * 2654435761u) % (unsigned)m);      /* scattered gather */
             bb[i] = ((i * 40503u) % 2001) / 1000.0 - 1.0; ga[i] = 1.0 + (i % 5);
         }
         for (size_t k = 0; k < 2 * (size_t)m; k++) { ty[k] = (signed char)(k % 3 == 0 ? GLP_DB : GLP_LO); lo[k] = -0.5; hi[k] = 0.5; }
@@ -278,10 +279,18 @@ extern "C" int glpb_bench_kernel(const char *name, int m, int n, int reps, doubl
         signed char *ds = t.up(st.data(), n);
         double *dr = t.up(rho.data(), m), *dtr = t.zero<double>(n), *dsv = t.zero<double>(n);
         if (!t.ok) return GLPB_ENOMEM;
-        const int g = (int)(((long)n * 8 + 255) / 256);
-        for (int r = 0; r < 3; r++) k_trow<8><<<g, 256>>>(ctrl, m, n, dp[0], di[0], dv[0], dh, ds, dr, nullptr, dtr, dsv, 1);
+        /* rho staged in shared memory when it fits (the C3 row count does): one CTA of 1024 threads per SM,
+           walking the columns with a grid stride, 4 columns per group and step */
+        const bool stage = (size_t)m * 8 <= 200 * 1024;
+        int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+        const int th = stage ? 1024 : 256;
+        const int g = stage ? sms : (int)std::min<long>((((long)n * 8 / 4) + 255) / 256, 148L * 64);
+        const size_t sh = stage ? (size_t)m * 8 : 0;
+        if (stage) cudaFuncSetAttribute(k_trow<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh);
+        const int wm = 1 | (stage ? 2 : 0);
+        for (int r = 0; r < 3; r++) k_trow<8><<<g, th, sh>>>(ctrl, m, n, dp[0], di[0], dv[0], dh, ds, dr, nullptr, dtr, dsv, wm);
         cudaEventRecord(e0);
-        for (int r = 0; r < reps; r++) { int c = r % copies; k_trow<8><<<g, 256>>>(ctrl, m, n, dp[c], di[c], dv[c], dh, ds, dr, nullptr, dtr, dsv, 1); }
+        for (int r = 0; r < reps; r++) { int c = r % copies; k_trow<8><<<g, th, sh>>>(ctrl, m, n, dp[c], di[c], dv[c], dh, ds, dr, nullptr, dtr, dsv, wm); }
         cudaEventRecord(e1);
         *bytes = 12.0 * (double)nnz + 13.0 * n + 8.0 * m;
     } else {

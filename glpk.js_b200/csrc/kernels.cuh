@@ -203,6 +203,33 @@ __device__ __forceinline__ void scan_chuzc_primal(Key &v, int start, int stride,
         price_primal(v, j, j == jx ? stx : (int)stat[j], cbar[j], gamma[j], tol_dj);
 }
 
+/* The same scan with 16-byte loads: a thread takes 4 consecutive columns per step (stat as
+   one 4-byte word, cbar and gamma as two double2 each: 68 bytes in flight per thread and step),
+   steps of one thread are independent so several are in flight.  The arrays must be 16-byte
+   (stat: 4-byte) aligned -- the handle's own arrays are; otherwise the scalar scan is used.
+   Selection is index-aware, so the visiting order does not matter. */
+__device__ __forceinline__ void scan_chuzc_primal_v4(Key &v, int tid, int nthreads, int n,
+                                                     const signed char *stat, const double *cbar,
+                                                     const double *gamma, double tol_dj)
+{
+    const int n4 = n >> 2;
+    const uchar4 *s4 = reinterpret_cast<const uchar4 *>(stat);
+    const double2 *c2 = reinterpret_cast<const double2 *>(cbar);
+    const double2 *g2 = reinterpret_cast<const double2 *>(gamma);
+#pragma unroll 2
+    for (int q = tid; q < n4; q += nthreads) {
+        const uchar4 st = __ldg(s4 + q);
+        const double2 ca = __ldg(c2 + 2 * q), cb = __ldg(c2 + 2 * q + 1);
+        const double2 ga = __ldg(g2 + 2 * q), gb = __ldg(g2 + 2 * q + 1);
+        const int j = q << 2;
+        price_primal(v, j, (signed char)st.x, ca.x, ga.x, tol_dj);
+        price_primal(v, j + 1, (signed char)st.y, ca.y, ga.y, tol_dj);
+        price_primal(v, j + 2, (signed char)st.z, cb.x, gb.x, tol_dj);
+        price_primal(v, j + 3, (signed char)st.w, cb.y, gb.y, tol_dj);
+    }
+    for (int j = (n4 << 2) + tid; j < n; j += nthreads) price_primal(v, j, stat[j], cbar[j], gamma[j], tol_dj);
+}
+
 /* Algorithmic bytes: 17 per column (stat 1 + cbar 8 + gamma 8). */
 __global__ void k_chuzc_primal(Ctrl *ctrl, int n, const signed char *__restrict__ stat,
                                const double *__restrict__ cbar, const double *__restrict__ gamma,
@@ -211,6 +238,10 @@ __global__ void k_chuzc_primal(Ctrl *ctrl, int n, const signed char *__restrict_
     if (ctrl->status != ST_OK) return;
     Key none = {0.0, 0.0, 0.0, INT_MAX, 0};
     Key v = none;
+    const bool aligned = (((uintptr_t)stat & 3) | ((uintptr_t)cbar & 15) | ((uintptr_t)gamma & 15)) == 0;
+    if (aligned)
+        scan_chuzc_primal_v4(v, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x, n, stat, cbar, gamma, tol_dj);
+    else
     scan_chuzc_primal(v, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x, n, stat, cbar, gamma,
                       tol_dj, -1, 0);
     grid_reduce(v, none, scratch, &ctrl->ticket[0], CombArgMax(), [=](const Key &r) {
@@ -262,8 +293,28 @@ __global__ void k_chuzr_dual(Ctrl *ctrl, int m, const signed char *__restrict__ 
     if (ctrl->status != ST_OK) return;
     Key none = {0.0, 0.0, 0.0, INT_MAX, 0};
     Key v = none;
-    scan_chuzr_dual(v, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x, m, type, lb, ub, head,
-                    bbar, gamma, tol_bnd, -1, 0);
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    if ((((uintptr_t)head & 15) | ((uintptr_t)bbar & 15) | ((uintptr_t)gamma & 15)) == 0) {
+        /* 4 basic positions per step: head as one int4, bbar / gamma as two double2 each; the 12
+           gathers of type / lb / ub through head are issued together before any is used */
+        const int m4 = m >> 2;
+        const int4 *h4 = reinterpret_cast<const int4 *>(head);
+        const double2 *b2 = reinterpret_cast<const double2 *>(bbar), *g2 = reinterpret_cast<const double2 *>(gamma);
+        for (int q = tid; q < m4; q += nth) {
+            const int4 k = __ldg(h4 + q);
+            const double2 ba = __ldg(b2 + 2 * q), bb = __ldg(b2 + 2 * q + 1), ga = __ldg(g2 + 2 * q), gb = __ldg(g2 + 2 * q + 1);
+            const int t0 = type[k.x], t1 = type[k.y], t2 = type[k.z], t3 = type[k.w];
+            const double l0 = lb[k.x], l1 = lb[k.y], l2 = lb[k.z], l3 = lb[k.w];
+            const double u0 = ub[k.x], u1 = ub[k.y], u2 = ub[k.z], u3 = ub[k.w];
+            const int i = q << 2;
+            price_dual(v, i, t0, l0, u0, ba.x, ga.x, tol_bnd);
+            price_dual(v, i + 1, t1, l1, u1, ba.y, ga.y, tol_bnd);
+            price_dual(v, i + 2, t2, l2, u2, bb.x, gb.x, tol_bnd);
+            price_dual(v, i + 3, t3, l3, u3, bb.y, gb.y, tol_bnd);
+        }
+        scan_chuzr_dual(v, (m4 << 2) + tid, nth, m, type, lb, ub, head, bbar, gamma, tol_bnd, -1, 0);
+    } else
+    scan_chuzr_dual(v, tid, nth, m, type, lb, ub, head, bbar, gamma, tol_bnd, -1, 0);
     grid_reduce(v, none, scratch, &ctrl->ticket[0], CombArgMax(), [=](const Key &r) {
         bool found = (r.a > 0.0 && r.pos != INT_MAX);
         ctrl->p = found ? r.pos : P_NONE;
@@ -530,35 +581,68 @@ __global__ void k_trow(Ctrl *ctrl, int m, int n, const int *__restrict__ a_ptr,
 {
     if (ctrl->status != ST_OK) return;
     if (u != nullptr && !gamma_on(ctrl)) u = nullptr;   /* PSE inner products only while weights are live */
-    const int gid = (blockIdx.x * blockDim.x + threadIdx.x) / G;
+    /* every group of G lanes takes TROW_C columns per step and walks them in lock step, so the
+       dependent chain stat -> head -> a_ptr -> (a_ind, a_val) -> rho of one column overlaps with
+       the chains of the others (the pass is latency-, not bandwidth-limited otherwise) */
+    constexpr int C = 4;
+    /* launched with m*8 bytes of dynamic shared memory (want_max & 2): rho is staged there once per
+       CTA, so that the 16 gathers per column hit shared memory instead of L1/L2 */
+    extern __shared__ double trow_sh_rho[];
+    if (want_max & 2) {
+        for (int r = threadIdx.x; r < m; r += blockDim.x) trow_sh_rho[r] = rho[r];
+        __syncthreads();
+        rho = trow_sh_rho;
+    }
+    const int ngroups = (gridDim.x * blockDim.x) / G;
+    const int g0 = (blockIdx.x * blockDim.x + threadIdx.x) / G;
     const int lane = threadIdx.x % G;
-    double t = 0.0, s = 0.0;
-    bool live = (gid < n) && stat[gid] != GLP_NS;
-    if (live) {
-        int k = head[m + gid];
-        if (k < m) {
-            if (lane == 0) { t = -rho[k]; if (u) s = u[k]; }
-        } else {
-            int beg = a_ptr[k - m], end = a_ptr[k - m + 1];
-            for (int ptr = beg + lane; ptr < end; ptr += G) {
-                int r = a_ind[ptr];
-                double a = a_val[ptr];
-                t += rho[r] * a;
-                if (u) s -= a * u[r];
+    double amax = 0.0;
+    for (int base = g0 * C;; base += ngroups * C) {
+        if (__all_sync(FULLMASK, base >= n)) break;         /* the groups of a warp leave together: shuffles below */
+        int beg[C], end[C], kk[C];
+        double t[C], s[C];
+#pragma unroll
+        for (int c = 0; c < C; c++) {
+            const int j = base + c;
+            t[c] = s[c] = 0.0; beg[c] = end[c] = 0; kk[c] = -1;
+            if (j < n && stat[j] != GLP_NS) kk[c] = head[m + j];
+        }
+#pragma unroll
+        for (int c = 0; c < C; c++)
+            if (kk[c] >= m) { beg[c] = a_ptr[kk[c] - m]; end[c] = a_ptr[kk[c] - m + 1]; }
+            else if (kk[c] >= 0 && lane == 0) { t[c] = -rho[kk[c]]; if (u) s[c] = u[kk[c]]; }
+        int len = 0;
+#pragma unroll
+        for (int c = 0; c < C; c++) len = max(len, end[c] - beg[c]);
+        for (int o = lane; o < len; o += G) {
+            int r[C]; double a[C];
+#pragma unroll
+            for (int c = 0; c < C; c++) {
+                const bool in = beg[c] + o < end[c];
+                r[c] = in ? a_ind[beg[c] + o] : -1;
+                a[c] = in ? a_val[beg[c] + o] : 0.0;
+            }
+#pragma unroll
+            for (int c = 0; c < C; c++)
+                if (r[c] >= 0) { t[c] += rho[r[c]] * a[c]; if (u) s[c] -= a[c] * u[r[c]]; }
+        }
+#pragma unroll
+        for (int c = 0; c < C; c++) {
+            t[c] = group_sum<G>(t[c]);
+            if (u) s[c] = group_sum<G>(s[c]);
+            const int j = base + c;
+            if (j < n && lane == 0) {
+                trow[j] = t[c];
+                if (u) svec[j] = s[c];
+                amax = fmax(amax, fabs(t[c]));
             }
         }
     }
-    t = group_sum<G>(t);
-    if (u) s = group_sum<G>(s);
-    if (gid < n && lane == 0) {
-        trow[gid] = t;
-        if (u) svec[gid] = s;
-    }
-    if (want_max) {
+    if (want_max & 1) {
         /* |trow|_inf: warp max, then one atomic per block (bit pattern of a
            non-negative double orders like an unsigned integer) */
         __shared__ double wmax[32];
-        double a = (gid < n && lane == 0) ? fabs(t) : 0.0;
+        double a = amax;
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) a = fmax(a, __shfl_down_sync(FULLMASK, a, off));
         if ((threadIdx.x & 31) == 0) wmax[threadIdx.x >> 5] = a;

@@ -11,7 +11,7 @@ import subprocess
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libglpb200.so")
+LIB_PATH = os.environ.get("GLPB_LIB") or os.path.join(HERE, "libglpb200.so")     # GLPB_LIB: another build of the same library (experiments)
 CSRC = os.path.join(HERE, "csrc")
 
 # ---- GLP_* constants (lib/glpk.js) ----

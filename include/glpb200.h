@@ -137,7 +137,7 @@ int glpb_mip_end(glpb_prob *P, int ret);
  * Driebeck-Tomlin choice and branch_on; the host only keeps the tree.
  * glpb_intopt takes this path by itself for eligible problems (environment
  * GLPB_BNB=serial keeps the one-LP-at-a-time driver).
- *   begin:  batch <= 0 -> 4 x SM count (GLPB_BNB_BATCH), slab_nodes <= 0 ->
+ *   begin:  batch <= 0 -> 16 x SM count (GLPB_BNB_BATCH), slab_nodes <= 0 ->
  *           262144 (GLPB_BNB_SLAB); the root LP must be solved (GLP_EROOT).
  *   round:  1 = a round was run (*done nodes), 0 = local pool empty,
  *           GLP_ETMLIM / GLP_ESTOP (node_lim) / GLP_EMIPGAP / GLP_EFAIL.

@@ -33,7 +33,9 @@ def to_oracle(d):
                 c_coef=d["coef"], c_kind=d["kind"], A_ptr=d["A_ptr"], A_ind=d["A_ind"], A_val=d["A_val"])
 
 
-def highs(d):
+def highs(d, method="highs"):
+    """method "highs" = HiGHS' choice (dual simplex; fine for C2, did not finish C3 within 2.3 h in the
+    build container), "highs-ipm" = interior point with crossover (C3: 329 s)"""
     from scipy.optimize import linprog
     from scipy.sparse import csc_matrix, vstack
     m, n = d["m"], d["n"]
@@ -50,10 +52,10 @@ def highs(d):
         bounds.append((lb[m + j] if tj in (O.GLP_LO, O.GLP_DB, O.GLP_FX) else None,
                        ub[m + j] if tj in (O.GLP_UP, O.GLP_DB, O.GLP_FX) else None))
     t0 = time.time()
-    r = linprog(sign * d["coef"], A_ub=A_ub, b_ub=b_ub, bounds=bounds, method="highs",
+    r = linprog(sign * d["coef"], A_ub=A_ub, b_ub=b_ub, bounds=bounds, method=method,
                 options=dict(primal_feasibility_tolerance=1e-9, dual_feasibility_tolerance=1e-9))
     return dict(status=int(r.status), obj=float(sign * r.fun), seconds=time.time() - t0,
-                nit=int(getattr(r, "nit", -1)))
+                nit=int(getattr(r, "nit", -1)), method=method)
 
 
 def load_pins():
@@ -62,8 +64,11 @@ def load_pins():
 
 
 def save_pins(pins):
+    merged = load_pins()            # other modes of this script may have written in the meantime
+    for k, v in pins.items():
+        merged.setdefault(k, {}).update(v)
     with open(os.path.join(HERE, "lp_pins.json"), "w") as f:
-        json.dump(pins, f, indent=1, sort_keys=True)
+        json.dump(merged, f, indent=1, sort_keys=True)
 
 
 def oracle_run(cfg, name, meth, snap_every, mid_at):
@@ -117,7 +122,7 @@ if __name__ == "__main__":
         for name, cfg in (("c2", C2), ("c3", C3)):
             d = O.generate(cfg["which"], **cfg["kw"])
             pins.setdefault(name, {})["config"] = dict(cfg["kw"], gen=cfg["which"], nnz=int(d["nnz"]))
-            pins[name]["highs"] = highs(d)
+            pins[name]["highs"] = highs(d, "highs" if name == "c2" else "highs-ipm")
             print(name, pins[name]["highs"], flush=True)
             save_pins(pins)
     elif what == "highs-mkp":

@@ -182,6 +182,6 @@ def test_sharded_driver_single_rank_on_device():
     Q = nat.Problem(nat.generate("mkp", m=30, n=500, seed=20240701))
     assert Q.simplex(meth=nat.GLP_PRIMAL) == 0
     r2 = bnb.sharded_bnb_batched(bnb.BatchWorker(Q), bnb.TensorComm(), minimize=False, node_lim=5000)
-    assert r2["ret"] == 0 and 5000 <= r2["total_nodes"] < 5000 + 3 * 592 * 2 and r2["open_left"] > 0
+    assert r2["ret"] == 0 and 5000 <= r2["total_nodes"] < 5000 + 3 * 2368 * 2 and r2["open_left"] > 0
     P.close()
     Q.close()

@@ -22,6 +22,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 # objective of C2 (packing LP 2048 x 4096, seed 20240501) from a full solve of the
 # oracle (228 s on the build container); the device must reproduce it to 1e-9
 C2_OBJ = 89464.4101453462
+# independent optima of both benchmark LPs from HiGHS (tests/golden/make_c3_pins.py)
+with open(os.path.join(HERE, "golden", "lp_pins.json")) as _f:
+    LP_PINS = json.load(_f)
 
 
 def solve_in_subprocess(args, env=None, timeout=600):
@@ -81,6 +84,8 @@ def test_c2_full_size_objective_and_kkt():
     r = solve_in_subprocess(["packing", 2048, 4096])
     assert (r["rc"], r["status"]) == (0, O.GLP_OPT)
     assert abs(r["obj"] - C2_OBJ) <= 1e-9 * C2_OBJ, r["obj"]
+    hp = LP_PINS["c2"]["highs"]
+    assert hp["status"] == 0 and abs(r["obj"] - hp["obj"]) <= 1e-9 * abs(hp["obj"]), (r["obj"], hp["obj"])   # independent solver
     assert max(r["kkt"].values()) <= 1e-9, r["kkt"]
     assert r["launches"] < r["it"], "the iterations must run inside the persistent engine"
 
@@ -93,6 +98,8 @@ def test_c3_full_size_properties():
     r = solve_in_subprocess(["covering", 16384, 32768], timeout=900)
     assert (r["rc"], r["status"]) == (0, O.GLP_OPT)
     assert max(r["kkt"].values()) <= 1e-9, r["kkt"]
+    hp = LP_PINS["c3"]["highs"]           # HiGHS interior point + crossover, 329 s in the build container
+    assert hp["status"] == 0 and abs(r["obj"] - hp["obj"]) <= 1e-9 * abs(hp["obj"]), (r["obj"], hp["obj"])
     assert r["k"] > 2560, "kernel larger than the shared-memory panel: distributed mode was exercised"
     # same optimum whichever way the basis changes are applied
     r2 = solve_in_subprocess(["covering", 16384, 32768], {"GLPB_DEFER": "0", "GLPB_REFAC_DIV": "4"}, timeout=900)

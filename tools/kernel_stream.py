@@ -17,8 +17,10 @@ try:
 except Exception:
     pass
 cases = [("chuzc_primal", 0, n) for n in (4096, 32768, 1 << 20, 1 << 24, 1 << 26)]
-cases += [("chuzr_dual", m, 0) for m in (16384, 1 << 20, 1 << 24)]
-cases += [("trow", 16384, 32768), ("trow", 1 << 20, 1 << 21), ("trow", 1 << 22, 1 << 23)]
+cases += [("chuzr_dual", m, 0) for m in (16384, 1 << 20, 1 << 24)]          # basis header scattered at random
+cases += [("chuzr_dual_seq", m, 0) for m in (1 << 20, 1 << 24)]             # header ascending (as after glp_factorize)
+cases += [("trow", 16384, 32768), ("trow", 1 << 20, 1 << 21), ("trow", 1 << 22, 1 << 23)]    # rho gathered from 8-32 MB (L2)
+cases += [("trow", 16384, 1 << 22), ("trow", 65536, 1 << 23)]                                 # the C3 row count, more columns
 cases += [("update_rank1", k, 0) for k in (609, 2048, 6353)]
 print("peak (measured copy) %.1f GB/s" % peak)
 for name, m, n in cases:
