@@ -885,6 +885,16 @@ struct Loop : Dev {
         P->n_launch++; P->n_eng_launch++;
         int rc = sync_ctrl(P);
         if (rc == 0 && P->prof) P->n_eng_prof_iter[dual ? 1 : 0] += P->h_ctrl->n_done;
+        /* GLPB_ENG_LOG=file: one line per engine launch (ordinal, iterations, kernel size) so that an ncu
+           capture of launch number i can be put per iteration */
+        static const char *logf = getenv("GLPB_ENG_LOG");
+        if (rc == 0 && logf) {
+            if (FILE *f = fopen(logf, "a")) {
+                fprintf(f, "%ld %s iters %d k %d status %d\n", (long)P->n_eng_launch, dual ? "dual" : "primal",
+                        P->h_ctrl->n_done, P->h_ctrl->k, P->h_ctrl->status);
+                fclose(f);
+            }
+        }
         return rc;
     }
 
