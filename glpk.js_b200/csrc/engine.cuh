@@ -36,6 +36,9 @@
 #define ENG_MAXG 160         /* scratch slot width (>= number of SMs)            */
 #define ENG_LCAP 2048        /* staged entries of one sparse column / row        */
 #define ENG_RING 4           /* rotating barrier slots                           */
+#ifndef ENG_SU
+#define ENG_SU 8            /* columns per trip of the dense stream's load loop   */
+#endif
 #define ENG_DB 32            /* deferred basis changes before T is rewritten     */
 
 /* one 128-byte line per (ring slot, CTA): the arrival flag and the partial
@@ -56,6 +59,7 @@ struct EngArgs {
     const int *a_ptr, *a_ind; const double *a_val;
     const int *at_ptr, *at_ind; const double *at_val;
     signed char *type, *stat, *refsp;
+    const signed char *orig_type; /* types of the problem itself (dual phase 1 works on modified ones) */
     double *lb, *ub, *coef;
     int *head, *bind;
     double *bbar, *cbar, *gamma, *tcol, *trow, *rho, *svec;
@@ -76,6 +80,8 @@ struct EngArgs {
     int use_tma;              /* 1: TMA-staged dense T*v stream where it applies */
     int hdr_smem;             /* 1: keep per-CTA copies of the basis header in shared memory */
     int local_max;            /* ratio tests up to this length are replicated per CTA */
+    int pf_dist;              /* dense T*v stream: L2 prefetch distance in column steps (0 = off) */
+    int tie_stop;             /* 1: an exact tie in a ratio test stops the engine (ST_TIE)  */
     int *rslot, *slot_pos, *cslot, *slot_row;
     EngSlot *slots;           /* [ENG_RING][ENG_MAXG] arrival flags + CTA partials, zeroed by the host */
     long long *prof_cyc;      /* optional: SM cycles per phase, CTA 0 (NULL = off)  */
@@ -207,11 +213,7 @@ __device__ Key eng_allreduce(EngCtx &X, const EngArgs &A, Key v, const Key &none
             r.a = __ldcg(&sl->a); r.b = __ldcg(&sl->b); r.c = __ldcg(&sl->c);
             r.pos = __ldcg(&sl->pos); r.aux = __ldcg(&sl->aux);
         }
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            Key o = key_shfl_down(r, off);
-            comb(r, o);
-        }
+        r = warp_reduce(r, none, comb);
         if (X.lane == 0) wres[X.warp] = r;
     }
     __syncthreads();
@@ -364,12 +366,26 @@ __device__ void eng_gemv_rows(const EngCtx &X, const EngArgs &A, int k, int L, c
             double ax0 = 0.0, ay0 = 0.0, ax1 = 0.0, ay1 = 0.0;
             int e = cfirst;
             if (in0) {
-                for (; e + 7 * cstep < L; e += 8 * cstep) {
-                    double2 t[8];
+                /* Under the 64-register cap of a 1024-thread CTA ptxas keeps only three of the eight loads of
+                   a trip in flight (SASS: the destinations R16/R20/R24 are reused), which leaves the stream
+                   short of memory-level parallelism.  The sectors are therefore requested from DRAM a little
+                   ahead of the loads with prefetch.global.L2 -- no register, no shared memory: every even lane
+                   asks for the 32-byte sector it shares with its neighbour, pf_dist column steps ahead
+                   (measured on C3: distance 1-2 steps = 32-64 columns, 3-7 MB in flight over the chip, -3.6 %
+                   solve time; 8 trips ahead and more thrash L2 and cost 8 %; profiles/r02j_pf_sweep.txt). */
+                const size_t pfo = (size_t)A.pf_dist * cstep * ldt;
+                const bool pfl = A.pf_dist > 0 && !(X.lane & 1);
+                for (; e + (ENG_SU - 1) * cstep < L; e += ENG_SU * cstep) {
+                    if (pfl && e + (A.pf_dist + ENG_SU) * cstep <= L) {
 #pragma unroll
-                    for (int x = 0; x < 8; x++) t[x] = __ldcg((const double2 *)(Tb2 + (size_t)(e + x * cstep) * ldt));
+                        for (int x = 0; x < ENG_SU; x++)
+                            asm volatile("prefetch.global.L2 [%0];" ::"l"(Tb2 + (size_t)(e + x * cstep) * ldt + pfo));
+                    }
+                    double2 t[ENG_SU];
 #pragma unroll
-                    for (int x = 0; x < 8; x += 2) {
+                    for (int x = 0; x < ENG_SU; x++) t[x] = __ldcg((const double2 *)(Tb2 + (size_t)(e + x * cstep) * ldt));
+#pragma unroll
+                    for (int x = 0; x < ENG_SU; x += 2) {
                         const double v0 = val[e + x * cstep], v1 = val[e + (x + 1) * cstep];
                         ax0 += t[x].x * v0; ay0 += t[x].y * v0;
                         ax1 += t[x + 1].x * v1; ay1 += t[x + 1].y * v1;
@@ -671,6 +687,42 @@ __device__ __forceinline__ void eng_ftran_tail(const EngCtx &X, const EngArgs &A
         });
 }
 
+/* two FTRAN tails in one pass over the rows of A (dual engine: tcol from (hz, ycol) and the tail of
+   u = inv(B) v from (v, ycol2)): the row's indices and values are loaded once, the dependent chain
+   head -> at_ptr -> (at_ind, at_val) -> gather is walked once instead of twice */
+__device__ __forceinline__ void eng_ftran_tail2(const EngCtx &X, const EngArgs &A,
+                                                const double *h1, const double *ycol1, double *x1,
+                                                const double *h2, const double *ycol2, double *x2)
+{
+    const int m = A.m;
+    const int LP = eng_pick_lp(X, m, A.avg_row);
+    eng_items<2>(X, m, LP,
+        [&](int i, int l, int lp, double *a) {
+            const int kk = X.head[i];
+            if (kk >= m) return;
+            const int beg = __ldg(A.at_ptr + kk), end = __ldg(A.at_ptr + kk + 1);
+            double p0 = 0.0, p1 = 0.0, q0 = 0.0, q1 = 0.0;
+            int ptr = beg + l;
+            for (; ptr + lp < end; ptr += 2 * lp) {
+                const int c0 = __ldg(A.at_ind + ptr), c1 = __ldg(A.at_ind + ptr + lp);
+                const double v0 = __ldg(A.at_val + ptr), v1 = __ldg(A.at_val + ptr + lp);
+                const double y0 = ycol1[c0], y1 = ycol1[c1], z0 = ycol2[c0], z1 = ycol2[c1];
+                p0 += v0 * y0; p1 += v1 * y1; q0 += v0 * z0; q1 += v1 * z1;
+            }
+            if (ptr < end) {
+                const int c0 = __ldg(A.at_ind + ptr);
+                const double v0 = __ldg(A.at_val + ptr);
+                p0 += v0 * ycol1[c0]; q0 += v0 * ycol2[c0];
+            }
+            a[0] = p0 + p1; a[1] = q0 + q1;
+        },
+        [&](int i, const double *a) {
+            const int kk = X.head[i];
+            if (kk < m) { x1[i] = h1[kk] + a[0]; x2[i] = h2[kk] + a[1]; }
+            else { x1[i] = ycol1[kk - m]; x2[i] = ycol2[kk - m]; }
+        });
+}
+
 /* BTRAN, first half: w[b] = c[pos_b] + sum_{r in R_B} A[r, j_b] c[bind[r]],
    with c given by position (v) and by row of a basic auxiliary (vrow) */
 __device__ __forceinline__ void eng_btran_head(const EngCtx &X, const EngArgs &A, int k)
@@ -721,9 +773,22 @@ __device__ void eng_rho(EngCtx &X, const EngArgs &A, int k, int p, int nd)
         if (nd > 0) __syncthreads();
         const double *row = A.T + bp;
         for (int cs = X.gtid; cs < k; cs += X.gsize) {
-            double a = __ldcg(row + (size_t)cs * ldt);
-            for (int j = 0; j < nd; j++) a += fs[j] * A.Rd[(size_t)j * ldt + cs];
-            A.rho[X.slot_row[cs]] = a;
+            /* the strided element of T, the slot's row and the deferred terms are independent loads: all
+               issued before the first use (a chain of nd dependent L2 round trips otherwise) */
+            const double t0 = __ldcg(row + (size_t)cs * ldt);
+            const int r = X.slot_row[cs];
+            const double *Rc = A.Rd + cs;
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+            int j = 0;
+            for (; j + 7 < nd; j += 8) {
+                const double r0 = Rc[(size_t)j * ldt], r1 = Rc[(size_t)(j + 1) * ldt], r2 = Rc[(size_t)(j + 2) * ldt],
+                             r3 = Rc[(size_t)(j + 3) * ldt], r4 = Rc[(size_t)(j + 4) * ldt], r5 = Rc[(size_t)(j + 5) * ldt],
+                             r6 = Rc[(size_t)(j + 6) * ldt], r7 = Rc[(size_t)(j + 7) * ldt];
+                a0 += fs[j] * r0; a1 += fs[j + 1] * r1; a2 += fs[j + 2] * r2; a3 += fs[j + 3] * r3;
+                a0 += fs[j + 4] * r4; a1 += fs[j + 5] * r5; a2 += fs[j + 6] * r6; a3 += fs[j + 7] * r7;
+            }
+            for (; j < nd; j++) a0 += fs[j] * Rc[(size_t)j * ldt];
+            A.rho[r] = t0 + ((a0 + a1) + (a2 + a3));
         }
         return;
     }
@@ -1249,7 +1314,7 @@ __global__ void __launch_bounds__(ENG_NT, 1) k_engine_primal(EngArgs A)
                     if (ok[x]) { const Key c = ratio_primal_key(cand[x], 1, pos); CombRatio1()(v, c); }
                 }
                 Key r = eng_blockall(X, v, none, CombRatio1());
-                if (X.tid == 0) fin_ratio_primal(&S, r, 1, sgn, A.rtol, nullptr);
+                if (X.tid == 0) fin_ratio_primal(&S, r, 1, sgn, A.rtol, nullptr, A.tie_stop != 0);
                 __syncthreads();
                 if (S.status == ST_OK && !S.skip2) {
                     const double tmax = S.tmax;
@@ -1261,21 +1326,21 @@ __global__ void __launch_bounds__(ENG_NT, 1) k_engine_primal(EngArgs A)
                             CombRatio2()(v, c);
                         }
                     r = eng_blockall(X, v, none, CombRatio2());
-                    if (X.tid == 0) fin_ratio_primal(&S, r, 2, sgn, A.rtol, nullptr);
+                    if (X.tid == 0) fin_ratio_primal(&S, r, 2, sgn, A.rtol, nullptr, A.tie_stop != 0);
                     __syncthreads();
                 }
             } else {
                 scan_ratio_primal(v, X.tid, ENG_NT, 1, S.phase, sgn, S.eps, 0.0, A.rtol, A.type, A.lb, A.ub,
                                   A.coef, X.head, A.bbar, A.tcol, nullptr, m);
                 Key r = eng_blockall(X, v, none, CombRatio1());
-                if (X.tid == 0) fin_ratio_primal(&S, r, 1, sgn, A.rtol, nullptr);
+                if (X.tid == 0) fin_ratio_primal(&S, r, 1, sgn, A.rtol, nullptr, A.tie_stop != 0);
                 __syncthreads();
                 if (S.status == ST_OK && !S.skip2) {
                     v = none;
                     scan_ratio_primal(v, X.tid, ENG_NT, 2, S.phase, sgn, S.eps, S.tmax, A.rtol, A.type, A.lb, A.ub,
                                       A.coef, X.head, A.bbar, A.tcol, nullptr, m);
                     r = eng_blockall(X, v, none, CombRatio2());
-                    if (X.tid == 0) fin_ratio_primal(&S, r, 2, sgn, A.rtol, nullptr);
+                    if (X.tid == 0) fin_ratio_primal(&S, r, 2, sgn, A.rtol, nullptr, A.tie_stop != 0);
                     __syncthreads();
                 }
             }
@@ -1297,7 +1362,7 @@ __global__ void __launch_bounds__(ENG_NT, 1) k_engine_primal(EngArgs A)
             Key r = eng_allreduce(X, A, v, none, CombRatio1());
             if (X.cta == 0 && X.tid == 0) A.cbar[q] = S.d1;     /* every CTA has read the old value by now */
             cbar_q_pending = false;
-            if (X.tid == 0) fin_ratio_primal(&S, r, 1, sgn, A.rtol, nullptr);
+            if (X.tid == 0) fin_ratio_primal(&S, r, 1, sgn, A.rtol, nullptr, A.tie_stop != 0);
             __syncthreads();
             eng_mark(X, A, PP_R1, 45.0 * m);
             if (S.status == ST_OK && !S.skip2) {
@@ -1305,7 +1370,7 @@ __global__ void __launch_bounds__(ENG_NT, 1) k_engine_primal(EngArgs A)
                 scan_ratio_primal(v, X.gtid, X.gsize, 2, S.phase, sgn, S.eps, S.tmax, A.rtol, A.type, A.lb, A.ub,
                                   A.coef, X.head, A.bbar, A.tcol, nullptr, m);
                 r = eng_allreduce(X, A, v, none, CombRatio2());
-                if (X.tid == 0) fin_ratio_primal(&S, r, 2, sgn, A.rtol, nullptr);
+                if (X.tid == 0) fin_ratio_primal(&S, r, 2, sgn, A.rtol, nullptr, A.tie_stop != 0);
                 __syncthreads();
                 eng_mark(X, A, PP_R2, 45.0 * m);
             }
@@ -1418,11 +1483,30 @@ __global__ void __launch_bounds__(ENG_NT, 1) k_engine_primal(EngArgs A)
                 }
                 price_primal(pv, t, st, dj, g, A.tol_dj);
             }
-            for (int t = X.gtid; t < m; t += X.gsize) {
-                if (t == p) A.bbar[t] = xq + teta;
-                else if (teta != 0.0) {
-                    const double tc = A.tcol[t];
-                    if (tc != 0.0) A.bbar[t] += tc * teta;
+            /* phase 1: does anything still violate its bound after this iteration (check_feas at the top of
+               the reference's next iteration, lib/glpspx01.js:1768-1775)?  The count rides on the pricing key. */
+            int ninf = 0;
+            if (phase != 1) {
+                for (int t = X.gtid; t < m; t += X.gsize) {
+                    if (t == p) A.bbar[t] = xq + teta;
+                    else if (teta != 0.0) {
+                        const double tc = A.tcol[t];
+                        if (tc != 0.0) A.bbar[t] += tc * teta;
+                    }
+                }
+            } else {
+                for (int t = X.gtid; t < m; t += X.gsize) {
+                    double b;
+                    if (t == p) { b = xq + teta; A.bbar[t] = b; continue; }      /* xN[q] enters with a zero auxiliary cost */
+                    b = A.bbar[t];
+                    if (teta != 0.0) {
+                        const double tc = A.tcol[t];
+                        if (tc != 0.0) { b += tc * teta; A.bbar[t] = b; }
+                    }
+                    const int k = X.head[t];
+                    const double c = A.coef[k];
+                    if (c < 0.0) ninf += (b < A.lb[k] - relax(A.tol_bnd, A.lb[k])) ? 1 : 0;
+                    else if (c > 0.0) ninf += (b > A.ub[k] + relax(A.tol_bnd, A.ub[k])) ? 1 : 0;
                 }
             }
             /* keep the dense right-hand side of eval_tcol all-zero */
@@ -1433,8 +1517,10 @@ __global__ void __launch_bounds__(ENG_NT, 1) k_engine_primal(EngArgs A)
                         A.hz[__ldg(A.a_ind + ptr)] = 0.0;
             }
             if (p >= 0 && S.k + (C.bnew >= 0) > 0) eng_update_T(X, A, C);
-            Key r = eng_allreduce(X, A, pv, pnone, CombArgMax());
+            pv.aux = ninf;
+            Key r = eng_allreduce(X, A, pv, pnone, CombArgMaxCnt());
             qnext = (r.a > 0.0 && r.pos != INT_MAX) ? r.pos : P_NONE;
+            const bool feasible_now = (phase == 1 && r.aux == 0);
             eng_mark(X, A, PP_F, 24.0 * m + 17.0 * n + (p >= 0 ? 40.0 * n + 16.0 * S.k * (double)S.k : 0.0));
             /* the O(1) remainder: every CTA has arrived, nobody reads the old header any more */
             if (X.tid == 0) {
@@ -1449,6 +1535,7 @@ __global__ void __launch_bounds__(ENG_NT, 1) k_engine_primal(EngArgs A)
             if (X.tid == 0) {
                 if (p >= 0) S.k = C.knew;
                 iter_end(&S, p >= 0, 0);
+                if (feasible_now && S.status == ST_OK) S.status = ST_PHASE;
             }
             eng_header_done(X, A);
         }
@@ -1529,13 +1616,13 @@ __global__ void __launch_bounds__(ENG_NT, 1) k_engine_dual(EngArgs A)
             Key v = none;
             scan_ratio_dual(v, X.tid, ENG_NT, 1, sgn, S.eps, 0.0, A.rtol, X.stat, A.cbar, A.trow, nullptr, n);
             Key r = eng_blockall(X, v, none, CombRatio1());
-            if (X.tid == 0) fin_ratio_dual(&S, r, 1, sgn, A.rtol, nullptr);
+            if (X.tid == 0) fin_ratio_dual(&S, r, 1, sgn, A.rtol, nullptr, A.tie_stop != 0);
             __syncthreads();
             if (S.status == ST_OK && !S.skip2) {
                 v = none;
                 scan_ratio_dual(v, X.tid, ENG_NT, 2, sgn, S.eps, S.tmax, A.rtol, X.stat, A.cbar, A.trow, nullptr, n);
                 r = eng_blockall(X, v, none, CombRatio2());
-                if (X.tid == 0) fin_ratio_dual(&S, r, 2, sgn, A.rtol, nullptr);
+                if (X.tid == 0) fin_ratio_dual(&S, r, 2, sgn, A.rtol, nullptr, A.tie_stop != 0);
                 __syncthreads();
             }
             if (S.status != ST_OK) break;
@@ -1550,7 +1637,7 @@ __global__ void __launch_bounds__(ENG_NT, 1) k_engine_dual(EngArgs A)
             scan_ratio_dual(v, X.gtid, X.gsize, 1, sgn, S.eps, 0.0, A.rtol, X.stat, A.cbar, A.trow, nullptr, n);
             if (pse) eng_gamma_rhs(X, A);
             Key r = eng_allreduce(X, A, v, none, CombRatio1());
-            if (X.tid == 0) fin_ratio_dual(&S, r, 1, sgn, A.rtol, nullptr);
+            if (X.tid == 0) fin_ratio_dual(&S, r, 1, sgn, A.rtol, nullptr, A.tie_stop != 0);
             __syncthreads();
             eng_mark(X, A, PD_R1, 17.0 * n + (pse ? 17.0 * nnzA + 16.0 * m : 0.0));
             if (S.status != ST_OK) break;
@@ -1571,7 +1658,7 @@ __global__ void __launch_bounds__(ENG_NT, 1) k_engine_dual(EngArgs A)
                 v = none;
                 scan_ratio_dual(v, X.gtid, X.gsize, 2, sgn, S.eps, S.tmax, A.rtol, X.stat, A.cbar, A.trow, nullptr, n);
                 r = eng_allreduce(X, A, v, none, CombRatio2());
-                if (X.tid == 0) fin_ratio_dual(&S, r, 2, sgn, A.rtol, nullptr);
+                if (X.tid == 0) fin_ratio_dual(&S, r, 2, sgn, A.rtol, nullptr, A.tie_stop != 0);
                 __syncthreads();
                 eng_mark(X, A, PD_R2, 17.0 * n + (need_z ? 16.0 * nd * S.k : 0.0));
                 if (S.status != ST_OK) break;
@@ -1604,8 +1691,8 @@ __global__ void __launch_bounds__(ENG_NT, 1) k_engine_dual(EngArgs A)
         /* ---- tcol, second half, and the tail of u = inv(B) v ---- */
         {
             Key dummy = {0.0, 0.0, 0.0, 0, 0};
-            if (pse) eng_ftran_tail<false>(X, A, S, A.v, A.ycol2, A.u, dummy);
-            eng_ftran_tail<false>(X, A, S, A.hz, A.ycol, A.tcol, dummy);
+            if (pse) eng_ftran_tail2(X, A, A.hz, A.ycol, A.tcol, A.v, A.ycol2, A.u);
+            else eng_ftran_tail<false>(X, A, S, A.hz, A.ycol, A.tcol, dummy);
             eng_bar(X, A);
             if (X.tid == 0) {
                 /* k_dual_prep: lib/glpspx02.js:1913-1938, :1103-1115 */
@@ -1636,11 +1723,35 @@ __global__ void __launch_bounds__(ENG_NT, 1) k_engine_dual(EngArgs A)
             const double pivot = C.tp;
             const double xq = get_xN(X.stat, X.head, A.lb, A.ub, m, q);
             const bool drop = (A.type[kp] == GLP_FX && A.refsp[kp]);
-            for (int t = X.gtid; t < n; t += X.gsize) {
-                if (t == q) A.cbar[q] = new_dq;
-                else if (new_dq != 0.0) {
-                    const double tr = A.trow[t];
-                    if (tr != 0.0) A.cbar[t] -= tr * new_dq;
+            /* phase 1: is the basis dual feasible after this iteration (check_feas at the top of the reference's
+               next iteration, lib/glpspx02.js:1681-1696)?  The count rides on the pricing key. */
+            int ninf = 0;
+            if (S.phase != 1) {
+                for (int t = X.gtid; t < n; t += X.gsize) {
+                    if (t == q) A.cbar[q] = new_dq;
+                    else if (new_dq != 0.0) {
+                        const double tr = A.trow[t];
+                        if (tr != 0.0) A.cbar[t] -= tr * new_dq;
+                    }
+                }
+            } else {
+                for (int t = X.gtid; t < n; t += X.gsize) {
+                    double d;
+                    int kk;
+                    if (t == q) { d = new_dq; A.cbar[q] = d; kk = kp; }        /* xB[p] takes the place of xN[q] */
+                    else {
+                        d = A.cbar[t];
+                        if (new_dq != 0.0) {
+                            const double tr = A.trow[t];
+                            if (tr != 0.0) { d -= tr * new_dq; A.cbar[t] = d; }
+                        }
+                        kk = X.head[m + t];
+                    }
+                    const int ty = A.orig_type[kk];
+                    bool bad = false;
+                    if (d < -A.tol_dj) bad = (ty == GLP_LO || ty == GLP_FR);
+                    if (d > +A.tol_dj) bad = bad || (ty == GLP_UP || ty == GLP_FR);
+                    ninf += bad ? 1 : 0;
                 }
             }
             Key pnone = {0.0, 0.0, 0.0, INT_MAX, 0};
@@ -1695,18 +1806,21 @@ __global__ void __launch_bounds__(ENG_NT, 1) k_engine_dual(EngArgs A)
             }
             if (defer) { eng_defer_apply(X, A, C, nd); nd++; }
             else if (S.k + (C.bnew >= 0) > 0) eng_update_T(X, A, C);
-            Key r = eng_allreduce(X, A, pv, pnone, CombArgMax());
+            pv.aux = ninf;
+            Key r = eng_allreduce(X, A, pv, pnone, CombArgMaxCnt());
             {
                 const bool found = (r.a > 0.0 && r.pos != INT_MAX);
                 pnext = found ? r.pos : P_NONE;
                 dnext = found ? r.b : 0.0;
             }
+            const bool feasible_now = (S.phase == 1 && r.aux == 0);
             eng_mark(X, A, PD_UPD, 24.0 * n + 40.0 * m + 37.0 * m + (defer ? 40.0 * S.k : 16.0 * S.k * (double)S.k));
             const int new_stat = (A.type[kp] == GLP_FX) ? GLP_NS : (S.delta > 0.0 ? GLP_NL : GLP_NU);
             if (X.tid == 0) eng_bookkeep(X, A, C, new_stat, pse && drop);
             if (X.tid == 0) {
                 S.k = C.knew;
                 iter_end(&S, true, 1);
+                if (feasible_now && S.status == ST_OK) S.status = ST_PHASE;
             }
             eng_header_done(X, A);
         }

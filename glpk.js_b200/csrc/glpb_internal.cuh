@@ -62,6 +62,11 @@ enum {
     ST_LIMIT = 8,      /* iteration limit reached                              */
     ST_REFSP = 9,      /* reference space must be reset (refct == 0)           */
     ST_OBJLIM = 10,    /* dual: objective crossed obj_ll / obj_ul              */
+    ST_PHASE = 12,     /* phase 1: the iteration just completed left nothing infeasible; the host
+                          repeats the reference's check_feas and switches to phase 2             */
+    /* raised inside an iteration by the engines only */
+    ST_TIE = 11,       /* exact tie in a ratio test: the host repeats the iteration with the
+                          reference's sort_tcol / sort_trow list order (k_sort_list)          */
 };
 
 #define P_NONE (-1)
@@ -81,7 +86,7 @@ struct Ctrl {
        back to back; the host seeds it at the start of a batch */
     int it_cnt, it_max, refct, upd_cnt, period, n_done;
     int rigorous, bbar_fresh, cbar_fresh, binv_fresh, pse;
-    int pad0;
+    int list_num;       /* entries of the ratio-test list k_sort_list left          */
     double obj_ll, obj_ul, zeta;
     double teta, delta, new_dq, tmax;
     double tcol_max, trow_max, eps;
@@ -148,6 +153,8 @@ struct glpb_prob {
     double *yk2 = nullptr, *zn = nullptr;  /* [ldt] engine work in kernel space */
     struct EngSlot *eng_slots = nullptr;   /* engine: barrier flags + partials [ENG_RING][ENG_MAXG] */
     double *eng_cols = nullptr;            /* engine: ycol, ycol2, trowcol [3n] and vrow [m] */
+    int *sort_list = nullptr, *sort_tmp = nullptr;   /* ratio-test list in the reference's order [max(m,n)], scratch [2 max(m,n) + 2] */
+    long n_tie = 0;                        /* iterations the engines handed over because of an exact tie */
     double *eng_fr = nullptr;              /* engine: deferred terms Fd, Rd [2][ENG_DB][ldt] and zbuf [ENG_DB] */
     long long *eng_cyc = nullptr;          /* engine: SM cycles per phase [16] */
     double *eng_bytes = nullptr;           /* engine: algorithmic bytes per phase [16] */

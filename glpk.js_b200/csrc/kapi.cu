@@ -161,6 +161,31 @@ extern "C" int glpb_k_ratio_dual(int n, const signed char *stat, const double *c
     return 0;
 }
 
+/* sort_tcol / sort_trow: the significant entries of vec[1..n] (|v| >= eps) in the order the reference's
+   swap loop leaves them (lib/glpspx01.js:795-804, lib/glpspx02.js:780-789); list[1..*num], 1-based */
+extern "C" int glpb_k_sort_list(int n, const double *vec, double eps, int *list, int *num)
+{
+    int rc = need_device();
+    if (rc) return rc;
+    if (n < 1 || !vec || !list || !num) return GLPB_EINVAL;
+    Tmp t;
+    double *d_vec = t.up(vec + 1, n);
+    int *d_list = t.zero<int>(n), *d_tmp = t.zero<int>(2 * (size_t)n + 2);
+    Ctrl hc;
+    memset(&hc, 0, sizeof hc);
+    hc.eps = eps;
+    Ctrl *ctrl = t.up(&hc, 1);
+    if (!t.ok) return GLPB_ENOMEM;
+    k_sort_list<<<1, 1024>>>(ctrl, d_vec, n, d_list, d_tmp);
+    Ctrl h;
+    if ((rc = finish(t, ctrl, &h))) return rc;
+    *num = h.list_num;
+    std::vector<int> out(n);
+    if (cudaMemcpy(out.data(), d_list, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return GLPB_ENODEV;
+    for (int i = 0; i < h.list_num; i++) list[i + 1] = out[i] + 1;
+    return 0;
+}
+
 extern "C" int glpb_k_trow(int m, int n, const int *A_ptr, const int *A_ind, const double *A_val,
                            const int *head, const signed char *stat, const double *rho,
                            double *trow_vec)

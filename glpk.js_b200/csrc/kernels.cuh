@@ -33,28 +33,45 @@ __device__ __forceinline__ Key key_shfl_down(const Key &v, int off)
     return o;
 }
 
+/* reduction over the lanes of a warp, result in lane 0.  `none` is the identity of comb
+   (comb(none, x) = x), which most lanes hold in the selection passes -- a ratio test has a
+   handful of candidates among thousands of entries: a warp without a live value skips the
+   shuffle tree (40 SHFL per Key), a warp with ONE live value fetches it with a single round. */
+template <class Comb>
+__device__ __forceinline__ Key warp_reduce(Key v, const Key &none, Comb comb)
+{
+    const bool live = !(v.pos == none.pos && v.aux == none.aux && v.a == none.a && v.b == none.b && v.c == none.c);
+    const unsigned int mask = __ballot_sync(FULLMASK, live);
+    if (mask == 0u) return v;
+    if ((mask & (mask - 1u)) == 0u) {
+        const int src = __ffs(mask) - 1;
+        Key o;
+        o.a = __shfl_sync(FULLMASK, v.a, src); o.b = __shfl_sync(FULLMASK, v.b, src); o.c = __shfl_sync(FULLMASK, v.c, src);
+        o.pos = __shfl_sync(FULLMASK, v.pos, src); o.aux = __shfl_sync(FULLMASK, v.aux, src);
+        return o;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        Key o = key_shfl_down(v, off);
+        comb(v, o);
+    }
+    return v;
+}
+
 /* result valid in thread 0 of the block; all threads must call */
 template <class Comb>
 __device__ Key block_reduce(Key v, const Key &none, Comb comb)
 {
     __shared__ Key sm[32];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-        Key o = key_shfl_down(v, off);
-        comb(v, o);
-    }
+    v = warp_reduce(v, none, comb);
     __syncthreads(); /* protect sm against a previous use */
     if (lane == 0) sm[w] = v;
     __syncthreads();
     const int nw = (blockDim.x + 31) >> 5;
     if (w == 0) {
         v = (lane < nw) ? sm[lane] : none;
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            Key o = key_shfl_down(v, off);
-            comb(v, o);
-        }
+        v = warp_reduce(v, none, comb);
     }
     return v;
 }
@@ -98,16 +115,41 @@ struct CombArgMax { /* larger a wins, then smaller pos */
         if (o.a > v.a || (o.a == v.a && o.pos < v.pos)) v = o;
     }
 };
+/* Ratio tests: candidates that agree in every compared field are ordered by `pos`.
+   With a materialised list (k_sort_list) pos is the place in the reference's own
+   sort_tcol / sort_trow order and the winner is the reference's; in dense scans pos
+   is the index, and the winner of an exact tie carries RATIO_TIE in aux so that the
+   caller can have the iteration decided in list order instead.  The bound-flip
+   candidate (pos -1) is examined first by the reference as well: no tie. */
+#define RATIO_TIE 512
 struct CombRatio1 { /* smaller a (ratio), then larger b (|alfa|), then smaller pos */
     __device__ void operator()(Key &v, const Key &o) const
     {
-        if (o.a < v.a || (o.a == v.a && (o.b > v.b || (o.b == v.b && o.pos < v.pos)))) v = o;
+        if (o.a < v.a || (o.a == v.a && o.b > v.b)) v = o;
+        else if (o.a == v.a && o.b == v.b && o.pos != v.pos && o.pos != INT_MAX && v.pos != INT_MAX) {
+            const int tie = ((o.pos >= 0 && v.pos >= 0) ? RATIO_TIE : 0) | ((o.aux | v.aux) & RATIO_TIE);
+            if (o.pos < v.pos) v = o;
+            v.aux |= tie;
+        }
     }
 };
 struct CombRatio2 { /* larger b (|alfa|), then smaller pos */
     __device__ void operator()(Key &v, const Key &o) const
     {
-        if (o.b > v.b || (o.b == v.b && o.pos < v.pos)) v = o;
+        if (o.b > v.b) v = o;
+        else if (o.b == v.b && o.pos != v.pos && o.pos != INT_MAX && v.pos != INT_MAX) {
+            const int tie = ((o.pos >= 0 && v.pos >= 0) ? RATIO_TIE : 0) | ((o.aux | v.aux) & RATIO_TIE);
+            if (o.pos < v.pos) v = o;
+            v.aux |= tie;
+        }
+    }
+};
+struct CombArgMaxCnt { /* CombArgMax on (a, pos); aux is a count that is summed */
+    __device__ void operator()(Key &v, const Key &o) const
+    {
+        const int cnt = v.aux + o.aux;
+        if (o.a > v.a || (o.a == v.a && o.pos < v.pos)) v = o;
+        v.aux = cnt;
     }
 };
 struct CombSum2 { /* a and b are sums, c is a maximum, aux a count, pos unused */
@@ -400,7 +442,7 @@ __device__ __forceinline__ void scan_ratio_primal(Key &v, int start, int stride,
 /* what the reference does with the winner of a pass (chuzr, :1009-1028, and
    the pivot-size test of the main loop, :1960-1975) */
 __device__ __forceinline__ void fin_ratio_primal(Ctrl *ctrl, const Key &r, int pass, double s, double rtol,
-                                                 const int *ind)
+                                                 const int *ind, bool tie_stop = false)
 {
     int p, p_stat = r.aux & 255;
     double teta = r.a;
@@ -412,6 +454,8 @@ __device__ __forceinline__ void fin_ratio_primal(Ctrl *ctrl, const Key &r, int p
         ctrl->tmax = teta;
         if (!ctrl->skip2) { ctrl->p = p; return; }
     }
+    /* the decisive pass ended in an exact tie that only the reference's list order settles */
+    if (tie_stop && ind == nullptr && (r.aux & RATIO_TIE)) { ctrl->p = p; ctrl->status = ST_TIE; return; }
     if (p >= 0 && (r.aux & 256)) p_stat = GLP_NS;        /* a fixed variable leaves: lib/glpspx01.js:1019 */
     ctrl->p = p;
     ctrl->p_stat = p_stat;
@@ -435,6 +479,7 @@ __device__ __forceinline__ void ratio_primal_body(Ctrl *ctrl, int pass, int m, c
     if (ctrl->status != ST_OK) return;
     if (pass == 2 && ctrl->skip2) return;
     const int q = ctrl->q, phase = ctrl->phase;
+    if (num < 0) num = ctrl->list_num;                /* the list k_sort_list left */
     const double s = (ctrl->d1 > 0.0 ? -1.0 : +1.0); /* d1 holds the (corrected) cbar[q] */
     const double eps = (ind == nullptr ? ctrl->eps : 0.0);
     const double tmax = ctrl->tmax;
@@ -508,7 +553,7 @@ __device__ __forceinline__ void scan_ratio_dual(Key &v, int start, int stride, i
 }
 
 __device__ __forceinline__ void fin_ratio_dual(Ctrl *ctrl, const Key &r, int pass, double s, double rtol,
-                                               const int *ind)
+                                               const int *ind, bool tie_stop = false)
 {
     int q = (r.pos == INT_MAX) ? P_NONE : (ind ? ind[r.pos] : r.pos);
     double teta = r.a;
@@ -517,6 +562,7 @@ __device__ __forceinline__ void fin_ratio_dual(Ctrl *ctrl, const Key &r, int pas
         ctrl->tmax = teta;
         if (!ctrl->skip2) { ctrl->q = q; return; }
     }
+    if (tie_stop && ind == nullptr && (r.aux & RATIO_TIE)) { ctrl->q = q; ctrl->status = ST_TIE; return; }
     ctrl->q = q;
     ctrl->new_dq = __dmul_rn(s, teta);
     if (q == P_NONE) { ctrl->status = ST_NONE2; return; }
@@ -534,6 +580,7 @@ __device__ __forceinline__ void ratio_dual_body(Ctrl *ctrl, int pass, const sign
     if (ctrl->status != ST_OK) return;
     if (pass == 2 && ctrl->skip2) return;
     const double s = (ctrl->delta > 0.0 ? +1.0 : -1.0);
+    if (num < 0) num = ctrl->list_num;                /* the list k_sort_list left */
     const double eps = (ind == nullptr ? ctrl->eps : 0.0);
     const double tmax = ctrl->tmax;
     Key none = {DBL_MAX, 0.0, 0.0, INT_MAX, 0};
@@ -553,6 +600,97 @@ __global__ void k_ratio_dual(Ctrl *ctrl, int pass, const signed char *__restrict
     ratio_dual_body(ctrl, 1, stat, cbar, trow, ind, num, rtol, scratch);
     __syncthreads();
     ratio_dual_body(ctrl, 2, stat, cbar, trow, ind, num, rtol, scratch);
+}
+
+/* sort_tcol / sort_trow (lib/glpspx01.js:773-806, lib/glpspx02.js:754-791) in closed form.
+   The reference lists the non-zeros of the vector in ascending index order (eval_tcol,
+   eval_trow1/2) and then moves the significant ones (|v| >= eps) to the front with a loop that
+   always examines the LAST entry of the shrinking list: a significant entry is swapped with the
+   entry at the growing front, an insignificant one is dropped.  Entries are therefore drawn
+   from the back after an insignificant one and from the front after a significant one, which
+   gives, with Ns significant entries and list indices j = 1, 2, ...:
+     - a significant entry with j <= Ns - 1 ends up at place j + 1;
+     - the other significant entries take the remaining places in DESCENDING index order,
+       the remaining places being 1 and every j + 1 whose entry j <= Ns - 1 is insignificant.
+   One CTA; two chunked scans of the vector.  list[0..num) = indices in the reference's order,
+   ctrl->list_num = num = Ns.  tmp: 2 N + 2 ints. */
+__global__ void k_sort_list(Ctrl *ctrl, const double *__restrict__ vec, int N, int *__restrict__ list, int *__restrict__ tmp)
+{
+    if (ctrl->status != ST_OK) return;
+    __shared__ int wsum[32];
+    __shared__ int s_tot;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nt = blockDim.x, nw = nt >> 5;
+    const double eps = ctrl->eps;
+    /* block-wide inclusive scan of a packed pair of counters (non-zero: low 16 bits, significant: high) */
+    auto scan = [&](int x, int &total) {
+        int v = x;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int o = __shfl_up_sync(FULLMASK, v, off);
+            if (lane >= off) v += o;
+        }
+        __syncthreads();
+        if (lane == 31) wsum[warp] = v;
+        __syncthreads();
+        if (warp == 0) {
+            int w = (lane < nw) ? wsum[lane] : 0, ws = w;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const int o = __shfl_up_sync(FULLMASK, ws, off);
+                if (lane >= off) ws += o;
+            }
+            wsum[lane] = ws - w;
+            if (lane == 31) s_tot = ws;
+        }
+        __syncthreads();
+        total = s_tot;
+        return v + wsum[warp];
+    };
+    /* pass 1: Ns */
+    int cnt = 0;
+    for (int i = tid; i < N; i += nt) {
+        const double v = vec[i];
+        cnt += (v != 0.0 && !(fabs(v) < eps)) ? 1 : 0;
+    }
+    int Ns;
+    {
+        /* counts per thread can exceed 16 bits: plain sum by the same scan in two halves */
+        int t0, t1;
+        scan(cnt & 0xffff, t0);
+        scan(cnt >> 16, t1);
+        Ns = t0 + (t1 << 16);
+    }
+    const int F = Ns - 1;
+    int *freerank = tmp, *backelem = tmp + N + 1;          /* 1-based, [r] */
+    /* pass 2 */
+    int carry_nz = 0, carry_sg = 0, my_back = 0;
+    for (int base = 0; base < N; base += nt) {
+        const int i = base + tid;
+        const double v = (i < N) ? vec[i] : 0.0;
+        const int nz = (v != 0.0) ? 1 : 0, sg = (nz && !(fabs(v) < eps)) ? 1 : 0;
+        int tot;
+        const int inc = scan(nz | (sg << 16), tot);
+        const int j = carry_nz + (inc & 0xffff), sgi = carry_sg + (inc >> 16);
+        if (nz) {
+            if (sg) {
+                if (j <= F) list[j] = i;                   /* place j + 1 */
+                else { backelem[Ns - (sgi - 1)] = i; my_back++; }   /* r = significant entries with list index >= j */
+            } else if (j <= F)
+                freerank[(j - sgi) + 1] = j + 1;           /* the (t+1)-th free place, t = its ordinal among the insignificant */
+        }
+        carry_nz += tot & 0xffff; carry_sg += tot >> 16;
+    }
+    /* the entries drawn from the back take the free places in turn: r = 1 -> place 1 */
+    int nback, nback_hi;
+    scan(my_back & 0xffff, nback);
+    scan(my_back >> 16, nback_hi);
+    nback += nback_hi << 16;
+    __syncthreads();
+    for (int r = 1 + tid; r <= nback; r += nt) {
+        const int place = (r == 1) ? 1 : freerank[r];
+        list[place - 1] = backelem[r];
+    }
+    if (tid == 0) ctrl->list_num = Ns;
 }
 
 /* ------------------------------------------------------------------ */
@@ -1650,6 +1788,36 @@ __global__ void k_tab_rows(const Ctrl *ctrl, int m, int n, const int *__restrict
 }
 
 /* seeds the device-resident loop state before a batch of iterations */
+/* The reference looks at the basic solution at the top of EVERY iteration of phase 1 and switches to phase 2 as
+   soon as nothing violates its bound any more (primal check_feas, lib/glpspx01.js:1768-1775; dual check_feas,
+   lib/glpspx02.js:1681-1696).  Inside a batch of enqueued iterations this kernel makes that test after each
+   iteration and ends the batch (ST_PHASE); the host loop then repeats the test where the reference makes it and
+   changes the phase.  One CTA. */
+__global__ void k_phase1_stop(Ctrl *ctrl, int dual, int m, int n, const int *__restrict__ head,
+                              const signed char *__restrict__ orig_type, const double *__restrict__ lb,
+                              const double *__restrict__ ub, const double *__restrict__ coef,
+                              const double *__restrict__ bbar, const double *__restrict__ cbar, double tol)
+{
+    if (ctrl->status != ST_OK || ctrl->phase != 1) return;
+    int bad = 0;
+    if (!dual) {
+        for (int i = threadIdx.x; i < m && !bad; i += blockDim.x) {
+            const int k = head[i];
+            const double b = bbar[i], c = coef[k];
+            if (c < 0.0) bad = b < lb[k] - relax(tol, lb[k]);
+            else if (c > 0.0) bad = b > ub[k] + relax(tol, ub[k]);
+        }
+    } else {
+        for (int j = threadIdx.x; j < n && !bad; j += blockDim.x) {
+            const double d = cbar[j];
+            const int t = orig_type[head[m + j]];
+            if (d < -tol) bad = (t == GLP_LO || t == GLP_FR);
+            if (d > +tol) bad = bad || (t == GLP_UP || t == GLP_FR);
+        }
+    }
+    if (!__syncthreads_or(bad) && threadIdx.x == 0) ctrl->status = ST_PHASE;
+}
+
 __global__ void k_batch_begin(Ctrl *ctrl, int phase, int it_cnt, int it_max, int refct, int upd_cnt,
                               int period, int rigorous, int bbar_fresh, int cbar_fresh, int binv_fresh,
                               int pse, double obj_ll, double obj_ul, double zeta)

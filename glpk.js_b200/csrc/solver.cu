@@ -156,7 +156,7 @@ extern "C" void glpb_destroy(glpb_prob *P)
                     P->svec, P->w1, P->w2, P->w3, P->w4, P->w5, P->yk, P->wk, P->yk2, P->zn, P->eng_slots, P->eng_cols, P->eng_fr,
                     P->eng_cyc, P->eng_bytes, P->T, P->T2, P->ref_slots, P->ref_flags, P->ref_xp, P->partial,
                     P->rslot, P->slot_pos, P->cslot, P->slot_row, P->gj_piv, P->gj_row,
-                    P->scratch, P->ctrl};
+                    P->scratch, P->ctrl, P->sort_list, P->sort_tmp};
     for (void *p : ptrs) if (p) cudaFree(p);
     P->prof = 0; prof_collect(P);
     for (auto &kind : P->graphs)
@@ -197,6 +197,7 @@ static int create_device(glpb_prob *P)
     DA(gj_piv, P->ldt); DA(gj_row, P->ldt);
     DA(scratch, 4096);
     DA(ctrl, 1);
+    DA(sort_list, std::max(m, n)); DA(sort_tmp, 2 * (size_t)std::max(m, n) + 2);
 #undef DA
     CK(cudaMallocHost((void **)&P->h_ctrl, sizeof(Ctrl)));
     /* pinned staging: bounds/costs [6 x (m+n) doubles + n+1], types [2(m+n)], header [2(m+n) ints + n],
@@ -798,8 +799,19 @@ struct Loop : Dev {
     int batch_size() const
     {
         static const int env = getenv("GLPB_BATCH") ? std::max(1, atoi(getenv("GLPB_BATCH"))) : 16;
-        return (rigorous > 0 || P->trace) ? 1 : env;
+        return (rigorous > 0 || P->trace || tie_resume) ? 1 : env;
     }
+
+    /* Exact ties of a ratio test are settled in the order of the reference's sort_tcol / sort_trow
+       list (k_sort_list).  The per-kernel path always scans that list; the engines scan the dense
+       vector, flag an exact tie (ST_TIE) and hand that one iteration over.  GLPB_TIES=0: ties go to
+       the lowest index everywhere (no list, no hand-over). */
+    static bool list_order()
+    {
+        static const bool off = getenv("GLPB_TIES") && atoi(getenv("GLPB_TIES")) == 0;
+        return !off;
+    }
+    bool tie_resume = false;      /* the next iteration repeats the one the engine stopped in */
 
     /* seed the device-resident loop state; the dense rhs of eval_tcol is
        cleared here because an aborted iteration may have left a column in it */
@@ -816,7 +828,7 @@ struct Loop : Dev {
     bool engine_ok() const
     {
         static const bool off = getenv("GLPB_ENGINE") && atoi(getenv("GLPB_ENGINE")) == 0;
-        return !off && P->eng_ready && rigorous == 0 && !P->trace;
+        return !off && P->eng_ready && rigorous == 0 && !P->trace && !tie_resume;
     }
 
     /* grid of the persistent engine: every SM once the problem is big enough to
@@ -843,7 +855,7 @@ struct Loop : Dev {
         A.tol_bnd = parm.tol_bnd; A.tol_dj = parm.tol_dj; A.tol_piv = parm.tol_piv; A.rtol = rtol;
         A.a_ptr = P->a_ptr; A.a_ind = P->a_ind; A.a_val = P->a_val;
         A.at_ptr = P->at_ptr; A.at_ind = P->at_ind; A.at_val = P->at_val;
-        A.type = P->type; A.stat = P->stat; A.refsp = P->refsp;
+        A.type = P->type; A.stat = P->stat; A.refsp = P->refsp; A.orig_type = P->orig_type;
         A.lb = P->lb; A.ub = P->ub; A.coef = P->coef;
         A.head = P->head; A.bind = P->bind;
         A.bbar = P->bbar; A.cbar = P->cbar; A.gamma = P->gamma; A.tcol = P->tcol; A.trow = P->trow;
@@ -864,6 +876,9 @@ struct Loop : Dev {
         A.use_tma = P->eng_tma;
         A.hdr_smem = P->eng_hdr;
         A.local_max = env_local;
+        A.tie_stop = list_order() ? 1 : 0;
+        static const int env_pf = getenv("GLPB_PF") ? std::max(0, atoi(getenv("GLPB_PF"))) : 2;
+        A.pf_dist = env_pf;
         A.prof_cyc = P->prof ? P->eng_cyc + (dual ? 12 : 0) : nullptr;
         A.prof_bytes = P->prof ? P->eng_bytes + (dual ? 12 : 0) : nullptr;
         const int G = engine_grid();
@@ -990,7 +1005,10 @@ struct Loop : Dev {
     int refac_period() const
     {
         static const bool fixed = getenv("GLPB_REFAC_AUTO") && atoi(getenv("GLPB_REFAC_AUTO")) == 0;
-        static const int div = getenv("GLPB_REFAC_DIV") ? std::max(1, atoi(getenv("GLPB_REFAC_DIV"))) : 2;
+        /* k updates between refactorisations (measured on C3: 27 instead of 53 refactorisations, -1.5 s of
+           22.3 s, same 120552 iterations, objective to 5e-14 of the HiGHS pin, KKT 5e-16; the accuracy triggers
+           of the reference -- piv1/piv2 at 1e-8, d1/d2, check_stab -- still force one when needed) */
+        static const int div = getenv("GLPB_REFAC_DIV") ? std::max(1, atoi(getenv("GLPB_REFAC_DIV"))) : 1;
         return fixed ? P->bfcp.nfs_max : std::max(P->bfcp.nfs_max, k / div);
     }
     bool it_limit() const { return parm.it_lim < INT_MAX && it_cnt - it_beg >= parm.it_lim; }
@@ -1121,19 +1139,25 @@ struct Primal : Loop {
             const int B = eng ? 0 : batch_size();
             if (!eng) batch_begin(B, -DBL_MAX, +DBL_MAX);
             for (int b = 0; b < B; b++) {
-                chuzc(1);
+                /* an iteration taken over from the engine keeps the engine's q: the engine has already
+                   replaced cbar[q] by the recomputed value (reeval_cost), pricing again could differ */
+                if (!tie_resume) chuzc(1);
                 eval_tcol();
                 LAUNCH(P, k_primal_prep, red_blocks(m), red_threads(m), 0, P->ctrl, m, P->head, P->coef, P->tcol,
                        P->refsp, P->cbar, P->w3, parm.tol_piv, P->scratch);
+                /* sort_tcol: the significant entries in the reference's list order, so that exact ties
+                   of the ratio test fall the way they do there (num = -1: count left on the device) */
+                const int *lst = list_order() ? P->sort_list : nullptr;
+                if (lst) LAUNCH(P, k_sort_list, 1, 1024, 0, P->ctrl, P->tcol, m, P->sort_list, P->sort_tmp);
                 if (red_blocks(m) == 1) {
                     P->next_bytes = 90.0 * m;
                     LAUNCH(P, k_ratio_primal, 1, 1024, 0, P->ctrl, 0, m, P->type, P->lb, P->ub, P->coef, P->head,
-                           P->bbar, P->tcol, (const int *)nullptr, m, rtol, P->scratch);
+                           P->bbar, P->tcol, lst, lst ? -1 : m, rtol, P->scratch);
                 } else
                     for (int pass = 1; pass <= 2; pass++) {
                         P->next_bytes = 45.0 * m;
                         LAUNCH(P, k_ratio_primal, grid1(m), 256, 0, P->ctrl, pass, m, P->type, P->lb, P->ub, P->coef,
-                               P->head, P->bbar, P->tcol, (const int *)nullptr, m, rtol, P->scratch);
+                               P->head, P->bbar, P->tcol, lst, lst ? -1 : m, rtol, P->scratch);
                     }
                 eval_rho();
                 if (pse) dev_btran(*this, P->w3, P->w2, 1);
@@ -1146,16 +1170,24 @@ struct Primal : Loop {
                        P->type, P->lb, P->ub, P->coef, P->bbar, P->cbar, P->gamma, P->refsp, P->tcol, P->trow,
                        P->svec, P->w5);
                 update_basis(0);
+                if (phase == 1)
+                    LAUNCH(P, k_phase1_stop, 1, 1024, 0, P->ctrl, 0, m, n, P->head, P->orig_type, P->lb, P->ub, P->coef,
+                           P->bbar, P->cbar, parm.tol_bnd);
             }
             if (!eng && (rc = sync_ctrl(P))) return rc;
             trace_iter("primal");
             const Ctrl &c = *P->h_ctrl;
             batch_end();
+            tie_resume = false;
             switch (c.status) {
-            case ST_OK: case ST_LIMIT: case ST_REFSP:
+            case ST_OK: case ST_LIMIT: case ST_REFSP: case ST_PHASE:
                 break;
             case ST_REFAC:
                 binv_st = 0;
+                break;
+            case ST_TIE:
+                tie_resume = true;      /* this iteration again, through the list-ordered ratio test */
+                P->n_tie++;
                 break;
             case ST_NONE1:
                 if (bbar_st != 1 || cbar_st != 1) {
@@ -1386,15 +1418,18 @@ struct Dual : Loop {
                                           P->a_ind, P->a_val, P->head, P->stat, P->rho, (const double *)nullptr,
                                           P->trow, P->svec, 1));
                 LAUNCH(P, k_dual_rowmax, 1, 1, 0, P->ctrl, parm.tol_bnd); /* sic: tol_bnd, lib/glpspx02.js:1851 */
+                /* sort_trow: see the primal loop */
+                const int *lst = list_order() ? P->sort_list : nullptr;
+                if (lst) LAUNCH(P, k_sort_list, 1, 1024, 0, P->ctrl, P->trow, n, P->sort_list, P->sort_tmp);
                 if (red_blocks(n) == 1) {
                     P->next_bytes = 34.0 * n;
-                    LAUNCH(P, k_ratio_dual, 1, 1024, 0, P->ctrl, 0, P->stat, P->cbar, P->trow, (const int *)nullptr,
-                           n, rtol, P->scratch);
+                    LAUNCH(P, k_ratio_dual, 1, 1024, 0, P->ctrl, 0, P->stat, P->cbar, P->trow, lst,
+                           lst ? -1 : n, rtol, P->scratch);
                 } else
                     for (int pass = 1; pass <= 2; pass++) {
                         P->next_bytes = 17.0 * n;
                         LAUNCH(P, k_ratio_dual, grid1(n), 256, 0, P->ctrl, pass, P->stat, P->cbar, P->trow,
-                               (const int *)nullptr, n, rtol, P->scratch);
+                               lst, lst ? -1 : n, rtol, P->scratch);
                     }
                 eval_tcol();
                 LAUNCH(P, k_dual_prep, red_blocks(n), red_threads(n), 0, P->ctrl, m, n, P->head, P->refsp, P->trow,
@@ -1407,17 +1442,25 @@ struct Dual : Loop {
                 LAUNCH(P, k_dual_update, cdiv(std::max(m, n), 256), 256, 0, P->ctrl, m, n, P->head, P->stat, P->type,
                        P->lb, P->ub, P->bbar, P->cbar, P->gamma, P->refsp, P->tcol, P->trow, P->w2, P->w5);
                 update_basis(1);
+                if (phase == 1)
+                    LAUNCH(P, k_phase1_stop, 1, 1024, 0, P->ctrl, 1, m, n, P->head, P->orig_type, P->lb, P->ub, P->coef,
+                           P->bbar, P->cbar, parm.tol_dj);
             }
             if (!eng && (rc = sync_ctrl(P))) return rc;
             trace_iter("dual");
             const Ctrl &c = *P->h_ctrl;
             batch_end();
+            tie_resume = false;
             obj_track = c.obj;
             switch (c.status) {
-            case ST_OK: case ST_LIMIT: case ST_REFSP: case ST_OBJLIM:
+            case ST_OK: case ST_LIMIT: case ST_REFSP: case ST_OBJLIM: case ST_PHASE:
                 break;
             case ST_REFAC:
                 binv_st = 0;
+                break;
+            case ST_TIE:
+                tie_resume = true;      /* this iteration again, through the list-ordered ratio test */
+                P->n_tie++;
                 break;
             case ST_NONE1:
                 if (phase == 2 && bbar_st != 1 && cbar_st != 1 && final_round) {
@@ -1726,9 +1769,9 @@ extern "C" int glpb_get_solution(glpb_prob *P, int *stat, double *prim, double *
 extern "C" int glpb_get_counters(glpb_prob *P, long *out, int count)
 {
     if (!P || !out) return GLPB_EINVAL;
-    long v[8] = {P->n_iter, P->n_refac, P->n_launch, P->n_sync, P->n_update,
-                 (long)(P->h_ctrl ? P->h_ctrl->k : 0), (long)P->last_solve_us, P->n_graph};
-    for (int i = 0; i < count && i < 8; i++) out[i] = v[i];
+    long v[9] = {P->n_iter, P->n_refac, P->n_launch, P->n_sync, P->n_update,
+                 (long)(P->h_ctrl ? P->h_ctrl->k : 0), (long)P->last_solve_us, P->n_graph, P->n_tie};
+    for (int i = 0; i < count && i < 9; i++) out[i] = v[i];
     return 0;
 }
 

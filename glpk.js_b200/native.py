@@ -71,7 +71,7 @@ SYMBOLS = [
     "glpb_mip_begin", "glpb_mip_run", "glpb_mip_get_incumbent", "glpb_mip_set_cutoff", "glpb_mip_open_count",
     "glpb_mip_record_bytes", "glpb_mip_export_nodes", "glpb_mip_import_nodes", "glpb_mip_end",
     "glpb_btran", "glpb_k_chuzc_primal", "glpb_k_chuzr_dual", "glpb_k_ratio_primal",
-    "glpb_k_ratio_dual", "glpb_k_trow", "glpb_bench_kernel", "glpb_gen_packing",
+    "glpb_k_ratio_dual", "glpb_k_trow", "glpb_k_sort_list", "glpb_bench_kernel", "glpb_gen_packing",
     "glpb_gen_covering", "glpb_gen_mkp", "glpb_free_problem", "glpb_rng_fill",
     "glpb_scale_prob", "glpb_adv_basis", "glpb_read_lp", "glpb_free_names",
     "glpb_set_pivot_log", "glpb_get_pivot_log", "glpb_debug_get", "glpb_bnb_begin", "glpb_bnb_round", "glpb_bnb_open_count", "glpb_bnb_get_incumbent", "glpb_bnb_set_cutoff", "glpb_bnb_clear",
@@ -138,6 +138,7 @@ def load():
     L.glpb_k_ratio_primal.argtypes = [ci, ci] + [vp] * 5 + [ci, vp, cd, ci, vp, vp, ci, cd, vp, vp, vp]
     L.glpb_k_ratio_dual.argtypes = [ci, vp, vp, cd, vp, vp, ci, cd, vp, vp]
     L.glpb_k_trow.argtypes = [ci, ci] + [vp] * 7
+    L.glpb_k_sort_list.argtypes = [ci, vp, cd, vp, vp]
     L.glpb_bench_kernel.argtypes = [C.c_char_p, ci, ci, ci, vp, vp]
     L.glpb_gen_packing.argtypes = [ci, ci, cd, ci, vp]
     L.glpb_gen_covering.argtypes = [ci, ci, ci, ci, ci, vp]
@@ -495,9 +496,9 @@ class Problem:
         return [(int(qp[2 * i]), int(qp[2 * i + 1])) for i in range(cnt.value)]
 
     def counters(self):
-        out = (C.c_long * 8)()
-        self.L.glpb_get_counters(self.h, out, 8)
-        keys = ["iterations", "refactorizations", "launches", "syncs", "updates", "k", "solve_us", "graph_launches"]
+        out = (C.c_long * 9)()
+        self.L.glpb_get_counters(self.h, out, 9)
+        keys = ["iterations", "refactorizations", "launches", "syncs", "updates", "k", "solve_us", "graph_launches", "ties"]
         return {k: int(out[i]) for i, k in enumerate(keys)}
 
     def set_profile(self, on):
@@ -574,6 +575,16 @@ def k_trow(m, n, A_ptr, A_ind, A_val, head, stat, rho):
     out = np.zeros(1 + n)
     _check(load().glpb_k_trow(m, n, *[_p(x) for x in a], _p(out)), "k_trow")
     return out
+
+
+def k_sort_list(n, vec, eps):
+    """sort_tcol / sort_trow: indices (1-based) of the entries of vec[1..n] with |v| >= eps in the order the
+    reference's swap loop leaves them"""
+    vec = _f64(vec)
+    lst = np.zeros(1 + n, np.int32)
+    num = C.c_int()
+    _check(load().glpb_k_sort_list(n, _p(vec), eps, _p(lst), C.byref(num)), "k_sort_list")
+    return lst[1:1 + num.value].copy()
 
 
 def bench_kernel(name, m, n, reps=50):

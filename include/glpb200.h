@@ -215,6 +215,13 @@ int glpb_k_ratio_primal(int m, int n, const signed char *type, const double *lb,
 int glpb_k_ratio_dual(int n, const signed char *stat, const double *cbar,
                       double delta, const int *trow_ind, const double *trow_vec,
                       int trow_num, double rtol, int *q, double *new_dq);
+/* sort_tcol, lib/glpspx01.js:773-806 / sort_trow, lib/glpspx02.js:754-791: the
+ * entries of vec[1..n] with |v| >= eps, in the order the reference's swap loop
+ * leaves them (the order its ratio tests examine, which settles exact ties);
+ * out list[1..*num].  The solver's own per-kernel path runs the same kernel
+ * before every ratio test; the persistent engines stop at an exact tie and hand
+ * the iteration to that path (GLPB_TIES=0: lowest index instead). */
+int glpb_k_sort_list(int n, const double *vec, double eps, int *list, int *num);
 /* eval_trow1, lib/glpspx02.js:655-693 (pivot row as column dots).  A in CSA
  * layout; rho[1..m]; out trow_vec[1..n] */
 int glpb_k_trow(int m, int n, const int *A_ptr, const int *A_ind,

@@ -167,3 +167,29 @@ def random_mip(seed):
     d["r_lb"] = np.where(np.isin(rt, (O.GLP_LO, O.GLP_DB)), ax - slack, np.where(rt == O.GLP_FX, ax, 0.0))
     d["r_ub"] = np.where(rt == O.GLP_UP, ax + slack, np.where(rt == O.GLP_DB, ax + slack, np.where(rt == O.GLP_FX, ax, 0.0)))
     return d
+
+
+def transport_lp(seed, ns=6, nd=7):
+    """A small transportation LP with unit coefficients and small integer data: totally unimodular, so every
+    basis inverse, every ratio and every reduced cost is an integer computed exactly in floating point --
+    whatever the order of the arithmetic.  Its ratio tests tie all the time, and the ties are EXACT on every
+    implementation, which makes the pivot sequence a test of tie order alone (sort_tcol / sort_trow)."""
+    rng = np.random.default_rng(seed)
+    supply = rng.integers(3, 9, ns)
+    demand = rng.integers(1, 6, nd)
+    demand[-1] += max(0, int(supply.sum() - demand.sum()) // 2)
+    m, n = ns + nd, ns * nd
+    ptr, ind, val = [0], [], []
+    for s in range(ns):
+        for t in range(nd):
+            ind += [s, ns + t]
+            val += [1.0, 1.0]
+            ptr.append(len(ind))
+    rt = np.array([O.GLP_UP] * ns + [O.GLP_LO] * nd, np.int32)
+    rl = np.concatenate([np.zeros(ns), np.minimum(demand, supply.sum() // nd).astype(float)])
+    ru = np.concatenate([supply.astype(float), np.zeros(nd)])
+    ct = np.where(rng.random(n) < 0.3, O.GLP_DB, O.GLP_LO).astype(np.int32)
+    cu = np.where(ct == O.GLP_DB, rng.integers(1, 4, n), 0).astype(float)
+    return dict(m=m, n=n, dir=O.GLP_MIN, c0=0.0, r_type=rt, r_lb=rl, r_ub=ru, c_type=ct, c_lb=np.zeros(n), c_ub=cu,
+                c_coef=rng.integers(1, 5, n).astype(float), c_kind=np.full(n, O.GLP_CV, np.int32),
+                A_ptr=np.array(ptr, np.int32), A_ind=np.array(ind, np.int32), A_val=np.array(val, np.float64))

@@ -48,16 +48,23 @@ def weights_after(dn, meth, name, mname):
 
 with open(os.path.join(H.GOLDEN, "ref_runs.json")) as f:
     REF = json.load(f)["generated"]
+with open(os.path.join(H.GOLDEN, "ref_runs.json")) as f:
+    FIX = json.load(f)
 out = []
-for name, e in REF.items():
-    if name.startswith("random_lp_"):
+# the reference's own fixtures (LP relaxations of gap.lpt / todd.lpt are combinatorial: exact ties in nearly
+# every ratio test, settled only by the order sort_tcol / sort_trow leave) and the generated LPs
+CASES = [(n, FIX[n]) for n in ("test", "gap", "todd")] + list(REF.items())
+for name, e in CASES:
+    if name in ("test", "gap", "todd"):
+        dn = H.to_native(H.load_golden(name))
+    elif name.startswith("random_lp_"):
         dn = H.to_native(H.random_lp(int(name.rsplit("_", 1)[1])))
     elif name in ("packing", "covering"):
         g = dict(e["gen"])
         dn = nat.generate(g.pop("kind"), **g)
     else:
         continue
-    for mname, meth in (("primal", nat.GLP_PRIMAL), ("dual", nat.GLP_DUAL)):
+    for mname, meth in (("primal", nat.GLP_PRIMAL), ("dual", nat.GLP_DUAL), ("dualp", nat.GLP_DUALP)):
         ref = e.get("trace_" + mname)
         if ref is None:
             continue
@@ -66,6 +73,7 @@ for name, e in REF.items():
         rc = P.simplex(meth=meth)
         s = P.solution()
         got = P.pivot_log(4096)
+        P_ties = P.counters().get("ties", 0)
         P.close()
         want = [[r["q"], r["p"]] for r in ref["pivots"] if r.get("q", 0) != 0 and r.get("p", 0) != 0]
         got = [list(x) for x in got]
@@ -73,6 +81,50 @@ for name, e in REF.items():
         out.append(dict(name=name, meth=mname, rc_ok=bool(rc == ref["ret"] and s["status"] == ref["status"]),
                         obj_ok=bool(ref["status"] != 5 or abs(s["obj"] - ref["obj"]) <= 1e-9 * max(1.0, abs(ref["obj"]))),
                         iterations=int(s["it_cnt"]), ref_iterations=int(ref["it_cnt"]),
-                        same_sequence=bool(got == want), first_difference=int(k), weights=weights_after(dn, meth, name, mname),
+                        same_sequence=bool(got == want), first_difference=int(k), ties=int(P_ties),
+                        weights=weights_after(dn, meth, name, mname) if mname != "dualp" and name != "gap" else [],
+                        around=[got[max(0, k - 1):k + 2], want[max(0, k - 1):k + 2]] if got != want else None))
+
+
+def oracle_pivots(d, meth):
+    """(q, p) per iteration from the oracle (which reproduces the reference's sequences, test_ref_golden.py)"""
+    import oracle_lib as O
+    Q = O.Problem.from_arrays(d)
+    seq, cur = [], {}
+
+    def hook(ev, csa):
+        if ev == O.EV_P_CHUZC:
+            cur["q"] = O.csa_scalars(csa)["q"]
+        elif ev == O.EV_P_CHUZR:
+            seq.append([cur["q"], O.csa_scalars(csa)["p"]])
+        elif ev == O.EV_D_CHUZR:
+            cur["p"] = O.csa_scalars(csa)["p"]
+        elif ev == O.EV_D_CHUZC:
+            seq.append([O.csa_scalars(csa)["q"], cur["p"]])
+    Q.set_hook(hook)
+    rc = Q.simplex(meth=meth)
+    s = Q.solution()
+    return rc, s, [x for x in seq if x[0] != 0 and x[1] != 0]
+
+
+# exact ties: transportation LPs (unit coefficients, integer data: every quantity is an integer on every
+# implementation), the sequence against the oracle's
+for seed in range(1, 7):
+    d = H.transport_lp(seed)
+    dn = H.to_native(d)
+    for mname, meth in (("primal", nat.GLP_PRIMAL), ("dual", nat.GLP_DUAL)):
+        orc, osol, want = oracle_pivots(d, meth)
+        P = nat.Problem(dn)
+        P.set_pivot_log(4096)
+        rc = P.simplex(meth=meth)
+        s = P.solution()
+        got = [list(x) for x in P.pivot_log(4096)]
+        ties = P.counters().get("ties", 0)
+        P.close()
+        k = next((i for i, (a, b) in enumerate(zip(got, want)) if a != b), min(len(got), len(want)))
+        out.append(dict(name="transport_%d" % seed, meth=mname, rc_ok=bool(rc == orc and s["status"] == osol["status"]),
+                        obj_ok=bool(abs(s["obj"] - osol["obj"]) <= 1e-9 * max(1.0, abs(osol["obj"]))),
+                        iterations=int(s["it_cnt"]), ref_iterations=int(osol["it_cnt"]), same_sequence=bool(got == want),
+                        first_difference=int(k), ties=int(ties), weights=[],
                         around=[got[max(0, k - 1):k + 2], want[max(0, k - 1):k + 2]] if got != want else None))
 print(json.dumps(out))

@@ -204,3 +204,57 @@ def test_pivot_row_kernel_on_the_references_rho():
         assert np.max(np.abs(got[1:] - v["trow_vec"][1:])) <= 1e-12 * scale * 16, g
         n_checked += 1
     assert n_checked >= 20
+
+
+# ---- sort_tcol / sort_trow: the list order that settles exact ties ----
+def _literal_sort(vec, eps):
+    """the reference's loop, statement for statement (lib/glpspx01.js:764-806): non-zeros in ascending order,
+    then the swap loop that examines the last entry of the shrinking list"""
+    n = len(vec) - 1
+    ind = [0] + [i for i in range(1, n + 1) if vec[i] != 0.0]
+    nnz, num = len(ind) - 1, 0
+    while num < nnz:
+        i = ind[nnz]
+        if abs(vec[i]) < eps:
+            nnz -= 1
+        else:
+            num += 1
+            ind[nnz] = ind[num]
+            ind[num] = i
+    return ind[1:num + 1]
+
+
+def test_sort_list_equals_the_references_swap_order():
+    """k_sort_list (closed form, two scans) against (a) the lists the reference itself handed to its ratio tests
+    (tests/golden/ref_vectors.npz: tcol_ind / trow_ind after sort_tcol / sort_trow, captured from lib/glpspx0[12].js
+    run by minijs) and (b) the literal loop on random vectors with many insignificant and zero entries"""
+    Z = np.load(H.GOLDEN + "/ref_vectors.npz")
+    groups = sorted({k.rsplit("/", 1)[0] for k in Z.files if "/p_chuzr_" in k or "/d_chuzc_" in k})
+    assert len(groups) >= 80
+    checked = nontrivial = 0
+    for g in groups:
+        primal = "/p_chuzr_" in g
+        vec = Z[g + ("/tcol_vec" if primal else "/trow_vec")]
+        ind = Z[g + ("/tcol_ind" if primal else "/trow_ind")]
+        num = int(Z[g + ("/tcol_num" if primal else "/trow_num")])
+        n = len(vec) - 1
+        big = float(np.max(np.abs(vec[1:]))) if n else 0.0
+        eps = (1e-10 if primal else 1e-7) * (1.0 + 0.01 * big)      # smcp.tol_piv / sic tol_bnd (lib/glpspx02.js:1851)
+        got = nat.k_sort_list(n, vec, eps)
+        assert list(got) == [int(x) for x in ind[1:num + 1]], (g, list(got)[:10], list(ind[1:num + 1])[:10])
+        checked += 1
+        nontrivial += list(got) != sorted(got)
+    assert checked >= 80 and nontrivial >= 50
+    rng = np.random.default_rng(7)
+    for trial in range(60):
+        n = int(rng.integers(1, 5000)) if trial < 50 else int(rng.integers(40000, 70000))
+        vec = np.zeros(1 + n)
+        kind = rng.random(n)
+        vec[1:] = np.where(kind < 0.3, 0.0, np.where(kind < 0.6, 1e-12 * rng.standard_normal(n), rng.standard_normal(n)))
+        if trial % 7 == 0:
+            vec[1:] = np.where(rng.random(n) < 0.5, 1.0, 0.0)      # everything significant or zero
+        if trial % 11 == 0:
+            vec[1:] = 1e-13                                        # nothing significant
+        eps = 1e-9
+        got = nat.k_sort_list(n, vec, eps)
+        assert list(got) == _literal_sort(vec, eps), (trial, n)
