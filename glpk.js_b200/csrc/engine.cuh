@@ -81,6 +81,7 @@ struct EngArgs {
     int hdr_smem;             /* 1: keep per-CTA copies of the basis header in shared memory */
     int local_max;            /* ratio tests up to this length are replicated per CTA */
     int pf_dist;              /* dense T*v stream: L2 prefetch distance in column steps (0 = off) */
+    int pf_first;             /* first of the 8 columns of a trip that is prefetched (experiments) */
     int tie_stop;             /* 1: an exact tie in a ratio test stops the engine (ST_TIE)  */
     int *rslot, *slot_pos, *cslot, *slot_row;
     EngSlot *slots;           /* [ENG_RING][ENG_MAXG] arrival flags + CTA partials, zeroed by the host */
@@ -88,8 +89,9 @@ struct EngArgs {
     double *prof_bytes;       /* optional: algorithmic bytes per phase              */
 };
 
-struct EngCtx {
+template <bool HL> struct EngCtxT {
     int G, cta, tid, lane, warp, gtid, gsize;
+    int vtid;                 /* grid-wide index of the plain grid-stride loops, see eng_init */
     unsigned int seq;         /* barrier sequence number, identical in every thread */
     unsigned int dseq;        /* sequence number of the header-update hand-off     */
     long long t_last;
@@ -104,6 +106,13 @@ struct EngCtx {
     signed char *stat;
     int hdr_local;            /* 1: the pointers above are this CTA's private copies */
 };
+
+/* The basis header and the slot maps as the engine reads them: HL = true (small problems), per-CTA copies in
+   shared memory whose pointers live in the context; HL = false, the arrays in global memory, addressed straight
+   from the kernel parameters -- no pointer of the context stays live in a register (the 1024-thread kernel
+   has 64 registers per thread; seven 64-bit pointers were a quarter of them). */
+template <bool HL> __device__ __forceinline__ constexpr bool eng_hl(const EngCtxT<HL> &) { return HL; }
+#define XHDR(f) (eng_hl(X) ? X.f : A.f)
 
 __device__ __forceinline__ unsigned int eng_ld_relaxed(const unsigned int *p)
 {
@@ -123,13 +132,15 @@ __device__ __forceinline__ void eng_fence_acq() { asm volatile("fence.acq_rel.gp
    becoming visible in L2.  Slots rotate so that a CTA that runs ahead cannot
    overwrite a flag a slower CTA has not seen yet (it can be at most one
    barrier ahead). */
-__device__ __forceinline__ void eng_arrive(EngCtx &X, const EngArgs &A)
+template <bool HL>
+__device__ __forceinline__ void eng_arrive(EngCtxT<HL> &X, const EngArgs &A)
 {
     __syncthreads();
     X.seq++;
     if (X.G > 1 && X.tid == 0) eng_st_release(&A.slots[(X.seq & (ENG_RING - 1)) * ENG_MAXG + X.cta].flag, X.seq);
 }
-__device__ __forceinline__ void eng_wait(EngCtx &X, const EngArgs &A)
+template <bool HL>
+__device__ __forceinline__ void eng_wait(EngCtxT<HL> &X, const EngArgs &A)
 {
     if (X.G > 1) {
         if (X.tid < X.G) {
@@ -140,7 +151,8 @@ __device__ __forceinline__ void eng_wait(EngCtx &X, const EngArgs &A)
         __syncthreads();
     }
 }
-__device__ __forceinline__ void eng_bar(EngCtx &X, const EngArgs &A)
+template <bool HL>
+__device__ __forceinline__ void eng_bar(EngCtxT<HL> &X, const EngArgs &A)
 {
     eng_arrive(X, A);
     eng_wait(X, A);
@@ -151,10 +163,11 @@ __device__ __forceinline__ void eng_bar(EngCtx &X, const EngArgs &A)
    barrier of the iteration -- nobody reads the old header any more -- and then
    raises this flag; nobody reads the new header before seeing it.  Costs one
    flag round trip instead of a second grid barrier. */
-__device__ __forceinline__ void eng_header_done(EngCtx &X, const EngArgs &A)
+template <bool HL>
+__device__ __forceinline__ void eng_header_done(EngCtxT<HL> &X, const EngArgs &A)
 {
     X.dseq++;
-    if (X.G > 1 && !X.hdr_local) {
+    if (X.G > 1 && !HL) {
         unsigned int *done = &A.slots[ENG_RING * ENG_MAXG].flag;
         __syncthreads();        /* CTA 0: thread 0's header writes are ordered before the release */
         if (X.tid == 0) {
@@ -170,7 +183,8 @@ __device__ __forceinline__ void eng_header_done(EngCtx &X, const EngArgs &A)
 
 /* phase accounting for bench.py's roofline leg: CTA 0 leaves every barrier
    together with the grid, so its cycle stamps bound the phase */
-__device__ __forceinline__ void eng_mark(EngCtx &X, const EngArgs &A, int phase, double bytes)
+template <bool HL>
+__device__ __forceinline__ void eng_mark(EngCtxT<HL> &X, const EngArgs &A, int phase, double bytes)
 {
     if (A.prof_cyc != nullptr && X.cta == 0 && X.tid == 0) {
         const long long t = clock64();
@@ -183,8 +197,8 @@ __device__ __forceinline__ void eng_mark(EngCtx &X, const EngArgs &A, int phase,
 /* Barrier that carries a reduction: the CTA partial travels with the arrival
    flag; thread i of every CTA picks up partial i as soon as flag i is up and the
    G partials are combined in index order (deterministic, same in every CTA). */
-template <class Comb>
-__device__ Key eng_allreduce(EngCtx &X, const EngArgs &A, Key v, const Key &none, Comb comb)
+template <class Comb, bool HL>
+__device__ Key eng_allreduce(EngCtxT<HL> &X, const EngArgs &A, Key v, const Key &none, Comb comb)
 {
     __shared__ Key wres[ENG_MAXG / 32];
     v = block_reduce(v, none, comb);      /* its __syncthreads also fence this CTA's phase writes */
@@ -226,7 +240,8 @@ __device__ Key eng_allreduce(EngCtx &X, const EngArgs &A, Key v, const Key &none
 /* lanes per item for the segmented sums below: as many as the grid offers for
    nitems in ONE round (rounds of the multi-warp form are separated by
    __syncthreads), but no more than entries, and at least 4 */
-__device__ __forceinline__ int eng_pick_lp(const EngCtx &X, int nitems, double avg_len)
+template <bool HL>
+__device__ __forceinline__ int eng_pick_lp(const EngCtxT<HL> &X, int nitems, double avg_len)
 {
     int LP = 4;
     while (LP < 1024 && (long)nitems * LP * 2 <= (long)X.gsize && LP < avg_len) LP <<= 1;
@@ -238,8 +253,8 @@ __device__ __forceinline__ int eng_pick_lp(const EngCtx &X, int nitems, double a
    CTA, partial sums meet in shared memory in a fixed order.  body(i, l, LP, a)
    accumulates lane l's share into a[0..NV); out(i, a) runs in one thread.
    All threads of the grid must call with identical nitems and LP. */
-template <int NV, class Body, class Out>
-__device__ __forceinline__ void eng_items(const EngCtx &X, int nitems, int LP, Body body, Out out)
+template <int NV, class Body, class Out, bool HL>
+__device__ __forceinline__ void eng_items(const EngCtxT<HL> &X, int nitems, int LP, Body body, Out out)
 {
     __shared__ double part[NV][32];
     if (LP <= 32) {
@@ -307,9 +322,37 @@ __device__ __forceinline__ double eng_spdot(const int *ind, const double *val, i
     return (a0 + a1) + (a2 + a3);
 }
 
+/* sum_{j<n} term(j).  Unrolling by eight (ENG_SUM8: the loads of eight terms issued before the first product is
+   consumed) was measured 2 % SLOWER on C3: the extra live registers cost the dense stream more than the
+   shorter latency chains of these short loops gain (same-box A/B, profiles/r02s_ab.txt). */
+template <class Term>
+__device__ __forceinline__ double eng_sum8(int n, Term term)
+{
+#ifndef ENG_SUM8
+    double s0 = 0.0;
+    for (int jj = 0; jj < n; jj++) s0 += term(jj);
+    return s0;
+#endif
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    int j = 0;
+    for (; j + 7 < n; j += 8) {
+        const double t0 = term(j), t1 = term(j + 1), t2 = term(j + 2), t3 = term(j + 3),
+                     t4 = term(j + 4), t5 = term(j + 5), t6 = term(j + 6), t7 = term(j + 7);
+        a0 += t0; a1 += t1; a2 += t2; a3 += t3; a0 += t4; a1 += t5; a2 += t6; a3 += t7;
+    }
+    if (j + 3 < n) {
+        const double t0 = term(j), t1 = term(j + 1), t2 = term(j + 2), t3 = term(j + 3);
+        a0 += t0; a1 += t1; a2 += t2; a3 += t3;
+        j += 4;
+    }
+    for (; j < n; j++) a0 += term(j);
+    return (a0 + a1) + (a2 + a3);
+}
+
 /* ordered compaction inside a CTA: returns the position of this thread's
    element among the flagged ones and the total; all threads must call */
-__device__ __forceinline__ int eng_compact(const EngCtx &X, bool flag, int &total)
+template <bool HL>
+__device__ __forceinline__ int eng_compact(const EngCtxT<HL> &X, bool flag, int &total)
 {
     __shared__ int cnt[33];
     const unsigned int b = __ballot_sync(FULLMASK, flag);
@@ -337,7 +380,8 @@ __device__ __forceinline__ int eng_compact(const EngCtx &X, bool flag, int &tota
    Every CTA owns one contiguous range of rows (a multiple of 4, i.e. whole 32-byte
    sectors) and walks it in chunks of RB rows; its 32 warps split the list and
    the partial sums meet in shared memory in a fixed order.  Streams 8 L k bytes. */
-__device__ void eng_gemv_rows(const EngCtx &X, const EngArgs &A, int k, int L, const int *idx,
+template <bool HL>
+__device__ void eng_gemv_rows(const EngCtxT<HL> &X, const EngArgs &A, int k, int L, const int *idx,
                               const double *val, double *y, double *ycol, bool accumulate,
                               int nd, const double *z)
 {
@@ -379,7 +423,8 @@ __device__ void eng_gemv_rows(const EngCtx &X, const EngArgs &A, int k, int L, c
                     if (pfl && e + (A.pf_dist + ENG_SU) * cstep <= L) {
 #pragma unroll
                         for (int x = 0; x < ENG_SU; x++)
-                            asm volatile("prefetch.global.L2 [%0];" ::"l"(Tb2 + (size_t)(e + x * cstep) * ldt + pfo));
+                            if (x >= A.pf_first)
+                                asm volatile("prefetch.global.L2 [%0];" ::"l"(Tb2 + (size_t)(e + x * cstep) * ldt + pfo));
                     }
                     double2 t[ENG_SU];
 #pragma unroll
@@ -411,10 +456,10 @@ __device__ void eng_gemv_rows(const EngCtx &X, const EngArgs &A, int k, int L, c
                 for (int w = 0; w < 32; w++) s += red2[w][X.tid];
                 const int b2 = b0 + X.tid;
                 if (b2 < q1) {
-                    for (int j = 0; j < nd; j++) s += A.Fd[(size_t)j * ldt + b2] * z[j];
+                    s += eng_sum8(nd, [&](int j) { return A.Fd[(size_t)j * ldt + b2] * z[j]; });
                     if (accumulate) s += y[b2];
                     y[b2] = s;
-                    ycol[X.head[X.slot_pos[b2]] - A.m] = s;
+                    ycol[XHDR(head)[XHDR(slot_pos)[b2]] - A.m] = s;
                 }
             }
             __syncthreads();
@@ -461,10 +506,10 @@ __device__ void eng_gemv_rows(const EngCtx &X, const EngArgs &A, int k, int L, c
             for (int w = 0; w < 32; w++) s += red[w][X.tid];
             const int b2 = b0 + X.tid;
             if (b2 < q1) {
-                for (int j = 0; j < nd; j++) s += A.Fd[(size_t)j * ldt + b2] * z[j];
+                s += eng_sum8(nd, [&](int j) { return A.Fd[(size_t)j * ldt + b2] * z[j]; });
                 if (accumulate) s += y[b2];
                 y[b2] = s;
-                ycol[X.head[X.slot_pos[b2]] - A.m] = s;      /* the same value by basic column */
+                ycol[XHDR(head)[XHDR(slot_pos)[b2]] - A.m] = s;      /* the same value by basic column */
             }
         }
         __syncthreads();
@@ -519,12 +564,14 @@ __device__ __forceinline__ void eng_bulk_g2s(void *dst, const void *src, unsigne
 #define ENG_TNC 64
 #define ENG_TST 4
 #define ENG_TMA_SMEM (ENG_TST * ENG_TNC * 64)       /* doubles */
-__device__ __forceinline__ bool eng_gemv_tma_ok(const EngCtx &X, const EngArgs &A, int k)
+template <bool HL>
+__device__ __forceinline__ bool eng_gemv_tma_ok(const EngCtxT<HL> &X, const EngArgs &A, int k)
 {
     const int RPC = (((k + X.G - 1) / X.G) + 3) & ~3;
     return RPC > 16 && RPC <= 64 && A.dcap >= ENG_TMA_SMEM && k >= 4 * ENG_TNC;
 }
-__device__ void eng_gemv_dense_tma(const EngCtx &X, const EngArgs &A, int k, const double *v, double *y, double *ycol,
+template <bool HL>
+__device__ void eng_gemv_dense_tma(const EngCtxT<HL> &X, const EngArgs &A, int k, const double *v, double *y, double *ycol,
                                    int nd, const double *z)
 {
     __shared__ __align__(8) unsigned long long full_bar[ENG_TST], empty_bar[ENG_TST];
@@ -590,9 +637,9 @@ __device__ void eng_gemv_dense_tma(const EngCtx &X, const EngArgs &A, int k, con
 #pragma unroll
         for (int w = 0; w < 16; w++) sum += red2[w][X.tid];
         const int b2 = q0 + X.tid;
-        for (int j = 0; j < nd; j++) sum += A.Fd[(size_t)j * ldt + b2] * z[j];
+        sum += eng_sum8(nd, [&](int j) { return A.Fd[(size_t)j * ldt + b2] * z[j]; });
         y[b2] = sum;
-        ycol[X.head[X.slot_pos[b2]] - A.m] = sum;
+        ycol[XHDR(head)[XHDR(slot_pos)[b2]] - A.m] = sum;
     }
     __syncthreads();
     if (X.tid == 0)
@@ -604,7 +651,8 @@ __device__ void eng_gemv_dense_tma(const EngCtx &X, const EngArgs &A, int k, con
    lib/glpspx01.js:690-727): y = T h_N over the entries of column q that fall
    on rows of R_N.  CTA 0 also scatters h into the dense vector hz that the
    second half reads. */
-__device__ void eng_ftran_head_col(EngCtx &X, const EngArgs &A, int k, int kq, double *y, double *ycol, int nd)
+template <bool HL>
+__device__ void eng_ftran_head_col(EngCtxT<HL> &X, const EngArgs &A, int k, int kq, double *y, double *ycol, int nd)
 {
     __shared__ double zs[ENG_DB];
     const int m = A.m;
@@ -613,7 +661,7 @@ __device__ void eng_ftran_head_col(EngCtx &X, const EngArgs &A, int k, int kq, d
     if (!work && X.cta != 0) return;
     if (kq < m) {
         if (X.tid == 0) {
-            X.sh_i[0] = X.cslot[kq]; X.sh_d[0] = -1.0;
+            X.sh_i[0] = XHDR(cslot)[kq]; X.sh_d[0] = -1.0;
             if (X.cta == 0) A.hz[kq] = -1.0;
         }
         __syncthreads();
@@ -633,7 +681,7 @@ __device__ void eng_ftran_head_col(EngCtx &X, const EngArgs &A, int k, int kq, d
             int r = 0, cs = -1;
             double a = 0.0;
             if (valid) {
-                r = __ldg(A.a_ind + e); a = __ldg(A.a_val + e); cs = X.cslot[r];
+                r = __ldg(A.a_ind + e); a = __ldg(A.a_val + e); cs = XHDR(cslot)[r];
                 if (X.cta == 0) A.hz[r] = a;
             }
             int tot;
@@ -645,7 +693,7 @@ __device__ void eng_ftran_head_col(EngCtx &X, const EngArgs &A, int k, int kq, d
         if (X.tid < nd) {
             const double *Rj = A.Rd + (size_t)X.tid * A.ldt;
             double zz = 0.0;
-            for (int e = 0; e < L; e++) zz += X.sh_d[e] * Rj[X.sh_i[e]];
+            zz = eng_sum8(L, [&](int e) { return X.sh_d[e] * Rj[X.sh_i[e]]; });
             zs[X.tid] = zz;
         }
         __syncthreads();
@@ -658,8 +706,8 @@ __device__ void eng_ftran_head_col(EngCtx &X, const EngArgs &A, int k, int kq, d
    basic column (ycol, zero on non-basic columns): a basic auxiliary variable
    gathers its row of A, a basic structural one reads its own entry.
    PREP (primal): the reductions of k_primal_prep ride along. */
-template <bool PREP>
-__device__ __forceinline__ void eng_ftran_tail(const EngCtx &X, const EngArgs &A, const Ctrl &S,
+template <bool PREP, bool HL>
+__device__ __forceinline__ void eng_ftran_tail(const EngCtxT<HL> &X, const EngArgs &A, const Ctrl &S,
                                                const double *h, const double *ycol, double *x, Key &acc)
 {
     const int m = A.m;
@@ -667,11 +715,11 @@ __device__ __forceinline__ void eng_ftran_tail(const EngCtx &X, const EngArgs &A
     const int LP = eng_pick_lp(X, m, A.avg_row);
     eng_items<1>(X, m, LP,
         [&](int i, int l, int lp, double *a) {
-            const int kk = X.head[i];
+            const int kk = XHDR(head)[i];
             if (kk < m) a[0] = eng_spdot(A.at_ind, A.at_val, __ldg(A.at_ptr + kk), __ldg(A.at_ptr + kk + 1), l, lp, ycol);
         },
         [&](int i, const double *a) {
-            const int kk = X.head[i];
+            const int kk = XHDR(head)[i];
             const double t = (kk < m) ? h[kk] + a[0] : ycol[kk - m];
             x[i] = t;
             if (PREP) {
@@ -690,7 +738,8 @@ __device__ __forceinline__ void eng_ftran_tail(const EngCtx &X, const EngArgs &A
 /* two FTRAN tails in one pass over the rows of A (dual engine: tcol from (hz, ycol) and the tail of
    u = inv(B) v from (v, ycol2)): the row's indices and values are loaded once, the dependent chain
    head -> at_ptr -> (at_ind, at_val) -> gather is walked once instead of twice */
-__device__ __forceinline__ void eng_ftran_tail2(const EngCtx &X, const EngArgs &A,
+template <bool HL>
+__device__ __forceinline__ void eng_ftran_tail2(const EngCtxT<HL> &X, const EngArgs &A,
                                                 const double *h1, const double *ycol1, double *x1,
                                                 const double *h2, const double *ycol2, double *x2)
 {
@@ -698,7 +747,7 @@ __device__ __forceinline__ void eng_ftran_tail2(const EngCtx &X, const EngArgs &
     const int LP = eng_pick_lp(X, m, A.avg_row);
     eng_items<2>(X, m, LP,
         [&](int i, int l, int lp, double *a) {
-            const int kk = X.head[i];
+            const int kk = XHDR(head)[i];
             if (kk >= m) return;
             const int beg = __ldg(A.at_ptr + kk), end = __ldg(A.at_ptr + kk + 1);
             double p0 = 0.0, p1 = 0.0, q0 = 0.0, q1 = 0.0;
@@ -717,7 +766,7 @@ __device__ __forceinline__ void eng_ftran_tail2(const EngCtx &X, const EngArgs &
             a[0] = p0 + p1; a[1] = q0 + q1;
         },
         [&](int i, const double *a) {
-            const int kk = X.head[i];
+            const int kk = XHDR(head)[i];
             if (kk < m) { x1[i] = h1[kk] + a[0]; x2[i] = h2[kk] + a[1]; }
             else { x1[i] = ycol1[kk - m]; x2[i] = ycol2[kk - m]; }
         });
@@ -725,20 +774,22 @@ __device__ __forceinline__ void eng_ftran_tail2(const EngCtx &X, const EngArgs &
 
 /* BTRAN, first half: w[b] = c[pos_b] + sum_{r in R_B} A[r, j_b] c[bind[r]],
    with c given by position (v) and by row of a basic auxiliary (vrow) */
-__device__ __forceinline__ void eng_btran_head(const EngCtx &X, const EngArgs &A, int k)
+template <bool HL>
+__device__ __forceinline__ void eng_btran_head(const EngCtxT<HL> &X, const EngArgs &A, int k)
 {
     const int m = A.m;
     const int LP = eng_pick_lp(X, k, A.avg_col);
     eng_items<1>(X, k, LP,
         [&](int b, int l, int lp, double *a) {
-            const int j = X.head[X.slot_pos[b]] - m;
+            const int j = XHDR(head)[XHDR(slot_pos)[b]] - m;
             a[0] = eng_spdot(A.a_ind, A.a_val, __ldg(A.a_ptr + j), __ldg(A.a_ptr + j + 1), l, lp, A.vrow);
         },
-        [&](int b, const double *a) { A.wk[b] = A.v[X.slot_pos[b]] + a[0]; });
+        [&](int b, const double *a) { A.wk[b] = A.v[XHDR(slot_pos)[b]] + a[0]; });
 }
 
 /* zn[cs] = sum_b T[b, cs] w[b]: column dots, coalesced.  8 k^2 bytes. */
-__device__ __forceinline__ void eng_gemvT(const EngCtx &X, const EngArgs &A, int k, const double *w, double *zn)
+template <bool HL>
+__device__ __forceinline__ void eng_gemvT(const EngCtxT<HL> &X, const EngArgs &A, int k, const double *w, double *zn)
 {
     const int LP = max(32, eng_pick_lp(X, k, (double)k / 2));
     eng_items<1>(X, k, LP,
@@ -759,35 +810,38 @@ __device__ __forceinline__ void eng_gemvT(const EngCtx &X, const EngArgs &A, int
 
 /* rho = row p of inv(B) (eval_rho, lib/glpspx01.js:1030-1042), read out of T
    (plus the nd deferred rank-1 terms) */
-__device__ void eng_rho(EngCtx &X, const EngArgs &A, int k, int p, int nd)
+template <bool HL>
+__device__ void eng_rho(EngCtxT<HL> &X, const EngArgs &A, int k, int p, int nd)
 {
     __shared__ double fs[ENG_DB];
     const int m = A.m;
     const size_t ldt = (size_t)A.ldt;
-    const int kp = X.head[p];
-    for (int r = X.gtid; r < m; r += X.gsize)
-        if (X.cslot[r] < 0) A.rho[r] = (X.bind[r] == p) ? 1.0 : 0.0;
+    /* head[p] and rslot[p] are fetched together, and the deferred factors Fd_j[bp] are read (as broadcasts)
+       next to the Rd_j[cs] they multiply: two levels of dependent loads instead of four, no staging barrier */
+    const int kp = XHDR(head)[p];
+    const int bp0 = XHDR(rslot)[p];
+    for (int r = X.vtid; r < m; r += X.gsize) {
+        const int c = XHDR(cslot)[r], b = XHDR(bind)[r];
+        if (c < 0) A.rho[r] = (b == p) ? 1.0 : 0.0;
+    }
     if (kp >= m) {
-        const int bp = X.rslot[p];
-        if (X.tid < nd) fs[X.tid] = A.Fd[(size_t)X.tid * ldt + bp];
-        if (nd > 0) __syncthreads();
+        const int bp = bp0;
         const double *row = A.T + bp;
-        for (int cs = X.gtid; cs < k; cs += X.gsize) {
-            /* the strided element of T, the slot's row and the deferred terms are independent loads: all
-               issued before the first use (a chain of nd dependent L2 round trips otherwise) */
+        const double *Fp = A.Fd + bp;
+        for (int cs = X.vtid; cs < k; cs += X.gsize) {
             const double t0 = __ldcg(row + (size_t)cs * ldt);
-            const int r = X.slot_row[cs];
+            const int r = XHDR(slot_row)[cs];
             const double *Rc = A.Rd + cs;
             double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
             int j = 0;
-            for (; j + 7 < nd; j += 8) {
+            for (; j + 3 < nd; j += 4) {
                 const double r0 = Rc[(size_t)j * ldt], r1 = Rc[(size_t)(j + 1) * ldt], r2 = Rc[(size_t)(j + 2) * ldt],
-                             r3 = Rc[(size_t)(j + 3) * ldt], r4 = Rc[(size_t)(j + 4) * ldt], r5 = Rc[(size_t)(j + 5) * ldt],
-                             r6 = Rc[(size_t)(j + 6) * ldt], r7 = Rc[(size_t)(j + 7) * ldt];
-                a0 += fs[j] * r0; a1 += fs[j + 1] * r1; a2 += fs[j + 2] * r2; a3 += fs[j + 3] * r3;
-                a0 += fs[j + 4] * r4; a1 += fs[j + 5] * r5; a2 += fs[j + 6] * r6; a3 += fs[j + 7] * r7;
+                             r3 = Rc[(size_t)(j + 3) * ldt];
+                const double f0 = Fp[(size_t)j * ldt], f1 = Fp[(size_t)(j + 1) * ldt], f2 = Fp[(size_t)(j + 2) * ldt],
+                             f3 = Fp[(size_t)(j + 3) * ldt];
+                a0 += f0 * r0; a1 += f1 * r1; a2 += f2 * r2; a3 += f3 * r3;
             }
-            for (; j < nd; j++) a0 += fs[j] * Rc[(size_t)j * ldt];
+            for (; j < nd; j++) a0 += Fp[(size_t)j * ldt] * Rc[(size_t)j * ldt];
             A.rho[r] = t0 + ((a0 + a1) + (a2 + a3));
         }
         return;
@@ -803,17 +857,17 @@ __device__ void eng_rho(EngCtx &X, const EngArgs &A, int k, int p, int nd)
             const bool valid = e < segend;
             int pb = m;
             double a = 0.0;
-            if (valid) { pb = X.bind[m + __ldg(A.at_ind + e)]; a = __ldg(A.at_val + e); }
+            if (valid) { pb = XHDR(bind)[m + __ldg(A.at_ind + e)]; a = __ldg(A.at_val + e); }
             int tot;
             const int pos = eng_compact(X, valid && pb < m, tot);
-            if (valid && pb < m) { X.sh_i[L + pos] = X.rslot[pb]; X.sh_d[L + pos] = a; }
+            if (valid && pb < m) { X.sh_i[L + pos] = XHDR(rslot)[pb]; X.sh_d[L + pos] = a; }
             L += tot;
         }
         __syncthreads();
         if (X.tid < nd) {
             const double *Fj = A.Fd + (size_t)X.tid * ldt;
             double ww = 0.0;
-            for (int e = 0; e < L; e++) ww += X.sh_d[e] * Fj[X.sh_i[e]];
+            ww = eng_sum8(L, [&](int e) { return X.sh_d[e] * Fj[X.sh_i[e]]; });
             fs[X.tid] = ww;
         }
         if (nd > 0) __syncthreads();
@@ -832,9 +886,9 @@ __device__ void eng_rho(EngCtx &X, const EngArgs &A, int k, int p, int nd)
                 a[0] = a0 + a1;
             },
             [&](int cs, const double *a) {
-                const int r = X.slot_row[cs];
+                const int r = XHDR(slot_row)[cs];
                 double v = a[0];
-                for (int j = 0; j < nd; j++) v += fs[j] * A.Rd[(size_t)j * ldt + cs];
+                v += eng_sum8(nd, [&](int j) { return fs[j] * A.Rd[(size_t)j * ldt + cs]; });
                 A.rho[r] = acc ? A.rho[r] + v : v;
             });
         first = false;
@@ -846,8 +900,8 @@ __device__ void eng_rho(EngCtx &X, const EngArgs &A, int k, int p, int nd)
    columns; with PSE also s_j = N_j' u (primal update_gamma) from the same pass.
    Dual: acc.c collects |trow|_inf, acc.a the sum of trow_j^2 over the reference
    space, and trowcol gets the reference-space part of trow by column. */
-template <bool DUAL>
-__device__ __forceinline__ void eng_trow(const EngCtx &X, const EngArgs &A, const Ctrl &S, Key &acc)
+template <bool DUAL, bool HL>
+__device__ __forceinline__ void eng_trow(const EngCtxT<HL> &X, const EngArgs &A, const Ctrl &S, Key &acc)
 {
     const int m = A.m, n = A.n;
     const bool pse = gamma_on(&S);
@@ -855,8 +909,8 @@ __device__ __forceinline__ void eng_trow(const EngCtx &X, const EngArgs &A, cons
     const int LP = eng_pick_lp(X, n, A.avg_col);
     eng_items<2>(X, n, LP,
         [&](int j, int l, int lp, double *a) {
-            if (X.stat[j] == GLP_NS) return;
-            const int k = X.head[m + j];
+            if (XHDR(stat)[j] == GLP_NS) return;
+            const int k = XHDR(head)[m + j];
             if (k < m) {
                 if (l == 0) { a[0] = -A.rho[k]; if (want_s) a[1] = A.u[k]; }
                 return;
@@ -890,7 +944,7 @@ __device__ __forceinline__ void eng_trow(const EngCtx &X, const EngArgs &A, cons
             if (want_s) A.svec[j] = a[1];
             if (DUAL) {
                 acc.c = fmax(acc.c, fabs(t));
-                const int k = X.head[m + j];
+                const int k = XHDR(head)[m + j];
                 const bool in = pse && t != 0.0 && A.refsp[k];
                 if (in) acc.a += t * t;
                 if (k >= m) A.trowcol[k - m] = in ? t : 0.0;
@@ -901,7 +955,8 @@ __device__ __forceinline__ void eng_trow(const EngCtx &X, const EngArgs &A, cons
 /* dual update_gamma, first half (lib/glpspx02.js:1103-1132), by rows:
    v[r] = sum_{j in C, non-basic} N_j[r] trow_j; the entries on rows of R_N are
    also written in kernel order (wk) for the dense product with T */
-__device__ __forceinline__ void eng_gamma_rhs(const EngCtx &X, const EngArgs &A)
+template <bool HL>
+__device__ __forceinline__ void eng_gamma_rhs(const EngCtxT<HL> &X, const EngArgs &A)
 {
     const int m = A.m;
     const int LP = eng_pick_lp(X, m, A.avg_row);
@@ -910,10 +965,10 @@ __device__ __forceinline__ void eng_gamma_rhs(const EngCtx &X, const EngArgs &A)
             a[0] = -eng_spdot(A.at_ind, A.at_val, __ldg(A.at_ptr + row), __ldg(A.at_ptr + row + 1), l, lp, A.trowcol);
         },
         [&](int row, const double *a) {
-            const int pr = X.bind[row];
+            const int pr = XHDR(bind)[row];
             const double val = a[0] + ((pr >= m && A.refsp[row]) ? A.trow[pr - m] : 0.0);
             A.v[row] = val;
-            const int cs = X.cslot[row];
+            const int cs = XHDR(cslot)[row];
             if (cs >= 0) A.wk[cs] = val;
         });
 }
@@ -924,15 +979,16 @@ struct EngChange {
     double tp;
 };
 
-__device__ __forceinline__ void eng_describe_change(const EngCtx &X, const EngArgs &A, const Ctrl &S, EngChange &C)
+template <bool HL>
+__device__ __forceinline__ void eng_describe_change(const EngCtxT<HL> &X, const EngArgs &A, const Ctrl &S, EngChange &C)
 {
     const int m = A.m;
     C.p = S.p; C.q = S.q; C.k = S.k;
-    C.kp = X.head[C.p]; C.kq = X.head[m + C.q];
+    C.kp = XHDR(head)[C.p]; C.kq = XHDR(head)[m + C.q];
     C.LS = (C.kp < m); C.ES = (C.kq < m);
     C.tp = A.tcol[C.p];
-    C.csq = C.ES ? X.cslot[C.kq] : -1;
-    C.bp = C.LS ? -1 : X.rslot[C.p];
+    C.csq = C.ES ? XHDR(cslot)[C.kq] : -1;
+    C.bp = C.LS ? -1 : XHDR(rslot)[C.p];
     C.ctgt = C.LS ? (C.ES ? C.csq : C.k) : -1;
     C.bnew = (C.LS && !C.ES) ? C.k : -1;
     C.knew = C.k;
@@ -948,7 +1004,8 @@ __device__ __forceinline__ void eng_describe_change(const EngCtx &X, const EngAr
    Algorithmic bytes: 16 k^2. */
 #define ENG_UR 128
 #define ENG_UC 32
-__device__ void eng_update_T(const EngCtx &X, const EngArgs &A, const EngChange &C)
+template <bool HL>
+__device__ void eng_update_T(const EngCtxT<HL> &X, const EngArgs &A, const EngChange &C)
 {
     const int k = C.k;
     const size_t ldt = (size_t)A.ldt;
@@ -962,7 +1019,7 @@ __device__ void eng_update_T(const EngCtx &X, const EngArgs &A, const EngChange 
         const int c0 = (tile / ntr) * ENG_UC;
         if (b >= kd) continue;
         const int sb = (removal && b == C.bp) ? k - 1 : b;
-        const int i = X.slot_pos[sb];
+        const int i = XHDR(slot_pos)[sb];
         const bool isp = (i == C.p);
         const double f = isp ? -1.0 / tp : A.tcol[i] / tp;
 #pragma unroll
@@ -972,7 +1029,7 @@ __device__ void eng_update_T(const EngCtx &X, const EngArgs &A, const EngChange 
             double *dst = A.T + (size_t)cs * ldt + b;
             if (C.LS && C.ES && cs == C.csq) { *dst = -A.tcol[i] / tp; continue; }
             const int scs = (removal && cs == C.csq) ? k - 1 : cs;
-            const double rs = A.rho[X.slot_row[scs]];
+            const double rs = A.rho[XHDR(slot_row)[scs]];
             if (isp) { *dst = rs * f; continue; }
             const bool moved = (sb != b) || (scs != cs);
             if (f != 0.0 || moved) {
@@ -983,9 +1040,9 @@ __device__ void eng_update_T(const EngCtx &X, const EngArgs &A, const EngChange 
     }
     if (C.bnew >= 0) {
         /* a row and a column join: column k (rows 0..k) and row k (columns 0..k-1) */
-        for (int t = X.gtid; t < 2 * k + 1; t += X.gsize) {
-            if (t < k) A.T[(size_t)k * ldt + t] = -A.tcol[X.slot_pos[t]] / tp;
-            else if (t < 2 * k) A.T[(size_t)(t - k) * ldt + k] = -A.rho[X.slot_row[t - k]] / tp;
+        for (int t = X.vtid; t < 2 * k + 1; t += X.gsize) {
+            if (t < k) A.T[(size_t)k * ldt + t] = -A.tcol[XHDR(slot_pos)[t]] / tp;
+            else if (t < 2 * k) A.T[(size_t)(t - k) * ldt + k] = -A.rho[XHDR(slot_row)[t - k]] / tp;
             else A.T[(size_t)k * ldt + k] = -1.0 / tp;
         }
     }
@@ -996,7 +1053,8 @@ __device__ void eng_update_T(const EngCtx &X, const EngArgs &A, const EngChange 
    touches T: a replaced row or column is written directly (and its entries in
    the earlier terms are zeroed), a leaving row/column is filled from the last
    one, in T and in every stored term alike. */
-__device__ void eng_defer_apply(const EngCtx &X, const EngArgs &A, const EngChange &C, int nd)
+template <bool HL>
+__device__ void eng_defer_apply(const EngCtxT<HL> &X, const EngArgs &A, const EngChange &C, int nd)
 {
     const int k = C.k;
     const size_t ldt = (size_t)A.ldt;
@@ -1006,26 +1064,26 @@ __device__ void eng_defer_apply(const EngCtx &X, const EngArgs &A, const EngChan
     /* entries that the structural part below rewrites are left to it (one writer per cell) */
     const int skipF = removal ? C.bp : -1;
     const int skipR = (removal || (C.LS && C.ES)) ? C.csq : -1;
-    for (int t = X.gtid; t < k; t += X.gsize) {
-        const int i = X.slot_pos[t];
+    for (int t = X.vtid; t < k; t += X.gsize) {
+        const int i = XHDR(slot_pos)[t];
         if (t != skipF) Fn[t] = (i == C.p) ? 0.0 : -A.tcol[i] / tp;    /* row of p: replaced below */
-        if (t != skipR) Rn[t] = A.rho[X.slot_row[t]];
+        if (t != skipR) Rn[t] = A.rho[XHDR(slot_row)[t]];
     }
     if (C.LS && C.ES) {
         /* column csq is replaced: T[:, csq] = -tcol_S / tp */
-        for (int t = X.gtid; t < k; t += X.gsize) A.T[(size_t)C.csq * ldt + t] = -A.tcol[X.slot_pos[t]] / tp;
-        for (int j = X.gtid; j <= nd; j += X.gsize) A.Rd[(size_t)j * ldt + C.csq] = 0.0;
+        for (int t = X.vtid; t < k; t += X.gsize) A.T[(size_t)C.csq * ldt + t] = -A.tcol[XHDR(slot_pos)[t]] / tp;
+        for (int j = X.vtid; j <= nd; j += X.gsize) A.Rd[(size_t)j * ldt + C.csq] = 0.0;
     } else if (C.LS && !C.ES) {
         /* a row and a column join at slot k */
-        for (int t = X.gtid; t < 2 * k + 1; t += X.gsize) {
-            if (t < k) A.T[(size_t)k * ldt + t] = -A.tcol[X.slot_pos[t]] / tp;
-            else if (t < 2 * k) A.T[(size_t)(t - k) * ldt + k] = -A.rho[X.slot_row[t - k]] / tp;
+        for (int t = X.vtid; t < 2 * k + 1; t += X.gsize) {
+            if (t < k) A.T[(size_t)k * ldt + t] = -A.tcol[XHDR(slot_pos)[t]] / tp;
+            else if (t < 2 * k) A.T[(size_t)(t - k) * ldt + k] = -A.rho[XHDR(slot_row)[t - k]] / tp;
             else A.T[(size_t)k * ldt + k] = -1.0 / tp;
         }
-        for (int j = X.gtid; j <= nd; j += X.gsize) { A.Fd[(size_t)j * ldt + k] = 0.0; A.Rd[(size_t)j * ldt + k] = 0.0; }
+        for (int j = X.vtid; j <= nd; j += X.gsize) { A.Fd[(size_t)j * ldt + k] = 0.0; A.Rd[(size_t)j * ldt + k] = 0.0; }
     } else if (removal) {
         /* row bp and column csq leave: the last row/column moves into the hole */
-        for (int t = X.gtid; t < 2 * k; t += X.gsize) {
+        for (int t = X.vtid; t < 2 * k; t += X.gsize) {
             if (t < k) {            /* destination (bp, c = t), c < k - 1 */
                 const int c = t;
                 if (C.bp != k - 1 && c < k - 1) {
@@ -1038,16 +1096,16 @@ __device__ void eng_defer_apply(const EngCtx &X, const EngArgs &A, const EngChan
                     A.T[(size_t)C.csq * ldt + sr] = __ldcg(A.T + (size_t)(k - 1) * ldt + sr);
             }
         }
-        for (int j = X.gtid; j <= nd; j += X.gsize) {
-            if (C.bp != k - 1) A.Fd[(size_t)j * ldt + C.bp] = (j == nd) ? -A.tcol[X.slot_pos[k - 1]] / tp
+        for (int j = X.vtid; j <= nd; j += X.gsize) {
+            if (C.bp != k - 1) A.Fd[(size_t)j * ldt + C.bp] = (j == nd) ? -A.tcol[XHDR(slot_pos)[k - 1]] / tp
                                                                        : A.Fd[(size_t)j * ldt + (k - 1)];
-            if (C.csq != k - 1) A.Rd[(size_t)j * ldt + C.csq] = (j == nd) ? A.rho[X.slot_row[k - 1]]
+            if (C.csq != k - 1) A.Rd[(size_t)j * ldt + C.csq] = (j == nd) ? A.rho[XHDR(slot_row)[k - 1]]
                                                                          : A.Rd[(size_t)j * ldt + (k - 1)];
         }
     } else {
         /* a structural variable replaces a structural one: row bp = -rho_N / tp */
-        for (int c = X.gtid; c < k; c += X.gsize) A.T[(size_t)c * ldt + C.bp] = -A.rho[X.slot_row[c]] / tp;
-        for (int j = X.gtid; j < nd; j += X.gsize) A.Fd[(size_t)j * ldt + C.bp] = 0.0;
+        for (int c = X.vtid; c < k; c += X.gsize) A.T[(size_t)c * ldt + C.bp] = -A.rho[XHDR(slot_row)[c]] / tp;
+        for (int j = X.vtid; j < nd; j += X.gsize) A.Fd[(size_t)j * ldt + C.bp] = 0.0;
     }
 }
 
@@ -1070,7 +1128,8 @@ __device__ __forceinline__ void eng_dmma(double &c0, double &c1, double a, doubl
    arithmetic of the others. */
 #define ENG_RS 68
 #define ENG_FLUSH_SMEM (ENG_DB * ENG_RS)
-__device__ void eng_flush(const EngCtx &X, const EngArgs &A, int k, int nd)
+template <bool HL>
+__device__ void eng_flush(const EngCtxT<HL> &X, const EngArgs &A, int k, int nd)
 {
     if (nd <= 0 || k <= 0) return;
     const size_t ldt = (size_t)A.ldt;
@@ -1152,10 +1211,11 @@ __device__ void eng_bookkeep_hdr(int *head, int *bind, int *rslot, int *slot_pos
 /* the whole O(1) remainder of a basis change: thread 0 of every CTA updates its
    private header (if any), thread 0 of CTA 0 the arrays in global memory and the
    vectors whose zero pattern follows the basis */
-__device__ void eng_bookkeep(const EngCtx &X, const EngArgs &A, const EngChange &C, int new_stat, bool drop_refsp)
+template <bool HL>
+__device__ void eng_bookkeep(const EngCtxT<HL> &X, const EngArgs &A, const EngChange &C, int new_stat, bool drop_refsp)
 {
     const int m = A.m;
-    if (X.hdr_local)
+    if (HL)
         eng_bookkeep_hdr(X.head, X.bind, X.rslot, X.slot_pos, X.cslot, X.slot_row, X.stat, m, C, new_stat);
     if (X.cta != 0) return;
     eng_bookkeep_hdr(A.head, A.bind, A.rslot, A.slot_pos, A.cslot, A.slot_row, A.stat, m, C, new_stat);
@@ -1166,21 +1226,28 @@ __device__ void eng_bookkeep(const EngCtx &X, const EngArgs &A, const EngChange 
     if (!C.ES) A.trowcol[C.kq - m] = 0.0;
 }
 
-__device__ __forceinline__ void eng_init(EngCtx &X, const EngArgs &A, double *dyn)
+template <bool HL>
+__device__ __forceinline__ void eng_init(EngCtxT<HL> &X, const EngArgs &A, double *dyn)
 {
     X.G = gridDim.x; X.cta = blockIdx.x; X.tid = threadIdx.x;
     X.lane = X.tid & 31; X.warp = X.tid >> 5;
+    /* vtid: grid-wide thread index with groups of four warps interleaved over the CTAs (virtual group =
+       (tid / 128) * G + cta): the first N entries of a grid-stride loop land on threads 0..127 of every CTA,
+       then on threads 128..255, ... instead of filling CTA 0, 1, 2, ... to the brim.  The vectors of the small
+       phases (m, n, k entries against 150 k threads) are gathers bound by one SM's load/store path: on C3 the
+       update loops ran on 16 of 148 SMs.  128 consecutive entries stay together so that the warps of a group
+       still share the 128-byte lines of the index arrays in L1 (interleaving single warps cost more in L2
+       requests than it gained: profiles/r02m_interleave.txt). */
     X.gtid = X.cta * ENG_NT + X.tid; X.gsize = X.G * ENG_NT;
+    X.vtid = ((((X.tid >> 7) * X.G + X.cta) << 7) | (X.tid & 127));
     X.seq = 0u;
     X.dseq = 0u;
     X.t_last = clock64();
     X.sh_d = dyn;
     X.sh_i = (int *)(dyn + A.dcap);
     X.sh_red2 = (double *)(X.sh_i + ENG_LCAP);
-    X.head = A.head; X.bind = A.bind; X.rslot = A.rslot; X.slot_pos = A.slot_pos;
-    X.cslot = A.cslot; X.slot_row = A.slot_row; X.stat = A.stat;
-    X.hdr_local = 0;
-    if (A.hdr_smem) {
+    X.hdr_local = HL ? 1 : 0;
+    if (HL) {
         const int m = A.m, n = A.n, ldt = A.ldt;
         int *base = (int *)(X.sh_red2 + 32 * 65);
         X.head = base; X.bind = X.head + (m + n); X.rslot = X.bind + (m + n); X.cslot = X.rslot + m;
@@ -1190,14 +1257,13 @@ __device__ __forceinline__ void eng_init(EngCtx &X, const EngArgs &A, double *dy
         for (int t = X.tid; t < m; t += ENG_NT) { X.rslot[t] = A.rslot[t]; X.cslot[t] = A.cslot[t]; }
         for (int t = X.tid; t < ldt; t += ENG_NT) { X.slot_pos[t] = A.slot_pos[t]; X.slot_row[t] = A.slot_row[t]; }
         for (int t = X.tid; t < n; t += ENG_NT) X.stat[t] = A.stat[t];
-        X.hdr_local = 1;
         __syncthreads();
     }
 }
 
 /* block-wide reduction whose result every thread of the CTA gets */
-template <class Comb>
-__device__ Key eng_blockall(const EngCtx &X, Key v, const Key &none, Comb comb)
+template <class Comb, bool HL>
+__device__ Key eng_blockall(const EngCtxT<HL> &X, Key v, const Key &none, Comb comb)
 {
     __shared__ Key res;
     v = block_reduce(v, none, comb);
@@ -1221,12 +1287,13 @@ enum { /* phase slots of the cycle accounting (12 per engine) */
 /* ------------------------------------------------------------------ */
 /* primal engine: lib/glpspx01.js:1868-2056                           */
 /* ------------------------------------------------------------------ */
+template <bool HL>
 __global__ void __launch_bounds__(ENG_NT, 1) k_engine_primal(EngArgs A)
 {
     extern __shared__ __align__(128) double eng_dyn[];
     __shared__ Ctrl S;
     __shared__ EngChange C;
-    EngCtx X;
+    EngCtxT<HL> X;
     eng_init(X, A, eng_dyn);
     const int m = A.m, n = A.n;
     const bool local_ratio = (m <= A.local_max);
@@ -1240,7 +1307,7 @@ __global__ void __launch_bounds__(ENG_NT, 1) k_engine_primal(EngArgs A)
         if (it == 0) {
             Key none = {0.0, 0.0, 0.0, INT_MAX, 0};
             Key v = none;
-            scan_chuzc_primal(v, X.gtid, X.gsize, n, X.stat, A.cbar, A.gamma, A.tol_dj, -1, 0);
+            scan_chuzc_primal(v, X.vtid, X.gsize, n, XHDR(stat), A.cbar, A.gamma, A.tol_dj, -1, 0);
             Key r = eng_allreduce(X, A, v, none, CombArgMax());
             qnext = (r.a > 0.0 && r.pos != INT_MAX) ? r.pos : P_NONE;
             eng_mark(X, A, PP_PRICE0, 17.0 * n);
@@ -1253,7 +1320,7 @@ __global__ void __launch_bounds__(ENG_NT, 1) k_engine_primal(EngArgs A)
         __syncthreads();
         if (S.status != ST_OK) break;
         const int q = S.q;
-        const int kq = X.head[m + q];
+        const int kq = XHDR(head)[m + q];
         const double nnz_q = (kq < m) ? 1.0 : (double)(__ldg(A.a_ptr + (kq - m) + 1) - __ldg(A.a_ptr + (kq - m)));
         /* ---- A: tcol, first half ---- */
         eng_ftran_head_col(X, A, S.k, kq, A.yk, A.ycol, 0);
@@ -1310,7 +1377,7 @@ __global__ void __launch_bounds__(ENG_NT, 1) k_engine_primal(EngArgs A)
                 for (int x = 0; x < 2; x++) {
                     const int pos = X.tid + x * ENG_NT;
                     ok[x] = (pos < m) && ratio_primal_elem(cand[x], pos, S.phase, sgn, S.eps, A.rtol, A.type, A.lb, A.ub,
-                                                           A.coef, X.head, A.bbar, A.tcol);
+                                                           A.coef, XHDR(head), A.bbar, A.tcol);
                     if (ok[x]) { const Key c = ratio_primal_key(cand[x], 1, pos); CombRatio1()(v, c); }
                 }
                 Key r = eng_blockall(X, v, none, CombRatio1());
@@ -1331,14 +1398,14 @@ __global__ void __launch_bounds__(ENG_NT, 1) k_engine_primal(EngArgs A)
                 }
             } else {
                 scan_ratio_primal(v, X.tid, ENG_NT, 1, S.phase, sgn, S.eps, 0.0, A.rtol, A.type, A.lb, A.ub,
-                                  A.coef, X.head, A.bbar, A.tcol, nullptr, m);
+                                  A.coef, XHDR(head), A.bbar, A.tcol, nullptr, m);
                 Key r = eng_blockall(X, v, none, CombRatio1());
                 if (X.tid == 0) fin_ratio_primal(&S, r, 1, sgn, A.rtol, nullptr, A.tie_stop != 0);
                 __syncthreads();
                 if (S.status == ST_OK && !S.skip2) {
                     v = none;
                     scan_ratio_primal(v, X.tid, ENG_NT, 2, S.phase, sgn, S.eps, S.tmax, A.rtol, A.type, A.lb, A.ub,
-                                      A.coef, X.head, A.bbar, A.tcol, nullptr, m);
+                                      A.coef, XHDR(head), A.bbar, A.tcol, nullptr, m);
                     r = eng_blockall(X, v, none, CombRatio2());
                     if (X.tid == 0) fin_ratio_primal(&S, r, 2, sgn, A.rtol, nullptr, A.tie_stop != 0);
                     __syncthreads();
@@ -1353,11 +1420,11 @@ __global__ void __launch_bounds__(ENG_NT, 1) k_engine_primal(EngArgs A)
             eng_mark(X, A, PP_B, 0.0);
             Key none = {DBL_MAX, 0.0, 0.0, INT_MAX, 0};
             Key v = none;
-            if (X.gtid == 0 && A.type[kq] == GLP_DB) {
+            if (X.vtid == 0 && A.type[kq] == GLP_DB) {
                 v.a = __dsub_rn(A.ub[kq], A.lb[kq]); v.b = 1.0; v.pos = -1; v.aux = 0;
             }
-            scan_ratio_primal(v, X.gtid, X.gsize, 1, S.phase, sgn, S.eps, 0.0, A.rtol, A.type, A.lb, A.ub,
-                              A.coef, X.head, A.bbar, A.tcol, nullptr, m);
+            scan_ratio_primal(v, X.vtid, X.gsize, 1, S.phase, sgn, S.eps, 0.0, A.rtol, A.type, A.lb, A.ub,
+                              A.coef, XHDR(head), A.bbar, A.tcol, nullptr, m);
             if (pse) eng_btran_head(X, A, S.k);
             Key r = eng_allreduce(X, A, v, none, CombRatio1());
             if (X.cta == 0 && X.tid == 0) A.cbar[q] = S.d1;     /* every CTA has read the old value by now */
@@ -1367,8 +1434,8 @@ __global__ void __launch_bounds__(ENG_NT, 1) k_engine_primal(EngArgs A)
             eng_mark(X, A, PP_R1, 45.0 * m);
             if (S.status == ST_OK && !S.skip2) {
                 v = none;
-                scan_ratio_primal(v, X.gtid, X.gsize, 2, S.phase, sgn, S.eps, S.tmax, A.rtol, A.type, A.lb, A.ub,
-                                  A.coef, X.head, A.bbar, A.tcol, nullptr, m);
+                scan_ratio_primal(v, X.vtid, X.gsize, 2, S.phase, sgn, S.eps, S.tmax, A.rtol, A.type, A.lb, A.ub,
+                                  A.coef, XHDR(head), A.bbar, A.tcol, nullptr, m);
                 r = eng_allreduce(X, A, v, none, CombRatio2());
                 if (X.tid == 0) fin_ratio_primal(&S, r, 2, sgn, A.rtol, nullptr, A.tie_stop != 0);
                 __syncthreads();
@@ -1402,9 +1469,9 @@ __global__ void __launch_bounds__(ENG_NT, 1) k_engine_primal(EngArgs A)
                         for (; b < k; b += lp) a0 += __ldcg(col + b) * A.wk[b];
                         a[0] = (a0 + a1) + (a2 + a3);
                     },
-                    [&](int cs, const double *a) { A.u[X.slot_row[cs]] = a[0]; });
-                for (int r = X.gtid; r < m; r += X.gsize)
-                    if (X.cslot[r] < 0) A.u[r] = A.vrow[r];
+                    [&](int cs, const double *a) { A.u[XHDR(slot_row)[cs]] = a[0]; });
+                for (int r = X.vtid; r < m; r += X.gsize)
+                    if (XHDR(cslot)[r] < 0) A.u[r] = A.vrow[r];
             }
             eng_bar(X, A);
             eng_mark(X, A, PP_C, 12.0 * m + 8.0 * S.k + (pse ? 8.0 * S.k * (double)S.k + 20.0 * m : 0.0));
@@ -1433,21 +1500,21 @@ __global__ void __launch_bounds__(ENG_NT, 1) k_engine_primal(EngArgs A)
                 pricing of the next iteration from the values just written ---- */
         {
             const double teta = S.teta;
-            const double xq = get_xN(X.stat, X.head, A.lb, A.ub, m, q);
+            const double xq = get_xN(XHDR(stat), XHDR(head), A.lb, A.ub, m, q);
             int new_stat;
             if (p >= 0) new_stat = S.p_stat;
-            else new_stat = (X.stat[q] == GLP_NL) ? GLP_NU : GLP_NL;
+            else new_stat = (XHDR(stat)[q] == GLP_NL) ? GLP_NU : GLP_NL;
             const double new_dq = S.new_dq;
             const double pivot = (p >= 0) ? A.trow[q] : 1.0;
             const int kp = (p >= 0) ? C.kp : 0;
             const int phase = S.phase;
             Key pnone = {0.0, 0.0, 0.0, INT_MAX, 0};
             Key pv = pnone;
-            for (int t = X.gtid; t < n; t += X.gsize) {
+            for (int t = X.vtid; t < n; t += X.gsize) {
                 double dj, g;
                 int st;
                 if (p < 0) {
-                    dj = A.cbar[t]; g = A.gamma[t]; st = X.stat[t];
+                    dj = A.cbar[t]; g = A.gamma[t]; st = XHDR(stat)[t];
                     if (t == q) { dj = S.d1; A.cbar[q] = dj; st = new_stat; }     /* reeval_cost result */
                 }
                 else if (t == q) {
@@ -1466,13 +1533,13 @@ __global__ void __launch_bounds__(ENG_NT, 1) k_engine_primal(EngArgs A)
                     st = new_stat;
                 } else {
                     const double tr = A.trow[t];
-                    dj = A.cbar[t]; g = A.gamma[t]; st = X.stat[t];
+                    dj = A.cbar[t]; g = A.gamma[t]; st = XHDR(stat)[t];
                     if (tr != 0.0) {
                         dj -= tr * new_dq;
                         A.cbar[t] = dj;
                         if (pse) {
                             const double tt = tr / pivot;
-                            const int k = X.head[m + t];
+                            const int k = XHDR(head)[m + t];
                             const double t1 = g + tt * tt * S.gamma_q + 2.0 * tt * A.svec[t];
                             const double t2 = (A.refsp[k] ? 1.0 : 0.0) + S.delta_q * tt * tt;
                             g = (t1 >= t2 ? t1 : t2);
@@ -1487,7 +1554,7 @@ __global__ void __launch_bounds__(ENG_NT, 1) k_engine_primal(EngArgs A)
                the reference's next iteration, lib/glpspx01.js:1768-1775)?  The count rides on the pricing key. */
             int ninf = 0;
             if (phase != 1) {
-                for (int t = X.gtid; t < m; t += X.gsize) {
+                for (int t = X.vtid; t < m; t += X.gsize) {
                     if (t == p) A.bbar[t] = xq + teta;
                     else if (teta != 0.0) {
                         const double tc = A.tcol[t];
@@ -1495,7 +1562,7 @@ __global__ void __launch_bounds__(ENG_NT, 1) k_engine_primal(EngArgs A)
                     }
                 }
             } else {
-                for (int t = X.gtid; t < m; t += X.gsize) {
+                for (int t = X.vtid; t < m; t += X.gsize) {
                     double b;
                     if (t == p) { b = xq + teta; A.bbar[t] = b; continue; }      /* xN[q] enters with a zero auxiliary cost */
                     b = A.bbar[t];
@@ -1503,7 +1570,7 @@ __global__ void __launch_bounds__(ENG_NT, 1) k_engine_primal(EngArgs A)
                         const double tc = A.tcol[t];
                         if (tc != 0.0) { b += tc * teta; A.bbar[t] = b; }
                     }
-                    const int k = X.head[t];
+                    const int k = XHDR(head)[t];
                     const double c = A.coef[k];
                     if (c < 0.0) ninf += (b < A.lb[k] - relax(A.tol_bnd, A.lb[k])) ? 1 : 0;
                     else if (c > 0.0) ninf += (b > A.ub[k] + relax(A.tol_bnd, A.ub[k])) ? 1 : 0;
@@ -1528,7 +1595,7 @@ __global__ void __launch_bounds__(ENG_NT, 1) k_engine_primal(EngArgs A)
                     if (phase == 1 && X.cta == 0) A.coef[C.kp] = 0.0;       /* lib/glpspx01.js:2016-2020 */
                     eng_bookkeep(X, A, C, new_stat, false);
                 } else {
-                    if (X.hdr_local) X.stat[q] = (signed char)new_stat;
+                    if (HL) X.stat[q] = (signed char)new_stat;
                     if (X.cta == 0) A.stat[q] = (signed char)new_stat;
                 }
             }
@@ -1546,12 +1613,13 @@ __global__ void __launch_bounds__(ENG_NT, 1) k_engine_primal(EngArgs A)
 /* ------------------------------------------------------------------ */
 /* dual engine: lib/glpspx02.js:1780-1966                             */
 /* ------------------------------------------------------------------ */
+template <bool HL>
 __global__ void __launch_bounds__(ENG_NT, 1) k_engine_dual(EngArgs A)
 {
     extern __shared__ __align__(128) double eng_dyn[];
     __shared__ Ctrl S;
     __shared__ EngChange C;
-    EngCtx X;
+    EngCtxT<HL> X;
     eng_init(X, A, eng_dyn);
     const int m = A.m, n = A.n;
     const bool local_ratio = (n <= A.local_max);
@@ -1567,7 +1635,7 @@ __global__ void __launch_bounds__(ENG_NT, 1) k_engine_dual(EngArgs A)
         if (it == 0) {
             Key none = {0.0, 0.0, 0.0, INT_MAX, 0};
             Key v = none;
-            scan_chuzr_dual(v, X.gtid, X.gsize, m, A.type, A.lb, A.ub, X.head, A.bbar, A.gamma, A.tol_bnd, -1, 0);
+            scan_chuzr_dual(v, X.vtid, X.gsize, m, A.type, A.lb, A.ub, XHDR(head), A.bbar, A.gamma, A.tol_bnd, -1, 0);
             Key r = eng_allreduce(X, A, v, none, CombArgMax());
             const bool found = (r.a > 0.0 && r.pos != INT_MAX);
             pnext = found ? r.pos : P_NONE;
@@ -1586,6 +1654,7 @@ __global__ void __launch_bounds__(ENG_NT, 1) k_engine_dual(EngArgs A)
         const bool pse = gamma_on(&S);
         const double sgn = (S.delta > 0.0 ? +1.0 : -1.0);
         /* ---- rho ---- */
+        eng_mark(X, A, 10, 0.0);                  /* header hand-off of the previous iteration + loop top */
         eng_rho(X, A, S.k, p, nd);
         eng_bar(X, A);
         eng_mark(X, A, PD_RHO, 12.0 * m + 8.0 * S.k + 8.0 * nd * S.k);
@@ -1614,13 +1683,13 @@ __global__ void __launch_bounds__(ENG_NT, 1) k_engine_dual(EngArgs A)
         if (local_ratio) {
             Key none = {DBL_MAX, 0.0, 0.0, INT_MAX, 0};
             Key v = none;
-            scan_ratio_dual(v, X.tid, ENG_NT, 1, sgn, S.eps, 0.0, A.rtol, X.stat, A.cbar, A.trow, nullptr, n);
+            scan_ratio_dual(v, X.tid, ENG_NT, 1, sgn, S.eps, 0.0, A.rtol, XHDR(stat), A.cbar, A.trow, nullptr, n);
             Key r = eng_blockall(X, v, none, CombRatio1());
             if (X.tid == 0) fin_ratio_dual(&S, r, 1, sgn, A.rtol, nullptr, A.tie_stop != 0);
             __syncthreads();
             if (S.status == ST_OK && !S.skip2) {
                 v = none;
-                scan_ratio_dual(v, X.tid, ENG_NT, 2, sgn, S.eps, S.tmax, A.rtol, X.stat, A.cbar, A.trow, nullptr, n);
+                scan_ratio_dual(v, X.tid, ENG_NT, 2, sgn, S.eps, S.tmax, A.rtol, XHDR(stat), A.cbar, A.trow, nullptr, n);
                 r = eng_blockall(X, v, none, CombRatio2());
                 if (X.tid == 0) fin_ratio_dual(&S, r, 2, sgn, A.rtol, nullptr, A.tie_stop != 0);
                 __syncthreads();
@@ -1634,7 +1703,7 @@ __global__ void __launch_bounds__(ENG_NT, 1) k_engine_dual(EngArgs A)
         } else {
             Key none = {DBL_MAX, 0.0, 0.0, INT_MAX, 0};
             Key v = none;
-            scan_ratio_dual(v, X.gtid, X.gsize, 1, sgn, S.eps, 0.0, A.rtol, X.stat, A.cbar, A.trow, nullptr, n);
+            scan_ratio_dual(v, X.vtid, X.gsize, 1, sgn, S.eps, 0.0, A.rtol, XHDR(stat), A.cbar, A.trow, nullptr, n);
             if (pse) eng_gamma_rhs(X, A);
             Key r = eng_allreduce(X, A, v, none, CombRatio1());
             if (X.tid == 0) fin_ratio_dual(&S, r, 1, sgn, A.rtol, nullptr, A.tie_stop != 0);
@@ -1656,7 +1725,7 @@ __global__ void __launch_bounds__(ENG_NT, 1) k_engine_dual(EngArgs A)
             }
             if (!S.skip2) {
                 v = none;
-                scan_ratio_dual(v, X.gtid, X.gsize, 2, sgn, S.eps, S.tmax, A.rtol, X.stat, A.cbar, A.trow, nullptr, n);
+                scan_ratio_dual(v, X.vtid, X.gsize, 2, sgn, S.eps, S.tmax, A.rtol, XHDR(stat), A.cbar, A.trow, nullptr, n);
                 r = eng_allreduce(X, A, v, none, CombRatio2());
                 if (X.tid == 0) fin_ratio_dual(&S, r, 2, sgn, A.rtol, nullptr, A.tie_stop != 0);
                 __syncthreads();
@@ -1668,7 +1737,7 @@ __global__ void __launch_bounds__(ENG_NT, 1) k_engine_dual(EngArgs A)
             }
         }
         const int q = S.q;
-        const int kq = X.head[m + q];
+        const int kq = XHDR(head)[m + q];
         /* ---- tcol, first half, and the dense product y2 = T v_N of update_gamma ---- */
         if (pse && S.k > 0) {
             __shared__ double zd[ENG_DB];
@@ -1703,7 +1772,7 @@ __global__ void __launch_bounds__(ENG_NT, 1) k_engine_dual(EngArgs A)
                     !((piv1 > 0.0 && piv2 > 0.0) || (piv1 < 0.0 && piv2 < 0.0)))
                     S.status = ST_PIV12;
                 else {
-                    const double eta = (A.refsp[X.head[p]] ? 1.0 : 0.0);
+                    const double eta = (A.refsp[XHDR(head)[p]] ? 1.0 : 0.0);
                     S.delta_q = eta;
                     S.gamma_q = eta + (pse ? S.scal : 0.0);
                     S.teta = S.delta / piv1;
@@ -1721,71 +1790,64 @@ __global__ void __launch_bounds__(ENG_NT, 1) k_engine_dual(EngArgs A)
             const double teta = S.teta, new_dq = S.new_dq;
             const int kp = C.kp;
             const double pivot = C.tp;
-            const double xq = get_xN(X.stat, X.head, A.lb, A.ub, m, q);
+            const double xq = get_xN(XHDR(stat), XHDR(head), A.lb, A.ub, m, q);
             const bool drop = (A.type[kp] == GLP_FX && A.refsp[kp]);
             /* phase 1: is the basis dual feasible after this iteration (check_feas at the top of the reference's
                next iteration, lib/glpspx02.js:1681-1696)?  The count rides on the pricing key. */
             int ninf = 0;
-            if (S.phase != 1) {
-                for (int t = X.gtid; t < n; t += X.gsize) {
-                    if (t == q) A.cbar[q] = new_dq;
-                    else if (new_dq != 0.0) {
-                        const double tr = A.trow[t];
-                        if (tr != 0.0) A.cbar[t] -= tr * new_dq;
-                    }
-                }
-            } else {
-                for (int t = X.gtid; t < n; t += X.gsize) {
-                    double d;
-                    int kk;
-                    if (t == q) { d = new_dq; A.cbar[q] = d; kk = kp; }        /* xB[p] takes the place of xN[q] */
-                    else {
-                        d = A.cbar[t];
-                        if (new_dq != 0.0) {
-                            const double tr = A.trow[t];
-                            if (tr != 0.0) { d -= tr * new_dq; A.cbar[t] = d; }
-                        }
-                        kk = X.head[m + t];
-                    }
-                    const int ty = A.orig_type[kk];
-                    bool bad = false;
-                    if (d < -A.tol_dj) bad = (ty == GLP_LO || ty == GLP_FR);
-                    if (d > +A.tol_dj) bad = bad || (ty == GLP_UP || ty == GLP_FR);
-                    ninf += bad ? 1 : 0;
-                }
-            }
             Key pnone = {0.0, 0.0, 0.0, INT_MAX, 0};
             Key pv = pnone;
-            for (int t = X.gtid; t < m; t += X.gsize) {
-                double bi, g = A.gamma[t];
-                int k;
-                if (t == p) {
-                    k = kq;
-                    bi = xq + teta;
-                    A.bbar[p] = bi;
-                    if (pse) {
-                        g = 1.0;
-                        if (A.type[kq] != GLP_FR) {
-                            g = S.gamma_q / (pivot * pivot);
-                            if (g < DBL_EPSILON) g = DBL_EPSILON;
-                            if (drop) {
-                                const double tt = 1.0 / pivot;
-                                g -= tt * tt;
-                                if (g < DBL_EPSILON) g = DBL_EPSILON;
-                            }
-                        }
-                        A.gamma[p] = g;
+            /* One pass over the reduced costs (n) and the basic values / weights (m): every entry's loads are
+               issued before anything depends on them -- first (trow, cbar | gamma, head, bbar, tcol, u), then what
+               hangs on head (type, lb, ub, refsp) -- so that the phase costs two rounds of L2 latency instead of
+               one per nested condition.  Phase 1 adds the reference's check_feas on the updated reduced costs
+               (lib/glpspx02.js:1681-1696); the count rides on the pricing key. */
+            const bool ph1 = (S.phase == 1);
+            const int nm = max(n, m);
+            for (int t = X.vtid; t < nm; t += X.gsize) {
+                const bool inn = t < n, inm = t < m;
+                double tr = 0.0, dj = 0.0, g = 0.0, bi = 0.0, tc = 0.0, ut = 0.0;
+                int k = 0, kk = 0;
+                if (inn) { tr = A.trow[t]; dj = A.cbar[t]; if (ph1) kk = XHDR(head)[m + t]; }
+                if (inm) { g = A.gamma[t]; k = XHDR(head)[t]; bi = A.bbar[t]; tc = A.tcol[t]; ut = A.u[t]; }
+                if (inm && t == p) k = kq;
+                int tk = 0, rk = 0, ty = 0;
+                double lk = 0.0, uk = 0.0;
+                if (inm) { tk = A.type[k]; lk = A.lb[k]; uk = A.ub[k]; rk = A.refsp[k]; }
+                if (inn && ph1) ty = A.orig_type[t == q ? kp : kk];
+                if (inn) {
+                    if (t == q) { dj = new_dq; A.cbar[q] = dj; }
+                    else if (new_dq != 0.0 && tr != 0.0) { dj -= tr * new_dq; A.cbar[t] = dj; }
+                    if (ph1) {
+                        bool bad = false;
+                        if (dj < -A.tol_dj) bad = (ty == GLP_LO || ty == GLP_FR);
+                        if (dj > +A.tol_dj) bad = bad || (ty == GLP_UP || ty == GLP_FR);
+                        ninf += bad ? 1 : 0;
                     }
-                } else {
-                    k = X.head[t];
-                    bi = A.bbar[t];
-                    const double tc = A.tcol[t];
-                    if (tc != 0.0) {
+                }
+                if (inm) {
+                    if (t == p) {
+                        bi = xq + teta;
+                        A.bbar[p] = bi;
+                        if (pse) {
+                            g = 1.0;
+                            if (tk != GLP_FR) {
+                                g = S.gamma_q / (pivot * pivot);
+                                if (g < DBL_EPSILON) g = DBL_EPSILON;
+                                if (drop) {
+                                    const double tt = 1.0 / pivot;
+                                    g -= tt * tt;
+                                    if (g < DBL_EPSILON) g = DBL_EPSILON;
+                                }
+                            }
+                            A.gamma[p] = g;
+                        }
+                    } else if (tc != 0.0) {
                         if (teta != 0.0) { bi += tc * teta; A.bbar[t] = bi; }
-                        if (pse && A.type[k] != GLP_FR) {
+                        if (pse && tk != GLP_FR) {
                             const double tt = tc / pivot;
-                            const double t1 = g + tt * tt * S.gamma_q + 2.0 * tt * A.u[t];
-                            const double t2 = (A.refsp[k] ? 1.0 : 0.0) + S.delta_q * tt * tt;
+                            const double t1 = g + tt * tt * S.gamma_q + 2.0 * tt * ut;
+                            const double t2 = (rk ? 1.0 : 0.0) + S.delta_q * tt * tt;
                             g = (t1 >= t2 ? t1 : t2);
                             if (g < DBL_EPSILON) g = DBL_EPSILON;
                             if (drop) {
@@ -1795,8 +1857,8 @@ __global__ void __launch_bounds__(ENG_NT, 1) k_engine_dual(EngArgs A)
                             A.gamma[t] = g;
                         }
                     }
+                    price_dual(pv, t, tk, lk, uk, bi, g, A.tol_bnd);
                 }
-                price_dual(pv, t, A.type[k], A.lb[k], A.ub[k], bi, g, A.tol_bnd);
             }
             if (X.cta == 0) {
                 if (kq < m) { if (X.tid == 0) A.hz[kq] = 0.0; }
@@ -1807,6 +1869,7 @@ __global__ void __launch_bounds__(ENG_NT, 1) k_engine_dual(EngArgs A)
             if (defer) { eng_defer_apply(X, A, C, nd); nd++; }
             else if (S.k + (C.bnew >= 0) > 0) eng_update_T(X, A, C);
             pv.aux = ninf;
+            eng_mark(X, A, 11, 0.0);              /* CTA 0's own share of the update; PD_UPD = all-reduce + header hand-off */
             Key r = eng_allreduce(X, A, pv, pnone, CombArgMaxCnt());
             {
                 const bool found = (r.a > 0.0 && r.pos != INT_MAX);

@@ -228,12 +228,16 @@ static int create_device(glpb_prob *P)
         P->eng_dcap = dcap;
         P->eng_smem = (int)((size_t)dcap * 8 + fixed + (P->eng_hdr ? hdr : 0));
         if (!coop || P->sm_count > ENG_MAXG) { glpb_set_error("device lacks cooperative launch"); return GLPB_ENODEV; }
-        CK(cudaFuncSetAttribute(k_engine_primal, cudaFuncAttributeMaxDynamicSharedMemorySize, P->eng_smem));
-        CK(cudaFuncSetAttribute(k_engine_dual, cudaFuncAttributeMaxDynamicSharedMemorySize, P->eng_smem));
+        /* two instantiations of each engine: basis header in per-CTA shared memory (small LPs) or read straight
+           from global memory through the kernel parameters (no header pointer held in registers) */
+        CK(cudaFuncSetAttribute(k_engine_primal<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, P->eng_smem));
+        CK(cudaFuncSetAttribute(k_engine_dual<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, P->eng_smem));
+        CK(cudaFuncSetAttribute(k_engine_primal<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, P->eng_smem));
+        CK(cudaFuncSetAttribute(k_engine_dual<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, P->eng_smem));
         CK(cudaFuncSetAttribute(k_refactor, cudaFuncAttributeMaxDynamicSharedMemorySize, REF_SMEM_MAX));
         CK(cudaFuncSetAttribute(k_rho_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, RHO_SMEM_MAX));
         int occ = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_engine_dual, ENG_NT, P->eng_smem));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_engine_dual<true>, ENG_NT, P->eng_smem));
         if (occ < 1) { glpb_set_error("engine does not fit an SM"); return GLPB_ENODEV; }
         P->eng_ready = 1;
     }
@@ -879,6 +883,8 @@ struct Loop : Dev {
         A.tie_stop = list_order() ? 1 : 0;
         static const int env_pf = getenv("GLPB_PF") ? std::max(0, atoi(getenv("GLPB_PF"))) : 2;
         A.pf_dist = env_pf;
+        static const int env_pff = getenv("GLPB_PF_FIRST") ? std::max(0, atoi(getenv("GLPB_PF_FIRST"))) : 0;
+        A.pf_first = env_pff;
         A.prof_cyc = P->prof ? P->eng_cyc + (dual ? 12 : 0) : nullptr;
         A.prof_bytes = P->prof ? P->eng_bytes + (dual ? 12 : 0) : nullptr;
         const int G = engine_grid();
@@ -886,7 +892,9 @@ struct Loop : Dev {
         CK(cudaMemsetAsync(P->eng_cols, 0, (3 * (size_t)n + m) * sizeof(double), P->stream));
         void *args[] = {&A};
         prof_begin(P, dual ? "k_engine_dual" : "k_engine_primal");
-        cudaError_t e = cudaLaunchCooperativeKernel(dual ? (const void *)k_engine_dual : (const void *)k_engine_primal,
+        const void *kfn = P->eng_hdr ? (dual ? (const void *)k_engine_dual<true> : (const void *)k_engine_primal<true>)
+                                     : (dual ? (const void *)k_engine_dual<false> : (const void *)k_engine_primal<false>);
+        cudaError_t e = cudaLaunchCooperativeKernel(kfn,
                                                     dim3(G), dim3(ENG_NT), args, (size_t)P->eng_smem, P->stream);
         prof_end(P);
         if (e == cudaErrorCooperativeLaunchTooLarge) {
@@ -1811,7 +1819,7 @@ extern "C" const char *glpb_profile_report(glpb_prob *P)
                                      "PC_rho_gemvT", "PD_unused", "PE_trow_svec", "PF_update_T_chuzc", "PB1_tail", "PB2_allreduce", "PB3_btran_head",
                                      "D0_chuzr_first", "D1_rho", "D2_trow", "DR1_ratio1_gamma_rhs", "DR2_ratio2",
                                      "DX_ratio_local_gamma_rhs", "D3_gemvN_tcol_head", "D4_tcol_tail_utail",
-                                     "D5_update_T_chuzr", "D9", "D10", "D11"};
+                                     "D5_update_T_chuzr", "D9_flush", "D1a_rho_own_work", "D5a_update_own_work"};
         for (int half = 0; half < 2; half++) {
             const char *kn = half ? "k_engine_dual" : "k_engine_primal";
             auto itp = P->prof_acc.find(kn);
