@@ -81,6 +81,7 @@ struct EngArgs {
     int hdr_smem;             /* 1: keep per-CTA copies of the basis header in shared memory */
     int local_max;            /* ratio tests up to this length are replicated per CTA */
     int pf_dist;              /* dense T*v stream: L2 prefetch distance in column steps (0 = off) */
+    int use_async;            /* 1: dense T*v stream through cp.async into a shared-memory ring */
     int pf_first;             /* first of the 8 columns of a trip that is prefetched (experiments) */
     int tie_stop;             /* 1: an exact tie in a ratio test stops the engine (ST_TIE)  */
     int *rslot, *slot_pos, *cslot, *slot_row;
@@ -375,6 +376,62 @@ __device__ __forceinline__ int eng_compact(const EngCtxT<HL> &X, bool flag, int 
     return pos;
 }
 
+/* ---- the dense stream through cp.async (LDGSTS): the 16-byte pieces of the next ENG_AD columns of a lane travel
+   from global to ITS OWN slots of a shared-memory ring without passing through registers, so the bytes in
+   flight per lane are bounded by shared memory (ENG_AD x 16) instead of by the three 16-byte loads the register
+   allocation of the 1024-thread kernel leaves room for.  Every lane reads back only what it copied itself:
+   no barrier, only cp.async.wait_group. ---- */
+#ifndef ENG_AD
+#define ENG_AD 6
+#endif
+__device__ __forceinline__ void eng_cp_async16(void *smem_dst, const void *gsrc)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned int)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void eng_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void eng_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+/* one lane's share: columns e0, e0 + 32, ... < L of the two rows at Tb2; slot s of the lane at ring + s * sstride */
+__device__ __forceinline__ void eng_dense_stream_async(const double *Tb2, size_t ldt, int e0, int L, const double *val,
+                                                       double *ring, int sstride, double &ax, double &ay)
+{
+    const int cnt = (L - e0 + 31) >> 5;
+    const size_t step = 32 * ldt;
+    const double *src = Tb2 + (size_t)e0 * ldt;
+#pragma unroll
+    for (int s = 0; s < ENG_AD; s++) {
+        if (s < cnt) eng_cp_async16(ring + s * sstride, src + s * step);
+        eng_cp_async_commit();
+    }
+    const double *nxt = src + ENG_AD * step;
+    const double *v = val + e0;
+    double a0 = 0.0, b0 = 0.0, a1 = 0.0, b1 = 0.0;
+    int i = 0;
+    for (; i + ENG_AD <= cnt; i += ENG_AD) {
+#pragma unroll
+        for (int s = 0; s < ENG_AD; s++) {
+            eng_cp_async_wait<ENG_AD - 1>();
+            const double2 t = *(const double2 *)(ring + s * sstride);
+            const double vv = v[(i + s) * 32];
+            if (s & 1) { a1 += t.x * vv; b1 += t.y * vv; } else { a0 += t.x * vv; b0 += t.y * vv; }
+            if (i + s + ENG_AD < cnt) eng_cp_async16(ring + s * sstride, nxt + (size_t)(i + s) * step);
+            eng_cp_async_commit();
+        }
+    }
+#pragma unroll
+    for (int s = 0; s < ENG_AD; s++) {
+        if (i + s < cnt) {
+            eng_cp_async_wait<ENG_AD - 1>();
+            const double2 t = *(const double2 *)(ring + s * sstride);
+            const double vv = v[(i + s) * 32];
+            a0 += t.x * vv; b0 += t.y * vv;
+        }
+        eng_cp_async_commit();
+    }
+    eng_cp_async_wait<0>();
+    ax = a0 + a1; ay = b0 + b1;
+}
+
 /* y[b] (+)= sum_e T[b, idx[e]] * val[e] + sum_{j<nd} Fd_j[b] z[j], b < k, for the
    list (idx, val) of L entries (idx == NULL: idx[e] = e, the dense case).
    Every CTA owns one contiguous range of rows (a multiple of 4, i.e. whole 32-byte
@@ -399,7 +456,10 @@ __device__ void eng_gemv_rows(const EngCtxT<HL> &X, const EngArgs &A, int k, int
                thread.  Up to 32 rows left: half a warp per column, two columns per warp
                instruction; 33..64 rows: the whole chunk in ONE pass, a warp per column
                (each column of T is touched once, in one contiguous piece). */
-            const bool wide = rem > 32;
+#ifndef ENG_WIDE_MIN
+#define ENG_WIDE_MIN 32
+#endif
+            const bool wide = rem > ENG_WIDE_MIN;
             const int CH = wide ? min(rem, 64) : 32;             /* rows of this chunk */
             const int r2 = wide ? X.lane : (X.lane & 15), sub2 = wide ? 0 : (X.lane >> 4);
             const int cstep = wide ? 32 : 64, cfirst = wide ? X.warp : sub2 + 2 * X.warp;
@@ -409,6 +469,18 @@ __device__ void eng_gemv_rows(const EngCtxT<HL> &X, const EngArgs &A, int k, int
             const double *Tb2 = A.T + (in0 ? ba : q0);
             double ax0 = 0.0, ay0 = 0.0, ax1 = 0.0, ay1 = 0.0;
             int e = cfirst;
+            /* ring of the cp.async variant: behind the staged vector in the dynamic shared memory, one slot row of
+               nact 16-byte pieces per (warp, stage) */
+            const int nact = (lim - b0 + 1) >> 1;
+            const int kpad = (L + 1) & ~1;
+            const bool use_async = wide && A.use_async && val == X.sh_d &&
+                                   (size_t)(A.dcap - kpad) * 8 >= (size_t)32 * ENG_AD * nact * 16;
+            if (use_async) {
+                if (in0) {
+                    double *ring = X.sh_d + kpad + ((size_t)X.warp * ENG_AD * nact + r2) * 2;
+                    eng_dense_stream_async(Tb2, ldt, cfirst, L, val, ring, nact * 2, ax0, ay0);
+                }
+            } else
             if (in0) {
                 /* Under the 64-register cap of a 1024-thread CTA ptxas keeps only three of the eight loads of
                    a trip in flight (SASS: the destinations R16/R20/R24 are reused), which leaves the stream

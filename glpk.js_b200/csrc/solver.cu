@@ -885,6 +885,8 @@ struct Loop : Dev {
         A.pf_dist = env_pf;
         static const int env_pff = getenv("GLPB_PF_FIRST") ? std::max(0, atoi(getenv("GLPB_PF_FIRST"))) : 0;
         A.pf_first = env_pff;
+        static const int env_async = getenv("GLPB_ASYNC") ? atoi(getenv("GLPB_ASYNC")) : 0;
+        A.use_async = env_async;
         A.prof_cyc = P->prof ? P->eng_cyc + (dual ? 12 : 0) : nullptr;
         A.prof_bytes = P->prof ? P->eng_bytes + (dual ? 12 : 0) : nullptr;
         const int G = engine_grid();

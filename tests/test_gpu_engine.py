@@ -141,3 +141,38 @@ def test_pivot_sequence_equals_the_references(engine):
     w = [x for r in res for x in r["weights"]]
     assert len(w) >= 20 and all(x["same_head"] for x in w), [x for x in w if not x["same_head"]][:3]
     assert max(x["gamma_rel_err"] for x in w) <= 1e-9, sorted(w, key=lambda x: -x["gamma_rel_err"])[:3]
+
+
+def test_c3_full_size_pivot_sequence_equals_the_oracles():
+    """BASELINE.json configs[2] at FULL size (16384 x 32768): the first 5000 iterations take the oracle's (q, p) one for
+    one and leave the oracle's basis -- all 49152 statuses (the oracle needs 7 s for them, the device 0.4 s).  Measured
+    once beyond that (tools/c3_first_diff.py, tools/c3_prefix_check.py): identical through iteration 10705, basis
+    identical after 10000 iterations; at iteration 10706 dual pricing picks another row and the paths separate (76 % of
+    the basis still shared after 60000 iterations, same optimum, same 120552 iterations in total on the device)."""
+    import numpy as np
+    K = 5000
+    d = nat.generate("covering", m=16384, n=32768, kmin=8, kspan=17, seed=20240601)
+    Q = O.Problem.from_arrays(H.to_oracle(d))
+    seq, cur = [], {}
+
+    def hook(ev, csa):
+        if ev == O.EV_D_CHUZR:
+            cur["p"] = O.csa_scalars(csa)["p"]
+        elif ev == O.EV_D_CHUZC:
+            seq.append((O.csa_scalars(csa)["q"], cur["p"]))
+    Q.set_hook(hook)
+    Q.simplex(meth=O.GLP_DUAL, it_lim=K)
+    Q.set_hook(None)
+    ref = np.asarray(Q.solution()["stat"]).astype(int)
+    P = nat.Problem(d)
+    P.set_pivot_log(K + 8)
+    P.simplex(meth=nat.GLP_DUAL, it_lim=K)
+    got = [tuple(x) for x in P.pivot_log(K + 8)]
+    stat = np.asarray(P.solution()["stat"]).astype(int)
+    cnt = P.counters()
+    P.close()
+    assert len(seq) == K and len(got) == K
+    first = next((i for i, (a, b) in enumerate(zip(got, seq)) if a != b), None)
+    assert first is None, (first, got[first - 1:first + 2], seq[first - 1:first + 2])
+    assert np.array_equal(stat, ref)
+    assert cnt["launches"] < K // 10, "the iterations ran inside the persistent engine"
