@@ -133,10 +133,10 @@ def oracle_run_record(w):
         last = r["log"][-1]
         out = {"complete": not r.get("partial", True), "iterations": int(r.get("it_cnt", last["it"])),
                "seconds": round(float(r.get("seconds", last["seconds"])), 1), "cores": 1,
-               "where": "build container (not this box), one thread; tests/golden/make_c3_pins.py"}
+               "where": "build container, tests/golden/make_c3_pins.py"}
         out["iter_per_s"] = out["iterations"] / max(1e-9, out["seconds"])
         if not out["complete"]:
-            out["note"] = "still running when committed: iterations done so far, the rate keeps falling"
+            out["note"] = "still running when committed"
         return out
     except Exception:
         return None
@@ -177,7 +177,7 @@ class CpuSampler:
         if os.path.exists(path):
             z = np.load(path)
             self.mid_stat = z["stat"].astype(np.int32)
-            self.mid_from = "the oracle's own basis after %d iterations (committed fixture)" % int(z["it"])
+            self.mid_from = "the oracle's own basis after %d iterations (fixture)" % int(z["it"])
         elif w.get("cpu_mid"):
             P = O.Problem.from_arrays(self.od)
             P.simplex(meth=self.meth, it_lim=w["cpu_mid"])
@@ -217,7 +217,7 @@ class CpuSampler:
             dtm = iterating + setup * itm / 100.0
             self.windows["mid"] = {"iterations": int(itm), "seconds": round(dtm, 3), "seconds_iterating": round(iterating, 3),
                                    "seconds_factorise_bbar_cbar": round(setup, 3),
-                                   "charged": "iterating + set-up x iterations / 100 (one refactorisation per nfs_max = 100 updates)"}
+                                   "charged": "iterating + set-up x iterations / 100"}
             dt += dtm
             it += itm
         return it, dt
@@ -226,8 +226,8 @@ class CpuSampler:
         w = self.w
         s = "first %d iterations from the standard basis" % w["cpu_it_lim"]
         if self.mid_stat is not None:
-            s += " + %d iterations (plus the amortised share of one refactorisation per 100 updates) from %s" % (w["cpu_mid_lim"], self.mid_from)
-        return s + "; C++ port of the reference, 1 thread (no JS engine on the box)"
+            s += " + %d iterations (+ amortised share of one refactorisation per 100 updates) from %s" % (w["cpu_mid_lim"], self.mid_from)
+        return s + "; C++ port of the reference, 1 thread"
 
 
 def run_reference(args, w, rank):
@@ -337,10 +337,10 @@ def bnb_block(args, rank, local_rank, world, n_steps, n_warm):
            "node_lim_per_gpu": node_lim, "batch_per_gpu": args.bnb_batch or "16 x SM count", "host_threads_per_gpu": 1,
            "nodes_per_step": sum(nodes) / max(1, n_steps), "gpu_launches": int(launches) * world,
            "rounds_per_step": rounds / max(1, n_steps),
-           "workload": w["name"],
+           "workload": "knapsack MIP m=30 n=500 (BASELINE.json configs[4]), batched node LPs sharded over the ranks",
            "optimum_check": {"instance": "knapsack m=%d n=%d seed=%d, solved to completion on %d GPU(s)" % (
                MKP_CHECK["m"], MKP_CHECK["n"], MKP_CHECK["seed"], world), "optimum": rc["obj"], "expected": expected,
-               "expected_from": "HiGHS (scipy.optimize.milp) and the oracle, tests/golden/lp_pins.json",
+               "expected_from": "HiGHS + oracle, tests/golden/lp_pins.json",
                "ret": rc["ret"], "open_left": rc["open_left"], "nodes": rc["total_nodes"], "seconds": round(tc, 3),
                "solution_feasible_integral": x_ok, "migrated_nodes": rc["moved_out"]},
            "optimum_ok": bool(expected is not None and rc["obj"] is not None and rc["ret"] == 0 and rc["open_left"] == 0
@@ -359,7 +359,7 @@ def bnb_cpu_baseline(node_lim=1500):
     Q.intopt(node_lim=node_lim)
     dt = time.perf_counter() - t0
     return {"value": Q.mip()["nodes"] / dt, "unit": "nodes/s", "cores": 1, "kind": "port",
-            "sample": "%d nodes of the same search (node limit), C++ port of the reference, 1 thread" % Q.mip()["nodes"]}
+            "sample": "%d nodes of the same search, C++ port, 1 thread" % Q.mip()["nodes"]}
 
 
 def run_bnb_line(args, rank, local_rank, world):
@@ -454,7 +454,7 @@ def roofline_of(prof, eng_name, peak, peak_src, traffic):
     tp = phases[top_phase]
     ach = eng["bytes"] / (eng["ms"] * 1e-3) / 1e9
     roof = {"bound": "hbm", "kernel": eng_name, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-            "traffic": traffic.get("dram_bytes_per_iteration"), "traffic_source": traffic.get("source"),
+            "traffic": traffic.get("dram_bytes_per_iteration"), "traffic_source": "profiles/traffic.json (ncu --set full, per iteration)",
             "peak_source": peak_src, "launch_unit": "one simplex iteration of the persistent engine (all phases)",
             "bytes_per_launch": eng["bytes"] / eng["count"], "us_per_launch": 1000.0 * eng["ms"] / eng["count"],
             "share_of_device_time": eng["ms"] / tot_ms,
