@@ -198,18 +198,18 @@ __device__ __forceinline__ void eng_mark(EngCtxT<HL> &X, const EngArgs &A, int p
 /* Barrier that carries a reduction: the CTA partial travels with the arrival
    flag; thread i of every CTA picks up partial i as soon as flag i is up and the
    G partials are combined in index order (deterministic, same in every CTA). */
+/* The two halves of the all-reduce, so that work which does not depend on its result can run between them:
+   post = CTA partial into the slot + arrival flag (release: everything this CTA wrote so far is ordered before it),
+   collect = wait for all G flags (acquire), combine the G partials in index order.  No other barrier or
+   all-reduce may be started in between (the slots rotate on the shared sequence number). */
 template <class Comb, bool HL>
-__device__ Key eng_allreduce(EngCtxT<HL> &X, const EngArgs &A, Key v, const Key &none, Comb comb)
+__device__ void eng_allreduce_post(EngCtxT<HL> &X, const EngArgs &A, Key v, const Key &none, Comb comb, Key *wres)
 {
-    __shared__ Key wres[ENG_MAXG / 32];
     v = block_reduce(v, none, comb);      /* its __syncthreads also fence this CTA's phase writes */
     X.seq++;
     if (X.G == 1) {
         if (X.tid == 0) wres[0] = v;
-        __syncthreads();
-        Key r = wres[0];
-        __syncthreads();
-        return r;
+        return;
     }
     EngSlot *ring = A.slots + (X.seq & (ENG_RING - 1)) * ENG_MAXG;
     if (X.tid == 0) {
@@ -217,6 +217,17 @@ __device__ Key eng_allreduce(EngCtxT<HL> &X, const EngArgs &A, Key v, const Key 
         __stcg(&d->a, v.a); __stcg(&d->b, v.b); __stcg(&d->c, v.c); __stcg(&d->pos, v.pos); __stcg(&d->aux, v.aux);
         eng_st_release(&ring[X.cta].flag, X.seq);
     }
+}
+template <class Comb, bool HL>
+__device__ Key eng_allreduce_collect(EngCtxT<HL> &X, const EngArgs &A, const Key &none, Comb comb, Key *wres)
+{
+    if (X.G == 1) {
+        __syncthreads();
+        Key r = wres[0];
+        __syncthreads();
+        return r;
+    }
+    EngSlot *ring = A.slots + (X.seq & (ENG_RING - 1)) * ENG_MAXG;
     const int nw = (X.G + 31) >> 5;
     if (X.warp < nw) {
         Key r = none;
@@ -236,6 +247,13 @@ __device__ Key eng_allreduce(EngCtxT<HL> &X, const EngArgs &A, Key v, const Key 
     for (int w = 1; w < nw; w++) comb(r, wres[w]);
     __syncthreads();
     return r;
+}
+template <class Comb, bool HL>
+__device__ Key eng_allreduce(EngCtxT<HL> &X, const EngArgs &A, Key v, const Key &none, Comb comb)
+{
+    __shared__ Key wres[ENG_MAXG / 32];
+    eng_allreduce_post(X, A, v, none, comb, wres);
+    return eng_allreduce_collect(X, A, none, comb, wres);
 }
 
 /* lanes per item for the segmented sums below: as many as the grid offers for
@@ -437,11 +455,14 @@ __device__ __forceinline__ void eng_dense_stream_async(const double *Tb2, size_t
    Every CTA owns one contiguous range of rows (a multiple of 4, i.e. whole 32-byte
    sectors) and walks it in chunks of RB rows; its 32 warps split the list and
    the partial sums meet in shared memory in a fixed order.  Streams 8 L k bytes. */
-template <bool HL>
+template <bool HL, class Pre>
 __device__ void eng_gemv_rows(const EngCtxT<HL> &X, const EngArgs &A, int k, int L, const int *idx,
                               const double *val, double *y, double *ycol, bool accumulate,
-                              int nd, const double *z)
+                              int nd, const double *z, Pre pre)
 {
+    /* pre(): called ONCE by every thread of every CTA, after the first chunk has been streamed and before
+       anything reads z (or at the end, for a CTA without rows): the place where a pending all-reduce is collected */
+    bool pre_done = false;
     __shared__ double red[32][33];
     const int RPC = (((k + X.G - 1) / X.G) + 3) & ~3;          /* rows per CTA */
     const int q0 = min(k, X.cta * RPC), q1 = min(k, q0 + RPC);
@@ -522,6 +543,7 @@ __device__ void eng_gemv_rows(const EngCtxT<HL> &X, const EngArgs &A, int k, int
             double (*red2)[65] = (double (*)[65])X.sh_red2;      /* [32][65] */
             if (sub2 == 0) { red2[X.warp][2 * r2] = ax; red2[X.warp][2 * r2 + 1] = ay; }
             __syncthreads();
+            if (!pre_done) { pre(); pre_done = true; }
             if (X.tid < CH) {
                 double s = 0.0;
 #pragma unroll 8
@@ -572,6 +594,7 @@ __device__ void eng_gemv_rows(const EngCtxT<HL> &X, const EngArgs &A, int k, int
         for (int off = RB; off < 32; off <<= 1) acc += __shfl_xor_sync(FULLMASK, acc, off);
         if (sub == 0) red[X.warp][r] = acc;
         __syncthreads();
+        if (!pre_done) { pre(); pre_done = true; }
         if (X.tid < RB) {
             double s = 0.0;
 #pragma unroll 8
@@ -586,6 +609,7 @@ __device__ void eng_gemv_rows(const EngCtxT<HL> &X, const EngArgs &A, int k, int
         }
         __syncthreads();
     }
+    if (!pre_done) pre();
 }
 
 /* ---- TMA (bulk asynchronous copy) + mbarrier helpers ---- */
@@ -739,7 +763,7 @@ __device__ void eng_ftran_head_col(EngCtxT<HL> &X, const EngArgs &A, int k, int 
         __syncthreads();
         if (X.tid < nd) zs[X.tid] = -A.Rd[(size_t)X.tid * A.ldt + X.sh_i[0]];
         __syncthreads();
-        eng_gemv_rows(X, A, k, 1, X.sh_i, X.sh_d, y, ycol, false, nd, zs);
+        eng_gemv_rows(X, A, k, 1, X.sh_i, X.sh_d, y, ycol, false, nd, zs, [] {});
         return;
     }
     const int beg = __ldg(A.a_ptr + (kq - m)), end = __ldg(A.a_ptr + (kq - m) + 1);
@@ -769,7 +793,7 @@ __device__ void eng_ftran_head_col(EngCtxT<HL> &X, const EngArgs &A, int k, int 
             zs[X.tid] = zz;
         }
         __syncthreads();
-        eng_gemv_rows(X, A, k, L, X.sh_i, X.sh_d, y, ycol, !first, nd, zs);
+        eng_gemv_rows(X, A, k, L, X.sh_i, X.sh_d, y, ycol, !first, nd, zs, [] {});
         first = false;
     }
 }
@@ -1702,6 +1726,7 @@ __global__ void __launch_bounds__(ENG_NT, 1) k_engine_dual(EngArgs A)
     int pnext = P_NONE;
     double dnext = 0.0;
     int nd = 0;                   /* deferred rank-1 terms on top of T */
+    __shared__ Key wres2[ENG_MAXG / 32];
     for (int it = 0; it < A.max_iters && S.status == ST_OK; it++) {
         /* ---- pricing (chuzr): see the primal engine ---- */
         if (it == 0) {
@@ -1725,6 +1750,7 @@ __global__ void __launch_bounds__(ENG_NT, 1) k_engine_dual(EngArgs A)
         const int p = S.p;
         const bool pse = gamma_on(&S);
         const double sgn = (S.delta > 0.0 ? +1.0 : -1.0);
+        int pend = 0;                 /* 1: pass 2 of the ratio test posted, 2: barrier arrived -- not collected yet */
         /* ---- rho ---- */
         eng_mark(X, A, 10, 0.0);                  /* header hand-off of the previous iteration + loop top */
         eng_rho(X, A, S.k, p, nd);
@@ -1795,37 +1821,61 @@ __global__ void __launch_bounds__(ENG_NT, 1) k_engine_dual(EngArgs A)
                     __syncthreads();
                 }
             }
+            /* Pass 2 is only POSTED here (its partial and arrival flag go out); the result is collected after the
+               dense product below has streamed T: that product needs v, which is complete, but neither q nor z --
+               the all-reduce's round trip and the wait for the slowest CTA hide behind 8 k^2 bytes of HBM traffic. */
             if (!S.skip2) {
                 v = none;
                 scan_ratio_dual(v, X.vtid, X.gsize, 2, sgn, S.eps, S.tmax, A.rtol, XHDR(stat), A.cbar, A.trow, nullptr, n);
-                r = eng_allreduce(X, A, v, none, CombRatio2());
-                if (X.tid == 0) fin_ratio_dual(&S, r, 2, sgn, A.rtol, nullptr, A.tie_stop != 0);
-                __syncthreads();
+                eng_allreduce_post(X, A, v, none, CombRatio2(), wres2);
+                pend = 1;
                 eng_mark(X, A, PD_R2, 17.0 * n + (need_z ? 16.0 * nd * S.k : 0.0));
-                if (S.status != ST_OK) break;
             } else if (need_z) {
-                eng_bar(X, A);
+                eng_arrive(X, A);
+                pend = 2;
                 eng_mark(X, A, PD_R2, 16.0 * nd * S.k);
             }
         }
-        const int q = S.q;
-        const int kq = XHDR(head)[m + q];
-        /* ---- tcol, first half, and the dense product y2 = T v_N of update_gamma ---- */
+        /* second half of the exchange started above: afterwards q is known and every CTA's z_j is visible */
+        auto finish_ratio = [&]() {
+            if (pend == 1) {
+                const Key none2 = {DBL_MAX, 0.0, 0.0, INT_MAX, 0};
+                const Key r2 = eng_allreduce_collect(X, A, none2, CombRatio2(), wres2);
+                if (X.tid == 0) fin_ratio_dual(&S, r2, 2, sgn, A.rtol, nullptr, A.tie_stop != 0);
+                __syncthreads();
+            } else if (pend == 2)
+                eng_wait(X, A);
+            pend = 0;
+        };
+        /* ---- the dense product y2 = T v_N of update_gamma, then tcol, first half ---- */
         if (pse && S.k > 0) {
             __shared__ double zd[ENG_DB];
             const int k = S.k;
             const double *val = A.wk;
-            if (X.tid < nd) zd[X.tid] = __ldcg(A.zbuf + X.tid);
             const bool tma = A.use_tma && eng_gemv_tma_ok(X, A, k);
             if (!tma && k <= A.dcap) {
                 for (int e = X.tid; e < k; e += ENG_NT) X.sh_d[e] = A.wk[e];
                 val = X.sh_d;
             }
+            if (tma) {
+                finish_ratio();
+                if (X.tid < nd) zd[X.tid] = __ldcg(A.zbuf + X.tid);
+                __syncthreads();
+                eng_gemv_dense_tma(X, A, k, A.wk, A.yk2, A.ycol2, nd, zd);
+            } else {
+                __syncthreads();
+                eng_gemv_rows(X, A, k, k, nullptr, val, A.yk2, A.ycol2, false, nd, zd, [&]() {
+                    finish_ratio();
+                    if (X.tid < nd) zd[X.tid] = __ldcg(A.zbuf + X.tid);
+                    __syncthreads();
+                });
+            }
             __syncthreads();
-            if (tma) eng_gemv_dense_tma(X, A, k, A.wk, A.yk2, A.ycol2, nd, zd);
-            else eng_gemv_rows(X, A, k, k, nullptr, val, A.yk2, A.ycol2, false, nd, zd);
-            __syncthreads();
-        }
+        } else
+            finish_ratio();
+        if (S.status != ST_OK) break;
+        const int q = S.q;
+        const int kq = XHDR(head)[m + q];
         eng_ftran_head_col(X, A, S.k, kq, A.yk, A.ycol, nd);
         eng_bar(X, A);
         eng_mark(X, A, PD_TCOL1, (pse ? 8.0 * S.k * (double)S.k + 16.0 * S.k : 0.0) + 8.0 * S.k);
