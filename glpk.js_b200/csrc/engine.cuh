@@ -39,7 +39,9 @@
 #ifndef ENG_SU
 #define ENG_SU 8            /* columns per trip of the dense stream's load loop   */
 #endif
-#define ENG_DB 32            /* deferred basis changes before T is rewritten     */
+#ifndef ENG_DB
+#define ENG_DB 32            /* deferred basis changes before T is rewritten (a multiple of 32) */
+#endif
 
 /* one 128-byte line per (ring slot, CTA): the arrival flag and the partial
    result that travels with it.  A line of its own keeps the G pollers of a
@@ -1257,17 +1259,23 @@ __device__ void eng_flush(const EngCtxT<HL> &X, const EngArgs &A, int k, int nd)
                 acc[x][0] = (rok && col < k) ? __ldcg(tp[x]) : 0.0;
                 acc[x][1] = (rok && col + 1 < k) ? __ldcg(tp[x] + ldt) : 0.0;
             }
-            double af[8];
+            /* the deferred terms in batches of 32 (eight k-steps of the m8n8k4 tile product) */
 #pragma unroll
-            for (int kk = 0; kk < 8; kk++)
-                af[kk] = (4 * kk + t < nd && rok) ? __ldcg(A.Fd + (size_t)(4 * kk + t) * ldt + row) : 0.0;
+            for (int kb = 0; kb < ENG_DB / 4; kb += 8) {
+                if (kb < ksteps) {
+                    double af[8];
 #pragma unroll
-            for (int kk = 0; kk < 8; kk++) {
-                if (kk < ksteps) {
+                    for (int kk = 0; kk < 8; kk++)
+                        af[kk] = (4 * (kb + kk) + t < nd && rok) ? __ldcg(A.Fd + (size_t)(4 * (kb + kk) + t) * ldt + row) : 0.0;
 #pragma unroll
-                    for (int x = 0; x < 4; x++) {
-                        const double b = Rs[(4 * kk + t) * ENG_RS + (cq * 4 + x) * 8 + g];
-                        eng_dmma(acc[x][0], acc[x][1], af[kk], b);
+                    for (int kk = 0; kk < 8; kk++) {
+                        if (kb + kk < ksteps) {
+#pragma unroll
+                            for (int x = 0; x < 4; x++) {
+                                const double b = Rs[(4 * (kb + kk) + t) * ENG_RS + (cq * 4 + x) * 8 + g];
+                                eng_dmma(acc[x][0], acc[x][1], af[kk], b);
+                            }
+                        }
                     }
                 }
             }
