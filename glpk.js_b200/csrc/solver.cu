@@ -1821,7 +1821,7 @@ extern "C" const char *glpb_profile_report(glpb_prob *P)
                                      "PC_rho_gemvT", "PD_unused", "PE_trow_svec", "PF_update_T_chuzc", "PB1_tail", "PB2_allreduce", "PB3_btran_head",
                                      "D0_chuzr_first", "D1_rho", "D2_trow", "DR1_ratio1_gamma_rhs", "DR2_ratio2",
                                      "DX_ratio_local_gamma_rhs", "D3_gemvN_tcol_head", "D4_tcol_tail_utail",
-                                     "D5_update_T_chuzr", "D9_flush", "D1a_rho_own_work", "D5a_update_own_work"};
+                                     "D5_update_allreduce_header", "D9_flush", "D1a_header_handoff", "D5a_update_own_work"};
         for (int half = 0; half < 2; half++) {
             const char *kn = half ? "k_engine_dual" : "k_engine_primal";
             auto itp = P->prof_acc.find(kn);
