@@ -854,6 +854,9 @@ struct Loop : Dev {
         batch_begin(0, obj_ll, obj_ul);
         EngArgs A;
         A.ctrl = P->ctrl; A.m = m; A.n = n; A.ldt = P->ldt; A.max_iters = iters;
+        /* smcp.tm_lim is tested by the host between launches: with a time limit set, a launch is kept short
+           (64 iterations: ~10 ms at the C3 size) so that the overshoot stays bounded */
+        if (parm.tm_lim < INT_MAX) A.max_iters = std::min(iters, 64);
         A.dcap = P->eng_dcap;
         A.avg_col = (double)P->nnz / n; A.avg_row = (double)P->nnz / m;
         A.tol_bnd = parm.tol_bnd; A.tol_dj = parm.tol_dj; A.tol_piv = parm.tol_piv; A.rtol = rtol;

@@ -261,3 +261,23 @@ def test_facade_factorize_ftran_btran_in_unscaled_space():
         glpk.glp_set_row_bnds(sp, i, glpk.GLP_UP, 0.0, 4.0)
         glpk.glp_set_row_stat(sp, i, glpk.GLP_NU)
     assert glpk.glp_factorize(sp) in (glpk.GLP_ESING, glpk.GLP_ECOND) and not glpk.glp_bf_exists(sp)
+
+
+def test_time_limit_is_honoured_inside_long_engine_runs():
+    """smcp.tm_lim (lib/glpspx02.js:1801-1830): the host tests it between engine launches, which are kept short
+    when a limit is set -- the covering LP 8192 x 16384 needs seconds, a 150 ms limit must come back as GLP_ETMLIM
+    within a few launches of the limit and leave a basis the next call continues from"""
+    import time
+    d = nat.generate("covering", m=8192, n=16384, kmin=8, kspan=17, seed=20240601)
+    P = nat.Problem(d)
+    t0 = time.perf_counter()
+    rc = P.simplex(meth=nat.GLP_DUAL, tm_lim=150)
+    dt = time.perf_counter() - t0
+    it1 = P.solution()["it_cnt"]
+    assert rc == nat.GLP_ETMLIM, rc
+    assert 0.15 <= dt <= 0.60, dt
+    assert it1 > 100
+    rc = P.simplex(meth=nat.GLP_DUAL)
+    s = P.solution()
+    assert rc == 0 and s["status"] == O.GLP_OPT and s["it_cnt"] > it1
+    P.close()
