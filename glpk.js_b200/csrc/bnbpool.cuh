@@ -103,8 +103,27 @@ struct glpb_bnb {
         return 0;
     }
 #else
-    static int dalloc(void **p, size_t b) { return cudaMalloc(p, b ? b : 1) == cudaSuccess ? 0 : 1; }
-    static void dfree(void *p) { if (p) cudaFree(p); }
+    /* Stream-ordered allocation from the device's default pool, which is told to keep what is freed: the node slab
+       (17 KB per node, 4.5 GB at the default capacity) is then mapped once per process and handed back and forth
+       between successive searches instead of going through cudaMalloc / cudaFree each time (50-300 ms of
+       driver time per search, the run-to-run spread of the nodes/s figure). */
+    int dalloc(void **p, size_t b)
+    {
+        static int pool_ready[64] = {0};
+        const int dev = P->device;
+        if (dev >= 0 && dev < 64 && !pool_ready[dev]) {
+            cudaMemPool_t pool;
+            if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+                unsigned long long keep = ~0ull;
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            }
+            pool_ready[dev] = 1;
+        }
+        if (cudaMallocAsync(p, b ? b : 1, P->stream) == cudaSuccess) return 0;
+        cudaGetLastError();
+        return cudaMalloc(p, b ? b : 1) == cudaSuccess ? 0 : 1;
+    }
+    void dfree(void *p) { if (p && cudaFreeAsync(p, P->stream) != cudaSuccess) { cudaGetLastError(); cudaFree(p); } }
     int h2d(void *d, const void *s, size_t b) { return cudaMemcpyAsync(d, s, b, cudaMemcpyHostToDevice, P->stream) != cudaSuccess; }
     int d2h(void *d, const void *s, size_t b) { return cudaMemcpyAsync(d, s, b, cudaMemcpyDeviceToHost, P->stream) != cudaSuccess; }
     int d2d(void *d, const void *s, size_t b) { return cudaMemcpyAsync(d, s, b, cudaMemcpyDeviceToDevice, P->stream) != cudaSuccess; }
