@@ -290,7 +290,7 @@ def bnb_block(args, rank, local_rank, world, n_steps, n_warm):
         l0 = P.counters()["launches"]
         t0 = time.perf_counter()
         res = bnb.sharded_bnb_batched(bnb.BatchWorker(P), comm, minimize=False, batch=args.bnb_batch, node_lim=node_lim,
-                                      msg_lev=0)
+                                      max_ship=getattr(args, "bnb_ship", 64), msg_lev=0)
         barrier()
         dt = time.perf_counter() - t0
         if s >= n_warm:
@@ -311,7 +311,7 @@ def bnb_block(args, rank, local_rank, world, n_steps, n_warm):
     assert Pc.simplex(meth=nat.GLP_PRIMAL) == 0
     barrier()
     t0 = time.perf_counter()
-    rc = bnb.sharded_bnb_batched(bnb.BatchWorker(Pc), comm, minimize=False, batch=args.bnb_batch, msg_lev=0)
+    rc = bnb.sharded_bnb_batched(bnb.BatchWorker(Pc), comm, minimize=False, batch=args.bnb_batch, max_ship=getattr(args, "bnb_ship", 64), msg_lev=0)
     barrier()
     tc = time.perf_counter() - t0
     x_ok = None
@@ -484,6 +484,7 @@ def main():
     ap.add_argument("--no-bnb", action="store_true", help="skip the branch-and-bound block")
     ap.add_argument("--bnb-nodes", type=int, default=0, help="node LPs per GPU and step of the bnb block (0 = 150000)")
     ap.add_argument("--bnb-batch", type=int, default=0, help="open nodes per launch and GPU (0 = 16 x SM count)")
+    ap.add_argument("--bnb-ship", type=int, default=64, help="node records a donor rank ships per exchange")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
