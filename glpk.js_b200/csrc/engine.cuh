@@ -1462,7 +1462,8 @@ __global__ void __launch_bounds__(ENG_NT, 1) k_engine_primal(EngArgs A)
         }
         const double sgn = (S.d1 > 0.0 ? -1.0 : +1.0);
         const bool pse = gamma_on(&S);
-        bool cbar_q_pending = true;    /* reeval_cost result cbar[q] = d1 (lib/glpspx01.js:1915-1918) not stored yet */
+        bool cbar_q_pending = true;
+        bool pend_bar = false;        /* arrived at the barrier after the replicated ratio test, not waited yet */    /* reeval_cost result cbar[q] = d1 (lib/glpspx01.js:1915-1918) not stored yet */
         /* ---- Harris ratio test (chuzr); the first half of u = inv(B') v rides along ---- */
         if (local_ratio) {
             if (pse) eng_btran_head(X, A, S.k);
@@ -1517,9 +1518,11 @@ __global__ void __launch_bounds__(ENG_NT, 1) k_engine_primal(EngArgs A)
             }
             eng_mark(X, A, PP_R1, 45.0 * m * (S.skip2 ? 1.0 : 2.0));
             /* one barrier: w (first half of u) is complete, and nobody still scans bbar/tcol
-               when the update phase of a bound flip rewrites bbar */
-            eng_bar(X, A);
-            eng_mark(X, A, PP_B, 0.0);
+               when the update phase of a bound flip rewrites bbar.  Only the ARRIVAL happens here: rho, which
+               needs p (known to every CTA from its own copy of the ratio test) but not w, is computed before
+               the wait, so the barrier's round trip hides behind it. */
+            eng_arrive(X, A);
+            pend_bar = true;
         } else {
             eng_mark(X, A, PP_B, 0.0);
             Key none = {DBL_MAX, 0.0, 0.0, INT_MAX, 0};
@@ -1550,13 +1553,16 @@ __global__ void __launch_bounds__(ENG_NT, 1) k_engine_primal(EngArgs A)
             /* a slower CTA may still be reading cbar[q] in its own copy of the d1/d2 test:
                the value stored here makes that test come out the same way */
             if (cbar_q_pending && X.cta == 0 && X.tid == 0) A.cbar[q] = S.d1;
+            if (pend_bar) { eng_wait(X, A); pend_bar = false; }
             break;
         }
         const int p = S.p;
-        if (cbar_q_pending && X.cta == 0 && X.tid == 0) A.cbar[q] = S.d1;   /* all CTAs are past the d1/d2 test */
+        if (cbar_q_pending && X.cta == 0 && X.tid == 0) A.cbar[q] = S.d1;   /* see above: harmless for a CTA still at the d1/d2 test */
+        if (p < 0 && pend_bar) { eng_wait(X, A); pend_bar = false; eng_mark(X, A, PP_B, 0.0); }
         if (p >= 0) {
             /* ---- C: rho and the second half of u ---- */
             eng_rho(X, A, S.k, p, 0);
+            if (pend_bar) { eng_wait(X, A); pend_bar = false; eng_mark(X, A, PP_B, 0.0); }
             if (pse) {
                 const int k = S.k;
                 const int LP = max(32, eng_pick_lp(X, k, (double)k / 2));
