@@ -18,11 +18,14 @@ tests) sits on the device's two basis solves.  Of the functions the reference
 exports from glpapi01-09/12, glpcpx and glpscl only ``glp_bf_updated`` and the
 sensitivity analysis (``glp_analyze_bound/coef``) are not mirrored.
 
-What is NOT here on purpose ("out of scope" / "next"): the LP/MIP
-presolver's transformations (``glpnpp*.js``), MathProg, cut generators.
-``presolve: GLP_ON`` runs the reference's flow around an identity presolve:
-copy of the problem, ``glp_scale_prob``, ``glp_adv_basis``, solve, solution
-stored back the way ``npp_unload_sol`` does.
+``presolve: GLP_ON`` runs the reference's flow (lib/glpapi06.js:41-146,
+lib/glpapi09.js:116-256) with the LP / MIP presolver of the native library
+(``glpb_npp_*``, csrc/presolve.cpp: the transformations of lib/glpnpp01-05.js):
+reduced problem, ``glp_scale_prob``, ``glp_adv_basis``, solve on the device,
+recovery of the solution, stored back the way ``npp_unload_sol`` does.
+
+What is NOT here on purpose ("out of scope"): MathProg, cut
+generators, interior point.
 """
 import math
 
@@ -1922,23 +1925,40 @@ def _solve_lp(P, parm, device):
     return ret
 
 
-def _clone(P):
-    """What npp_load_prob + npp_build_prob leave when no transformation applies:
-    a fresh problem with the same rows, columns and coefficients, unit scale
-    factors and the default statuses of new rows/columns."""
+def _npp_load(P, sol):
+    """npp_create_wksp + npp_load_prob(npp, P, GLP_OFF, sol, GLP_OFF) (lib/glpnpp01.js:262-394): the
+    problem as it stands -- unscaled, every column in list order -- into a native presolver workspace
+    (csrc/presolve.cpp)."""
+    d, _, _ = _arrays(P)
+    return native.Presolver(d, sol)
+
+
+def _npp_build(P, npp):
+    """npp_build_prob (lib/glpnpp01.js:396-472): the reduced problem as a fresh problem object, built
+    through the same API calls in the same order, so rows, columns and both element lists end up in the
+    reference's state.  Names are not carried (the callers load with names = GLP_OFF)."""
+    r = npp.build()
     Q = glp_prob()
-    Q.name, Q.obj, Q.dir, Q.c0 = P.name, P.obj, P.dir, P.c0
-    Q.m, Q.n, Q.nnz = P.m, P.n, P.nnz
-    for i in range(1, P.m + 1):
-        r, q = P.row[i], _Row(i)
-        q.name, q.type, q.lb, q.ub, q.elems = r.name, r.type, r.lb, r.ub, list(r.elems)
-        Q.row.append(q)
-    for j in range(1, P.n + 1):
-        c, q = P.col[j], _Col(j)
-        q.name, q.kind, q.type, q.lb, q.ub, q.coef = c.name, c.kind, c.type, c.lb, c.ub, c.coef
-        q.elems = list(c.elems)
-        Q.col.append(q)
+    Q.dir = P.dir
+    Q.c0 = float(r["c0"])
+    m, n = r["m"], r["n"]
+    if m:
+        glp_add_rows(Q, m)
+    for i in range(1, m + 1):
+        glp_set_row_bnds(Q, i, int(r["type"][i - 1]), float(r["lb"][i - 1]), float(r["ub"][i - 1]))
+    if n:
+        glp_add_cols(Q, n)
+    ptr = r["A_ptr"]
+    for j in range(1, n + 1):
+        k = m + j - 1
+        glp_set_col_kind(Q, j, GLP_IV if int(r["kind"][j - 1]) == GLP_IV else GLP_CV)
+        glp_set_col_bnds(Q, j, int(r["type"][k]), float(r["lb"][k]), float(r["ub"][k]))
+        Q.col[j].coef = float(r["coef"][j - 1])
+        a, b = int(ptr[j - 1]), int(ptr[j])
+        glp_set_mat_col(Q, j, b - a, [0] + [int(i) + 1 for i in r["A_ind"][a:b]],
+                        [0.0] + [float(v) for v in r["A_val"][a:b]])
     Q.bfcp = None if P.bfcp is None else dict(P.bfcp)   # inherited (lib/glpapi06.js:103-105)
+    Q._npp_ref = (r["row_ref"], r["col_ref"])
     return Q
 
 
@@ -1959,26 +1979,34 @@ def _bound_value(x):
     return {GLP_NL: x.lb, GLP_NU: x.ub, GLP_NF: 0.0, GLP_NS: x.lb}[x.stat]
 
 
-def _unload_basic(P, lp):
-    """npp_unload_sol, basic solution (lib/glpnpp01.js:589-682) with identity
-    recovery: statuses and the free values come from the solved copy, the rest
-    is recomputed from the ORIGINAL coefficients."""
+def _postprocess_basic(npp, lp):
+    """npp_postprocess, basic solution (lib/glpnpp01.js:474-570)"""
+    r_stat = [lp.row[i].stat for i in range(1, lp.m + 1)]
+    r_dual = [lp.row[i].dual for i in range(1, lp.m + 1)]
+    c_stat = [lp.col[j].stat for j in range(1, lp.n + 1)]
+    c_prim = [lp.col[j].prim for j in range(1, lp.n + 1)]
+    return npp.postprocess(c_prim, r_stat, r_dual, c_stat)
+
+
+def _unload_basic(P, p_stat, d_stat, r_stat, r_dual, c_stat, c_value):
+    """npp_unload_sol, basic solution (lib/glpnpp01.js:589-682): statuses, row duals and column values
+    come from the recovery, the rest is recomputed from the ORIGINAL coefficients."""
     P.valid = 0
-    P.pbs_stat, P.dbs_stat = lp.pbs_stat, lp.dbs_stat
+    P.pbs_stat, P.dbs_stat = p_stat, d_stat
     P.obj_val = P.c0
     P.some = 0
     for i in range(1, P.m + 1):
-        row, src = P.row[i], lp.row[i]
-        row.stat = src.stat
-        row.dual = src.dual
+        row = P.row[i]
+        row.stat = int(r_stat[i - 1])
+        row.dual = float(r_dual[i - 1])
         if row.stat == GLP_BS:
             row.dual = 0.0
         else:
             row.prim = _bound_value(row)
     for j in range(1, P.n + 1):
-        col, src = P.col[j], lp.col[j]
-        col.stat = src.stat
-        col.prim = src.prim
+        col = P.col[j]
+        col.stat = int(c_stat[j - 1])
+        col.prim = float(c_value[j - 1])
         if col.stat == GLP_BS:
             col.dual = 0.0
         else:
@@ -2000,13 +2028,13 @@ def _unload_basic(P, lp):
             col.dual = temp
 
 
-def _unload_mip(P, mip):
+def _unload_mip(P, mip_stat, c_value):
     """npp_unload_sol, MIP solution (lib/glpnpp01.js:734-756)"""
-    P.mip_stat = mip.mip_stat
+    P.mip_stat = mip_stat
     P.mip_obj = P.c0
     for j in range(1, P.n + 1):
         col = P.col[j]
-        col.mipx = mip.col[j].mipx
+        col.mipx = float(c_value[j - 1])
         P.mip_obj += col.coef * col.mipx
     for i in range(1, P.m + 1):
         temp = 0.0
@@ -2022,33 +2050,51 @@ def _drop_device(P):
 
 
 def _preprocess_and_solve_lp(P, parm, device):
-    """lib/glpapi06.js:40-146 around an identity presolve (the transformations of
-    glpnpp*.js are not built): working copy, automatic scaling, triangular crash
-    basis, solve on the device, solution stored back as npp_unload_sol does."""
+    """lib/glpapi06.js:40-146: presolve in the native library (csrc/presolve.cpp), automatic scaling and
+    triangular crash basis of the REDUCED problem, solve on the device, recovery of the solution."""
     if parm.msg_lev >= GLP_MSG_ALL:
         xprintf("Preprocessing...")
-    lp = _clone(P)
-    if parm.msg_lev >= GLP_MSG_ALL:
-        xprintf(_size_line(lp))
+    npp = _npp_load(P, GLP_SOL)
     try:
-        _quiet(parm.msg_lev, glp_scale_prob, lp, GLP_SF_AUTO)
-        _quiet(parm.msg_lev, glp_adv_basis, lp, 0)
-        lp.it_cnt = P.it_cnt
-        ret = _solve_lp(lp, parm, device)
-        P.it_cnt = lp.it_cnt
+        ret = npp.simplex()
+        if ret != 0:
+            if parm.msg_lev >= GLP_MSG_ALL:
+                xprintf("PROBLEM HAS NO PRIMAL FEASIBLE SOLUTION" if ret == GLP_ENOPFS
+                        else "PROBLEM HAS NO DUAL FEASIBLE SOLUTION")
+            return ret
+        lp = _npp_build(P, npp)
+        if lp.m == 0 and lp.n == 0:
+            lp.pbs_stat = lp.dbs_stat = GLP_FEAS
+            lp.obj_val = lp.c0
+            if parm.msg_lev >= GLP_MSG_ON and parm.out_dly == 0:
+                xprintf("%d: obj = %s  infeas = 0.0" % (P.it_cnt, _num(lp.obj_val)))
+            if parm.msg_lev >= GLP_MSG_ALL:
+                xprintf("OPTIMAL SOLUTION FOUND BY LP PREPROCESSOR")
+        else:
+            if parm.msg_lev >= GLP_MSG_ALL:
+                xprintf(_size_line(lp))
+            try:
+                _quiet(parm.msg_lev, glp_scale_prob, lp, GLP_SF_AUTO)
+                _quiet(parm.msg_lev, glp_adv_basis, lp, 0)
+                lp.it_cnt = P.it_cnt
+                ret = _solve_lp(lp, parm, device)
+                P.it_cnt = lp.it_cnt
+            finally:
+                _drop_device(lp)
+            if not (ret == 0 and lp.pbs_stat == GLP_FEAS and lp.dbs_stat == GLP_FEAS):
+                if parm.msg_lev >= GLP_MSG_ERR:
+                    xprintf("glp_simplex: unable to recover undefined or non-optimal solution")
+                if ret == 0:
+                    if lp.pbs_stat == GLP_NOFEAS:
+                        ret = GLP_ENOPFS
+                    elif lp.dbs_stat == GLP_NOFEAS:
+                        ret = GLP_ENODFS
+                return ret
+        r_stat, r_dual, c_stat, c_value = _postprocess_basic(npp, lp)
+        _unload_basic(P, lp.pbs_stat, lp.dbs_stat, r_stat, r_dual, c_stat, c_value)
+        return 0
     finally:
-        _drop_device(lp)
-    if not (ret == 0 and lp.pbs_stat == GLP_FEAS and lp.dbs_stat == GLP_FEAS):
-        if parm.msg_lev >= GLP_MSG_ERR:
-            xprintf("glp_simplex: unable to recover undefined or non-optimal solution")
-        if ret == 0:
-            if lp.pbs_stat == GLP_NOFEAS:
-                ret = GLP_ENOPFS
-            elif lp.dbs_stat == GLP_NOFEAS:
-                ret = GLP_ENODFS
-        return ret
-    _unload_basic(P, lp)
-    return 0
+        npp.close()
 
 
 def glp_simplex(P, parm=None, device=0):
@@ -2174,48 +2220,81 @@ def _int_stats_line(P):
 
 
 def _preprocess_and_solve_mip(P, parm, device):
-    """lib/glpapi09.js:116-256 around an identity presolve (see
-    _preprocess_and_solve_lp): copy, scaling GM|EQ|2N|SKIP, crash basis, LP
-    relaxation, branch-and-bound on the device, MIP solution stored back."""
+    """lib/glpapi09.js:116-256: MIP presolve in the native library (csrc/presolve.cpp), scaling
+    GM|EQ|2N|SKIP and crash basis of the reduced problem, LP relaxation and branch-and-bound on the
+    device, recovery of the MIP solution."""
     if parm.msg_lev >= GLP_MSG_ALL:
         xprintf("Preprocessing...")
-    mip = _clone(P)
-    if parm.msg_lev >= GLP_MSG_ALL:
-        xprintf(_size_line(mip))
-        xprintf(_int_stats_line(mip))
+    npp = _npp_load(P, GLP_MIP)
     try:
-        _quiet(parm.msg_lev, glp_scale_prob, mip, GLP_SF_GM | GLP_SF_EQ | GLP_SF_2N | GLP_SF_SKIP)
-        _quiet(parm.msg_lev, glp_adv_basis, mip, 0)
-        if parm.msg_lev >= GLP_MSG_ALL:
-            xprintf("Solving LP relaxation...")
-        smcp = SMCP()
-        smcp.msg_lev = parm.msg_lev
-        mip.it_cnt = P.it_cnt
-        ret = glp_simplex(mip, smcp, device=device)
-        P.it_cnt = mip.it_cnt
+        ret = npp.integer(parm.binarize == GLP_ON)
+        if parm.msg_lev >= GLP_MSG_ALL:      # what npp_integer / npp_binarize_prob print (glpnpp04.js:92-97, glpnpp05.js:475-514)
+            k = npp.counts()
+            if k["bin_vars"] > 0:
+                xprintf("%d integer variable(s) were replaced by %d binary ones" % (k["bin_vars"], k["bin_bins"]))
+            if k["bin_rows"] > 0:
+                xprintf("%d row(s) were added due to binarization" % k["bin_rows"])
+            if k["bin_fails"] > 0:
+                xprintf("Binarization failed for %d integer variable(s)" % k["bin_fails"])
+            if k["packing"] > 0:
+                xprintf("%d hidden packing inequaliti(es) were detected" % k["packing"])
+            if k["covering"] > 0:
+                xprintf("%d hidden covering inequaliti(es) were detected" % k["covering"])
+            if k["reduced"] > 0:
+                xprintf("%d constraint coefficient(s) were reduced" % k["reduced"])
         if ret != 0:
-            if parm.msg_lev >= GLP_MSG_ERR:
-                xprintf("glp_intopt: cannot solve LP relaxation")
-            return GLP_EFAIL
-        ret = glp_get_status(mip)
-        if ret == GLP_OPT:
-            ret = 0
-        elif ret == GLP_NOFEAS:
-            ret = GLP_ENOPFS
-        elif ret == GLP_UNBND:
-            ret = GLP_ENODFS
-        if ret != 0:
+            if parm.msg_lev >= GLP_MSG_ALL:
+                xprintf("PROBLEM HAS NO PRIMAL FEASIBLE SOLUTION" if ret == GLP_ENOPFS
+                        else "LP RELAXATION HAS NO DUAL FEASIBLE SOLUTION")
             return ret
-        mip.it_cnt = P.it_cnt
-        ret = _solve_mip(mip, parm, device)
-        P.it_cnt = mip.it_cnt
-    finally:
-        _drop_device(mip)
-    if mip.mip_stat not in (GLP_OPT, GLP_FEAS):
-        P.mip_stat = mip.mip_stat
+        mip = _npp_build(P, npp)
+        if mip.m == 0 and mip.n == 0:
+            mip.mip_stat = GLP_OPT
+            mip.mip_obj = mip.c0
+            if parm.msg_lev >= GLP_MSG_ALL:
+                xprintf("Objective value = %s" % _num(mip.mip_obj))
+                xprintf("INTEGER OPTIMAL SOLUTION FOUND BY MIP PREPROCESSOR")
+            ret = 0
+        else:
+            if parm.msg_lev >= GLP_MSG_ALL:
+                xprintf(_size_line(mip))
+                xprintf(_int_stats_line(mip))
+            try:
+                _quiet(parm.msg_lev, glp_scale_prob, mip, GLP_SF_GM | GLP_SF_EQ | GLP_SF_2N | GLP_SF_SKIP)
+                _quiet(parm.msg_lev, glp_adv_basis, mip, 0)
+                if parm.msg_lev >= GLP_MSG_ALL:
+                    xprintf("Solving LP relaxation...")
+                smcp = SMCP()
+                smcp.msg_lev = parm.msg_lev
+                mip.it_cnt = P.it_cnt
+                ret = glp_simplex(mip, smcp, device=device)
+                P.it_cnt = mip.it_cnt
+                if ret != 0:
+                    if parm.msg_lev >= GLP_MSG_ERR:
+                        xprintf("glp_intopt: cannot solve LP relaxation")
+                    return GLP_EFAIL
+                ret = glp_get_status(mip)
+                if ret == GLP_OPT:
+                    ret = 0
+                elif ret == GLP_NOFEAS:
+                    ret = GLP_ENOPFS
+                elif ret == GLP_UNBND:
+                    ret = GLP_ENODFS
+                if ret != 0:
+                    return ret
+                mip.it_cnt = P.it_cnt
+                ret = _solve_mip(mip, parm, device)
+                P.it_cnt = mip.it_cnt
+            finally:
+                _drop_device(mip)
+            if mip.mip_stat not in (GLP_OPT, GLP_FEAS):
+                P.mip_stat = mip.mip_stat
+                return ret
+        _, _, _, c_value = npp.postprocess([mip.col[j].mipx for j in range(1, mip.n + 1)])
+        _unload_mip(P, mip.mip_stat, c_value)
         return ret
-    _unload_mip(P, mip)
-    return ret
+    finally:
+        npp.close()
 
 
 def _check_iocp(parm):

@@ -28,6 +28,7 @@ GLP_BR_FFV, GLP_BR_LFV, GLP_BR_MFV, GLP_BR_DTH, GLP_BR_PCH = 1, 2, 3, 4, 5
 GLP_BT_DFS, GLP_BT_BFS, GLP_BT_BLB, GLP_BT_BPH = 1, 2, 3, 4
 GLP_PP_NONE, GLP_PP_ROOT, GLP_PP_ALL = 0, 1, 2
 GLP_ON, GLP_OFF = 1, 0
+GLP_SOL, GLP_IPT, GLP_MIP = 1, 2, 3
 GLP_SF_GM, GLP_SF_EQ, GLP_SF_2N, GLP_SF_SKIP, GLP_SF_AUTO = 0x01, 0x10, 0x20, 0x40, 0x80
 (GLP_EBADB, GLP_ESING, GLP_ECOND, GLP_EBOUND, GLP_EFAIL, GLP_EOBJLL, GLP_EOBJUL, GLP_EITLIM,
  GLP_ETMLIM, GLP_ENOPFS, GLP_ENODFS, GLP_EROOT, GLP_ESTOP, GLP_EMIPGAP) = range(1, 15)
@@ -76,6 +77,8 @@ SYMBOLS = [
     "glpb_scale_prob", "glpb_adv_basis", "glpb_read_lp", "glpb_free_names",
     "glpb_set_pivot_log", "glpb_get_pivot_log", "glpb_debug_get", "glpb_bnb_begin", "glpb_bnb_round", "glpb_bnb_open_count", "glpb_bnb_get_incumbent", "glpb_bnb_set_cutoff", "glpb_bnb_clear",
     "glpb_bnb_record_bytes", "glpb_bnb_export_nodes", "glpb_bnb_import_nodes", "glpb_bnb_stats", "glpb_bnb_end",
+    "glpb_npp_create", "glpb_npp_destroy", "glpb_npp_load_prob", "glpb_npp_simplex", "glpb_npp_integer",
+    "glpb_npp_get_counts", "glpb_npp_get_size", "glpb_npp_build_prob", "glpb_npp_postprocess",
 ]
 
 _lib = None
@@ -164,6 +167,17 @@ def load():
     L.glpb_bnb_import_nodes.argtypes = [vp, vp, ci]
     L.glpb_bnb_stats.argtypes = [vp, vp, ci]
     L.glpb_bnb_end.argtypes = [vp, ci]
+    L.glpb_npp_create.argtypes = []
+    L.glpb_npp_create.restype = vp
+    L.glpb_npp_destroy.argtypes = [vp]
+    L.glpb_npp_destroy.restype = None
+    L.glpb_npp_load_prob.argtypes = [vp, ci, ci, ci, cd] + [vp] * 8 + [ci]
+    L.glpb_npp_simplex.argtypes = [vp]
+    L.glpb_npp_integer.argtypes = [vp, ci]
+    L.glpb_npp_get_counts.argtypes = [vp, vp, ci]
+    L.glpb_npp_get_size.argtypes = [vp, vp, vp, vp]
+    L.glpb_npp_build_prob.argtypes = [vp] * 12
+    L.glpb_npp_postprocess.argtypes = [vp] * 9
     _lib = L
     return L
 
@@ -274,6 +288,97 @@ def adv_basis(m, n, A_ptr, A_ind, R_ptr, R_ind, type_, lb, ub):
     if rc != 0:
         raise ValueError("glpb_adv_basis: invalid arguments (rc=%d)" % rc)
     return stat, size.value
+
+
+class Presolver:
+    """One presolver workspace (glpb_npp_*, csrc/presolve.cpp): host only.  `d` as for Problem -- type/lb/ub
+    [m+n], coef, kind, dir, c0 and the matrix by columns -- but unscaled and with every column's elements in
+    the reference's list order."""
+
+    KINDS = ("free_row", "fixed_col", "make_equality", "make_fixed", "empty_col", "eq_singlet", "ineq_singlet",
+             "implied_slack", "implied_free", "forcing_row", "inactive_bound", "lbnd_col", "binarize")
+
+    def __init__(self, d, sol):
+        L = load()
+        self.L, self.sol = L, int(sol)
+        self.m, self.n = int(d["m"]), int(d["n"])
+        self.h = C.c_void_p(L.glpb_npp_create())
+        if not self.h:
+            raise MemoryError("glpb_npp_create")
+        a = [_i32(d["type"]), _f64(d["lb"]), _f64(d["ub"]), _f64(d["coef"]), _i32(d.get("kind")),
+             _i32(d["A_ptr"]), _i32(d["A_ind"]), _f64(d["A_val"])]
+        rc = L.glpb_npp_load_prob(self.h, self.m, self.n, int(d["dir"]), float(d["c0"]), *[_p(x) for x in a],
+                                  self.sol)
+        if rc != 0:
+            self.close()
+            raise ValueError("glpb_npp_load_prob: invalid arguments (rc=%d)" % rc)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.glpb_npp_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def simplex(self):
+        """npp_simplex: 0 / GLP_ENOPFS / GLP_ENODFS"""
+        rc = self.L.glpb_npp_simplex(self.h)
+        if rc < 0:
+            raise ValueError("glpb_npp_simplex (rc=%d)" % rc)
+        return rc
+
+    def integer(self, binarize=False):
+        """npp_integer: 0 / GLP_ENOPFS / GLP_ENODFS"""
+        rc = self.L.glpb_npp_integer(self.h, 1 if binarize else 0)
+        if rc < 0:
+            raise ValueError("glpb_npp_integer (rc=%d)" % rc)
+        return rc
+
+    def counts(self):
+        out = np.zeros(21, np.int32)
+        self.L.glpb_npp_get_counts(self.h, _p(out), 21)
+        return dict(zip(("packing", "covering", "reduced", "bin_vars", "bin_bins", "bin_rows", "bin_fails",
+                         "stack") + self.KINDS, (int(x) for x in out)))
+
+    def build(self):
+        """npp_build_prob: the reduced problem as a dict in the layout of Problem (+ row_ref / col_ref)."""
+        m, n, nz = C.c_int(0), C.c_int(0), C.c_int(0)
+        self.L.glpb_npp_get_size(self.h, C.byref(m), C.byref(n), C.byref(nz))
+        m, n, nz = m.value, n.value, nz.value
+        c0 = C.c_double(0.0)
+        type_, lb, ub = np.zeros(m + n, np.int32), np.zeros(m + n), np.zeros(m + n)
+        coef, kind = np.zeros(n), np.ones(n, np.int32)
+        A_ptr, A_ind, A_val = np.zeros(n + 1, np.int32), np.zeros(nz, np.int32), np.zeros(nz)
+        row_ref, col_ref = np.zeros(m, np.int32), np.zeros(n, np.int32)
+        rc = self.L.glpb_npp_build_prob(self.h, C.byref(c0), _p(type_), _p(lb), _p(ub), _p(coef), _p(kind),
+                                        _p(A_ptr), _p(A_ind), _p(A_val), _p(row_ref), _p(col_ref))
+        if rc != 0:
+            raise ValueError("glpb_npp_build_prob (rc=%d)" % rc)
+        self.rm, self.rn = m, n
+        return dict(m=m, n=n, c0=c0.value, type=type_, lb=lb, ub=ub, coef=coef, kind=kind, A_ptr=A_ptr,
+                    A_ind=A_ind, A_val=A_val, row_ref=row_ref, col_ref=col_ref)
+
+    def postprocess(self, c_value, r_stat=None, r_dual=None, c_stat=None):
+        """npp_postprocess: (r_stat, r_dual, c_stat, c_value) of the ORIGINAL problem (MIP: the first three
+        are None)."""
+        basic = self.sol == 1
+        cv = _f64(c_value)
+        o_cv = np.zeros(self.n)
+        if basic:
+            rs, rd, cs = _i32(r_stat), _f64(r_dual), _i32(c_stat)
+            o_rs, o_rd, o_cs = np.zeros(self.m, np.int32), np.zeros(self.m), np.zeros(self.n, np.int32)
+            rc = self.L.glpb_npp_postprocess(self.h, _p(rs), _p(rd), _p(cs), _p(cv), _p(o_rs), _p(o_rd),
+                                             _p(o_cs), _p(o_cv))
+        else:
+            o_rs = o_rd = o_cs = None
+            rc = self.L.glpb_npp_postprocess(self.h, None, None, None, _p(cv), None, None, None, _p(o_cv))
+        if rc != 0:
+            raise RuntimeError("glpb_npp_postprocess: solution cannot be recovered (rc=%d)" % rc)
+        return o_rs, o_rd, o_cs, o_cv
 
 
 class Problem:

@@ -292,6 +292,69 @@ int glpb_adv_basis(int m, int n, const int *A_ptr, const int *A_ind, const int *
 int glpb_read_lp(const char *text, long len, glpb_problem_data *out, char **names, long *names_len);
 void glpb_free_names(char *names);
 
+/* ---- LP / MIP presolver (csrc/presolve.cpp) --------------
+ * Host only, no device involved.  One workspace per `presolve: GLP_ON` solve,
+ * used in the order of lib/glpapi06.js:41-146 (LP) / lib/glpapi09.js:116-256
+ * (MIP):
+ *
+ *   glpb_npp_create                      npp_create_wksp   lib/glpnpp01.js:2-22
+ *   glpb_npp_load_prob(.., sol)          npp_load_prob(npp, P, GLP_OFF, sol, GLP_OFF)   :262-394
+ *   glpb_npp_simplex | glpb_npp_integer  npp_simplex | npp_integer   lib/glpnpp05.js:430-521
+ *   glpb_npp_get_size, glpb_npp_build_prob   npp_build_prob          lib/glpnpp01.js:396-472
+ *        ... scale, crash basis, glpb_create / glpb_simplex / glpb_intopt on the REDUCED problem ...
+ *   glpb_npp_postprocess                 npp_postprocess             lib/glpnpp01.js:474-570
+ *   glpb_npp_destroy
+ *
+ * load_prob: type/lb/ub [m+n] (rows first), coef/kind [n] and the matrix by
+ * columns as for glpb_create, but UNSCALED and with the elements of every column
+ * in the reference's LIST order (the order glp_get_mat_col returns): the order
+ * of the reduced problem's rows, columns and elements follows from it.  sol =
+ * GLP_SOL (1) or GLP_MIP (3); kind is read for GLP_MIP only.
+ *
+ * simplex / integer return 0, GLP_ENOPFS (0x0A) or GLP_ENODFS (0x0B) like the
+ * reference; `binarize` = iocp.binarize.  get_counts (optional): what
+ * npp_integer prints -- [0] hidden packing, [1] hidden covering inequalities,
+ * [2] reduced coefficients, [3..6] binarization (variables replaced, binaries
+ * created, rows added, failures), [7] entries on the recovery stack, [8..20] of
+ * those per transformation (free row, fixed column, make equality, make fixed,
+ * empty column, equality singleton, inequality singleton, implied slack, implied
+ * free, forcing row, inactive bound, shifted lower bound, binarized column).
+ *
+ * build_prob emits the reduced problem (sizes from get_size) in the layout
+ * glpb_create takes: c0 and coef in the ORIGINAL objective sense, bounds with
+ * -/+DBL_MAX for absent ones plus the GLP_* type npp_build_prob derives, the
+ * elements of every column in the order the reference hands them to
+ * glp_set_mat_col (a binding that mirrors the reference's list state prepends
+ * them one by one), row_ref/col_ref (optional) = reference numbers of the
+ * reduced rows / columns in the workspace.  The workspace keeps only the
+ * recovery stack afterwards.
+ *
+ * postprocess takes the solution of the reduced problem -- basic: r_stat,
+ * r_dual [m'], c_stat, c_value (= prim) [n']; MIP: c_value (= mipx) only, the
+ * other inputs and outputs may be NULL -- runs the recovery stack and returns
+ * what npp_unload_sol then copies into the original problem (lib/glpnpp01.js:
+ * 596-660): row statuses and duals [orig m] (duals already in the original
+ * objective sense), column statuses and values [orig n].  Primal values of
+ * non-basic variables, row activities and reduced costs are recomputed by the
+ * binding from ITS coefficients exactly as npp_unload_sol does.  Returns 0,
+ * GLPB_EINVAL, or GLPB_ESTATE where the reference's xassert(tse.func() == 0)
+ * would throw. */
+typedef struct glpb_npp glpb_npp;
+glpb_npp *glpb_npp_create(void);
+void glpb_npp_destroy(glpb_npp *npp);                /* idempotent on NULL */
+int glpb_npp_load_prob(glpb_npp *npp, int m, int n, int dir, double c0, const int *type,
+                       const double *lb, const double *ub, const double *coef, const int *kind,
+                       const int *A_ptr, const int *A_ind, const double *A_val, int sol);
+int glpb_npp_simplex(glpb_npp *npp);
+int glpb_npp_integer(glpb_npp *npp, int binarize);
+int glpb_npp_get_counts(glpb_npp *npp, int *out, int count);
+int glpb_npp_get_size(glpb_npp *npp, int *m, int *n, int *nnz);
+int glpb_npp_build_prob(glpb_npp *npp, double *c0, int *type, double *lb, double *ub, double *coef,
+                        int *kind, int *A_ptr, int *A_ind, double *A_val, int *row_ref, int *col_ref);
+int glpb_npp_postprocess(glpb_npp *npp, const int *r_stat, const double *r_dual, const int *c_stat,
+                         const double *c_value, int *out_r_stat, double *out_r_dual,
+                         int *out_c_stat, double *out_c_value);
+
 #ifdef __cplusplus
 }
 #endif

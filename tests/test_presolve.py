@@ -1,0 +1,147 @@
+"""LP / MIP presolver (glpb_npp_*, csrc/presolve.cpp) against the REFERENCE'S OWN presolver.
+
+tests/golden/ref_npp.json was produced by oracle/jsref/make_npp_golden.py: the unmodified
+lib/glpnpp01-05.js run on the reference's fixtures and on 64 generated problems.  Everything here is
+host code (no device): bit-exact comparison of
+  * the return code (0 / GLP_ENOPFS / GLP_ENODFS) and the depth of the recovery stack,
+  * the reduced problem npp_build_prob leaves -- row order, column order, bounds, costs, the constant
+    term and the element order inside every column (it decides scaling, crash basis and pivots),
+  * npp_postprocess: fed the solution the reference found for the reduced problem, the recovered
+    statuses / multipliers / values must be the reference's,
+  * npp_unload_sol through the facade: the solution stored into the original problem object.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import glpk_js_b200 as G
+from glpk_js_b200 import glpk as F, native
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+with open(os.path.join(HERE, "golden", "ref_npp.json")) as f:
+    CASES = {k: v for k, v in json.load(f).items() if not k.startswith("_")}
+
+
+def facade_problem(d):
+    """the problem object in the reference's list state: columns exactly in the recorded list order"""
+    P = F.glp_create_prob()
+    F.glp_set_obj_dir(P, d["dir"])
+    P.c0 = d["c0"]
+    if d["m"]:
+        F.glp_add_rows(P, d["m"])
+    if d["n"]:
+        F.glp_add_cols(P, d["n"])
+    for i in range(d["m"]):
+        r = P.row[i + 1]
+        r.type, r.lb, r.ub = d["r_type"][i], d["r_lb"][i], d["r_ub"][i]
+        r.stat = F.GLP_BS
+    for j in range(d["n"]):
+        c = P.col[j + 1]
+        c.type, c.lb, c.ub, c.coef, c.kind = d["c_type"][j], d["c_lb"][j], d["c_ub"][j], d["c_coef"][j], d["c_kind"][j]
+        for e in range(d["A_ptr"][j], d["A_ptr"][j + 1]):
+            c.elems.append((d["A_ind"][e] + 1, d["A_val"][e]))
+    # row lists as glp_sort_matrix leaves them (ascending columns, lib/glpapi01.js:620-649): the presolver
+    # never reads them, the recomputation of row activities in npp_unload_sol does
+    for j in range(1, d["n"] + 1):
+        for (i, v) in P.col[j].elems:
+            P.row[i].elems.append((j, v))
+    P.nnz = len(d["A_val"])
+    return P
+
+
+def same_problem(Q, red):
+    assert (Q.m, Q.n) == (red["m"], red["n"])
+    assert Q.c0 == red["c0"] and Q.dir == red["dir"]
+    for i in range(Q.m):
+        r = Q.row[i + 1]
+        assert (r.type, r.lb, r.ub) == (red["r_type"][i], red["r_lb"][i], red["r_ub"][i]), ("row", i + 1)
+    ptr, ind, val = F._csc(Q)
+    assert list(ptr) == red["A_ptr"]
+    assert list(ind) == red["A_ind"]
+    assert list(val) == red["A_val"]
+    for j in range(Q.n):
+        c = Q.col[j + 1]
+        assert (c.type, c.lb, c.ub, c.coef, c.kind) == (
+            red["c_type"][j], red["c_lb"][j], red["c_ub"][j], red["c_coef"][j], red["c_kind"][j]), ("col", j + 1)
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_presolver_matches_reference(name):
+    case = CASES[name]
+    P = facade_problem(case["problem"])
+    npp = F._npp_load(P, case["sol"])
+    try:
+        ret = npp.simplex() if case["sol"] == F.GLP_SOL else npp.integer(bool(case["binarize"]))
+        assert ret == case["ret"]
+        assert npp.counts()["stack"] == case["n_tse"]
+        if ret != 0:
+            return
+        Q = F._npp_build(P, npp)
+        same_problem(Q, case["reduced"])
+        assert list(Q._npp_ref[0]) == case["reduced"]["row_ref"]
+        assert list(Q._npp_ref[1]) == case["reduced"]["col_ref"]
+        if "post" not in case:
+            return
+        gin, post, un = case["in"], case["post"], case["unloaded"]
+        sgn = 1.0 if case["problem"]["dir"] == F.GLP_MIN else -1.0
+        if case["sol"] == F.GLP_SOL:
+            r_stat, r_dual, c_stat, c_value = npp.postprocess(gin["c_value"], gin["r_stat"], gin["r_dual"],
+                                                              gin["c_stat"])
+            assert list(r_stat) == post["r_stat"]
+            assert list(c_stat) == post["c_stat"]
+            assert list(c_value) == post["c_value"]
+            assert list(r_dual) == [sgn * v for v in post["r_pi"]]
+            F._unload_basic(P, un["prim_stat"], un["dual_stat"], r_stat, r_dual, c_stat, c_value)
+            assert P.obj_val == un["obj"]
+            assert [P.row[i].stat for i in range(1, P.m + 1)] == un["row_stat"]
+            assert [P.col[j].stat for j in range(1, P.n + 1)] == un["col_stat"]
+            assert [P.row[i].prim for i in range(1, P.m + 1)] == un["row_prim"]
+            assert [P.row[i].dual for i in range(1, P.m + 1)] == un["row_dual"]
+            assert [P.col[j].prim for j in range(1, P.n + 1)] == un["col_prim"]
+            assert [P.col[j].dual for j in range(1, P.n + 1)] == un["col_dual"]
+        else:
+            _, _, _, c_value = npp.postprocess(gin["c_value"])
+            assert list(c_value) == post["c_value"]
+            F._unload_mip(P, un["mip_stat"], c_value)
+            assert P.mip_obj == un["mip_obj"]
+            assert [P.col[j].mipx for j in range(1, P.n + 1)] == un["col_val"]
+            assert [P.row[i].mipx for i in range(1, P.m + 1)] == un["row_val"]
+    finally:
+        npp.close()
+
+
+def test_golden_covers_the_transformations():
+    """the generated cases are only worth something if they reach the presolver's branches"""
+    rets = [c["ret"] for c in CASES.values()]
+    assert rets.count(0) >= 45 and rets.count(F.GLP_ENOPFS) >= 5
+    assert sum(1 for c in CASES.values() if c["ret"] == 0 and c["reduced"]["m"] == 0) >= 2      # solved by the presolver
+    assert sum(1 for c in CASES.values() if c["ret"] == 0 and c["reduced"]["m"] >= 4) >= 20
+    grown = [c for c in CASES.values() if c["ret"] == 0 and c["sol"] == F.GLP_MIP and
+             (c["reduced"]["n"] > c["problem"]["n"] or max(c["reduced"]["row_ref"] + [0]) > c["problem"]["m"])]
+    assert len(grown) >= 3          # binarization / row copies added rows or columns
+
+
+def test_workspace_argument_checks():
+    L = native.load()
+    assert L.glpb_npp_simplex(None) == native.GLPB_EINVAL
+    assert L.glpb_npp_postprocess(None, *([None] * 8)) == native.GLPB_EINVAL
+    L.glpb_npp_destroy(None)
+    d = dict(m=1, n=1, dir=1, c0=0.0, type=[F.GLP_UP, F.GLP_LO], lb=[0.0, 0.0], ub=[4.0, 0.0], coef=[-1.0],
+             kind=[1], A_ptr=[0, 1], A_ind=[0], A_val=[2.0])
+    with pytest.raises(ValueError):
+        native.Presolver(dict(d, A_ind=[3]), F.GLP_SOL)         # row index out of range
+    with pytest.raises(ValueError):
+        native.Presolver(dict(d, type=[9, 2]), F.GLP_SOL)       # invalid type
+    npp = native.Presolver(d, F.GLP_SOL)
+    assert L.glpb_npp_integer(npp.h, 0) == native.GLPB_EINVAL   # loaded for a basic solution
+    assert L.glpb_npp_postprocess(npp.h, *([None] * 8)) == native.GLPB_EINVAL   # not built yet
+    assert npp.simplex() == 0
+    red = npp.build()
+    # max x s.t. 2x <= 4, x >= 0: the singleton row becomes a column bound, the column is then empty and fixed
+    assert (red["m"], red["n"]) == (0, 0) and red["c0"] == -2.0
+    r_stat, r_dual, c_stat, c_value = npp.postprocess([], [], [], [])
+    assert list(c_value) == [2.0] and list(c_stat) == [F.GLP_BS] and list(r_stat) == [F.GLP_NU]
+    assert list(r_dual) == [-0.5]
+    npp.close()
