@@ -121,6 +121,15 @@ def test_golden_covers_the_transformations():
     grown = [c for c in CASES.values() if c["ret"] == 0 and c["sol"] == F.GLP_MIP and
              (c["reduced"]["n"] > c["problem"]["n"] or max(c["reduced"]["row_ref"] + [0]) > c["problem"]["m"])]
     assert len(grown) >= 3          # binarization / row copies added rows or columns
+    total = {}
+    for case in CASES.values():
+        npp = F._npp_load(facade_problem(case["problem"]), case["sol"])
+        npp.simplex() if case["sol"] == F.GLP_SOL else npp.integer(bool(case["binarize"]))
+        for k, v in npp.counts().items():
+            total[k] = total.get(k, 0) + v
+        npp.close()
+    for kind in native.Presolver.KINDS + ("packing", "covering", "reduced", "bin_vars", "bin_rows"):
+        assert total[kind] > 0, kind    # every transformation on the path is reached by some case
 
 
 def test_workspace_argument_checks():
