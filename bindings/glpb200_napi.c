@@ -260,6 +260,146 @@ static napi_value ReadLp(napi_env env, napi_callback_info info)
     return r;
 }
 
+/* ---- presolver workspace (glpb_npp_*): the handle remembers the sizes every later array is checked against ---- */
+typedef struct { glpb_npp *npp; int om, on, sol, rm, rn, rnz, loaded, built; } shim_npp;
+static void finalize_npp(napi_env env, void *data, void *hint) { shim_npp *h = (shim_npp *)data; (void)env; (void)hint; glpb_npp_destroy(h->npp); free(h); }
+
+static shim_npp *npp_handle(napi_env env, napi_value v)
+{
+    void *p = NULL;
+    if (napi_get_value_external(env, v, &p) != napi_ok || !p) { napi_throw_type_error(env, NULL, "glpb200: not a presolver workspace"); return NULL; }
+    return (shim_npp *)p;
+}
+
+/* nppCreate() -> external workspace (npp_create_wksp, lib/glpnpp01.js:2-22); freed by the finalizer */
+static napi_value NppCreate(napi_env env, napi_callback_info info)
+{
+    napi_value r; (void)info;
+    shim_npp *h = (shim_npp *)calloc(1, sizeof *h);
+    if (!h || !(h->npp = glpb_npp_create())) { free(h); napi_throw_error(env, NULL, "glpb200.nppCreate: out of memory"); return NULL; }
+    if (napi_create_external(env, h, finalize_npp, NULL, &r) != napi_ok) { glpb_npp_destroy(h->npp); free(h); napi_throw_error(env, NULL, "napi_create_external"); return NULL; }
+    return r;
+}
+
+/* nppLoadProb(npp, m, n, dir, c0, Int32 type, F64 lb, F64 ub, F64 coef, Int32 kind|null, Int32 A_ptr, Int32 A_ind, F64 A_val, sol)
+   (npp_load_prob(npp, P, GLP_OFF, sol, GLP_OFF), lib/glpnpp01.js:262-394; columns in list order, unscaled) */
+static napi_value NppLoadProb(napi_env env, napi_callback_info info)
+{
+    size_t argc = 14; napi_value a[14];
+    NAPI_OK(napi_get_cb_info(env, info, &argc, a, NULL, NULL));
+    if (argc < 14) { napi_throw_type_error(env, NULL, "glpb200.nppLoadProb: 14 arguments expected"); return NULL; }
+    shim_npp *h = npp_handle(env, a[0]); if (!h) return NULL;
+    int32_t m, n, dir, sol; double c0;
+    NAPI_OK(napi_get_value_int32(env, a[1], &m));
+    NAPI_OK(napi_get_value_int32(env, a[2], &n));
+    NAPI_OK(napi_get_value_int32(env, a[3], &dir));
+    NAPI_OK(napi_get_value_double(env, a[4], &c0));
+    NAPI_OK(napi_get_value_int32(env, a[13], &sol));
+    if (m < 0 || n < 0 || h->loaded) { napi_throw_range_error(env, NULL, "glpb200.nppLoadProb: bad sizes or workspace already loaded"); return NULL; }
+    const size_t mn = (size_t)m + (size_t)n;
+    int *type = I32(a[5], mn, "type"); if (!type && mn) return NULL;
+    double *lb = F64(a[6], mn, "lb"); if (!lb && mn) return NULL;
+    double *ub = F64(a[7], mn, "ub"); if (!ub && mn) return NULL;
+    double *coef = F64(a[8], (size_t)n, "coef"); if (!coef && n) return NULL;
+    int *kind = NULL;
+    if (!is_nullish(env, a[9])) { kind = I32(a[9], (size_t)n, "kind"); if (!kind && n) return NULL; }
+    int *ptr = I32(a[10], (size_t)n + 1, "A_ptr"); if (!ptr) return NULL;
+    if (ptr[n] < 0) { napi_throw_range_error(env, NULL, "glpb200.nppLoadProb: A_ptr[n] < 0"); return NULL; }
+    int *ind = I32(a[11], (size_t)ptr[n], "A_ind"); if (!ind && ptr[n]) return NULL;
+    double *val = F64(a[12], (size_t)ptr[n], "A_val"); if (!val && ptr[n]) return NULL;
+    int rc = glpb_npp_load_prob(h->npp, m, n, dir, c0, type, lb, ub, coef, kind, ptr, ind, val, sol);
+    if (rc != 0) { napi_throw_range_error(env, NULL, "glpb200.nppLoadProb: invalid problem data"); return NULL; }
+    h->om = m; h->on = n; h->sol = sol; h->loaded = 1;
+    return ret_int(env, 0);
+}
+
+/* nppSimplex(npp) / nppInteger(npp, binarize) -> 0 | GLP_ENOPFS | GLP_ENODFS (lib/glpnpp05.js:430-521) */
+static napi_value NppSimplex(napi_env env, napi_callback_info info)
+{
+    size_t argc = 1; napi_value a[1];
+    NAPI_OK(napi_get_cb_info(env, info, &argc, a, NULL, NULL));
+    shim_npp *h = argc >= 1 ? npp_handle(env, a[0]) : NULL; if (!h) return NULL;
+    int rc = glpb_npp_simplex(h->npp);
+    if (rc < 0) { napi_throw_error(env, NULL, "glpb200.nppSimplex: workspace not loaded for a basic solution"); return NULL; }
+    return ret_int(env, rc);
+}
+
+static napi_value NppInteger(napi_env env, napi_callback_info info)
+{
+    size_t argc = 2; napi_value a[2]; int32_t binarize = 0;
+    NAPI_OK(napi_get_cb_info(env, info, &argc, a, NULL, NULL));
+    shim_npp *h = argc >= 1 ? npp_handle(env, a[0]) : NULL; if (!h) return NULL;
+    if (argc >= 2 && !is_nullish(env, a[1])) NAPI_OK(napi_get_value_int32(env, a[1], &binarize));
+    int rc = glpb_npp_integer(h->npp, binarize);
+    if (rc < 0) { napi_throw_error(env, NULL, "glpb200.nppInteger: workspace not loaded for a MIP solution"); return NULL; }
+    return ret_int(env, rc);
+}
+
+/* nppBuildProb(npp) -> { m, n, c0, type, lb, ub, coef, kind, ptr, ind, val, rowRef, colRef } (npp_build_prob,
+   lib/glpnpp01.js:396-472): the reduced problem; the arrays are allocated here with the sizes the library reports */
+static napi_value NppBuildProb(napi_env env, napi_callback_info info)
+{
+    size_t argc = 1; napi_value a[1], r, v, ab; void *p;
+    NAPI_OK(napi_get_cb_info(env, info, &argc, a, NULL, NULL));
+    shim_npp *h = argc >= 1 ? npp_handle(env, a[0]) : NULL; if (!h) return NULL;
+    if (!h->loaded || h->built) { napi_throw_error(env, NULL, "glpb200.nppBuildProb: workspace not loaded or already built"); return NULL; }
+    int m = 0, n = 0, nz = 0; double c0 = 0.0;
+    if (glpb_npp_get_size(h->npp, &m, &n, &nz) != 0) { napi_throw_error(env, NULL, "glpb_npp_get_size"); return NULL; }
+    NAPI_OK(napi_create_object(env, &r));
+    void *buf[10]; const size_t cnt[10] = { (size_t)m + n, (size_t)m + n, (size_t)m + n, (size_t)n, (size_t)n, (size_t)n + 1, (size_t)nz, (size_t)nz, (size_t)m, (size_t)n };
+    static const char *key[10] = { "type", "lb", "ub", "coef", "kind", "ptr", "ind", "val", "rowRef", "colRef" };
+    static const int is_f64[10] = { 0, 1, 1, 1, 0, 0, 0, 1, 0, 0 };
+    for (int k = 0; k < 10; k++) {
+        NAPI_OK(napi_create_arraybuffer(env, cnt[k] * (is_f64[k] ? 8 : 4), &p, &ab));
+        NAPI_OK(napi_create_typedarray(env, is_f64[k] ? napi_float64_array : napi_int32_array, cnt[k], ab, 0, &v));
+        NAPI_OK(napi_set_named_property(env, r, key[k], v));
+        buf[k] = p;
+    }
+    int rc = glpb_npp_build_prob(h->npp, &c0, (int *)buf[0], (double *)buf[1], (double *)buf[2], (double *)buf[3], (int *)buf[4],
+                                 (int *)buf[5], (int *)buf[6], (double *)buf[7], (int *)buf[8], (int *)buf[9]);
+    if (rc != 0) { napi_throw_error(env, NULL, "glpb_npp_build_prob"); return NULL; }
+    h->rm = m; h->rn = n; h->rnz = nz; h->built = 1;
+    napi_create_int32(env, m, &v); napi_set_named_property(env, r, "m", v);
+    napi_create_int32(env, n, &v); napi_set_named_property(env, r, "n", v);
+    napi_create_double(env, c0, &v); napi_set_named_property(env, r, "c0", v);
+    return r;
+}
+
+/* nppPostprocess(npp, Int32 r_stat|null, F64 r_dual|null, Int32 c_stat|null, F64 c_value) ->
+   { rowStat, rowDual, colStat, colValue } of the ORIGINAL problem (npp_postprocess, lib/glpnpp01.js:474-570);
+   inputs sized by the REDUCED problem, outputs by the original one, both known from the handle */
+static napi_value NppPostprocess(napi_env env, napi_callback_info info)
+{
+    size_t argc = 5; napi_value a[5], r, v, ab; void *p;
+    NAPI_OK(napi_get_cb_info(env, info, &argc, a, NULL, NULL));
+    if (argc < 5) { napi_throw_type_error(env, NULL, "glpb200.nppPostprocess: 5 arguments expected"); return NULL; }
+    shim_npp *h = npp_handle(env, a[0]); if (!h) return NULL;
+    if (!h->built) { napi_throw_error(env, NULL, "glpb200.nppPostprocess: reduced problem not built"); return NULL; }
+    const int basic = h->sol == 1;   /* GLP_SOL */
+    int *rs = NULL, *cs = NULL; double *rd = NULL;
+    if (basic) {
+        rs = I32(a[1], (size_t)h->rm, "r_stat"); if (!rs && h->rm) return NULL;
+        rd = F64(a[2], (size_t)h->rm, "r_dual"); if (!rd && h->rm) return NULL;
+        cs = I32(a[3], (size_t)h->rn, "c_stat"); if (!cs && h->rn) return NULL;
+    }
+    double *cv = F64(a[4], (size_t)h->rn, "c_value"); if (!cv && h->rn) return NULL;
+    NAPI_OK(napi_create_object(env, &r));
+    void *out[4] = { NULL, NULL, NULL, NULL };
+    const size_t cnt[4] = { (size_t)h->om, (size_t)h->om, (size_t)h->on, (size_t)h->on };
+    static const char *key[4] = { "rowStat", "rowDual", "colStat", "colValue" };
+    static const int is_f64[4] = { 0, 1, 0, 1 };
+    for (int k = 0; k < 4; k++) {
+        if (!basic && k < 3) continue;
+        NAPI_OK(napi_create_arraybuffer(env, cnt[k] * (is_f64[k] ? 8 : 4), &p, &ab));
+        NAPI_OK(napi_create_typedarray(env, is_f64[k] ? napi_float64_array : napi_int32_array, cnt[k], ab, 0, &v));
+        NAPI_OK(napi_set_named_property(env, r, key[k], v));
+        out[k] = p;
+    }
+    int rc = glpb_npp_postprocess(h->npp, rs, rd, cs, cv, (int *)out[0], (double *)out[1], (int *)out[2], (double *)out[3]);
+    if (rc != 0) { napi_throw_error(env, NULL, "glpb200.nppPostprocess: solution cannot be recovered"); return NULL; }   /* the reference's xassert */
+    return r;
+}
+
 static napi_value Init(napi_env env, napi_value exports)
 {
     napi_property_descriptor d[] = {
@@ -269,6 +409,9 @@ static napi_value Init(napi_env env, napi_value exports)
         { "getMip", 0, GetMip, 0, 0, 0, napi_default, 0 },
         { "scaleProb", 0, ScaleProb, 0, 0, 0, napi_default, 0 }, { "advBasis", 0, AdvBasis, 0, 0, 0, napi_default, 0 },
         { "readLp", 0, ReadLp, 0, 0, 0, napi_default, 0 },
+        { "nppCreate", 0, NppCreate, 0, 0, 0, napi_default, 0 }, { "nppLoadProb", 0, NppLoadProb, 0, 0, 0, napi_default, 0 },
+        { "nppSimplex", 0, NppSimplex, 0, 0, 0, napi_default, 0 }, { "nppInteger", 0, NppInteger, 0, 0, 0, napi_default, 0 },
+        { "nppBuildProb", 0, NppBuildProb, 0, 0, 0, napi_default, 0 }, { "nppPostprocess", 0, NppPostprocess, 0, 0, 0, napi_default, 0 },
     };
     napi_define_properties(env, exports, sizeof d / sizeof d[0], d);
     return exports;

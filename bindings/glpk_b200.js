@@ -67,7 +67,66 @@ function rowsOf(P, m) {
     return { ptr, ind: Int32Array.from(ind) };
 }
 
-exports.install = function (glp) {
+/* preprocess_and_solve_lp (lib/glpapi06.js:41-146) with the native presolver (addon.npp*, csrc/presolve.cpp)
+   in place of npp_load_prob / npp_simplex / npp_build_prob / npp_postprocess; npp_unload_sol
+   (lib/glpnpp01.js:589-682) stays here because it writes the caller's own glp_prob */
+function presolveLp(glp, P, parm) {
+    const d = marshal(glp, P), npp = addon.nppCreate();     // marshal: unscaled problem -> rii/sjj unused here
+    addon.nppLoadProb(npp, d.m, d.n, P.dir, P.c0, d.type, d.lb, d.ub, d.coef, d.kind, d.ptr, d.ind, d.val, glp.GLP_SOL);
+    let ret = addon.nppSimplex(npp);
+    if (ret !== 0) return ret;
+    const r = addon.nppBuildProb(npp), lp = glp.glp_create_prob();
+    glp.glp_set_obj_dir(lp, P.dir); glp.glp_set_obj_coef(lp, 0, r.c0);
+    if (r.m) glp.glp_add_rows(lp, r.m);
+    for (let i = 1; i <= r.m; i++) glp.glp_set_row_bnds(lp, i, r.type[i - 1], r.lb[i - 1], r.ub[i - 1]);
+    if (r.n) glp.glp_add_cols(lp, r.n);
+    for (let j = 1; j <= r.n; j++) {
+        const k = r.m + j - 1, a = r.ptr[j - 1], len = r.ptr[j] - a;
+        glp.glp_set_col_bnds(lp, j, r.type[k], r.lb[k], r.ub[k]); glp.glp_set_obj_coef(lp, j, r.coef[j - 1]);
+        const ind = new Int32Array(1 + len), val = new Float64Array(1 + len);
+        for (let t = 0; t < len; t++) { ind[1 + t] = r.ind[a + t] + 1; val[1 + t] = r.val[a + t]; }
+        glp.glp_set_mat_col(lp, j, len, ind, val);            // prepends: the reference's list state
+    }
+    if (r.m === 0 && r.n === 0) { lp.pbs_stat = lp.dbs_stat = glp.GLP_FEAS; lp.obj_val = lp.c0; }
+    else {
+        glp.glp_scale_prob(lp, glp.GLP_SF_AUTO); glp.glp_adv_basis(lp, 0);
+        lp.it_cnt = P.it_cnt;
+        const inner = Object.assign(new glp.SMCP(), parm, { presolve: glp.GLP_OFF });
+        ret = glp.glp_simplex(lp, inner);                     // the device solve of the REDUCED problem
+        P.it_cnt = lp.it_cnt;
+        if (!(ret === 0 && lp.pbs_stat === glp.GLP_FEAS && lp.dbs_stat === glp.GLP_FEAS)) {
+            if (ret === 0) ret = lp.pbs_stat === glp.GLP_NOFEAS ? glp.GLP_ENOPFS : glp.GLP_ENODFS;
+            return ret;
+        }
+    }
+    const s = addon.nppPostprocess(npp,
+        Int32Array.from({ length: r.m }, (_, i) => lp.row[i + 1].stat), Float64Array.from({ length: r.m }, (_, i) => lp.row[i + 1].dual),
+        Int32Array.from({ length: r.n }, (_, j) => lp.col[j + 1].stat), Float64Array.from({ length: r.n }, (_, j) => lp.col[j + 1].prim));
+    /* npp_unload_sol, basic solution */
+    const bound = (x) => (x.stat === glp.GLP_NU ? x.ub : x.stat === glp.GLP_NF ? 0.0 : x.lb);
+    P.valid = 0; P.pbs_stat = lp.pbs_stat; P.dbs_stat = lp.dbs_stat; P.obj_val = P.c0; P.some = 0;
+    for (let i = 1; i <= d.m; i++) {
+        const row = P.row[i]; row.stat = s.rowStat[i - 1]; row.dual = s.rowDual[i - 1];
+        if (row.stat === glp.GLP_BS) row.dual = 0.0; else row.prim = bound(row);
+    }
+    for (let j = 1; j <= d.n; j++) {
+        const col = P.col[j]; col.stat = s.colStat[j - 1]; col.prim = s.colValue[j - 1];
+        if (col.stat === glp.GLP_BS) col.dual = 0.0; else col.prim = bound(col);
+        P.obj_val += col.coef * col.prim;
+    }
+    for (let i = 1; i <= d.m; i++) {
+        const row = P.row[i];
+        if (row.stat === glp.GLP_BS) { let t = 0.0; for (let a = row.ptr; a != null; a = a.r_next) t += a.val * a.col.prim; row.prim = t; }
+    }
+    for (let j = 1; j <= d.n; j++) {
+        const col = P.col[j];
+        if (col.stat !== glp.GLP_BS) { let t = col.coef; for (let a = col.ptr; a != null; a = a.c_next) t -= a.val * a.row.dual; col.dual = t; }
+    }
+    return 0;
+}
+
+exports.install = function (glp, opts) {
+    opts = opts || {};
     const simplex0 = glp.glp_simplex, intopt0 = glp.glp_intopt;
     /* glp_scale_prob / glp_adv_basis (lib/glpscl.js, lib/glpini01.js): O(nnz) host work in the
        native library instead of linked-list walks; same factors, same statuses */
@@ -89,7 +148,8 @@ exports.install = function (glp) {
     };
     glp.glp_simplex = function (P, parm) {
         parm = parm || new glp.SMCP();
-        if (parm.presolve) return simplex0(P, parm);      // the JS presolver calls back into solve_lp
+        if (parm.presolve)      // native presolver on request, else the JS presolver (it calls back into solve_lp)
+            return opts.nativePresolve ? presolveLp(glp, P, parm) : simplex0(P, parm);
         const d = device(glp, P);
         const ret = addon.simplex(P._glpb,
             Int32Array.from([parm.msg_lev, parm.meth, parm.pricing, parm.r_test, parm.it_lim, parm.tm_lim, parm.out_frq, parm.out_dly, 0]),

@@ -2322,6 +2322,14 @@ def glp_intopt(P, parm=None, device=0):
     if parm is None:
         parm = IOCP()
     _check_iocp(parm)
+    # options whose machinery is outside this path (SURVEY 8 "out of scope": cut generators lib/glpios05-08,
+    # feasibility pump lib/glpios10, pseudocost branching lib/glpios09.js:365-660): valid in the reference,
+    # refused here instead of being silently ignored
+    for name in ("mir_cuts", "gmi_cuts", "cov_cuts", "clq_cuts", "fp_heur"):
+        if getattr(parm, name) == GLP_ON:
+            xerror("glp_intopt: %s = GLP_ON; not supported by the B200 path" % name)
+    if parm.br_tech == GLP_BR_PCH:
+        xerror("glp_intopt: br_tech = GLP_BR_PCH; not supported by the B200 path")
     P.mip_stat, P.mip_obj = GLP_UNDEF, 0.0
     ret = _check_db_bounds(P, "glp_intopt", parm.msg_lev)
     if ret != 0:

@@ -33,6 +33,7 @@ napi_status napi_get_value_external(napi_env env, napi_value value, void **resul
 napi_status napi_get_value_string_utf8(napi_env env, napi_value value, char *buf, size_t bufsize, size_t *result);
 napi_status napi_create_external(napi_env env, void *data, napi_finalize finalize_cb, void *finalize_hint, napi_value *result);
 napi_status napi_create_int32(napi_env env, int32_t value, napi_value *result);
+napi_status napi_create_double(napi_env env, double value, napi_value *result);
 napi_status napi_create_object(napi_env env, napi_value *result);
 napi_status napi_create_arraybuffer(napi_env env, size_t byte_length, void **data, napi_value *result);
 napi_status napi_create_typedarray(napi_env env, napi_typedarray_type type, size_t length, napi_value arraybuffer, size_t byte_offset,

@@ -154,3 +154,12 @@ def test_workspace_argument_checks():
     assert list(c_value) == [2.0] and list(c_stat) == [F.GLP_BS] and list(r_stat) == [F.GLP_NU]
     assert list(r_dual) == [-0.5]
     npp.close()
+
+
+@pytest.mark.parametrize("opt", ["mir_cuts", "gmi_cuts", "cov_cuts", "clq_cuts", "fp_heur", "br_tech"])
+def test_intopt_refuses_options_outside_the_path(opt):
+    """valid in the reference, no machinery behind them here: refused loudly, never silently ignored"""
+    P = facade_problem(CASES["npp_mip_2"]["problem"])
+    parm = F.IOCP({opt: F.GLP_BR_PCH if opt == "br_tech" else F.GLP_ON})
+    with pytest.raises(F.GlpkError, match="not supported by the B200 path"):
+        F.glp_intopt(P, parm)
