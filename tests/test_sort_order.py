@@ -83,3 +83,54 @@ def test_closed_form_reproduces_the_references_own_lists():
         nz = [i for i in range(1, len(vec)) if vec[i] != 0.0]
         order = closed_form([not (abs(vec[i]) < eps) for i in nz])
         assert [nz[j - 1] for j in order] == [int(x) for x in ind[1:num + 1]], g
+
+
+def test_row_wise_pivot_row_is_the_column_wise_one_bit_for_bit():
+    """lib/glpspx02.js:735-752 switches between eval_trow1 (column dots, :655-693) and eval_trow2 (row
+    scatter for sparse rho, :695-733) on the density of rho.  With the columns of A stored in ascending row
+    order -- which is how init_csa receives them after glp_sort_matrix / glp_read_lp -- both forms add the
+    SAME products in the SAME order for every column (the row scatter merely skips the exact zeros), so the
+    switch changes the reference's running time, not one bit of trow: the device, which always walks the
+    columns, has nothing to reproduce.  Literal restatement of both loops on random data."""
+    import numpy as np
+    rng = np.random.default_rng(7)
+    for trial in range(30):
+        m, n = int(rng.integers(5, 40)), int(rng.integers(5, 60))
+        A = np.where(rng.random((m, n)) < 0.3, rng.uniform(-3, 3, (m, n)), 0.0)
+        rho = np.where(rng.random(m) < (0.1 if trial % 2 else 0.5), rng.uniform(-2, 2, m), 0.0)
+        # a basis header: N = the first n of a random permutation of the m+n variables
+        head = rng.permutation(m + n) + 1
+        nonbasic = head[m:]                       # x[k] = xN[j], k = head[m+j]
+        bind = np.zeros(m + n + 1, dtype=int)
+        for pos, k in enumerate(head, 1):
+            bind[k] = pos
+        fixed = rng.random(n) < 0.1               # stat[j] == GLP_NS
+        # eval_trow1
+        t1 = np.zeros(n)
+        for j in range(n):
+            if fixed[j]:
+                continue
+            k = nonbasic[j]
+            if k <= m:
+                t1[j] = -rho[k - 1]
+            else:
+                temp = 0.0
+                for i in range(m):                # column k-m, ascending rows
+                    if A[i, k - m - 1] != 0.0:
+                        temp += rho[i] * A[i, k - m - 1]
+                t1[j] = temp
+        # eval_trow2
+        t2 = np.zeros(n)
+        for i in range(m):
+            temp = rho[i]
+            if temp == 0.0:
+                continue
+            j = bind[i + 1] - m
+            if j >= 1 and not fixed[j - 1]:
+                t2[j - 1] -= temp
+            for c in range(n):                    # row i, ascending columns
+                if A[i, c] != 0.0:
+                    j = bind[m + c + 1] - m
+                    if j >= 1 and not fixed[j - 1]:
+                        t2[j - 1] += temp * A[i, c]
+        assert np.array_equal(t1, t2)             # == on every double (0.0 == -0.0: both leave trow_ind alone)
