@@ -296,6 +296,16 @@ def main():
         cases["npp_mip_%d" % seed] = c
         print("npp_mip", seed, c["ret"], c["n_tse"], c.get("reduced", {}).get("m"), c.get("reduced", {}).get("n"),
               c.get("unloaded", {}).get("mip_obj"), round(time.time() - t0, 1), flush=True)
+    for seed in range(101, 107):        # larger LPs: a real reduced problem is left for the simplex
+        c = run_case(ref, npp_lp(seed, m=40 + 5 * (seed % 4), n=60 + 7 * (seed % 3)), GLP_SOL)
+        cases["npp_lp_%d" % seed] = c
+        print("npp_lp", seed, c["ret"], c["n_tse"], c.get("reduced", {}).get("m"), c.get("reduced", {}).get("n"),
+              c.get("unloaded", {}).get("obj"), round(time.time() - t0, 1), flush=True)
+    for seed in range(201, 205):
+        c = run_case(ref, npp_mip(seed, m=14, n=20), GLP_MIP, binarize=seed % 2)
+        cases["npp_mip_%d" % seed] = c
+        print("npp_mip", seed, c["ret"], c["n_tse"], c.get("reduced", {}).get("m"), c.get("reduced", {}).get("n"),
+              c.get("unloaded", {}).get("mip_obj"), round(time.time() - t0, 1), flush=True)
     with open(os.path.join(GOLD, "ref_npp.json"), "w") as f:
         json.dump(cases, f)
     print("wrote ref_npp.json (%d bytes, %d cases)" % (os.path.getsize(os.path.join(GOLD, "ref_npp.json")),

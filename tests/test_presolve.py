@@ -1,7 +1,7 @@
 """LP / MIP presolver (glpb_npp_*, csrc/presolve.cpp) against the REFERENCE'S OWN presolver.
 
 tests/golden/ref_npp.json was produced by oracle/jsref/make_npp_golden.py: the unmodified
-lib/glpnpp01-05.js run on the reference's fixtures and on 64 generated problems.  Everything here is
+lib/glpnpp01-05.js run on the reference's fixtures and on 74 generated problems.  Everything here is
 host code (no device): bit-exact comparison of
   * the return code (0 / GLP_ENOPFS / GLP_ENODFS) and the depth of the recovery stack,
   * the reduced problem npp_build_prob leaves -- row order, column order, bounds, costs, the constant
