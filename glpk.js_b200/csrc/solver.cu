@@ -1014,7 +1014,7 @@ struct Loop : Dev {
 
     /* refactorisation period: bfcp.nfs_max (the reference's eta-file limit, default 100);
        the explicit inverse needs a fresh start only for accuracy, so for large
-       kernels the period grows with k unless GLPB_REFAC_AUTO=0 */
+       kernels the period grows with k -- max(nfs_max, 4k) -- unless GLPB_REFAC_AUTO=0 */
     int refac_period() const
     {
         static const bool fixed = getenv("GLPB_REFAC_AUTO") && atoi(getenv("GLPB_REFAC_AUTO")) == 0;
@@ -1022,7 +1022,12 @@ struct Loop : Dev {
            22.3 s, same 120552 iterations, objective to 5e-14 of the HiGHS pin, KKT 5e-16; the accuracy triggers
            of the reference -- piv1/piv2 at 1e-8, d1/d2, check_stab -- still force one when needed) */
         static const int div = getenv("GLPB_REFAC_DIV") ? std::max(1, atoi(getenv("GLPB_REFAC_DIV"))) : 1;
-        return fixed ? P->bfcp.nfs_max : std::max(P->bfcp.nfs_max, k / div);
+        /* round 2, same box (profiles/r03_ab_refac_mul.txt): periods k / 2k / 4k give 27 / 14 / 8 refactorisations
+           and 18.64 / 17.94 / 17.62 s on C3, 415 / 392 / 381 ms on C2, the SAME 120552 resp. 6728 iterations,
+           objective to 5e-14 of the pin, KKT 4e-16 */
+        static const int mul = getenv("GLPB_REFAC_MUL") ? std::max(1, atoi(getenv("GLPB_REFAC_MUL"))) : 4;
+        if (fixed || k / div <= P->bfcp.nfs_max) return P->bfcp.nfs_max;   /* small kernels: the reference's limit */
+        return (int)std::min<long>((long)k * mul / div, 1 << 28);
     }
     bool it_limit() const { return parm.it_lim < INT_MAX && it_cnt - it_beg >= parm.it_lim; }
     bool tm_limit() const { return parm.tm_lim < INT_MAX && (now_ms() - tm_beg) >= parm.tm_lim; }

@@ -53,7 +53,10 @@ typedef struct glpb_iocp {
  * inverse of the structural kernel of B instead of F*H*V, so only the update
  * count (nfs_max -> refactorisation period) and the pivot tolerances apply. */
 typedef struct glpb_bfcp {
-    int nfs_max;        /* refactorise after this many updates (default 100) */
+    int nfs_max;        /* refactorise after max(nfs_max, 4k) updates, k = basic structurals (default 100;
+                           the explicit inverse has no eta file to outgrow: the period only bounds
+                           rounding, the reference's accuracy triggers still force a fresh start;
+                           GLPB_REFAC_AUTO=0 in the environment pins the period to nfs_max) */
     double piv_tol;     /* relative pivot threshold in the dense inverse      */
     double upd_tol;     /* reserved                                           */
 } glpb_bfcp;
