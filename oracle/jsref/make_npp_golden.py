@@ -50,7 +50,7 @@ def null(x):
 
 # ---------------------------------------------------------------- problem generators (recorded in the golden)
 
-def npp_lp(seed, m=10, n=14):
+def npp_lp(seed, m=10, n=14, wild=False):
     """feasible by construction (bounds drawn around a point x0), rich in presolvable structure"""
     rs = np.random.RandomState(seed)
     A = np.zeros((m, n))
@@ -109,6 +109,8 @@ def npp_lp(seed, m=10, n=14):
     coef = np.array([float(rs.choice([-3, -2, -1, 0, 0, 1, 2, 3, 5])) for _ in range(n)])
     # keep the objective bounded: no improving direction along an infinite bound
     for j in range(n):
+        if wild:
+            break       # any sign: dual infeasible / unbounded problems (GLP_ENODFS, non-optimal reduced LPs)
         if c_type[j] == FR:
             coef[j] = 0.0
         elif c_type[j] == LO:
@@ -300,6 +302,11 @@ def main():
         c = run_case(ref, npp_lp(seed, m=40 + 5 * (seed % 4), n=60 + 7 * (seed % 3)), GLP_SOL)
         cases["npp_lp_%d" % seed] = c
         print("npp_lp", seed, c["ret"], c["n_tse"], c.get("reduced", {}).get("m"), c.get("reduced", {}).get("n"),
+              c.get("unloaded", {}).get("obj"), round(time.time() - t0, 1), flush=True)
+    for seed in range(301, 313):        # objective of any sign: dual infeasibility found by the presolver or by the simplex
+        c = run_case(ref, npp_lp(seed, m=7 + seed % 5, n=9 + seed % 6, wild=True), GLP_SOL)
+        cases["npp_lp_%d" % seed] = c
+        print("npp_lp wild", seed, c["ret"], c["n_tse"], c.get("reduced_lp_ret"), c.get("reduced_lp", {}).get("status"),
               c.get("unloaded", {}).get("obj"), round(time.time() - t0, 1), flush=True)
     for seed in range(201, 205):
         c = run_case(ref, npp_mip(seed, m=14, n=20), GLP_MIP, binarize=seed % 2)

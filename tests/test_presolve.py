@@ -1,7 +1,7 @@
 """LP / MIP presolver (glpb_npp_*, csrc/presolve.cpp) against the REFERENCE'S OWN presolver.
 
 tests/golden/ref_npp.json was produced by oracle/jsref/make_npp_golden.py: the unmodified
-lib/glpnpp01-05.js run on the reference's fixtures and on 74 generated problems.  Everything here is
+lib/glpnpp01-05.js run on the reference's fixtures and on 86 generated problems.  Everything here is
 host code (no device): bit-exact comparison of
   * the return code (0 / GLP_ENOPFS / GLP_ENODFS) and the depth of the recovery stack,
   * the reduced problem npp_build_prob leaves -- row order, column order, bounds, costs, the constant
@@ -115,7 +115,7 @@ def test_presolver_matches_reference(name):
 def test_golden_covers_the_transformations():
     """the generated cases are only worth something if they reach the presolver's branches"""
     rets = [c["ret"] for c in CASES.values()]
-    assert rets.count(0) >= 45 and rets.count(F.GLP_ENOPFS) >= 5
+    assert rets.count(0) >= 45 and rets.count(F.GLP_ENOPFS) >= 5 and rets.count(F.GLP_ENODFS) >= 5
     assert sum(1 for c in CASES.values() if c["ret"] == 0 and c["reduced"]["m"] == 0) >= 2      # solved by the presolver
     assert sum(1 for c in CASES.values() if c["ret"] == 0 and c["reduced"]["m"] >= 4) >= 20
     grown = [c for c in CASES.values() if c["ret"] == 0 and c["sol"] == F.GLP_MIP and
