@@ -1280,54 +1280,66 @@ int glpb_npp_load_prob(glpb_npp *npp, int m, int n, int dir, double c0, const in
                        const double *ub, const double *coef, const int *kind, const int *A_ptr,
                        const int *A_ind, const double *A_val, int sol)
 {
-    if (!npp || m < 0 || n < 0 || !(dir == 1 || dir == 2) || !(sol == SOL || sol == MIP)) return GLPB_EINVAL;
-    if ((m + n > 0 && (!type || !lb || !ub)) || (n > 0 && (!coef || !A_ptr))) return GLPB_EINVAL;
-    if (npp->nrows || npp->ncols) return GLPB_EINVAL;
-    if (n > 0) {
-        if (A_ptr[0] != 0) return GLPB_EINVAL;
-        for (int j = 0; j < n; j++) if (A_ptr[j + 1] < A_ptr[j]) return GLPB_EINVAL;
-        if (A_ptr[n] > 0 && (!A_ind || !A_val)) return GLPB_EINVAL;
-        for (int e = 0; e < A_ptr[n]; e++) if (A_ind[e] < 0 || A_ind[e] >= m) return GLPB_EINVAL;
-    }
-    for (int k = 0; k < m + n; k++) if (type[k] < FR || type[k] > FX) return GLPB_EINVAL;
-    const double sgn = dir == 1 ? +1.0 : -1.0;
-    npp->orig_dir = dir; npp->orig_m = m; npp->orig_n = n; npp->orig_nnz = n > 0 ? A_ptr[n] : 0;
-    npp->c0 = sgn * c0;
-    npp->sol = sol;
-    npp->row.reserve(m + 1); npp->col.reserve(n + 1); npp->el.reserve(npp->orig_nnz + 1);
-    auto bounds = [&](int k, double &l, double &u) {
-        switch (type[k]) {
-        case FR: l = -INF; u = +INF; break;
-        case LO: l = lb[k]; u = +INF; break;
-        case UP: l = -INF; u = ub[k]; break;
-        case DB: l = lb[k]; u = ub[k]; break;
-        default: l = u = lb[k]; break;
+    try {
+        if (!npp || m < 0 || n < 0 || !(dir == 1 || dir == 2) || !(sol == SOL || sol == MIP)) return GLPB_EINVAL;
+        if ((m + n > 0 && (!type || !lb || !ub)) || (n > 0 && (!coef || !A_ptr))) return GLPB_EINVAL;
+        if (npp->nrows || npp->ncols) return GLPB_EINVAL;
+        if (n > 0) {
+            if (A_ptr[0] != 0) return GLPB_EINVAL;
+            for (int j = 0; j < n; j++) if (A_ptr[j + 1] < A_ptr[j]) return GLPB_EINVAL;
+            if (A_ptr[n] > 0 && (!A_ind || !A_val)) return GLPB_EINVAL;
+            for (int e = 0; e < A_ptr[n]; e++) if (A_ind[e] < 0 || A_ind[e] >= m) return GLPB_EINVAL;
         }
-    };
-    for (int i = 0; i < m; i++) {
-        const int r = npp->add_row();
-        bounds(i, npp->row[r].lb, npp->row[r].ub);
+        for (int k = 0; k < m + n; k++) if (type[k] < FR || type[k] > FX) return GLPB_EINVAL;
+        const double sgn = dir == 1 ? +1.0 : -1.0;
+        npp->orig_dir = dir; npp->orig_m = m; npp->orig_n = n; npp->orig_nnz = n > 0 ? A_ptr[n] : 0;
+        npp->c0 = sgn * c0;
+        npp->sol = sol;
+        npp->row.reserve(m + 1); npp->col.reserve(n + 1); npp->el.reserve(npp->orig_nnz + 1);
+        auto bounds = [&](int k, double &l, double &u) {
+            switch (type[k]) {
+            case FR: l = -INF; u = +INF; break;
+            case LO: l = lb[k]; u = +INF; break;
+            case UP: l = -INF; u = ub[k]; break;
+            case DB: l = lb[k]; u = ub[k]; break;
+            default: l = u = lb[k]; break;
+            }
+        };
+        for (int i = 0; i < m; i++) {
+            const int r = npp->add_row();
+            bounds(i, npp->row[r].lb, npp->row[r].ub);
+        }
+        for (int j = 0; j < n; j++) {
+            const int c = npp->add_col();
+            if (sol == MIP) npp->col[c].is_int = (kind && kind[j] == IV) ? 1 : 0;
+            bounds(m + j, npp->col[c].lb, npp->col[c].ub);
+            npp->col[c].coef = sgn * coef[j];
+            for (int e = A_ptr[j]; e < A_ptr[j + 1]; e++) npp->add_aij(A_ind[e] + 1, c, A_val[e]);
+        }
+        return 0;
+    } catch (const std::bad_alloc &) {
+        return GLPB_ENOMEM;
     }
-    for (int j = 0; j < n; j++) {
-        const int c = npp->add_col();
-        if (sol == MIP) npp->col[c].is_int = (kind && kind[j] == IV) ? 1 : 0;
-        bounds(m + j, npp->col[c].lb, npp->col[c].ub);
-        npp->col[c].coef = sgn * coef[j];
-        for (int e = A_ptr[j]; e < A_ptr[j + 1]; e++) npp->add_aij(A_ind[e] + 1, c, A_val[e]);
-    }
-    return 0;
 }
 
 int glpb_npp_simplex(glpb_npp *npp)
 {
-    if (!npp || npp->sol != SOL || npp->built) return GLPB_EINVAL;
-    return npp->process_prob(0);
+    try {
+        if (!npp || npp->sol != SOL || npp->built) return GLPB_EINVAL;
+        return npp->process_prob(0);
+    } catch (const std::bad_alloc &) {
+        return GLPB_ENOMEM;
+    }
 }
 
 int glpb_npp_integer(glpb_npp *npp, int binarize)
 {
-    if (!npp || npp->sol != MIP || npp->built) return GLPB_EINVAL;
-    return npp->integer(binarize);
+    try {
+        if (!npp || npp->sol != MIP || npp->built) return GLPB_EINVAL;
+        return npp->integer(binarize);
+    } catch (const std::bad_alloc &) {
+        return GLPB_ENOMEM;
+    }
 }
 
 int glpb_npp_get_counts(glpb_npp *npp, int *out, int count)
@@ -1358,86 +1370,94 @@ int glpb_npp_get_size(glpb_npp *npp, int *m, int *n, int *nnz)
 int glpb_npp_build_prob(glpb_npp *npp, double *c0, int *type, double *lb, double *ub, double *coef, int *kind,
                         int *A_ptr, int *A_ind, double *A_val, int *row_ref, int *col_ref)
 {
-    if (!npp || npp->built || !c0 || !A_ptr) return GLPB_EINVAL;
-    const double sgn = npp->orig_dir == 1 ? +1.0 : -1.0;
-    *c0 = sgn * npp->c0;
-    auto kind_of = [](double l, double u) {
-        if (l == -INF && u == +INF) return FR;
-        if (u == +INF) return LO;
-        if (l == -INF) return UP;
-        if (l != u) return DB;
-        return FX;
-    };
-    int m = 0, n = 0, nz = 0;
-    for (int r = npp->r_head; r; r = npp->row[r].next) m++;
-    npp->row_ref.assign(1, 0);
-    npp->col_ref.assign(1, 0);
-    int i = 0;
-    for (int r = npp->r_head; r; r = npp->row[r].next, i++) {
-        Row &x = npp->row[r];
-        x.temp = i;
-        type[i] = kind_of(x.lb, x.ub); lb[i] = x.lb; ub[i] = x.ub;
-        npp->row_ref.push_back(r);
-        if (row_ref) row_ref[i] = r;
-    }
-    A_ptr[0] = 0;
-    for (int c = npp->c_head; c; c = npp->col[c].next, n++) {
-        const Col &y = npp->col[c];
-        type[m + n] = kind_of(y.lb, y.ub); lb[m + n] = y.lb; ub[m + n] = y.ub;
-        coef[n] = sgn * y.coef;
-        if (kind) kind[n] = y.is_int ? IV : 1;
-        for (int a = y.ptr; a; a = npp->el[a].c_next, nz++) {
-            A_ind[nz] = npp->row[npp->el[a].row].temp;
-            A_val[nz] = npp->el[a].val;
+    try {
+        if (!npp || npp->built || !c0 || !A_ptr) return GLPB_EINVAL;
+        const double sgn = npp->orig_dir == 1 ? +1.0 : -1.0;
+        *c0 = sgn * npp->c0;
+        auto kind_of = [](double l, double u) {
+            if (l == -INF && u == +INF) return FR;
+            if (u == +INF) return LO;
+            if (l == -INF) return UP;
+            if (l != u) return DB;
+            return FX;
+        };
+        int m = 0, n = 0, nz = 0;
+        for (int r = npp->r_head; r; r = npp->row[r].next) m++;
+        npp->row_ref.assign(1, 0);
+        npp->col_ref.assign(1, 0);
+        int i = 0;
+        for (int r = npp->r_head; r; r = npp->row[r].next, i++) {
+            Row &x = npp->row[r];
+            x.temp = i;
+            type[i] = kind_of(x.lb, x.ub); lb[i] = x.lb; ub[i] = x.ub;
+            npp->row_ref.push_back(r);
+            if (row_ref) row_ref[i] = r;
         }
-        A_ptr[n + 1] = nz;
-        npp->col_ref.push_back(c);
-        if (col_ref) col_ref[n] = c;
+        A_ptr[0] = 0;
+        for (int c = npp->c_head; c; c = npp->col[c].next, n++) {
+            const Col &y = npp->col[c];
+            type[m + n] = kind_of(y.lb, y.ub); lb[m + n] = y.lb; ub[m + n] = y.ub;
+            coef[n] = sgn * y.coef;
+            if (kind) kind[n] = y.is_int ? IV : 1;
+            for (int a = y.ptr; a; a = npp->el[a].c_next, nz++) {
+                A_ind[nz] = npp->row[npp->el[a].row].temp;
+                A_val[nz] = npp->el[a].val;
+            }
+            A_ptr[n + 1] = nz;
+            npp->col_ref.push_back(c);
+            if (col_ref) col_ref[n] = c;
+        }
+        npp->m = m; npp->n = n; npp->nnz = nz;
+        npp->built = true;
+        npp->c0 = 0.0;
+        npp->r_head = npp->r_tail = npp->c_head = npp->c_tail = 0;
+        return 0;
+    } catch (const std::bad_alloc &) {
+        return GLPB_ENOMEM;
     }
-    npp->m = m; npp->n = n; npp->nnz = nz;
-    npp->built = true;
-    npp->c0 = 0.0;
-    npp->r_head = npp->r_tail = npp->c_head = npp->c_tail = 0;
-    return 0;
 }
 
 int glpb_npp_postprocess(glpb_npp *npp, const int *r_stat, const double *r_dual, const int *c_stat,
                          const double *c_value, int *out_r_stat, double *out_r_dual, int *out_c_stat,
                          double *out_c_value)
 {
-    if (!npp || !npp->built) return GLPB_EINVAL;
-    if (npp->n > 0 && !c_value) return GLPB_EINVAL;
-    const bool basic = npp->sol == SOL;
-    if (basic && ((npp->m > 0 && (!r_stat || !r_dual)) || (npp->n > 0 && !c_stat))) return GLPB_EINVAL;
-    const double sgn = npp->orig_dir == 1 ? +1.0 : -1.0;
-    if (basic) {
-        npp->r_stat.assign(npp->nrows + 1, 0);
-        npp->c_stat.assign(npp->ncols + 1, 0);
-        npp->r_pi.assign(npp->nrows + 1, DBL_MAX);
-    }
-    npp->c_value.assign(npp->ncols + 1, DBL_MAX);
-    for (int i = 1; i <= npp->m; i++)
+    try {
+        if (!npp || !npp->built) return GLPB_EINVAL;
+        if (npp->n > 0 && !c_value) return GLPB_EINVAL;
+        const bool basic = npp->sol == SOL;
+        if (basic && ((npp->m > 0 && (!r_stat || !r_dual)) || (npp->n > 0 && !c_stat))) return GLPB_EINVAL;
+        const double sgn = npp->orig_dir == 1 ? +1.0 : -1.0;
         if (basic) {
-            const int k = npp->row_ref[i];
-            npp->r_stat[k] = (signed char)r_stat[i - 1];
-            npp->r_pi[k] = sgn * r_dual[i - 1];
+            npp->r_stat.assign(npp->nrows + 1, 0);
+            npp->c_stat.assign(npp->ncols + 1, 0);
+            npp->r_pi.assign(npp->nrows + 1, DBL_MAX);
         }
-    for (int j = 1; j <= npp->n; j++) {
-        const int k = npp->col_ref[j];
-        if (basic) npp->c_stat[k] = (signed char)c_stat[j - 1];
-        npp->c_value[k] = c_value[j - 1];
+        npp->c_value.assign(npp->ncols + 1, DBL_MAX);
+        for (int i = 1; i <= npp->m; i++)
+            if (basic) {
+                const int k = npp->row_ref[i];
+                npp->r_stat[k] = (signed char)r_stat[i - 1];
+                npp->r_pi[k] = sgn * r_dual[i - 1];
+            }
+        for (int j = 1; j <= npp->n; j++) {
+            const int k = npp->col_ref[j];
+            if (basic) npp->c_stat[k] = (signed char)c_stat[j - 1];
+            npp->c_value[k] = c_value[j - 1];
+        }
+        for (size_t t = npp->stack.size(); t-- > 0;)
+            if (npp->recover(npp->stack[t]) != 0) return GLPB_ESTATE;
+        for (int i = 1; i <= npp->orig_m && basic; i++) {
+            if (out_r_stat) out_r_stat[i - 1] = npp->r_stat[i];
+            if (out_r_dual) out_r_dual[i - 1] = sgn * npp->r_pi[i];
+        }
+        for (int j = 1; j <= npp->orig_n; j++) {
+            if (basic && out_c_stat) out_c_stat[j - 1] = npp->c_stat[j];
+            if (out_c_value) out_c_value[j - 1] = npp->c_value[j];
+        }
+        return 0;
+    } catch (const std::bad_alloc &) {
+        return GLPB_ENOMEM;
     }
-    for (size_t t = npp->stack.size(); t-- > 0;)
-        if (npp->recover(npp->stack[t]) != 0) return GLPB_ESTATE;
-    for (int i = 1; i <= npp->orig_m && basic; i++) {
-        if (out_r_stat) out_r_stat[i - 1] = npp->r_stat[i];
-        if (out_r_dual) out_r_dual[i - 1] = sgn * npp->r_pi[i];
-    }
-    for (int j = 1; j <= npp->orig_n; j++) {
-        if (basic && out_c_stat) out_c_stat[j - 1] = npp->c_stat[j];
-        if (out_c_value) out_c_value[j - 1] = npp->c_value[j];
-    }
-    return 0;
 }
 
 } // extern "C"

@@ -341,7 +341,8 @@ void glpb_free_names(char *names);
  * non-basic variables, row activities and reduced costs are recomputed by the
  * binding from ITS coefficients exactly as npp_unload_sol does.  Returns 0,
  * GLPB_EINVAL, or GLPB_ESTATE where the reference's xassert(tse.func() == 0)
- * would throw. */
+ * would throw.  Every call returns GLPB_ENOMEM instead of letting an allocation
+ * failure cross the C ABI. */
 typedef struct glpb_npp glpb_npp;
 glpb_npp *glpb_npp_create(void);
 void glpb_npp_destroy(glpb_npp *npp);                /* idempotent on NULL */
