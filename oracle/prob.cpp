@@ -334,8 +334,9 @@ static int solve_lp(Prob &P, const SMCP &parm, const Hook *hook)
     return ret;
 }
 
-/* lib/glpapi06.js:261-339 glp_simplex (presolve OFF path only; the LP
-   presolver is SURVEY 8f "next") */
+/* lib/glpapi06.js:261-339 glp_simplex (presolve OFF path only: the oracle has no
+   restatement of the presolver -- the product's one is checked against the
+   reference's own runs directly, tests/golden/ref_npp.json) */
 int simplex(Prob &P, const SMCP &parm, const Hook *hook)
 {
     P.pbs_stat = P.dbs_stat = GLP_UNDEF;
