@@ -731,6 +731,7 @@ def glp_adv_basis(P, flags=0):
     ub = np.array([P.row[i].ub for i in range(1, m + 1)] + [P.col[j].ub for j in range(1, n + 1)])
     stat, size = native.adv_basis(m, n, cptr, cind, rptr, rind, type_, lb, ub)
     P.tri_size = size
+    xprintf("Size of triangular part = %d" % size)     # lib/glpini01.js:287-288 (LPX message level: default 3)
     for i in range(1, m + 1):
         glp_set_row_stat(P, i, int(stat[i - 1]))
     for j in range(1, n + 1):
@@ -1963,16 +1964,13 @@ def _npp_build(P, npp):
 
 
 def _quiet(msg_lev, fn, *args):
-    """The reference mutes the terminal around scaling / crash basis unless
-    msg_lev >= GLP_MSG_ALL (lib/glpapi06.js:107-128)."""
-    global _print_func
-    saved = _print_func
-    if msg_lev < GLP_MSG_ALL:
-        _print_func = None
-    try:
-        return fn(*args)
-    finally:
-        _print_func = saved
+    """lib/glpapi06.js:107-128 / lib/glpapi09.js:201-213 switch env.term_out off around scaling and the
+    crash basis unless msg_lev >= GLP_MSG_ALL -- but the reference's xprintf (lib/glpapi.js:30-35) never
+    reads env.term_out, so those messages reach the print function at every msg_lev (the reference run
+    under minijs prints 'Scaling...' ... 'Size of triangular part = 5' with msg_lev = GLP_MSG_OFF).
+    Mirrored as it behaves, not as it was meant."""
+    del msg_lev
+    return fn(*args)
 
 
 def _bound_value(x):
@@ -2228,20 +2226,21 @@ def _preprocess_and_solve_mip(P, parm, device):
     npp = _npp_load(P, GLP_MIP)
     try:
         ret = npp.integer(parm.binarize == GLP_ON)
-        if parm.msg_lev >= GLP_MSG_ALL:      # what npp_integer / npp_binarize_prob print (glpnpp04.js:92-97, glpnpp05.js:475-514)
-            k = npp.counts()
-            if k["bin_vars"] > 0:
-                xprintf("%d integer variable(s) were replaced by %d binary ones" % (k["bin_vars"], k["bin_bins"]))
-            if k["bin_rows"] > 0:
-                xprintf("%d row(s) were added due to binarization" % k["bin_rows"])
-            if k["bin_fails"] > 0:
-                xprintf("Binarization failed for %d integer variable(s)" % k["bin_fails"])
-            if k["packing"] > 0:
-                xprintf("%d hidden packing inequaliti(es) were detected" % k["packing"])
-            if k["covering"] > 0:
-                xprintf("%d hidden covering inequaliti(es) were detected" % k["covering"])
-            if k["reduced"] > 0:
-                xprintf("%d constraint coefficient(s) were reduced" % k["reduced"])
+        # what npp_integer / npp_binarize_prob print (glpnpp04.js:92-97, glpnpp05.js:475-514) -- at EVERY msg_lev:
+        # the env.term_out switch around the call (glpapi09.js:142-147) is inert, see _quiet
+        k = npp.counts()
+        if k["bin_vars"] > 0:
+            xprintf("%d integer variable(s) were replaced by %d binary ones" % (k["bin_vars"], k["bin_bins"]))
+        if k["bin_rows"] > 0:
+            xprintf("%d row(s) were added due to binarization" % k["bin_rows"])
+        if k["bin_fails"] > 0:
+            xprintf("Binarization failed for %d integer variable(s)" % k["bin_fails"])
+        if k["packing"] > 0:
+            xprintf("%d hidden packing inequaliti(es) were detected" % k["packing"])
+        if k["covering"] > 0:
+            xprintf("%d hidden covering inequaliti(es) were detected" % k["covering"])
+        if k["reduced"] > 0:
+            xprintf("%d constraint coefficient(s) were reduced" % k["reduced"])
         if ret != 0:
             if parm.msg_lev >= GLP_MSG_ALL:
                 xprintf("PROBLEM HAS NO PRIMAL FEASIBLE SOLUTION" if ret == GLP_ENOPFS

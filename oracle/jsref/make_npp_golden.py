@@ -272,6 +272,35 @@ def run_case(ref, src, sol, binarize=0):
     return out
 
 
+def terminal_output(ref, src, sol, binarize, msg_lev):
+    """what the reference prints for the WHOLE call glp_simplex / glp_intopt(presolve: GLP_ON) at msg_lev"""
+    from minijs import NativeFunc, js_to_str
+    lines = []
+    saved = ref.call("glp_get_print_func")
+    ref.call("glp_set_print_func", NativeFunc(lambda this, a: lines.append(js_to_str(a[0]) if a else ""), "print"))
+    try:
+        P = ref.make(src)
+        if sol == GLP_SOL:
+            ret = ref.call("glp_simplex", P, ref.smcp(presolve=1, msg_lev=msg_lev))
+        else:
+            ref.call("glp_simplex", P, ref.smcp(msg_lev=0))
+            del lines[:]
+            ret = ref.call("glp_intopt", P, ref.iocp(presolve=1, binarize=binarize, msg_lev=msg_lev))
+    finally:
+        ref.call("glp_set_print_func", saved)
+    return dict(ret=int(ret), lines=lines)
+
+
+def add_terminal_output(ref, case, src):
+    """only where the whole call stays on the host: rejected by the presolver or solved by it"""
+    if case["ret"] != 0 or (case["reduced"]["m"] == 0 and case["reduced"]["n"] == 0):
+        case["terminal"] = {str(lev): terminal_output(ref, src, case["sol"], case["binarize"], lev) for lev in (0, 3)}
+    else:
+        # the solvers are silent at GLP_MSG_OFF; what still reaches the print function are the messages of
+        # glp_scale_prob / glp_adv_basis on the REDUCED problem (the reference's term_out switch is inert)
+        case["terminal_off"] = terminal_output(ref, src, case["sol"], case["binarize"], 0)
+
+
 def main():
     ref = Ref()
     cases = {"_about": "generated by oracle/jsref/make_npp_golden.py from the unmodified reference sources "
@@ -290,11 +319,13 @@ def main():
                   round(time.time() - t0, 1), flush=True)
     for seed in range(1, 41):
         c = run_case(ref, npp_lp(seed, m=8 + seed % 7, n=10 + seed % 9), GLP_SOL)
+        add_terminal_output(ref, c, npp_lp(seed, m=8 + seed % 7, n=10 + seed % 9))
         cases["npp_lp_%d" % seed] = c
         print("npp_lp", seed, c["ret"], c["n_tse"], c.get("reduced", {}).get("m"), c.get("reduced", {}).get("n"),
               c.get("unloaded", {}).get("obj"), round(time.time() - t0, 1), flush=True)
     for seed in range(1, 25):
         c = run_case(ref, npp_mip(seed), GLP_MIP, binarize=seed % 2)
+        add_terminal_output(ref, c, npp_mip(seed))
         cases["npp_mip_%d" % seed] = c
         print("npp_mip", seed, c["ret"], c["n_tse"], c.get("reduced", {}).get("m"), c.get("reduced", {}).get("n"),
               c.get("unloaded", {}).get("mip_obj"), round(time.time() - t0, 1), flush=True)
@@ -305,6 +336,7 @@ def main():
               c.get("unloaded", {}).get("obj"), round(time.time() - t0, 1), flush=True)
     for seed in range(301, 313):        # objective of any sign: dual infeasibility found by the presolver or by the simplex
         c = run_case(ref, npp_lp(seed, m=7 + seed % 5, n=9 + seed % 6, wild=True), GLP_SOL)
+        add_terminal_output(ref, c, npp_lp(seed, m=7 + seed % 5, n=9 + seed % 6, wild=True))
         cases["npp_lp_%d" % seed] = c
         print("npp_lp wild", seed, c["ret"], c["n_tse"], c.get("reduced_lp_ret"), c.get("reduced_lp", {}).get("status"),
               c.get("unloaded", {}).get("obj"), round(time.time() - t0, 1), flush=True)

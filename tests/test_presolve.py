@@ -163,3 +163,82 @@ def test_intopt_refuses_options_outside_the_path(opt):
     parm = F.IOCP({opt: F.GLP_BR_PCH if opt == "br_tech" else F.GLP_ON})
     with pytest.raises(F.GlpkError, match="not supported by the B200 path"):
         F.glp_intopt(P, parm)
+
+
+HOST_ONLY = sorted(k for k, c in CASES.items() if "terminal" in c)
+
+
+@pytest.mark.parametrize("name", HOST_ONLY)
+def test_whole_call_on_the_host_when_the_presolver_decides(name):
+    """Problems the presolver rejects (GLP_ENOPFS / GLP_ENODFS) or solves outright (empty reduced problem) never
+    reach the device: glp_simplex / glp_intopt(presolve: GLP_ON) of the facade, whole call, against the
+    reference's whole call -- return code, every line of terminal output at msg_lev OFF and ALL, and the
+    solution stored in the problem object."""
+    case = CASES[name]
+    for lev in (F.GLP_MSG_OFF, F.GLP_MSG_ALL):
+        ref = case["terminal"][str(lev)]
+        P = facade_problem(case["problem"])
+        lines = []
+        F.glp_set_print_func(lines.append)
+        try:
+            if case["sol"] == F.GLP_SOL:
+                parm = F.SMCP({"presolve": F.GLP_ON})
+                parm.msg_lev = lev
+                ret = F.glp_simplex(P, parm)
+            else:
+                parm = F.IOCP({"presolve": F.GLP_ON, "binarize": F.GLP_ON if case["binarize"] else F.GLP_OFF})
+                parm.msg_lev = lev
+                ret = F.glp_intopt(P, parm)
+        finally:
+            F.glp_set_print_func(None)
+        assert ret == ref["ret"] == case["ret"]
+        assert lines == ref["lines"]
+        assert P._dev is None                       # nothing was uploaded
+        if ret != 0:
+            continue
+        un = case["unloaded"]
+        if case["sol"] == F.GLP_SOL:
+            assert (F.glp_get_status(P), P.obj_val) == (un["status"], un["obj"])
+            assert [P.col[j].prim for j in range(1, P.n + 1)] == un["col_prim"]
+            assert [P.col[j].stat for j in range(1, P.n + 1)] == un["col_stat"]
+            assert [P.row[i].dual for i in range(1, P.m + 1)] == un["row_dual"]
+        else:
+            assert (F.glp_mip_status(P), P.mip_obj) == (un["mip_stat"], un["mip_obj"])
+            assert [P.col[j].mipx for j in range(1, P.n + 1)] == un["col_val"]
+
+
+class _DeviceReached(Exception):
+    pass
+
+
+NEEDS_DEVICE = sorted(k for k, c in CASES.items() if "terminal_off" in c)
+
+
+@pytest.mark.parametrize("name", NEEDS_DEVICE)
+def test_messages_up_to_the_device_solve(name, monkeypatch):
+    """At GLP_MSG_OFF the solvers are silent, so everything the reference printed during the whole
+    presolve-ON call came from npp_integer, glp_scale_prob and glp_adv_basis ON THE REDUCED PROBLEM (its
+    term_out switch is inert): scale ranges after every pass, size of the triangular part.  The facade must
+    have printed exactly those lines by the time it hands the reduced problem to the device -- a check of the
+    reduced problem, the native scaling and the native crash basis in one."""
+    case = CASES[name]
+
+    def stop(*a, **k):
+        raise _DeviceReached()
+    monkeypatch.setattr(F, "_solve_lp", stop)
+    P = facade_problem(case["problem"])
+    lines = []
+    F.glp_set_print_func(lines.append)
+    try:
+        with pytest.raises(_DeviceReached):
+            if case["sol"] == F.GLP_SOL:
+                parm = F.SMCP({"presolve": F.GLP_ON})
+                parm.msg_lev = F.GLP_MSG_OFF
+                F.glp_simplex(P, parm)
+            else:
+                parm = F.IOCP({"presolve": F.GLP_ON, "binarize": F.GLP_ON if case["binarize"] else F.GLP_OFF})
+                parm.msg_lev = F.GLP_MSG_OFF
+                F.glp_intopt(P, parm)
+    finally:
+        F.glp_set_print_func(None)
+    assert lines == case["terminal_off"]["lines"]
