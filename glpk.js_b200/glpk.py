@@ -64,19 +64,41 @@ def xprintf(data):
 
 
 def _num(x):
-    """A number the way JavaScript's string concatenation shows it."""
+    """A number the way JavaScript's string concatenation shows it: Number::toString(10) of ECMAScript --
+    the shortest round-trip digits (Python's repr yields the same ones) laid out by the position n of the
+    decimal point: digits padded with zeros for k <= n <= 21, a point inside for 0 < n <= 21, '0.000ddd'
+    for -6 < n <= 0, exponent form otherwise."""
     x = float(x)
     if x != x:
         return "NaN"
     if x in (math.inf, -math.inf):
         return "Infinity" if x > 0 else "-Infinity"
-    if x == math.floor(x) and abs(x) < 1e21:
-        return "%d" % x
+    if x == 0:
+        return "0"
+    if x < 0:
+        return "-" + _num(-x)
     r = repr(x)
     if "e" in r:
         mant, ex = r.split("e")
-        r = "%se%s%d" % (mant, "+" if int(ex) >= 0 else "-", abs(int(ex)))
-    return r
+        digits, n = mant.replace(".", ""), int(ex) + 1
+    else:
+        ip, fp = r.split(".")
+        if ip != "0":
+            digits, n = ip + fp, len(ip)
+        else:
+            digits = fp.lstrip("0")
+            n = -(len(fp) - len(digits))
+    digits = digits.rstrip("0") or "0"
+    k = len(digits)
+    if k <= n <= 21:
+        return digits + "0" * (n - k)
+    if 0 < n <= 21:
+        return digits[:n] + "." + digits[n:]
+    if -6 < n <= 0:
+        return "0." + "0" * (-n) + digits
+    e = n - 1
+    tail = "e" + ("+" if e > 0 else "-") + str(abs(e))
+    return (digits if k == 1 else digits[0] + "." + digits[1:]) + tail
 
 
 class SMCP:

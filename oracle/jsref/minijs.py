@@ -113,6 +113,9 @@ def to_num(v):
 
 
 def js_num_to_str(v):
+    """Number::toString(10) of ECMAScript (sec. 6.1.6.1.20): the shortest round-trip digits (Python's repr
+    yields the same ones) laid out by the position n of the decimal point: digits padded with zeros for
+    k <= n <= 21, a point inside for 0 < n <= 21, '0.000ddd' for -6 < n <= 0, exponent form otherwise."""
     if isinstance(v, bool):
         return "true" if v else "false"
     if isinstance(v, int):
@@ -123,16 +126,32 @@ def js_num_to_str(v):
         return "Infinity"
     if v == -INF:
         return "-Infinity"
-    if v == int(v) and abs(v) < 1e21:
-        return str(int(v))
-    r = repr(v)
+    if v == 0:
+        return "0"
+    if v < 0:
+        return "-" + js_num_to_str(-v)
+    r = repr(float(v))
     if "e" in r:
         mant, ex = r.split("e")
-        ex = int(ex)
-        if -7 <= ex < 21:
-            return ("%.*f" % (max(0, len(mant.replace("-", "").replace(".", "")) - 1 - ex), v)).rstrip("0").rstrip(".") if ex < 0 else r
-        return mant + "e" + ("+" if ex > 0 else "-") + str(abs(ex))
-    return r
+        digits, n = mant.replace(".", ""), int(ex) + 1
+    else:
+        ip, fp = r.split(".")
+        if ip != "0":
+            digits, n = ip + fp, len(ip)
+        else:
+            digits = fp.lstrip("0")
+            n = -(len(fp) - len(digits))
+    digits = digits.rstrip("0") or "0"
+    k = len(digits)
+    if k <= n <= 21:
+        return digits + "0" * (n - k)
+    if 0 < n <= 21:
+        return digits[:n] + "." + digits[n:]
+    if -6 < n <= 0:
+        return "0." + "0" * (-n) + digits
+    e = n - 1
+    tail = "e" + ("+" if e > 0 else "-") + str(abs(e))
+    return (digits if k == 1 else digits[0] + "." + digits[1:]) + tail
 
 
 def js_to_str(v):
