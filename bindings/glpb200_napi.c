@@ -260,6 +260,57 @@ static napi_value ReadLp(napi_env env, napi_callback_info info)
     return r;
 }
 
+/* writeLp(m, n, dir, c0, Int32 type, F64 lb, F64 ub, F64 coef, Int32 kind|null, Int32 col_len, Int32 R_ptr, Int32 R_ind,
+           F64 R_val, probName|null, names|null) -> { text, lines } -- glp_write_lp (lib/glpcpx.js:755-999); `names` is
+   one string of 1+m+n NUL-terminated names (objective, rows, columns; "" = none), rows in list order */
+static napi_value WriteLp(napi_env env, napi_callback_info info)
+{
+    size_t argc = 15, len = 0; napi_value a[15], r, v;
+    NAPI_OK(napi_get_cb_info(env, info, &argc, a, NULL, NULL));
+    if (argc < 15) { napi_throw_type_error(env, NULL, "glpb200.writeLp: 15 arguments expected"); return NULL; }
+    int32_t m, n, dir; double c0;
+    NAPI_OK(napi_get_value_int32(env, a[0], &m));
+    NAPI_OK(napi_get_value_int32(env, a[1], &n));
+    NAPI_OK(napi_get_value_int32(env, a[2], &dir));
+    NAPI_OK(napi_get_value_double(env, a[3], &c0));
+    if (m < 0 || n < 0) { napi_throw_range_error(env, NULL, "glpb200.writeLp: m, n must not be negative"); return NULL; }
+    const size_t mn = (size_t)m + (size_t)n;
+    int *type = I32(a[4], mn, "type"); if (!type && mn) return NULL;
+    double *lb = F64(a[5], mn, "lb"); if (!lb && mn) return NULL;
+    double *ub = F64(a[6], mn, "ub"); if (!ub && mn) return NULL;
+    double *coef = F64(a[7], (size_t)n, "coef"); if (!coef && n) return NULL;
+    int *kind = NULL;
+    if (!is_nullish(env, a[8])) { kind = I32(a[8], (size_t)n, "kind"); if (!kind && n) return NULL; }
+    int *col_len = I32(a[9], (size_t)n, "col_len"); if (!col_len && n) return NULL;
+    int *rptr = I32(a[10], (size_t)m + 1, "R_ptr"); if (!rptr) return NULL;
+    if (rptr[m] < 0) { napi_throw_range_error(env, NULL, "glpb200.writeLp: R_ptr[m] < 0"); return NULL; }
+    int *rind = I32(a[11], (size_t)rptr[m], "R_ind"); if (!rind && rptr[m]) return NULL;
+    double *rval = F64(a[12], (size_t)rptr[m], "R_val"); if (!rval && rptr[m]) return NULL;
+    char *pname = NULL, *names = NULL, *text = NULL; long tlen = 0; int lines = 0;
+    if (!is_nullish(env, a[13])) {
+        NAPI_OK(napi_get_value_string_utf8(env, a[13], NULL, 0, &len));
+        if (!(pname = (char *)malloc(len + 1))) { napi_throw_error(env, NULL, "glpb200.writeLp: out of memory"); return NULL; }
+        napi_get_value_string_utf8(env, a[13], pname, len + 1, &len);
+    }
+    if (!is_nullish(env, a[14])) {
+        NAPI_OK(napi_get_value_string_utf8(env, a[14], NULL, 0, &len));
+        if (!(names = (char *)malloc(len + 2))) { free(pname); napi_throw_error(env, NULL, "glpb200.writeLp: out of memory"); return NULL; }
+        napi_get_value_string_utf8(env, a[14], names, len + 1, &len);
+        names[len + 1] = '\0';
+        size_t count = 0;                            /* the block must hold 1+m+n terminated names */
+        for (size_t i = 0; i < len; i++) count += names[i] == '\0';
+        if (count < 1 + mn) { free(pname); free(names); napi_throw_range_error(env, NULL, "glpb200.writeLp: names block too short"); return NULL; }
+    }
+    int rc = glpb_write_lp(m, n, dir, c0, type, lb, ub, coef, kind, col_len, rptr, rind, rval, pname, names, &text, &tlen, &lines);
+    free(pname); free(names);
+    if (rc != 0) { napi_throw_range_error(env, NULL, "glpb200.writeLp: invalid problem data"); return NULL; }
+    if (napi_create_object(env, &r) != napi_ok) { glpb_free_names(text); napi_throw_error(env, NULL, "napi_create_object"); return NULL; }
+    napi_create_string_utf8(env, text, (size_t)tlen, &v); napi_set_named_property(env, r, "text", v);
+    napi_create_int32(env, lines, &v); napi_set_named_property(env, r, "lines", v);
+    glpb_free_names(text);
+    return r;
+}
+
 /* ---- presolver workspace (glpb_npp_*): the handle remembers the sizes every later array is checked against ---- */
 typedef struct { glpb_npp *npp; int om, on, sol, rm, rn, rnz, loaded, built; } shim_npp;
 static void finalize_npp(napi_env env, void *data, void *hint) { shim_npp *h = (shim_npp *)data; (void)env; (void)hint; glpb_npp_destroy(h->npp); free(h); }
@@ -408,7 +459,7 @@ static napi_value Init(napi_env env, napi_value exports)
         { "intopt", 0, Intopt, 0, 0, 0, napi_default, 0 }, { "getSolution", 0, GetSolution, 0, 0, 0, napi_default, 0 },
         { "getMip", 0, GetMip, 0, 0, 0, napi_default, 0 },
         { "scaleProb", 0, ScaleProb, 0, 0, 0, napi_default, 0 }, { "advBasis", 0, AdvBasis, 0, 0, 0, napi_default, 0 },
-        { "readLp", 0, ReadLp, 0, 0, 0, napi_default, 0 },
+        { "readLp", 0, ReadLp, 0, 0, 0, napi_default, 0 }, { "writeLp", 0, WriteLp, 0, 0, 0, napi_default, 0 },
         { "nppCreate", 0, NppCreate, 0, 0, 0, napi_default, 0 }, { "nppLoadProb", 0, NppLoadProb, 0, 0, 0, napi_default, 0 },
         { "nppSimplex", 0, NppSimplex, 0, 0, 0, napi_default, 0 }, { "nppInteger", 0, NppInteger, 0, 0, 0, napi_default, 0 },
         { "nppBuildProb", 0, NppBuildProb, 0, 0, 0, napi_default, 0 }, { "nppPostprocess", 0, NppPostprocess, 0, 0, 0, napi_default, 0 },

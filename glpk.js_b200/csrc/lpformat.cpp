@@ -23,6 +23,8 @@
 #include "../../include/glpb200.h"
 #include <cctype>
 #include <cfloat>
+#include <charconv>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -407,3 +409,172 @@ int glpb_read_lp(const char *text, long len, glpb_problem_data *out, char **name
 void glpb_free_names(char *names) { free(names); }
 
 } // extern "C"
+
+/* ------------------------------------------------------------------ writer
+ * glp_write_lp (lib/glpcpx.js:755-999).  The text is assembled in one buffer,
+ * lines separated by '\n'; a binding replays it through the caller's callback.
+ * Numbers are written the way the reference's string concatenation shows them:
+ * ECMAScript Number::toString(10) -- the shortest digits that round-trip
+ * (std::to_chars yields the same ones), laid out by the position n of the
+ * decimal point. */
+namespace {
+
+std::string js_number(double v)
+{
+    if (v != v) return "NaN";
+    if (std::isinf(v)) return v > 0 ? "Infinity" : "-Infinity";
+    if (v == 0.0) return "0";
+    if (v < 0) return "-" + js_number(-v);
+    char buf[64];
+    auto r = std::to_chars(buf, buf + sizeof buf, v, std::chars_format::scientific);
+    std::string sci(buf, r.ptr);                       /* d[.ddd]e[+-]xx, shortest round-trip */
+    const size_t epos = sci.find('e');
+    std::string digits;
+    for (size_t i = 0; i < epos; i++) if (sci[i] != '.') digits.push_back(sci[i]);
+    while (digits.size() > 1 && digits.back() == '0') digits.pop_back();
+    const int n = atoi(sci.c_str() + epos + 1) + 1;
+    const int k = (int)digits.size();
+    if (k <= n && n <= 21) return digits + std::string(n - k, '0');
+    if (0 < n && n <= 21) return digits.substr(0, n) + "." + digits.substr(n);
+    if (-6 < n && n <= 0) return "0." + std::string(-n, '0') + digits;
+    const int e = n - 1;
+    std::string tail = std::string("e") + (e > 0 ? "+" : "-") + std::to_string(e < 0 ? -e : e);
+    return (k == 1 ? digits : digits.substr(0, 1) + "." + digits.substr(1)) + tail;
+}
+
+/* check_name (lib/glpcpx.js:757-766); adjust_name (:768-780) assigns into an immutable
+   string and therefore changes nothing, so a name with a blank or a dash is simply invalid */
+bool name_ok(const char *s)
+{
+    if (!s || !*s) return false;
+    if (s[0] == '.' || isdigit((unsigned char)s[0])) return false;
+    for (const unsigned char *p = (const unsigned char *)s; *p; p++)
+        if (!(*p < 128 && isalnum(*p)) && !strchr(NAME_EXTRA, *p)) return false;
+    return true;
+}
+
+struct LpText {
+    std::string text, line;
+    int count = 0;
+    void out(const std::string &l) { text += l; text.push_back('\n'); count++; }
+    void begin(const std::string &l) { line = l; }
+    void add(const std::string &term)                   /* lines are broken before column 73 */
+    {
+        if (line.size() + term.size() > 72) { out(line); line.clear(); }
+        line += term;
+    }
+    void end() { out(line); }
+};
+
+std::string signed_term(double v, const std::string &name)
+{
+    if (v == +1.0) return " + " + name;
+    if (v == -1.0) return " - " + name;
+    if (v > 0.0) return " + " + js_number(v) + " " + name;
+    return " - " + js_number(-v) + " " + name;
+}
+
+} // namespace
+
+extern "C" int glpb_write_lp(int m, int n, int dir, double c0, const int *type, const double *lb, const double *ub,
+                             const double *coef, const int *kind, const int *col_len, const int *R_ptr,
+                             const int *R_ind, const double *R_val, const char *prob_name, const char *names,
+                             char **text, long *text_len, int *lines)
+{
+    if (m < 0 || n < 0 || !text || !(dir == 1 || dir == 2)) return GLPB_EINVAL;
+    if (m > 0 && n > 0 && (!type || !lb || !ub || !coef || !col_len || !R_ptr || (R_ptr[m] > 0 && (!R_ind || !R_val))))
+        return GLPB_EINVAL;
+    try {
+        /* names block as glpb_read_lp returns it: objective, m rows, n columns, NUL-terminated; an empty
+           string stands for "no name" */
+        std::vector<const char *> nm(1 + m + n, nullptr);
+        if (names) {
+            const char *p = names;
+            for (int k = 0; k < 1 + m + n; k++) { nm[k] = p; p += strlen(p) + 1; }
+        }
+        auto row_name = [&](int i) -> std::string {     /* i = 0: the objective */
+            if (name_ok(nm[i])) return nm[i];
+            return i == 0 ? std::string("obj") : "r_" + std::to_string(i);
+        };
+        auto col_name = [&](int j) -> std::string {
+            if (name_ok(nm[m + j])) return nm[m + j];
+            return "x_" + std::to_string(j);
+        };
+        LpText T;
+        T.out(std::string("\\* Problem: ") + (prob_name ? prob_name : "Unknown") + " *\\");
+        T.out("");
+        if (!(m > 0 && n > 0)) {
+            T.out("\\* WARNING: PROBLEM HAS NO ROWS/COLUMNS *\\");
+            T.out("");
+        } else {
+            T.out(dir == 1 ? "Minimize" : "Maximize");
+            T.begin(" " + row_name(0) + ":");
+            int terms = 0;
+            for (int j = 1; j <= n; j++) {
+                const double c = coef[j - 1];
+                if (c != 0.0 || col_len[j - 1] == 0) {
+                    terms++;
+                    T.add(c == 0.0 ? " + 0 " + col_name(j) : signed_term(c, col_name(j)));
+                }
+            }
+            if (terms == 0) T.line += " 0 " + col_name(1);
+            T.end();
+            if (c0 != 0.0) T.out("\\* constant term = " + js_number(c0) + " *\\");
+            T.out("");
+            T.out("Subject To");
+            for (int i = 1; i <= m; i++) {
+                const int t = type[i - 1];
+                if (t == 1) continue;                    /* GLP_FR */
+                T.begin(" " + row_name(i) + ":");
+                for (int e = R_ptr[i - 1]; e < R_ptr[i]; e++) {
+                    if (R_ind[e] < 0 || R_ind[e] >= n) return GLPB_EINVAL;
+                    T.add(signed_term(R_val[e], col_name(R_ind[e] + 1)));
+                }
+                if (t == 4) T.add(" - ~r_" + std::to_string(i));
+                else if (R_ptr[i] == R_ptr[i - 1]) T.line += " 0 " + col_name(1);
+                if (t == 2) T.add(" >= " + js_number(lb[i - 1]));
+                else if (t == 3) T.add(" <= " + js_number(ub[i - 1]));
+                else T.add(" = " + js_number(lb[i - 1]));
+                T.end();
+            }
+            T.out("");
+            bool flag = false;
+            for (int i = 1; i <= m; i++) {
+                if (type[i - 1] != 4) continue;
+                if (!flag) { T.out("Bounds"); flag = true; }
+                T.out(" 0 <= ~r_" + std::to_string(i) + " <= " + js_number(ub[i - 1] - lb[i - 1]));
+            }
+            for (int j = 1; j <= n; j++) {
+                const int k = m + j - 1, t = type[k];
+                if (t == 2 && lb[k] == 0.0) continue;
+                if (!flag) { T.out("Bounds"); flag = true; }
+                const std::string name = col_name(j);
+                if (t == 1) T.out(" " + name + " free");
+                else if (t == 2) T.out(" " + name + " >= " + js_number(lb[k]));
+                else if (t == 3) T.out(" -Inf <= " + name + " <= " + js_number(ub[k]));
+                else if (t == 4) T.out(" " + js_number(lb[k]) + " <= " + name + " <= " + js_number(ub[k]));
+                else T.out(" " + name + " = " + js_number(lb[k]));
+            }
+            if (flag) { T.text.push_back('\n'); }
+            T.count++;                                   /* the reference counts this line even when it does not write it (:973) */
+            flag = false;
+            for (int j = 1; j <= n; j++) {
+                if (!kind || kind[j - 1] == 1) continue; /* GLP_CV */
+                if (!flag) { T.out("Generals"); flag = true; }
+                T.out(" " + col_name(j));
+            }
+            if (flag) T.out("");
+        }
+        T.out("End");
+        char *p = (char *)malloc(T.text.size() + 1);
+        if (!p) return GLPB_ENOMEM;
+        memcpy(p, T.text.data(), T.text.size());
+        p[T.text.size()] = '\0';
+        *text = p;
+        if (text_len) *text_len = (long)T.text.size();
+        if (lines) *lines = T.count;
+        return 0;
+    } catch (const std::bad_alloc &) {
+        return GLPB_ENOMEM;
+    }
+}

@@ -1198,7 +1198,26 @@ def _read_lp(P, text):
 
 # ---- marshalling to the device handle ----
 def glp_write_lp(P, parm, callback):
-    """lib/glpcpx.js:755-998: CPLEX LP text, one ``callback(line)`` per line.
+    """lib/glpcpx.js:755-998: CPLEX LP text, one ``callback(line)`` per line.  The text is produced by the
+    native writer (``glpb_write_lp``, csrc/lpformat.cpp); ``_write_lp_py`` below is the Python restatement
+    kept as its cross-check (tests/test_writer_golden.py: both equal the reference's own writer)."""
+    _check(P, "glp_write_lp")
+    xprintf("Writing problem data")
+    if not (P.m > 0 and P.n > 0):
+        xprintf("Warning: problem has no rows/columns")
+    d, _, _ = _arrays(P)
+    rptr, rind, rval = _csr(P)
+    col_len = [len(P.col[j].elems) for j in range(1, P.n + 1)]
+    names = (P.obj, [P.row[i].name for i in range(1, P.m + 1)], [P.col[j].name for j in range(1, P.n + 1)])
+    lines, count = native.write_lp(d, col_len, rptr, rind, rval, P.name, names)
+    for line in lines:
+        callback(line)
+    xprintf("%d lines were written" % count)
+    return 0
+
+
+def _write_lp_py(P, parm, callback):
+    """lib/glpcpx.js:755-998 restated in Python (cross-check of the native writer).
     (The reference's adjust_name assigns into an immutable string and so changes
     nothing: a name with a blank or a dash is replaced by r_i / x_j.)"""
     _check(P, "glp_write_lp")

@@ -74,7 +74,7 @@ SYMBOLS = [
     "glpb_btran", "glpb_k_chuzc_primal", "glpb_k_chuzr_dual", "glpb_k_ratio_primal",
     "glpb_k_ratio_dual", "glpb_k_trow", "glpb_k_sort_list", "glpb_bench_kernel", "glpb_gen_packing",
     "glpb_gen_covering", "glpb_gen_mkp", "glpb_free_problem", "glpb_rng_fill",
-    "glpb_scale_prob", "glpb_adv_basis", "glpb_read_lp", "glpb_free_names",
+    "glpb_scale_prob", "glpb_adv_basis", "glpb_read_lp", "glpb_free_names", "glpb_write_lp",
     "glpb_set_pivot_log", "glpb_get_pivot_log", "glpb_debug_get", "glpb_bnb_begin", "glpb_bnb_round", "glpb_bnb_open_count", "glpb_bnb_get_incumbent", "glpb_bnb_set_cutoff", "glpb_bnb_clear",
     "glpb_bnb_record_bytes", "glpb_bnb_export_nodes", "glpb_bnb_import_nodes", "glpb_bnb_stats", "glpb_bnb_end",
     "glpb_npp_create", "glpb_npp_destroy", "glpb_npp_load_prob", "glpb_npp_simplex", "glpb_npp_integer",
@@ -152,6 +152,7 @@ def load():
     L.glpb_adv_basis.argtypes = [ci, ci] + [vp] * 9
     L.glpb_read_lp.argtypes = [C.c_char_p, C.c_long, vp, vp, vp]
     L.glpb_free_names.argtypes = [vp]
+    L.glpb_write_lp.argtypes = [ci, ci, ci, cd] + [vp] * 9 + [C.c_char_p, C.c_char_p, vp, vp, vp]
     L.glpb_set_pivot_log.argtypes = [vp, ci]
     L.glpb_get_pivot_log.argtypes = [vp, vp, ci, vp]
     L.glpb_debug_get.argtypes = [vp, C.c_char_p, vp, ci]
@@ -257,6 +258,28 @@ def read_lp(text):
     L.glpb_free_problem(C.byref(pd))
     parts = blob.split("\0")[:-1]
     return d, dict(obj=parts[0], rows=parts[1:1 + d["m"]], cols=parts[1 + d["m"]:1 + d["m"] + d["n"]])
+
+
+def write_lp(d, col_len, R_ptr, R_ind, R_val, prob_name=None, names=None):
+    """glpb_write_lp: (lines, count) of the CPLEX LP text of problem `d` (layout of Problem, unscaled); rows
+    in list order; names = (obj, [rows], [cols]) with None for a missing name.  Host only."""
+    L = load()
+    m, n = int(d["m"]), int(d["n"])
+    keep = [_i32(d["type"]), _f64(d["lb"]), _f64(d["ub"]), _f64(d["coef"]), _i32(d.get("kind")), _i32(col_len),
+            _i32(R_ptr), _i32(R_ind), _f64(R_val)]
+    blob = None
+    if names is not None:
+        obj, rows, cols = names
+        blob = b"".join((x or "").encode() + b"\0" for x in [obj] + list(rows) + list(cols))
+    text, tlen, count = C.c_void_p(), C.c_long(), C.c_int()
+    rc = L.glpb_write_lp(m, n, int(d["dir"]), float(d["c0"]), *[_p(a) for a in keep],
+                         None if prob_name is None else prob_name.encode(), blob,
+                         C.byref(text), C.byref(tlen), C.byref(count))
+    if rc != 0:
+        raise ValueError("glpb_write_lp: invalid arguments (rc=%d)" % rc)
+    raw = C.string_at(text, tlen.value).decode()
+    L.glpb_free_names(text)
+    return raw.split("\n")[:-1], count.value
 
 
 def scale_prob(m, n, A_ptr, A_ind, A_val, flags):

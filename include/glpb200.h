@@ -295,6 +295,25 @@ int glpb_adv_basis(int m, int n, const int *A_ptr, const int *A_ind, const int *
 int glpb_read_lp(const char *text, long len, glpb_problem_data *out, char **names, long *names_len);
 void glpb_free_names(char *names);
 
+/* glpb_write_lp replaces glp_write_lp (lib/glpcpx.js:755-999): the problem as CPLEX
+ * LP text, identical line for line to what the reference hands to its callback
+ * (numbers as JavaScript's string concatenation shows them, lines broken before
+ * column 73, r_<i> / x_<j> / obj for missing or invalid names -- the reference's
+ * adjust_name assigns into an immutable string and changes nothing).  type/lb/ub
+ * [m+n], coef/kind [n] as for glpb_create (unscaled); col_len[n] = number of
+ * elements per column (an empty column is written into the objective with a zero
+ * coefficient); rows R_ptr/R_ind/R_val (0-based column indices) in the reference's
+ * LIST order, which is the order of the terms of every constraint.  prob_name and
+ * names are optional; names = one block of 1+m+n NUL-terminated strings
+ * (objective, rows, columns -- the layout glpb_read_lp returns), "" = no name.
+ * *text receives a malloc'ed NUL-terminated buffer, lines separated by '\n'
+ * (release it with glpb_free_names); *lines = the count the reference reports in
+ * "<count> lines were written".  Returns 0, GLPB_EINVAL or GLPB_ENOMEM. */
+int glpb_write_lp(int m, int n, int dir, double c0, const int *type, const double *lb,
+                  const double *ub, const double *coef, const int *kind, const int *col_len,
+                  const int *R_ptr, const int *R_ind, const double *R_val, const char *prob_name,
+                  const char *names, char **text, long *text_len, int *lines);
+
 /* ---- LP / MIP presolver (csrc/presolve.cpp) --------------
  * Host only, no device involved.  One workspace per `presolve: GLP_ON` solve,
  * used in the order of lib/glpapi06.js:41-146 (LP) / lib/glpapi09.js:116-256

@@ -262,7 +262,7 @@ def test_napi_shim_is_well_formed_c_and_create_validates_the_column_pointer():
                          capture_output=True, text=True)
     assert out.returncode == 0, out.stderr
     src = open(os.path.join(root, "bindings", "glpb200_napi.c")).read()
-    for entry in ("Create", "SetBasis", "SetBounds", "Simplex", "Intopt", "GetSolution", "GetMip", "ScaleProb", "AdvBasis", "ReadLp",
+    for entry in ("Create", "SetBasis", "SetBounds", "Simplex", "Intopt", "GetSolution", "GetMip", "ScaleProb", "AdvBasis", "ReadLp", "WriteLp",
                   "NppCreate", "NppLoadProb", "NppSimplex", "NppInteger", "NppBuildProb", "NppPostprocess"):
         assert ("static napi_value %s(" % entry) in src
     assert src.count("typed_n(") >= 3 and "typed(env" not in src          # every array goes through the checked accessor

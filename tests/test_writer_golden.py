@@ -24,12 +24,20 @@ def test_writer_matches_reference(name):
         assert F.glp_read_lp_from_string(P, None, case["text"]) == 0
     else:
         P = T.facade_problem(case["problem"])
-    lines, msgs = [], []
-    F.glp_set_print_func(msgs.append)
-    try:
-        ret = F.glp_write_lp(P, None, lines.append)
-    finally:
-        F.glp_set_print_func(None)
-    assert ret == case["ret"]
-    assert lines == case["lines"]
-    assert msgs == case["messages"]
+    if "names" in case:
+        nm = case["names"]
+        P.name, P.obj = nm["prob"], nm["obj"]
+        for i, x in enumerate(nm["rows"], 1):
+            P.row[i].name = x
+        for j, x in enumerate(nm["cols"], 1):
+            P.col[j].name = x
+    for writer in (F.glp_write_lp, F._write_lp_py):      # the native writer and its Python cross-check
+        lines, msgs = [], []
+        F.glp_set_print_func(msgs.append)
+        try:
+            ret = writer(P, None, lines.append)
+        finally:
+            F.glp_set_print_func(None)
+        assert ret == case["ret"]
+        assert lines == case["lines"]
+        assert msgs == case["messages"]
