@@ -240,6 +240,11 @@ def run_case(ref, src, sol, binarize=0):
         # the flow of preprocess_and_solve_lp / _mip on the reduced problem
         fn("glp_scale_prob", lp, 0x80 if sol == GLP_SOL else (0x01 | 0x10 | 0x20 | 0x40))
         fn("glp_adv_basis", lp, 0)
+        # the inputs of the hot path proper: scale factors and the crash basis of the reduced problem
+        out["prep"] = dict(rii=[float(lp["row"][i]["rii"]) for i in range(1, m + 1)],
+                           sjj=[float(lp["col"][j]["sjj"]) for j in range(1, n + 1)],
+                           row_stat=[int(lp["row"][i]["stat"]) for i in range(1, m + 1)],
+                           col_stat=[int(lp["col"][j]["stat"]) for j in range(1, n + 1)])
         r1 = int(ref.call("glp_simplex", lp, ref.smcp()))
         out["reduced_lp_ret"] = r1
         out["reduced_lp"] = ref.lp_result(lp)

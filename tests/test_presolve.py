@@ -211,7 +211,7 @@ class _DeviceReached(Exception):
     pass
 
 
-NEEDS_DEVICE = sorted(k for k, c in CASES.items() if "terminal_off" in c)
+NEEDS_DEVICE = sorted(k for k, c in CASES.items() if "prep" in c)       # generated problems and the fixtures
 
 
 @pytest.mark.parametrize("name", NEEDS_DEVICE)
@@ -223,7 +223,10 @@ def test_messages_up_to_the_device_solve(name, monkeypatch):
     reduced problem, the native scaling and the native crash basis in one."""
     case = CASES[name]
 
-    def stop(*a, **k):
+    handed = []
+
+    def stop(lp, *a, **k):
+        handed.append(lp)
         raise _DeviceReached()
     monkeypatch.setattr(F, "_solve_lp", stop)
     P = facade_problem(case["problem"])
@@ -241,4 +244,11 @@ def test_messages_up_to_the_device_solve(name, monkeypatch):
                 F.glp_intopt(P, parm)
     finally:
         F.glp_set_print_func(None)
-    assert lines == case["terminal_off"]["lines"]
+    if "terminal_off" in case:
+        assert lines == case["terminal_off"]["lines"]
+    # ... and the problem handed over carries the reference's scale factors and crash basis, bit for bit
+    lp, prep = handed[0], case["prep"]
+    assert [lp.row[i].rii for i in range(1, lp.m + 1)] == prep["rii"]
+    assert [lp.col[j].sjj for j in range(1, lp.n + 1)] == prep["sjj"]
+    assert [lp.row[i].stat for i in range(1, lp.m + 1)] == prep["row_stat"]
+    assert [lp.col[j].stat for j in range(1, lp.n + 1)] == prep["col_stat"]
