@@ -17,6 +17,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <new>
 #include <vector>
 
 namespace {
@@ -271,7 +272,7 @@ extern "C" {
 /* replaces glp_scale_prob (lib/glpscl.js:216-225) */
 int glpb_scale_prob(int m, int n, const int *A_ptr, const int *A_ind, const double *A_val,
                     int flags, double *rii, double *sjj, double *report)
-{
+try {
     if (m < 0 || n < 0 || !rii || !sjj || (n > 0 && !A_ptr)) return GLPB_EINVAL;
     if (flags & ~(GLPB_SF_GM | GLPB_SF_EQ | GLPB_SF_2N | GLPB_SF_SKIP | GLPB_SF_AUTO)) return GLPB_EINVAL;
     static const int zero_ptr[1] = {0};
@@ -322,13 +323,15 @@ int glpb_scale_prob(int m, int n, const int *A_ptr, const int *A_ind, const doub
         note(3);
     }
     return done();
+} catch (const std::bad_alloc &) {
+    return GLPB_ENOMEM;   /* nothing crosses the C ABI as an exception */
 }
 
 /* replaces glp_adv_basis(lp, 0) (lib/glpini01.js:281-363) */
 int glpb_adv_basis(int m, int n, const int *A_ptr, const int *A_ind, const int *R_ptr,
                    const int *R_ind, const int *type, const double *lb, const double *ub,
                    int *stat, int *tri_size)
-{
+try {
     if (m <= 0 || n <= 0 || !A_ptr || !R_ptr || !type || !lb || !ub || !stat) return GLPB_EINVAL;
     if (A_ptr[n] != R_ptr[m]) return GLPB_EINVAL;
     for (int e = 0; e < A_ptr[n]; e++)
@@ -358,6 +361,8 @@ int glpb_adv_basis(int m, int n, const int *A_ptr, const int *A_ind, const int *
         }
     }
     return 0;
+} catch (const std::bad_alloc &) {
+    return GLPB_ENOMEM;   /* nothing crosses the C ABI as an exception */
 }
 
 } // extern "C"

@@ -31,6 +31,7 @@
 #include <cstring>
 #include <string>
 #include <unordered_map>
+#include <new>
 #include <vector>
 
 void glpb_set_error(const char *fmt, ...);
@@ -336,7 +337,7 @@ extern "C" {
 
 /* replaces glp_read_lp (lib/glpcpx.js:10-753) */
 int glpb_read_lp(const char *text, long len, glpb_problem_data *out, char **names, long *names_len)
-{
+try {
     if (!text || len < 0 || !out) return GLPB_EINVAL;
     memset(out, 0, sizeof *out);
     if (names) *names = nullptr;
@@ -404,6 +405,8 @@ int glpb_read_lp(const char *text, long len, glpb_problem_data *out, char **name
         if (names_len) *names_len = (long)blob.size();
     }
     return 0;
+} catch (const std::bad_alloc &) {
+    return GLPB_ENOMEM;   /* nothing crosses the C ABI as an exception */
 }
 
 void glpb_free_names(char *names) { free(names); }
