@@ -5,6 +5,7 @@ plain-Python restatement of lib/glpscl.js and lib/glpini01.js in
 oracle/hostprep.py -- bit-exact scale factors, identical statuses -- plus the
 properties the algorithms guarantee.  No device is needed."""
 import importlib.util
+import json
 import math
 import os
 import random
@@ -978,3 +979,32 @@ def test_native_reader_equals_the_references_reader(name):
     P = glpk.glp_create_prob()
     assert glpk.glp_read_lp_from_string(P, None, rec["text"]) == 0
     assert [P.row[i].name for i in range(1, P.m + 1)] == names["rows"]
+
+
+# ---- glp_scale_prob / glp_adv_basis against THE REFERENCE'S OWN runs (tests/golden/ref_hostprep_cases.json:
+# lib/glpscl.js and lib/glpini01.js executed by minijs, oracle/jsref/fuzz_hostprep.py --golden): matrices with up
+# to twelve decades of dynamic range, every combination of scaling flags
+with open(os.path.join(H.GOLDEN, "ref_hostprep_cases.json")) as _f:
+    REF_PREP = {k: v for k, v in json.load(_f).items() if not k.startswith("_")}
+
+
+@pytest.mark.parametrize("name", sorted(REF_PREP))
+def test_scaling_and_crash_basis_match_the_reference_bit_for_bit(name):
+    import test_presolve as T
+    case = REF_PREP[name]
+    Q = T.facade_problem(case["problem"])
+    for j in range(1, Q.n + 1):             # statuses of a freshly built problem (rows basic, columns by type)
+        c = Q.col[j]
+        glpk._set_bnds(c, "", j, c.type, c.lb, c.ub)
+    lines = []
+    glpk.glp_set_print_func(lines.append)
+    try:
+        glpk.glp_scale_prob(Q, case["flags"])
+        glpk.glp_adv_basis(Q, 0)
+    finally:
+        glpk.glp_set_print_func(None)
+    assert [Q.row[i].rii for i in range(1, Q.m + 1)] == case["rii"]
+    assert [Q.col[j].sjj for j in range(1, Q.n + 1)] == case["sjj"]
+    assert [Q.row[i].stat for i in range(1, Q.m + 1)] == case["row_stat"]
+    assert [Q.col[j].stat for j in range(1, Q.n + 1)] == case["col_stat"]
+    assert lines == case["lines"]
