@@ -32,7 +32,7 @@ def main():
                 if tag == "lp":
                     case = G.run_case(ref, G.npp_lp(seed, m=6 + seed % 23, n=8 + seed % 31, wild=seed % 3 == 0), G.GLP_SOL)
                 else:
-                    case = G.run_case(ref, G.npp_mip(seed, m=6 + seed % 9, n=9 + seed % 8), G.GLP_MIP, binarize=seed % 2)
+                    case = G.run_case(ref, G.npp_mip(seed, m=6 + seed % 9, n=9 + seed % 8, wide=seed % 5 == 0), G.GLP_MIP, binarize=seed % 2)
             except Exception as e:      # the reference itself threw (e.g. xassert): not a case
                 print("seed", seed, tag, "reference raised", type(e).__name__, str(e)[:80], flush=True)
                 continue

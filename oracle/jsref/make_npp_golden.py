@@ -121,7 +121,7 @@ def npp_lp(seed, m=10, n=14, wild=False):
                 coef * (1 if seed % 2 == 0 else -1), np.ones(n, int))
 
 
-def npp_mip(seed, m=9, n=12):
+def npp_mip(seed, m=9, n=12, wide=False):
     """binaries in knapsack-like rows, bounded general integers (binarization), a few continuous columns"""
     rs = np.random.RandomState(1000 + seed)
     kind = np.array([2] * (n - 3) + [1] * 3)
@@ -129,6 +129,8 @@ def npp_mip(seed, m=9, n=12):
     for j in range(n - 3):
         if rs.rand() < 0.3:
             c_lb[j] = float(rs.choice([0, 0, 1, -2])); c_ub[j] = c_lb[j] + float(rs.choice([2, 3, 5, 7, 9]))
+            if wide and rs.rand() < 0.5:    # ranges the binarization refuses (> 4095) or bounds beyond 1e6
+                c_ub[j] = c_lb[j] + float(rs.choice([4095, 4096, 5000, 2000000]))
     for j in range(n - 3, n):
         c_lb[j] = 0.0; c_ub[j] = float(rs.choice([4, 10, 25]))
     A = np.zeros((m, n))
@@ -350,20 +352,24 @@ def main():
         cases["npp_mip_%d" % seed] = c
         print("npp_mip", seed, c["ret"], c["n_tse"], c.get("reduced", {}).get("m"), c.get("reduced", {}).get("n"),
               c.get("unloaded", {}).get("mip_obj"), round(time.time() - t0, 1), flush=True)
+    for seed in (285, 405, 655, 1085):   # integer ranges the binarization refuses or turns into 12 binaries: presolve only
+        c = run_case_presolve_only(ref, npp_mip(seed, m=6 + seed % 9, n=9 + seed % 8, wide=True), GLP_MIP, binarize=1)
+        cases["npp_wide_%d" % seed] = c
+        print("npp_wide", seed, c["ret"], c["n_tse"], c.get("reduced", {}).get("m"), c.get("reduced", {}).get("n"), flush=True)
     with open(os.path.join(GOLD, "ref_npp.json"), "w") as f:
         json.dump(cases, f)
     print("wrote ref_npp.json (%d bytes, %d cases)" % (os.path.getsize(os.path.join(GOLD, "ref_npp.json")),
                                                       len(cases) - 1))
 
 
-def run_case_presolve_only(ref, src, sol):
+def run_case_presolve_only(ref, src, sol, binarize=0):
     g = ref.g
     fn = lambda name, *a: g[name].call(g, list(a))
     P = ref.make(src)
-    out = {"problem": problem_arrays(ref, P), "sol": sol, "binarize": 0}
+    out = {"problem": problem_arrays(ref, P), "sol": sol, "binarize": binarize}
     npp = fn("npp_create_wksp")
     fn("npp_load_prob", npp, P, 0, sol, 0)
-    out["ret"] = int(fn("npp_integer", npp, ref.iocp()))
+    out["ret"] = int(fn("npp_integer", npp, ref.iocp(binarize=binarize)))
     n_tse, t = 0, npp["top"]
     while not null(t):
         n_tse += 1

@@ -1,7 +1,7 @@
 """LP / MIP presolver (glpb_npp_*, csrc/presolve.cpp) against the REFERENCE'S OWN presolver.
 
 tests/golden/ref_npp.json was produced by oracle/jsref/make_npp_golden.py: the unmodified
-lib/glpnpp01-05.js run on the reference's fixtures and on 86 generated problems.  Everything here is
+lib/glpnpp01-05.js run on the reference's fixtures and on 90 generated problems.  Everything here is
 host code (no device): bit-exact comparison of
   * the return code (0 / GLP_ENOPFS / GLP_ENODFS) and the depth of the recovery stack,
   * the reduced problem npp_build_prob leaves -- row order, column order, bounds, costs, the constant
@@ -128,7 +128,7 @@ def test_golden_covers_the_transformations():
         for k, v in npp.counts().items():
             total[k] = total.get(k, 0) + v
         npp.close()
-    for kind in native.Presolver.KINDS + ("packing", "covering", "reduced", "bin_vars", "bin_rows"):
+    for kind in native.Presolver.KINDS + ("packing", "covering", "reduced", "bin_vars", "bin_rows", "bin_fails"):
         assert total[kind] > 0, kind    # every transformation on the path is reached by some case
 
 
