@@ -357,27 +357,36 @@ def glp_set_mat_col(P, j, length, ind, val):
 
 
 def glp_load_matrix(P, ne, ia, ja, ar):
-    """lib/glpapi01.js:464-560: replace the whole matrix by ne triplets (1-based)."""
+    """lib/glpapi01.js:464-560: replace the whole matrix by ne triplets (1-based).  List order as the
+    reference leaves it: every ROW list holds its elements in reverse input order (prepended as they
+    come); the COLUMN lists are built afterwards by walking rows 1..m and prepending, so every column
+    list runs over DESCENDING row indices; zero elements are removed last."""
     for r in P.row[1:]:
         r.elems = []
     for c in P.col[1:]:
         c.elems = []
     P.nnz = 0
-    seen = set()
+    if ne < 0:
+        xerror("glp_load_matrix: ne = %d; invalid number of constraint coefficients" % ne)
     for k in range(1, ne + 1):
         i, j = ia[k], ja[k]
         if not (1 <= i <= P.m):
             xerror("glp_load_matrix: ia[%d] = %d; row index out of range" % (k, i))
         if not (1 <= j <= P.n):
             xerror("glp_load_matrix: ja[%d] = %d; column index out of range" % (k, j))
-        if (i, j) in seen:
-            xerror("glp_load_matrix: ia[%d] = %d; ja[%d] = %d; duplicate indices not allowed" % (k, i, k, j))
-        seen.add((i, j))
-        if ar[k] == 0.0:
-            continue
         P.row[i].elems.insert(0, (j, float(ar[k])))
-        P.col[j].elems.insert(0, (i, float(ar[k])))
-        P.nnz += 1
+    for i in range(1, P.m + 1):
+        for (j, v) in P.row[i].elems:
+            col = P.col[j]
+            if col.elems and col.elems[0][0] == i:
+                k = next(k for k in range(1, ne + 1) if ia[k] == i and ja[k] == j)
+                xerror("glp_load_mat: ia[%d] = %d; ja[%d] = %d; duplicate indices not allowed" % (k, i, k, j))
+            col.elems.insert(0, (i, v))
+    for r in P.row[1:]:
+        r.elems = [e for e in r.elems if e[1] != 0.0]
+    for c in P.col[1:]:
+        c.elems = [e for e in c.elems if e[1] != 0.0]
+    P.nnz = sum(len(c.elems) for c in P.col[1:])
     P.valid = 0
     P._dirty = True
 
