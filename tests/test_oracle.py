@@ -275,3 +275,20 @@ def test_napi_shim_is_well_formed_c_and_create_validates_the_column_pointer():
         h = L.glpb_create(1, 2, 2, 1, 0.0, t.ctypes.data, z.ctypes.data, z.ctypes.data, z[:2].ctypes.data, None, None, None,
                           ptr.ctypes.data, np.zeros(2, np.int32).ctypes.data, np.ones(2).ctypes.data, 0)
         assert not h and "A_ptr" in nat.last_error()
+
+
+def test_oracle_own_c3_run_agrees_with_the_highs_pin_once_complete():
+    """tests/golden/c3_oracle_run.json is written by the oracle's own uninterrupted solve of the headline LP
+    (tests/golden/make_c3_pins.py oracle-c3; > 10 h on one core).  While it is a progress log there is nothing
+    to check beyond its shape; once complete, the oracle's optimum must be the HiGHS pin's."""
+    import json
+    with open(os.path.join(H.GOLDEN, "c3_oracle_run.json")) as f:
+        run = json.load(f)
+    with open(os.path.join(H.GOLDEN, "lp_pins.json")) as f:
+        pin = json.load(f)["c3"]["highs"]["obj"]
+    its = [e["it"] for e in run["log"]]
+    assert its == sorted(its) and all(e["k"] <= e["n"] for e in run["log"])
+    if not run.get("partial", True):
+        assert run["rc"] == 0 and run["status"] == O.GLP_OPT
+        assert abs(run["obj"] - pin) <= 1e-9 * abs(pin)
+        assert run["it_cnt"] >= its[-1]
